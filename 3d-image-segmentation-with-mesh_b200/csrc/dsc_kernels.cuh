@@ -1,0 +1,795 @@
+// dsc_kernels.cuh -- sm_100a kernels of the DSC image-energy path.
+//
+// HBM layout (all arrays SoA, see DESIGN.md "Data layout"):
+//   volume     VoxT[X*Y*Z]            x fastest (DEMO/image3d.h:66-68); u8/u16/f32/f64
+//   sum_table  double[X*Y*Z]          z prefix sums (DEMO/image3d.cpp:166-176)
+//   pos4       double4[n_nodes]       xyz + pad: one 32 B sector per node gather
+//   tet_nodes  uint4[n_tets]          get_nodes(t) order, one 16 B load per tet
+//   tet_label  int[n_tets]
+//   face_nodes uint[3*n_faces], face_tets uint[2*n_faces], face_is_boundary u8[n_faces]
+//   node CSR   node_off uint[n_nodes+1], node_inc uint[3*n_faces] = (face<<2)|corner, faces ascending
+//   tet_bary   double[4*2025]         barycentric sample table (generated dsc_tables.h)
+// None of this is GEMM-shaped; tensor cores are not used.  The kernels are gather/scan work
+// bounded by HBM/L2 bandwidth and, for the tet pass, the FP64 pipe (21 non-fused DMUL/DADD per
+// sample position, which must not be contracted -- see dsc_device.cuh).
+#pragma once
+#include "dsc_device.cuh"
+
+namespace dsc {
+
+constexpr int kMaxPhase = 8;
+constexpr int kMaxRayHits = 96;
+constexpr unsigned kNoTet = 0xFFFFFFFFu;
+
+__constant__ double c_gauss[4 * 42];
+__constant__ int c_gauss_off[8];
+
+struct VolumeView {
+    const void *data;
+    const double *sum_table;
+    int X, Y, Z;
+};
+
+struct MeshView {
+    const double4 *pos4;
+    const uint4 *tet_nodes;
+    const int *tet_label;
+    const unsigned *face_nodes;
+    const unsigned *face_tets;
+    const unsigned char *face_is_boundary;
+    const unsigned *node_off;
+    const unsigned *node_inc;
+    unsigned n_nodes, n_tets, n_faces;
+};
+
+template <typename T> struct VoxTraits;
+template <> struct VoxTraits<unsigned char> { static constexpr bool integral = true; DSC_D static double denom() { return 255.0; } };
+template <> struct VoxTraits<unsigned short> { static constexpr bool integral = true; DSC_D static double denom() { return 65535.0; } };
+template <> struct VoxTraits<float> { static constexpr bool integral = false; DSC_D static double denom() { return 1.0; } };
+template <> struct VoxTraits<double> { static constexpr bool integral = false; DSC_D static double denom() { return 1.0; } };
+
+// exact voxel decode: byte/255.0 as DEMO/image3d.cpp:127 (IEEE division), u16/65535.0, float widened
+template <typename T> DSC_D double decode(T v)
+{
+    if (VoxTraits<T>::integral) return (double)v / VoxTraits<T>::denom();
+    return (double)v;
+}
+
+// image3d::get_value (DEMO/image3d.cpp:480-491): 0 outside the volume, never clamped
+template <typename T> DSC_D double fetch(const T *__restrict__ vol, int X, int Y, int Z, int x, int y, int z)
+{
+    if ((unsigned)x < (unsigned)X && (unsigned)y < (unsigned)Y && (unsigned)z < (unsigned)Z)
+        return decode<T>(__ldg(vol + ((size_t)z * Y + y) * X + x));
+    return 0.0;
+}
+
+// image3d::get_value_f (DEMO/image3d.cpp:226-251): floor, 8 fetches, lerp along x, then y, then z
+template <typename T> DSC_D double fetch_trilinear(const T *__restrict__ vol, int X, int Y, int Z, V3 pt)
+{
+    double fx = floor(pt.x), fy = floor(pt.y), fz = floor(pt.z);
+    int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    double rx = pt.x - (double)ix, ry = pt.y - (double)iy, rz = pt.z - (double)iz;
+    double v000 = fetch(vol, X, Y, Z, ix, iy, iz), v100 = fetch(vol, X, Y, Z, ix + 1, iy, iz);
+    double v001 = fetch(vol, X, Y, Z, ix, iy, iz + 1), v101 = fetch(vol, X, Y, Z, ix + 1, iy, iz + 1);
+    double v010 = fetch(vol, X, Y, Z, ix, iy + 1, iz), v110 = fetch(vol, X, Y, Z, ix + 1, iy + 1, iz);
+    double v011 = fetch(vol, X, Y, Z, ix, iy + 1, iz + 1), v111 = fetch(vol, X, Y, Z, ix + 1, iy + 1, iz + 1);
+    double c00 = v000 * (1 - rx) + v100 * rx;
+    double c01 = v001 * (1 - rx) + v101 * rx;
+    double c10 = v010 * (1 - rx) + v110 * rx;
+    double c11 = v011 * (1 - rx) + v111 * rx;
+    double c0 = c00 * (1 - ry) + c10 * ry;
+    double c1 = c01 * (1 - ry) + c11 * ry;
+    return c0 * (1 - rz) + c1 * rz;
+}
+
+DSC_D V3 load_pos(const double4 *__restrict__ pos4, unsigned n)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(pos4 + n);
+    double2 a = __ldg(p), b = __ldg(p + 1);
+    return {a.x, a.y, b.x};
+}
+
+DSC_D double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// =================================================================================================
+// Per-tet integration: image3d::get_tetra_intensity / get_energy / get_variation
+// (DEMO/image3d.cpp:351-426) over all tets, fused with the per-label reduction.
+//
+// G lanes cooperate on one tet (G = 8 or 32): all of them read the tet's 4 node ids and 4 positions
+// (broadcast loads), compute volume -> level n -> n^3 sample points; lane j takes samples j, j+G,...
+// from the flat barycentric table (coalesced 32 B rows), computes the position with the reference's
+// operation order, truncates to the voxel index and gathers the voxel.  A G-wide xor-shuffle tree
+// reduces the lane sums.  The per-label sums live in registers of lane (label-1) of each group, are
+// reduced per CTA and written as one partial row per CTA; tet_finalize_kernel adds the rows in CTA
+// order, so the result is bit-reproducible run to run (no atomics on doubles anywhere).
+// =================================================================================================
+struct TetArgs {
+    VolumeView vol;
+    MeshView mesh;
+    const double *tet_bary;
+    unsigned tet_begin, tet_end;
+    int include_bound;
+    int nb_phase;
+    int nc;
+    double c[kMaxPhase];
+    double *tet_total, *tet_vol, *tet_mean, *tet_energy, *tet_variation;
+    double *partials;                // [gridDim.x][3*kMaxPhase]: total, sumsq, volume
+    unsigned long long *sample_count; // algorithmic samples processed (for the roofline figure)
+};
+
+template <typename VoxT, int G, bool WITH_C>
+__global__ void __launch_bounds__(256) tet_integrate_kernel(const TetArgs a)
+{
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const int lane_g = threadIdx.x & (G - 1);
+    const unsigned groups_per_block = blockDim.x / G;
+    const unsigned total_groups = gridDim.x * groups_per_block;
+    const unsigned gid = blockIdx.x * groups_per_block + threadIdx.x / G;
+    const unsigned n_work = a.tet_end - a.tet_begin;
+    const unsigned iters = (n_work + total_groups - 1) / total_groups;
+
+    double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane_g + 1
+    unsigned long long nsamp = 0;
+
+    for (unsigned it = 0; it < iters; it++) {
+        const unsigned w = it * total_groups + gid;
+        const bool valid = w < n_work;
+        const unsigned t = a.tet_begin + (valid ? w : 0);
+        int label = 0;
+        bool active = false;
+        double s = 0, sq = 0, v = 0;
+        double sqc[kMaxPhase], adc[kMaxPhase];
+        if (WITH_C) {
+#pragma unroll
+            for (int k = 0; k < kMaxPhase; k++) sqc[k] = adc[k] = 0;
+        }
+        int n3 = 0;
+        if (valid) {
+            label = __ldg(a.mesh.tet_label + t);
+            active = a.include_bound || label != 0;
+        }
+        if (active) {
+            const uint4 nd = __ldg(a.mesh.tet_nodes + t);
+            const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+            const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+            v = tet_volume(p0, p1, p2, p3);
+            const int L = tet_level(v);
+            n3 = (L + 1) * (L + 1) * (L + 1);
+            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2); // sum of k^3, k <= L
+            const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+            unsigned long long isum = 0, isq = 0;
+            for (int i = lane_g; i < n3; i += G) {
+                const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
+                // get_coord: ((p0*b0 + p1*b1) + p2*b2) + p3*b3 per component (DEMO/tet_dis_coord.hpp:27)
+                const double px = ((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y;
+                const double py = ((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y;
+                const double pz = ((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y;
+                const int ix = (int)px, iy = (int)py, iz = (int)pz; // truncation toward 0, image3d.cpp:366
+                if (VoxTraits<VoxT>::integral && !WITH_C) {
+                    // integer voxels: exact integer sums, one division per tet instead of one per sample
+                    if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) {
+                        const unsigned long long q = (unsigned long long)__ldg(vol + ((size_t)iz * Y + iy) * X + ix);
+                        isum += q;
+                        isq += q * q;
+                    }
+                } else {
+                    const double I = fetch(vol, X, Y, Z, ix, iy, iz);
+                    s += I;
+                    sq += I * I;
+                    if (WITH_C) {
+#pragma unroll
+                        for (int k = 0; k < kMaxPhase; k++)
+                            if (k < a.nc) {
+                                const double d = I - a.c[k];
+                                sqc[k] += d * d;
+                                adc[k] += fabs(d);
+                            }
+                    }
+                }
+            }
+            if (VoxTraits<VoxT>::integral && !WITH_C) {
+                const double dn = VoxTraits<VoxT>::denom();
+                s = (double)isum / dn;
+                sq = (double)isq / (dn * dn);
+            }
+        }
+        // group reduction (all 32 lanes take part; idle groups carry zeros)
+#pragma unroll
+        for (int m = G / 2; m >= 1; m >>= 1) {
+            s += shfl_xor_d(s, m);
+            sq += shfl_xor_d(sq, m);
+            if (WITH_C) {
+#pragma unroll
+                for (int k = 0; k < kMaxPhase; k++) {
+                    sqc[k] += shfl_xor_d(sqc[k], m);
+                    adc[k] += shfl_xor_d(adc[k], m);
+                }
+            }
+        }
+        if (active) {
+            // total = total * v / a.size()  (image3d.cpp:371)
+            const double tot = s * v / (double)n3;
+            const double tsq = sq * v / (double)n3;
+            if (lane_g == 0) {
+                nsamp += (unsigned long long)n3;
+                if (a.tet_total) a.tet_total[t] = tot;
+                if (a.tet_vol) a.tet_vol[t] = v;
+                if (a.tet_mean) a.tet_mean[t] = tot / v;
+                if (WITH_C) {
+#pragma unroll
+                    for (int k = 0; k < kMaxPhase; k++)
+                        if (k < a.nc) {
+                            if (a.tet_energy) a.tet_energy[(size_t)t * a.nc + k] = sqc[k] * v / (double)n3;
+                            if (a.tet_variation) a.tet_variation[(size_t)t * a.nc + k] = adc[k];
+                        }
+                }
+            }
+            if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
+                acc_tot += tot;
+                acc_sq += tsq;
+                acc_vol += v;
+            }
+        } else if (valid && lane_g == 0) {
+            if (a.tet_total) a.tet_total[t] = -1.0;
+            if (a.tet_vol) a.tet_vol[t] = -1.0;
+            if (a.tet_mean) a.tet_mean[t] = -1.0;
+            if (WITH_C)
+                for (int k = 0; k < a.nc; k++) {
+                    if (a.tet_energy) a.tet_energy[(size_t)t * a.nc + k] = -1.0;
+                    if (a.tet_variation) a.tet_variation[(size_t)t * a.nc + k] = -1.0;
+                }
+        }
+    }
+
+    // ---- CTA reduction of the per-label sums: lanes with equal (lane & (G-1)) hold the same label
+#pragma unroll
+    for (int m = 16; m >= G; m >>= 1) {
+        acc_tot += shfl_xor_d(acc_tot, m);
+        acc_sq += shfl_xor_d(acc_sq, m);
+        acc_vol += shfl_xor_d(acc_vol, m);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
+    __shared__ double sm[8][3 * kMaxPhase];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < kMaxPhase && lane < G) {
+        sm[warp][lane] = acc_tot;
+        sm[warp][kMaxPhase + lane] = acc_sq;
+        sm[warp][2 * kMaxPhase + lane] = acc_vol;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * kMaxPhase) {
+        double r = 0;
+        const int nw = blockDim.x >> 5;
+        for (int wdx = 0; wdx < nw; wdx++) r += sm[wdx][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
+    }
+    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+}
+
+// Adds the per-CTA partial rows in CTA order and derives the means: out[0..P) total, [P..2P) sumsq,
+// [2P..3P) volume (P = nb_phase), mean[k] = total/volume.
+__global__ void tet_finalize_kernel(const double *partials, int n_rows, int nb_phase, double *sums, double *mean)
+{
+    const int k = threadIdx.x;
+    if (k >= 3 * kMaxPhase) return;
+    const int which = k / kMaxPhase, ph = k % kMaxPhase;
+    double r = 0;
+    for (int i = 0; i < n_rows; i++) r += partials[(size_t)i * 3 * kMaxPhase + k];
+    if (ph < nb_phase) sums[which * nb_phase + ph] = r;
+    __shared__ double tot[kMaxPhase], vol[kMaxPhase];
+    if (which == 0) tot[ph] = r;
+    if (which == 2) vol[ph] = r;
+    __syncthreads();
+    if (mean && k < nb_phase) mean[k] = tot[k] / vol[k];
+}
+
+__global__ void means_from_sums_kernel(const double *sums, int nb_phase, double *mean)
+{
+    const int k = threadIdx.x;
+    if (k < nb_phase) mean[k] = sums[k] / sums[2 * nb_phase + k];
+}
+
+// Bit-exactness witness: one thread per tet walks its sample points in table order and hashes the
+// truncated voxel coordinates (order-sensitive FNV-1a), exactly what oracle/ref_driver.cpp records
+// with the reference's own table and macro.
+__global__ void tet_sample_hash_kernel(MeshView mesh, const double *__restrict__ tet_bary, unsigned long long *hash, int *nsamp)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= mesh.n_tets) return;
+    const uint4 nd = __ldg(mesh.tet_nodes + t);
+    const V3 p0 = load_pos(mesh.pos4, nd.x), p1 = load_pos(mesh.pos4, nd.y), p2 = load_pos(mesh.pos4, nd.z), p3 = load_pos(mesh.pos4, nd.w);
+    const double v = tet_volume(p0, p1, p2, p3);
+    const int L = tet_level(v);
+    const int n3 = (L + 1) * (L + 1) * (L + 1);
+    const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+    unsigned long long h = 1469598103934665603ull;
+    for (int i = 0; i < n3; i++) {
+        const double *b = tet_bary + 4 * (size_t)(off + i);
+        const double px = ((p0.x * b[0] + p1.x * b[1]) + p2.x * b[2]) + p3.x * b[3];
+        const double py = ((p0.y * b[0] + p1.y * b[1]) + p2.y * b[2]) + p3.y * b[3];
+        const double pz = ((p0.z * b[0] + p1.z * b[1]) + p2.z * b[2]) + p3.z * b[3];
+        const int c[3] = {(int)px, (int)py, (int)pz};
+#pragma unroll
+        for (int k = 0; k < 3; k++) { h ^= (unsigned long long)(unsigned)c[k]; h *= 1099511628211ull; }
+    }
+    hash[t] = h;
+    nsamp[t] = n3;
+}
+
+// is_point_inside (DEMO/segment_function.cpp:2576-2580) on the 4-point Util::barycentric_coords
+// (is_mesh/util.h:349-364): all four normalised signed volumes >= 0.
+__global__ void points_in_tets_kernel(MeshView mesh, unsigned n, const unsigned *tet_idx, const double *pts, unsigned char *inside)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 nd = __ldg(mesh.tet_nodes + tet_idx[i]);
+    const V3 a = load_pos(mesh.pos4, nd.x), b = load_pos(mesh.pos4, nd.y), c = load_pos(mesh.pos4, nd.z), d = load_pos(mesh.pos4, nd.w);
+    const V3 p = {pts[3 * (size_t)i], pts[3 * (size_t)i + 1], pts[3 * (size_t)i + 2]};
+    double c0 = signed_volume(p, b, c, d), c1 = signed_volume(a, p, c, d), c2 = signed_volume(a, b, p, d), c3 = signed_volume(a, b, c, p);
+    const double s = ((c0 + c1) + c2) + c3;
+    c0 /= s; c1 /= s; c2 /= s; c3 /= s;
+    inside[i] = (c0 >= 0 && c1 >= 0 && c2 >= 0 && c3 >= 0) ? 1 : 0;
+}
+
+// =================================================================================================
+// External force: segment_function::compute_external_force (DEMO/segment_function.cpp:1425-1473)
+// =================================================================================================
+struct FaceGeom {
+    V3 p[3];
+    V3 norm;
+    double area, c0, c1;
+    int gs;
+};
+
+DSC_D int first_not_in(uint4 tn, unsigned f0, unsigned f1, unsigned f2)
+{   // (get_nodes(tid) - nids).front(), is_mesh/is_mesh.h:632-637
+    if (tn.x != f0 && tn.x != f1 && tn.x != f2) return tn.x;
+    if (tn.y != f0 && tn.y != f1 && tn.y != f2) return tn.y;
+    if (tn.z != f0 && tn.z != f1 && tn.z != f2) return tn.z;
+    return tn.w;
+}
+
+// DSC::get_normal(fid, tid): normal_direction over get_sorted_nodes(fid, tid)
+// (src/DSC.h:3120-3124; is_mesh/is_mesh.h:632-637, 981-1000; is_mesh/util.h:366-376)
+DSC_D V3 face_normal_wrt(const MeshView &m, unsigned f0, unsigned f1, unsigned f2, uint4 tn)
+{
+    const unsigned apex = first_not_in(tn, f0, f1, f2);
+    const V3 A = load_pos(m.pos4, f0), B = load_pos(m.pos4, f1), C = load_pos(m.pos4, f2), Q = load_pos(m.pos4, apex);
+    const V3 x = sub(Q, A), y = sub(B, A), z = sub(C, A);
+    const bool cw = dot(x, cross(y, z)) > 0.;
+    const V3 a = cw ? B : A, b = cw ? A : B;
+    return normalize(cross(sub(b, a), sub(C, a)));
+}
+
+DSC_D V3 tet_barycenter(const MeshView &m, uint4 tn)
+{   // (a + b + c + d)*0.25 in get_nodes(t) order (src/DSC.h:3254-3258, is_mesh/util.h:100-103)
+    const V3 a = load_pos(m.pos4, tn.x), b = load_pos(m.pos4, tn.y), c = load_pos(m.pos4, tn.z), d = load_pos(m.pos4, tn.w);
+    return mul(add(add(add(a, b), c), d), 0.25);
+}
+
+DSC_D bool face_setup(const MeshView &m, unsigned f, int nb_phase, const double *__restrict__ mean, FaceGeom &g, unsigned n[3])
+{
+    const unsigned t0 = __ldg(m.face_tets + 2 * (size_t)f), t1 = __ldg(m.face_tets + 2 * (size_t)f + 1);
+    if (t0 == kNoTet || t1 == kNoTet) return false; // the reference would read tets[1] out of range here
+    n[0] = __ldg(m.face_nodes + 3 * (size_t)f);
+    n[1] = __ldg(m.face_nodes + 3 * (size_t)f + 1);
+    n[2] = __ldg(m.face_nodes + 3 * (size_t)f + 2);
+    g.p[0] = load_pos(m.pos4, n[0]); g.p[1] = load_pos(m.pos4, n[1]); g.p[2] = load_pos(m.pos4, n[2]);
+    const int l0 = __ldg(m.tet_label + t0), l1 = __ldg(m.tet_label + t1);
+    // phase_intensity (DEMO/segment_function.h:149-156): -0.3 for the label-0 side
+    g.c0 = (l0 >= 1 && l0 <= nb_phase) ? mean[l0 - 1] : -0.3;
+    g.c1 = (l1 >= 1 && l1 <= nb_phase) ? mean[l1 - 1] : -0.3;
+    const uint4 tn0 = __ldg(m.tet_nodes + t0), tn1 = __ldg(m.tet_nodes + t1);
+    // get_normal(fid): sorted w.r.t. the co-boundary tet with the highest label, first wins (is_mesh.h:639-663)
+    V3 N = face_normal_wrt(m, n[0], n[1], n[2], l1 > l0 ? tn1 : tn0);
+    const V3 l01 = sub(tet_barycenter(m, tn1), tet_barycenter(m, tn0));
+    N = mul(N, dot(N, l01));
+    g.norm = divs(N, length(N)); // Vec3d::normalize
+    g.area = tri_area(g.p[0], g.p[1], g.p[2]);
+    g.gs = gauss_set(g.area);
+    return true;
+}
+
+struct ForceArgs {
+    VolumeView vol;
+    MeshView mesh;
+    int nb_phase;
+    const double *mean;
+    double *forces;
+    unsigned begin, end; // node range (gather) or face range (atomic)
+    unsigned long long *gauss_count;
+};
+
+// Gather form: one thread per node; walks the node's incident interface faces in ascending face
+// order and, inside a face, the Gauss points in table order -- the order in which the reference
+// executes forces[verts[ii]] += f*c.coord[ii] (:1459-1468) -- so the result is bit-identical to the
+// reference's, needs no atomics and does not depend on the number of GPUs.
+template <typename VoxT> __global__ void __launch_bounds__(128) force_gather_kernel(const ForceArgs a)
+{
+    const unsigned v = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.end) return;
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    double fx = 0, fy = 0, fz = 0;
+    const unsigned e0 = __ldg(a.mesh.node_off + v), e1 = __ldg(a.mesh.node_off + v + 1);
+    unsigned long long ng = 0;
+    for (unsigned e = e0; e < e1; e++) {
+        const unsigned inc = __ldg(a.mesh.node_inc + e);
+        const unsigned f = inc >> 2, corner = inc & 3u;
+        FaceGeom g;
+        unsigned n[3];
+        if (!face_setup(a.mesh, f, a.nb_phase, a.mean, g, n)) continue;
+        for (int q = c_gauss_off[g.gs]; q < c_gauss_off[g.gs + 1]; q++) {
+            const double w = c_gauss[4 * q], b0 = c_gauss[4 * q + 1], b1 = c_gauss[4 * q + 2], b2 = c_gauss[4 * q + 3];
+            const V3 p = add(add(mul(g.p[0], b0), mul(g.p[1], b1)), mul(g.p[2], b2)); // get_coord_tri
+            const double I = fetch_trilinear(vol, a.vol.X, a.vol.Y, a.vol.Z, p);
+            const V3 fv = mul(g.norm, (2 * I - g.c0 - g.c1) * (g.c0 - g.c1) * w * g.area);
+            const double bc = corner == 0 ? b0 : (corner == 1 ? b1 : b2);
+            fx += fv.x * bc; fy += fv.y * bc; fz += fv.z * bc;
+            if (corner == 0) ng++;
+        }
+    }
+    a.forces[3 * (size_t)v] = fx;
+    a.forces[3 * (size_t)v + 1] = fy;
+    a.forces[3 * (size_t)v + 2] = fz;
+    if (ng) atomicAdd(a.gauss_count, ng);
+}
+
+// Scatter form: one thread per interface face, per-corner sums over the Gauss points, then nine
+// FP64 red.global.add per face.  Order of additions across faces is not fixed (1e-6 parity only).
+template <typename VoxT> __global__ void __launch_bounds__(128) force_atomic_kernel(const ForceArgs a)
+{
+    const unsigned f = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.end) return;
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    FaceGeom g;
+    unsigned n[3];
+    if (!face_setup(a.mesh, f, a.nb_phase, a.mean, g, n)) return;
+    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    unsigned long long ng = 0;
+    for (int q = c_gauss_off[g.gs]; q < c_gauss_off[g.gs + 1]; q++) {
+        const double w = c_gauss[4 * q];
+        const double b[3] = {c_gauss[4 * q + 1], c_gauss[4 * q + 2], c_gauss[4 * q + 3]};
+        const V3 p = add(add(mul(g.p[0], b[0]), mul(g.p[1], b[1])), mul(g.p[2], b[2]));
+        const double I = fetch_trilinear(vol, a.vol.X, a.vol.Y, a.vol.Z, p);
+        const V3 fv = mul(g.norm, (2 * I - g.c0 - g.c1) * (g.c0 - g.c1) * w * g.area);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { acc[k][0] += fv.x * b[k]; acc[k][1] += fv.y * b[k]; acc[k][2] += fv.z * b[k]; }
+        ng++;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        atomicAdd(a.forces + 3 * (size_t)n[k], acc[k][0]);
+        atomicAdd(a.forces + 3 * (size_t)n[k] + 1, acc[k][1]);
+        atomicAdd(a.forces + 3 * (size_t)n[k] + 2, acc[k][2]);
+    }
+    atomicAdd(a.gauss_count, ng);
+}
+
+// =================================================================================================
+// z prefix-sum table: image3d::build_sum_table (DEMO/image3d.cpp:166-176).  One thread per (x,y)
+// column runs the same sequential recurrence, so the table is bit-exact; loads/stores are coalesced
+// along x.
+// =================================================================================================
+template <typename VoxT> __global__ void sum_table_kernel(const VoxT *__restrict__ vol, double *__restrict__ table, int X, int Y, int Z)
+{
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t XY = (size_t)X * Y;
+    if (col >= XY) return;
+    double s = decode<VoxT>(vol[col]);
+    table[col] = s;
+    for (int z = 1; z < Z; z++) {
+        s = s + decode<VoxT>(vol[col + (size_t)z * XY]);
+        table[col + (size_t)z * XY] = s;
+    }
+}
+
+// =================================================================================================
+// z-ray pass: update_average_intensity / compute_energy (DEMO/segment_function.cpp:1600-1764, 2331-2492)
+//   1. raster (count) : per face, bounding-box pixels, 2-D barycentric inside test -> hits per (phase, column)
+//   2. exclusive scan of the hit counts
+//   3. raster (fill)  : same walk, hits written to their ray's segment (slot by integer atomic)
+//   4. resolve        : one thread per ray restores face order, sorts with the libstdc++ algorithm,
+//                       erases adjacent duplicates, pairs the hits and accumulates
+// =================================================================================================
+struct RayArgs {
+    VolumeView vol;
+    MeshView mesh;
+    int nb_phase;
+    unsigned face_begin, face_end;
+    unsigned *ray_count;   // [nb_phase*X*Y]
+    unsigned *ray_offset;  // exclusive scan of ray_count
+    unsigned *ray_cursor;  // zeroed before fill
+    uint2 *hits;           // (face index, packed hit)
+};
+
+template <bool FILL> __global__ void __launch_bounds__(128) zray_raster_kernel(const RayArgs a)
+{
+    const unsigned f = a.face_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.face_end) return;
+    const MeshView &m = a.mesh;
+    if (__ldg(m.face_is_boundary + f)) return; // is_interface() and !is_boundary(), :1628
+    const unsigned t0 = __ldg(m.face_tets + 2 * (size_t)f), t1 = __ldg(m.face_tets + 2 * (size_t)f + 1);
+    if (t0 == kNoTet || t1 == kNoTet) return;
+    const int phase0 = __ldg(m.tet_label + t0) - 1, phase1 = __ldg(m.tet_label + t1) - 1;
+    const unsigned n0 = __ldg(m.face_nodes + 3 * (size_t)f), n1 = __ldg(m.face_nodes + 3 * (size_t)f + 1), n2 = __ldg(m.face_nodes + 3 * (size_t)f + 2);
+    const V3 q0 = load_pos(m.pos4, n0), q1 = load_pos(m.pos4, n1), q2 = load_pos(m.pos4, n2);
+    const V3 nrm = face_normal_wrt(m, n0, n1, n2, __ldg(m.tet_nodes + t0)); // get_normal(fid, tet[0]), :1639
+    const bool in_1 = dot(nrm, V3{0, 0, 1}) > 0;
+    const int X = a.vol.X, Y = a.vol.Y;
+    const size_t XY = (size_t)X * Y;
+    // bounding_box (:1578-1593) and the loop bounds floor(ld) .. round(ru) (:1644-1646), clipped to the image
+    const double ldx = fmin(fmin(q0.x, q1.x), q2.x), ldy = fmin(fmin(q0.y, q1.y), q2.y);
+    const double rux = fmax(fmax(q0.x, q1.x), q2.x), ruy = fmax(fmax(q0.y, q1.y), q2.y);
+    const double fx0 = floor(ldx), fy0 = floor(ldy), rx1 = round(rux), ry1 = round(ruy);
+    const int x0 = fx0 < 0 ? 0 : (fx0 > (double)X ? X : (int)fx0), y0 = fy0 < 0 ? 0 : (fy0 > (double)Y ? Y : (int)fy0);
+    const int x1 = rx1 < 0 ? 0 : (rx1 > (double)X ? X : (int)rx1), y1 = ry1 < 0 ? 0 : (ry1 > (double)Y ? Y : (int)ry1);
+    // 2-D barycentric_coords (is_mesh/util.h:283-315) with z of all operands 0
+    const V3 A = {q0.x, q0.y, 0}, B = {q1.x, q1.y, 0}, C = {q2.x, q2.y, 0};
+    const V3 v0 = sub(B, A), v1 = sub(C, A);
+    const double d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1);
+    const double denom = d00 * d11 - d01 * d01;
+    if (fabs(denom) < 1e-8) return; // bError
+    for (int x = x0; x < x1; x++)
+        for (int y = y0; y < y1; y++) {
+            const V3 p = {x + 0.5, y + 0.5, 0};
+            const V3 v2 = sub(p, A);
+            const double d20 = dot(v2, v0), d21 = dot(v2, v1);
+            const double bc1 = (d11 * d20 - d01 * d21) / denom;
+            const double bc2 = (d00 * d21 - d01 * d20) / denom;
+            const double bc0 = 1. - bc1 - bc2;
+            if (bc0 > -1e-8 && bc1 > -1e-8 && bc2 > -1e-8) {
+                const double pz = (q0.z * bc0 + q1.z * bc1) + q2.z * bc2;
+                const int zz = (int)nearbyint(pz);
+                const size_t col = (size_t)y * X + x;
+                if (phase0 >= 0 && phase0 < a.nb_phase) {
+                    const size_t r = (size_t)phase0 * XY + col;
+                    if (FILL) {
+                        const unsigned slot = atomicAdd(a.ray_cursor + r, 1u);
+                        a.hits[a.ray_offset[r] + slot] = make_uint2(f, (unsigned)((zz << 1) | (in_1 ? 0 : 1)));
+                    } else atomicAdd(a.ray_count + r, 1u);
+                }
+                if (phase1 >= 0 && phase1 < a.nb_phase) {
+                    const size_t r = (size_t)phase1 * XY + col;
+                    if (FILL) {
+                        const unsigned slot = atomicAdd(a.ray_cursor + r, 1u);
+                        a.hits[a.ray_offset[r] + slot] = make_uint2(f, (unsigned)((zz << 1) | (in_1 ? 1 : 0)));
+                    } else atomicAdd(a.ray_count + r, 1u);
+                }
+            }
+        }
+}
+
+// ---- exclusive scan over unsigned counts (three small kernels; n up to 1024*4096 elements per level)
+constexpr int kScanItems = 4096; // elements per CTA (1024 threads x 4)
+
+__global__ void __launch_bounds__(1024) scan_block_kernel(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned *block_sums, size_t n)
+{
+    __shared__ unsigned warp_sums[32];
+    const size_t base = (size_t)blockIdx.x * kScanItems + (size_t)threadIdx.x * 4;
+    unsigned v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = base + k < n ? in[base + k] : 0u;
+    const unsigned mine = v[0] + v[1] + v[2] + v[3];
+    unsigned incl = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = warp_sums[lane];
+        unsigned wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        warp_sums[lane] = wi - w; // exclusive
+        if (lane == 31 && block_sums) block_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    unsigned run = warp_sums[warp] + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+__global__ void scan_sums_kernel(unsigned *block_sums, unsigned n_blocks, unsigned *total)
+{   // single thread block, sequential carry over chunks of 1024
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned base = 0; base < n_blocks; base += 1024) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned mine = i < n_blocks ? block_sums[i] : 0u;
+        unsigned incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = warp_sums[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            warp_sums[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned excl = carry + warp_sums[warp] + incl - mine;
+        if (i < n_blocks) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + mine;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void __launch_bounds__(1024) scan_add_kernel(unsigned *out, const unsigned *block_sums, size_t n)
+{
+    const size_t base = (size_t)blockIdx.x * kScanItems + (size_t)threadIdx.x * 4;
+    const unsigned add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (base + k < n) out[base + k] += add;
+}
+
+struct ResolveArgs {
+    VolumeView vol;
+    int nb_phase;
+    int mode;                  // 0 = means (sum table), 1 = energy data term
+    double c[kMaxPhase];       // mode 1: phase means
+    const unsigned *ray_count;
+    const unsigned *ray_offset;
+    const uint2 *hits;
+    unsigned col_begin, col_end; // column range of this partition
+    double *partial_sum;         // [nb_phase][gridDim.x]
+    long long *partial_cnt;      // [nb_phase][gridDim.x]
+    int *overflow;
+};
+
+template <typename VoxT> __global__ void __launch_bounds__(128) zray_resolve_kernel(const ResolveArgs a)
+{
+    const int phase = blockIdx.y;
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const size_t XY = (size_t)X * Y;
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    double sum = 0;
+    long long cnt = 0;
+    const unsigned col = a.col_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < a.col_end) {
+        const size_t r = (size_t)phase * XY + col;
+        const unsigned n_hits = __ldg(a.ray_count + r);
+        if (n_hits > 1) { // rays with a single hit are ignored (:1701)
+            if (n_hits > (unsigned)kMaxRayHits) {
+                atomicExch(a.overflow, 1);
+            } else {
+                unsigned fidx[kMaxRayHits];
+                int h[kMaxRayHits];
+                const uint2 *src = a.hits + __ldg(a.ray_offset + r);
+                int n = (int)n_hits;
+                // restore the reference's push order = ascending face key (the fill order is arbitrary)
+                for (int i = 0; i < n; i++) {
+                    const uint2 e = src[i];
+                    int j = i - 1;
+                    while (j >= 0 && fidx[j] > e.x) { fidx[j + 1] = fidx[j]; h[j + 1] = h[j]; j--; }
+                    fidx[j + 1] = e.x; h[j + 1] = (int)e.y;
+                }
+                std_sort_hits(h, n);
+                n = erase_adjacent_duplicates(h, n);
+                if ((n & 1) == 0) { // odd rays are silently dropped (:1721, 1741)
+                    const int x = (int)(col % X), y = (int)(col / X);
+                    for (int j = 0; j < n / 2; j++) {
+                        int z1 = h[2 * j] >> 1, z2 = h[2 * j + 1] >> 1;
+                        if (z1 < 0) z1 = 0;
+                        if (z2 < z1) z2 = z1;
+                        cnt += z2 - z1;
+                        if (a.mode == 0) {
+                            int lo = z1, hi = z2; // image3d::sum_line_z clamps (image3d.cpp:193-201)
+                            if (hi >= Z) { hi = Z - 1; if (lo >= Z) lo = Z - 1; }
+                            sum += a.vol.sum_table[(size_t)hi * XY + col] - a.vol.sum_table[(size_t)lo * XY + col];
+                        } else {
+                            const double cc = a.c[phase];
+                            for (int k = z1 + 1; k < z2; k++) {
+                                const double d = fetch(vol, X, Y, Z, x, y, k) - cc;
+                                sum += d * d; // std::pow(., 2)
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // CTA reduction -> one partial per (phase, CTA); finalize adds them in CTA order
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        sum += shfl_xor_d(sum, m);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, m);
+    }
+    __shared__ double ssum[4];
+    __shared__ long long scnt[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { ssum[warp] = sum; scnt[warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        long long c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { s += ssum[w]; c += scnt[w]; }
+        a.partial_sum[(size_t)phase * gridDim.x + blockIdx.x] = s;
+        a.partial_cnt[(size_t)phase * gridDim.x + blockIdx.x] = c;
+    }
+}
+
+// sums[0..P) = total, [P..2P) = 0 (no squared sum on this path), [2P..3P) = voxel count
+__global__ void zray_finalize_kernel(const double *partial_sum, const long long *partial_cnt, int n_blocks, int nb_phase, double *sums, double *mean)
+{
+    const int k = threadIdx.x;
+    if (k >= nb_phase) return;
+    double s = 0;
+    long long c = 0;
+    for (int i = 0; i < n_blocks; i++) { s += partial_sum[(size_t)k * n_blocks + i]; c += partial_cnt[(size_t)k * n_blocks + i]; }
+    sums[k] = s;
+    sums[nb_phase + k] = 0;
+    sums[2 * nb_phase + k] = (double)c;
+    if (mean) mean[k] = s / (double)c;
+}
+
+// m_vertex_bound of update_vertex_boundary (DEMO/segment_function.cpp:2158-2171) from the snapshot
+__global__ void vertex_bound_kernel(MeshView m, unsigned char *vb)
+{
+    const unsigned f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.n_faces) return;
+    const unsigned t0 = m.face_tets[2 * (size_t)f], t1 = m.face_tets[2 * (size_t)f + 1];
+    if (t0 == kNoTet || t1 == kNoTet) return;
+    if (m.tet_label[t0] == 0 || m.tet_label[t1] == 0) {
+        vb[m.face_nodes[3 * (size_t)f]] = 1;
+        vb[m.face_nodes[3 * (size_t)f + 1]] = 1;
+        vb[m.face_nodes[3 * (size_t)f + 2]] = 1;
+    }
+}
+
+// alpha * sum of areas of interface faces whose nodes are not all vertex-bound (:2482-2489);
+// one partial per CTA, added in CTA order by the caller's finalize.
+__global__ void __launch_bounds__(256) area_term_kernel(MeshView m, const unsigned char *vb, double alpha, double *partials)
+{
+    const unsigned f = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0;
+    if (f < m.n_faces) {
+        const unsigned n0 = m.face_nodes[3 * (size_t)f], n1 = m.face_nodes[3 * (size_t)f + 1], n2 = m.face_nodes[3 * (size_t)f + 2];
+        if (!(vb[n0] && vb[n1] && vb[n2])) s = alpha * tri_area(load_pos(m.pos4, n0), load_pos(m.pos4, n1), load_pos(m.pos4, n2));
+    }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) s += shfl_xor_d(s, k);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += sm[w];
+        partials[blockIdx.x] = r;
+    }
+}
+
+__global__ void sum_partials_kernel(const double *partials, int n, double *out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double r = 0;
+        for (int i = 0; i < n; i++) r += partials[i];
+        *out = r;
+    }
+}
+
+} // namespace dsc

@@ -1,0 +1,923 @@
+// dscgpu.cu -- C ABI (include/dscgpu.h) over the sm_100a kernels in dsc_kernels.cuh.
+// Host-side responsibilities: context and HBM buffer management, pinned staging of the mesh
+// snapshot, the node->face CSR (counting sort), launch configuration, CUDA-event timers.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <new>
+
+#include "../../include/dscgpu.h"
+#include "dsc_kernels.cuh"
+#include "dsc_tables.h"
+
+using namespace dsc;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256; // headroom: meshes change size every iteration
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+size_t dtype_size(int dt) { return dt == DSCGPU_U8 ? 1 : dt == DSCGPU_U16 ? 2 : dt == DSCGPU_F32 ? 4 : 8; }
+
+} // namespace
+
+struct dscgpu_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int dims[3] = {0, 0, 0};
+    int dtype = DSCGPU_F32;
+    void *d_vol = nullptr;
+    double *d_sum_table = nullptr;
+    bool has_sum_table = false;
+    double *d_tet_bary = nullptr;
+
+    bool has_snapshot = false;
+    uint32_t n_nodes = 0, n_tets = 0, n_faces = 0;
+    DevBuf pos4, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc;
+    // pinned staging (host side of the snapshot)
+    PinBuf h_pos4, h_tet_nodes, h_tet_label, h_face_nodes, h_face_tets, h_face_isb, h_node_off, h_node_inc, h_out;
+    uint32_t st_nodes = 0, st_tets = 0, st_faces = 0;
+    bool staging_valid = false;
+
+    uint32_t tet_b = 0, tet_e = 0, face_b = 0, face_e = 0, node_b = 0, node_e = 0;
+
+    DevBuf partials, sums, mean, forces, counters;
+    DevBuf o_total, o_vol, o_mean, o_energy, o_variation, o_hash, o_nsamp;
+    DevBuf ray_count, ray_offset, ray_cursor, hits, block_sums, ray_psum, ray_pcnt, misc, vbound, pit;
+
+    cudaEvent_t ev[DSCGPU_T_COUNT][2];
+    bool ev_used[DSCGPU_T_COUNT];
+    bool timers_on = false;
+    uint64_t launches = 0;
+    int lanes_per_tet = 0;
+    int auto_lanes = 8;
+    int tet_grid = 0;
+    std::string err;
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            char b__[512];                                                                            \
+            snprintf(b__, sizeof b__, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            ctx->err = b__;                                                                           \
+            return DSCGPU_ERR_CUDA;                                                                   \
+        }                                                                                             \
+    } while (0)
+
+#define ARG(cond, msg)                  \
+    do {                                \
+        if (!(cond)) {                  \
+            ctx->err = msg;             \
+            return DSCGPU_ERR_ARG;      \
+        }                               \
+    } while (0)
+
+namespace {
+
+struct TimerScope {
+    dscgpu_ctx *c;
+    int which;
+    TimerScope(dscgpu_ctx *ctx, int w) : c(ctx), which(w)
+    {
+        if (c->timers_on) { cudaEventRecord(c->ev[w][0], c->stream); }
+    }
+    ~TimerScope()
+    {
+        if (c->timers_on) { cudaEventRecord(c->ev[which][1], c->stream); c->ev_used[which] = true; }
+    }
+};
+
+VolumeView vol_view(const dscgpu_ctx *c) { return VolumeView{c->d_vol, c->d_sum_table, c->dims[0], c->dims[1], c->dims[2]}; }
+
+MeshView mesh_view(const dscgpu_ctx *c)
+{
+    MeshView m;
+    m.pos4 = c->pos4.as<double4>();
+    m.tet_nodes = c->tet_nodes.as<uint4>();
+    m.tet_label = c->tet_label.as<int>();
+    m.face_nodes = c->face_nodes.as<unsigned>();
+    m.face_tets = c->face_tets.as<unsigned>();
+    m.face_is_boundary = c->face_isb.as<unsigned char>();
+    m.node_off = c->node_off.as<unsigned>();
+    m.node_inc = c->node_inc.as<unsigned>();
+    m.n_nodes = c->n_nodes; m.n_tets = c->n_tets; m.n_faces = c->n_faces;
+    return m;
+}
+
+// counters: [0] samples, [1] gauss points, [2] overflow flag (int), [3] scan total (unsigned)
+unsigned long long *ctr(dscgpu_ctx *c, int i) { return c->counters.as<unsigned long long>() + i; }
+
+template <typename VoxT, int G, bool WITH_C> int launch_tet_t(dscgpu_ctx *ctx, TetArgs &a)
+{
+    auto kern = tet_integrate_kernel<VoxT, G, WITH_C>;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    if (occ < 1) occ = 1;
+    unsigned n_work = a.tet_end - a.tet_begin;
+    unsigned groups_per_block = 256 / G;
+    unsigned need = (n_work + groups_per_block - 1) / groups_per_block;
+    unsigned grid = (unsigned)(ctx->num_sms * occ);
+    if (need < grid) grid = need ? need : 1;
+    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
+    a.partials = ctx->partials.as<double>();
+    ctx->tet_grid = (int)grid;
+    kern<<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT> int launch_tet_v(dscgpu_ctx *ctx, TetArgs &a, int G, bool with_c)
+{
+    if (G == 32) return with_c ? launch_tet_t<VoxT, 32, true>(ctx, a) : launch_tet_t<VoxT, 32, false>(ctx, a);
+    return with_c ? launch_tet_t<VoxT, 8, true>(ctx, a) : launch_tet_t<VoxT, 8, false>(ctx, a);
+}
+
+int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
+{
+    int G = ctx->lanes_per_tet ? ctx->lanes_per_tet : ctx->auto_lanes;
+    if (G != 32) G = 8;
+    switch (ctx->dtype) {
+    case DSCGPU_U8: return launch_tet_v<unsigned char>(ctx, a, G, with_c);
+    case DSCGPU_U16: return launch_tet_v<unsigned short>(ctx, a, G, with_c);
+    case DSCGPU_F32: return launch_tet_v<float>(ctx, a, G, with_c);
+    default: return launch_tet_v<double>(ctx, a, G, with_c);
+    }
+}
+
+// tet pass + finalize; leaves sums (3*nb) in ctx->sums and means in ctx->mean (device)
+int run_tet_pass(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, double *d_total, double *d_vol, double *d_mean,
+                 double *d_energy, double *d_variation, double *d_sums_out, double *d_mean_out)
+{
+    TetArgs a;
+    a.vol = vol_view(ctx);
+    a.mesh = mesh_view(ctx);
+    a.tet_bary = ctx->d_tet_bary;
+    a.tet_begin = ctx->tet_b; a.tet_end = ctx->tet_e;
+    a.include_bound = include_bound;
+    a.nb_phase = nb_phase;
+    a.nc = nc;
+    for (int k = 0; k < kMaxPhase; k++) a.c[k] = (c && k < nc) ? c[k] : 0.0;
+    a.tet_total = d_total; a.tet_vol = d_vol; a.tet_mean = d_mean; a.tet_energy = d_energy; a.tet_variation = d_variation;
+    a.sample_count = ctr(ctx, 0);
+    CK(cudaMemsetAsync(ctr(ctx, 0), 0, sizeof(unsigned long long), ctx->stream));
+    {
+        TimerScope ts(ctx, DSCGPU_T_TET);
+        int r = launch_tet(ctx, a, nc > 0 && (d_energy || d_variation));
+        if (r) return r;
+    }
+    {
+        TimerScope ts(ctx, DSCGPU_T_PHASE_FINAL);
+        tet_finalize_kernel<<<1, 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums_out, d_mean_out);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return DSCGPU_OK;
+}
+
+template <typename VoxT> int launch_force_t(dscgpu_ctx *ctx, ForceArgs &a, int mode)
+{
+    unsigned n = a.end - a.begin;
+    if (n == 0) return DSCGPU_OK;
+    unsigned grid = (n + 127) / 128;
+    if (mode == DSCGPU_FORCE_GATHER) force_gather_kernel<VoxT><<<grid, 128, 0, ctx->stream>>>(a);
+    else force_atomic_kernel<VoxT><<<grid, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, double *d_forces)
+{
+    ForceArgs a;
+    a.vol = vol_view(ctx);
+    a.mesh = mesh_view(ctx);
+    a.nb_phase = nb_phase;
+    a.mean = d_mean;
+    a.forces = d_forces;
+    a.gauss_count = ctr(ctx, 1);
+    CK(cudaMemsetAsync(ctr(ctx, 1), 0, sizeof(unsigned long long), ctx->stream));
+    TimerScope ts(ctx, DSCGPU_T_FORCE);
+    bool whole_nodes = ctx->node_b == 0 && ctx->node_e == ctx->n_nodes;
+    if (mode == DSCGPU_FORCE_GATHER) {
+        a.begin = ctx->node_b; a.end = ctx->node_e;
+        // nodes outside this context's range must read as zero for the all-reduce
+        if (!whole_nodes) CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
+    } else {
+        a.begin = ctx->face_b; a.end = ctx->face_e;
+        CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
+    }
+    switch (ctx->dtype) {
+    case DSCGPU_U8: return launch_force_t<unsigned char>(ctx, a, mode);
+    case DSCGPU_U16: return launch_force_t<unsigned short>(ctx, a, mode);
+    case DSCGPU_F32: return launch_force_t<float>(ctx, a, mode);
+    default: return launch_force_t<double>(ctx, a, mode);
+    }
+}
+
+int exclusive_scan(dscgpu_ctx *ctx, const unsigned *in, unsigned *out, size_t n, unsigned *d_total)
+{
+    unsigned n_blocks = (unsigned)((n + kScanItems - 1) / kScanItems);
+    CK(ctx->block_sums.ensure((size_t)n_blocks * sizeof(unsigned)));
+    scan_block_kernel<<<n_blocks, 1024, 0, ctx->stream>>>(in, out, ctx->block_sums.as<unsigned>(), n);
+    scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->block_sums.as<unsigned>(), n_blocks, d_total);
+    scan_add_kernel<<<n_blocks, 1024, 0, ctx->stream>>>(out, ctx->block_sums.as<unsigned>(), n);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT> void launch_resolve_t(dscgpu_ctx *ctx, const ResolveArgs &a, dim3 grid)
+{
+    zray_resolve_kernel<VoxT><<<grid, 128, 0, ctx->stream>>>(a);
+}
+
+// z-ray pass; mode 0 leaves sums/means on the device, mode 1 leaves the data term in sums[0..nb)
+int run_zray(dscgpu_ctx *ctx, int nb_phase, int mode, const double *c_host, double *d_sums_out, double *d_mean_out)
+{
+    const size_t XY = (size_t)ctx->dims[0] * ctx->dims[1];
+    const size_t n_rays = XY * nb_phase;
+    TimerScope ts(ctx, DSCGPU_T_ZRAY);
+    CK(ctx->ray_count.ensure(n_rays * sizeof(unsigned)));
+    CK(ctx->ray_offset.ensure(n_rays * sizeof(unsigned)));
+    CK(ctx->ray_cursor.ensure(n_rays * sizeof(unsigned)));
+    CK(cudaMemsetAsync(ctx->ray_count.p, 0, n_rays * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->ray_cursor.p, 0, n_rays * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctr(ctx, 2), 0, 2 * sizeof(unsigned long long), ctx->stream));
+    RayArgs ra;
+    ra.vol = vol_view(ctx);
+    ra.mesh = mesh_view(ctx);
+    ra.nb_phase = nb_phase;
+    ra.face_begin = 0; ra.face_end = ctx->n_faces; // every context rasterises all faces; rays are partitioned
+    ra.ray_count = ctx->ray_count.as<unsigned>();
+    ra.ray_offset = ctx->ray_offset.as<unsigned>();
+    ra.ray_cursor = ctx->ray_cursor.as<unsigned>();
+    ra.hits = nullptr;
+    unsigned fgrid = (ctx->n_faces + 127) / 128;
+    if (fgrid) {
+        zray_raster_kernel<false><<<fgrid, 128, 0, ctx->stream>>>(ra);
+        ctx->launches++;
+    }
+    unsigned *d_total = reinterpret_cast<unsigned *>(ctr(ctx, 3));
+    int r = exclusive_scan(ctx, ra.ray_count, ra.ray_offset, n_rays, d_total);
+    if (r) return r;
+    unsigned total_hits = 0;
+    CK(cudaMemcpyAsync(&total_hits, d_total, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->hits.ensure(((size_t)total_hits + 1) * sizeof(uint2)));
+    ra.hits = ctx->hits.as<uint2>();
+    if (fgrid) {
+        zray_raster_kernel<true><<<fgrid, 128, 0, ctx->stream>>>(ra);
+        ctx->launches++;
+    }
+    ResolveArgs rs;
+    rs.vol = vol_view(ctx);
+    rs.nb_phase = nb_phase;
+    rs.mode = mode;
+    for (int k = 0; k < kMaxPhase; k++) rs.c[k] = (c_host && k < nb_phase) ? c_host[k] : 0.0;
+    rs.ray_count = ra.ray_count; rs.ray_offset = ra.ray_offset; rs.hits = ra.hits;
+    // ray partition: contiguous column range derived from the tet partition fraction
+    unsigned col_b = 0, col_e = (unsigned)XY;
+    if (ctx->n_tets && !(ctx->tet_b == 0 && ctx->tet_e == ctx->n_tets)) {
+        col_b = (unsigned)((double)ctx->tet_b / ctx->n_tets * XY);
+        col_e = ctx->tet_e == ctx->n_tets ? (unsigned)XY : (unsigned)((double)ctx->tet_e / ctx->n_tets * XY);
+    }
+    rs.col_begin = col_b; rs.col_end = col_e;
+    unsigned n_blocks = (col_e - col_b + 127) / 128;
+    if (n_blocks == 0) n_blocks = 1;
+    CK(ctx->ray_psum.ensure((size_t)n_blocks * nb_phase * sizeof(double)));
+    CK(ctx->ray_pcnt.ensure((size_t)n_blocks * nb_phase * sizeof(long long)));
+    rs.partial_sum = ctx->ray_psum.as<double>();
+    rs.partial_cnt = ctx->ray_pcnt.as<long long>();
+    rs.overflow = reinterpret_cast<int *>(ctr(ctx, 2));
+    dim3 grid(n_blocks, nb_phase);
+    switch (ctx->dtype) {
+    case DSCGPU_U8: launch_resolve_t<unsigned char>(ctx, rs, grid); break;
+    case DSCGPU_U16: launch_resolve_t<unsigned short>(ctx, rs, grid); break;
+    case DSCGPU_F32: launch_resolve_t<float>(ctx, rs, grid); break;
+    default: launch_resolve_t<double>(ctx, rs, grid); break;
+    }
+    zray_finalize_kernel<<<1, 32, 0, ctx->stream>>>(rs.partial_sum, rs.partial_cnt, (int)n_blocks, nb_phase, d_sums_out, d_mean_out);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+int check_overflow(dscgpu_ctx *ctx)
+{
+    int of = 0;
+    CK(cudaMemcpyAsync(&of, ctr(ctx, 2), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (of) {
+        ctx->err = "a z-ray collected more than DSCGPU_MAX_RAY_HITS interface hits";
+        return DSCGPU_ERR_RAY_OVERFLOW;
+    }
+    return DSCGPU_OK;
+}
+
+int ensure_scratch(dscgpu_ctx *ctx)
+{
+    CK(ctx->sums.ensure(3 * kMaxPhase * sizeof(double)));
+    CK(ctx->mean.ensure(kMaxPhase * sizeof(double)));
+    CK(ctx->counters.ensure(8 * sizeof(unsigned long long)));
+    CK(ctx->misc.ensure(64));
+    return DSCGPU_OK;
+}
+
+void fill_stats(dscgpu_phase_stats *st, const double *sums, const double *mean, int nb_phase)
+{
+    memset(st, 0, sizeof(*st));
+    for (int k = 0; k < nb_phase; k++) {
+        st->total[k] = sums[k];
+        st->sumsq[k] = sums[nb_phase + k];
+        st->volume[k] = sums[2 * nb_phase + k];
+        st->mean[k] = mean[k];
+    }
+}
+
+// node -> incident interface faces CSR by counting sort; faces are visited in ascending index, so
+// every node's list is ascending (= the reference's accumulation order in compute_external_force)
+void build_node_csr(uint32_t n_nodes, uint32_t n_faces, const uint32_t *face_nodes, uint32_t *off, uint32_t *inc)
+{
+    memset(off, 0, sizeof(uint32_t) * ((size_t)n_nodes + 1));
+    for (size_t i = 0; i < 3 * (size_t)n_faces; i++) {
+        uint32_t v = face_nodes[i];
+        if (v < n_nodes) off[v + 1]++;
+    }
+    for (uint32_t v = 0; v < n_nodes; v++) off[v + 1] += off[v];
+    std::vector<uint32_t> cur(off, off + n_nodes);
+    for (uint32_t f = 0; f < n_faces; f++)
+        for (uint32_t k = 0; k < 3; k++) {
+            uint32_t v = face_nodes[3 * (size_t)f + k];
+            if (v < n_nodes) inc[cur[v]++] = (f << 2) | k;
+        }
+}
+
+} // namespace
+
+extern "C" {
+
+int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype, const void *voxels_host)
+{
+    if (!out) return DSCGPU_ERR_ARG;
+    *out = nullptr;
+    dscgpu_ctx *ctx = new (std::nothrow) dscgpu_ctx();
+    if (!ctx) return DSCGPU_ERR_ARG;
+    *out = ctx; // returned even on failure so that dscgpu_last_error can be read; caller destroys it
+    for (int i = 0; i < DSCGPU_T_COUNT; i++) { ctx->ev[i][0] = ctx->ev[i][1] = nullptr; ctx->ev_used[i] = false; }
+    ARG(dims && dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "dims must be positive");
+    ARG(dtype >= DSCGPU_U8 && dtype <= DSCGPU_F64, "unknown voxel dtype");
+    int n_dev = 0;
+    CK(cudaGetDeviceCount(&n_dev));
+    ARG(device >= 0 && device < n_dev, "no such CUDA device (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    ctx->device = device;
+    CK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < DSCGPU_T_COUNT; i++) { CK(cudaEventCreate(&ctx->ev[i][0])); CK(cudaEventCreate(&ctx->ev[i][1])); }
+    ctx->dims[0] = dims[0]; ctx->dims[1] = dims[1]; ctx->dims[2] = dims[2];
+    ctx->dtype = dtype;
+    size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    CK(cudaMalloc(&ctx->d_vol, n * dtype_size(dtype)));
+    if (voxels_host) CK(cudaMemcpyAsync(ctx->d_vol, voxels_host, n * dtype_size(dtype), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&ctx->d_tet_bary, sizeof(DSC_TET_BARY)));
+    CK(cudaMemcpyAsync(ctx->d_tet_bary, DSC_TET_BARY, sizeof(DSC_TET_BARY), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyToSymbolAsync(c_gauss, DSC_GAUSS, sizeof(DSC_GAUSS), 0, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyToSymbolAsync(c_gauss_off, DSC_GAUSS_SET_OFFSET, sizeof(DSC_GAUSS_SET_OFFSET), 0, cudaMemcpyHostToDevice, ctx->stream));
+    int r = ensure_scratch(ctx);
+    if (r) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSCGPU_OK;
+}
+
+int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
+{
+    if (!ctx) return DSCGPU_OK;
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    DevBuf *bufs[] = {&ctx->pos4, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
+                      &ctx->partials, &ctx->sums, &ctx->mean, &ctx->forces, &ctx->counters, &ctx->o_total, &ctx->o_vol, &ctx->o_mean, &ctx->o_energy,
+                      &ctx->o_variation, &ctx->o_hash, &ctx->o_nsamp, &ctx->ray_count, &ctx->ray_offset, &ctx->ray_cursor, &ctx->hits, &ctx->block_sums,
+                      &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
+    for (DevBuf *b : bufs) b->release();
+    PinBuf *pins[] = {&ctx->h_pos4, &ctx->h_tet_nodes, &ctx->h_tet_label, &ctx->h_face_nodes, &ctx->h_face_tets, &ctx->h_face_isb, &ctx->h_node_off,
+                      &ctx->h_node_inc, &ctx->h_out};
+    for (PinBuf *b : pins) b->release();
+    if (ctx->d_vol) cudaFree(ctx->d_vol);
+    if (ctx->d_sum_table) cudaFree(ctx->d_sum_table);
+    if (ctx->d_tet_bary) cudaFree(ctx->d_tet_bary);
+    for (int i = 0; i < DSCGPU_T_COUNT; i++) {
+        if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]);
+        if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return DSCGPU_OK;
+}
+
+const char *dscgpu_last_error(const dscgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dscgpu_set_stream(dscgpu_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return DSCGPU_OK;
+}
+
+int dscgpu_synchronize(dscgpu_ctx *ctx)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSCGPU_OK;
+}
+
+void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx) { return ctx ? ctx->d_vol : nullptr; }
+double *dscgpu_sum_table_ptr_dev(dscgpu_ctx *ctx) { return ctx ? ctx->d_sum_table : nullptr; }
+
+int dscgpu_build_sum_table(dscgpu_ctx *ctx)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    size_t n = (size_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2];
+    if (!ctx->d_sum_table) CK(cudaMalloc(&ctx->d_sum_table, n * sizeof(double)));
+    size_t XY = (size_t)ctx->dims[0] * ctx->dims[1];
+    unsigned grid = (unsigned)((XY + 127) / 128);
+    TimerScope ts(ctx, DSCGPU_T_SUMTABLE);
+    switch (ctx->dtype) {
+    case DSCGPU_U8: sum_table_kernel<unsigned char><<<grid, 128, 0, ctx->stream>>>((const unsigned char *)ctx->d_vol, ctx->d_sum_table, ctx->dims[0], ctx->dims[1], ctx->dims[2]); break;
+    case DSCGPU_U16: sum_table_kernel<unsigned short><<<grid, 128, 0, ctx->stream>>>((const unsigned short *)ctx->d_vol, ctx->d_sum_table, ctx->dims[0], ctx->dims[1], ctx->dims[2]); break;
+    case DSCGPU_F32: sum_table_kernel<float><<<grid, 128, 0, ctx->stream>>>((const float *)ctx->d_vol, ctx->d_sum_table, ctx->dims[0], ctx->dims[1], ctx->dims[2]); break;
+    default: sum_table_kernel<double><<<grid, 128, 0, ctx->stream>>>((const double *)ctx->d_vol, ctx->d_sum_table, ctx->dims[0], ctx->dims[1], ctx->dims[2]); break;
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->has_sum_table = true;
+    return DSCGPU_OK;
+}
+
+int dscgpu_get_sum_table(dscgpu_ctx *ctx, double *table_host)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    if (!ctx->has_sum_table) { ctx->err = "sum table not built"; return DSCGPU_ERR_NO_SUMTABLE; }
+    size_t n = (size_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2];
+    CK(cudaMemcpyAsync(table_host, ctx->d_sum_table, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSCGPU_OK;
+}
+
+int dscgpu_snapshot_staging_get(dscgpu_ctx *ctx, uint32_t n_nodes, uint32_t n_tets, uint32_t n_faces, dscgpu_snapshot_staging *out)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(out, "null staging struct");
+    // the previous upload may still be reading the pinned arrays
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->h_pos4.ensure((size_t)n_nodes * 4 * sizeof(double)));
+    CK(ctx->h_tet_nodes.ensure((size_t)n_tets * 4 * sizeof(uint32_t)));
+    CK(ctx->h_tet_label.ensure((size_t)n_tets * sizeof(int32_t)));
+    CK(ctx->h_face_nodes.ensure((size_t)n_faces * 3 * sizeof(uint32_t)));
+    CK(ctx->h_face_tets.ensure((size_t)n_faces * 2 * sizeof(uint32_t)));
+    CK(ctx->h_face_isb.ensure((size_t)n_faces));
+    CK(ctx->h_node_off.ensure(((size_t)n_nodes + 1) * sizeof(uint32_t)));
+    CK(ctx->h_node_inc.ensure((size_t)n_faces * 3 * sizeof(uint32_t)));
+    ctx->st_nodes = n_nodes; ctx->st_tets = n_tets; ctx->st_faces = n_faces;
+    ctx->staging_valid = true;
+    out->pos4 = ctx->h_pos4.as<double>();
+    out->tet_nodes = ctx->h_tet_nodes.as<uint32_t>();
+    out->tet_label = ctx->h_tet_label.as<int32_t>();
+    out->face_nodes = ctx->h_face_nodes.as<uint32_t>();
+    out->face_tets = ctx->h_face_tets.as<uint32_t>();
+    out->face_is_boundary = ctx->h_face_isb.as<uint8_t>();
+    return DSCGPU_OK;
+}
+
+int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(ctx->staging_valid, "dscgpu_snapshot_staging_get was not called");
+    const uint32_t nn = ctx->st_nodes, nt = ctx->st_tets, nf = ctx->st_faces;
+    ARG(nf < (1u << 30), "too many interface faces");
+    // validate indices once on the host: a bad key must not become a wild device read
+    const uint32_t *tn = ctx->h_tet_nodes.as<uint32_t>();
+    for (size_t i = 0; i < 4 * (size_t)nt; i++) ARG(tn[i] < nn, "tet_nodes holds a node key >= n_nodes_buffer");
+    const uint32_t *fn = ctx->h_face_nodes.as<uint32_t>();
+    for (size_t i = 0; i < 3 * (size_t)nf; i++) ARG(fn[i] < nn, "face_nodes holds a node key >= n_nodes_buffer");
+    const uint32_t *ft = ctx->h_face_tets.as<uint32_t>();
+    for (size_t i = 0; i < 2 * (size_t)nf; i++) ARG(ft[i] < nt || ft[i] == DSCGPU_NO_TET, "face_tets holds a tet index >= n_tets");
+    build_node_csr(nn, nf, fn, ctx->h_node_off.as<uint32_t>(), ctx->h_node_inc.as<uint32_t>());
+
+    CK(ctx->pos4.ensure((size_t)nn * 32));
+    CK(ctx->tet_nodes.ensure((size_t)nt * 16));
+    CK(ctx->tet_label.ensure((size_t)nt * 4));
+    CK(ctx->face_nodes.ensure((size_t)nf * 12));
+    CK(ctx->face_tets.ensure((size_t)nf * 8));
+    CK(ctx->face_isb.ensure((size_t)nf));
+    CK(ctx->node_off.ensure(((size_t)nn + 1) * 4));
+    CK(ctx->node_inc.ensure((size_t)nf * 12));
+    {
+        TimerScope ts(ctx, DSCGPU_T_H2D);
+        cudaStream_t s = ctx->stream;
+        if (nn) CK(cudaMemcpyAsync(ctx->pos4.p, ctx->h_pos4.p, (size_t)nn * 32, cudaMemcpyHostToDevice, s));
+        if (nt) CK(cudaMemcpyAsync(ctx->tet_nodes.p, ctx->h_tet_nodes.p, (size_t)nt * 16, cudaMemcpyHostToDevice, s));
+        if (nt) CK(cudaMemcpyAsync(ctx->tet_label.p, ctx->h_tet_label.p, (size_t)nt * 4, cudaMemcpyHostToDevice, s));
+        if (nf) CK(cudaMemcpyAsync(ctx->face_nodes.p, ctx->h_face_nodes.p, (size_t)nf * 12, cudaMemcpyHostToDevice, s));
+        if (nf) CK(cudaMemcpyAsync(ctx->face_tets.p, ctx->h_face_tets.p, (size_t)nf * 8, cudaMemcpyHostToDevice, s));
+        if (nf) CK(cudaMemcpyAsync(ctx->face_isb.p, ctx->h_face_isb.p, (size_t)nf, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->node_off.p, ctx->h_node_off.p, ((size_t)nn + 1) * 4, cudaMemcpyHostToDevice, s));
+        if (nf) CK(cudaMemcpyAsync(ctx->node_inc.p, ctx->h_node_inc.p, (size_t)nf * 12, cudaMemcpyHostToDevice, s));
+    }
+    ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
+    ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
+    ctx->has_snapshot = true;
+
+    // choose lanes per tet from a sample of tet volumes (heuristic only; never affects results)
+    {
+        const double *p4 = ctx->h_pos4.as<double>();
+        double acc = 0;
+        int cnt = 0;
+        uint32_t step = nt / 1024 + 1;
+        for (uint32_t t = 0; t < nt; t += step) {
+            const uint32_t *q = tn + 4 * (size_t)t;
+            V3 a{p4[4 * (size_t)q[0]], p4[4 * (size_t)q[0] + 1], p4[4 * (size_t)q[0] + 2]};
+            V3 b{p4[4 * (size_t)q[1]], p4[4 * (size_t)q[1] + 1], p4[4 * (size_t)q[1] + 2]};
+            V3 c{p4[4 * (size_t)q[2]], p4[4 * (size_t)q[2] + 1], p4[4 * (size_t)q[2] + 2]};
+            V3 d{p4[4 * (size_t)q[3]], p4[4 * (size_t)q[3] + 1], p4[4 * (size_t)q[3] + 2]};
+            int L = tet_level(tet_volume(a, b, c, d));
+            acc += (L + 1) * (L + 1) * (L + 1);
+            cnt++;
+        }
+        ctx->auto_lanes = (cnt && acc / cnt >= 200.0) ? 32 : 8;
+    }
+    return DSCGPU_OK;
+}
+
+int dscgpu_set_snapshot(dscgpu_ctx *ctx, const dscgpu_snapshot *s)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(s, "null snapshot");
+    ARG(s->n_nodes_buffer == 0 || s->pos, "pos is null");
+    ARG(s->n_tets == 0 || (s->tet_nodes && s->tet_label), "tet arrays are null");
+    ARG(s->n_faces == 0 || (s->face_nodes && s->face_tets && s->face_is_boundary), "face arrays are null");
+    dscgpu_snapshot_staging st;
+    int r = dscgpu_snapshot_staging_get(ctx, s->n_nodes_buffer, s->n_tets, s->n_faces, &st);
+    if (r) return r;
+    for (size_t i = 0; i < s->n_nodes_buffer; i++) {
+        st.pos4[4 * i] = s->pos[3 * i]; st.pos4[4 * i + 1] = s->pos[3 * i + 1]; st.pos4[4 * i + 2] = s->pos[3 * i + 2]; st.pos4[4 * i + 3] = 0.0;
+    }
+    if (s->n_tets) {
+        memcpy(st.tet_nodes, s->tet_nodes, (size_t)s->n_tets * 16);
+        memcpy(st.tet_label, s->tet_label, (size_t)s->n_tets * 4);
+    }
+    if (s->n_faces) {
+        memcpy(st.face_nodes, s->face_nodes, (size_t)s->n_faces * 12);
+        memcpy(st.face_tets, s->face_tets, (size_t)s->n_faces * 8);
+        memcpy(st.face_is_boundary, s->face_is_boundary, (size_t)s->n_faces);
+    }
+    return dscgpu_commit_snapshot(ctx);
+}
+
+int dscgpu_set_partition(dscgpu_ctx *ctx, uint32_t tb, uint32_t te, uint32_t fb, uint32_t fe, uint32_t nb, uint32_t ne)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    if (!ctx->has_snapshot) { ctx->err = "no snapshot"; return DSCGPU_ERR_NO_SNAPSHOT; }
+    ARG(tb <= te && te <= ctx->n_tets && fb <= fe && fe <= ctx->n_faces && nb <= ne && ne <= ctx->n_nodes, "partition out of range");
+    ctx->tet_b = tb; ctx->tet_e = te; ctx->face_b = fb; ctx->face_e = fe; ctx->node_b = nb; ctx->node_e = ne;
+    return DSCGPU_OK;
+}
+
+#define NEED_SNAPSHOT()                                              \
+    do {                                                             \
+        if (!ctx) return DSCGPU_ERR_ARG;                             \
+        if (!ctx->has_snapshot) {                                    \
+            ctx->err = "dscgpu_set_snapshot has not been called";    \
+            return DSCGPU_ERR_NO_SNAPSHOT;                           \
+        }                                                            \
+    } while (0)
+
+int dscgpu_tet_integrate(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, double *tet_total, double *tet_vol,
+                         double *tet_mean, double *tet_energy, double *tet_variation, dscgpu_phase_stats *stats)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE, "nb_phase out of range");
+    ARG(nc >= 0 && nc <= DSCGPU_MAX_PHASE && (nc == 0 || c), "nc out of range or c null");
+    const size_t nt = ctx->n_tets;
+    double *d_total = nullptr, *d_vol = nullptr, *d_mean = nullptr, *d_en = nullptr, *d_var = nullptr;
+    if (tet_total) { CK(ctx->o_total.ensure(nt * 8)); d_total = ctx->o_total.as<double>(); }
+    if (tet_vol) { CK(ctx->o_vol.ensure(nt * 8)); d_vol = ctx->o_vol.as<double>(); }
+    if (tet_mean) { CK(ctx->o_mean.ensure(nt * 8)); d_mean = ctx->o_mean.as<double>(); }
+    if (tet_energy && nc) { CK(ctx->o_energy.ensure(nt * nc * 8)); d_en = ctx->o_energy.as<double>(); }
+    if (tet_variation && nc) { CK(ctx->o_variation.ensure(nt * nc * 8)); d_var = ctx->o_variation.as<double>(); }
+    // tets outside the partition keep -1
+    if (d_total && !(ctx->tet_b == 0 && ctx->tet_e == ctx->n_tets)) {
+        // (partitioned per-tet outputs are only used by tests; fill with a recognisable pattern)
+        CK(cudaMemsetAsync(d_total, 0xFF, nt * 8, ctx->stream));
+    }
+    int r = run_tet_pass(ctx, nb_phase, include_bound, nc, c, d_total, d_vol, d_mean, d_en, d_var, ctx->sums.as<double>(), ctx->mean.as<double>());
+    if (r) return r;
+    {
+        TimerScope ts(ctx, DSCGPU_T_D2H);
+        cudaStream_t s = ctx->stream;
+        if (d_total) CK(cudaMemcpyAsync(tet_total, d_total, nt * 8, cudaMemcpyDeviceToHost, s));
+        if (d_vol) CK(cudaMemcpyAsync(tet_vol, d_vol, nt * 8, cudaMemcpyDeviceToHost, s));
+        if (d_mean) CK(cudaMemcpyAsync(tet_mean, d_mean, nt * 8, cudaMemcpyDeviceToHost, s));
+        if (d_en) CK(cudaMemcpyAsync(tet_energy, d_en, nt * nc * 8, cudaMemcpyDeviceToHost, s));
+        if (d_var) CK(cudaMemcpyAsync(tet_variation, d_var, nt * nc * 8, cudaMemcpyDeviceToHost, s));
+    }
+    double h_sums[3 * kMaxPhase], h_mean[kMaxPhase];
+    CK(cudaMemcpyAsync(h_sums, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_mean, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (stats) fill_stats(stats, h_sums, h_mean, nb_phase);
+    return DSCGPU_OK;
+}
+
+int dscgpu_tet_sample_hash(dscgpu_ctx *ctx, uint64_t *tet_hash, int32_t *tet_nsamp)
+{
+    NEED_SNAPSHOT();
+    ARG(tet_hash && tet_nsamp, "null output");
+    const size_t nt = ctx->n_tets;
+    if (nt == 0) return DSCGPU_OK;
+    CK(ctx->o_hash.ensure(nt * 8));
+    CK(ctx->o_nsamp.ensure(nt * 4));
+    tet_sample_hash_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(mesh_view(ctx), ctx->d_tet_bary, ctx->o_hash.as<unsigned long long>(),
+                                                                              ctx->o_nsamp.as<int>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(tet_hash, ctx->o_hash.p, nt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(tet_nsamp, ctx->o_nsamp.p, nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSCGPU_OK;
+}
+
+int dscgpu_points_in_tets(dscgpu_ctx *ctx, uint32_t n, const uint32_t *tet_idx, const double *pts, uint8_t *inside)
+{
+    NEED_SNAPSHOT();
+    if (n == 0) return DSCGPU_OK;
+    ARG(tet_idx && pts && inside, "null argument");
+    for (uint32_t i = 0; i < n; i++) ARG(tet_idx[i] < ctx->n_tets, "tet index out of range");
+    size_t bytes = (size_t)n * (4 + 24 + 1) + 64;
+    CK(ctx->pit.ensure(bytes));
+    double *d_pts = ctx->pit.as<double>();
+    unsigned *d_idx = reinterpret_cast<unsigned *>(d_pts + 3 * (size_t)n);
+    unsigned char *d_in = reinterpret_cast<unsigned char *>(d_idx + n);
+    CK(cudaMemcpyAsync(d_pts, pts, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_idx, tet_idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    points_in_tets_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(mesh_view(ctx), n, d_idx, d_pts, d_in);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(inside, d_in, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSCGPU_OK;
+}
+
+int dscgpu_zray_means(dscgpu_ctx *ctx, int nb_phase, dscgpu_phase_stats *stats)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE, "nb_phase out of range");
+    if (!ctx->has_sum_table) { ctx->err = "dscgpu_build_sum_table has not been called"; return DSCGPU_ERR_NO_SUMTABLE; }
+    int r = run_zray(ctx, nb_phase, 0, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>());
+    if (r) return r;
+    double h_sums[3 * kMaxPhase], h_mean[kMaxPhase];
+    CK(cudaMemcpyAsync(h_sums, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_mean, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    r = check_overflow(ctx);
+    if (r) return r;
+    if (stats) fill_stats(stats, h_sums, h_mean, nb_phase);
+    return DSCGPU_OK;
+}
+
+int dscgpu_vertex_bound(dscgpu_ctx *ctx, uint8_t *vertex_bound)
+{
+    NEED_SNAPSHOT();
+    CK(ctx->vbound.ensure((size_t)ctx->n_nodes + 1));
+    CK(cudaMemsetAsync(ctx->vbound.p, 0, (size_t)ctx->n_nodes + 1, ctx->stream));
+    if (ctx->n_faces) {
+        vertex_bound_kernel<<<(ctx->n_faces + 127) / 128, 128, 0, ctx->stream>>>(mesh_view(ctx), ctx->vbound.as<unsigned char>());
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (vertex_bound) {
+        CK(cudaMemcpyAsync(vertex_bound, ctx->vbound.p, ctx->n_nodes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return DSCGPU_OK;
+}
+
+int dscgpu_zray_energy(dscgpu_ctx *ctx, int nb_phase, const double *mean, double alpha, const uint8_t *vertex_bound, double *energy_data,
+                       double *energy_area)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && mean, "bad arguments");
+    int r = run_zray(ctx, nb_phase, 1, mean, ctx->sums.as<double>(), nullptr);
+    if (r) return r;
+    double h_sums[3 * kMaxPhase];
+    CK(cudaMemcpyAsync(h_sums, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    r = check_overflow(ctx);
+    if (r) return r;
+    double d = 0;
+    for (int k = 0; k < nb_phase; k++) d += h_sums[k]; // phases are accumulated one after another (:2449-2479)
+    if (energy_data) *energy_data = d;
+    // area term
+    if (vertex_bound) {
+        CK(ctx->vbound.ensure((size_t)ctx->n_nodes + 1));
+        CK(cudaMemcpyAsync(ctx->vbound.p, vertex_bound, ctx->n_nodes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        r = dscgpu_vertex_bound(ctx, nullptr);
+        if (r) return r;
+    }
+    double area = 0;
+    if (ctx->n_faces) {
+        unsigned grid = (ctx->n_faces + 255) / 256;
+        CK(ctx->ray_psum.ensure(((size_t)grid + 1) * sizeof(double)));
+        area_term_kernel<<<grid, 256, 0, ctx->stream>>>(mesh_view(ctx), ctx->vbound.as<unsigned char>(), alpha, ctx->ray_psum.as<double>());
+        sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(ctx->ray_psum.as<double>(), (int)grid, ctx->ray_psum.as<double>() + grid);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&area, ctx->ray_psum.as<double>() + grid, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (energy_area) *energy_area = area;
+    return DSCGPU_OK;
+}
+
+int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mode, double *forces)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && mean && forces, "bad arguments");
+    ARG(mode == DSCGPU_FORCE_GATHER || mode == DSCGPU_FORCE_ATOMIC, "unknown force mode");
+    size_t bytes = sizeof(double) * 3 * (size_t)ctx->n_nodes;
+    CK(ctx->forces.ensure(bytes + 8));
+    CK(cudaMemcpyAsync(ctx->mean.p, mean, nb_phase * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int r = run_forces(ctx, nb_phase, ctx->mean.as<double>(), mode, ctx->forces.as<double>());
+    if (r) return r;
+    {
+        TimerScope ts(ctx, DSCGPU_T_D2H);
+        if (bytes) CK(cudaMemcpyAsync(forces, ctx->forces.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSCGPU_OK;
+}
+
+int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb_phase, int mean_mode, int force_mode, dscgpu_phase_stats *stats,
+                            double *forces)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE, "nb_phase out of range");
+    int r;
+    if (snap) {
+        r = dscgpu_set_snapshot(ctx, snap);
+        if (r) return r;
+    } else if (ctx->staging_valid) {
+        r = dscgpu_commit_snapshot(ctx);
+        if (r) return r;
+    }
+    NEED_SNAPSHOT();
+    size_t fbytes = sizeof(double) * 3 * (size_t)ctx->n_nodes;
+    CK(ctx->forces.ensure(fbytes + 8));
+    CK(ctx->h_out.ensure(fbytes + 4 * kMaxPhase * sizeof(double)));
+    if (mean_mode == DSCGPU_MEAN_ZRAY) {
+        if (!ctx->has_sum_table) { ctx->err = "dscgpu_build_sum_table has not been called"; return DSCGPU_ERR_NO_SUMTABLE; }
+        r = run_zray(ctx, nb_phase, 0, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>());
+    } else {
+        r = run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>());
+    }
+    if (r) return r;
+    r = run_forces(ctx, nb_phase, ctx->mean.as<double>(), force_mode, ctx->forces.as<double>());
+    if (r) return r;
+    double *h = ctx->h_out.as<double>();
+    {
+        TimerScope ts(ctx, DSCGPU_T_D2H);
+        CK(cudaMemcpyAsync(h, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h + 3 * kMaxPhase, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (forces && fbytes) CK(cudaMemcpyAsync(h + 4 * kMaxPhase, ctx->forces.p, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (mean_mode == DSCGPU_MEAN_ZRAY) {
+        r = check_overflow(ctx);
+        if (r) return r;
+    } else {
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (stats) fill_stats(stats, h, h + 3 * kMaxPhase, nb_phase);
+    if (forces && fbytes) memcpy(forces, h + 4 * kMaxPhase, fbytes);
+    return DSCGPU_OK;
+}
+
+int dscgpu_tet_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_sums, "bad arguments");
+    return run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_sums, nullptr);
+}
+
+int dscgpu_zray_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_sums, "bad arguments");
+    if (!ctx->has_sum_table) { ctx->err = "dscgpu_build_sum_table has not been called"; return DSCGPU_ERR_NO_SUMTABLE; }
+    int r = run_zray(ctx, nb_phase, 0, nullptr, d_sums, nullptr);
+    if (r) return r;
+    return check_overflow(ctx);
+}
+
+int dscgpu_means_from_sums_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_sums, double *d_mean)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_sums && d_mean, "bad arguments");
+    means_from_sums_kernel<<<1, 32, 0, ctx->stream>>>(d_sums, nb_phase, d_mean);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+int dscgpu_face_forces_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, double *d_forces)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_mean && d_forces, "bad arguments");
+    return run_forces(ctx, nb_phase, d_mean, mode, d_forces);
+}
+
+int dscgpu_enable_timers(dscgpu_ctx *ctx, int on)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ctx->timers_on = on != 0;
+    return DSCGPU_OK;
+}
+
+int dscgpu_get_timer(dscgpu_ctx *ctx, int which, float *ms)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(which >= 0 && which < DSCGPU_T_COUNT && ms, "bad timer");
+    *ms = 0;
+    if (!ctx->ev_used[which]) return DSCGPU_OK;
+    CK(cudaEventSynchronize(ctx->ev[which][1]));
+    CK(cudaEventElapsedTime(ms, ctx->ev[which][0], ctx->ev[which][1]));
+    return DSCGPU_OK;
+}
+
+uint64_t dscgpu_launch_count(const dscgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(lanes == 0 || lanes == 8 || lanes == 32, "lanes per tet must be 0, 8 or 32");
+    ctx->lanes_per_tet = lanes;
+    return DSCGPU_OK;
+}
+
+static uint64_t read_counter(dscgpu_ctx *ctx, int i)
+{
+    unsigned long long v = 0;
+    if (!ctx || !ctx->counters.p) return 0;
+    cudaMemcpyAsync(&v, ctr(ctx, i), sizeof(v), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return v;
+}
+uint64_t dscgpu_last_sample_count(dscgpu_ctx *ctx) { return read_counter(ctx, 0); }
+uint64_t dscgpu_last_gauss_count(dscgpu_ctx *ctx) { return read_counter(ctx, 1); }
+
+int dscgpu_host_sort_hits(int n, int32_t *z, uint8_t *b_in)
+{
+    if (n < 0 || (n > 0 && (!z || !b_in))) return DSCGPU_ERR_ARG;
+    std::vector<int> v(n);
+    for (int i = 0; i < n; i++) v[i] = (int)((unsigned)z[i] << 1) | (b_in[i] ? 1 : 0);
+    if (n > 0) std_sort_hits(v.data(), n);
+    for (int i = 0; i < n; i++) { z[i] = v[i] >> 1; b_in[i] = (uint8_t)(v[i] & 1); }
+    return DSCGPU_OK;
+}
+
+} // extern "C"

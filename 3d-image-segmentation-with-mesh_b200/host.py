@@ -1,0 +1,368 @@
+"""ctypes host side of the C ABI (include/dscgpu.h), mirroring the reference's call surface.
+
+The reference reaches this path through direct member calls on one ``segment_function`` object
+that owns an ``image3d`` (DEMO/segment_function.h:87-218, DEMO/image3d.h:29-86).  The two
+classes below keep those names, argument meanings and result fields so the parity tests read
+like calls into the reference:
+
+    img = Image3D(volume)                   # image3d::load / _voxels / build_sum_table
+    seg = SegmentFunction(img, nb_phase=3)  # segment_function with NB_PHASE, m_alpha
+    seg.set_snapshot(snap)                  # the flattened is_mesh/DSC state (see dscgpu_snapshot)
+    seg.update_average_intensity()          # -> _mean_intensities, _total_intensities, _phase_volume
+    seg.compute_external_force()            # -> _forces   [n_nodes_buffer, 3]
+    seg.compute_energy()                    # -> (data term, alpha * area term)
+
+Everything computes on the GPU through libdscgpu.so; a missing library or device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MAX_PHASE = 8
+NO_TET = 0xFFFFFFFF
+FORCE_GATHER, FORCE_ATOMIC = 0, 1
+MEAN_TET, MEAN_ZRAY = 0, 1
+DTYPE_CODE = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}
+TIMERS = {"tet": 0, "phase_final": 1, "force": 2, "zray": 3, "sumtable": 4, "h2d": 5, "d2h": 6}
+
+
+class DscGpuError(RuntimeError):
+    pass
+
+
+class _Snapshot(C.Structure):
+    _fields_ = [("n_nodes_buffer", C.c_uint32), ("pos", C.c_void_p), ("n_tets", C.c_uint32), ("tet_nodes", C.c_void_p),
+                ("tet_label", C.c_void_p), ("n_faces", C.c_uint32), ("face_nodes", C.c_void_p), ("face_tets", C.c_void_p),
+                ("face_is_boundary", C.c_void_p)]
+
+
+class _Staging(C.Structure):
+    _fields_ = [("pos4", C.c_void_p), ("tet_nodes", C.c_void_p), ("tet_label", C.c_void_p), ("face_nodes", C.c_void_p),
+                ("face_tets", C.c_void_p), ("face_is_boundary", C.c_void_p)]
+
+
+class _PhaseStats(C.Structure):
+    _fields_ = [("total", C.c_double * MAX_PHASE), ("sumsq", C.c_double * MAX_PHASE), ("volume", C.c_double * MAX_PHASE),
+                ("mean", C.c_double * MAX_PHASE)]
+
+
+def library_path():
+    return os.path.join(_HERE, "libdscgpu.so")
+
+
+def load_library():
+    """Loads libdscgpu.so, building it with nvcc first if it is missing or stale.  Never falls back."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    from . import build as _build
+    path = library_path()
+    try:
+        path = _build.build()
+    except Exception as e:  # no nvcc on this machine: use a prebuilt library if it is there
+        if not os.path.exists(path):
+            raise DscGpuError("libdscgpu.so is missing and cannot be built (%s); there is no CPU fallback" % e)
+    lib = C.CDLL(path)
+    lib.dscgpu_last_error.restype = C.c_char_p
+    lib.dscgpu_launch_count.restype = C.c_uint64
+    lib.dscgpu_last_sample_count.restype = C.c_uint64
+    lib.dscgpu_last_gauss_count.restype = C.c_uint64
+    lib.dscgpu_volume_ptr_dev.restype = C.c_void_p
+    lib.dscgpu_sum_table_ptr_dev.restype = C.c_void_p
+    for name in ("dscgpu_ctx_destroy", "dscgpu_last_error", "dscgpu_set_stream", "dscgpu_synchronize", "dscgpu_build_sum_table",
+                 "dscgpu_commit_snapshot", "dscgpu_launch_count", "dscgpu_last_sample_count", "dscgpu_last_gauss_count",
+                 "dscgpu_volume_ptr_dev", "dscgpu_sum_table_ptr_dev"):
+        getattr(lib, name).argtypes = [C.c_void_p] + ([C.c_void_p] if name == "dscgpu_set_stream" else [])
+    _LIB = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def host_sort_hits(z, b_in):
+    """Host instance of the device-side restatement of libstdc++ std::sort used by the z-ray kernel."""
+    z = np.ascontiguousarray(z, np.int32).copy()
+    b = np.ascontiguousarray(b_in, np.uint8).copy()
+    r = load_library().dscgpu_host_sort_hits(C.c_int(len(z)), _ptr(z), _ptr(b))
+    if r != 0:
+        raise DscGpuError("dscgpu_host_sort_hits failed")
+    return z, b
+
+
+class Image3D:
+    """Device-resident voxel volume: the GPU counterpart of ``image3d`` (DEMO/image3d.h:29-86).
+
+    ``volume`` is indexed [z, y, x] (x fastest, DEMO/image3d.h:66-68) with dtype uint8, uint16,
+    float32 or float64; see include/dscgpu.h for the decode rule.
+    """
+
+    def __init__(self, volume, device=0):
+        volume = np.ascontiguousarray(volume)
+        if volume.ndim != 3 or volume.dtype not in DTYPE_CODE:
+            raise ValueError("volume must be a 3-D array of uint8/uint16/float32/float64")
+        self.lib = load_library()
+        self.shape = volume.shape
+        self.dtype = volume.dtype
+        self._dim = (volume.shape[2], volume.shape[1], volume.shape[0])
+        self.device = device
+        self._ctx = C.c_void_p()
+        dims = (C.c_int * 3)(*self._dim)
+        r = self.lib.dscgpu_ctx_create(C.byref(self._ctx), C.c_int(device), dims, C.c_int(DTYPE_CODE[volume.dtype]), _ptr(volume))
+        if r != 0:
+            msg = self.lib.dscgpu_last_error(self._ctx).decode() if self._ctx else "context allocation failed"
+            if self._ctx:
+                self.lib.dscgpu_ctx_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+            raise DscGpuError("dscgpu_ctx_create: " + msg)
+        self._has_table = False
+
+    def _check(self, r, what):
+        if r != 0:
+            raise DscGpuError("%s failed (%d): %s" % (what, r, self.lib.dscgpu_last_error(self._ctx).decode()))
+
+    def dimension(self):
+        return self._dim
+
+    def build_sum_table(self):
+        """image3d::build_sum_table (DEMO/image3d.cpp:143-177)."""
+        self._check(self.lib.dscgpu_build_sum_table(self._ctx), "dscgpu_build_sum_table")
+        self._has_table = True
+
+    def sum_table(self):
+        out = np.empty(self.shape, np.float64)
+        self._check(self.lib.dscgpu_get_sum_table(self._ctx, _ptr(out)), "dscgpu_get_sum_table")
+        return out
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.dscgpu_set_stream(self._ctx, C.c_void_p(cuda_stream_ptr)), "dscgpu_set_stream")
+
+    def synchronize(self):
+        self._check(self.lib.dscgpu_synchronize(self._ctx), "dscgpu_synchronize")
+
+    def volume_ptr_dev(self):
+        return self.lib.dscgpu_volume_ptr_dev(self._ctx)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.dscgpu_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SegmentFunction:
+    """GPU counterpart of the image-energy members of ``segment_function`` (DEMO/segment_function.h:87-218)."""
+
+    def __init__(self, img, nb_phase, alpha=0.1):
+        if not 1 <= nb_phase <= MAX_PHASE:
+            raise ValueError("NB_PHASE must be in 1..%d" % MAX_PHASE)
+        self._img = img
+        self.lib = img.lib
+        self.NB_PHASE = nb_phase
+        self.m_alpha = alpha
+        self._mean_intensities = None
+        self._total_intensities = None
+        self._phase_volume = None
+        self._phase_sumsq = None
+        self._forces = None
+        self.n_nodes_buffer = self.n_tets = self.n_faces = 0
+        self._keep = None
+
+    # -- snapshot ---------------------------------------------------------------------------
+    def set_snapshot(self, snap):
+        """Uploads the flattened mesh (keys: pos, tet_nodes, tet_label, face_nodes, face_tets, face_is_boundary)."""
+        pos = np.ascontiguousarray(snap["pos"], np.float64).reshape(-1, 3)
+        tn = np.ascontiguousarray(snap["tet_nodes"], np.uint32).reshape(-1, 4)
+        tl = np.ascontiguousarray(snap["tet_label"], np.int32).reshape(-1)
+        fn = np.ascontiguousarray(snap["face_nodes"], np.uint32).reshape(-1, 3)
+        ft = np.ascontiguousarray(snap["face_tets"], np.uint32).reshape(-1, 2)
+        fb = np.ascontiguousarray(snap["face_is_boundary"], np.uint8).reshape(-1)
+        if len(tl) != len(tn) or len(ft) != len(fn) or len(fb) != len(fn):
+            raise ValueError("inconsistent snapshot array lengths")
+        s = _Snapshot(len(pos), pos.ctypes.data, len(tn), tn.ctypes.data, tl.ctypes.data, len(fn), fn.ctypes.data, ft.ctypes.data,
+                      fb.ctypes.data)
+        self._img._check(self.lib.dscgpu_set_snapshot(self._img._ctx, C.byref(s)), "dscgpu_set_snapshot")
+        self.n_nodes_buffer, self.n_tets, self.n_faces = len(pos), len(tn), len(fn)
+
+    def staging(self, n_nodes_buffer, n_tets, n_faces):
+        """Pinned host arrays to flatten a mesh into without an extra copy; follow with commit_snapshot()."""
+        st = _Staging()
+        self._img._check(self.lib.dscgpu_snapshot_staging_get(self._img._ctx, C.c_uint32(n_nodes_buffer), C.c_uint32(n_tets),
+                                                              C.c_uint32(n_faces), C.byref(st)), "dscgpu_snapshot_staging_get")
+
+        def view(ptr, ctype, n, shape):
+            if n == 0:
+                return np.zeros(shape, dtype=ctype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).reshape(shape)
+
+        self.n_nodes_buffer, self.n_tets, self.n_faces = n_nodes_buffer, n_tets, n_faces
+        return {"pos4": view(st.pos4, C.c_double, 4 * n_nodes_buffer, (n_nodes_buffer, 4)),
+                "tet_nodes": view(st.tet_nodes, C.c_uint32, 4 * n_tets, (n_tets, 4)),
+                "tet_label": view(st.tet_label, C.c_int32, n_tets, (n_tets,)),
+                "face_nodes": view(st.face_nodes, C.c_uint32, 3 * n_faces, (n_faces, 3)),
+                "face_tets": view(st.face_tets, C.c_uint32, 2 * n_faces, (n_faces, 2)),
+                "face_is_boundary": view(st.face_is_boundary, C.c_uint8, n_faces, (n_faces,))}
+
+    def commit_snapshot(self):
+        self._img._check(self.lib.dscgpu_commit_snapshot(self._img._ctx), "dscgpu_commit_snapshot")
+
+    def set_partition(self, tet_range, face_range, node_range):
+        self._img._check(self.lib.dscgpu_set_partition(self._img._ctx, *[C.c_uint32(int(v)) for v in (*tet_range, *face_range, *node_range)]),
+                         "dscgpu_set_partition")
+
+    # -- per-tet integration ------------------------------------------------------------------
+    def _stats_out(self, st):
+        P = self.NB_PHASE
+        self._total_intensities = np.array(st.total[:P])
+        self._phase_sumsq = np.array(st.sumsq[:P])
+        self._phase_volume = np.array(st.volume[:P])
+        self._mean_intensities = np.array(st.mean[:P])
+
+    def tet_integrate(self, c=None, per_tet=True, include_bound=False, update_means=True):
+        """image3d::get_tetra_intensity (+ get_energy/get_variation for every c[k]) over all tets and the
+        per-label reduction.  Returns a dict of per-tet arrays and the per-phase statistics."""
+        nt = self.n_tets
+        nc = 0 if c is None else len(c)
+        cc = None if c is None else np.ascontiguousarray(c, np.float64)
+        out = {}
+        if per_tet:
+            out["total"] = np.empty(nt)
+            out["vol"] = np.empty(nt)
+            out["mean"] = np.empty(nt)
+            if nc:
+                out["energy"] = np.empty((nt, nc))
+                out["variation"] = np.empty((nt, nc))
+        st = _PhaseStats()
+        r = self.lib.dscgpu_tet_integrate(self._img._ctx, C.c_int(self.NB_PHASE), C.c_int(1 if include_bound else 0), C.c_int(nc), _ptr(cc),
+                                          _ptr(out.get("total")), _ptr(out.get("vol")), _ptr(out.get("mean")), _ptr(out.get("energy")),
+                                          _ptr(out.get("variation")), C.byref(st))
+        self._img._check(r, "dscgpu_tet_integrate")
+        P = self.NB_PHASE
+        out["phase_total"] = np.array(st.total[:P])
+        out["phase_sumsq"] = np.array(st.sumsq[:P])
+        out["phase_volume"] = np.array(st.volume[:P])
+        out["phase_mean"] = np.array(st.mean[:P])
+        if update_means:
+            self._stats_out(st)
+        return out
+
+    def tet_sample_hash(self):
+        h = np.zeros(self.n_tets, np.uint64)
+        n = np.zeros(self.n_tets, np.int32)
+        self._img._check(self.lib.dscgpu_tet_sample_hash(self._img._ctx, _ptr(h), _ptr(n)), "dscgpu_tet_sample_hash")
+        return h, n
+
+    def points_in_tets(self, tet_idx, pts):
+        ti = np.ascontiguousarray(tet_idx, np.uint32)
+        p = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        out = np.zeros(len(ti), np.uint8)
+        self._img._check(self.lib.dscgpu_points_in_tets(self._img._ctx, C.c_uint32(len(ti)), _ptr(ti), _ptr(p), _ptr(out)), "dscgpu_points_in_tets")
+        return out
+
+    # -- the reference's members --------------------------------------------------------------
+    def update_average_intensity(self):
+        """segment_function::update_average_intensity (DEMO/segment_function.cpp:1600-1764), z-ray estimator."""
+        if not self._img._has_table:
+            self._img.build_sum_table()
+        st = _PhaseStats()
+        self._img._check(self.lib.dscgpu_zray_means(self._img._ctx, C.c_int(self.NB_PHASE), C.byref(st)), "dscgpu_zray_means")
+        self._stats_out(st)
+        return self._mean_intensities
+
+    def compute_external_force(self, mode=FORCE_GATHER, mean=None):
+        """segment_function::compute_external_force (DEMO/segment_function.cpp:1425-1473)."""
+        m = np.ascontiguousarray(self._mean_intensities if mean is None else mean, np.float64)
+        if len(m) != self.NB_PHASE:
+            raise ValueError("need NB_PHASE mean intensities")
+        f = np.empty((self.n_nodes_buffer, 3))
+        self._img._check(self.lib.dscgpu_face_forces(self._img._ctx, C.c_int(self.NB_PHASE), _ptr(m), C.c_int(mode), _ptr(f)), "dscgpu_face_forces")
+        self._forces = f
+        return f
+
+    def compute_energy(self, mean=None, vertex_bound=None):
+        """segment_function::compute_energy (DEMO/segment_function.cpp:2331-2492): (data, alpha*area)."""
+        m = np.ascontiguousarray(self._mean_intensities if mean is None else mean, np.float64)
+        vb = None if vertex_bound is None else np.ascontiguousarray(vertex_bound, np.uint8)
+        d = C.c_double(0)
+        a = C.c_double(0)
+        self._img._check(self.lib.dscgpu_zray_energy(self._img._ctx, C.c_int(self.NB_PHASE), _ptr(m), C.c_double(self.m_alpha), _ptr(vb),
+                                                     C.byref(d), C.byref(a)), "dscgpu_zray_energy")
+        return d.value, a.value
+
+    def vertex_bound(self):
+        vb = np.zeros(self.n_nodes_buffer, np.uint8)
+        self._img._check(self.lib.dscgpu_vertex_bound(self._img._ctx, _ptr(vb)), "dscgpu_vertex_bound")
+        return vb
+
+    def image_force_eval(self, snap=None, mean_mode=MEAN_TET, force_mode=FORCE_GATHER, want_forces=True):
+        """One full evaluation through host buffers: upload + means + forces + download."""
+        sp = None
+        if snap is not None:
+            pos = np.ascontiguousarray(snap["pos"], np.float64).reshape(-1, 3)
+            tn = np.ascontiguousarray(snap["tet_nodes"], np.uint32).reshape(-1, 4)
+            tl = np.ascontiguousarray(snap["tet_label"], np.int32).reshape(-1)
+            fn = np.ascontiguousarray(snap["face_nodes"], np.uint32).reshape(-1, 3)
+            ft = np.ascontiguousarray(snap["face_tets"], np.uint32).reshape(-1, 2)
+            fb = np.ascontiguousarray(snap["face_is_boundary"], np.uint8).reshape(-1)
+            self._keep = (pos, tn, tl, fn, ft, fb)
+            sp = _Snapshot(len(pos), pos.ctypes.data, len(tn), tn.ctypes.data, tl.ctypes.data, len(fn), fn.ctypes.data, ft.ctypes.data,
+                           fb.ctypes.data)
+            self.n_nodes_buffer, self.n_tets, self.n_faces = len(pos), len(tn), len(fn)
+        if mean_mode == MEAN_ZRAY and not self._img._has_table:
+            self._img.build_sum_table()
+        f = np.empty((self.n_nodes_buffer, 3)) if want_forces else None
+        st = _PhaseStats()
+        r = self.lib.dscgpu_image_force_eval(self._img._ctx, C.byref(sp) if sp is not None else None, C.c_int(self.NB_PHASE), C.c_int(mean_mode),
+                                             C.c_int(force_mode), C.byref(st), _ptr(f))
+        self._img._check(r, "dscgpu_image_force_eval")
+        self._stats_out(st)
+        self._forces = f
+        return self._mean_intensities, f
+
+    # -- device-resident pieces (multi-GPU composition) ---------------------------------------
+    def tet_phase_sums_dev(self, d_sums_ptr):
+        self._img._check(self.lib.dscgpu_tet_phase_sums_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_sums_ptr)), "dscgpu_tet_phase_sums_dev")
+
+    def zray_phase_sums_dev(self, d_sums_ptr):
+        if not self._img._has_table:
+            self._img.build_sum_table()
+        self._img._check(self.lib.dscgpu_zray_phase_sums_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_sums_ptr)), "dscgpu_zray_phase_sums_dev")
+
+    def means_from_sums_dev(self, d_sums_ptr, d_mean_ptr):
+        self._img._check(self.lib.dscgpu_means_from_sums_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_sums_ptr), C.c_void_p(d_mean_ptr)),
+                         "dscgpu_means_from_sums_dev")
+
+    def face_forces_dev(self, d_mean_ptr, d_forces_ptr, mode=FORCE_GATHER):
+        self._img._check(self.lib.dscgpu_face_forces_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_mean_ptr), C.c_int(mode),
+                                                         C.c_void_p(d_forces_ptr)), "dscgpu_face_forces_dev")
+
+    # -- instrumentation --------------------------------------------------------------------------
+    def enable_timers(self, on=True):
+        self._img._check(self.lib.dscgpu_enable_timers(self._img._ctx, C.c_int(1 if on else 0)), "dscgpu_enable_timers")
+
+    def timer_ms(self, name):
+        ms = C.c_float(0)
+        self._img._check(self.lib.dscgpu_get_timer(self._img._ctx, C.c_int(TIMERS[name]), C.byref(ms)), "dscgpu_get_timer")
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.dscgpu_launch_count(self._img._ctx))
+
+    def last_sample_count(self):
+        return int(self.lib.dscgpu_last_sample_count(self._img._ctx))
+
+    def last_gauss_count(self):
+        return int(self.lib.dscgpu_last_gauss_count(self._img._ctx))
+
+    def set_lanes_per_tet(self, lanes):
+        self._img._check(self.lib.dscgpu_set_lanes_per_tet(self._img._ctx, C.c_int(lanes)), "dscgpu_set_lanes_per_tet")

@@ -1,0 +1,215 @@
+/* dscgpu.h -- C ABI of the B200-native DSC image-energy path.
+ *
+ * Drop-in boundary for the per-iteration image-energy evaluation of the reference
+ * (tuannt8/3D-image-segmentation-with-mesh).  The reference has no FFI: the path is reached by
+ * direct C++ member calls (DEMO/segment_function.cpp:2242-2247, 2258-2260, 2276-2277).  Each
+ * entry point below names the reference member(s) it replaces; the C++ adapter that binds them
+ * to a live is_mesh/DSC complex is include/dscgpu_adapter.hpp, the ctypes binding is
+ * 3d-image-segmentation-with-mesh_b200/host.py, and INTEGRATION.md shows the patch a maintainer
+ * of the reference would apply.
+ *
+ * Conventions: plain C, opaque context, caller-owned HOST buffers unless the name ends in _dev,
+ * int status return (0 = ok, <0 = error; dscgpu_last_error() gives the text), no exceptions
+ * cross the boundary, no internal locking (the reference calls this path from one thread only,
+ * DEMO/user_interface.cpp:388-396).  There is no CPU fallback: every call needs a CUDA device.
+ *
+ * Volume layout: x fastest, index = z*X*Y + y*X + x (DEMO/image3d.h:66-68).  Voxel decode:
+ *   U8  -> v/255.0 (DEMO/image3d.cpp:127),  U16 -> v/65535.0,  F32 -> widened,  F64 as is;
+ * reads outside the volume give 0 (BOUND_INTENSITY, DEMO/image3d.h:24, image3d.cpp:480-491).
+ *
+ * Labels: tet label 0 = BOUND_LABEL (DEMO/image3d.h:23); phases are labels 1..nb_phase and
+ * every per-phase output is indexed by label-1 (DEMO/segment_function.cpp:1445-1446).
+ */
+#ifndef DSCGPU_H
+#define DSCGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSCGPU_MAX_PHASE 8
+#define DSCGPU_NO_TET 0xFFFFFFFFu
+
+enum dscgpu_dtype { DSCGPU_U8 = 0, DSCGPU_U16 = 1, DSCGPU_F32 = 2, DSCGPU_F64 = 3 };
+
+enum dscgpu_status {
+    DSCGPU_OK = 0,
+    DSCGPU_ERR_CUDA = -1,        /* a CUDA runtime call failed */
+    DSCGPU_ERR_ARG = -2,         /* bad argument */
+    DSCGPU_ERR_NO_SNAPSHOT = -3, /* mesh snapshot not set */
+    DSCGPU_ERR_NO_SUMTABLE = -4, /* dscgpu_build_sum_table not called */
+    DSCGPU_ERR_RAY_OVERFLOW = -5 /* a z-ray has more hits than DSCGPU_MAX_RAY_HITS */
+};
+
+#define DSCGPU_MAX_RAY_HITS 96
+
+typedef struct dscgpu_ctx dscgpu_ctx;
+
+/* Flattened SoA snapshot of the mesh, taken through the reference's read-only getters in
+ * ascending key order (kernel iteration order, is_mesh/kernel.h:178-196):
+ *   pos        3*n_nodes_buffer doubles, indexed by raw node key (get_no_nodes_buffer(),
+ *              is_mesh/is_mesh.h:150; free cells may hold anything)
+ *   tet_nodes  4*n_tets node keys in get_nodes(t) order (is_mesh/is_mesh.h:673-679)
+ *   tet_label  n_tets labels (get_label, is_mesh/is_mesh.h:250-253); label-0 tets must be present
+ *   face_nodes 3*n_faces node keys in get_nodes(f) order (is_mesh/is_mesh.h:665-671), for every
+ *              face with is_interface() (is_mesh/attributes.h:195-252), ascending face key
+ *   face_tets  2*n_faces INDICES into the tet arrays, in get_tets(f) order; DSCGPU_NO_TET when
+ *              the face has a single co-boundary tet
+ *   face_is_boundary  n_faces bytes, FaceAttributes::is_boundary()
+ */
+typedef struct dscgpu_snapshot {
+    uint32_t n_nodes_buffer;
+    const double *pos;
+    uint32_t n_tets;
+    const uint32_t *tet_nodes;
+    const int32_t *tet_label;
+    uint32_t n_faces;
+    const uint32_t *face_nodes;
+    const uint32_t *face_tets;
+    const uint8_t *face_is_boundary;
+} dscgpu_snapshot;
+
+/* Per-phase results.  total/volume/mean are what the reference keeps in _total_intensities,
+ * _phase_volume, _mean_intensities (DEMO/segment_function.h:129-131). */
+typedef struct dscgpu_phase_stats {
+    double total[DSCGPU_MAX_PHASE];
+    double sumsq[DSCGPU_MAX_PHASE]; /* sum I^2 * v/n^3 per phase (tet path only) */
+    double volume[DSCGPU_MAX_PHASE];
+    double mean[DSCGPU_MAX_PHASE];
+} dscgpu_phase_stats;
+
+/* -- lifetime ---------------------------------------------------------------------------- */
+
+/* Replaces image3d::load's upload part (DEMO/image3d.cpp:95-133): copies the voxel volume
+ * (dims = {X,Y,Z}) to HBM once and installs the sample tables (set_size(),
+ * DEMO/tet_dis_coord.cpp:3129-3144).  voxels_host may be NULL to allocate only (fill later
+ * with dscgpu_volume_ptr_dev). */
+int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype, const void *voxels_host);
+int dscgpu_ctx_destroy(dscgpu_ctx *ctx);
+const char *dscgpu_last_error(const dscgpu_ctx *ctx);
+/* Launch everything on this cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+int dscgpu_set_stream(dscgpu_ctx *ctx, void *cuda_stream);
+int dscgpu_synchronize(dscgpu_ctx *ctx);
+/* Device pointer of the voxel volume (dtype as created) and of the z prefix-sum table (FP64). */
+void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx);
+double *dscgpu_sum_table_ptr_dev(dscgpu_ctx *ctx);
+
+/* image3d::build_sum_table (DEMO/image3d.cpp:143-177): S[x,y,z] = S[x,y,z-1] + V[x,y,z], bit-exact. */
+int dscgpu_build_sum_table(dscgpu_ctx *ctx);
+/* Copies the table back (X*Y*Z doubles) -- tests only. */
+int dscgpu_get_sum_table(dscgpu_ctx *ctx, double *table_host);
+
+/* Uploads a snapshot (replaces the per-call mesh walks of DEMO/segment_function.cpp:1435-1447,
+ * 1626-1634 and image3d.cpp's std::vector<vec3> arguments).  Host pointers are not retained. */
+int dscgpu_set_snapshot(dscgpu_ctx *ctx, const dscgpu_snapshot *snap);
+/* Zero-copy variant: the library hands out PINNED host arrays sized for the given counts; the host
+ * flattens the mesh straight into them (pos4 holds 4 doubles per node: x, y, z, unused) and
+ * dscgpu_commit_snapshot uploads them without an intermediate copy. */
+typedef struct dscgpu_snapshot_staging {
+    double *pos4;
+    uint32_t *tet_nodes;
+    int32_t *tet_label;
+    uint32_t *face_nodes;
+    uint32_t *face_tets;
+    uint8_t *face_is_boundary;
+} dscgpu_snapshot_staging;
+int dscgpu_snapshot_staging_get(dscgpu_ctx *ctx, uint32_t n_nodes_buffer, uint32_t n_tets, uint32_t n_faces, dscgpu_snapshot_staging *out);
+int dscgpu_commit_snapshot(dscgpu_ctx *ctx);
+/* Multi-GPU: restrict the work of this context to tets [tet_begin,tet_end), interface faces
+ * [face_begin,face_end) and (for the gather force kernel) nodes [node_begin,node_end); the
+ * snapshot itself stays whole.  Reset by dscgpu_set_snapshot. */
+int dscgpu_set_partition(dscgpu_ctx *ctx, uint32_t tet_begin, uint32_t tet_end, uint32_t face_begin, uint32_t face_end,
+                         uint32_t node_begin, uint32_t node_end);
+
+/* -- per-tet integration ------------------------------------------ */
+
+/* image3d::get_tetra_intensity / get_energy / get_variation batched over all tets
+ * (DEMO/image3d.cpp:351-426; callers DEMO/segment_function.cpp:165-186, 618-643, 850-889).
+ * Any output pointer may be NULL.  Tets with label 0 are skipped (outputs -1) unless
+ * include_bound != 0.
+ *   tet_total[t] = *total_inten, tet_vol[t] = *volume, tet_mean[t] = return value
+ *   nc, c[nc]    : candidate intensities; tet_energy[t*nc+k] = get_energy(t, c[k]),
+ *                  tet_variation[t*nc+k] = get_variation(t, c[k])
+ *   stats        : per-label reduction of tet_total / sum I^2 / tet_vol and mean = total/volume
+ */
+int dscgpu_tet_integrate(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, double *tet_total, double *tet_vol,
+                         double *tet_mean, double *tet_energy, double *tet_variation, dscgpu_phase_stats *stats);
+/* Order-sensitive FNV-1a hash of the truncated voxel coordinates of every sample point of every
+ * tet, and the sample count: the bit-exactness witness for the sample -> voxel classification. */
+int dscgpu_tet_sample_hash(dscgpu_ctx *ctx, uint64_t *tet_hash, int32_t *tet_nsamp);
+/* is_point_inside (DEMO/segment_function.cpp:2576-2580): 4-point barycentric voxel-in-tet predicate. */
+int dscgpu_points_in_tets(dscgpu_ctx *ctx, uint32_t n, const uint32_t *tet_idx, const double *pts, uint8_t *inside);
+
+/* -- z-ray means and energy ---------------------------------------------- */
+
+/* segment_function::update_average_intensity (DEMO/segment_function.cpp:1600-1764): fills
+ * total (= _total_intensities), volume (= _phase_volume, integer-valued voxel counts, bit-exact)
+ * and mean.  Needs dscgpu_build_sum_table. */
+int dscgpu_zray_means(dscgpu_ctx *ctx, int nb_phase, dscgpu_phase_stats *stats);
+/* segment_function::compute_energy (DEMO/segment_function.cpp:2331-2492): the two numbers of its
+ * "=== Energy; area = data - area" line.  vertex_bound (n_nodes_buffer bytes) may be NULL, in
+ * which case m_vertex_bound is derived from the snapshot as update_vertex_boundary does (:2158-2171). */
+int dscgpu_zray_energy(dscgpu_ctx *ctx, int nb_phase, const double *mean, double alpha, const uint8_t *vertex_bound,
+                       double *energy_data, double *energy_area);
+/* m_vertex_bound as derived from the snapshot (n_nodes_buffer bytes). */
+int dscgpu_vertex_bound(dscgpu_ctx *ctx, uint8_t *vertex_bound);
+
+/* -- external force ----------------------------------------------------------- */
+
+enum dscgpu_force_mode {
+    DSCGPU_FORCE_GATHER = 0, /* one thread per node walks its incident interface faces in ascending
+                                order: same addition order as the reference, no atomics, bit-reproducible */
+    DSCGPU_FORCE_ATOMIC = 1  /* one thread per face, FP64 red.global.add scatter */
+};
+/* segment_function::compute_external_force (DEMO/segment_function.cpp:1425-1473): forces is
+ * 3*n_nodes_buffer doubles indexed by raw node key (= _forces). */
+int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mode, double *forces);
+
+/* -- fused evaluation and device-resident variants ------------------------------------------- */
+
+enum dscgpu_mean_mode { DSCGPU_MEAN_TET = 0, DSCGPU_MEAN_ZRAY = 1 };
+/* One full image-force evaluation = snapshot upload + per-tet integration + per-phase means
+ * (tet-sampled or z-ray) + external forces + result download: what segment() needs from
+ * update_average_intensity + compute_external_force (DEMO/segment_function.cpp:2244-2247). */
+int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb_phase, int mean_mode, int force_mode,
+                            dscgpu_phase_stats *stats, double *forces);
+
+/* Device-resident pieces for multi-GPU composition (NCCL all-reduce happens between them, on
+ * the caller's stream set with dscgpu_set_stream):
+ *   d_sums   3*nb_phase doubles: total[nb], sumsq[nb], volume[nb] of this context's partition
+ *   d_mean   nb_phase doubles
+ *   d_forces 3*n_nodes_buffer doubles, overwritten */
+int dscgpu_tet_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums);
+int dscgpu_zray_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums);
+int dscgpu_means_from_sums_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_sums, double *d_mean);
+int dscgpu_face_forces_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, double *d_forces);
+
+/* -- instrumentation -------------------------------------------------------------------------- */
+
+enum dscgpu_timer {
+    DSCGPU_T_TET = 0, DSCGPU_T_PHASE_FINAL = 1, DSCGPU_T_FORCE = 2, DSCGPU_T_ZRAY = 3, DSCGPU_T_SUMTABLE = 4,
+    DSCGPU_T_H2D = 5, DSCGPU_T_D2H = 6, DSCGPU_T_COUNT = 7
+};
+/* When enabled, kernels are bracketed by CUDA events on the launching stream; dscgpu_get_timer
+ * synchronizes and returns the duration of the last launch of that class in ms. */
+int dscgpu_enable_timers(dscgpu_ctx *ctx, int on);
+int dscgpu_get_timer(dscgpu_ctx *ctx, int which, float *ms);
+/* Number of kernels this library has launched on the context since creation. */
+uint64_t dscgpu_launch_count(const dscgpu_ctx *ctx);
+/* Tunables: lanes per tet of the integration kernel (1, 8 or 32; 0 = choose from the mesh). */
+int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes);
+/* Algorithmic sample count of the last tet pass (sum of n^3 over processed tets). */
+uint64_t dscgpu_last_sample_count(dscgpu_ctx *ctx);
+uint64_t dscgpu_last_gauss_count(dscgpu_ctx *ctx);
+
+/* libstdc++ std::sort restated for the z-ray hits (introsort, threshold 16, median-of-3), run on
+ * the HOST instance of the same __host__ __device__ code the kernel uses -- lets CPU-only tests
+ * fuzz it against the real std::sort. */
+int dscgpu_host_sort_hits(int n, int32_t *z, uint8_t *b_in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSCGPU_H */

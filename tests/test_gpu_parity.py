@@ -1,0 +1,248 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: against the reference-produced
+golden fixtures and, on seeded synthetic inputs, against the flat oracle.
+
+Bars (BASELINE.json north_star): bit-exact for sample->voxel classification (hash), sample levels,
+voxel counts (_phase_volume), the sum table, vertex_bound, the voxel-in-tet predicate and -- because
+the gather kernel keeps the reference's addition order -- the forces; 1e-6 relative (FP64 parallel
+sums) for totals, means and energies; 1e-6 for the atomic force kernel.
+"""
+import numpy as np
+import pytest
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6  # FP64 accumulation tolerance stated by north_star
+
+
+def _seg(pkg, g):
+    img = pkg.Image3D(g["volume"])
+    seg = pkg.SegmentFunction(img, g["meta"]["nb_phase"], g["meta"]["alpha"])
+    seg.set_snapshot(golden_io.snapshot_of(g))
+    return img, seg
+
+
+@pytest.fixture(scope="module", params=golden_io.CASES)
+def case(request, pkg):
+    g = golden_io.load(request.param)
+    img, seg = _seg(pkg, g)
+    yield g, img, seg
+    img.close()
+
+
+def test_sample_classification_bit_exact(case):
+    g, img, seg = case
+    h, n = seg.tet_sample_hash()
+    assert np.array_equal(n, g["tet_nsamp"])
+    assert np.array_equal(h, g["tet_hash"])
+
+
+@pytest.mark.parametrize("lanes", [8, 32])
+def test_tet_integrate_matches_reference(case, lanes):
+    g, img, seg = case
+    seg.set_lanes_per_tet(lanes)
+    lab = g["tet_label"] != 0
+    o = seg.tet_integrate(c=g["mean"])
+    assert np.array_equal(o["vol"][lab], g["tet_vol"][lab])  # volumes are computed in the reference's order: bit-exact
+    np.testing.assert_allclose(o["total"][lab], g["tet_total"][lab], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(o["mean"][lab], g["tet_mean"][lab], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(o["variation"][lab], g["tet_variation"][lab], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(o["energy"][lab], g["tet_energy"][lab], rtol=RTOL, atol=1e-12)
+    assert np.all(o["total"][~lab] == -1.0)
+    # per-label reduction vs the sequential reduction of the reference's per-tet values
+    P = g["meta"]["nb_phase"]
+    tot = np.array([g["tet_total"][g["tet_label"] == k + 1].sum() for k in range(P)])
+    vol = np.array([g["tet_vol"][g["tet_label"] == k + 1].sum() for k in range(P)])
+    np.testing.assert_allclose(o["phase_total"], tot, rtol=RTOL)
+    np.testing.assert_allclose(o["phase_volume"], vol, rtol=RTOL)
+    np.testing.assert_allclose(o["phase_mean"], tot / vol, rtol=RTOL)
+    seg.set_lanes_per_tet(0)
+
+
+def test_tet_integrate_fast_path_equals_full_path(case):
+    g, img, seg = case
+    a = seg.tet_integrate(c=None)
+    b = seg.tet_integrate(c=g["mean"])
+    np.testing.assert_allclose(a["total"], b["total"], rtol=1e-12)
+    np.testing.assert_allclose(a["phase_sumsq"], b["phase_sumsq"], rtol=1e-9)
+
+
+def test_sum_table_bit_exact(case, flat):
+    g, img, seg = case
+    img.build_sum_table()
+    assert np.array_equal(img.sum_table(), flat.build_sum_table(g["volume"]))
+
+
+def test_update_average_intensity(case):
+    g, img, seg = case
+    mean = seg.update_average_intensity()
+    assert np.array_equal(seg._phase_volume, g["phase_volume"])  # voxel counts: bit-exact
+    np.testing.assert_allclose(seg._total_intensities, g["total"], rtol=RTOL)
+    np.testing.assert_allclose(mean, g["mean"], rtol=RTOL)
+
+
+def test_compute_external_force_gather_bit_exact(case, pkg):
+    g, img, seg = case
+    F = seg.compute_external_force(mode=pkg.FORCE_GATHER, mean=g["mean"])
+    assert np.array_equal(F, g["forces"])
+
+
+def test_compute_external_force_atomic(case, pkg):
+    g, img, seg = case
+    F = seg.compute_external_force(mode=pkg.FORCE_ATOMIC, mean=g["mean"])
+    scale = np.abs(g["forces"]).max()
+    np.testing.assert_allclose(F, g["forces"], rtol=RTOL, atol=RTOL * scale)
+
+
+def test_compute_energy(case):
+    g, img, seg = case
+    vb = seg.vertex_bound()
+    assert np.array_equal(vb, g["vertex_bound"])
+    d, a = seg.compute_energy(mean=g["mean"])
+    np.testing.assert_allclose(d, g["meta"]["energy_data"], rtol=RTOL)
+    np.testing.assert_allclose(a, g["meta"]["energy_area"], rtol=RTOL)
+    d2, a2 = seg.compute_energy(mean=g["mean"], vertex_bound=g["vertex_bound"])
+    assert d2 == d and a2 == a
+
+
+def test_points_in_tets_bit_exact(case):
+    g, img, seg = case
+    assert np.array_equal(seg.points_in_tets(g["pit_tet"], g["pit_pts"]), g["pit_inside"])
+
+
+def test_full_evaluation_through_host_buffers(case, pkg):
+    g, img, seg = case
+    s = golden_io.snapshot_of(g)
+    mean, F = seg.image_force_eval(s, mean_mode=pkg.MEAN_ZRAY, force_mode=pkg.FORCE_GATHER)
+    np.testing.assert_allclose(mean, g["mean"], rtol=RTOL)
+    assert np.array_equal(seg._phase_volume, g["phase_volume"])
+    scale = np.abs(g["forces"]).max()
+    np.testing.assert_allclose(F, g["forces"], rtol=1e-5, atol=1e-6 * scale)  # means differ in the last bits -> forces too
+    mean_t, F_t = seg.image_force_eval(s, mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_ATOMIC)
+    P = g["meta"]["nb_phase"]
+    tot = np.array([g["tet_total"][g["tet_label"] == k + 1].sum() for k in range(P)])
+    vol = np.array([g["tet_vol"][g["tet_label"] == k + 1].sum() for k in range(P)])
+    np.testing.assert_allclose(mean_t, tot / vol, rtol=RTOL)
+
+
+def test_partition_sums_compose(case, pkg):
+    """Multi-GPU contract: partial results of disjoint partitions add up to the whole (emulated on one GPU)."""
+    g, img, seg = case
+    whole = seg.tet_integrate(per_tet=False)
+    F_whole = seg.compute_external_force(mean=g["mean"])
+    nt, nf, nn = seg.n_tets, seg.n_faces, seg.n_nodes_buffer
+    tot = np.zeros_like(whole["phase_total"])
+    vol = np.zeros_like(tot)
+    F = np.zeros_like(F_whole)
+    Fa = np.zeros_like(F_whole)
+    R = 3
+    for r in range(R):
+        rng = lambda n: (n * r // R, n * (r + 1) // R)
+        seg.set_partition(rng(nt), rng(nf), rng(nn))
+        o = seg.tet_integrate(per_tet=False)
+        tot += o["phase_total"]
+        vol += o["phase_volume"]
+        F += seg.compute_external_force(mode=pkg.FORCE_GATHER, mean=g["mean"])
+        Fa += seg.compute_external_force(mode=pkg.FORCE_ATOMIC, mean=g["mean"])
+    seg.set_partition((0, nt), (0, nf), (0, nn))
+    np.testing.assert_allclose(tot, whole["phase_total"], rtol=1e-12)
+    np.testing.assert_allclose(vol, whole["phase_volume"], rtol=1e-12)
+    assert np.array_equal(F, F_whole)  # gather partitions by node: disjoint slices, x + 0 = x
+    np.testing.assert_allclose(Fa, F_whole, rtol=RTOL, atol=RTOL * np.abs(F_whole).max())
+
+
+# ---- seeded synthetic inputs against the flat oracle ------------------------------------------------
+
+@pytest.mark.parametrize("dtype,n,edge,jitter", [(np.float32, 40, 3.1, 0.3), (np.uint16, 36, 5.0, 0.25), (np.uint8, 33, 7.7, 0.3),
+                                                  (np.float64, 24, 12.0, 0.2), (np.float32, 30, 40.0, 0.1)])
+def test_synthetic_vs_oracle(pkg, flat, dtype, n, edge, jitter):
+    syn = pkg.synthetic
+    vol = syn.shells_phantom(n, sigma=0.04, seed=7, dtype=np.float32)
+    if dtype == np.float64:
+        vol = vol.astype(np.float64) * 1.000001
+    elif dtype != np.float32:
+        vol = syn.shells_phantom(n, sigma=0.04, seed=7, dtype=dtype)
+    P = 3
+    snap = syn.build_case(vol, edge, P, (0.3, 0.7),
+                          lambda pos, tets, base: flat.tet_integrate(vol, tets, pos, want_hash=False)["mean"], jitter=jitter, seed=11)
+    img = pkg.Image3D(vol)
+    seg = pkg.SegmentFunction(img, P, 0.01)
+    seg.set_snapshot(snap)
+    ref = flat.tet_integrate(vol, snap["tet_nodes"], snap["pos"], c=[0.2, 0.5, 0.8])
+    h, ns = seg.tet_sample_hash()
+    assert np.array_equal(h, ref["hash"]) and np.array_equal(ns, ref["nsamp"])
+    o = seg.tet_integrate(c=[0.2, 0.5, 0.8], include_bound=True)
+    assert np.array_equal(o["vol"], ref["vol"])
+    np.testing.assert_allclose(o["total"], ref["total"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(o["variation"], ref["ad"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(o["energy"], ref["sq"], rtol=RTOL, atol=1e-12)
+    if len(snap["face_nodes"]):
+        z = flat.zray(vol, snap, P, mode=0)
+        mean = seg.update_average_intensity()
+        assert np.array_equal(seg._phase_volume, z["count"])
+        ok = z["count"] > 0
+        np.testing.assert_allclose(seg._total_intensities[ok], z["total"][ok], rtol=RTOL)
+        m = np.where(ok, z["mean"], 0.5)
+        F_ref = flat.face_forces(vol, snap, P, m)
+        assert np.array_equal(seg.compute_external_force(mean=m), F_ref)
+        e = flat.zray(vol, snap, P, mode=1, mean=m, alpha=0.01)
+        d, a = seg.compute_energy(mean=m)
+        np.testing.assert_allclose([d, a], [e["energy_data"], e["energy_area"]], rtol=RTOL)
+    img.close()
+
+
+def test_edge_cases(pkg):
+    vol = np.zeros((8, 8, 8), np.float32)
+    img = pkg.Image3D(vol)
+    seg = pkg.SegmentFunction(img, 2)
+    with pytest.raises(pkg.DscGpuError):  # no snapshot yet
+        seg.tet_integrate()
+    empty = {"pos": np.zeros((0, 3)), "tet_nodes": np.zeros((0, 4), np.uint32), "tet_label": np.zeros(0, np.int32),
+             "face_nodes": np.zeros((0, 3), np.uint32), "face_tets": np.zeros((0, 2), np.uint32), "face_is_boundary": np.zeros(0, np.uint8)}
+    seg.set_snapshot(empty)  # empty mesh is legal
+    o = seg.tet_integrate()
+    assert o["total"].size == 0 and np.all(o["phase_total"] == 0)
+    assert seg.compute_external_force(mean=[0.1, 0.9]).shape == (0, 3)
+    bad = dict(empty)
+    bad["pos"] = np.zeros((4, 3))
+    bad["tet_nodes"] = np.array([[0, 1, 2, 9]], np.uint32)  # node key out of range
+    bad["tet_label"] = np.array([1], np.int32)
+    with pytest.raises(pkg.DscGpuError):
+        seg.set_snapshot(bad)
+    # a degenerate (zero volume) tet and a tet fully outside the image must not crash and read zeros
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [-50, -50, -50], [-40, -50, -50], [-50, -40, -50], [-50, -50, -40]], float)
+    snap = dict(empty)
+    snap["pos"] = pos
+    snap["tet_nodes"] = np.array([[0, 1, 2, 3], [4, 5, 6, 7]], np.uint32)
+    snap["tet_label"] = np.array([1, 2], np.int32)
+    seg.set_snapshot(snap)
+    o = seg.tet_integrate()
+    assert o["vol"][0] == 0.0 and o["total"][1] == 0.0 and abs(o["vol"][1] - 1000.0 / 6.0) < 1e-9
+    img.close()
+
+
+def test_ray_overflow_is_reported(pkg):
+    # > DSCGPU_MAX_RAY_HITS stacked interfaces over one column must fail loudly, not silently truncate
+    n_layers = 120
+    vol = np.zeros((n_layers + 4, 4, 4), np.float32)
+    pos = []
+    for k in range(n_layers + 1):
+        z = k * 1.0
+        pos += [[-4.0, -4.0, z], [12.0, -4.0, z], [-4.0, 12.0, z]]
+    pos = np.array(pos, float)
+    tets, labels = [], []
+    for k in range(n_layers):
+        a = 3 * k
+        # a prism split in 3 tets between layer k and k+1
+        for t in ([a, a + 1, a + 2, a + 3], [a + 1, a + 2, a + 3, a + 4], [a + 2, a + 3, a + 4, a + 5]):
+            tets.append(t)
+            labels.append(1 + (k % 2))
+    tets = np.array(tets, np.uint32)
+    labels = np.array(labels, np.int32)
+    fn, ft, fb = pkg.synthetic.interface_faces(tets, labels, len(pos))
+    img = pkg.Image3D(vol)
+    seg = pkg.SegmentFunction(img, 2)
+    seg.set_snapshot({"pos": pos, "tet_nodes": tets, "tet_label": labels, "face_nodes": fn, "face_tets": ft, "face_is_boundary": fb})
+    with pytest.raises(pkg.DscGpuError, match="DSCGPU_MAX_RAY_HITS"):
+        seg.update_average_intensity()
+    img.close()

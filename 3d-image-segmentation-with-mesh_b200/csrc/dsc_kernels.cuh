@@ -747,6 +747,26 @@ __global__ void zray_finalize_kernel(const double *partial_sum, const long long 
     if (mean) mean[k] = s / (double)c;
 }
 
+// Snapshot index validation on the device: out-of-range node keys / tet indices are neutralised (0 / NO_TET) so that no
+// later kernel can read out of bounds, and *flag is raised; the host reports the error at its next synchronisation.
+__global__ void validate_snapshot_kernel(unsigned *tet_nodes, size_t n_tn, unsigned *face_nodes, size_t n_fn, unsigned *face_tets, size_t n_ft,
+                                         unsigned n_nodes, unsigned n_tets, int *flag)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_tn + n_fn + n_ft; i += stride) {
+        if (i < n_tn) {
+            if (tet_nodes[i] >= n_nodes) { tet_nodes[i] = 0; bad = true; }
+        } else if (i < n_tn + n_fn) {
+            if (face_nodes[i - n_tn] >= n_nodes) { face_nodes[i - n_tn] = 0; bad = true; }
+        } else {
+            const unsigned t = face_tets[i - n_tn - n_fn];
+            if (t >= n_tets && t != kNoTet) { face_tets[i - n_tn - n_fn] = kNoTet; bad = true; }
+        }
+    }
+    if (bad) atomicExch(flag, 1);
+}
+
 // m_vertex_bound of update_vertex_boundary (DEMO/segment_function.cpp:2158-2171) from the snapshot
 __global__ void vertex_bound_kernel(MeshView m, unsigned char *vb)
 {

@@ -70,7 +70,8 @@ struct dscgpu_ctx {
     uint32_t n_nodes = 0, n_tets = 0, n_faces = 0;
     DevBuf pos4, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc;
     // pinned staging (host side of the snapshot)
-    PinBuf h_pos4, h_tet_nodes, h_tet_label, h_face_nodes, h_face_tets, h_face_isb, h_node_off, h_node_inc, h_out;
+    PinBuf h_pos4, h_tet_nodes, h_tet_label, h_face_nodes, h_face_tets, h_face_isb, h_node_off, h_node_inc, h_out, h_flag;
+    bool validation_pending = false;
     uint32_t st_nodes = 0, st_tets = 0, st_faces = 0;
     bool staging_valid = false;
 
@@ -110,6 +111,25 @@ struct dscgpu_ctx {
     } while (0)
 
 namespace {
+
+// every synchronising entry point ends here: waits for the stream and raises a deferred snapshot validation error
+int sync_and_check(dscgpu_ctx *ctx)
+{
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaStreamSynchronize failed: ") + cudaGetErrorString(e);
+        return DSCGPU_ERR_CUDA;
+    }
+    if (ctx->validation_pending) {
+        ctx->validation_pending = false;
+        if (*ctx->h_flag.as<int>() != 0) {
+            ctx->has_snapshot = false;
+            ctx->err = "snapshot rejected: tet_nodes/face_nodes hold a node key >= n_nodes_buffer or face_tets a tet index >= n_tets";
+            return DSCGPU_ERR_ARG;
+        }
+    }
+    return DSCGPU_OK;
+}
 
 struct TimerScope {
     dscgpu_ctx *c;
@@ -344,7 +364,7 @@ int check_overflow(dscgpu_ctx *ctx)
 {
     int of = 0;
     CK(cudaMemcpyAsync(&of, ctr(ctx, 2), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    { int rs = sync_and_check(ctx); if (rs) return rs; }
     if (of) {
         ctx->err = "a z-ray collected more than DSCGPU_MAX_RAY_HITS interface hits";
         return DSCGPU_ERR_RAY_OVERFLOW;
@@ -438,7 +458,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
                       &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
     for (DevBuf *b : bufs) b->release();
     PinBuf *pins[] = {&ctx->h_pos4, &ctx->h_tet_nodes, &ctx->h_tet_label, &ctx->h_face_nodes, &ctx->h_face_tets, &ctx->h_face_isb, &ctx->h_node_off,
-                      &ctx->h_node_inc, &ctx->h_out};
+                      &ctx->h_node_inc, &ctx->h_out, &ctx->h_flag};
     for (PinBuf *b : pins) b->release();
     if (ctx->d_vol) cudaFree(ctx->d_vol);
     if (ctx->d_sum_table) cudaFree(ctx->d_sum_table);
@@ -464,8 +484,7 @@ int dscgpu_set_stream(dscgpu_ctx *ctx, void *cuda_stream)
 int dscgpu_synchronize(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    CK(cudaStreamSynchronize(ctx->stream));
-    return DSCGPU_OK;
+    return sync_and_check(ctx);
 }
 
 void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx) { return ctx ? ctx->d_vol : nullptr; }
@@ -532,13 +551,8 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     ARG(ctx->staging_valid, "dscgpu_snapshot_staging_get was not called");
     const uint32_t nn = ctx->st_nodes, nt = ctx->st_tets, nf = ctx->st_faces;
     ARG(nf < (1u << 30), "too many interface faces");
-    // validate indices once on the host: a bad key must not become a wild device read
     const uint32_t *tn = ctx->h_tet_nodes.as<uint32_t>();
-    for (size_t i = 0; i < 4 * (size_t)nt; i++) ARG(tn[i] < nn, "tet_nodes holds a node key >= n_nodes_buffer");
     const uint32_t *fn = ctx->h_face_nodes.as<uint32_t>();
-    for (size_t i = 0; i < 3 * (size_t)nf; i++) ARG(fn[i] < nn, "face_nodes holds a node key >= n_nodes_buffer");
-    const uint32_t *ft = ctx->h_face_tets.as<uint32_t>();
-    for (size_t i = 0; i < 2 * (size_t)nf; i++) ARG(ft[i] < nt || ft[i] == DSCGPU_NO_TET, "face_tets holds a tet index >= n_tets");
     build_node_csr(nn, nf, fn, ctx->h_node_off.as<uint32_t>(), ctx->h_node_inc.as<uint32_t>());
 
     CK(ctx->pos4.ensure((size_t)nn * 32));
@@ -562,6 +576,23 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
         if (nf) CK(cudaMemcpyAsync(ctx->node_inc.p, ctx->h_node_inc.p, (size_t)nf * 12, cudaMemcpyHostToDevice, s));
     }
     ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
+    // index validation runs on the device (a host pass over 8 M ids would dominate the end-to-end step): bad ids are
+    // replaced by 0 / NO_TET so that no kernel can read out of range, and the error is raised at the next synchronisation
+    {
+        CK(ctx->h_flag.ensure(sizeof(int)));
+        CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ctx->stream));
+        size_t n_ids = 4 * (size_t)nt + 3 * (size_t)nf + 2 * (size_t)nf;
+        if (n_ids) {
+            unsigned grid = (unsigned)std::min<size_t>((n_ids + 255) / 256, (size_t)ctx->num_sms * 16);
+            validate_snapshot_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->tet_nodes.as<unsigned>(), 4 * (size_t)nt, ctx->face_nodes.as<unsigned>(),
+                                                                  3 * (size_t)nf, ctx->face_tets.as<unsigned>(), 2 * (size_t)nf, nn, nt,
+                                                                  reinterpret_cast<int *>(ctr(ctx, 4)));
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(ctx->h_flag.p, ctr(ctx, 4), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->validation_pending = true;
+    }
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
 
@@ -573,6 +604,7 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
         uint32_t step = nt / 1024 + 1;
         for (uint32_t t = 0; t < nt; t += step) {
             const uint32_t *q = tn + 4 * (size_t)t;
+            if (q[0] >= nn || q[1] >= nn || q[2] >= nn || q[3] >= nn) continue;
             V3 a{p4[4 * (size_t)q[0]], p4[4 * (size_t)q[0] + 1], p4[4 * (size_t)q[0] + 2]};
             V3 b{p4[4 * (size_t)q[1]], p4[4 * (size_t)q[1] + 1], p4[4 * (size_t)q[1] + 2]};
             V3 c{p4[4 * (size_t)q[2]], p4[4 * (size_t)q[2] + 1], p4[4 * (size_t)q[2] + 2]};
@@ -608,7 +640,9 @@ int dscgpu_set_snapshot(dscgpu_ctx *ctx, const dscgpu_snapshot *s)
         memcpy(st.face_tets, s->face_tets, (size_t)s->n_faces * 8);
         memcpy(st.face_is_boundary, s->face_is_boundary, (size_t)s->n_faces);
     }
-    return dscgpu_commit_snapshot(ctx);
+    r = dscgpu_commit_snapshot(ctx);
+    if (r) return r;
+    return sync_and_check(ctx); // this entry point reports a bad snapshot immediately
 }
 
 int dscgpu_set_partition(dscgpu_ctx *ctx, uint32_t tb, uint32_t te, uint32_t fb, uint32_t fe, uint32_t nb, uint32_t ne)
@@ -661,7 +695,7 @@ int dscgpu_tet_integrate(dscgpu_ctx *ctx, int nb_phase, int include_bound, int n
     double h_sums[3 * kMaxPhase], h_mean[kMaxPhase];
     CK(cudaMemcpyAsync(h_sums, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(h_mean, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    { int rs = sync_and_check(ctx); if (rs) return rs; }
     if (stats) fill_stats(stats, h_sums, h_mean, nb_phase);
     return DSCGPU_OK;
 }
@@ -680,8 +714,7 @@ int dscgpu_tet_sample_hash(dscgpu_ctx *ctx, uint64_t *tet_hash, int32_t *tet_nsa
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(tet_hash, ctx->o_hash.p, nt * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(tet_nsamp, ctx->o_nsamp.p, nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return DSCGPU_OK;
+    return sync_and_check(ctx);
 }
 
 int dscgpu_points_in_tets(dscgpu_ctx *ctx, uint32_t n, const uint32_t *tet_idx, const double *pts, uint8_t *inside)
@@ -701,8 +734,7 @@ int dscgpu_points_in_tets(dscgpu_ctx *ctx, uint32_t n, const uint32_t *tet_idx, 
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(inside, d_in, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return DSCGPU_OK;
+    return sync_and_check(ctx);
 }
 
 int dscgpu_zray_means(dscgpu_ctx *ctx, int nb_phase, dscgpu_phase_stats *stats)
@@ -789,8 +821,7 @@ int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mo
         TimerScope ts(ctx, DSCGPU_T_D2H);
         if (bytes) CK(cudaMemcpyAsync(forces, ctx->forces.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    return DSCGPU_OK;
+    return sync_and_check(ctx);
 }
 
 int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb_phase, int mean_mode, int force_mode, dscgpu_phase_stats *stats,
@@ -830,7 +861,8 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
         r = check_overflow(ctx);
         if (r) return r;
     } else {
-        CK(cudaStreamSynchronize(ctx->stream));
+        r = sync_and_check(ctx);
+        if (r) return r;
     }
     if (stats) fill_stats(stats, h, h + 3 * kMaxPhase, nb_phase);
     if (forces && fbytes) memcpy(forces, h + 4 * kMaxPhase, fbytes);

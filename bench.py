@@ -1,0 +1,447 @@
+#!/usr/bin/env python3
+"""Benchmark of the DSC image-force evaluation (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C4] [--impl reference]
+
+A step = one full image-force evaluation of the workload: per-tet voxel integration + per-phase
+means + interface-face Gauss-quadrature forces.  Metric = (tets + interface faces)
+processed per second, whole job.
+
+  value      device-timed (CUDA events on the launching stream, max over ranks), mesh snapshot and volume
+             already resident in HBM; L2 is flushed between timed steps.
+  e2e        same evaluation through the C ABI with HOST buffers: pinned snapshot -> H2D -> kernels ->
+             D2H of the per-phase statistics and the vertex forces, every step.
+  roofline   dominant kernel (per-tet integration): algorithmic bytes / CUDA-event duration vs the measured
+             HBM copy peak in MEASURED_PEAKS.json.
+  cpu_baseline  the reference's CPU path on this box's host cores, on a bounded sample of the same workload.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref/dsc_ref, the unmodified
+reference sources built by oracle/Makefile; falls back to the flat oracle port when that binary is absent)
+on the same workload family, bounded so that the run ends within minutes.
+Multi-GPU: one process per GPU (torchrun); tets / faces / nodes are partitioned, the volume and the snapshot
+are replicated, and the only collectives are two NCCL all-reduces (per-phase sums, vertex forces).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DSC image-force evals/sec (tets+faces/s)"
+UNIT = "tets+faces/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="C4")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mean-mode", default="tet", choices=["tet", "zray"])
+    ap.add_argument("--force-mode", default="gather", choices=["gather", "atomic"])
+    ap.add_argument("--jitter", type=float, default=0.2)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------
+def build_workload(pkg, cfg_name, seg_factory, jitter):
+    syn = pkg.synthetic
+    cfg = syn.CONFIGS[cfg_name]
+    vol = syn.make_volume(cfg_name)
+    img, seg = seg_factory(vol, cfg["nb_phase"])
+    edge = syn.edge_for_cells(cfg["n"], cfg["cells"])
+
+    def tet_mean(pos, tets, base):
+        seg.set_snapshot({"pos": pos, "tet_nodes": tets, "tet_label": base, "face_nodes": np.zeros((0, 3), np.uint32),
+                          "face_tets": np.zeros((0, 2), np.uint32), "face_is_boundary": np.zeros(0, np.uint8)})
+        return seg.tet_integrate(include_bound=True, update_means=False)["mean"]
+
+    snap = syn.build_case(vol, edge, cfg["nb_phase"], cfg["thresholds"], tet_mean, jitter=jitter, seed=5)
+    return vol, cfg, edge, snap, img, seg
+
+
+def algorithmic_bytes(snap, n_samples, n_gauss, voxel_bytes, per_tet_outputs=False):
+    """per tet 16 B ids + 4 B label + 96 B positions + n^3 voxel reads (+24 B outputs when written);
+    per interface face 60 B ids/labels + 120 B positions + 8 voxel reads per Gauss point + 144 B force read-modify-write."""
+    n_tets = int((snap["tet_label"] != 0).sum())
+    n_bound = len(snap["tet_label"]) - n_tets
+    tet_b = n_tets * (16 + 4 + 96 + (24 if per_tet_outputs else 0)) + n_bound * 4 + n_samples * voxel_bytes
+    face_b = len(snap["face_nodes"]) * (60 + 120 + 144) + n_gauss * 8 * voxel_bytes
+    return tet_b, face_b
+
+
+def flush_l2(torch, buf):
+    buf.add_(1)  # read+write of a buffer larger than the 126 MB L2
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ----------------------------------------------------------------------------------------------------
+def reference_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "dsc_ref")
+    return p if os.path.exists(p) else None
+
+
+def run_reference_sample(pkg, cfg_name, target_seconds, jitter):
+    """Times the reference CPU path on a bounded sample of the workload: the same phantom family and the same mesh
+    edge length, on a sub-volume sized so that one pass takes roughly `target_seconds`.  Returns dict."""
+    syn = pkg.synthetic
+    cfg = syn.CONFIGS[cfg_name]
+    edge = syn.edge_for_cells(cfg["n"], cfg["cells"])
+    binp = reference_binary()
+    # the reference builds an is_mesh complex (std::map based, ~6 us/tet) and samples ~1 us/tet: keep ~150 K tets
+    n_sub = min(cfg["n"], 192 if target_seconds >= 10 else 128)
+    if cfg_name == "C2":
+        vol = syn.sphere_phantom(n_sub, radius=40.0 * n_sub / 128)
+    else:
+        lv = {"C3": ((0.1, 0.5, 0.9), (0.40, 0.24), 0.05), "C4": ((0.1, 0.5, 0.9), (0.40, 0.24), 0.02),
+              "C5": ((0.1, 0.4, 0.65, 0.9), (0.42, 0.30, 0.16), 0.03)}[cfg_name]
+        vol = syn.shells_phantom(n_sub, levels=lv[0], radii=lv[1], sigma=lv[2], seed=1234, dtype=cfg["dtype"])
+    dt = {np.dtype(np.uint8): "u8", np.dtype(np.uint16): "u16", np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}[vol.dtype]
+    sample = "%s phantom cropped to %d^3 %s, same edge length %.3f, jitter %.2f" % (cfg_name, n_sub, dt, edge, jitter)
+    if binp:
+        with tempfile.TemporaryDirectory() as tmp:
+            vp = os.path.join(tmp, "vol.raw")
+            vol.tofile(vp)
+            cmd = [binp, "--mode", "time", "--volume", vp, "--vol-dtype", dt, "--dims", str(n_sub), str(n_sub), str(n_sub), "--edge", repr(edge),
+                   "--nb-phase", str(cfg["nb_phase"]), "--alpha", "0.01", "--labels", "thres", "--thres", ",".join(str(t) for t in cfg["thresholds"]),
+                   "--jitter", str(jitter), "--jitter-seed", "5", "--repeat", "2"]
+            t0 = time.time()
+            out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
+            wall = time.time() - t0
+        r = json.loads(out.strip().splitlines()[-1])
+        units = r["n_tets"] + r["n_if"]
+        t_eval = r["t_tet_pass_s"] + r["t_external_force_s"]  # per-tet integration + per-phase means + face forces
+        return {"value": units / t_eval, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": sample + "; unmodified reference sources (oracle/_ref/dsc_ref), get_tetra_intensity pass + compute_external_force, best of 2",
+                "detail": r, "wall_s": wall, "units": units, "t_eval_s": t_eval}
+    # fallback: flat oracle port, all host threads
+    from oracle import flat
+    thr = flat.num_threads()
+    snap = syn.build_case(vol, edge, cfg["nb_phase"], cfg["thresholds"],
+                          lambda pos, tets, base: flat.tet_integrate(vol, tets, pos, want_hash=False, threads=thr)["mean"], jitter=jitter, seed=5)
+    mask = (snap["tet_label"] != 0).astype(np.uint8)
+    best = 1e30
+    for _ in range(2):
+        t0 = time.time()
+        o = flat.tet_integrate(vol, snap["tet_nodes"], snap["pos"], tet_mask=mask, want_hash=False, threads=thr)
+        tot, volu, mean = flat.phase_reduce(snap["tet_label"], o["total"], o["vol"], cfg["nb_phase"])
+        flat.face_forces(vol, snap, cfg["nb_phase"], mean, threads=thr)
+        best = min(best, time.time() - t0)
+    units = len(snap["tet_nodes"]) + len(snap["face_nodes"])
+    return {"value": units / best, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample + "; flat oracle port (oracle/flat_oracle.cpp), OpenMP",
+            "units": units, "t_eval_s": best}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    vals = []
+    info = None
+    t_all = time.time()
+    for i in range(args.warmup + args.steps):
+        info = run_reference_sample(pkg, args.config, 4.0, args.jitter)
+        if i >= args.warmup:
+            vals.append(info["t_eval_s"])
+        if time.time() - t_all > 240:  # keep the whole run within a few minutes
+            break
+    if not vals:
+        vals = [info["t_eval_s"]]
+    t = float(np.mean(vals))
+    value = info["units"] / t
+    cfg = pkg.synthetic.CONFIGS[args.config]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %d^3 %s phantom, %d phases (bounded sample, see cpu_baseline.sample)" % (
+                args.config, cfg["n"], np.dtype(cfg["dtype"]).name, cfg["nb_phase"])},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    pkg = load_package()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the image-energy kernels have no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def seg_factory(vol, nb_phase):
+        img = pkg.Image3D(vol, device=local_rank)
+        return img, pkg.SegmentFunction(img, nb_phase, 0.01)
+
+    t0 = time.time()
+    vol, cfg, edge, snap, img, seg = build_workload(pkg, args.config, seg_factory, args.jitter)
+    P = cfg["nb_phase"]
+    n_tets, n_faces, n_nodes = len(snap["tet_nodes"]), len(snap["face_nodes"]), len(snap["pos"])
+    units = n_tets + n_faces
+    build_s = time.time() - t0
+    mean_mode = pkg.MEAN_TET if args.mean_mode == "tet" else pkg.MEAN_ZRAY
+    force_mode = pkg.FORCE_GATHER if args.force_mode == "gather" else pkg.FORCE_ATOMIC
+
+    # all launches go to torch's current stream so that torch.cuda.Event brackets them
+    stream = torch.cuda.current_stream(dev)
+    img.set_stream(stream.cuda_stream)
+    if mean_mode == pkg.MEAN_ZRAY:
+        img.build_sum_table()
+    seg.set_snapshot(snap)
+    # weak scaling is not what north_star asks for C4 (fixed 2M-tet mesh split over N GPUs): strong scaling
+    rng = lambda n: (n * rank // world, n * (rank + 1) // world)
+    if world > 1:
+        seg.set_partition(rng(n_tets), rng(n_faces), rng(n_nodes))
+    d_sums = torch.zeros(3 * P, dtype=torch.float64, device=dev)
+    d_mean = torch.zeros(P, dtype=torch.float64, device=dev)
+    d_forces = torch.zeros(3 * n_nodes, dtype=torch.float64, device=dev)
+    l2_buf = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+    seg.enable_timers(True)
+
+    launches_per_step = [0]
+
+    def step_device():
+        n0 = seg.launch_count()
+        if mean_mode == pkg.MEAN_TET:
+            seg.tet_phase_sums_dev(d_sums.data_ptr())
+        else:
+            seg.zray_phase_sums_dev(d_sums.data_ptr())
+        if world > 1:
+            dist.all_reduce(d_sums)
+        seg.means_from_sums_dev(d_sums.data_ptr(), d_mean.data_ptr())
+        seg.face_forces_dev(d_mean.data_ptr(), d_forces.data_ptr(), force_mode)
+        if world > 1:
+            dist.all_reduce(d_forces)
+        launches_per_step[0] = seg.launch_count() - n0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing: K steps, each bracketed by events, L2 flushed in between ----------------
+    for _ in range(max(3, args.warmup)):
+        flush_l2(torch, l2_buf)
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    tet_ms, force_ms = [], []
+    barrier()
+    for i in range(args.steps):
+        flush_l2(torch, l2_buf)
+        ev[i][0].record(stream)
+        step_device()
+        ev[i][1].record(stream)
+        torch.cuda.synchronize(dev)
+        tet_ms.append(seg.timer_ms("tet" if mean_mode == pkg.MEAN_TET else "zray"))
+        force_ms.append(seg.timer_ms("force"))
+    barrier()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    n_samples = seg.last_sample_count()
+    n_gauss = seg.last_gauss_count()
+    total_ms = float(step_ms.sum())
+    t = torch.tensor([total_ms, float(np.sum(tet_ms))], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(n_samples), float(n_gauss)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms_max, tet_ms_max = t.tolist()
+    n_samples_all, n_gauss_all = [int(x) for x in cnt.tolist()]
+    ms_per_step = total_ms_max / args.steps
+    value = units / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------------------------
+    # Every step: the host flattens the mesh into the library's pinned staging arrays (here: a copy from the resident
+    # numpy snapshot, standing in for the is_mesh walk), H2D, kernels, D2H of the statistics and the forces.
+    st = seg.staging(n_nodes, n_tets, n_faces)
+    host_forces = np.empty((n_nodes, 3))
+
+    def fill_staging():
+        st["pos4"][:, :3] = snap["pos"]
+        st["tet_nodes"][...] = snap["tet_nodes"]
+        st["tet_label"][...] = snap["tet_label"]
+        st["face_nodes"][...] = snap["face_nodes"]
+        st["face_tets"][...] = snap["face_tets"]
+        st["face_is_boundary"][...] = snap["face_is_boundary"]
+
+    fill_staging()
+    h2d_bytes = n_nodes * 32 + n_tets * 20 + n_faces * (12 + 8 + 1) + (n_nodes + 1) * 4 + n_faces * 12
+    d2h_bytes = n_nodes * 24 + 4 * P * 8
+
+    def step_e2e():
+        if world == 1:
+            seg.staging(n_nodes, n_tets, n_faces)  # same pinned arrays (already filled); marks the snapshot dirty
+            seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode)
+        else:
+            seg.staging(n_nodes, n_tets, n_faces)
+            seg.commit_snapshot()
+            seg.set_partition(rng(n_tets), rng(n_faces), rng(n_nodes))
+            step_device()
+            host_forces[...] = d_forces.view(-1, 3).cpu().numpy()
+            d_mean.cpu()
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = te.item() / e2e_steps * 1e3
+    e2e_value = units / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    tet_bytes, face_bytes = algorithmic_bytes(snap, n_samples_all, n_gauss_all, vol.dtype.itemsize)
+    tet_bytes_rank = tet_bytes / world
+    kernel_ms = tet_ms_max / args.steps
+    achieved = tet_bytes_rank / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "tet_traffic.json")
+    if os.path.exists(tp) and world == 1:
+        try:
+            traffic = json.load(open(tp)).get(args.config)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "tet_integrate_kernel" if mean_mode == pkg.MEAN_TET else "zray pass", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": tet_bytes_rank, "peak_source": peak_src,
+                "whole_step": {"algorithmic_bytes": tet_bytes + face_bytes, "achieved": (tet_bytes + face_bytes) / world / (ms_per_step * 1e-3) / 1e9}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_baseline = run_reference_sample(pkg, args.config, args.cpu_baseline_seconds, args.jitter)
+            cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # the baseline is a reported extra; never fail the bench for it
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %d^3 %s %d-phase phantom, %d tets (%d labelled), %d interface faces, %d nodes, grid mesh edge %.3f jitter %.2f" % (
+            args.config, cfg["n"], vol.dtype.name, P, n_tets, int((snap["tet_label"] != 0).sum()), n_faces, n_nodes, edge, args.jitter),
+            "mean_mode": args.mean_mode, "force_mode": args.force_mode, "l2": "flushed between timed steps (256 MB write)",
+            "partition": "tets/faces/nodes split in %d contiguous ranges, volume+snapshot replicated" % world,
+            "samples_per_step": n_samples_all, "gauss_points_per_step": n_gauss_all},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches_per_step[0] * args.steps),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "kernel_ms": {"tet_or_zray": float(np.mean(tet_ms)), "force": float(np.mean(force_ms)), "step_min": float(step_ms.min()),
+                      "step_max": float(step_ms.max())},
+        "setup_s": build_s,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -32,6 +32,7 @@ struct VolumeView {
 
 struct MeshView {
     const double4 *pos4;
+    const float4 *pos4f; // float copy of pos4 (FP32 filter path), written by pos_to_float_kernel
     const uint4 *tet_nodes;
     const int *tet_label;
     const unsigned *face_nodes;
@@ -82,11 +83,39 @@ template <typename T> DSC_D double fetch_trilinear(const T *__restrict__ vol, in
     return c0 * (1 - rz) + c1 * rz;
 }
 
+// raw element fetch through a 3-D texture (cudaArray, block-linear layout, point sampling, border mode: reads
+// outside the volume return 0 = BOUND_INTENSITY, exactly like image3d::get_value)
+template <typename T> DSC_D T tex_fetch(cudaTextureObject_t tex, int x, int y, int z)
+{
+    return tex3D<T>(tex, (float)x + 0.5f, (float)y + 0.5f, (float)z + 0.5f);
+}
+
 DSC_D V3 load_pos(const double4 *__restrict__ pos4, unsigned n)
 {
     const double2 *p = reinterpret_cast<const double2 *>(pos4 + n);
     double2 a = __ldg(p), b = __ldg(p + 1);
     return {a.x, a.y, b.x};
+}
+
+// Exact float -> double widening with integer ops.  F2F.F64.F32 runs on the XU pipe, which the FP64<->int/float
+// conversions of this kernel saturate (ncu: xu_realtime 84 %); the ALU pipe is idle.  Normal numbers only need the
+// exponent re-biased (+896) and the mantissa shifted; zeros, denormals, infinities and NaNs take the F2F path.
+DSC_D double widen_exact(float f)
+{
+    const unsigned b = __float_as_uint(f);
+    const unsigned e = b & 0x7f800000u;
+    if (e == 0u || e == 0x7f800000u) return (double)f;
+    const unsigned hi = (((b & 0x7fffffffu) >> 3) + 0x38000000u) | (b & 0x80000000u);
+    const unsigned lo = b << 29;
+    return __hiloint2double((int)hi, (int)lo);
+}
+
+__global__ void pos_to_float_kernel(const double4 *__restrict__ pos4, float4 *__restrict__ pos4f, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 a = reinterpret_cast<const double2 *>(pos4 + i)[0], b = reinterpret_cast<const double2 *>(pos4 + i)[1];
+    pos4f[i] = make_float4((float)a.x, (float)a.y, (float)b.x, 0.f);
 }
 
 DSC_D double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
@@ -113,6 +142,8 @@ struct TetArgs {
     int nc;
     double c[kMaxPhase];
     double *tet_total, *tet_vol, *tet_mean, *tet_energy, *tet_variation;
+    const float4 *tet_bary_f;        // the same table rounded to float (FP32 filter path)
+    cudaTextureObject_t tex;         // 3-D texture over the volume (0 when unavailable)
     double *partials;                // [gridDim.x][3*kMaxPhase]: total, sumsq, volume
     unsigned long long *sample_count; // algorithmic samples processed (for the roofline figure)
 };
@@ -254,6 +285,604 @@ __global__ void __launch_bounds__(256) tet_integrate_kernel(const TetArgs a)
     __shared__ double sm[8][3 * kMaxPhase];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane < kMaxPhase && lane < G) {
+        sm[warp][lane] = acc_tot;
+        sm[warp][kMaxPhase + lane] = acc_sq;
+        sm[warp][2 * kMaxPhase + lane] = acc_vol;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * kMaxPhase) {
+        double r = 0;
+        const int nw = blockDim.x >> 5;
+        for (int wdx = 0; wdx < nw; wdx++) r += sm[wdx][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
+    }
+    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Optimised G-lanes-per-tet form (hot path without per-c outputs): as tet_integrate_kernel, plus
+//   * the barycentric table rows of levels n <= kSmemLevels are staged in shared memory once per CTA
+//     (float4 rows for the FP32 filter, double rows for the exact path), so the L1 only serves voxel gathers;
+//   * samples are processed in batches of UNROLL per lane: indices first, then UNROLL gathers back to back;
+//   * FILTER: FP32 position + error bound in front of the exact FP64 position (see the thread-per-tet kernel
+//     below for the bound); tets that are not strictly inside the volume take the exact path.
+// Lanes of a group take consecutive table rows, which are spatially adjacent sample points (the table is
+// generated sub-cube by sub-cube), so the G gathers of one step fall into 2-3 cache lines.
+// -------------------------------------------------------------------------------------------------
+constexpr int kSmemLevels = 5;                                                        // n = 1..5
+constexpr int kSmemRows = (kSmemLevels * (kSmemLevels + 1) / 2) * (kSmemLevels * (kSmemLevels + 1) / 2); // 225 rows
+
+template <typename VoxT, int G, int UNROLL, bool FILTER>
+__global__ void __launch_bounds__(256) tet_integrate_g_kernel(const TetArgs a)
+{
+    __shared__ float4 s_tabf[FILTER ? kSmemRows : 1];
+    __shared__ double2 s_tabd[2 * kSmemRows];
+    for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
+    if (FILTER)
+        for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_tabf[i] = a.tet_bary_f[i];
+    __syncthreads();
+
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const size_t XY = (size_t)X * Y;
+    const int lane_g = threadIdx.x & (G - 1);
+    const unsigned groups_per_block = blockDim.x / G;
+    const unsigned total_groups = gridDim.x * groups_per_block;
+    const unsigned gid = blockIdx.x * groups_per_block + threadIdx.x / G;
+    const unsigned n_work = a.tet_end - a.tet_begin;
+    const unsigned iters = (n_work + total_groups - 1) / total_groups;
+    const float MAGIC = 12582912.0f; // 1.5 * 2^23
+    const int MAGIC_BITS = 0x4B400000;
+
+    double acc_tot = 0, acc_sq = 0, acc_vol = 0;
+    unsigned long long nsamp = 0;
+
+    for (unsigned it = 0; it < iters; it++) {
+        const unsigned w = it * total_groups + gid;
+        const bool valid = w < n_work;
+        const unsigned t = a.tet_begin + (valid ? w : 0);
+        int label = 0;
+        bool active = false;
+        double s = 0, sq = 0, v = 0;
+        int n3 = 0;
+        if (valid) {
+            label = __ldg(a.mesh.tet_label + t);
+            active = a.include_bound || label != 0;
+        }
+        if (active) {
+            const uint4 nd = __ldg(a.mesh.tet_nodes + t);
+            const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+            const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+            v = tet_volume(p0, p1, p2, p3);
+            const int L = tet_level(v);
+            n3 = (L + 1) * (L + 1) * (L + 1);
+            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+            // float copies of the vertices come from HBM (pos4f): converting per lane would saturate the XU pipe
+            const float4 f0 = __ldg(a.mesh.pos4f + nd.x), f1 = __ldg(a.mesh.pos4f + nd.y), f2 = __ldg(a.mesh.pos4f + nd.z), f3 = __ldg(a.mesh.pos4f + nd.w);
+            const float ax = f0.x, ay = f0.y, az = f0.z, bx = f1.x, by = f1.y, bz = f1.z;
+            const float cx = f2.x, cy = f2.y, cz = f2.z, dx = f3.x, dy = f3.y, dz = f3.z;
+            // conservative interior test on the float copies (they are within 2^-24 relative of the doubles; margin 0.5):
+            // every vertex, hence every sample point (a convex combination up to 1e-5), lies in [1, dim-1) on each axis
+            const float lo = fminf(fminf(fminf(fminf(ax, ay), az), fminf(fminf(bx, by), bz)), fminf(fminf(fminf(cx, cy), cz), fminf(fminf(dx, dy), dz)));
+            const float hx = fmaxf(fmaxf(ax, bx), fmaxf(cx, dx)), hy = fmaxf(fmaxf(ay, by), fmaxf(cy, dy)), hz = fmaxf(fmaxf(az, bz), fmaxf(cz, dz));
+            const bool interior = lo >= 1.5f && hx < (float)X - 1.5f && hy < (float)Y - 1.5f && hz < (float)Z - 1.5f;
+            const float M = fmaxf(fmaxf(hx, hy), hz);
+            const bool in_smem = L < kSmemLevels;
+            unsigned long long isum = 0, isq = 0;
+            // Samples are processed in batches of UNROLL per lane: all voxel indices of a batch are computed first
+            // (branch-free), then all gathers are issued back to back, then accumulated -- UNROLL loads in flight per
+            // lane instead of one (the gather latency, not bandwidth, bounds this kernel otherwise).  Indices are 32-bit
+            // (the host only selects this kernel when X*Y*Z < 2^31); -1 marks "reads as 0".
+            const double2 *__restrict__ tbg = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+            const int XYi = X * Y;
+            auto exact_index = [&](int i) -> int {
+                // get_coord: ((p0*b0 + p1*b1) + p2*b2) + p3*b3 per component (DEMO/tet_dis_coord.hpp:27), truncated (image3d.cpp:366)
+                double2 b01, b23;
+                if (in_smem) { b01 = s_tabd[2 * (off + i)]; b23 = s_tabd[2 * (off + i) + 1]; }
+                else { b01 = __ldg(tbg + 2 * i); b23 = __ldg(tbg + 2 * i + 1); }
+                const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                const bool inb = (unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z;
+                return inb ? iz * XYi + iy * X + ix : -1;
+            };
+            auto gather_and_accumulate = [&](const int (&idx)[UNROLL]) {
+                VoxT val[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    if constexpr (VoxTraits<VoxT>::integral) {
+                        const unsigned q = (unsigned)val[u];
+                        isum += q;
+                        isq += (unsigned long long)q * q;
+                    } else {
+                        double I;
+                        if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val[u]);
+                        else I = (double)val[u];
+                        s += I;
+                        sq = fma(I, I, sq); // second moment: tolerance quantity, fused on purpose
+                    }
+                }
+            };
+            if (FILTER && interior && in_smem && M < 65536.0f) {
+                const float thr = 0.5f - (M + 1.0f) * 9.5367431640625e-07f; // 0.5 - delta, delta = 2^-20 (M + 1)
+                const int last = n3 - 1;
+                const unsigned fold = (unsigned)MAGIC_BITS * (unsigned)(XYi + X + 1); // wraps, as intended
+                const float4 *__restrict__ tf = s_tabf + off;
+                for (int base = lane_g; base < n3; base += G * UNROLL) {
+                    int idx[UNROLL];
+                    unsigned unsafe = 0;
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        const int i = base + u * G;
+                        const bool ok = i <= last;
+                        const float4 b = tf[min(i, last)];
+                        const float qx = fmaf(b.w, dx, fmaf(b.z, cx, fmaf(b.y, bx, fmaf(b.x, ax, -0.5f))));
+                        const float qy = fmaf(b.w, dy, fmaf(b.z, cy, fmaf(b.y, by, fmaf(b.x, ay, -0.5f))));
+                        const float qz = fmaf(b.w, dz, fmaf(b.z, cz, fmaf(b.y, bz, fmaf(b.x, az, -0.5f))));
+                        const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
+                        const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
+                        // (iz*XY + iy*X + ix) with the three MAGIC_BITS offsets folded into one constant
+                        const int lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) - fold);
+                        idx[u] = ok ? lin : -1;
+                        if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) unsafe |= 1u << u;
+                    }
+                    if (unsafe) { // a coordinate within delta of a voxel boundary: exact reference arithmetic for those samples
+#pragma unroll
+                        for (int u = 0; u < UNROLL; u++)
+                            if (unsafe & (1u << u)) idx[u] = exact_index(base + u * G);
+                    }
+                    gather_and_accumulate(idx);
+                }
+            } else {
+                for (int base = lane_g; base < n3; base += G * UNROLL) {
+                    int idx[UNROLL];
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        const int i = base + u * G;
+                        idx[u] = i < n3 ? exact_index(i) : -1;
+                    }
+                    gather_and_accumulate(idx);
+                }
+            }
+            if (VoxTraits<VoxT>::integral) {
+                const double dn = VoxTraits<VoxT>::denom();
+                s = (double)isum / dn;
+                sq = (double)isq / (dn * dn);
+            }
+        }
+#pragma unroll
+        for (int m = G / 2; m >= 1; m >>= 1) {
+            s += shfl_xor_d(s, m);
+            sq += shfl_xor_d(sq, m);
+        }
+        if (active) {
+            const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
+            const double tsq = sq * v / (double)n3;
+            if (lane_g == 0) {
+                nsamp += (unsigned long long)n3;
+                if (a.tet_total) a.tet_total[t] = tot;
+                if (a.tet_vol) a.tet_vol[t] = v;
+                if (a.tet_mean) a.tet_mean[t] = tot / v;
+            }
+            if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
+                acc_tot += tot;
+                acc_sq += tsq;
+                acc_vol += v;
+            }
+        } else if (valid && lane_g == 0) {
+            if (a.tet_total) a.tet_total[t] = -1.0;
+            if (a.tet_vol) a.tet_vol[t] = -1.0;
+            if (a.tet_mean) a.tet_mean[t] = -1.0;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= G; m >>= 1) {
+        acc_tot += shfl_xor_d(acc_tot, m);
+        acc_sq += shfl_xor_d(acc_sq, m);
+        acc_vol += shfl_xor_d(acc_vol, m);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
+    __shared__ double sm[8][3 * kMaxPhase];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < kMaxPhase && lane < G) {
+        sm[warp][lane] = acc_tot;
+        sm[warp][kMaxPhase + lane] = acc_sq;
+        sm[warp][2 * kMaxPhase + lane] = acc_vol;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * kMaxPhase) {
+        double r = 0;
+        const int nw = blockDim.x >> 5;
+        for (int wdx = 0; wdx < nw; wdx++) r += sm[wdx][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
+    }
+    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Two-phase CTA form (the default hot path): setup once per tet, sampling with a warp per tet.
+//
+// Each CTA walks batches of kBatch consecutive tets:
+//   phase A  one THREAD per tet: label, node ids, FP64 positions -> exact volume, sample level, float copies of the
+//            vertices, FP32-filter threshold; the record goes to shared memory.  The three dependent global loads of
+//            a tet are issued by 256 threads at once and overlap with phase B of the other CTAs on the SM, instead of
+//            sitting on every warp's critical path, and the setup arithmetic is no longer replicated per lane.
+//   phase B  one WARP per tet: lane j takes samples j, j+32, ... (consecutive table rows = spatially adjacent points,
+//            so a 32-lane gather touches only a few cache lines); positions come from the shared record (broadcast
+//            LDS), the barycentric rows from shared memory.  The voxel index uses the FP32 filter with exact FP64
+//            fallback (see below); two 32-sample chunks are indexed before their gathers are issued.
+// Per-label sums: the label is warp-uniform in phase B, so each lane adds its partial (sum_lane * v / n^3) straight into
+// per-label registers (no per-tet shuffle reduction on the hot path); PER_TET additionally reduces per tet and writes
+// tet_total / tet_vol / tet_mean with the reference's (sum * v) / n^3 rounding.  One partial row per CTA, added in CTA
+// order by tet_finalize_kernel: bit-reproducible.
+// No conversion instruction remains in the per-sample path: F2I/F2F run on the XU pipe, which they saturated in the
+// earlier forms (ncu: xu_realtime 84 %); floor() is taken with the 1.5*2^23 trick on the FP32 pipe and the gathered
+// float is widened to double with integer ops.
+// -------------------------------------------------------------------------------------------------
+constexpr int kBatch = 256;
+
+template <typename VoxT, int PMAX, bool PER_TET>
+__global__ void __launch_bounds__(256) tet_integrate_ab_kernel(const TetArgs a)
+{
+    __shared__ float4 s_tabf[kSmemRows];
+    __shared__ double2 s_tabd[2 * kSmemRows];
+    __shared__ float4 r_pa[kBatch], r_pb[kBatch], r_pc[kBatch]; // (ax,ay,az,bx) (by,bz,cx,cy) (cz,dx,dy,dz)
+    __shared__ double r_v[kBatch];
+    __shared__ uint4 r_nd[kBatch];
+    __shared__ float r_thr[kBatch];
+    __shared__ int r_meta[kBatch]; // bits 0-7 label, 8-11 level, 12 active, 13 fast path allowed
+    for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
+    for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_tabf[i] = a.tet_bary_f[i];
+
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const int XYi = X * Y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned n_work = a.tet_end - a.tet_begin;
+    const unsigned n_batches = (n_work + kBatch - 1) / kBatch;
+    const float MAGIC = 12582912.0f; // 1.5 * 2^23
+    const unsigned fold = 0x4B400000u * (unsigned)(XYi + X + 1); // the three MAGIC_BITS offsets of (iz*XY + iy*X + ix); wraps, as intended
+
+    double acc_tot[PMAX], acc_sq[PMAX], acc_vol[PMAX];
+#pragma unroll
+    for (int k = 0; k < PMAX; k++) acc_tot[k] = acc_sq[k] = acc_vol[k] = 0.0;
+    unsigned long long nsamp = 0;
+
+    for (unsigned bt = blockIdx.x; bt < n_batches; bt += gridDim.x) {
+        const unsigned base_t = a.tet_begin + bt * kBatch;
+        const int nb = (int)min((unsigned)kBatch, a.tet_end - base_t);
+        __syncthreads(); // previous batch fully consumed (also covers the table staging on the first pass)
+        // ---------------- phase A: one thread per tet ----------------
+        if ((int)threadIdx.x < nb) {
+            const unsigned t = base_t + threadIdx.x;
+            const int label = __ldg(a.mesh.tet_label + t);
+            const bool active = a.include_bound || label != 0;
+            int meta = label & 0xff;
+            if (active) {
+                const uint4 nd = __ldg(a.mesh.tet_nodes + t);
+                const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                const double v = tet_volume(p0, p1, p2, p3);
+                const int L = tet_level(v);
+                const float ax = (float)p0.x, ay = (float)p0.y, az = (float)p0.z, bx = (float)p1.x, by = (float)p1.y, bz = (float)p1.z;
+                const float cx = (float)p2.x, cy = (float)p2.y, cz = (float)p2.z, dx = (float)p3.x, dy = (float)p3.y, dz = (float)p3.z;
+                // conservative interior test on the float copies (within 2^-24 relative of the doubles; margin 0.5): every
+                // vertex, hence every sample point (a convex combination up to 1e-5), lies in [1, dim-1) on each axis
+                const float lo = fminf(fminf(fminf(fminf(ax, ay), az), fminf(fminf(bx, by), bz)), fminf(fminf(fminf(cx, cy), cz), fminf(fminf(dx, dy), dz)));
+                const float hx = fmaxf(fmaxf(ax, bx), fmaxf(cx, dx)), hy = fmaxf(fmaxf(ay, by), fmaxf(cy, dy)), hz = fmaxf(fmaxf(az, bz), fmaxf(cz, dz));
+                const bool interior = lo >= 1.5f && hx < (float)X - 1.5f && hy < (float)Y - 1.5f && hz < (float)Z - 1.5f;
+                const float M = fmaxf(fmaxf(hx, hy), hz);
+                const bool fast = interior && L < kSmemLevels && M < 65536.0f;
+                r_pa[threadIdx.x] = make_float4(ax, ay, az, bx);
+                r_pb[threadIdx.x] = make_float4(by, bz, cx, cy);
+                r_pc[threadIdx.x] = make_float4(cz, dx, dy, dz);
+                r_v[threadIdx.x] = v;
+                r_nd[threadIdx.x] = nd;
+                r_thr[threadIdx.x] = 0.5f - (M + 1.0f) * 9.5367431640625e-07f; // 0.5 - delta, delta = 2^-20 (M + 1)
+                meta |= (L << 8) | (1 << 12) | (fast ? (1 << 13) : 0);
+            } else {
+                if (a.tet_total) a.tet_total[t] = -1.0;
+                if (a.tet_vol) a.tet_vol[t] = -1.0;
+                if (a.tet_mean) a.tet_mean[t] = -1.0;
+            }
+            r_meta[threadIdx.x] = meta;
+        }
+        __syncthreads();
+        // ---------------- phase B: one warp per tet ----------------
+        for (int j = warp; j < nb; j += 8) {
+            const int meta = r_meta[j];
+            if (!(meta & (1 << 12))) continue;
+            const int label = meta & 0xff;
+            const int L = (meta >> 8) & 0xf;
+            const int n3 = (L + 1) * (L + 1) * (L + 1);
+            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+            double s = 0, sq = 0;
+            unsigned long long isum = 0, isq = 0;
+            auto add_voxel = [&](VoxT val) {
+                if constexpr (VoxTraits<VoxT>::integral) {
+                    const unsigned q = (unsigned)val;
+                    isum += q;
+                    isq += (unsigned long long)q * q;
+                } else {
+                    double I;
+                    if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val);
+                    else I = (double)val;
+                    s += I;
+                    sq = fma(I, I, sq); // second moment: tolerance quantity, fused on purpose
+                }
+            };
+            if (meta & (1 << 13)) {
+                const float4 pa = r_pa[j], pb = r_pb[j], pc = r_pc[j];
+                const float thr = r_thr[j];
+                const float4 *__restrict__ tf = s_tabf + off;
+                const int last = n3 - 1;
+                auto exact_index = [&](int i) -> int {
+                    // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
+                    // (get_coord, DEMO/tet_dis_coord.hpp:27; truncation, image3d.cpp:366)
+                    const uint4 nd = r_nd[j];
+                    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                    const double2 b01 = s_tabd[2 * (off + i)], b23 = s_tabd[2 * (off + i) + 1];
+                    const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                    const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                    const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                    return iz * XYi + iy * X + ix; // interior tet: always in range
+                };
+                auto fast_index = [&](int i, bool ok) -> int {
+                    const float4 b = tf[min(i, last)];
+                    const float qx = fmaf(b.w, pc.y, fmaf(b.z, pb.z, fmaf(b.y, pa.w, fmaf(b.x, pa.x, -0.5f))));
+                    const float qy = fmaf(b.w, pc.z, fmaf(b.z, pb.w, fmaf(b.y, pb.x, fmaf(b.x, pa.y, -0.5f))));
+                    const float qz = fmaf(b.w, pc.w, fmaf(b.z, pc.x, fmaf(b.y, pb.y, fmaf(b.x, pa.z, -0.5f))));
+                    const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
+                    const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
+                    int lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) - fold);
+                    if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) lin = exact_index(i);
+                    return ok ? lin : -1;
+                };
+                for (int c0 = lane; c0 < n3; c0 += 64) {
+                    const int i1 = c0 + 32;
+                    const int idx0 = fast_index(c0, true);
+                    const int idx1 = fast_index(i1, i1 < n3);
+                    const VoxT v0 = __ldg(vol + idx0);
+                    const VoxT v1 = idx1 >= 0 ? __ldg(vol + idx1) : (VoxT)0;
+                    add_voxel(v0);
+                    add_voxel(v1);
+                }
+            } else {
+                // exact path: tets touching the volume border (bounds-checked reads, negative coordinates) or very large tets
+                const uint4 nd = r_nd[j];
+                const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+                for (int i = lane; i < n3; i += 32) {
+                    const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
+                    const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                    const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                    const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                    VoxT val = (VoxT)0;
+                    if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) val = __ldg(vol + (iz * XYi + iy * X + ix));
+                    add_voxel(val);
+                }
+            }
+            if constexpr (VoxTraits<VoxT>::integral) {
+                const double dn = VoxTraits<VoxT>::denom();
+                s = (double)isum / dn;
+                sq = (double)isq / (dn * dn);
+            }
+            const double v = r_v[j];
+            if (PER_TET) {
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) {
+                    s += shfl_xor_d(s, m);
+                    sq += shfl_xor_d(sq, m);
+                }
+                const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
+                const double tsq = sq * v / (double)n3;
+                if (lane == 0) {
+                    const unsigned t = base_t + j;
+                    if (a.tet_total) a.tet_total[t] = tot;
+                    if (a.tet_vol) a.tet_vol[t] = v;
+                    if (a.tet_mean) a.tet_mean[t] = tot / v;
+                }
+                s = lane == 0 ? tot : 0.0;
+                sq = lane == 0 ? tsq : 0.0;
+            } else {
+                const double wgt = v / (double)n3;
+                s *= wgt;
+                sq *= wgt;
+            }
+            const double vl = lane == 0 ? v : 0.0;
+#pragma unroll
+            for (int k = 0; k < PMAX; k++)
+                if (label == k + 1 && k < a.nb_phase) { acc_tot[k] += s; acc_sq[k] += sq; acc_vol[k] += vl; }
+            if (lane == 0) nsamp += (unsigned long long)n3;
+        }
+    }
+    // ---- CTA reduction: warp trees, then one row per CTA
+#pragma unroll
+    for (int k = 0; k < PMAX; k++)
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            acc_tot[k] += shfl_xor_d(acc_tot[k], m);
+            acc_sq[k] += shfl_xor_d(acc_sq[k], m);
+            acc_vol[k] += shfl_xor_d(acc_vol[k], m);
+        }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
+    __shared__ double sm[8][3 * kMaxPhase];
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kMaxPhase; k++) {
+            sm[warp][k] = k < PMAX ? acc_tot[k < PMAX ? k : 0] : 0.0;
+            sm[warp][kMaxPhase + k] = k < PMAX ? acc_sq[k < PMAX ? k : 0] : 0.0;
+            sm[warp][2 * kMaxPhase + k] = k < PMAX ? acc_vol[k < PMAX ? k : 0] : 0.0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * kMaxPhase) {
+        double r = 0;
+        for (int wdx = 0; wdx < 8; wdx++) r += sm[wdx][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
+    }
+    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Thread-per-tet form with an FP32 filter in front of the exact FP64 position.
+//
+// One thread owns one tet: setup (ids, positions, volume, level) is done once per tet instead of once per
+// lane, and the sample loop is unrolled so that several voxel gathers are in flight per thread.
+//
+// FILTER: the voxel a sample falls into only depends on floor() of its position, so the position is first
+// evaluated in FP32 (12 FFMA) with a rigorous error bound delta; when every coordinate is further than delta
+// from an integer, floor of the FP32 value equals floor of the reference's FP64 value and the exact 21-op
+// FP64 evaluation is skipped.  Otherwise (about 0.3 % of the samples at 512^3) the sample is re-evaluated with
+// the exact reference arithmetic.  Bound: inputs rounded to float (2^-24 relative each), 4 FMA roundings on
+// partial sums of magnitude <= M + 0.5 (M = largest |vertex coordinate| of the tet; the weights are >= 0 and sum
+// to ~1):  |q - r| <= 7 * 2^-24 * (M + 0.5); delta = 2^-20 * (M + 1) keeps a 2x margin.  The filter is only
+// used for tets whose vertices lie inside [1, dim-1) on every axis (no negative coordinates, no bounds checks
+// needed for any sample because samples are convex combinations of the vertices up to 1e-5).
+// floor via the 1.5*2^23 trick: the FMA chain starts at -0.5, t = q' + MAGIC rounds to the nearest integer n,
+// d = q' - n in [-0.5, 0.5], and floor(q) = n whenever |d| < 0.5 - delta.  No F2I conversion (XU pipe) needed.
+// -------------------------------------------------------------------------------------------------
+constexpr int kFetchLdg = 0, kFetchTex = 1;
+
+template <typename VoxT, int FETCH, bool FILTER>
+__global__ void __launch_bounds__(128) tet_integrate_tpt_kernel(const TetArgs a)
+{
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const size_t XY = (size_t)X * Y;
+    const int lane = threadIdx.x & 31;
+    const unsigned total_threads = gridDim.x * blockDim.x;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n_work = a.tet_end - a.tet_begin;
+    const unsigned iters = (n_work + total_threads - 1) / total_threads;
+    const float MAGIC = 12582912.0f; // 1.5 * 2^23
+    const int MAGIC_BITS = 0x4B400000;
+
+    double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane + 1
+    unsigned long long nsamp = 0;
+
+    for (unsigned it = 0; it < iters; it++) {
+        const unsigned w = it * total_threads + tid;
+        const bool valid = w < n_work;
+        const unsigned t = a.tet_begin + (valid ? w : 0);
+        int label = 0;
+        bool active = false;
+        double tot = 0, tsq = 0, v = 0;
+        if (valid) {
+            label = __ldg(a.mesh.tet_label + t);
+            active = a.include_bound || label != 0;
+        }
+        if (active) {
+            const uint4 nd = __ldg(a.mesh.tet_nodes + t);
+            const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+            const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+            v = tet_volume(p0, p1, p2, p3);
+            const int L = tet_level(v);
+            const int n3 = (L + 1) * (L + 1) * (L + 1);
+            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+            const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
+            const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
+            const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
+            const bool interior = lox >= 1.0 && loy >= 1.0 && loz >= 1.0 && hix < (double)(X - 1) && hiy < (double)(Y - 1) && hiz < (double)(Z - 1);
+            double s = 0, sq = 0;
+            unsigned long long isum = 0, isq = 0;
+            auto accumulate = [&](int ix, int iy, int iz, bool checked) {
+                if constexpr (VoxTraits<VoxT>::integral) {
+                    unsigned q;
+                    if constexpr (FETCH == kFetchTex) q = (unsigned)tex_fetch<VoxT>(a.tex, ix, iy, iz);
+                    else if (checked || ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z))
+                        q = (unsigned)__ldg(vol + (size_t)iz * XY + (size_t)iy * X + ix);
+                    else q = 0;
+                    isum += q;
+                    isq += (unsigned long long)q * q;
+                } else {
+                    double I;
+                    if constexpr (FETCH == kFetchTex) I = (double)tex_fetch<VoxT>(a.tex, ix, iy, iz);
+                    else if (checked || ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z))
+                        I = (double)__ldg(vol + (size_t)iz * XY + (size_t)iy * X + ix);
+                    else I = 0.0;
+                    s += I;
+                    sq = fma(I, I, sq); // second moment: tolerance quantity, fused on purpose
+                }
+            };
+            const double M = fmax(fmax(hix, hiy), hiz);
+            if (FILTER && interior && M < 65536.0) {
+                const float delta = (float)((M + 1.0) * 9.5367431640625e-07); // 2^-20
+                const float thr = 0.5f - delta;
+                const float ax = (float)p0.x, ay = (float)p0.y, az = (float)p0.z, bx = (float)p1.x, by = (float)p1.y, bz = (float)p1.z;
+                const float cx = (float)p2.x, cy = (float)p2.y, cz = (float)p2.z, dx = (float)p3.x, dy = (float)p3.y, dz = (float)p3.z;
+                const float4 *__restrict__ tf = a.tet_bary_f + off;
+                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+#pragma unroll 4
+                for (int i = 0; i < n3; i++) {
+                    const float4 b = __ldg(tf + i);
+                    const float qx = fmaf(b.w, dx, fmaf(b.z, cx, fmaf(b.y, bx, fmaf(b.x, ax, -0.5f))));
+                    const float qy = fmaf(b.w, dy, fmaf(b.z, cy, fmaf(b.y, by, fmaf(b.x, ay, -0.5f))));
+                    const float qz = fmaf(b.w, dz, fmaf(b.z, cz, fmaf(b.y, bz, fmaf(b.x, az, -0.5f))));
+                    const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
+                    const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
+                    int ix = __float_as_int(tx) - MAGIC_BITS, iy = __float_as_int(ty) - MAGIC_BITS, iz = __float_as_int(tz) - MAGIC_BITS;
+                    if (fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) {
+                        // too close to a voxel boundary for FP32: exact reference arithmetic
+                        const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
+                        ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                        iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                        iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                    }
+                    accumulate(ix, iy, iz, true);
+                }
+            } else {
+                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+#pragma unroll 2
+                for (int i = 0; i < n3; i++) {
+                    const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
+                    const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                    const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                    const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                    accumulate(ix, iy, iz, interior);
+                }
+            }
+            if (VoxTraits<VoxT>::integral) {
+                const double dn = VoxTraits<VoxT>::denom();
+                s = (double)isum / dn;
+                sq = (double)isq / (dn * dn);
+            }
+            tot = s * v / (double)n3;
+            tsq = sq * v / (double)n3;
+            nsamp += (unsigned long long)n3;
+            if (a.tet_total) a.tet_total[t] = tot;
+            if (a.tet_vol) a.tet_vol[t] = v;
+            if (a.tet_mean) a.tet_mean[t] = tot / v;
+        } else if (valid) {
+            if (a.tet_total) a.tet_total[t] = -1.0;
+            if (a.tet_vol) a.tet_vol[t] = -1.0;
+            if (a.tet_mean) a.tet_mean[t] = -1.0;
+        }
+        // per-label warp reduction: lane k keeps the sums of label k+1
+        for (int k = 0; k < a.nb_phase; k++) {
+            const bool m = active && label == k + 1;
+            double x = m ? tot : 0.0, y = m ? tsq : 0.0, z = m ? v : 0.0;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                x += shfl_xor_d(x, o);
+                y += shfl_xor_d(y, o);
+                z += shfl_xor_d(z, o);
+            }
+            if (lane == k) { acc_tot += x; acc_sq += y; acc_vol += z; }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
+    __shared__ double sm[4][3 * kMaxPhase];
+    const int warp = threadIdx.x >> 5;
+    if (lane < kMaxPhase) {
         sm[warp][lane] = acc_tot;
         sm[warp][kMaxPhase + lane] = acc_sq;
         sm[warp][2 * kMaxPhase + lane] = acc_vol;

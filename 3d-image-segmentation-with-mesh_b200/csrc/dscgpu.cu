@@ -65,10 +65,14 @@ struct dscgpu_ctx {
     double *d_sum_table = nullptr;
     bool has_sum_table = false;
     double *d_tet_bary = nullptr;
+    float4 *d_tet_bary_f = nullptr;
+    cudaArray_t vol_array = nullptr;
+    cudaTextureObject_t vol_tex = 0;
+    int tet_variant = 40; // see dscgpu_set_tet_variant; default = batched group kernel, 4 gathers in flight per lane
 
     bool has_snapshot = false;
     uint32_t n_nodes = 0, n_tets = 0, n_faces = 0;
-    DevBuf pos4, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc;
+    DevBuf pos4, pos4f, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc;
     // pinned staging (host side of the snapshot)
     PinBuf h_pos4, h_tet_nodes, h_tet_label, h_face_nodes, h_face_tets, h_face_isb, h_node_off, h_node_inc, h_out, h_flag;
     bool validation_pending = false;
@@ -150,6 +154,7 @@ MeshView mesh_view(const dscgpu_ctx *c)
 {
     MeshView m;
     m.pos4 = c->pos4.as<double4>();
+    m.pos4f = c->pos4f.as<float4>();
     m.tet_nodes = c->tet_nodes.as<uint4>();
     m.tet_label = c->tet_label.as<int>();
     m.face_nodes = c->face_nodes.as<unsigned>();
@@ -184,6 +189,91 @@ template <typename VoxT, int G, bool WITH_C> int launch_tet_t(dscgpu_ctx *ctx, T
     return DSCGPU_OK;
 }
 
+template <typename VoxT, int FETCH, bool FILTER> int launch_tpt_t(dscgpu_ctx *ctx, TetArgs &a)
+{
+    auto kern = tet_integrate_tpt_kernel<VoxT, FETCH, FILTER>;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
+    if (occ < 1) occ = 1;
+    unsigned n_work = a.tet_end - a.tet_begin;
+    unsigned need = (n_work + 127) / 128;
+    unsigned grid = (unsigned)(ctx->num_sms * occ);
+    if (need < grid) grid = need ? need : 1;
+    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
+    a.partials = ctx->partials.as<double>();
+    ctx->tet_grid = (int)grid;
+    kern<<<grid, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT> int launch_tpt_v(dscgpu_ctx *ctx, TetArgs &a, bool tex, bool filter)
+{
+    if (tex) return filter ? launch_tpt_t<VoxT, kFetchTex, true>(ctx, a) : launch_tpt_t<VoxT, kFetchTex, false>(ctx, a);
+    return filter ? launch_tpt_t<VoxT, kFetchLdg, true>(ctx, a) : launch_tpt_t<VoxT, kFetchLdg, false>(ctx, a);
+}
+
+template <typename VoxT, int PMAX, bool PER_TET> int launch_ab_t(dscgpu_ctx *ctx, TetArgs &a)
+{
+    auto kern = tet_integrate_ab_kernel<VoxT, PMAX, PER_TET>;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    if (occ < 1) occ = 1;
+    unsigned n_work = a.tet_end - a.tet_begin;
+    unsigned need = (n_work + kBatch - 1) / kBatch;
+    unsigned grid = (unsigned)(ctx->num_sms * occ);
+    if (need < grid) grid = need ? need : 1;
+    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
+    a.partials = ctx->partials.as<double>();
+    ctx->tet_grid = (int)grid;
+    kern<<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT> int launch_ab(dscgpu_ctx *ctx, TetArgs &a)
+{
+    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
+    if (a.nb_phase <= 4) return per_tet ? launch_ab_t<VoxT, 4, true>(ctx, a) : launch_ab_t<VoxT, 4, false>(ctx, a);
+    return per_tet ? launch_ab_t<VoxT, 8, true>(ctx, a) : launch_ab_t<VoxT, 8, false>(ctx, a);
+}
+
+template <typename VoxT, int G, int UNROLL, bool FILTER> int launch_g_t(dscgpu_ctx *ctx, TetArgs &a)
+{
+    auto kern = tet_integrate_g_kernel<VoxT, G, UNROLL, FILTER>;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    if (occ < 1) occ = 1;
+    unsigned n_work = a.tet_end - a.tet_begin;
+    unsigned groups_per_block = 256 / G;
+    unsigned need = (n_work + groups_per_block - 1) / groups_per_block;
+    unsigned grid = (unsigned)(ctx->num_sms * occ);
+    if (need < grid) grid = need ? need : 1;
+    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
+    a.partials = ctx->partials.as<double>();
+    ctx->tet_grid = (int)grid;
+    kern<<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT, int G> int launch_g_v(dscgpu_ctx *ctx, TetArgs &a, int unroll, bool filter)
+{
+    if (unroll >= 4) return filter ? launch_g_t<VoxT, G, 4, true>(ctx, a) : launch_g_t<VoxT, G, 4, false>(ctx, a);
+    if (unroll >= 2) return filter ? launch_g_t<VoxT, G, 2, true>(ctx, a) : launch_g_t<VoxT, G, 2, false>(ctx, a);
+    return filter ? launch_g_t<VoxT, G, 1, true>(ctx, a) : launch_g_t<VoxT, G, 1, false>(ctx, a);
+}
+
+template <typename VoxT> int launch_g(dscgpu_ctx *ctx, TetArgs &a, int G, int unroll, bool filter)
+{
+    if (G == 32) return launch_g_v<VoxT, 32>(ctx, a, unroll, filter);
+    if (G == 16) return launch_g_v<VoxT, 16>(ctx, a, unroll, filter);
+    return launch_g_v<VoxT, 8>(ctx, a, unroll, filter);
+}
+
 template <typename VoxT> int launch_tet_v(dscgpu_ctx *ctx, TetArgs &a, int G, bool with_c)
 {
     if (G == 32) return with_c ? launch_tet_t<VoxT, 32, true>(ctx, a) : launch_tet_t<VoxT, 32, false>(ctx, a);
@@ -192,7 +282,36 @@ template <typename VoxT> int launch_tet_v(dscgpu_ctx *ctx, TetArgs &a, int G, bo
 
 int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
 {
+    if ((ctx->tet_variant & 1) && !with_c) {
+        const bool tex = (ctx->tet_variant & 2) && ctx->vol_tex != 0;
+        const bool filter = (ctx->tet_variant & 4) != 0;
+        switch (ctx->dtype) {
+        case DSCGPU_U8: return launch_tpt_v<unsigned char>(ctx, a, tex, filter);
+        case DSCGPU_U16: return launch_tpt_v<unsigned short>(ctx, a, tex, filter);
+        case DSCGPU_F32: return launch_tpt_v<float>(ctx, a, tex, filter);
+        default: return launch_tpt_t<double, kFetchLdg, false>(ctx, a); // no double textures; filter pointless without FP32 data
+        }
+    }
     int G = ctx->lanes_per_tet ? ctx->lanes_per_tet : ctx->auto_lanes;
+    const bool fits32 = (double)ctx->dims[0] * ctx->dims[1] * ctx->dims[2] < 2147483648.0;
+    if ((ctx->tet_variant & 64) && !with_c && fits32) { // two-phase CTA kernel (32-bit voxel indices)
+        switch (ctx->dtype) {
+        case DSCGPU_U8: return launch_ab<unsigned char>(ctx, a);
+        case DSCGPU_U16: return launch_ab<unsigned short>(ctx, a);
+        case DSCGPU_F32: return launch_ab<float>(ctx, a);
+        default: return launch_ab<double>(ctx, a);
+        }
+    }
+    if ((ctx->tet_variant & 8) && !with_c && fits32) { // optimised group kernel (32-bit voxel indices): bits 4-5 = log2(unroll), bit 2 = FP32 filter
+        const int unroll = 1 << ((ctx->tet_variant >> 4) & 3);
+        const bool filter = (ctx->tet_variant & 4) != 0;
+        switch (ctx->dtype) {
+        case DSCGPU_U8: return launch_g<unsigned char>(ctx, a, G, unroll, filter);
+        case DSCGPU_U16: return launch_g<unsigned short>(ctx, a, G, unroll, filter);
+        case DSCGPU_F32: return launch_g<float>(ctx, a, G, unroll, filter);
+        default: return launch_g<double>(ctx, a, G, unroll, false);
+        }
+    }
     if (G != 32) G = 8;
     switch (ctx->dtype) {
     case DSCGPU_U8: return launch_tet_v<unsigned char>(ctx, a, G, with_c);
@@ -210,6 +329,8 @@ int run_tet_pass(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const
     a.vol = vol_view(ctx);
     a.mesh = mesh_view(ctx);
     a.tet_bary = ctx->d_tet_bary;
+    a.tet_bary_f = ctx->d_tet_bary_f;
+    a.tex = ctx->vol_tex;
     a.tet_begin = ctx->tet_b; a.tet_end = ctx->tet_e;
     a.include_bound = include_bound;
     a.nb_phase = nb_phase;
@@ -440,6 +561,13 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
     if (voxels_host) CK(cudaMemcpyAsync(ctx->d_vol, voxels_host, n * dtype_size(dtype), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMalloc(&ctx->d_tet_bary, sizeof(DSC_TET_BARY)));
     CK(cudaMemcpyAsync(ctx->d_tet_bary, DSC_TET_BARY, sizeof(DSC_TET_BARY), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        std::vector<float> tf(4 * DSC_TET_POINTS_TOTAL);
+        for (int i = 0; i < 4 * DSC_TET_POINTS_TOTAL; i++) tf[i] = (float)DSC_TET_BARY[i];
+        CK(cudaMalloc(&ctx->d_tet_bary_f, tf.size() * sizeof(float)));
+        CK(cudaMemcpy(ctx->d_tet_bary_f, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (const char *ev = getenv("DSCGPU_TET_VARIANT")) ctx->tet_variant = atoi(ev);
     CK(cudaMemcpyToSymbolAsync(c_gauss, DSC_GAUSS, sizeof(DSC_GAUSS), 0, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyToSymbolAsync(c_gauss_off, DSC_GAUSS_SET_OFFSET, sizeof(DSC_GAUSS_SET_OFFSET), 0, cudaMemcpyHostToDevice, ctx->stream));
     int r = ensure_scratch(ctx);
@@ -452,7 +580,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_OK;
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    DevBuf *bufs[] = {&ctx->pos4, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
+    DevBuf *bufs[] = {&ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
                       &ctx->partials, &ctx->sums, &ctx->mean, &ctx->forces, &ctx->counters, &ctx->o_total, &ctx->o_vol, &ctx->o_mean, &ctx->o_energy,
                       &ctx->o_variation, &ctx->o_hash, &ctx->o_nsamp, &ctx->ray_count, &ctx->ray_offset, &ctx->ray_cursor, &ctx->hits, &ctx->block_sums,
                       &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
@@ -463,6 +591,9 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
     if (ctx->d_vol) cudaFree(ctx->d_vol);
     if (ctx->d_sum_table) cudaFree(ctx->d_sum_table);
     if (ctx->d_tet_bary) cudaFree(ctx->d_tet_bary);
+    if (ctx->d_tet_bary_f) cudaFree(ctx->d_tet_bary_f);
+    if (ctx->vol_tex) cudaDestroyTextureObject(ctx->vol_tex);
+    if (ctx->vol_array) cudaFreeArray(ctx->vol_array);
     for (int i = 0; i < DSCGPU_T_COUNT; i++) {
         if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]);
         if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]);
@@ -556,6 +687,7 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     build_node_csr(nn, nf, fn, ctx->h_node_off.as<uint32_t>(), ctx->h_node_inc.as<uint32_t>());
 
     CK(ctx->pos4.ensure((size_t)nn * 32));
+    CK(ctx->pos4f.ensure((size_t)nn * 16));
     CK(ctx->tet_nodes.ensure((size_t)nt * 16));
     CK(ctx->tet_label.ensure((size_t)nt * 4));
     CK(ctx->face_nodes.ensure((size_t)nf * 12));
@@ -574,6 +706,11 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
         if (nf) CK(cudaMemcpyAsync(ctx->face_isb.p, ctx->h_face_isb.p, (size_t)nf, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->node_off.p, ctx->h_node_off.p, ((size_t)nn + 1) * 4, cudaMemcpyHostToDevice, s));
         if (nf) CK(cudaMemcpyAsync(ctx->node_inc.p, ctx->h_node_inc.p, (size_t)nf * 12, cudaMemcpyHostToDevice, s));
+    }
+    if (nn) {
+        pos_to_float_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->pos4.as<double4>(), ctx->pos4f.as<float4>(), nn);
+        ctx->launches++;
+        CK(cudaGetLastError());
     }
     ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
     // index validation runs on the device (a host pass over 8 M ids would dominate the end-to-end step): bad ids are
@@ -921,12 +1058,54 @@ int dscgpu_get_timer(dscgpu_ctx *ctx, int which, float *ms)
     return DSCGPU_OK;
 }
 
+int dscgpu_build_texture(dscgpu_ctx *ctx)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    if (ctx->vol_tex) return DSCGPU_OK;
+    ARG(ctx->dtype != DSCGPU_F64, "no texture path for float64 volumes");
+    cudaChannelFormatDesc desc;
+    if (ctx->dtype == DSCGPU_U8) desc = cudaCreateChannelDesc<unsigned char>();
+    else if (ctx->dtype == DSCGPU_U16) desc = cudaCreateChannelDesc<unsigned short>();
+    else desc = cudaCreateChannelDesc<float>();
+    cudaExtent ext = make_cudaExtent((size_t)ctx->dims[0], (size_t)ctx->dims[1], (size_t)ctx->dims[2]);
+    CK(cudaMalloc3DArray(&ctx->vol_array, &desc, ext));
+    cudaMemcpy3DParms cp = {};
+    cp.srcPtr = make_cudaPitchedPtr(ctx->d_vol, (size_t)ctx->dims[0] * dtype_size(ctx->dtype), (size_t)ctx->dims[0], (size_t)ctx->dims[1]);
+    cp.dstArray = ctx->vol_array;
+    cp.extent = ext;
+    cp.kind = cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpy3DAsync(&cp, ctx->stream));
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = ctx->vol_array;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    CK(cudaCreateTextureObject(&ctx->vol_tex, &rd, &td, nullptr));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DSCGPU_OK;
+}
+
+int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(variant >= 0 && variant < 128, "variant is a 7-bit field");
+    if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
+        int r = dscgpu_build_texture(ctx);
+        if (r) return r;
+    }
+    ctx->tet_variant = variant;
+    return DSCGPU_OK;
+}
+
 uint64_t dscgpu_launch_count(const dscgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(lanes == 0 || lanes == 8 || lanes == 32, "lanes per tet must be 0, 8 or 32");
+    ARG(lanes == 0 || lanes == 8 || lanes == 16 || lanes == 32, "lanes per tet must be 0, 8, 16 or 32");
     ctx->lanes_per_tet = lanes;
     return DSCGPU_OK;
 }

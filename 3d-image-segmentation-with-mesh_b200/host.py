@@ -364,5 +364,9 @@ class SegmentFunction:
     def last_gauss_count(self):
         return int(self.lib.dscgpu_last_gauss_count(self._img._ctx))
 
+    def set_tet_variant(self, variant):
+        """bit0 thread-per-tet, bit1 texture gather, bit2 FP32 filter (see include/dscgpu.h)."""
+        self._img._check(self.lib.dscgpu_set_tet_variant(self._img._ctx, C.c_int(variant)), "dscgpu_set_tet_variant")
+
     def set_lanes_per_tet(self, lanes):
         self._img._check(self.lib.dscgpu_set_lanes_per_tet(self._img._ctx, C.c_int(lanes)), "dscgpu_set_lanes_per_tet")

@@ -260,8 +260,11 @@ def main_b200(args):
     mean_mode = pkg.MEAN_TET if args.mean_mode == "tet" else pkg.MEAN_ZRAY
     force_mode = pkg.FORCE_GATHER if args.force_mode == "gather" else pkg.FORCE_ATOMIC
 
-    # all launches go to torch's current stream so that torch.cuda.Event brackets them
-    stream = torch.cuda.current_stream(dev)
+    # all launches go to one explicit (non-default) torch stream so that torch.cuda.Event brackets them;
+    # NCCL collectives issued under torch.cuda.stream(stream) are ordered on the same stream
+    stream = torch.cuda.Stream(device=dev)
+    assert stream.cuda_stream != 0
+    torch.cuda.set_stream(stream)
     img.set_stream(stream.cuda_stream)
     if mean_mode == pkg.MEAN_ZRAY:
         img.build_sum_table()
@@ -415,7 +418,7 @@ def main_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %d^3 %s %d-phase phantom, %d tets (%d labelled), %d interface faces, %d nodes, grid mesh edge %.3f jitter %.2f" % (
             args.config, cfg["n"], vol.dtype.name, P, n_tets, int((snap["tet_label"] != 0).sum()), n_faces, n_nodes, edge, args.jitter),

@@ -200,6 +200,15 @@ int dscgpu_get_timer(dscgpu_ctx *ctx, int which, float *ms);
 uint64_t dscgpu_launch_count(const dscgpu_ctx *ctx);
 /* Tunables: lanes per tet of the integration kernel (1, 8 or 32; 0 = choose from the mesh). */
 int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes);
+/* Implementation of the per-tet integration kernel (results are identical up to FP64 summation order):
+ *   0            v1: G lanes per tet (dscgpu_set_lanes_per_tet), one gather in flight per lane
+ *   bit 0 (1)    one thread per tet;  + bit 1 (2): gather through a 3-D texture;  + bit 2 (4): FP32 filter
+ *   bit 3 (8)    batched G-lanes-per-tet kernel: bits 4-5 = log2(gathers in flight per lane), bit 2 (4) = FP32 filter
+ *   bit 6 (64)   two-phase CTA kernel (setup per thread, sampling per warp, FP32 filter)
+ * Default 40 (= 8 | 2<<4).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
+ * Per-candidate outputs (tet_energy / tet_variation) always use the v1 kernel. */
+int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant);
+int dscgpu_build_texture(dscgpu_ctx *ctx);
 /* Algorithmic sample count of the last tet pass (sum of n^3 over processed tets). */
 uint64_t dscgpu_last_sample_count(dscgpu_ctx *ctx);
 uint64_t dscgpu_last_gauss_count(dscgpu_ctx *ctx);

@@ -246,3 +246,45 @@ def test_ray_overflow_is_reported(pkg):
     with pytest.raises(pkg.DscGpuError, match="DSCGPU_MAX_RAY_HITS"):
         seg.update_average_intensity()
     img.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3, 5, 7, 8, 12, 24, 40, 44, 56, 60, 64])
+def test_every_kernel_variant_classifies_identically(pkg, variant):
+    """All implementations of the tet pass (incl. the FP32-filtered ones) must put every sample in the same voxel:
+    per-tet sums of noisy data agree to rounding, and the volumes bit for bit."""
+    for name in ("c1_e8_it2", "sph48_f32", "sh40_u16", "c1n_e9_j"):
+        g = golden_io.load(name)
+        img, seg = _seg(pkg, g)
+        lab = g["tet_label"] != 0
+        seg.set_tet_variant(variant)
+        for lanes in ((8, 16, 32) if variant & 8 else (0,)):
+            seg.set_lanes_per_tet(lanes)
+            o = seg.tet_integrate()
+            assert np.array_equal(o["vol"][lab], g["tet_vol"][lab])
+            np.testing.assert_allclose(o["total"][lab], g["tet_total"][lab], rtol=1e-12, atol=1e-13)
+            P = g["meta"]["nb_phase"]
+            tot = np.array([g["tet_total"][g["tet_label"] == k + 1].sum() for k in range(P)])
+            np.testing.assert_allclose(o["phase_total"], tot, rtol=1e-9)
+            o2 = seg.tet_integrate(per_tet=False)
+            np.testing.assert_allclose(o2["phase_total"], tot, rtol=1e-9)
+            np.testing.assert_allclose(o2["phase_volume"], o["phase_volume"], rtol=1e-12)
+        img.close()
+
+
+def test_filter_variants_on_large_interior_mesh(pkg, flat):
+    """The FP32 filter only engages for tets strictly inside the volume; use a case where most tets are."""
+    syn = pkg.synthetic
+    vol = syn.shells_phantom(96, sigma=0.05, seed=3, dtype=np.float32)
+    snap = syn.build_case(vol, 6.3, 3, (0.3, 0.7), lambda pos, tets, base: flat.tet_integrate(vol, tets, pos, want_hash=False)["mean"],
+                          jitter=0.3, seed=17)
+    ref = flat.tet_integrate(vol, snap["tet_nodes"], snap["pos"], want_hash=False)
+    img = pkg.Image3D(vol)
+    seg = pkg.SegmentFunction(img, 3)
+    seg.set_snapshot(snap)
+    for variant in (5, 12, 44, 60, 64):
+        seg.set_tet_variant(variant)
+        o = seg.tet_integrate(include_bound=True)
+        assert np.array_equal(o["vol"], ref["vol"])
+        # float voxel sums of <= 729 terms are exact in double whatever the order: bit-equal totals <=> same voxels
+        assert np.array_equal(o["total"], ref["total"]), variant
+    img.close()

@@ -15,3 +15,4 @@ from . import build as _build  # noqa: F401
 from .host import (DscGpuError, Image3D, SegmentFunction, FORCE_ATOMIC, FORCE_GATHER, MEAN_TET, MEAN_ZRAY, library_path, load_library,
                    host_sort_hits)  # noqa: F401
 from . import synthetic  # noqa: F401
+from . import distributed  # noqa: F401

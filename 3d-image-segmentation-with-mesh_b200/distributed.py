@@ -1,0 +1,35 @@
+"""Multi-GPU composition of one image-force evaluation.
+
+One process per GPU.  The volume and the mesh snapshot are replicated; the work is partitioned into contiguous ranges of
+tets (per-tet integration), interface faces (scatter force kernel) and nodes (gather force kernel).  The only exchanges
+are two all-reduces: the 3*nb_phase per-phase sums (the means are needed by the force pass) and the 3*n_nodes_buffer
+vertex-force array.  `evaluate` is written against two callables so that the same control flow runs with the CUDA
+library over NCCL on GPUs and with any stand-in compute over gloo in the CPU tests.
+"""
+import numpy as np
+
+
+def partition(n, world, rank):
+    """Contiguous range [begin, end) of rank `rank` when n items are split over `world` ranks (sizes differ by at most 1)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad world/rank")
+    return n * rank // world, n * (rank + 1) // world
+
+
+def partitions(n_tets, n_faces, n_nodes, world, rank):
+    return partition(n_tets, world, rank), partition(n_faces, world, rank), partition(n_nodes, world, rank)
+
+
+def evaluate(phase_sums_fn, forces_fn, nb_phase, all_reduce):
+    """One evaluation on this rank's partition.
+
+    phase_sums_fn() -> array [3*nb_phase] (total, sumsq, volume of this rank's tets)
+    forces_fn(mean) -> array [n_nodes_buffer, 3] holding this rank's contribution (zeros elsewhere)
+    all_reduce(x)   -> sums x over ranks in place (NCCL / gloo) and returns it
+    Returns (mean[nb_phase], forces) identical on every rank.
+    """
+    sums = all_reduce(phase_sums_fn())
+    total, volume = sums[:nb_phase], sums[2 * nb_phase:3 * nb_phase]
+    mean = total / volume
+    forces = all_reduce(forces_fn(mean))
+    return mean, forces

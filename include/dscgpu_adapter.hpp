@@ -1,0 +1,152 @@
+// dscgpu_adapter.hpp -- C++ host adapter between a live reference mesh and the C ABI (include/dscgpu.h).
+//
+// Header-only; compile it in a translation unit that already sees the reference's headers
+// (DEMO/segment_function.h -> DSC.h, is_mesh.h, image3d.h).  It does what SURVEY.md 8(b) item 6 asks for:
+//   * snapshot_from_dsc(dsc, snap): flattens the is_mesh/DSC complex through its public read-only getters, in ascending
+//     key order, into the SoA arrays of dscgpu_snapshot -- the same walk the reference's own loops do
+//     (tetrahedra_begin()/faces_begin(), DEMO/segment_function.cpp:1435, 1626; get_nodes/get_tets/get_label/get_pos,
+//     is_mesh/is_mesh.h:250-253, 625-679);
+//   * ImageEnergy: owns a dscgpu context for one image3d and offers drop-in bodies for
+//       segment_function::update_average_intensity   (DEMO/segment_function.cpp:1600-1764)
+//       segment_function::compute_external_force     (DEMO/segment_function.cpp:1425-1473)
+//       segment_function::compute_energy             (DEMO/segment_function.cpp:2331-2492)
+//     that write the reference's public result members (_mean_intensities, _total_intensities, _phase_volume, _forces).
+// INTEGRATION.md shows the three-line patch to DEMO/segment_function.cpp that routes segment() through it.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dscgpu.h"
+
+namespace dscgpu {
+
+struct Snapshot {
+    std::vector<double> pos;            // 3 * get_no_nodes_buffer()
+    std::vector<uint32_t> tet_key;      // raw keys of the valid tets, ascending
+    std::vector<uint32_t> tet_nodes;    // 4 per tet, get_nodes(t) order
+    std::vector<int32_t> tet_label;
+    std::vector<uint32_t> face_key;     // raw keys of the interface faces, ascending
+    std::vector<uint32_t> face_nodes;   // 3 per face, get_nodes(f) order
+    std::vector<uint32_t> face_tets;    // 2 per face: indices into the tet arrays, get_tets(f) order
+    std::vector<uint8_t> face_is_boundary;
+
+    dscgpu_snapshot view() const
+    {
+        dscgpu_snapshot s;
+        s.n_nodes_buffer = (uint32_t)(pos.size() / 3);
+        s.pos = pos.data();
+        s.n_tets = (uint32_t)tet_label.size();
+        s.tet_nodes = tet_nodes.data();
+        s.tet_label = tet_label.data();
+        s.n_faces = (uint32_t)face_is_boundary.size();
+        s.face_nodes = face_nodes.data();
+        s.face_tets = face_tets.data();
+        s.face_is_boundary = face_is_boundary.data();
+        return s;
+    }
+};
+
+// DSC is DSC::DeformableSimplicialComplex<> (or any ISMesh with the same getters).
+template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s)
+{
+    const unsigned nnb = dsc.get_no_nodes_buffer();
+    s.pos.assign(3 * (size_t)nnb, 0.0);
+    for (auto nit = dsc.nodes_begin(); nit != dsc.nodes_end(); nit++) {
+        const unsigned k = nit.key();
+        const auto p = dsc.get_pos(nit.key());
+        s.pos[3 * (size_t)k] = p[0]; s.pos[3 * (size_t)k + 1] = p[1]; s.pos[3 * (size_t)k + 2] = p[2];
+    }
+    std::vector<int32_t> tet_index(dsc.get_no_tets_buffer(), -1);
+    s.tet_key.clear(); s.tet_nodes.clear(); s.tet_label.clear();
+    for (auto tit = dsc.tetrahedra_begin(); tit != dsc.tetrahedra_end(); tit++) {
+        tet_index[tit.key()] = (int32_t)s.tet_key.size();
+        s.tet_key.push_back(tit.key());
+        const auto nids = dsc.get_nodes(tit.key());
+        for (int k = 0; k < 4; k++) s.tet_nodes.push_back(nids[k]);
+        s.tet_label.push_back(dsc.get_label(tit.key()));
+    }
+    s.face_key.clear(); s.face_nodes.clear(); s.face_tets.clear(); s.face_is_boundary.clear();
+    for (auto fit = dsc.faces_begin(); fit != dsc.faces_end(); fit++) {
+        if (!fit->is_interface()) continue;
+        s.face_key.push_back(fit.key());
+        const auto nids = dsc.get_nodes(fit.key());
+        for (int k = 0; k < 3; k++) s.face_nodes.push_back(nids[k]);
+        const auto &tids = dsc.get_tets(fit.key());
+        s.face_tets.push_back((uint32_t)tet_index[tids[0]]);
+        s.face_tets.push_back(tids.size() > 1 ? (uint32_t)tet_index[tids[1]] : DSCGPU_NO_TET);
+        s.face_is_boundary.push_back(fit->is_boundary() ? 1 : 0);
+    }
+}
+
+class Error : public std::runtime_error {
+public:
+    explicit Error(const std::string &m) : std::runtime_error(m) {}
+};
+
+// IMG is the reference's image3d; SEG its segment_function.
+template <class IMG, class SEG> class ImageEnergy {
+public:
+    // Uploads img._voxels (FP64, exactly the reference's values) and builds the z prefix-sum table on the device.
+    explicit ImageEnergy(IMG &img, int device = 0, int force_mode = DSCGPU_FORCE_GATHER) : force_mode_(force_mode)
+    {
+        const int dims[3] = {img._dim[0], img._dim[1], img._dim[2]};
+        check(dscgpu_ctx_create(&ctx_, device, dims, DSCGPU_F64, img._voxels.data()), "dscgpu_ctx_create");
+        check(dscgpu_build_sum_table(ctx_), "dscgpu_build_sum_table");
+    }
+    ~ImageEnergy() { dscgpu_ctx_destroy(ctx_); }
+    ImageEnergy(const ImageEnergy &) = delete;
+    ImageEnergy &operator=(const ImageEnergy &) = delete;
+
+    // Call after anything that changed the mesh (deform, relabel, adapt) and after update_vertex_boundary().
+    void refresh(SEG &seg)
+    {
+        snapshot_from_dsc(*seg._dsc, snap_);
+        dscgpu_snapshot v = snap_.view();
+        check(dscgpu_set_snapshot(ctx_, &v), "dscgpu_set_snapshot");
+    }
+
+    // Body of segment_function::update_average_intensity.
+    void update_average_intensity(SEG &seg)
+    {
+        dscgpu_phase_stats st;
+        check(dscgpu_zray_means(ctx_, seg.NB_PHASE, &st), "dscgpu_zray_means");
+        seg._mean_intensities.assign(st.mean, st.mean + seg.NB_PHASE);
+        seg._total_intensities.assign(st.total, st.total + seg.NB_PHASE);
+        seg._phase_volume.assign(st.volume, st.volume + seg.NB_PHASE);
+    }
+
+    // Body of segment_function::compute_external_force; _forces is sized get_no_nodes_buffer() and indexed by node key.
+    void compute_external_force(SEG &seg)
+    {
+        const size_t nnb = snap_.pos.size() / 3;
+        forces_.resize(3 * nnb);
+        check(dscgpu_face_forces(ctx_, seg.NB_PHASE, seg._mean_intensities.data(), force_mode_, forces_.data()), "dscgpu_face_forces");
+        seg._forces.resize(nnb);
+        for (size_t i = 0; i < nnb; i++) {
+            seg._forces[i][0] = forces_[3 * i]; seg._forces[i][1] = forces_[3 * i + 1]; seg._forces[i][2] = forces_[3 * i + 2];
+        }
+    }
+
+    // The two numbers of compute_energy's "=== Energy; area = data - area" line.
+    void compute_energy(SEG &seg, double *data, double *area)
+    {
+        check(dscgpu_zray_energy(ctx_, seg.NB_PHASE, seg._mean_intensities.data(), seg.m_alpha, nullptr, data, area), "dscgpu_zray_energy");
+    }
+
+    const Snapshot &snapshot() const { return snap_; }
+    dscgpu_ctx *ctx() { return ctx_; }
+
+private:
+    void check(int r, const char *what)
+    {
+        if (r != DSCGPU_OK) throw Error(std::string(what) + ": " + dscgpu_last_error(ctx_));
+    }
+    dscgpu_ctx *ctx_ = nullptr;
+    Snapshot snap_;
+    std::vector<double> forces_;
+    int force_mode_;
+};
+
+} // namespace dscgpu

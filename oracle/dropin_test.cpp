@@ -1,0 +1,159 @@
+// oracle/dropin_test.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// The drop-in demonstration: the UNMODIFIED reference sources (same objects as oracle/_ref/dsc_ref) and the product's
+// C ABI (libdscgpu.so, through include/dscgpu_adapter.hpp) in ONE process, on the same live is_mesh/DSC complex.
+// For the initial mesh and after every segment() iteration (deform + relabel + adapt make the mesh irregular) it runs
+//     reference: update_vertex_boundary(); update_average_intensity(); compute_external_force(); compute_energy()
+//     GPU      : adapter.refresh(); adapter.update_average_intensity(); adapter.compute_external_force(); compute_energy()
+// on the same segment_function object and compares the public result members:
+//     _phase_volume bit-exact, _total_intensities/_mean_intensities 1e-6 relative, _forces bit-exact when fed the
+//     reference's means (gather kernel keeps the reference's addition order) and 1e-6 with its own means, energy 1e-6.
+// Exit code 0 = parity.  Needs a CUDA device (run under tests/test_dropin_gpu.py on the GPU box).
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <memory>
+#include <iostream>
+#include <sstream>
+
+#include "segment_function.h"
+#include "tet_dis_coord.hpp"
+#include "dscgpu_adapter.hpp"
+
+double noise_level = 0;
+int num_images = 0;
+bool arg_b_build_table_origin = true;
+
+typedef DSC::DeformableSimplicialComplex<> dsc_class;
+
+struct Quiet {
+    std::streambuf *old;
+    std::ostringstream ss;
+    Quiet() { old = std::cout.rdbuf(ss.rdbuf()); }
+    ~Quiet() { std::cout.rdbuf(old); }
+};
+
+static std::unique_ptr<dsc_class> make_grid(const image3d &img, double edge)
+{   // UI::init_dsc, DEMO/user_interface.cpp:550-630
+    vec3 dsc_dim = img.dimension_v() + vec3(2 * edge);
+    int NX = round(dsc_dim[0] / edge) + 1, NY = round(dsc_dim[1] / edge) + 1, NZ = round(dsc_dim[2] / edge) + 1;
+    double dx = dsc_dim[0] / (double)(NX - 1), dy = dsc_dim[1] / (double)(NY - 1), dz = dsc_dim[2] / (double)(NZ - 1);
+    std::vector<vec3> points;
+    std::vector<int> tets;
+    for (int iz = 0; iz < NZ; iz++)
+        for (int iy = 0; iy < NY; iy++)
+            for (int ix = 0; ix < NX; ix++) points.push_back(vec3(ix * dx, iy * dy, iz * dz) - vec3(edge));
+#define IC(x, y, z) ((z) * NX * NY + (y) * NX + (x))
+    for (int iz = 0; iz < NZ - 1; iz++)
+        for (int iy = 0; iy < NY - 1; iy++)
+            for (int ix = 0; ix < NX - 1; ix++) {
+                int v[] = {IC(ix, iy, iz), IC(ix + 1, iy, iz), IC(ix + 1, iy + 1, iz), IC(ix, iy + 1, iz),
+                           IC(ix, iy, iz + 1), IC(ix + 1, iy, iz + 1), IC(ix + 1, iy + 1, iz + 1), IC(ix, iy + 1, iz + 1)};
+                int tt[] = {0, 4, 5, 7, 0, 7, 5, 1, 0, 1, 3, 7, 1, 5, 6, 7, 1, 6, 7, 3, 1, 2, 6, 3};
+                for (int i = 0; i < 24; i++) tets.push_back(v[tt[i]]);
+            }
+    std::vector<int> labels(tets.size() / 4, 0);
+    std::unique_ptr<dsc_class> dsc(new dsc_class(points, tets, labels));
+    dsc->set_avg_edge_length(edge);
+    return dsc;
+}
+
+static bool close_rel(double a, double b, double tol) { return std::fabs(a - b) <= tol * std::max(std::fabs(a), std::fabs(b)) + 1e-300; }
+
+int main(int argc, char **argv)
+{
+    if (argc < 7) { fprintf(stderr, "usage: dsc_dropin volume.u8 X Y Z edge iters [nb_phase alpha]\n"); return 2; }
+    const int X = atoi(argv[2]), Y = atoi(argv[3]), Z = atoi(argv[4]);
+    const double edge = atof(argv[5]);
+    const int iters = atoi(argv[6]);
+    segment_function seg;
+    seg.NB_PHASE = argc > 7 ? atoi(argv[7]) : 3;
+    seg.m_alpha = argc > 8 ? atof(argv[8]) : 0.001;
+    seg.VARIATION_THRES_FOR_RELABELING = 0.5;
+    {
+        size_t n = (size_t)X * Y * Z;
+        std::vector<uint8_t> b(n);
+        FILE *f = fopen(argv[1], "rb");
+        if (!f || fread(b.data(), 1, n, f) != n) { fprintf(stderr, "cannot read volume\n"); return 2; }
+        fclose(f);
+        seg._img._dim[0] = X; seg._img._dim[1] = Y; seg._img._dim[2] = Z;
+        seg._img._voxels.resize(n);
+        for (size_t i = 0; i < n; i++) seg._img._voxels[i] = (double)b[i] / 255.0;
+        set_size();
+        seg._img.build_sum_table();
+    }
+    std::unique_ptr<dsc_class> dsc = make_grid(seg._img, edge);
+    dsc->set_min_edge_length(edge);
+    seg.set_min_edge_length(edge);
+    {   // UI::set_dsc_boundary_layer, DEMO/user_interface.cpp:441-462
+        std::vector<bool> bound(dsc->get_no_tets_buffer(), false);
+        for (auto nit = dsc->nodes_begin(); nit != dsc->nodes_end(); nit++)
+            if (nit->is_boundary()) for (auto t : dsc->get_tets(nit.key())) bound[t] = true;
+        for (auto tit = dsc->tetrahedra_begin(); tit != dsc->tetrahedra_end(); tit++) if (!bound[tit.key()]) dsc->set_label(tit.key(), 1);
+    }
+    seg._dsc = dsc.get();
+    { Quiet q; seg.initialization_discrete_opt(); }
+
+    int failures = 0;
+    try {
+        dscgpu::ImageEnergy<image3d, segment_function> gpu(seg._img, 0);
+        for (int it = 0; it <= iters; it++) {
+            // ---- reference ----
+            std::string log;
+            {
+                Quiet q;
+                std::cout.precision(17);
+                seg.update_vertex_boundary();
+                seg.update_average_intensity();
+                seg.compute_external_force();
+                seg.compute_energy();
+                log = q.ss.str();
+            }
+            double e_data_ref = 0, e_area_ref = 0;
+            size_t p = log.rfind("=== Energy; area = ");
+            if (p != std::string::npos) sscanf(log.c_str() + p, "=== Energy; area = %lf - %lf", &e_data_ref, &e_area_ref);
+            const std::vector<double> mean_ref = seg._mean_intensities, total_ref = seg._total_intensities, vol_ref = seg._phase_volume;
+            const std::vector<vec3> forces_ref = seg._forces;
+            // ---- GPU, same object, same mesh ----
+            gpu.refresh(seg);
+            gpu.compute_external_force(seg); // with the reference's means still in seg._mean_intensities: bit-exact bar
+            size_t bad_f = 0;
+            if (seg._forces.size() != forces_ref.size()) bad_f = 1;
+            else for (size_t i = 0; i < forces_ref.size(); i++) for (int c = 0; c < 3; c++) if (seg._forces[i][c] != forces_ref[i][c]) bad_f++;
+            gpu.update_average_intensity(seg);
+            bool ok = bad_f == 0;
+            for (int k = 0; k < seg.NB_PHASE; k++) {
+                if (seg._phase_volume[k] != vol_ref[k]) ok = false;
+                if (!close_rel(seg._total_intensities[k], total_ref[k], 1e-6)) ok = false;
+                if (!close_rel(seg._mean_intensities[k], mean_ref[k], 1e-6)) ok = false;
+            }
+            gpu.compute_external_force(seg); // with the GPU's own means: tolerance bar
+            double fmax = 0, dmax = 0;
+            for (size_t i = 0; i < forces_ref.size(); i++) for (int c = 0; c < 3; c++) {
+                fmax = std::max(fmax, std::fabs(forces_ref[i][c]));
+                dmax = std::max(dmax, std::fabs(forces_ref[i][c] - seg._forces[i][c]));
+            }
+            if (dmax > 1e-6 * fmax) ok = false;
+            double e_data = 0, e_area = 0;
+            gpu.compute_energy(seg, &e_data, &e_area);
+            if (!close_rel(e_data, e_data_ref, 1e-6) || !close_rel(e_area, e_area_ref, 1e-6)) ok = false;
+            printf("iter %d: %zu tets %zu interface faces | phase_volume %s | forces(ref means) %zu mismatching components | "
+                   "forces(gpu means) max abs diff %.3g of %.3g | energy %.10g/%.10g vs %.10g/%.10g | %s\n",
+                   it, gpu.snapshot().tet_label.size(), gpu.snapshot().face_is_boundary.size(),
+                   (seg._phase_volume == vol_ref) ? "bit-exact" : "DIFFERENT", bad_f, dmax, fmax, e_data, e_area, e_data_ref, e_area_ref,
+                   ok ? "OK" : "FAIL");
+            if (!ok) failures++;
+            // restore the reference's results and let the reference move the mesh
+            seg._mean_intensities = mean_ref; seg._total_intensities = total_ref; seg._phase_volume = vol_ref; seg._forces = forces_ref;
+            if (it < iters) { Quiet q; seg.segment(); }
+        }
+    } catch (const std::exception &e) {
+        fprintf(stderr, "drop-in test failed: %s\n", e.what());
+        return 3;
+    }
+    printf("%s\n", failures ? "DROP-IN PARITY FAILED" : "DROP-IN PARITY OK");
+    return failures ? 1 : 0;
+}

@@ -15,6 +15,10 @@
 #pragma once
 #include "dsc_device.cuh"
 
+#ifndef W2_MIN_BLOCKS
+#define W2_MIN_BLOCKS 3
+#endif
+
 namespace dsc {
 
 constexpr int kMaxPhase = 8;
@@ -143,6 +147,8 @@ struct TetArgs {
     double c[kMaxPhase];
     double *tet_total, *tet_vol, *tet_mean, *tet_energy, *tet_variation;
     const float4 *tet_bary_f;        // the same table rounded to float (FP32 filter path)
+    const float4 *tet_lat;           // lattice form of the table: (a1, a2, a3, eps) per row, see tet_integrate_w2_kernel
+    int want_sq;                     // fill the per-label second moment (costs one DFMA per sample)
     cudaTextureObject_t tex;         // 3-D texture over the volume (0 when unavailable)
     double *partials;                // [gridDim.x][3*kMaxPhase]: total, sumsq, volume
     unsigned long long *sample_count; // algorithmic samples processed (for the roofline figure)
@@ -503,6 +509,531 @@ __global__ void __launch_bounds__(256) tet_integrate_g_kernel(const TetArgs a)
 }
 
 // -------------------------------------------------------------------------------------------------
+// Warp-level two-phase form with origin-relative lattice coordinates (variant 128).
+//
+// A warp takes a tile of 32 consecutive tets.
+//   phase A  lane <-> tet: label, ids, FP64 positions -> exact volume and sample level (as the reference), then the
+//            record of the FP32 filter: integer origin O = floor(min corner), Q_k = P_k - O (exact in FP64), and
+//            Q0 - 0.5, E_k = (Q_k - Q_0) / (4n) rounded to float.  Records go to a per-warp slab of shared memory.
+//   phase B  8 lanes <-> tet (4 tets at a time, each group walks its own 8 tets of the tile): lane j takes table rows
+//            j, j+8, ... in batches of 4 (indices first, then 4 gathers in flight, then accumulate).
+// Lattice form of the sample position: the reference's 6-decimal weights are b_k = a_k/(4n) + eta_k with integer a_k,
+// sum a_k = 4n, |eta_k| <= 5e-7, eps = sum b_k - 1 (checked on the host when the table is built).  Hence, exactly,
+//     sum_k b_k P_k - O = Q_0 + sum_{k=1..3} a_k E_k + eps * O + tau,   |tau| <= 4 * 5e-7 * Rmax,  Rmax = max |Q_k|
+// so the FP32 path needs 12 FFMA per sample and its inputs are small numbers (|Q| < ~20 instead of ~512), which shrinks
+// the error bound -- and with it the fraction of samples that must be re-evaluated exactly -- by two orders of magnitude:
+//     |q - r| <= (41 Rmax + 5) * 2^-24 ;  delta = (48 Rmax + 8) * 2^-24.
+// floor() uses the 1.5*2^23 trick (no F2I), the voxel is widened with integer ops (no F2F): the XU pipe stays idle.
+// Tets touching the volume border, very large tets (n > kSmemLevels) and tets wider than 100 voxels use the exact path.
+// -------------------------------------------------------------------------------------------------
+template <typename VoxT, bool WANT_SQ, bool PER_TET>
+__global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(const TetArgs a)
+{
+    constexpr int G = 8, U = 4;
+    __shared__ float4 s_lat[kSmemRows];        // (a1, a2, a3, eps) per table row
+    __shared__ double2 s_tabd[2 * kSmemRows];  // exact rows for the fallback
+    __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0-.5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
+    __shared__ int2 w_m[8][32];                // meta, (O_linear - fold)
+    __shared__ double w_v[8][32];
+    __shared__ uint4 w_nd[8][32];
+    for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
+    for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_lat[i] = a.tet_lat[i];
+    __syncthreads();
+
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const int XYi = X * Y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane_g = lane & (G - 1), grp = lane >> 3;
+    const unsigned n_work = a.tet_end - a.tet_begin;
+    const unsigned n_tiles = (n_work + 31) / 32;
+    const unsigned total_warps = gridDim.x * 8;
+    const float MAGIC = 12582912.0f; // 1.5 * 2^23
+    const unsigned fold = 0x4B400000u * (unsigned)(XYi + X + 1);
+
+    double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane_g + 1
+    unsigned long long nsamp = 0;
+
+    for (unsigned tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += total_warps) {
+        const unsigned base_t = a.tet_begin + tile * 32;
+        const int nb = (int)min(32u, a.tet_end - base_t);
+        __syncwarp();
+        // ---------------- phase A: lane <-> tet ----------------
+        {
+            int meta = 0;
+            if (lane < nb) {
+                const unsigned t = base_t + lane;
+                const int label = __ldg(a.mesh.tet_label + t);
+                const bool active = a.include_bound || label != 0;
+                meta = label & 0xff;
+                if (active) {
+                    const uint4 nd = __ldg(a.mesh.tet_nodes + t);
+                    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                    const double v = tet_volume(p0, p1, p2, p3);
+                    const int L = tet_level(v);
+                    const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
+                    const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
+                    const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
+                    // strictly inside the volume with a margin: no sample can leave [1, dim-1), so no bounds checks, no negatives
+                    const bool interior = lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5;
+                    const double ox = floor(lox), oy = floor(loy), oz = floor(loz);
+                    const double rmax = fmax(fmax(hix - ox, hiy - oy), hiz - oz);
+                    const bool fast = interior && L < kSmemLevels && rmax < 100.0;
+                    if (fast) {
+                        const double inv4n = 1.0 / (double)(4 * (L + 1));
+                        const double q0x = p0.x - ox, q0y = p0.y - oy, q0z = p0.z - oz;
+                        w_q0[warp][lane] = make_float4((float)(q0x - 0.5), (float)(q0y - 0.5), (float)(q0z - 0.5),
+                                                       0.5f - (48.0f * (float)rmax + 8.0f) * 5.9604644775390625e-08f);
+                        w_e1[warp][lane] = make_float4((float)((p1.x - p0.x) * inv4n), (float)((p1.y - p0.y) * inv4n), (float)((p1.z - p0.z) * inv4n), (float)ox);
+                        w_e2[warp][lane] = make_float4((float)((p2.x - p0.x) * inv4n), (float)((p2.y - p0.y) * inv4n), (float)((p2.z - p0.z) * inv4n), (float)oy);
+                        w_e3[warp][lane] = make_float4((float)((p3.x - p0.x) * inv4n), (float)((p3.y - p0.y) * inv4n), (float)((p3.z - p0.z) * inv4n), (float)oz);
+                        const unsigned olin = (unsigned)((int)oz * XYi + (int)oy * X + (int)ox) - fold;
+                        w_m[warp][lane] = make_int2(meta | (L << 8) | (1 << 12) | (1 << 13), (int)olin);
+                    } else {
+                        w_m[warp][lane] = make_int2(meta | (L << 8) | (1 << 12), 0);
+                    }
+                    w_v[warp][lane] = v;
+                    w_nd[warp][lane] = nd;
+                } else {
+                    w_m[warp][lane] = make_int2(meta, 0);
+                    if (a.tet_total) a.tet_total[t] = -1.0;
+                    if (a.tet_vol) a.tet_vol[t] = -1.0;
+                    if (a.tet_mean) a.tet_mean[t] = -1.0;
+                }
+            } else {
+                w_m[warp][lane] = make_int2(0, 0);
+            }
+        }
+        __syncwarp();
+        // ---------------- phase B: 8 lanes <-> tet; group grp walks tets grp, grp+4, ... of the tile ----------------
+        for (int r = 0; r < 8; r++) {
+            const int j = r * 4 + grp;
+            const int2 mm = w_m[warp][j];
+            const int meta = mm.x;
+            const bool active = (meta & (1 << 12)) != 0;
+            const int label = meta & 0xff;
+            const int L = (meta >> 8) & 0xf;
+            const int n3 = active ? (L + 1) * (L + 1) * (L + 1) : 0;
+            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+            double s = 0, sq = 0;
+            unsigned long long isum = 0, isq = 0;
+            auto add_voxel = [&](VoxT val) {
+                if constexpr (VoxTraits<VoxT>::integral) {
+                    const unsigned q = (unsigned)val;
+                    isum += q;
+                    if (WANT_SQ) isq += (unsigned long long)q * q;
+                } else {
+                    double I;
+                    if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val);
+                    else I = (double)val;
+                    s += I;
+                    if (WANT_SQ) sq = fma(I, I, sq); // second moment: tolerance quantity, fused on purpose
+                }
+            };
+            if (meta & (1 << 13)) {
+                const float4 q0 = w_q0[warp][j], e1 = w_e1[warp][j], e2 = w_e2[warp][j], e3 = w_e3[warp][j];
+                const float thr = q0.w;
+                const unsigned obase = (unsigned)mm.y;
+                const float4 *__restrict__ tl = s_lat + off;
+                const int last = n3 - 1;
+                for (int base = lane_g; base < n3; base += G * U) {
+                    int idx[U];
+                    unsigned unsafe = 0;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = base + u * G;
+                        const bool ok = i <= last;
+                        const float4 c = tl[min(i, last)];
+                        const float qx = fmaf(c.z, e3.x, fmaf(c.y, e2.x, fmaf(c.x, e1.x, fmaf(c.w, e1.w, q0.x))));
+                        const float qy = fmaf(c.z, e3.y, fmaf(c.y, e2.y, fmaf(c.x, e1.y, fmaf(c.w, e2.w, q0.y))));
+                        const float qz = fmaf(c.z, e3.z, fmaf(c.y, e2.z, fmaf(c.x, e1.z, fmaf(c.w, e3.w, q0.z))));
+                        const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
+                        const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
+                        const int lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) + obase);
+                        idx[u] = ok ? lin : -1;
+                        if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) unsafe |= 1u << u;
+                    }
+                    if (unsafe) { // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
+                        const uint4 nd = w_nd[warp][j];
+                        const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                        const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+#pragma unroll
+                        for (int u = 0; u < U; u++)
+                            if (unsafe & (1u << u)) {
+                                const int i = base + u * G;
+                                const double2 b01 = s_tabd[2 * (off + i)], b23 = s_tabd[2 * (off + i) + 1];
+                                const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                                const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                                const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                                idx[u] = iz * XYi + iy * X + ix; // interior tet: always in range
+                            }
+                    }
+                    VoxT val[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
+#pragma unroll
+                    for (int u = 0; u < U; u++) add_voxel(val[u]);
+                }
+            } else if (active) {
+                // exact path (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491)
+                const uint4 nd = w_nd[warp][j];
+                const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+                for (int base = lane_g; base < n3; base += G * U) {
+                    int idx[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = base + u * G;
+                        idx[u] = -1;
+                        if (i < n3) {
+                            const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
+                            const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                            const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                            const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                            if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) idx[u] = iz * XYi + iy * X + ix;
+                        }
+                    }
+                    VoxT val[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
+#pragma unroll
+                    for (int u = 0; u < U; u++) add_voxel(val[u]);
+                }
+            }
+            if constexpr (VoxTraits<VoxT>::integral) {
+                const double dn = VoxTraits<VoxT>::denom();
+                s = (double)isum / dn;
+                if (WANT_SQ) sq = (double)isq / (dn * dn);
+            }
+#pragma unroll
+            for (int m = G / 2; m >= 1; m >>= 1) {
+                s += shfl_xor_d(s, m);
+                if (WANT_SQ) sq += shfl_xor_d(sq, m);
+            }
+            if (active) {
+                const double v = w_v[warp][j];
+                const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
+                const double tsq = WANT_SQ ? sq * v / (double)n3 : 0.0;
+                if (lane_g == 0) {
+                    nsamp += (unsigned long long)n3;
+                    if (PER_TET) {
+                        const unsigned t = base_t + j;
+                        if (a.tet_total) a.tet_total[t] = tot;
+                        if (a.tet_vol) a.tet_vol[t] = v;
+                        if (a.tet_mean) a.tet_mean[t] = tot / v;
+                    }
+                }
+                if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
+                    acc_tot += tot;
+                    acc_sq += tsq;
+                    acc_vol += v;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= G; m >>= 1) {
+        acc_tot += shfl_xor_d(acc_tot, m);
+        acc_sq += shfl_xor_d(acc_sq, m);
+        acc_vol += shfl_xor_d(acc_vol, m);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
+    __shared__ double sm[8][3 * kMaxPhase];
+    if (lane < kMaxPhase) {
+        sm[warp][lane] = acc_tot;
+        sm[warp][kMaxPhase + lane] = acc_sq;
+        sm[warp][2 * kMaxPhase + lane] = acc_vol;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * kMaxPhase) {
+        double r = 0;
+        for (int wdx = 0; wdx < 8; wdx++) r += sm[wdx][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
+    }
+    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+}
+
+// -------------------------------------------------------------------------------------------------
+// w3 (variant 256): w2 with the per-sample instruction count cut further and independent group progression.
+//   * the float chain starts at Q0 + 128 with O = floor(min corner) - 1, so the result t lies in [128, 256): its
+//     mantissa IS the fixed-point relative coordinate with 16 fraction bits.  floor = byte 2 of the bit pattern (one
+//     PRMT), the distance to the nearest voxel boundary is the low 16 bits: no FADD/F2I at all.  A sample is "unsafe"
+//     when its fraction is within K units of 2^-16 of an integer; K covers the c0 rounding (0.5), four FFMA roundings
+//     at ulp(t) = 2^-16 (2.0), the float rounding of E_k (6*2^-24*R) and the lattice perturbation tau (4*4.45e-7*R),
+//     R = Rmax + 1:  K = ceil(3 + 0.141 R).
+//   * each group of 8 lanes walks its own 8 tets of the tile at its own pace (a 27-sample tet next to a 64-sample
+//     tet no longer idles for a batch); group-local shuffles use the group's lane mask.
+//   * the widened voxel uses one special-value test per batch; the second moment is optional.
+// -------------------------------------------------------------------------------------------------
+template <typename VoxT, bool WANT_SQ, bool PER_TET>
+__global__ void __launch_bounds__(256, 3) tet_integrate_w3_kernel(const TetArgs a)
+{
+    constexpr int G = 8, U = 4;
+    __shared__ float4 s_lat[kSmemRows];
+    __shared__ double2 s_tabd[2 * kSmemRows];
+    __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0+128 xyz, K<<16 as bits) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
+    __shared__ int2 w_m[8][32];               // meta, O_linear
+    __shared__ double w_v[8][32];
+    __shared__ uint4 w_nd[8][32];
+    for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
+    for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_lat[i] = a.tet_lat[i];
+    __syncthreads();
+
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const int XYi = X * Y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane_g = lane & (G - 1), grp = lane >> 3;
+    const unsigned gmask = 0xFFu << (grp * 8);
+    const unsigned n_work = a.tet_end - a.tet_begin;
+    const unsigned n_tiles = (n_work + 31) / 32;
+    const unsigned total_warps = gridDim.x * 8;
+
+    double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane_g + 1
+    unsigned long long nsamp = 0;
+
+    for (unsigned tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += total_warps) {
+        const unsigned base_t = a.tet_begin + tile * 32;
+        const int nb = (int)min(32u, a.tet_end - base_t);
+        __syncwarp();
+        // ---------------- phase A: lane <-> tet ----------------
+        {
+            int meta = 0;
+            int olin = 0;
+            if (lane < nb) {
+                const unsigned t = base_t + lane;
+                const int label = __ldg(a.mesh.tet_label + t);
+                const bool active = a.include_bound || label != 0;
+                meta = label & 0xff;
+                if (active) {
+                    const uint4 nd = __ldg(a.mesh.tet_nodes + t);
+                    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                    const double v = tet_volume(p0, p1, p2, p3);
+                    const int L = tet_level(v);
+                    const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
+                    const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
+                    const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
+                    const bool interior = lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5;
+                    const double ox = floor(lox) - 1.0, oy = floor(loy) - 1.0, oz = floor(loz) - 1.0; // relative coordinates >= 1
+                    const double R = fmax(fmax(hix - ox, hiy - oy), hiz - oz) + 1.0;
+                    const bool fast = interior && L < kSmemLevels && R < 120.0;
+                    meta |= (L << 8) | (1 << 12);
+                    if (fast) {
+                        const double inv4n = 1.0 / (double)(4 * (L + 1));
+                        const unsigned K = (unsigned)ceil(3.0 + 0.141 * R);
+                        w_q0[warp][lane] = make_float4((float)((p0.x - ox) + 128.0), (float)((p0.y - oy) + 128.0), (float)((p0.z - oz) + 128.0), __uint_as_float(K << 16));
+                        w_e1[warp][lane] = make_float4((float)((p1.x - p0.x) * inv4n), (float)((p1.y - p0.y) * inv4n), (float)((p1.z - p0.z) * inv4n), (float)ox);
+                        w_e2[warp][lane] = make_float4((float)((p2.x - p0.x) * inv4n), (float)((p2.y - p0.y) * inv4n), (float)((p2.z - p0.z) * inv4n), (float)oy);
+                        w_e3[warp][lane] = make_float4((float)((p3.x - p0.x) * inv4n), (float)((p3.y - p0.y) * inv4n), (float)((p3.z - p0.z) * inv4n), (float)oz);
+                        olin = (int)oz * XYi + (int)oy * X + (int)ox;
+                        meta |= 1 << 13;
+                    }
+                    w_v[warp][lane] = v;
+                    w_nd[warp][lane] = nd;
+                } else {
+                    if (a.tet_total) a.tet_total[t] = -1.0;
+                    if (a.tet_vol) a.tet_vol[t] = -1.0;
+                    if (a.tet_mean) a.tet_mean[t] = -1.0;
+                }
+            }
+            w_m[warp][lane] = make_int2(meta, olin);
+        }
+        __syncwarp();
+        // ---------------- phase B: each group walks tets grp, grp+4, ... of the tile at its own pace ----------------
+        int r = 0;          // next tet slot of this group
+        bool have = false;  // a tet is in progress
+        int j = 0, n3 = 0, off = 0, base = 0, label = 0;
+        bool fastp = false;
+        float4 q0 = make_float4(0, 0, 0, 0), e1 = q0, e2 = q0, e3 = q0;
+        int obase = 0;
+        double s = 0, sq = 0;
+        unsigned long long isum = 0, isq = 0;
+        while (true) {
+            if (!have) {
+                while (r < 8) {
+                    const int2 mm = w_m[warp][r * 4 + grp];
+                    if (mm.x & (1 << 12)) {
+                        j = r * 4 + grp;
+                        label = mm.x & 0xff;
+                        const int L = (mm.x >> 8) & 0xf;
+                        n3 = (L + 1) * (L + 1) * (L + 1);
+                        off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+                        fastp = (mm.x & (1 << 13)) != 0;
+                        obase = mm.y;
+                        if (fastp) { q0 = w_q0[warp][j]; e1 = w_e1[warp][j]; e2 = w_e2[warp][j]; e3 = w_e3[warp][j]; }
+                        base = lane_g;
+                        s = 0; sq = 0; isum = 0; isq = 0;
+                        have = true;
+                        r++;
+                        break;
+                    }
+                    r++;
+                }
+            }
+            if (!__any_sync(0xffffffffu, have)) break;
+            if (have) {
+                int idx[U];
+                if (fastp) {
+                    const unsigned kk = __float_as_uint(q0.w); // K << 16
+                    const float4 *__restrict__ tl = s_lat + off;
+                    const int last = n3 - 1;
+                    unsigned worst = 0xffffffffu;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = base + u * G;
+                        const float4 c = tl[min(i, last)];
+                        const float tx = fmaf(c.z, e3.x, fmaf(c.y, e2.x, fmaf(c.x, e1.x, fmaf(c.w, e1.w, q0.x))));
+                        const float ty = fmaf(c.z, e3.y, fmaf(c.y, e2.y, fmaf(c.x, e1.y, fmaf(c.w, e2.w, q0.y))));
+                        const float tz = fmaf(c.z, e3.z, fmaf(c.y, e2.z, fmaf(c.x, e1.z, fmaf(c.w, e3.w, q0.z))));
+                        const unsigned ux = __float_as_uint(tx), uy = __float_as_uint(ty), uz = __float_as_uint(tz);
+                        // fraction field (16 bits) shifted to the top, biased by K: small value <=> within K units of an integer
+                        const unsigned fx = ux * 65536u + kk, fy = uy * 65536u + kk, fz = uz * 65536u + kk;
+                        const unsigned m = min(min(fx, fy), fz);
+                        const int lin = (int)(__byte_perm(uz, 0, 0x4442) * (unsigned)XYi + __byte_perm(uy, 0, 0x4442) * (unsigned)X + __byte_perm(ux, 0, 0x4442)) + obase;
+                        const bool ok = i <= last;
+                        idx[u] = ok ? lin : -1;
+                        worst = ok ? min(worst, m) : worst;
+                    }
+                    if (worst < 2u * kk) { // some coordinate within K*2^-16 of a voxel boundary: exact reference arithmetic decides
+                        const uint4 nd = w_nd[warp][j];
+                        const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                        const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            const int i = base + u * G;
+                            if (i <= last) {
+                                const double2 b01 = s_tabd[2 * (off + i)], b23 = s_tabd[2 * (off + i) + 1];
+                                const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                                const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                                const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                                idx[u] = iz * XYi + iy * X + ix; // interior tet: always in range
+                            }
+                        }
+                    }
+                } else {
+                    // exact path (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491)
+                    const uint4 nd = w_nd[warp][j];
+                    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = base + u * G;
+                        idx[u] = -1;
+                        if (i < n3) {
+                            const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
+                            const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                            const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                            const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                            if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) idx[u] = iz * XYi + iy * X + ix;
+                        }
+                    }
+                }
+                VoxT val[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
+                if constexpr (VoxTraits<VoxT>::integral) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const unsigned q = (unsigned)val[u];
+                        isum += q;
+                        if (WANT_SQ) isq += (unsigned long long)q * q;
+                    }
+                } else if constexpr (sizeof(VoxT) == 4) {
+                    // exact widening with integer ops; one test per batch for zeros / denormals / inf / nan (exponent 0 or 255)
+                    unsigned bits[U];
+                    bool special = false;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        bits[u] = __float_as_uint((float)val[u]);
+                        special |= ((bits[u] + 0x00800000u) & 0x7f000000u) == 0u;
+                    }
+                    if (!special) {
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            const unsigned hi = (((bits[u] & 0x7fffffffu) >> 3) + 0x38000000u) | (bits[u] & 0x80000000u);
+                            const double I = __hiloint2double((int)hi, (int)(bits[u] << 29));
+                            s += I;
+                            if (WANT_SQ) sq = fma(I, I, sq);
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            const double I = (double)(float)val[u];
+                            s += I;
+                            if (WANT_SQ) sq = fma(I, I, sq);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const double I = (double)val[u];
+                        s += I;
+                        if (WANT_SQ) sq = fma(I, I, sq);
+                    }
+                }
+                base += G * U;
+                if (base - lane_g >= n3) { // tet finished: group reduction and bookkeeping (the 8 lanes of the group are converged)
+                    if constexpr (VoxTraits<VoxT>::integral) {
+                        const double dn = VoxTraits<VoxT>::denom();
+                        s = (double)isum / dn;
+                        if (WANT_SQ) sq = (double)isq / (dn * dn);
+                    }
+#pragma unroll
+                    for (int m = G / 2; m >= 1; m >>= 1) {
+                        s += __shfl_xor_sync(gmask, s, m);
+                        if (WANT_SQ) sq += __shfl_xor_sync(gmask, sq, m);
+                    }
+                    const double v = w_v[warp][j];
+                    const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
+                    const double tsq = WANT_SQ ? sq * v / (double)n3 : 0.0;
+                    if (lane_g == 0) {
+                        nsamp += (unsigned long long)n3;
+                        if (PER_TET) {
+                            const unsigned t = base_t + j;
+                            if (a.tet_total) a.tet_total[t] = tot;
+                            if (a.tet_vol) a.tet_vol[t] = v;
+                            if (a.tet_mean) a.tet_mean[t] = tot / v;
+                        }
+                    }
+                    if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
+                        acc_tot += tot;
+                        acc_sq += tsq;
+                        acc_vol += v;
+                    }
+                    have = false;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= G; m >>= 1) {
+        acc_tot += shfl_xor_d(acc_tot, m);
+        acc_sq += shfl_xor_d(acc_sq, m);
+        acc_vol += shfl_xor_d(acc_vol, m);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
+    __shared__ double sm[8][3 * kMaxPhase];
+    if (lane < kMaxPhase) {
+        sm[warp][lane] = acc_tot;
+        sm[warp][kMaxPhase + lane] = acc_sq;
+        sm[warp][2 * kMaxPhase + lane] = acc_vol;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * kMaxPhase) {
+        double rr = 0;
+        for (int wdx = 0; wdx < 8; wdx++) rr += sm[wdx][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = rr;
+    }
+    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+}
+
+// -------------------------------------------------------------------------------------------------
 // Two-phase CTA form (the default hot path): setup once per tet, sampling with a warp per tet.
 //
 // Each CTA walks batches of kBatch consecutive tets:
@@ -523,6 +1054,9 @@ __global__ void __launch_bounds__(256) tet_integrate_g_kernel(const TetArgs a)
 // float is widened to double with integer ops.
 // -------------------------------------------------------------------------------------------------
 constexpr int kBatch = 256;
+#ifndef W2_MIN_BLOCKS
+#define W2_MIN_BLOCKS 3
+#endif
 
 template <typename VoxT, int PMAX, bool PER_TET>
 __global__ void __launch_bounds__(256) tet_integrate_ab_kernel(const TetArgs a)
@@ -1063,6 +1597,179 @@ template <typename VoxT> __global__ void __launch_bounds__(128) force_gather_ker
     a.forces[3 * (size_t)v + 1] = fy;
     a.forces[3 * (size_t)v + 2] = fz;
     if (ng) atomicAdd(a.gauss_count, ng);
+}
+
+// Warp-per-node gather (default): same result as force_gather_kernel, bit for bit, with the work of a node spread over
+// the warp.  Lane l evaluates incident face l of the node (normal, area, Gauss set, trilinear samples) and stores its
+// per-Gauss-point addends fv*coord to shared memory; lanes 0..2 then add the x/y/z components in the reference's order
+// (faces ascending, Gauss points in table order).  Only nodes that have interface faces are visited (active list built
+// with the CSR on the host); the force array is zeroed beforehand.
+struct ForceWarpArgs {
+    VolumeView vol;
+    MeshView mesh;
+    int nb_phase;
+    const double *mean;
+    double *forces;
+    const unsigned *active_nodes;
+    unsigned begin, end; // range in the active list
+    unsigned long long *gauss_count;
+};
+
+template <typename VoxT> __global__ void __launch_bounds__(128) force_warp_kernel(const ForceWarpArgs a)
+{
+    __shared__ double slab[4][32][12][3];
+    __shared__ int ng_s[4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned item = a.begin + blockIdx.x * 4 + warp;
+    if (item >= a.end) return;
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const unsigned v = __ldg(a.active_nodes + item);
+    const unsigned e0 = __ldg(a.mesh.node_off + v), e1 = __ldg(a.mesh.node_off + v + 1);
+    double acc = 0; // lanes 0..2: x, y, z of the node's force
+    unsigned long long ngc = 0;
+    for (unsigned eb = e0; eb < e1; eb += 32) {
+        const unsigned e = eb + lane;
+        int ng = 0;
+        if (e < e1) {
+            const unsigned inc = __ldg(a.mesh.node_inc + e);
+            const unsigned f = inc >> 2, corner = inc & 3u;
+            FaceGeom g;
+            unsigned n[3];
+            if (face_setup(a.mesh, f, a.nb_phase, a.mean, g, n)) {
+                for (int q = c_gauss_off[g.gs]; q < c_gauss_off[g.gs + 1]; q++) {
+                    const double w = c_gauss[4 * q], b0 = c_gauss[4 * q + 1], b1 = c_gauss[4 * q + 2], b2 = c_gauss[4 * q + 3];
+                    const V3 p = add(add(mul(g.p[0], b0), mul(g.p[1], b1)), mul(g.p[2], b2)); // get_coord_tri
+                    const double I = fetch_trilinear(vol, a.vol.X, a.vol.Y, a.vol.Z, p);
+                    const V3 fv = mul(g.norm, (2 * I - g.c0 - g.c1) * (g.c0 - g.c1) * w * g.area);
+                    const double bc = corner == 0 ? b0 : (corner == 1 ? b1 : b2);
+                    slab[warp][lane][ng][0] = fv.x * bc;
+                    slab[warp][lane][ng][1] = fv.y * bc;
+                    slab[warp][lane][ng][2] = fv.z * bc;
+                    ng++;
+                }
+                if (corner == 0) ngc += (unsigned long long)ng;
+            }
+        }
+        ng_s[warp][lane] = ng;
+        __syncwarp();
+        if (lane < 3) {
+            const int cnt = (int)min(32u, e1 - eb);
+            for (int l = 0; l < cnt; l++) {
+                const int m = ng_s[warp][l];
+                for (int q = 0; q < m; q++) acc += slab[warp][l][q][lane];
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < 3) a.forces[3 * (size_t)v + lane] = acc;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) ngc += __shfl_xor_sync(0xffffffffu, ngc, m);
+    if (lane == 0 && ngc) atomicAdd(a.gauss_count, ngc);
+}
+
+// Two-kernel deterministic gather (default):
+//   force_face_kernel  one thread per interface face: normal, area, Gauss set, and for every Gauss point the vector
+//                      f = Norm * ((2I - c0 - c1)(c0 - c1) w area) exactly as the reference forms it (:1463-1465),
+//                      stored face-major (12 slots of 3 doubles per face) together with the Gauss-set index;
+//   force_node_kernel  one thread per node that has interface faces: walks its CSR list (faces ascending) and adds
+//                      f * c.coord[corner] Gauss point by Gauss point -- the reference's addition order (:1466-1467),
+//                      so _forces is bit-identical, without atomics and independent of the GPU count.
+// All faces' dependent load chains run concurrently (one thread each), and the node pass only reads the compact f buffer.
+struct ForceFaceArgs {
+    VolumeView vol;
+    MeshView mesh;
+    int nb_phase;
+    const double *mean;
+    double *fbuf;        // [n_faces][12][3]
+    signed char *fset;   // [n_faces] Gauss set index, -1 = face skipped
+    unsigned begin, end; // face range
+    unsigned long long *gauss_count;
+};
+
+template <typename VoxT> __global__ void __launch_bounds__(128) force_face_kernel(const ForceFaceArgs a)
+{
+    const unsigned f = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.end) return;
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    FaceGeom g;
+    unsigned n[3];
+    if (!face_setup(a.mesh, f, a.nb_phase, a.mean, g, n)) { a.fset[f] = -1; return; }
+    a.fset[f] = (signed char)g.gs;
+    double *out = a.fbuf + (size_t)f * 36;
+    int k = 0;
+    for (int q = c_gauss_off[g.gs]; q < c_gauss_off[g.gs + 1]; q++, k++) {
+        const double w = c_gauss[4 * q], b0 = c_gauss[4 * q + 1], b1 = c_gauss[4 * q + 2], b2 = c_gauss[4 * q + 3];
+        const V3 p = add(add(mul(g.p[0], b0), mul(g.p[1], b1)), mul(g.p[2], b2)); // get_coord_tri
+        const double I = fetch_trilinear(vol, a.vol.X, a.vol.Y, a.vol.Z, p);
+        const V3 fv = mul(g.norm, (2 * I - g.c0 - g.c1) * (g.c0 - g.c1) * w * g.area);
+        out[3 * k] = fv.x; out[3 * k + 1] = fv.y; out[3 * k + 2] = fv.z;
+    }
+    atomicAdd(a.gauss_count, (unsigned long long)k);
+}
+
+struct ForceNodeArgs {
+    MeshView mesh;
+    const double *fbuf;
+    const signed char *fset;
+    double *forces;
+    unsigned begin, end; // node range
+};
+
+__global__ void __launch_bounds__(128) force_node_kernel(const ForceNodeArgs a)
+{
+    const unsigned v = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.end) return;
+    const unsigned e0 = __ldg(a.mesh.node_off + v), e1 = __ldg(a.mesh.node_off + v + 1);
+    double fx = 0, fy = 0, fz = 0;
+    for (unsigned e = e0; e < e1; e++) {
+        const unsigned inc = __ldg(a.mesh.node_inc + e);
+        const unsigned f = inc >> 2, corner = inc & 3u;
+        const int gs = a.fset[f];
+        if (gs < 0) continue;
+        const double *fb = a.fbuf + (size_t)f * 36;
+        int k = 0;
+        for (int q = c_gauss_off[gs]; q < c_gauss_off[gs + 1]; q++, k++) {
+            const double bc = c_gauss[4 * q + 1 + corner];
+            fx += fb[3 * k] * bc; fy += fb[3 * k + 1] * bc; fz += fb[3 * k + 2] * bc;
+        }
+    }
+    a.forces[3 * (size_t)v] = fx;
+    a.forces[3 * (size_t)v + 1] = fy;
+    a.forces[3 * (size_t)v + 2] = fz;
+}
+
+// ---- node -> incident interface faces CSR built on the device (was a host counting sort: ~1 ms of the end-to-end step)
+__global__ void csr_count_kernel(const unsigned *__restrict__ face_nodes, unsigned n_inc, unsigned n_nodes, unsigned *count)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inc) return;
+    const unsigned v = face_nodes[i];
+    if (v < n_nodes) atomicAdd(count + v, 1u);
+}
+
+__global__ void csr_fill_kernel(const unsigned *__restrict__ face_nodes, unsigned n_inc, unsigned n_nodes, const unsigned *__restrict__ off, unsigned *cursor,
+                                unsigned *inc)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inc) return;
+    const unsigned v = face_nodes[i];
+    if (v >= n_nodes) return;
+    const unsigned slot = atomicAdd(cursor + v, 1u);
+    inc[off[v] + slot] = ((i / 3u) << 2) | (i % 3u);
+}
+
+// every node's list sorted ascending (= face ascending: the reference's accumulation order)
+__global__ void csr_sort_kernel(const unsigned *__restrict__ off, unsigned *inc, unsigned n_nodes)
+{
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    const unsigned b = off[v], e = off[v + 1];
+    for (unsigned i = b + 1; i < e; i++) {
+        const unsigned x = inc[i];
+        unsigned j = i;
+        while (j > b && inc[j - 1] > x) { inc[j] = inc[j - 1]; j--; }
+        inc[j] = x;
+    }
 }
 
 // Scatter form: one thread per interface face, per-corner sums over the Gauss points, then nine

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -66,15 +67,18 @@ struct dscgpu_ctx {
     bool has_sum_table = false;
     double *d_tet_bary = nullptr;
     float4 *d_tet_bary_f = nullptr;
+    float4 *d_tet_lat = nullptr;
     cudaArray_t vol_array = nullptr;
     cudaTextureObject_t vol_tex = 0;
-    int tet_variant = 40; // see dscgpu_set_tet_variant; default = batched group kernel, 4 gathers in flight per lane
+    int force_thread_gather = 0; // 1: thread-per-node gather (first implementation) instead of warp-per-node
+    int hot_want_sq = 0; // dscgpu_image_force_eval / dscgpu_tet_phase_sums_dev skip the second moment unless asked
+    int tet_variant = 128; // see dscgpu_set_tet_variant; default = batched group kernel, 4 gathers in flight per lane
 
     bool has_snapshot = false;
     uint32_t n_nodes = 0, n_tets = 0, n_faces = 0;
-    DevBuf pos4, pos4f, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc;
+    DevBuf pos4, pos4f, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc, csr_count, csr_cursor, fbuf, fset;
     // pinned staging (host side of the snapshot)
-    PinBuf h_pos4, h_tet_nodes, h_tet_label, h_face_nodes, h_face_tets, h_face_isb, h_node_off, h_node_inc, h_out, h_flag;
+    PinBuf h_pos4, h_tet_nodes, h_tet_label, h_face_nodes, h_face_tets, h_face_isb, h_node_off, h_node_inc, h_node_active, h_out, h_flag;
     bool validation_pending = false;
     uint32_t st_nodes = 0, st_tets = 0, st_faces = 0;
     bool staging_valid = false;
@@ -214,6 +218,58 @@ template <typename VoxT> int launch_tpt_v(dscgpu_ctx *ctx, TetArgs &a, bool tex,
     return filter ? launch_tpt_t<VoxT, kFetchLdg, true>(ctx, a) : launch_tpt_t<VoxT, kFetchLdg, false>(ctx, a);
 }
 
+template <typename VoxT, bool WANT_SQ, bool PER_TET> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
+{
+    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET>;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    if (occ < 1) occ = 1;
+    unsigned n_work = a.tet_end - a.tet_begin;
+    unsigned need = (n_work + 255) / 256;
+    unsigned grid = (unsigned)(ctx->num_sms * occ);
+    if (need < grid) grid = need ? need : 1;
+    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
+    a.partials = ctx->partials.as<double>();
+    ctx->tet_grid = (int)grid;
+    kern<<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT> int launch_w2(dscgpu_ctx *ctx, TetArgs &a)
+{
+    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
+    if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true>(ctx, a) : launch_w2_t<VoxT, true, false>(ctx, a);
+    return per_tet ? launch_w2_t<VoxT, false, true>(ctx, a) : launch_w2_t<VoxT, false, false>(ctx, a);
+}
+
+template <typename VoxT, bool WANT_SQ, bool PER_TET> int launch_w3_t(dscgpu_ctx *ctx, TetArgs &a)
+{
+    auto kern = tet_integrate_w3_kernel<VoxT, WANT_SQ, PER_TET>;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    if (occ < 1) occ = 1;
+    unsigned n_work = a.tet_end - a.tet_begin;
+    unsigned need = (n_work + 255) / 256;
+    unsigned grid = (unsigned)(ctx->num_sms * occ);
+    if (need < grid) grid = need ? need : 1;
+    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
+    a.partials = ctx->partials.as<double>();
+    ctx->tet_grid = (int)grid;
+    kern<<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT> int launch_w3(dscgpu_ctx *ctx, TetArgs &a)
+{
+    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
+    if (a.want_sq) return per_tet ? launch_w3_t<VoxT, true, true>(ctx, a) : launch_w3_t<VoxT, true, false>(ctx, a);
+    return per_tet ? launch_w3_t<VoxT, false, true>(ctx, a) : launch_w3_t<VoxT, false, false>(ctx, a);
+}
+
 template <typename VoxT, int PMAX, bool PER_TET> int launch_ab_t(dscgpu_ctx *ctx, TetArgs &a)
 {
     auto kern = tet_integrate_ab_kernel<VoxT, PMAX, PER_TET>;
@@ -294,6 +350,22 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
     }
     int G = ctx->lanes_per_tet ? ctx->lanes_per_tet : ctx->auto_lanes;
     const bool fits32 = (double)ctx->dims[0] * ctx->dims[1] * ctx->dims[2] < 2147483648.0;
+    if ((ctx->tet_variant & 256) && !with_c && fits32) { // w3: lattice coordinates, fixed-point floor, independent groups
+        switch (ctx->dtype) {
+        case DSCGPU_U8: return launch_w3<unsigned char>(ctx, a);
+        case DSCGPU_U16: return launch_w3<unsigned short>(ctx, a);
+        case DSCGPU_F32: return launch_w3<float>(ctx, a);
+        default: return launch_w3<double>(ctx, a);
+        }
+    }
+    if ((ctx->tet_variant & 128) && !with_c && fits32) { // warp-level two-phase kernel with lattice coordinates
+        switch (ctx->dtype) {
+        case DSCGPU_U8: return launch_w2<unsigned char>(ctx, a);
+        case DSCGPU_U16: return launch_w2<unsigned short>(ctx, a);
+        case DSCGPU_F32: return launch_w2<float>(ctx, a);
+        default: return launch_w2<double>(ctx, a);
+        }
+    }
     if ((ctx->tet_variant & 64) && !with_c && fits32) { // two-phase CTA kernel (32-bit voxel indices)
         switch (ctx->dtype) {
         case DSCGPU_U8: return launch_ab<unsigned char>(ctx, a);
@@ -323,13 +395,15 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
 
 // tet pass + finalize; leaves sums (3*nb) in ctx->sums and means in ctx->mean (device)
 int run_tet_pass(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, double *d_total, double *d_vol, double *d_mean,
-                 double *d_energy, double *d_variation, double *d_sums_out, double *d_mean_out)
+                 double *d_energy, double *d_variation, double *d_sums_out, double *d_mean_out, int want_sq = 1)
 {
     TetArgs a;
     a.vol = vol_view(ctx);
     a.mesh = mesh_view(ctx);
     a.tet_bary = ctx->d_tet_bary;
     a.tet_bary_f = ctx->d_tet_bary_f;
+    a.tet_lat = ctx->d_tet_lat;
+    a.want_sq = want_sq;
     a.tex = ctx->vol_tex;
     a.tet_begin = ctx->tet_b; a.tet_end = ctx->tet_e;
     a.include_bound = include_bound;
@@ -376,7 +450,37 @@ int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, do
     a.gauss_count = ctr(ctx, 1);
     CK(cudaMemsetAsync(ctr(ctx, 1), 0, sizeof(unsigned long long), ctx->stream));
     TimerScope ts(ctx, DSCGPU_T_FORCE);
-    bool whole_nodes = ctx->node_b == 0 && ctx->node_e == ctx->n_nodes;
+    const bool whole_nodes = ctx->node_b == 0 && ctx->node_e == ctx->n_nodes;
+    if (mode == DSCGPU_FORCE_GATHER && !ctx->force_thread_gather) {
+        // two kernels: per-face Gauss vectors (all faces, on every rank: it is a few tens of microseconds), then per-node ordered sums
+        const unsigned nf = ctx->n_faces;
+        CK(ctx->fbuf.ensure((size_t)nf * 36 * sizeof(double) + 8));
+        CK(ctx->fset.ensure((size_t)nf + 8));
+        ForceFaceArgs fa;
+        fa.vol = a.vol; fa.mesh = a.mesh; fa.nb_phase = nb_phase; fa.mean = d_mean; fa.gauss_count = a.gauss_count;
+        fa.fbuf = ctx->fbuf.as<double>(); fa.fset = ctx->fset.as<signed char>();
+        fa.begin = 0; fa.end = nf;
+        if (nf) {
+            const unsigned grid = (nf + 127) / 128;
+            switch (ctx->dtype) {
+            case DSCGPU_U8: force_face_kernel<unsigned char><<<grid, 128, 0, ctx->stream>>>(fa); break;
+            case DSCGPU_U16: force_face_kernel<unsigned short><<<grid, 128, 0, ctx->stream>>>(fa); break;
+            case DSCGPU_F32: force_face_kernel<float><<<grid, 128, 0, ctx->stream>>>(fa); break;
+            default: force_face_kernel<double><<<grid, 128, 0, ctx->stream>>>(fa); break;
+            }
+            ctx->launches++;
+        }
+        if (!whole_nodes) CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
+        ForceNodeArgs na;
+        na.mesh = a.mesh; na.fbuf = fa.fbuf; na.fset = fa.fset; na.forces = d_forces;
+        na.begin = ctx->node_b; na.end = ctx->node_e;
+        if (na.end > na.begin) {
+            force_node_kernel<<<(na.end - na.begin + 127) / 128, 128, 0, ctx->stream>>>(na);
+            ctx->launches++;
+        }
+        CK(cudaGetLastError());
+        return DSCGPU_OK;
+    }
     if (mode == DSCGPU_FORCE_GATHER) {
         a.begin = ctx->node_b; a.end = ctx->node_e;
         // nodes outside this context's range must read as zero for the all-reduce
@@ -513,24 +617,6 @@ void fill_stats(dscgpu_phase_stats *st, const double *sums, const double *mean, 
     }
 }
 
-// node -> incident interface faces CSR by counting sort; faces are visited in ascending index, so
-// every node's list is ascending (= the reference's accumulation order in compute_external_force)
-void build_node_csr(uint32_t n_nodes, uint32_t n_faces, const uint32_t *face_nodes, uint32_t *off, uint32_t *inc)
-{
-    memset(off, 0, sizeof(uint32_t) * ((size_t)n_nodes + 1));
-    for (size_t i = 0; i < 3 * (size_t)n_faces; i++) {
-        uint32_t v = face_nodes[i];
-        if (v < n_nodes) off[v + 1]++;
-    }
-    for (uint32_t v = 0; v < n_nodes; v++) off[v + 1] += off[v];
-    std::vector<uint32_t> cur(off, off + n_nodes);
-    for (uint32_t f = 0; f < n_faces; f++)
-        for (uint32_t k = 0; k < 3; k++) {
-            uint32_t v = face_nodes[3 * (size_t)f + k];
-            if (v < n_nodes) inc[cur[v]++] = (f << 2) | k;
-        }
-}
-
 } // namespace
 
 extern "C" {
@@ -567,7 +653,31 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
         CK(cudaMalloc(&ctx->d_tet_bary_f, tf.size() * sizeof(float)));
         CK(cudaMemcpy(ctx->d_tet_bary_f, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
+    {
+        // lattice form of the sample table: b_k = a_k/(4n) + eta_k, integer a_k summing to 4n, |eta_k| <= 5e-7, eps = sum b_k - 1
+        std::vector<float> tl(4 * DSC_TET_POINTS_TOTAL);
+        for (int L = 0; L < DSC_TET_LEVELS; L++) {
+            const int n = L + 1;
+            for (int i = DSC_TET_LEVEL_OFFSET[L]; i < DSC_TET_LEVEL_OFFSET[L + 1]; i++) {
+                const double *b = DSC_TET_BARY + 4 * i;
+                long asum = 0;
+                double av[4];
+                for (int k = 0; k < 4; k++) {
+                    av[k] = (double)lrint(4.0 * n * b[k]);
+                    asum += (long)av[k];
+                    ARG(fabs(b[k] - av[k] / (4.0 * n)) <= 5.0e-7, "sample table is not the expected 6-decimal lattice");
+                }
+                ARG(asum == 4 * n, "sample table row does not sum to one on the lattice");
+                const double eps = ((b[0] + b[1]) + b[2]) + b[3] - 1.0;
+                ARG(fabs(eps) <= 2.1e-6, "sample table row sum too far from one");
+                tl[4 * i] = (float)av[1]; tl[4 * i + 1] = (float)av[2]; tl[4 * i + 2] = (float)av[3]; tl[4 * i + 3] = (float)eps;
+            }
+        }
+        CK(cudaMalloc(&ctx->d_tet_lat, tl.size() * sizeof(float)));
+        CK(cudaMemcpy(ctx->d_tet_lat, tl.data(), tl.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     if (const char *ev = getenv("DSCGPU_TET_VARIANT")) ctx->tet_variant = atoi(ev);
+    if (const char *ev = getenv("DSCGPU_FORCE_THREAD_GATHER")) ctx->force_thread_gather = atoi(ev);
     CK(cudaMemcpyToSymbolAsync(c_gauss, DSC_GAUSS, sizeof(DSC_GAUSS), 0, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyToSymbolAsync(c_gauss_off, DSC_GAUSS_SET_OFFSET, sizeof(DSC_GAUSS_SET_OFFSET), 0, cudaMemcpyHostToDevice, ctx->stream));
     int r = ensure_scratch(ctx);
@@ -580,18 +690,19 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_OK;
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    DevBuf *bufs[] = {&ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
+    DevBuf *bufs[] = {&ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
                       &ctx->partials, &ctx->sums, &ctx->mean, &ctx->forces, &ctx->counters, &ctx->o_total, &ctx->o_vol, &ctx->o_mean, &ctx->o_energy,
                       &ctx->o_variation, &ctx->o_hash, &ctx->o_nsamp, &ctx->ray_count, &ctx->ray_offset, &ctx->ray_cursor, &ctx->hits, &ctx->block_sums,
                       &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
     for (DevBuf *b : bufs) b->release();
     PinBuf *pins[] = {&ctx->h_pos4, &ctx->h_tet_nodes, &ctx->h_tet_label, &ctx->h_face_nodes, &ctx->h_face_tets, &ctx->h_face_isb, &ctx->h_node_off,
-                      &ctx->h_node_inc, &ctx->h_out, &ctx->h_flag};
+                      &ctx->h_node_inc, &ctx->h_node_active, &ctx->h_out, &ctx->h_flag};
     for (PinBuf *b : pins) b->release();
     if (ctx->d_vol) cudaFree(ctx->d_vol);
     if (ctx->d_sum_table) cudaFree(ctx->d_sum_table);
     if (ctx->d_tet_bary) cudaFree(ctx->d_tet_bary);
     if (ctx->d_tet_bary_f) cudaFree(ctx->d_tet_bary_f);
+    if (ctx->d_tet_lat) cudaFree(ctx->d_tet_lat);
     if (ctx->vol_tex) cudaDestroyTextureObject(ctx->vol_tex);
     if (ctx->vol_array) cudaFreeArray(ctx->vol_array);
     for (int i = 0; i < DSCGPU_T_COUNT; i++) {
@@ -663,8 +774,6 @@ int dscgpu_snapshot_staging_get(dscgpu_ctx *ctx, uint32_t n_nodes, uint32_t n_te
     CK(ctx->h_face_nodes.ensure((size_t)n_faces * 3 * sizeof(uint32_t)));
     CK(ctx->h_face_tets.ensure((size_t)n_faces * 2 * sizeof(uint32_t)));
     CK(ctx->h_face_isb.ensure((size_t)n_faces));
-    CK(ctx->h_node_off.ensure(((size_t)n_nodes + 1) * sizeof(uint32_t)));
-    CK(ctx->h_node_inc.ensure((size_t)n_faces * 3 * sizeof(uint32_t)));
     ctx->st_nodes = n_nodes; ctx->st_tets = n_tets; ctx->st_faces = n_faces;
     ctx->staging_valid = true;
     out->pos4 = ctx->h_pos4.as<double>();
@@ -684,8 +793,6 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     ARG(nf < (1u << 30), "too many interface faces");
     const uint32_t *tn = ctx->h_tet_nodes.as<uint32_t>();
     const uint32_t *fn = ctx->h_face_nodes.as<uint32_t>();
-    build_node_csr(nn, nf, fn, ctx->h_node_off.as<uint32_t>(), ctx->h_node_inc.as<uint32_t>());
-
     CK(ctx->pos4.ensure((size_t)nn * 32));
     CK(ctx->pos4f.ensure((size_t)nn * 16));
     CK(ctx->tet_nodes.ensure((size_t)nt * 16));
@@ -704,8 +811,26 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
         if (nf) CK(cudaMemcpyAsync(ctx->face_nodes.p, ctx->h_face_nodes.p, (size_t)nf * 12, cudaMemcpyHostToDevice, s));
         if (nf) CK(cudaMemcpyAsync(ctx->face_tets.p, ctx->h_face_tets.p, (size_t)nf * 8, cudaMemcpyHostToDevice, s));
         if (nf) CK(cudaMemcpyAsync(ctx->face_isb.p, ctx->h_face_isb.p, (size_t)nf, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->node_off.p, ctx->h_node_off.p, ((size_t)nn + 1) * 4, cudaMemcpyHostToDevice, s));
-        if (nf) CK(cudaMemcpyAsync(ctx->node_inc.p, ctx->h_node_inc.p, (size_t)nf * 12, cudaMemcpyHostToDevice, s));
+    }
+    {   // node -> incident interface faces CSR on the device: count, exclusive scan, fill (slot by integer atomic), sort each list
+        CK(ctx->csr_count.ensure(((size_t)nn + 1) * 4));
+        CK(ctx->csr_cursor.ensure(((size_t)nn + 1) * 4));
+        CK(cudaMemsetAsync(ctx->csr_count.p, 0, ((size_t)nn + 1) * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->csr_cursor.p, 0, ((size_t)nn + 1) * 4, ctx->stream));
+        const unsigned n_inc = 3u * nf;
+        if (n_inc) {
+            csr_count_kernel<<<(n_inc + 255) / 256, 256, 0, ctx->stream>>>(ctx->face_nodes.as<unsigned>(), n_inc, nn, ctx->csr_count.as<unsigned>());
+            ctx->launches++;
+        }
+        int rs = exclusive_scan(ctx, ctx->csr_count.as<unsigned>(), ctx->node_off.as<unsigned>(), (size_t)nn + 1, nullptr);
+        if (rs) return rs;
+        if (n_inc) {
+            csr_fill_kernel<<<(n_inc + 255) / 256, 256, 0, ctx->stream>>>(ctx->face_nodes.as<unsigned>(), n_inc, nn, ctx->node_off.as<unsigned>(),
+                                                                         ctx->csr_cursor.as<unsigned>(), ctx->node_inc.as<unsigned>());
+            csr_sort_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->node_off.as<unsigned>(), ctx->node_inc.as<unsigned>(), nn);
+            ctx->launches += 2;
+        }
+        CK(cudaGetLastError());
     }
     if (nn) {
         pos_to_float_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->pos4.as<double4>(), ctx->pos4f.as<float4>(), nn);
@@ -982,7 +1107,7 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
         if (!ctx->has_sum_table) { ctx->err = "dscgpu_build_sum_table has not been called"; return DSCGPU_ERR_NO_SUMTABLE; }
         r = run_zray(ctx, nb_phase, 0, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>());
     } else {
-        r = run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>());
+        r = run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), ctx->hot_want_sq);
     }
     if (r) return r;
     r = run_forces(ctx, nb_phase, ctx->mean.as<double>(), force_mode, ctx->forces.as<double>());
@@ -992,7 +1117,7 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
         TimerScope ts(ctx, DSCGPU_T_D2H);
         CK(cudaMemcpyAsync(h, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h + 3 * kMaxPhase, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        if (forces && fbytes) CK(cudaMemcpyAsync(h + 4 * kMaxPhase, ctx->forces.p, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (fbytes) CK(cudaMemcpyAsync(h + 4 * kMaxPhase, ctx->forces.p, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (mean_mode == DSCGPU_MEAN_ZRAY) {
         r = check_overflow(ctx);
@@ -1006,11 +1131,18 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
     return DSCGPU_OK;
 }
 
+const double *dscgpu_forces_pinned(dscgpu_ctx *ctx, uint32_t *n_nodes_buffer)
+{
+    if (!ctx || !ctx->h_out.p) return nullptr;
+    if (n_nodes_buffer) *n_nodes_buffer = ctx->n_nodes;
+    return ctx->h_out.as<double>() + 4 * kMaxPhase;
+}
+
 int dscgpu_tet_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums)
 {
     NEED_SNAPSHOT();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_sums, "bad arguments");
-    return run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_sums, nullptr);
+    return run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_sums, nullptr, ctx->hot_want_sq);
 }
 
 int dscgpu_zray_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums)
@@ -1091,7 +1223,7 @@ int dscgpu_build_texture(dscgpu_ctx *ctx)
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 128, "variant is a 7-bit field");
+    ARG(variant >= 0 && variant < 512, "variant is a 9-bit field");
     if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
         int r = dscgpu_build_texture(ctx);
         if (r) return r;

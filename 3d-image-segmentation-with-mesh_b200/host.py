@@ -73,6 +73,7 @@ def load_library():
     lib.dscgpu_last_gauss_count.restype = C.c_uint64
     lib.dscgpu_volume_ptr_dev.restype = C.c_void_p
     lib.dscgpu_sum_table_ptr_dev.restype = C.c_void_p
+    lib.dscgpu_forces_pinned.restype = C.POINTER(C.c_double)
     for name in ("dscgpu_ctx_destroy", "dscgpu_last_error", "dscgpu_set_stream", "dscgpu_synchronize", "dscgpu_build_sum_table",
                  "dscgpu_commit_snapshot", "dscgpu_launch_count", "dscgpu_last_sample_count", "dscgpu_last_gauss_count",
                  "dscgpu_volume_ptr_dev", "dscgpu_sum_table_ptr_dev"):
@@ -320,12 +321,17 @@ class SegmentFunction:
             self.n_nodes_buffer, self.n_tets, self.n_faces = len(pos), len(tn), len(fn)
         if mean_mode == MEAN_ZRAY and not self._img._has_table:
             self._img.build_sum_table()
-        f = np.empty((self.n_nodes_buffer, 3)) if want_forces else None
+        # want_forces: True -> copied into a fresh array; "pinned" -> zero-copy view of the context's pinned result buffer
+        f = np.empty((self.n_nodes_buffer, 3)) if want_forces is True else None
         st = _PhaseStats()
         r = self.lib.dscgpu_image_force_eval(self._img._ctx, C.byref(sp) if sp is not None else None, C.c_int(self.NB_PHASE), C.c_int(mean_mode),
                                              C.c_int(force_mode), C.byref(st), _ptr(f))
         self._img._check(r, "dscgpu_image_force_eval")
         self._stats_out(st)
+        if want_forces == "pinned" and self.n_nodes_buffer:
+            n = C.c_uint32(0)
+            ptr = self.lib.dscgpu_forces_pinned(self._img._ctx, C.byref(n))
+            f = np.ctypeslib.as_array(ptr, shape=(n.value * 3,)).reshape(-1, 3)
         self._forces = f
         return self._mean_intensities, f
 

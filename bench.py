@@ -349,13 +349,13 @@ def main_b200(args):
         st["face_is_boundary"][...] = snap["face_is_boundary"]
 
     fill_staging()
-    h2d_bytes = n_nodes * 32 + n_tets * 20 + n_faces * (12 + 8 + 1) + (n_nodes + 1) * 4 + n_faces * 12
+    h2d_bytes = n_nodes * 32 + n_tets * 20 + n_faces * (12 + 8 + 1)  # pos4, tet ids+labels, face ids/tets/flags; the CSR is built on the device
     d2h_bytes = n_nodes * 24 + 4 * P * 8
 
     def step_e2e():
         if world == 1:
             seg.staging(n_nodes, n_tets, n_faces)  # same pinned arrays (already filled); marks the snapshot dirty
-            seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode)
+            seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode, want_forces="pinned")
         else:
             seg.staging(n_nodes, n_tets, n_faces)
             seg.commit_snapshot()

@@ -176,6 +176,11 @@ enum dscgpu_mean_mode { DSCGPU_MEAN_TET = 0, DSCGPU_MEAN_ZRAY = 1 };
 int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb_phase, int mean_mode, int force_mode,
                             dscgpu_phase_stats *stats, double *forces);
 
+/* After dscgpu_image_force_eval: the forces as they arrived in the context's PINNED host buffer (3*n_nodes_buffer doubles,
+ * valid until the next call on the context).  Passing forces == NULL to dscgpu_image_force_eval and reading them here
+ * avoids one host-side copy per evaluation. */
+const double *dscgpu_forces_pinned(dscgpu_ctx *ctx, uint32_t *n_nodes_buffer);
+
 /* Device-resident pieces for multi-GPU composition (NCCL all-reduce happens between them, on
  * the caller's stream set with dscgpu_set_stream):
  *   d_sums   3*nb_phase doubles: total[nb], sumsq[nb], volume[nb] of this context's partition

@@ -118,6 +118,8 @@ def test_full_evaluation_through_host_buffers(case, pkg):
     assert np.array_equal(seg._phase_volume, g["phase_volume"])
     scale = np.abs(g["forces"]).max()
     np.testing.assert_allclose(F, g["forces"], rtol=1e-5, atol=1e-6 * scale)  # means differ in the last bits -> forces too
+    _, F_pin = seg.image_force_eval(s, mean_mode=pkg.MEAN_ZRAY, force_mode=pkg.FORCE_GATHER, want_forces="pinned")
+    assert np.array_equal(np.array(F_pin), F)  # zero-copy view of the pinned result buffer
     mean_t, F_t = seg.image_force_eval(s, mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_ATOMIC)
     P = g["meta"]["nb_phase"]
     tot = np.array([g["tet_total"][g["tet_label"] == k + 1].sum() for k in range(P)])
@@ -248,7 +250,7 @@ def test_ray_overflow_is_reported(pkg):
     img.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 5, 7, 8, 12, 24, 40, 44, 56, 60, 64])
+@pytest.mark.parametrize("variant", [0, 1, 3, 5, 7, 8, 12, 24, 40, 44, 56, 60, 64, 128, 256])
 def test_every_kernel_variant_classifies_identically(pkg, variant):
     """All implementations of the tet pass (incl. the FP32-filtered ones) must put every sample in the same voxel:
     per-tet sums of noisy data agree to rounding, and the volumes bit for bit."""
@@ -281,7 +283,7 @@ def test_filter_variants_on_large_interior_mesh(pkg, flat):
     img = pkg.Image3D(vol)
     seg = pkg.SegmentFunction(img, 3)
     seg.set_snapshot(snap)
-    for variant in (5, 12, 44, 60, 64):
+    for variant in (5, 12, 44, 60, 64, 128, 256):
         seg.set_tet_variant(variant)
         o = seg.tet_integrate(include_bound=True)
         assert np.array_equal(o["vol"], ref["vol"])

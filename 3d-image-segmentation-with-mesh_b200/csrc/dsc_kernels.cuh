@@ -1431,21 +1431,25 @@ __global__ void __launch_bounds__(128) tet_integrate_tpt_kernel(const TetArgs a)
     if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
 }
 
-// Adds the per-CTA partial rows in CTA order and derives the means: out[0..P) total, [P..2P) sumsq,
-// [2P..3P) volume (P = nb_phase), mean[k] = total/volume.
-__global__ void tet_finalize_kernel(const double *partials, int n_rows, int nb_phase, double *sums, double *mean)
+// Adds the per-CTA partial rows and derives the means: out[0..P) total, [P..2P) sumsq, [2P..3P) volume (P = nb_phase),
+// mean[k] = total/volume.  One warp per column group: lane l adds rows l, l+32, ... in order, then a fixed xor tree --
+// a deterministic order that depends only on the number of rows (a single thread per column took 70 us for 444 rows).
+__global__ void __launch_bounds__(32 * 3 * kMaxPhase) tet_finalize_kernel(const double *__restrict__ partials, int n_rows, int nb_phase, double *sums, double *mean)
 {
-    const int k = threadIdx.x;
-    if (k >= 3 * kMaxPhase) return;
-    const int which = k / kMaxPhase, ph = k % kMaxPhase;
+    const int col = threadIdx.x >> 5, lane = threadIdx.x & 31; // 24 warps, one per column
     double r = 0;
-    for (int i = 0; i < n_rows; i++) r += partials[(size_t)i * 3 * kMaxPhase + k];
-    if (ph < nb_phase) sums[which * nb_phase + ph] = r;
+    for (int i = lane; i < n_rows; i += 32) r += partials[(size_t)i * 3 * kMaxPhase + col];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) r += shfl_xor_d(r, m);
+    const int which = col / kMaxPhase, ph = col % kMaxPhase;
     __shared__ double tot[kMaxPhase], vol[kMaxPhase];
-    if (which == 0) tot[ph] = r;
-    if (which == 2) vol[ph] = r;
+    if (lane == 0) {
+        if (ph < nb_phase) sums[which * nb_phase + ph] = r;
+        if (which == 0) tot[ph] = r;
+        if (which == 2) vol[ph] = r;
+    }
     __syncthreads();
-    if (mean && k < nb_phase) mean[k] = tot[k] / vol[k];
+    if (mean && threadIdx.x < nb_phase) mean[threadIdx.x] = tot[threadIdx.x] / vol[threadIdx.x];
 }
 
 __global__ void means_from_sums_kernel(const double *sums, int nb_phase, double *mean)
@@ -2069,18 +2073,26 @@ template <typename VoxT> __global__ void __launch_bounds__(128) zray_resolve_ker
     }
 }
 
-// sums[0..P) = total, [P..2P) = 0 (no squared sum on this path), [2P..3P) = voxel count
+// sums[0..P) = total, [P..2P) = 0 (no squared sum on this path), [2P..3P) = voxel count.  One warp per phase: lane l adds
+// partials l, l+32, ... in order, then a fixed xor tree (deterministic; counts are integers and exact in any order).
 __global__ void zray_finalize_kernel(const double *partial_sum, const long long *partial_cnt, int n_blocks, int nb_phase, double *sums, double *mean)
 {
-    const int k = threadIdx.x;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= nb_phase) return;
     double s = 0;
     long long c = 0;
-    for (int i = 0; i < n_blocks; i++) { s += partial_sum[(size_t)k * n_blocks + i]; c += partial_cnt[(size_t)k * n_blocks + i]; }
-    sums[k] = s;
-    sums[nb_phase + k] = 0;
-    sums[2 * nb_phase + k] = (double)c;
-    if (mean) mean[k] = s / (double)c;
+    for (int i = lane; i < n_blocks; i += 32) { s += partial_sum[(size_t)k * n_blocks + i]; c += partial_cnt[(size_t)k * n_blocks + i]; }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        s += shfl_xor_d(s, m);
+        c += __shfl_xor_sync(0xffffffffu, c, m);
+    }
+    if (lane == 0) {
+        sums[k] = s;
+        sums[nb_phase + k] = 0;
+        sums[2 * nb_phase + k] = (double)c;
+        if (mean) mean[k] = s / (double)c;
+    }
 }
 
 // Snapshot index validation on the device: out-of-range node keys / tet indices are neutralised (0 / NO_TET) so that no
@@ -2140,12 +2152,13 @@ __global__ void __launch_bounds__(256) area_term_kernel(MeshView m, const unsign
 }
 
 __global__ void sum_partials_kernel(const double *partials, int n, double *out)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double r = 0;
-        for (int i = 0; i < n; i++) r += partials[i];
-        *out = r;
-    }
+{   // one warp: lane l adds partials l, l+32, ... in order, then a fixed xor tree
+    const int lane = threadIdx.x & 31;
+    double r = 0;
+    for (int i = lane; i < n; i += 32) r += partials[i];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) r += shfl_xor_d(r, m);
+    if (threadIdx.x == 0) *out = r;
 }
 
 } // namespace dsc

@@ -52,6 +52,8 @@ struct PinBuf {
     template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 
+constexpr unsigned kMaxPartialRows = 32768;
+
 size_t dtype_size(int dt) { return dt == DSCGPU_U8 ? 1 : dt == DSCGPU_U16 ? 2 : dt == DSCGPU_F32 ? 4 : 8; }
 
 } // namespace
@@ -59,7 +61,9 @@ size_t dtype_size(int dt) { return dt == DSCGPU_U8 ? 1 : dt == DSCGPU_U16 ? 2 : 
 struct dscgpu_ctx {
     int device = 0;
     int num_sms = 148;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_chunk[20];
+    int pipeline_chunks = 4; // tet-array upload chunks overlapped with the tet kernel in dscgpu_image_force_eval (0 = off)
     int dims[3] = {0, 0, 0};
     int dtype = DSCGPU_F32;
     void *d_vol = nullptr;
@@ -184,9 +188,9 @@ template <typename VoxT, int G, bool WITH_C> int launch_tet_t(dscgpu_ctx *ctx, T
     unsigned need = (n_work + groups_per_block - 1) / groups_per_block;
     unsigned grid = (unsigned)(ctx->num_sms * occ);
     if (need < grid) grid = need ? need : 1;
-    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
-    a.partials = ctx->partials.as<double>();
-    ctx->tet_grid = (int)grid;
+    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)grid;
     kern<<<grid, 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -203,9 +207,9 @@ template <typename VoxT, int FETCH, bool FILTER> int launch_tpt_t(dscgpu_ctx *ct
     unsigned need = (n_work + 127) / 128;
     unsigned grid = (unsigned)(ctx->num_sms * occ);
     if (need < grid) grid = need ? need : 1;
-    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
-    a.partials = ctx->partials.as<double>();
-    ctx->tet_grid = (int)grid;
+    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)grid;
     kern<<<grid, 128, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -228,9 +232,9 @@ template <typename VoxT, bool WANT_SQ, bool PER_TET> int launch_w2_t(dscgpu_ctx 
     unsigned need = (n_work + 255) / 256;
     unsigned grid = (unsigned)(ctx->num_sms * occ);
     if (need < grid) grid = need ? need : 1;
-    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
-    a.partials = ctx->partials.as<double>();
-    ctx->tet_grid = (int)grid;
+    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)grid;
     kern<<<grid, 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -254,9 +258,9 @@ template <typename VoxT, bool WANT_SQ, bool PER_TET> int launch_w3_t(dscgpu_ctx 
     unsigned need = (n_work + 255) / 256;
     unsigned grid = (unsigned)(ctx->num_sms * occ);
     if (need < grid) grid = need ? need : 1;
-    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
-    a.partials = ctx->partials.as<double>();
-    ctx->tet_grid = (int)grid;
+    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)grid;
     kern<<<grid, 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -280,9 +284,9 @@ template <typename VoxT, int PMAX, bool PER_TET> int launch_ab_t(dscgpu_ctx *ctx
     unsigned need = (n_work + kBatch - 1) / kBatch;
     unsigned grid = (unsigned)(ctx->num_sms * occ);
     if (need < grid) grid = need ? need : 1;
-    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
-    a.partials = ctx->partials.as<double>();
-    ctx->tet_grid = (int)grid;
+    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)grid;
     kern<<<grid, 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -307,9 +311,9 @@ template <typename VoxT, int G, int UNROLL, bool FILTER> int launch_g_t(dscgpu_c
     unsigned need = (n_work + groups_per_block - 1) / groups_per_block;
     unsigned grid = (unsigned)(ctx->num_sms * occ);
     if (need < grid) grid = need ? need : 1;
-    CK(ctx->partials.ensure((size_t)grid * 3 * kMaxPhase * sizeof(double)));
-    a.partials = ctx->partials.as<double>();
-    ctx->tet_grid = (int)grid;
+    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)grid;
     kern<<<grid, 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -393,38 +397,62 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
     }
 }
 
-// tet pass + finalize; leaves sums (3*nb) in ctx->sums and means in ctx->mean (device)
-int run_tet_pass(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, double *d_total, double *d_vol, double *d_mean,
-                 double *d_energy, double *d_variation, double *d_sums_out, double *d_mean_out, int want_sq = 1)
+struct TetPassOut {
+    double *d_total = nullptr, *d_vol = nullptr, *d_mean = nullptr, *d_energy = nullptr, *d_variation = nullptr;
+};
+
+// launches the tet kernel on [begin, end); partial rows accumulate in ctx->partials until tet_pass_finish
+int tet_pass_range(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, const TetPassOut &o, unsigned begin, unsigned end, int want_sq)
 {
+    if (end <= begin) return DSCGPU_OK;
     TetArgs a;
     a.vol = vol_view(ctx);
     a.mesh = mesh_view(ctx);
     a.tet_bary = ctx->d_tet_bary;
     a.tet_bary_f = ctx->d_tet_bary_f;
+    a.tex = ctx->vol_tex;
     a.tet_lat = ctx->d_tet_lat;
     a.want_sq = want_sq;
-    a.tex = ctx->vol_tex;
-    a.tet_begin = ctx->tet_b; a.tet_end = ctx->tet_e;
+    a.tet_begin = begin; a.tet_end = end;
     a.include_bound = include_bound;
     a.nb_phase = nb_phase;
     a.nc = nc;
     for (int k = 0; k < kMaxPhase; k++) a.c[k] = (c && k < nc) ? c[k] : 0.0;
-    a.tet_total = d_total; a.tet_vol = d_vol; a.tet_mean = d_mean; a.tet_energy = d_energy; a.tet_variation = d_variation;
+    a.tet_total = o.d_total; a.tet_vol = o.d_vol; a.tet_mean = o.d_mean; a.tet_energy = o.d_energy; a.tet_variation = o.d_variation;
     a.sample_count = ctr(ctx, 0);
+    return launch_tet(ctx, a, nc > 0 && (o.d_energy || o.d_variation));
+}
+
+int tet_pass_begin(dscgpu_ctx *ctx)
+{
+    ctx->tet_grid = 0;
     CK(cudaMemsetAsync(ctr(ctx, 0), 0, sizeof(unsigned long long), ctx->stream));
+    return DSCGPU_OK;
+}
+
+int tet_pass_finish(dscgpu_ctx *ctx, int nb_phase, double *d_sums_out, double *d_mean_out)
+{
+    TimerScope ts(ctx, DSCGPU_T_PHASE_FINAL);
+    tet_finalize_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums_out, d_mean_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+// tet pass + finalize over this context's partition; leaves sums (3*nb) and means on the device
+int run_tet_pass(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, double *d_total, double *d_vol, double *d_mean,
+                 double *d_energy, double *d_variation, double *d_sums_out, double *d_mean_out, int want_sq = 1)
+{
+    TetPassOut o;
+    o.d_total = d_total; o.d_vol = d_vol; o.d_mean = d_mean; o.d_energy = d_energy; o.d_variation = d_variation;
+    int r = tet_pass_begin(ctx);
+    if (r) return r;
     {
         TimerScope ts(ctx, DSCGPU_T_TET);
-        int r = launch_tet(ctx, a, nc > 0 && (d_energy || d_variation));
+        r = tet_pass_range(ctx, nb_phase, include_bound, nc, c, o, ctx->tet_b, ctx->tet_e, want_sq);
         if (r) return r;
     }
-    {
-        TimerScope ts(ctx, DSCGPU_T_PHASE_FINAL);
-        tet_finalize_kernel<<<1, 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums_out, d_mean_out);
-        ctx->launches++;
-        CK(cudaGetLastError());
-    }
-    return DSCGPU_OK;
+    return tet_pass_finish(ctx, nb_phase, d_sums_out, d_mean_out);
 }
 
 template <typename VoxT> int launch_force_t(dscgpu_ctx *ctx, ForceArgs &a, int mode)
@@ -459,9 +487,12 @@ int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, do
         ForceFaceArgs fa;
         fa.vol = a.vol; fa.mesh = a.mesh; fa.nb_phase = nb_phase; fa.mean = d_mean; fa.gauss_count = a.gauss_count;
         fa.fbuf = ctx->fbuf.as<double>(); fa.fset = ctx->fset.as<signed char>();
-        fa.begin = 0; fa.end = nf;
-        if (nf) {
-            const unsigned grid = (nf + 127) / 128;
+        // multi-GPU: this context evaluates the faces of its partition only; faces outside keep set -1 and contribute on another rank
+        const bool whole_faces = ctx->face_b == 0 && ctx->face_e == nf;
+        fa.begin = ctx->face_b; fa.end = ctx->face_e;
+        if (!whole_faces && nf) CK(cudaMemsetAsync(ctx->fset.p, 0xFF, nf, ctx->stream));
+        if (fa.end > fa.begin) {
+            const unsigned grid = (fa.end - fa.begin + 127) / 128;
             switch (ctx->dtype) {
             case DSCGPU_U8: force_face_kernel<unsigned char><<<grid, 128, 0, ctx->stream>>>(fa); break;
             case DSCGPU_U16: force_face_kernel<unsigned short><<<grid, 128, 0, ctx->stream>>>(fa); break;
@@ -470,10 +501,16 @@ int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, do
             }
             ctx->launches++;
         }
-        if (!whole_nodes) CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
         ForceNodeArgs na;
         na.mesh = a.mesh; na.fbuf = fa.fbuf; na.fset = fa.fset; na.forces = d_forces;
-        na.begin = ctx->node_b; na.end = ctx->node_e;
+        // with a face partition every node may receive a contribution from this rank; with all faces present the node
+        // range of the partition is enough (and the result is the reference's, bit for bit)
+        if (whole_faces) {
+            na.begin = ctx->node_b; na.end = ctx->node_e;
+            if (!whole_nodes) CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
+        } else {
+            na.begin = 0; na.end = ctx->n_nodes;
+        }
         if (na.end > na.begin) {
             force_node_kernel<<<(na.end - na.begin + 127) / 128, 128, 0, ctx->stream>>>(na);
             ctx->launches++;
@@ -579,7 +616,7 @@ int run_zray(dscgpu_ctx *ctx, int nb_phase, int mode, const double *c_host, doub
     case DSCGPU_F32: launch_resolve_t<float>(ctx, rs, grid); break;
     default: launch_resolve_t<double>(ctx, rs, grid); break;
     }
-    zray_finalize_kernel<<<1, 32, 0, ctx->stream>>>(rs.partial_sum, rs.partial_cnt, (int)n_blocks, nb_phase, d_sums_out, d_mean_out);
+    zray_finalize_kernel<<<1, 32 * kMaxPhase, 0, ctx->stream>>>(rs.partial_sum, rs.partial_cnt, (int)n_blocks, nb_phase, d_sums_out, d_mean_out);
     ctx->launches += 2;
     CK(cudaGetLastError());
     return DSCGPU_OK;
@@ -600,6 +637,7 @@ int check_overflow(dscgpu_ctx *ctx)
 int ensure_scratch(dscgpu_ctx *ctx)
 {
     CK(ctx->sums.ensure(3 * kMaxPhase * sizeof(double)));
+    CK(ctx->partials.ensure((size_t)kMaxPartialRows * 3 * kMaxPhase * sizeof(double)));
     CK(ctx->mean.ensure(kMaxPhase * sizeof(double)));
     CK(ctx->counters.ensure(8 * sizeof(unsigned long long)));
     CK(ctx->misc.ensure(64));
@@ -617,6 +655,113 @@ void fill_stats(dscgpu_phase_stats *st, const double *sums, const double *mean, 
     }
 }
 
+// node -> incident interface faces CSR on the device: count, exclusive scan, fill (slot by integer atomic), sort each list
+int build_csr_device(dscgpu_ctx *ctx)
+{
+    const uint32_t nn = ctx->n_nodes, nf = ctx->n_faces;
+    CK(ctx->csr_count.ensure(((size_t)nn + 1) * 4));
+    CK(ctx->csr_cursor.ensure(((size_t)nn + 1) * 4));
+    CK(cudaMemsetAsync(ctx->csr_count.p, 0, ((size_t)nn + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->csr_cursor.p, 0, ((size_t)nn + 1) * 4, ctx->stream));
+    const unsigned n_inc = 3u * nf;
+    if (n_inc) {
+        csr_count_kernel<<<(n_inc + 255) / 256, 256, 0, ctx->stream>>>(ctx->face_nodes.as<unsigned>(), n_inc, nn, ctx->csr_count.as<unsigned>());
+        ctx->launches++;
+    }
+    int rs = exclusive_scan(ctx, ctx->csr_count.as<unsigned>(), ctx->node_off.as<unsigned>(), (size_t)nn + 1, nullptr);
+    if (rs) return rs;
+    if (n_inc) {
+        csr_fill_kernel<<<(n_inc + 255) / 256, 256, 0, ctx->stream>>>(ctx->face_nodes.as<unsigned>(), n_inc, nn, ctx->node_off.as<unsigned>(),
+                                                                     ctx->csr_cursor.as<unsigned>(), ctx->node_inc.as<unsigned>());
+        csr_sort_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->node_off.as<unsigned>(), ctx->node_inc.as<unsigned>(), nn);
+        ctx->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+// Upload of the staged snapshot overlapped with the tet pass: positions first, then the tet arrays in chunks on a copy
+// stream; the compute stream validates and integrates chunk i while chunk i+1 is still in flight; faces last (CSR build,
+// forces follow).  Leaves the per-phase sums / means on the device like run_tet_pass.
+int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, double *d_sums_out, double *d_mean_out)
+{
+    const uint32_t nn = ctx->st_nodes, nt = ctx->st_tets, nf = ctx->st_faces;
+    ARG(nf < (1u << 30), "too many interface faces");
+    CK(ctx->pos4.ensure((size_t)nn * 32));
+    CK(ctx->pos4f.ensure((size_t)nn * 16));
+    CK(ctx->tet_nodes.ensure((size_t)nt * 16));
+    CK(ctx->tet_label.ensure((size_t)nt * 4));
+    CK(ctx->face_nodes.ensure((size_t)nf * 12));
+    CK(ctx->face_tets.ensure((size_t)nf * 8));
+    CK(ctx->face_isb.ensure((size_t)nf));
+    CK(ctx->node_off.ensure(((size_t)nn + 1) * 4));
+    CK(ctx->node_inc.ensure((size_t)nf * 12));
+    CK(ctx->csr_count.ensure(((size_t)nn + 1) * 4));
+    CK(ctx->csr_cursor.ensure(((size_t)nn + 1) * 4));
+    CK(ctx->h_flag.ensure(sizeof(int)));
+    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+    int C = ctx->pipeline_chunks;
+    if (C > 16) C = 16;
+    if (C < 1) C = 1;
+    // the copy stream must not overwrite arrays that kernels of the previous evaluation still read
+    CK(cudaEventRecord(ctx->ev_chunk[18], ks));
+    CK(cudaStreamWaitEvent(cs, ctx->ev_chunk[18], 0));
+    if (ctx->timers_on) CK(cudaEventRecord(ctx->ev[DSCGPU_T_H2D][0], cs));
+    if (nn) CK(cudaMemcpyAsync(ctx->pos4.p, ctx->h_pos4.p, (size_t)nn * 32, cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(ctx->ev_chunk[16], cs));
+    ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
+    ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
+    ctx->has_snapshot = true;
+    CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ks));
+    CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[16], 0));
+    if (nn) {
+        pos_to_float_kernel<<<(nn + 255) / 256, 256, 0, ks>>>(ctx->pos4.as<double4>(), ctx->pos4f.as<float4>(), nn);
+        ctx->launches++;
+    }
+    int r = tet_pass_begin(ctx);
+    if (r) return r;
+    TetPassOut none;
+    if (ctx->timers_on) CK(cudaEventRecord(ctx->ev[DSCGPU_T_TET][0], ks));
+    for (int c = 0; c < C; c++) {
+        const uint32_t b = (uint32_t)((uint64_t)nt * c / C), e = (uint32_t)((uint64_t)nt * (c + 1) / C);
+        if (e <= b) continue;
+        CK(cudaMemcpyAsync(ctx->tet_nodes.as<char>() + (size_t)b * 16, ctx->h_tet_nodes.as<char>() + (size_t)b * 16, (size_t)(e - b) * 16, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(ctx->tet_label.as<char>() + (size_t)b * 4, ctx->h_tet_label.as<char>() + (size_t)b * 4, (size_t)(e - b) * 4, cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(ctx->ev_chunk[c], cs));
+        CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[c], 0));
+        const size_t n_ids = 4 * (size_t)(e - b);
+        const unsigned grid = (unsigned)std::min<size_t>((n_ids + 255) / 256, (size_t)ctx->num_sms * 16);
+        validate_snapshot_kernel<<<grid, 256, 0, ks>>>(ctx->tet_nodes.as<unsigned>() + 4 * (size_t)b, n_ids, nullptr, 0, nullptr, 0, nn, nt,
+                                                      reinterpret_cast<int *>(ctr(ctx, 4)));
+        ctx->launches++;
+        r = tet_pass_range(ctx, nb_phase, 0, 0, nullptr, none, b, e, want_sq);
+        if (r) return r;
+    }
+    if (ctx->timers_on) { CK(cudaEventRecord(ctx->ev[DSCGPU_T_TET][1], ks)); ctx->ev_used[DSCGPU_T_TET] = true; }
+    if (nf) {
+        CK(cudaMemcpyAsync(ctx->face_nodes.p, ctx->h_face_nodes.p, (size_t)nf * 12, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(ctx->face_tets.p, ctx->h_face_tets.p, (size_t)nf * 8, cudaMemcpyHostToDevice, cs));
+        CK(cudaMemcpyAsync(ctx->face_isb.p, ctx->h_face_isb.p, (size_t)nf, cudaMemcpyHostToDevice, cs));
+    }
+    if (ctx->timers_on) { CK(cudaEventRecord(ctx->ev[DSCGPU_T_H2D][1], cs)); ctx->ev_used[DSCGPU_T_H2D] = true; }
+    CK(cudaEventRecord(ctx->ev_chunk[17], cs));
+    CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[17], 0));
+    {
+        const size_t n_ids = 3 * (size_t)nf + 2 * (size_t)nf;
+        if (n_ids) {
+            const unsigned grid = (unsigned)std::min<size_t>((n_ids + 255) / 256, (size_t)ctx->num_sms * 16);
+            validate_snapshot_kernel<<<grid, 256, 0, ks>>>(nullptr, 0, ctx->face_nodes.as<unsigned>(), 3 * (size_t)nf, ctx->face_tets.as<unsigned>(), 2 * (size_t)nf,
+                                                          nn, nt, reinterpret_cast<int *>(ctr(ctx, 4)));
+            ctx->launches++;
+        }
+        CK(cudaMemcpyAsync(ctx->h_flag.p, ctr(ctx, 4), sizeof(int), cudaMemcpyDeviceToHost, ks));
+        ctx->validation_pending = true;
+    }
+    r = build_csr_device(ctx);
+    if (r) return r;
+    return tet_pass_finish(ctx, nb_phase, d_sums_out, d_mean_out);
+}
+
 } // namespace
 
 extern "C" {
@@ -629,6 +774,7 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
     if (!ctx) return DSCGPU_ERR_ARG;
     *out = ctx; // returned even on failure so that dscgpu_last_error can be read; caller destroys it
     for (int i = 0; i < DSCGPU_T_COUNT; i++) { ctx->ev[i][0] = ctx->ev[i][1] = nullptr; ctx->ev_used[i] = false; }
+    for (int i = 0; i < 20; i++) ctx->ev_chunk[i] = nullptr;
     ARG(dims && dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "dims must be positive");
     ARG(dtype >= DSCGPU_U8 && dtype <= DSCGPU_F64, "unknown voxel dtype");
     int n_dev = 0;
@@ -638,6 +784,9 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
     ctx->device = device;
     CK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 20; i++) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+    if (const char *ev = getenv("DSCGPU_PIPELINE_CHUNKS")) ctx->pipeline_chunks = atoi(ev);
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < DSCGPU_T_COUNT; i++) { CK(cudaEventCreate(&ctx->ev[i][0])); CK(cudaEventCreate(&ctx->ev[i][1])); }
     ctx->dims[0] = dims[0]; ctx->dims[1] = dims[1]; ctx->dims[2] = dims[2];
@@ -709,6 +858,8 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
         if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]);
         if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]);
     }
+    for (int i = 0; i < 20; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return DSCGPU_OK;
@@ -812,25 +963,10 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
         if (nf) CK(cudaMemcpyAsync(ctx->face_tets.p, ctx->h_face_tets.p, (size_t)nf * 8, cudaMemcpyHostToDevice, s));
         if (nf) CK(cudaMemcpyAsync(ctx->face_isb.p, ctx->h_face_isb.p, (size_t)nf, cudaMemcpyHostToDevice, s));
     }
-    {   // node -> incident interface faces CSR on the device: count, exclusive scan, fill (slot by integer atomic), sort each list
-        CK(ctx->csr_count.ensure(((size_t)nn + 1) * 4));
-        CK(ctx->csr_cursor.ensure(((size_t)nn + 1) * 4));
-        CK(cudaMemsetAsync(ctx->csr_count.p, 0, ((size_t)nn + 1) * 4, ctx->stream));
-        CK(cudaMemsetAsync(ctx->csr_cursor.p, 0, ((size_t)nn + 1) * 4, ctx->stream));
-        const unsigned n_inc = 3u * nf;
-        if (n_inc) {
-            csr_count_kernel<<<(n_inc + 255) / 256, 256, 0, ctx->stream>>>(ctx->face_nodes.as<unsigned>(), n_inc, nn, ctx->csr_count.as<unsigned>());
-            ctx->launches++;
-        }
-        int rs = exclusive_scan(ctx, ctx->csr_count.as<unsigned>(), ctx->node_off.as<unsigned>(), (size_t)nn + 1, nullptr);
+    ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
+    {
+        int rs = build_csr_device(ctx);
         if (rs) return rs;
-        if (n_inc) {
-            csr_fill_kernel<<<(n_inc + 255) / 256, 256, 0, ctx->stream>>>(ctx->face_nodes.as<unsigned>(), n_inc, nn, ctx->node_off.as<unsigned>(),
-                                                                         ctx->csr_cursor.as<unsigned>(), ctx->node_inc.as<unsigned>());
-            csr_sort_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->node_off.as<unsigned>(), ctx->node_inc.as<unsigned>(), nn);
-            ctx->launches += 2;
-        }
-        CK(cudaGetLastError());
     }
     if (nn) {
         pos_to_float_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->pos4.as<double4>(), ctx->pos4f.as<float4>(), nn);
@@ -1092,12 +1228,34 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
     if (!ctx) return DSCGPU_ERR_ARG;
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE, "nb_phase out of range");
     int r;
+    bool tet_done = false;
     if (snap) {
-        r = dscgpu_set_snapshot(ctx, snap);
+        // stage the caller's arrays (host copy), upload below
+        dscgpu_snapshot_staging st;
+        ARG(snap->n_nodes_buffer == 0 || snap->pos, "pos is null");
+        ARG(snap->n_tets == 0 || (snap->tet_nodes && snap->tet_label), "tet arrays are null");
+        ARG(snap->n_faces == 0 || (snap->face_nodes && snap->face_tets && snap->face_is_boundary), "face arrays are null");
+        r = dscgpu_snapshot_staging_get(ctx, snap->n_nodes_buffer, snap->n_tets, snap->n_faces, &st);
         if (r) return r;
-    } else if (ctx->staging_valid) {
-        r = dscgpu_commit_snapshot(ctx);
-        if (r) return r;
+        for (size_t i = 0; i < snap->n_nodes_buffer; i++) {
+            st.pos4[4 * i] = snap->pos[3 * i]; st.pos4[4 * i + 1] = snap->pos[3 * i + 1]; st.pos4[4 * i + 2] = snap->pos[3 * i + 2]; st.pos4[4 * i + 3] = 0.0;
+        }
+        if (snap->n_tets) { memcpy(st.tet_nodes, snap->tet_nodes, (size_t)snap->n_tets * 16); memcpy(st.tet_label, snap->tet_label, (size_t)snap->n_tets * 4); }
+        if (snap->n_faces) {
+            memcpy(st.face_nodes, snap->face_nodes, (size_t)snap->n_faces * 12);
+            memcpy(st.face_tets, snap->face_tets, (size_t)snap->n_faces * 8);
+            memcpy(st.face_is_boundary, snap->face_is_boundary, (size_t)snap->n_faces);
+        }
+    }
+    if (snap || ctx->staging_valid) {
+        if (mean_mode == DSCGPU_MEAN_TET && ctx->pipeline_chunks > 0) {
+            r = upload_and_tet_pass_pipelined(ctx, nb_phase, ctx->hot_want_sq, ctx->sums.as<double>(), ctx->mean.as<double>());
+            if (r) return r;
+            tet_done = true;
+        } else {
+            r = dscgpu_commit_snapshot(ctx);
+            if (r) return r;
+        }
     }
     NEED_SNAPSHOT();
     size_t fbytes = sizeof(double) * 3 * (size_t)ctx->n_nodes;
@@ -1106,8 +1264,10 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
     if (mean_mode == DSCGPU_MEAN_ZRAY) {
         if (!ctx->has_sum_table) { ctx->err = "dscgpu_build_sum_table has not been called"; return DSCGPU_ERR_NO_SUMTABLE; }
         r = run_zray(ctx, nb_phase, 0, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>());
-    } else {
+    } else if (!tet_done) {
         r = run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), ctx->hot_want_sq);
+    } else {
+        r = DSCGPU_OK;
     }
     if (r) return r;
     r = run_forces(ctx, nb_phase, ctx->mean.as<double>(), force_mode, ctx->forces.as<double>());

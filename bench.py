@@ -338,7 +338,8 @@ def main_b200(args):
     # Every step: the host flattens the mesh into the library's pinned staging arrays (here: a copy from the resident
     # numpy snapshot, standing in for the is_mesh walk), H2D, kernels, D2H of the statistics and the forces.
     st = seg.staging(n_nodes, n_tets, n_faces)
-    host_forces = np.empty((n_nodes, 3))
+    pinned_forces = torch.empty(3 * n_nodes, dtype=torch.float64, pin_memory=True)
+    pinned_mean = torch.empty(P, dtype=torch.float64, pin_memory=True)
 
     def fill_staging():
         st["pos4"][:, :3] = snap["pos"]
@@ -361,8 +362,9 @@ def main_b200(args):
             seg.commit_snapshot()
             seg.set_partition(rng(n_tets), rng(n_faces), rng(n_nodes))
             step_device()
-            host_forces[...] = d_forces.view(-1, 3).cpu().numpy()
-            d_mean.cpu()
+            pinned_forces.copy_(d_forces, non_blocking=True)
+            pinned_mean.copy_(d_mean, non_blocking=True)
+            torch.cuda.synchronize(dev)
 
     for _ in range(3):
         step_e2e()

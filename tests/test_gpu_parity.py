@@ -149,7 +149,15 @@ def test_partition_sums_compose(case, pkg):
     seg.set_partition((0, nt), (0, nf), (0, nn))
     np.testing.assert_allclose(tot, whole["phase_total"], rtol=1e-12)
     np.testing.assert_allclose(vol, whole["phase_volume"], rtol=1e-12)
-    assert np.array_equal(F, F_whole)  # gather partitions by node: disjoint slices, x + 0 = x
+    # gather with a face partition: every rank adds its faces in order; the cross-rank sum re-associates (1e-12), it is
+    # bit-exact only when each context holds all faces (node-only partition, checked below)
+    np.testing.assert_allclose(F, F_whole, rtol=1e-12, atol=1e-12 * np.abs(F_whole).max())
+    Fn = np.zeros_like(F_whole)
+    for r in range(R):
+        seg.set_partition((0, nt), (0, nf), (nn * r // R, nn * (r + 1) // R))
+        Fn += seg.compute_external_force(mode=pkg.FORCE_GATHER, mean=g["mean"])
+    seg.set_partition((0, nt), (0, nf), (0, nn))
+    assert np.array_equal(Fn, F_whole)
     np.testing.assert_allclose(Fa, F_whole, rtol=RTOL, atol=RTOL * np.abs(F_whole).max())
 
 

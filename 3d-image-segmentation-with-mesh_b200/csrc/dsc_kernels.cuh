@@ -68,16 +68,26 @@ template <typename T> DSC_D double fetch(const T *__restrict__ vol, int X, int Y
     return 0.0;
 }
 
+// branch-free form of fetch: the load is always issued (from a clamped address) and the result selected, so that
+// independent fetches (the 8 corners of a trilinear cell) are in flight together instead of one per taken branch
+template <typename T> DSC_D double fetch_nb(const T *__restrict__ vol, int X, int Y, int Z, int x, int y, int z)
+{
+    const bool inb = (unsigned)x < (unsigned)X && (unsigned)y < (unsigned)Y && (unsigned)z < (unsigned)Z;
+    const size_t idx = inb ? ((size_t)z * Y + y) * X + x : 0;
+    const T raw = __ldg(vol + idx);
+    return inb ? decode<T>(raw) : 0.0;
+}
+
 // image3d::get_value_f (DEMO/image3d.cpp:226-251): floor, 8 fetches, lerp along x, then y, then z
 template <typename T> DSC_D double fetch_trilinear(const T *__restrict__ vol, int X, int Y, int Z, V3 pt)
 {
     double fx = floor(pt.x), fy = floor(pt.y), fz = floor(pt.z);
     int ix = (int)fx, iy = (int)fy, iz = (int)fz;
     double rx = pt.x - (double)ix, ry = pt.y - (double)iy, rz = pt.z - (double)iz;
-    double v000 = fetch(vol, X, Y, Z, ix, iy, iz), v100 = fetch(vol, X, Y, Z, ix + 1, iy, iz);
-    double v001 = fetch(vol, X, Y, Z, ix, iy, iz + 1), v101 = fetch(vol, X, Y, Z, ix + 1, iy, iz + 1);
-    double v010 = fetch(vol, X, Y, Z, ix, iy + 1, iz), v110 = fetch(vol, X, Y, Z, ix + 1, iy + 1, iz);
-    double v011 = fetch(vol, X, Y, Z, ix, iy + 1, iz + 1), v111 = fetch(vol, X, Y, Z, ix + 1, iy + 1, iz + 1);
+    double v000 = fetch_nb(vol, X, Y, Z, ix, iy, iz), v100 = fetch_nb(vol, X, Y, Z, ix + 1, iy, iz);
+    double v001 = fetch_nb(vol, X, Y, Z, ix, iy, iz + 1), v101 = fetch_nb(vol, X, Y, Z, ix + 1, iy, iz + 1);
+    double v010 = fetch_nb(vol, X, Y, Z, ix, iy + 1, iz), v110 = fetch_nb(vol, X, Y, Z, ix + 1, iy + 1, iz);
+    double v011 = fetch_nb(vol, X, Y, Z, ix, iy + 1, iz + 1), v111 = fetch_nb(vol, X, Y, Z, ix + 1, iy + 1, iz + 1);
     double c00 = v000 * (1 - rx) + v100 * rx;
     double c01 = v001 * (1 - rx) + v101 * rx;
     double c10 = v010 * (1 - rx) + v110 * rx;
@@ -1600,7 +1610,6 @@ template <typename VoxT> __global__ void __launch_bounds__(128) force_gather_ker
     a.forces[3 * (size_t)v] = fx;
     a.forces[3 * (size_t)v + 1] = fy;
     a.forces[3 * (size_t)v + 2] = fz;
-    if (ng) atomicAdd(a.gauss_count, ng);
 }
 
 // Warp-per-node gather (default): same result as force_gather_kernel, bit for bit, with the work of a node spread over
@@ -1666,9 +1675,6 @@ template <typename VoxT> __global__ void __launch_bounds__(128) force_warp_kerne
         __syncwarp();
     }
     if (lane < 3) a.forces[3 * (size_t)v + lane] = acc;
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) ngc += __shfl_xor_sync(0xffffffffu, ngc, m);
-    if (lane == 0 && ngc) atomicAdd(a.gauss_count, ngc);
 }
 
 // Two-kernel deterministic gather (default):
@@ -1690,25 +1696,35 @@ struct ForceFaceArgs {
     unsigned long long *gauss_count;
 };
 
+// kFaceLanes threads per face: thread s evaluates Gauss points s, s+kFaceLanes, ... of the face (sets have at most 12
+// points), so the dependent load chain of a face (ids -> labels/tet ids -> positions -> 8 voxel corners) is walked by a
+// few threads in parallel instead of once per Gauss point in sequence.
+constexpr int kFaceLanes = 4;
+
 template <typename VoxT> __global__ void __launch_bounds__(128) force_face_kernel(const ForceFaceArgs a)
 {
-    const unsigned f = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned f = a.begin + gt / kFaceLanes;
+    const int slot = (int)(gt % kFaceLanes);
     if (f >= a.end) return;
     const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
     FaceGeom g;
     unsigned n[3];
-    if (!face_setup(a.mesh, f, a.nb_phase, a.mean, g, n)) { a.fset[f] = -1; return; }
-    a.fset[f] = (signed char)g.gs;
-    double *out = a.fbuf + (size_t)f * 36;
-    int k = 0;
-    for (int q = c_gauss_off[g.gs]; q < c_gauss_off[g.gs + 1]; q++, k++) {
+    if (!face_setup(a.mesh, f, a.nb_phase, a.mean, g, n)) {
+        if (slot == 0) a.fset[f] = -1;
+        return;
+    }
+    const int q0 = c_gauss_off[g.gs], ng = c_gauss_off[g.gs + 1] - q0;
+    if (slot == 0) a.fset[f] = (signed char)g.gs;
+    for (int k = slot; k < ng; k += kFaceLanes) {
+        const int q = q0 + k;
         const double w = c_gauss[4 * q], b0 = c_gauss[4 * q + 1], b1 = c_gauss[4 * q + 2], b2 = c_gauss[4 * q + 3];
         const V3 p = add(add(mul(g.p[0], b0), mul(g.p[1], b1)), mul(g.p[2], b2)); // get_coord_tri
         const double I = fetch_trilinear(vol, a.vol.X, a.vol.Y, a.vol.Z, p);
         const V3 fv = mul(g.norm, (2 * I - g.c0 - g.c1) * (g.c0 - g.c1) * w * g.area);
-        out[3 * k] = fv.x; out[3 * k + 1] = fv.y; out[3 * k + 2] = fv.z;
+        double *out = a.fbuf + (size_t)f * 36 + 3 * k;
+        out[0] = fv.x; out[1] = fv.y; out[2] = fv.z;
     }
-    atomicAdd(a.gauss_count, (unsigned long long)k);
 }
 
 struct ForceNodeArgs {
@@ -1716,30 +1732,77 @@ struct ForceNodeArgs {
     const double *fbuf;
     const signed char *fset;
     double *forces;
-    unsigned begin, end; // node range
+    unsigned begin, end;          // node range handled by this context
+    const unsigned *active_nodes; // nodes that have interface faces, ascending (built with the CSR)
+    const unsigned *n_active;     // device-resident length of that list
 };
 
+// 8 lanes per node: lane l fetches the addends f*coord of incident entry l (up to 12 Gauss points) into shared memory,
+// then lanes 0..2 of the group add the x/y/z components in order (entries ascending = faces ascending, Gauss points in
+// table order).  The loads of a node run in parallel; only the additions are sequential, as the reference's are.
 __global__ void __launch_bounds__(128) force_node_kernel(const ForceNodeArgs a)
 {
-    const unsigned v = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= a.end) return;
-    const unsigned e0 = __ldg(a.mesh.node_off + v), e1 = __ldg(a.mesh.node_off + v + 1);
-    double fx = 0, fy = 0, fz = 0;
-    for (unsigned e = e0; e < e1; e++) {
-        const unsigned inc = __ldg(a.mesh.node_inc + e);
-        const unsigned f = inc >> 2, corner = inc & 3u;
-        const int gs = a.fset[f];
-        if (gs < 0) continue;
-        const double *fb = a.fbuf + (size_t)f * 36;
-        int k = 0;
-        for (int q = c_gauss_off[gs]; q < c_gauss_off[gs + 1]; q++, k++) {
-            const double bc = c_gauss[4 * q + 1 + corner];
-            fx += fb[3 * k] * bc; fy += fb[3 * k + 1] * bc; fz += fb[3 * k + 2] * bc;
+    __shared__ double slab[16][8][12][3]; // [group in CTA][entry lane][gauss][component]
+    __shared__ signed char ngs[16][8];
+    const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+    const unsigned item = blockIdx.x * 16 + grp;
+    const unsigned v = item < __ldg(a.n_active) ? __ldg(a.active_nodes + item) : 0xFFFFFFFFu;
+    const bool live = v != 0xFFFFFFFFu && v >= a.begin && v < a.end;
+    unsigned e0 = 0, e1 = 0;
+    if (live) { e0 = __ldg(a.mesh.node_off + v); e1 = __ldg(a.mesh.node_off + v + 1); }
+    double acc = 0; // lanes 0..2 of the group: x, y, z
+    for (unsigned eb = e0; eb < e1; eb += 8) {
+        const unsigned e = eb + lane8;
+        int ng = 0;
+        if (e < e1) {
+            const unsigned inc = __ldg(a.mesh.node_inc + e);
+            const unsigned f = inc >> 2, corner = inc & 3u;
+            const int gs = a.fset[f];
+            if (gs >= 0) {
+                const double *fb = a.fbuf + (size_t)f * 36;
+                const int q0 = c_gauss_off[gs];
+                ng = c_gauss_off[gs + 1] - q0;
+                for (int k = 0; k < ng; k++) {
+                    const double bc = c_gauss[4 * (q0 + k) + 1 + corner];
+                    slab[grp][lane8][k][0] = fb[3 * k] * bc;
+                    slab[grp][lane8][k][1] = fb[3 * k + 1] * bc;
+                    slab[grp][lane8][k][2] = fb[3 * k + 2] * bc;
+                }
+            }
+        }
+        ngs[grp][lane8] = (signed char)ng;
+        __syncwarp(gmask);
+        if (lane8 < 3) {
+            const int cnt = (int)min(8u, e1 - eb);
+            for (int l = 0; l < cnt; l++) {
+                const int m = ngs[grp][l];
+                for (int k = 0; k < m; k++) acc += slab[grp][l][k][lane8];
+            }
+        }
+        __syncwarp(gmask);
+    }
+    if (live && lane8 < 3) a.forces[3 * (size_t)v + lane8] = acc;
+}
+
+// Instrumentation only (bench roofline bytes): number of Gauss points the force pass evaluates, recomputed on demand so
+// that the force kernels carry no same-address atomics (93 K of them serialised in L2 and cost 0.09 ms).
+__global__ void gauss_count_kernel(MeshView m, unsigned begin, unsigned end, unsigned long long *count)
+{
+    const unsigned f = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long ng = 0;
+    if (f < end) {
+        const unsigned t0 = m.face_tets[2 * (size_t)f], t1 = m.face_tets[2 * (size_t)f + 1];
+        if (t0 != kNoTet && t1 != kNoTet) {
+            const double ar = tri_area(load_pos(m.pos4, m.face_nodes[3 * (size_t)f]), load_pos(m.pos4, m.face_nodes[3 * (size_t)f + 1]),
+                                       load_pos(m.pos4, m.face_nodes[3 * (size_t)f + 2]));
+            const int gs = gauss_set(ar);
+            ng = (unsigned long long)(c_gauss_off[gs + 1] - c_gauss_off[gs]);
         }
     }
-    a.forces[3 * (size_t)v] = fx;
-    a.forces[3 * (size_t)v + 1] = fy;
-    a.forces[3 * (size_t)v + 2] = fz;
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) ng += __shfl_xor_sync(0xffffffffu, ng, k);
+    if ((threadIdx.x & 31) == 0 && ng) atomicAdd(count, ng);
 }
 
 // ---- node -> incident interface faces CSR built on the device (was a host counting sort: ~1 ms of the end-to-end step)
@@ -1760,6 +1823,18 @@ __global__ void csr_fill_kernel(const unsigned *__restrict__ face_nodes, unsigne
     if (v >= n_nodes) return;
     const unsigned slot = atomicAdd(cursor + v, 1u);
     inc[off[v] + slot] = ((i / 3u) << 2) | (i % 3u);
+}
+
+__global__ void csr_flag_kernel(const unsigned *__restrict__ count, unsigned n_nodes, unsigned *flag)
+{
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v <= n_nodes) flag[v] = (v < n_nodes && count[v] > 0) ? 1u : 0u;
+}
+
+__global__ void csr_compact_kernel(const unsigned *__restrict__ count, const unsigned *__restrict__ apos, unsigned n_nodes, unsigned *active)
+{
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n_nodes && count[v] > 0) active[apos[v]] = v;
 }
 
 // every node's list sorted ascending (= face ascending: the reference's accumulation order)
@@ -1804,7 +1879,6 @@ template <typename VoxT> __global__ void __launch_bounds__(128) force_atomic_ker
         atomicAdd(a.forces + 3 * (size_t)n[k] + 1, acc[k][1]);
         atomicAdd(a.forces + 3 * (size_t)n[k] + 2, acc[k][2]);
     }
-    atomicAdd(a.gauss_count, ng);
 }
 
 // =================================================================================================

@@ -80,7 +80,7 @@ struct dscgpu_ctx {
 
     bool has_snapshot = false;
     uint32_t n_nodes = 0, n_tets = 0, n_faces = 0;
-    DevBuf pos4, pos4f, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc, csr_count, csr_cursor, fbuf, fset;
+    DevBuf pos4, pos4f, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc, csr_count, csr_cursor, csr_flag, csr_apos, node_active, fbuf, fset;
     // pinned staging (host side of the snapshot)
     PinBuf h_pos4, h_tet_nodes, h_tet_label, h_face_nodes, h_face_tets, h_face_isb, h_node_off, h_node_inc, h_node_active, h_out, h_flag;
     bool validation_pending = false;
@@ -492,7 +492,7 @@ int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, do
         fa.begin = ctx->face_b; fa.end = ctx->face_e;
         if (!whole_faces && nf) CK(cudaMemsetAsync(ctx->fset.p, 0xFF, nf, ctx->stream));
         if (fa.end > fa.begin) {
-            const unsigned grid = (fa.end - fa.begin + 127) / 128;
+            const unsigned grid = (unsigned)(((size_t)(fa.end - fa.begin) * kFaceLanes + 127) / 128);
             switch (ctx->dtype) {
             case DSCGPU_U8: force_face_kernel<unsigned char><<<grid, 128, 0, ctx->stream>>>(fa); break;
             case DSCGPU_U16: force_face_kernel<unsigned short><<<grid, 128, 0, ctx->stream>>>(fa); break;
@@ -507,12 +507,16 @@ int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, do
         // range of the partition is enough (and the result is the reference's, bit for bit)
         if (whole_faces) {
             na.begin = ctx->node_b; na.end = ctx->node_e;
-            if (!whole_nodes) CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
         } else {
             na.begin = 0; na.end = ctx->n_nodes;
         }
-        if (na.end > na.begin) {
-            force_node_kernel<<<(na.end - na.begin + 127) / 128, 128, 0, ctx->stream>>>(na);
+        na.active_nodes = ctx->node_active.as<unsigned>();
+        na.n_active = reinterpret_cast<const unsigned *>(ctr(ctx, 5));
+        // the node pass only writes nodes that have interface faces: everything else must read as zero
+        CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
+        const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * nf);
+        if (na.end > na.begin && max_active) {
+            force_node_kernel<<<(max_active + 15) / 16, 128, 0, ctx->stream>>>(na);
             ctx->launches++;
         }
         CK(cudaGetLastError());
@@ -670,6 +674,20 @@ int build_csr_device(dscgpu_ctx *ctx)
     }
     int rs = exclusive_scan(ctx, ctx->csr_count.as<unsigned>(), ctx->node_off.as<unsigned>(), (size_t)nn + 1, nullptr);
     if (rs) return rs;
+    {   // compact list of the nodes that have interface faces (ascending); its length stays on the device (counter 5)
+        CK(ctx->csr_flag.ensure(((size_t)nn + 1) * 4));
+        CK(ctx->csr_apos.ensure(((size_t)nn + 1) * 4));
+        CK(ctx->node_active.ensure(((size_t)nn + 1) * 4));
+        csr_flag_kernel<<<(nn + 256) / 256, 256, 0, ctx->stream>>>(ctx->csr_count.as<unsigned>(), nn, ctx->csr_flag.as<unsigned>());
+        ctx->launches++;
+        rs = exclusive_scan(ctx, ctx->csr_flag.as<unsigned>(), ctx->csr_apos.as<unsigned>(), (size_t)nn + 1, reinterpret_cast<unsigned *>(ctr(ctx, 5)));
+        if (rs) return rs;
+        if (nn) {
+            csr_compact_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->csr_count.as<unsigned>(), ctx->csr_apos.as<unsigned>(), nn,
+                                                                         ctx->node_active.as<unsigned>());
+            ctx->launches++;
+        }
+    }
     if (n_inc) {
         csr_fill_kernel<<<(n_inc + 255) / 256, 256, 0, ctx->stream>>>(ctx->face_nodes.as<unsigned>(), n_inc, nn, ctx->node_off.as<unsigned>(),
                                                                      ctx->csr_cursor.as<unsigned>(), ctx->node_inc.as<unsigned>());
@@ -839,7 +857,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_OK;
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    DevBuf *bufs[] = {&ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
+    DevBuf *bufs[] = {&ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
                       &ctx->partials, &ctx->sums, &ctx->mean, &ctx->forces, &ctx->counters, &ctx->o_total, &ctx->o_vol, &ctx->o_mean, &ctx->o_energy,
                       &ctx->o_variation, &ctx->o_hash, &ctx->o_nsamp, &ctx->ray_count, &ctx->ray_offset, &ctx->ray_cursor, &ctx->hits, &ctx->block_sums,
                       &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
@@ -1411,7 +1429,17 @@ static uint64_t read_counter(dscgpu_ctx *ctx, int i)
     return v;
 }
 uint64_t dscgpu_last_sample_count(dscgpu_ctx *ctx) { return read_counter(ctx, 0); }
-uint64_t dscgpu_last_gauss_count(dscgpu_ctx *ctx) { return read_counter(ctx, 1); }
+uint64_t dscgpu_last_gauss_count(dscgpu_ctx *ctx)
+{
+    if (!ctx || !ctx->has_snapshot || !ctx->counters.p) return 0;
+    cudaMemsetAsync(ctr(ctx, 1), 0, sizeof(unsigned long long), ctx->stream);
+    const unsigned n = ctx->face_e - ctx->face_b;
+    if (n) {
+        gauss_count_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(mesh_view(ctx), ctx->face_b, ctx->face_e, ctr(ctx, 1));
+        ctx->launches++;
+    }
+    return read_counter(ctx, 1);
+}
 
 int dscgpu_host_sort_hits(int n, int32_t *z, uint8_t *b_in)
 {

@@ -767,15 +767,13 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
 }
 
 // -------------------------------------------------------------------------------------------------
-// w3 (variant 256): w2 with the per-sample instruction count cut further and independent group progression.
+// w3 (variant 256): w2 with the per-sample instruction count cut further.
 //   * the float chain starts at Q0 + 128 with O = floor(min corner) - 1, so the result t lies in [128, 256): its
 //     mantissa IS the fixed-point relative coordinate with 16 fraction bits.  floor = byte 2 of the bit pattern (one
 //     PRMT), the distance to the nearest voxel boundary is the low 16 bits: no FADD/F2I at all.  A sample is "unsafe"
 //     when its fraction is within K units of 2^-16 of an integer; K covers the c0 rounding (0.5), four FFMA roundings
 //     at ulp(t) = 2^-16 (2.0), the float rounding of E_k (6*2^-24*R) and the lattice perturbation tau (4*4.45e-7*R),
 //     R = Rmax + 1:  K = ceil(3 + 0.141 R).
-//   * each group of 8 lanes walks its own 8 tets of the tile at its own pace (a 27-sample tet next to a 64-sample
-//     tet no longer idles for a batch); group-local shuffles use the group's lane mask.
 //   * the widened voxel uses one special-value test per batch; the second moment is optional.
 // -------------------------------------------------------------------------------------------------
 template <typename VoxT, bool WANT_SQ, bool PER_TET>
@@ -853,44 +851,39 @@ __global__ void __launch_bounds__(256, 3) tet_integrate_w3_kernel(const TetArgs 
             w_m[warp][lane] = make_int2(meta, olin);
         }
         __syncwarp();
-        // ---------------- phase B: each group walks tets grp, grp+4, ... of the tile at its own pace ----------------
-        int r = 0;          // next tet slot of this group
-        bool have = false;  // a tet is in progress
-        int j = 0, n3 = 0, off = 0, base = 0, label = 0;
-        bool fastp = false;
-        float4 q0 = make_float4(0, 0, 0, 0), e1 = q0, e2 = q0, e3 = q0;
-        int obase = 0;
-        double s = 0, sq = 0;
-        unsigned long long isum = 0, isq = 0;
-        while (true) {
-            if (!have) {
-                while (r < 8) {
-                    const int2 mm = w_m[warp][r * 4 + grp];
-                    if (mm.x & (1 << 12)) {
-                        j = r * 4 + grp;
-                        label = mm.x & 0xff;
-                        const int L = (mm.x >> 8) & 0xf;
-                        n3 = (L + 1) * (L + 1) * (L + 1);
-                        off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
-                        fastp = (mm.x & (1 << 13)) != 0;
-                        obase = mm.y;
-                        if (fastp) { q0 = w_q0[warp][j]; e1 = w_e1[warp][j]; e2 = w_e2[warp][j]; e3 = w_e3[warp][j]; }
-                        base = lane_g;
-                        s = 0; sq = 0; isum = 0; isq = 0;
-                        have = true;
-                        r++;
-                        break;
-                    }
-                    r++;
+        // ---------------- phase B: 8 lanes <-> tet; group grp takes tets grp, grp+4, ... of the tile ----------------
+        for (int r = 0; r < 8; r++) {
+            const int j = r * 4 + grp;
+            const int2 mm = w_m[warp][j];
+            const int meta = mm.x;
+            const bool active = (meta & (1 << 12)) != 0;
+            const int label = meta & 0xff;
+            const int L = (meta >> 8) & 0xf;
+            const int n3 = active ? (L + 1) * (L + 1) * (L + 1) : 0;
+            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+            double s = 0, sq = 0;
+            unsigned long long isum = 0, isq = 0;
+            auto add_voxel = [&](VoxT val) {
+                if constexpr (VoxTraits<VoxT>::integral) {
+                    const unsigned q = (unsigned)val;
+                    isum += q;
+                    if (WANT_SQ) isq += (unsigned long long)q * q;
+                } else {
+                    double I;
+                    if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val);
+                    else I = (double)val;
+                    s += I;
+                    if (WANT_SQ) sq = fma(I, I, sq);
                 }
-            }
-            if (!__any_sync(0xffffffffu, have)) break;
-            if (have) {
-                int idx[U];
-                if (fastp) {
-                    const unsigned kk = __float_as_uint(q0.w); // K << 16
-                    const float4 *__restrict__ tl = s_lat + off;
-                    const int last = n3 - 1;
+            };
+            if (meta & (1 << 13)) {
+                const float4 q0 = w_q0[warp][j], e1 = w_e1[warp][j], e2 = w_e2[warp][j], e3 = w_e3[warp][j];
+                const unsigned kk = __float_as_uint(q0.w); // K << 16
+                const int obase = mm.y;
+                const float4 *__restrict__ tl = s_lat + off;
+                const int last = n3 - 1;
+                for (int base = lane_g; base < n3; base += G * U) {
+                    int idx[U];
                     unsigned worst = 0xffffffffu;
 #pragma unroll
                     for (int u = 0; u < U; u++) {
@@ -900,9 +893,8 @@ __global__ void __launch_bounds__(256, 3) tet_integrate_w3_kernel(const TetArgs 
                         const float ty = fmaf(c.z, e3.y, fmaf(c.y, e2.y, fmaf(c.x, e1.y, fmaf(c.w, e2.w, q0.y))));
                         const float tz = fmaf(c.z, e3.z, fmaf(c.y, e2.z, fmaf(c.x, e1.z, fmaf(c.w, e3.w, q0.z))));
                         const unsigned ux = __float_as_uint(tx), uy = __float_as_uint(ty), uz = __float_as_uint(tz);
-                        // fraction field (16 bits) shifted to the top, biased by K: small value <=> within K units of an integer
-                        const unsigned fx = ux * 65536u + kk, fy = uy * 65536u + kk, fz = uz * 65536u + kk;
-                        const unsigned m = min(min(fx, fy), fz);
+                        // fraction field (16 bits) moved to the top and biased by K: a small value <=> within K*2^-16 of an integer
+                        const unsigned m = min(min(ux * 65536u + kk, uy * 65536u + kk), uz * 65536u + kk);
                         const int lin = (int)(__byte_perm(uz, 0, 0x4442) * (unsigned)XYi + __byte_perm(uy, 0, 0x4442) * (unsigned)X + __byte_perm(ux, 0, 0x4442)) + obase;
                         const bool ok = i <= last;
                         idx[u] = ok ? lin : -1;
@@ -924,12 +916,20 @@ __global__ void __launch_bounds__(256, 3) tet_integrate_w3_kernel(const TetArgs 
                             }
                         }
                     }
-                } else {
-                    // exact path (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491)
-                    const uint4 nd = w_nd[warp][j];
-                    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-                    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+                    VoxT val[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
+#pragma unroll
+                    for (int u = 0; u < U; u++) add_voxel(val[u]);
+                }
+            } else if (active) {
+                // exact path (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491)
+                const uint4 nd = w_nd[warp][j];
+                const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+                for (int base = lane_g; base < n3; base += G * U) {
+                    int idx[U];
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const int i = base + u * G;
@@ -942,80 +942,40 @@ __global__ void __launch_bounds__(256, 3) tet_integrate_w3_kernel(const TetArgs 
                             if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) idx[u] = iz * XYi + iy * X + ix;
                         }
                     }
+                    VoxT val[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
+#pragma unroll
+                    for (int u = 0; u < U; u++) add_voxel(val[u]);
                 }
-                VoxT val[U];
+            }
+            if constexpr (VoxTraits<VoxT>::integral) {
+                const double dn = VoxTraits<VoxT>::denom();
+                s = (double)isum / dn;
+                if (WANT_SQ) sq = (double)isq / (dn * dn);
+            }
 #pragma unroll
-                for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
-                if constexpr (VoxTraits<VoxT>::integral) {
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const unsigned q = (unsigned)val[u];
-                        isum += q;
-                        if (WANT_SQ) isq += (unsigned long long)q * q;
-                    }
-                } else if constexpr (sizeof(VoxT) == 4) {
-                    // exact widening with integer ops; one test per batch for zeros / denormals / inf / nan (exponent 0 or 255)
-                    unsigned bits[U];
-                    bool special = false;
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        bits[u] = __float_as_uint((float)val[u]);
-                        special |= ((bits[u] + 0x00800000u) & 0x7f000000u) == 0u;
-                    }
-                    if (!special) {
-#pragma unroll
-                        for (int u = 0; u < U; u++) {
-                            const unsigned hi = (((bits[u] & 0x7fffffffu) >> 3) + 0x38000000u) | (bits[u] & 0x80000000u);
-                            const double I = __hiloint2double((int)hi, (int)(bits[u] << 29));
-                            s += I;
-                            if (WANT_SQ) sq = fma(I, I, sq);
-                        }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < U; u++) {
-                            const double I = (double)(float)val[u];
-                            s += I;
-                            if (WANT_SQ) sq = fma(I, I, sq);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const double I = (double)val[u];
-                        s += I;
-                        if (WANT_SQ) sq = fma(I, I, sq);
+            for (int m = G / 2; m >= 1; m >>= 1) {
+                s += shfl_xor_d(s, m);
+                if (WANT_SQ) sq += shfl_xor_d(sq, m);
+            }
+            if (active) {
+                const double v = w_v[warp][j];
+                const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
+                const double tsq = WANT_SQ ? sq * v / (double)n3 : 0.0;
+                if (lane_g == 0) {
+                    nsamp += (unsigned long long)n3;
+                    if (PER_TET) {
+                        const unsigned t = base_t + j;
+                        if (a.tet_total) a.tet_total[t] = tot;
+                        if (a.tet_vol) a.tet_vol[t] = v;
+                        if (a.tet_mean) a.tet_mean[t] = tot / v;
                     }
                 }
-                base += G * U;
-                if (base - lane_g >= n3) { // tet finished: group reduction and bookkeeping (the 8 lanes of the group are converged)
-                    if constexpr (VoxTraits<VoxT>::integral) {
-                        const double dn = VoxTraits<VoxT>::denom();
-                        s = (double)isum / dn;
-                        if (WANT_SQ) sq = (double)isq / (dn * dn);
-                    }
-#pragma unroll
-                    for (int m = G / 2; m >= 1; m >>= 1) {
-                        s += __shfl_xor_sync(gmask, s, m);
-                        if (WANT_SQ) sq += __shfl_xor_sync(gmask, sq, m);
-                    }
-                    const double v = w_v[warp][j];
-                    const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
-                    const double tsq = WANT_SQ ? sq * v / (double)n3 : 0.0;
-                    if (lane_g == 0) {
-                        nsamp += (unsigned long long)n3;
-                        if (PER_TET) {
-                            const unsigned t = base_t + j;
-                            if (a.tet_total) a.tet_total[t] = tot;
-                            if (a.tet_vol) a.tet_vol[t] = v;
-                            if (a.tet_mean) a.tet_mean[t] = tot / v;
-                        }
-                    }
-                    if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
-                        acc_tot += tot;
-                        acc_sq += tsq;
-                        acc_vol += v;
-                    }
-                    have = false;
+                if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
+                    acc_tot += tot;
+                    acc_sq += tsq;
+                    acc_vol += v;
                 }
             }
         }

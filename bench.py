@@ -70,7 +70,7 @@ class ClockSampler:
             os.close(fd)
             q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -219,7 +219,7 @@ def main_reference(args):
     value = info["units"] / t
     cfg = pkg.synthetic.CONFIGS[args.config]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %d^3 %s phantom, %d phases (bounded sample, see cpu_baseline.sample)" % (
                 args.config, cfg["n"], np.dtype(cfg["dtype"]).name, cfg["nb_phase"])},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
@@ -302,13 +302,13 @@ def main_b200(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing: K steps, each bracketed by events, L2 flushed in between ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # samples clocks / throttle reasons from the warm-up to the end of the end-to-end loop
     for _ in range(max(3, args.warmup)):
         flush_l2(torch, l2_buf)
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     # ---- per-kernel durations (library CUDA events on the launching stream), eager launches ----
     tet_ms, force_ms = [], []
     for i in range(min(args.steps, 10)):
@@ -457,7 +457,7 @@ def main_b200(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "tet_integrate_kernel" if mean_mode == pkg.MEAN_TET else "zray pass", "kernel_ms": kernel_ms,
+                "kernel": "tet_integrate_w2_kernel" if mean_mode == pkg.MEAN_TET else "zray pass", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": tet_bytes_rank, "peak_source": peak_src,
                 "whole_step": {"algorithmic_bytes": tet_bytes + face_bytes, "achieved": (tet_bytes + face_bytes) / world / (ms_per_step * 1e-3) / 1e9}}
 

@@ -569,19 +569,28 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
         const int nb = (int)min(32u, a.tet_end - base_t);
         __syncwarp();
         // ---------------- phase A: lane <-> tet ----------------
+        // Records are stored in a permuted order: tets with at most 32 samples first, then the larger ones, inactive tets
+        // last -- the four groups of a phase-B round then mostly run the same number of batches (a 27-sample tet next to a
+        // 64-sample one would idle for a batch) and rounds past the last active tet are skipped.
+        int n_act = 0;
         {
-            int meta = 0;
+            int meta = 0, olin = 0;
+            bool active = false, big = false, fast = false;
+            float4 rq0 = make_float4(0, 0, 0, 0), re1 = rq0, re2 = rq0, re3 = rq0;
+            double rv = 0;
+            uint4 rnd = make_uint4(0, 0, 0, 0);
             if (lane < nb) {
                 const unsigned t = base_t + lane;
                 const int label = __ldg(a.mesh.tet_label + t);
-                const bool active = a.include_bound || label != 0;
-                meta = label & 0xff;
+                active = a.include_bound || label != 0;
+                meta = (label & 0xff) | (lane << 16);
                 if (active) {
                     const uint4 nd = __ldg(a.mesh.tet_nodes + t);
                     const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
                     const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
                     const double v = tet_volume(p0, p1, p2, p3);
                     const int L = tet_level(v);
+                    big = (L + 1) * (L + 1) * (L + 1) > G * U;
                     const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
                     const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
                     const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
@@ -589,35 +598,42 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     const bool interior = lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5;
                     const double ox = floor(lox), oy = floor(loy), oz = floor(loz);
                     const double rmax = fmax(fmax(hix - ox, hiy - oy), hiz - oz);
-                    const bool fast = interior && L < kSmemLevels && rmax < 100.0;
+                    fast = interior && L < kSmemLevels && rmax < 100.0;
+                    meta |= (L << 8) | (1 << 12);
                     if (fast) {
                         const double inv4n = 1.0 / (double)(4 * (L + 1));
-                        const double q0x = p0.x - ox, q0y = p0.y - oy, q0z = p0.z - oz;
-                        w_q0[warp][lane] = make_float4((float)(q0x - 0.5), (float)(q0y - 0.5), (float)(q0z - 0.5),
-                                                       0.5f - (48.0f * (float)rmax + 8.0f) * 5.9604644775390625e-08f);
-                        w_e1[warp][lane] = make_float4((float)((p1.x - p0.x) * inv4n), (float)((p1.y - p0.y) * inv4n), (float)((p1.z - p0.z) * inv4n), (float)ox);
-                        w_e2[warp][lane] = make_float4((float)((p2.x - p0.x) * inv4n), (float)((p2.y - p0.y) * inv4n), (float)((p2.z - p0.z) * inv4n), (float)oy);
-                        w_e3[warp][lane] = make_float4((float)((p3.x - p0.x) * inv4n), (float)((p3.y - p0.y) * inv4n), (float)((p3.z - p0.z) * inv4n), (float)oz);
-                        const unsigned olin = (unsigned)((int)oz * XYi + (int)oy * X + (int)ox) - fold;
-                        w_m[warp][lane] = make_int2(meta | (L << 8) | (1 << 12) | (1 << 13), (int)olin);
-                    } else {
-                        w_m[warp][lane] = make_int2(meta | (L << 8) | (1 << 12), 0);
+                        rq0 = make_float4((float)((p0.x - ox) - 0.5), (float)((p0.y - oy) - 0.5), (float)((p0.z - oz) - 0.5),
+                                          0.5f - (48.0f * (float)rmax + 8.0f) * 5.9604644775390625e-08f);
+                        re1 = make_float4((float)((p1.x - p0.x) * inv4n), (float)((p1.y - p0.y) * inv4n), (float)((p1.z - p0.z) * inv4n), (float)ox);
+                        re2 = make_float4((float)((p2.x - p0.x) * inv4n), (float)((p2.y - p0.y) * inv4n), (float)((p2.z - p0.z) * inv4n), (float)oy);
+                        re3 = make_float4((float)((p3.x - p0.x) * inv4n), (float)((p3.y - p0.y) * inv4n), (float)((p3.z - p0.z) * inv4n), (float)oz);
+                        olin = (int)((unsigned)((int)oz * XYi + (int)oy * X + (int)ox) - fold);
+                        meta |= 1 << 13;
                     }
-                    w_v[warp][lane] = v;
-                    w_nd[warp][lane] = nd;
+                    rv = v;
+                    rnd = nd;
                 } else {
-                    w_m[warp][lane] = make_int2(meta, 0);
                     if (a.tet_total) a.tet_total[t] = -1.0;
                     if (a.tet_vol) a.tet_vol[t] = -1.0;
                     if (a.tet_mean) a.tet_mean[t] = -1.0;
                 }
-            } else {
-                w_m[warp][lane] = make_int2(0, 0);
+            }
+            const unsigned m_small = __ballot_sync(0xffffffffu, active && !big);
+            const unsigned m_big = __ballot_sync(0xffffffffu, active && big);
+            const unsigned lt = (1u << lane) - 1u;
+            n_act = __popc(m_small) + __popc(m_big);
+            const int slot = active ? (big ? __popc(m_small) + __popc(m_big & lt) : __popc(m_small & lt))
+                                    : n_act + __popc(~(m_small | m_big) & lt);
+            w_m[warp][slot] = make_int2(meta, olin);
+            if (active) {
+                w_v[warp][slot] = rv;
+                w_nd[warp][slot] = rnd;
+                if (fast) { w_q0[warp][slot] = rq0; w_e1[warp][slot] = re1; w_e2[warp][slot] = re2; w_e3[warp][slot] = re3; }
             }
         }
         __syncwarp();
         // ---------------- phase B: 8 lanes <-> tet; group grp walks tets grp, grp+4, ... of the tile ----------------
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r * 4 < n_act; r++) {
             const int j = r * 4 + grp;
             const int2 mm = w_m[warp][j];
             const int meta = mm.x;
@@ -729,7 +745,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                 if (lane_g == 0) {
                     nsamp += (unsigned long long)n3;
                     if (PER_TET) {
-                        const unsigned t = base_t + j;
+                        const unsigned t = base_t + ((meta >> 16) & 31);
                         if (a.tet_total) a.tet_total[t] = tot;
                         if (a.tet_vol) a.tet_vol[t] = v;
                         if (a.tet_mean) a.tet_mean[t] = tot / v;
@@ -1426,6 +1442,32 @@ __global__ void means_from_sums_kernel(const double *sums, int nb_phase, double 
 {
     const int k = threadIdx.x;
     if (k < nb_phase) mean[k] = sums[k] / sums[2 * nb_phase + k];
+}
+
+// Neighbour-area term of get_energy_tetrahedron (DEMO/segment_function.cpp:629-640) added to the per-candidate variation
+// sums that the tet pass left in `energy`: one thread per (tet, candidate), faces in get_faces(t) order.
+__global__ void relabel_area_kernel(MeshView m, const unsigned *__restrict__ tet_face_nodes, const unsigned *__restrict__ tet_face_tets, int nb_phase,
+                                    double alpha, double *energy)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)m.n_tets * nb_phase) return;
+    const unsigned t = (unsigned)(i / nb_phase);
+    const int k = (int)(i % nb_phase);
+    const int old_label = m.tet_label[t];
+    if (old_label == 0) { energy[i] = -1.0; return; }
+    double e = energy[i];
+    for (int f = 0; f < 4; f++) {
+        const unsigned ta = tet_face_tets[((size_t)t * 4 + f) * 2], tb = tet_face_tets[((size_t)t * 4 + f) * 2 + 1];
+        if (ta == kNoTet || tb == kNoTet) continue;
+        int label0 = m.tet_label[ta];
+        const int label1 = m.tet_label[tb];
+        label0 = label0 == old_label ? label1 : label0;
+        if (label0 != k + 1) {
+            const unsigned *fn = tet_face_nodes + ((size_t)t * 4 + f) * 3;
+            e += tri_area(load_pos(m.pos4, fn[0]), load_pos(m.pos4, fn[1]), load_pos(m.pos4, fn[2])) * alpha;
+        }
+    }
+    energy[i] = e;
 }
 
 // Bit-exactness witness: one thread per tet walks its sample points in table order and hashes the

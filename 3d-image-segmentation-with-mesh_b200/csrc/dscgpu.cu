@@ -80,7 +80,8 @@ struct dscgpu_ctx {
 
     bool has_snapshot = false;
     uint32_t n_nodes = 0, n_tets = 0, n_faces = 0;
-    DevBuf pos4, pos4f, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc, csr_count, csr_cursor, csr_flag, csr_apos, node_active, fbuf, fset;
+    DevBuf pos4, pos4f, tet_nodes, tet_label, face_nodes, face_tets, face_isb, node_off, node_inc, csr_count, csr_cursor, csr_flag, csr_apos, node_active, fbuf, fset, tet_face_nodes, tet_face_tets;
+    bool has_tet_faces = false;
     // pinned staging (host side of the snapshot)
     PinBuf h_pos4, h_tet_nodes, h_tet_label, h_face_nodes, h_face_tets, h_face_isb, h_node_off, h_node_inc, h_node_active, h_out, h_flag;
     bool validation_pending = false;
@@ -730,6 +731,7 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
+    ctx->has_tet_faces = false;
     CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ks));
     CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[16], 0));
     if (nn) {
@@ -857,7 +859,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_OK;
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    DevBuf *bufs[] = {&ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
+    DevBuf *bufs[] = {&ctx->tet_face_nodes, &ctx->tet_face_tets, &ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
                       &ctx->partials, &ctx->sums, &ctx->mean, &ctx->forces, &ctx->counters, &ctx->o_total, &ctx->o_vol, &ctx->o_mean, &ctx->o_energy,
                       &ctx->o_variation, &ctx->o_hash, &ctx->o_nsamp, &ctx->ray_count, &ctx->ray_offset, &ctx->ray_cursor, &ctx->hits, &ctx->block_sums,
                       &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
@@ -1011,6 +1013,7 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     }
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
+    ctx->has_tet_faces = false;
 
     // choose lanes per tet from a sample of tet volumes (heuristic only; never affects results)
     {
@@ -1114,6 +1117,47 @@ int dscgpu_tet_integrate(dscgpu_ctx *ctx, int nb_phase, int include_bound, int n
     { int rs = sync_and_check(ctx); if (rs) return rs; }
     if (stats) fill_stats(stats, h_sums, h_mean, nb_phase);
     return DSCGPU_OK;
+}
+
+int dscgpu_set_tet_faces(dscgpu_ctx *ctx, const uint32_t *tet_face_nodes, const uint32_t *tet_face_tets)
+{
+    NEED_SNAPSHOT();
+    ARG(tet_face_nodes && tet_face_tets, "null argument");
+    const size_t nt = ctx->n_tets;
+    for (size_t i = 0; i < 12 * nt; i++) ARG(tet_face_nodes[i] < ctx->n_nodes, "tet_face_nodes holds a node key >= n_nodes_buffer");
+    for (size_t i = 0; i < 8 * nt; i++) ARG(tet_face_tets[i] < ctx->n_tets || tet_face_tets[i] == DSCGPU_NO_TET, "tet_face_tets holds a tet index >= n_tets");
+    CK(ctx->tet_face_nodes.ensure(nt * 48 + 4));
+    CK(ctx->tet_face_tets.ensure(nt * 32 + 4));
+    if (nt) {
+        CK(cudaMemcpyAsync(ctx->tet_face_nodes.p, tet_face_nodes, nt * 48, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->tet_face_tets.p, tet_face_tets, nt * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->has_tet_faces = true;
+    return sync_and_check(ctx);
+}
+
+int dscgpu_relabel_energies(dscgpu_ctx *ctx, int nb_phase, const double *mean, double alpha, double *energy)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && mean && energy, "bad arguments");
+    if (!ctx->has_tet_faces) { ctx->err = "dscgpu_set_tet_faces has not been called for this snapshot"; return DSCGPU_ERR_NO_SNAPSHOT; }
+    const size_t nt = ctx->n_tets;
+    if (nt == 0) return DSCGPU_OK;
+    CK(ctx->o_variation.ensure(nt * nb_phase * 8));
+    // per-candidate sum |I - c_k| over the tet's sample points (get_variation), whole mesh regardless of the partition
+    const uint32_t tb = ctx->tet_b, te = ctx->tet_e;
+    ctx->tet_b = 0; ctx->tet_e = ctx->n_tets;
+    int r = run_tet_pass(ctx, nb_phase, 0, nb_phase, mean, nullptr, nullptr, nullptr, nullptr, ctx->o_variation.as<double>(), ctx->sums.as<double>(),
+                         ctx->mean.as<double>());
+    ctx->tet_b = tb; ctx->tet_e = te;
+    if (r) return r;
+    const size_t n = nt * nb_phase;
+    relabel_area_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(mesh_view(ctx), ctx->tet_face_nodes.as<unsigned>(), ctx->tet_face_tets.as<unsigned>(),
+                                                                            nb_phase, alpha, ctx->o_variation.as<double>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(energy, ctx->o_variation.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_and_check(ctx);
 }
 
 int dscgpu_tet_sample_hash(dscgpu_ctx *ctx, uint64_t *tet_hash, int32_t *tet_nsamp)

@@ -257,6 +257,20 @@ class SegmentFunction:
             self._stats_out(st)
         return out
 
+    def relabel_energies(self, tet_face_nodes, tet_face_tets, mean=None):
+        """segment_function::get_energy_tetrahedron (DEMO/segment_function.cpp:618-643) for every labelled tet and every
+        candidate label: [n_tets, NB_PHASE]; -1 for label-0 tets."""
+        fn = np.ascontiguousarray(tet_face_nodes, np.uint32).reshape(-1)
+        ft = np.ascontiguousarray(tet_face_tets, np.uint32).reshape(-1)
+        if fn.size != 12 * self.n_tets or ft.size != 8 * self.n_tets:
+            raise ValueError("tet_face_nodes / tet_face_tets must describe 4 faces per tet")
+        self._img._check(self.lib.dscgpu_set_tet_faces(self._img._ctx, _ptr(fn), _ptr(ft)), "dscgpu_set_tet_faces")
+        m = np.ascontiguousarray(self._mean_intensities if mean is None else mean, np.float64)
+        out = np.empty((self.n_tets, self.NB_PHASE))
+        self._img._check(self.lib.dscgpu_relabel_energies(self._img._ctx, C.c_int(self.NB_PHASE), _ptr(m), C.c_double(self.m_alpha), _ptr(out)),
+                         "dscgpu_relabel_energies")
+        return out
+
     def tet_sample_hash(self):
         h = np.zeros(self.n_tets, np.uint64)
         n = np.zeros(self.n_tets, np.int32)

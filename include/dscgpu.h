@@ -136,6 +136,18 @@ int dscgpu_set_partition(dscgpu_ctx *ctx, uint32_t tet_begin, uint32_t tet_end, 
  */
 int dscgpu_tet_integrate(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, double *tet_total, double *tet_vol,
                          double *tet_mean, double *tet_energy, double *tet_variation, dscgpu_phase_stats *stats);
+/* SURVEY 8(f) row 1 -- batched relabel energies: segment_function::get_energy_tetrahedron (DEMO/segment_function.cpp:618-643)
+ * for every labelled tet and every candidate label 1..nb_phase, labels left untouched (what relabel_tetrahedra, :845-890,
+ * evaluates 2*NB_PHASE times per tet):
+ *   energy[t*nb_phase+k] = get_variation(t, mean[k]) + sum over the tet's 4 faces (get_faces(t) order) of alpha*area(face)
+ *                          when the label on the other side differs from k+1 (:633-640); -1 for label-0 tets.
+ * The tet -> face adjacency is an optional extension of the snapshot, set after dscgpu_set_snapshot:
+ *   tet_face_nodes 12*n_tets node keys: per tet its 4 faces, each in get_nodes(f) order (DSC::area, src/DSC.h:3216-3220)
+ *   tet_face_tets   8*n_tets tet indices: per face its co-boundary tets in get_tets(f) order, DSCGPU_NO_TET when single
+ *                   (such faces are skipped; the reference assumes there are none). */
+int dscgpu_set_tet_faces(dscgpu_ctx *ctx, const uint32_t *tet_face_nodes, const uint32_t *tet_face_tets);
+int dscgpu_relabel_energies(dscgpu_ctx *ctx, int nb_phase, const double *mean, double alpha, double *energy);
+
 /* Order-sensitive FNV-1a hash of the truncated voxel coordinates of every sample point of every
  * tet, and the sample count: the bit-exactness witness for the sample -> voxel classification. */
 int dscgpu_tet_sample_hash(dscgpu_ctx *ctx, uint64_t *tet_hash, int32_t *tet_nsamp);

@@ -163,3 +163,17 @@ def std_sort_hits(z, b_in):
     b = _c(b_in, np.uint8).copy()
     lib().fo_std_sort_hits(C.c_int(len(z)), _p(z), _p(b))
     return z, b
+
+
+def relabel_energies(vol, snap, tet_face_nodes, tet_face_tets, nb_phase, mean, alpha):
+    vol = np.ascontiguousarray(vol)
+    pos = _c(snap["pos"], np.float64)
+    tn = _c(snap["tet_nodes"], np.uint32)
+    tl = _c(snap["tet_label"], np.int32)
+    fn = _c(tet_face_nodes, np.uint32)
+    ft = _c(tet_face_tets, np.uint32)
+    mean = _c(mean, np.float64)
+    out = np.empty((len(tl), nb_phase))
+    lib().fo_relabel_energies(_dims(vol), DTYPE_CODE[vol.dtype], _p(vol), C.c_uint32(len(tl)), _p(tn), _p(tl), _p(pos), _p(fn), _p(ft),
+                              C.c_int(nb_phase), _p(mean), C.c_double(alpha), _p(out))
+    return out

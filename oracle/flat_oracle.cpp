@@ -408,6 +408,49 @@ int fo_points_in_tets(uint32_t n, const uint32_t *tet_idx, const double *pts, co
     return 0;
 }
 
+// Relabel energy of every labelled tet for every candidate label: segment_function::get_energy_tetrahedron
+// (DEMO/segment_function.cpp:618-643) as called by relabel_tetrahedra (:845-890) with the labels left untouched:
+//   energy[t][k] = get_variation(t, mean[k]) + sum over the 4 faces in get_faces(t) order of alpha * area(face) when the
+//   "other" label differs from k+1, where other = (label(tets[0]) == old ? label(tets[1]) : label(tets[0])) (:633-636).
+// tet_face_nodes [n_tets][4][3] in get_nodes(f) order, tet_face_tets [n_tets][4][2] in get_tets(f) order (tet indices).
+// Faces with a single co-boundary tet are skipped (the reference assumes there are none, comment at :632).
+int fo_relabel_energies(const int dims[3], int dtype, const void *voxels, uint32_t n_tets, const uint32_t *tet_nodes, const int32_t *tet_label,
+                        const double *pos, const uint32_t *tet_face_nodes, const uint32_t *tet_face_tets, int nb_phase, const double *mean, double alpha,
+                        double *energy)
+{
+    Vol V{dims[0], dims[1], dims[2], dtype, voxels};
+    for (uint32_t t = 0; t < n_tets; t++) {
+        for (int k = 0; k < nb_phase; k++) energy[(size_t)t * nb_phase + k] = -1.0;
+        const int old_label = tet_label[t];
+        if (old_label == 0) continue;
+        const uint32_t *tn = tet_nodes + 4 * (size_t)t;
+        V3 p0 = P(pos, tn[0]), p1 = P(pos, tn[1]), p2 = P(pos, tn[2]), p3 = P(pos, tn[3]);
+        double v = volume(p0, p1, p2, p3);
+        int lv = tet_level(v);
+        int o = DSC_TET_LEVEL_OFFSET[lv], n3 = DSC_TET_LEVEL_OFFSET[lv + 1] - o;
+        for (int k = 0; k < nb_phase; k++) {
+            double e = 0;
+            for (int i = 0; i < n3; i++) { // get_variation, DEMO/image3d.cpp:406-426
+                const double *b = DSC_TET_BARY + 4 * (o + i);
+                V3 pt = add(add(add(mul(p0, b[0]), mul(p1, b[1])), mul(p2, b[2])), mul(p3, b[3]));
+                e += std::abs(V.at((int)pt.x, (int)pt.y, (int)pt.z) - mean[k]);
+            }
+            for (int f = 0; f < 4; f++) {
+                const uint32_t ta = tet_face_tets[((size_t)t * 4 + f) * 2], tb = tet_face_tets[((size_t)t * 4 + f) * 2 + 1];
+                if (ta == 0xFFFFFFFFu || tb == 0xFFFFFFFFu) continue;
+                int label0 = tet_label[ta], label1 = tet_label[tb];
+                label0 = label0 == old_label ? label1 : label0;
+                if (label0 != k + 1) {
+                    const uint32_t *fn = tet_face_nodes + ((size_t)t * 4 + f) * 3;
+                    e += area(P(pos, fn[0]), P(pos, fn[1]), P(pos, fn[2])) * alpha;
+                }
+            }
+            energy[(size_t)t * nb_phase + k] = e;
+        }
+    }
+    return 0;
+}
+
 // reference sort used by the z-ray pass, exposed so that the product's device-side restatement of
 // libstdc++'s introsort can be fuzzed against the real std::sort (tests/test_introsort.py).
 int fo_std_sort_hits(int n, int32_t *z, uint8_t *b_in)

@@ -325,6 +325,24 @@ static void dump_state(const Args &a, segment_function &seg, const std::string &
         for (int k = 0; k < P; k++) tet_relabel_energy[i * P + k] = seg.get_energy_tetrahedron(tk, k + 1);
     }
 
+    // --- per-tet face adjacency as get_energy_tetrahedron walks it (segment_function.cpp:629-640): the 4 faces in get_faces(t)
+    //     order, each with its nodes in get_nodes(f) order (what DSC::area uses, src/DSC.h:3216-3220) and its co-boundary
+    //     tets in get_tets(f) order, as indices into the dumped tet arrays
+    std::vector<uint32_t> tet_face_nodes(nt * 12, 0), tet_face_tets(nt * 8, 0xFFFFFFFFu);
+    for (size_t i = 0; i < nt; i++) {
+        is_mesh::TetrahedronKey tk(tet_key[i]);
+        int fi = 0;
+        for (auto fid : dsc->get_faces(tk)) {
+            if (fi >= 4) break;
+            auto nids = dsc->get_nodes(fid);
+            for (int k = 0; k < 3; k++) tet_face_nodes[i * 12 + fi * 3 + k] = nids[k];
+            auto tids = dsc->get_tets(fid);
+            tet_face_tets[i * 8 + fi * 2] = (uint32_t)tet_index[tids[0]];
+            if (tids.size() > 1) tet_face_tets[i * 8 + fi * 2 + 1] = (uint32_t)tet_index[tids[1]];
+            fi++;
+        }
+    }
+
     // --- voxel-in-tet predicate goldens (segment_function.cpp:2576-2580) --------------------
     std::vector<uint32_t> pit_tet;
     std::vector<double> pit_pts;
@@ -378,6 +396,8 @@ static void dump_state(const Args &a, segment_function &seg, const std::string &
     write_bin(dir, "tet_variation.f64", tet_variation);
     write_bin(dir, "tet_energy.f64", tet_energy);
     write_bin(dir, "tet_relabel_energy.f64", tet_relabel_energy);
+    write_bin(dir, "tet_face_nodes.u32", tet_face_nodes);
+    write_bin(dir, "tet_face_tets.u32", tet_face_tets);
     write_bin(dir, "tet_hash.u64", tet_hash);
     write_bin(dir, "tet_nsamp.i32", tet_nsamp);
     write_bin(dir, "mean.f64", seg._mean_intensities);

@@ -96,6 +96,8 @@ def run_case(name, spec):
     arrs["face_nodes"] = arrs["face_nodes"].reshape(-1, 3)
     arrs["face_tets"] = arrs["face_tets"].reshape(-1, 2)
     arrs["pit_pts"] = arrs["pit_pts"].reshape(-1, 3)
+    arrs["tet_face_nodes"] = arrs["tet_face_nodes"].reshape(-1, 4, 3)
+    arrs["tet_face_tets"] = arrs["tet_face_tets"].reshape(-1, 4, 2)
     for k in ("tet_variation", "tet_energy", "tet_relabel_energy"):
         arrs[k] = arrs[k].reshape(-1, P)
     arrs["meta_json"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)

@@ -298,3 +298,15 @@ def test_filter_variants_on_large_interior_mesh(pkg, flat):
         # float voxel sums of <= 729 terms are exact in double whatever the order: bit-equal totals <=> same voxels
         assert np.array_equal(o["total"], ref["total"]), variant
     img.close()
+
+
+def test_relabel_energies(case):
+    """get_energy_tetrahedron for every tet and candidate label, against the reference's own values."""
+    g, img, seg = case
+    e = seg.relabel_energies(g["tet_face_nodes"], g["tet_face_tets"], mean=g["mean"])
+    lab = g["tet_label"] != 0
+    np.testing.assert_allclose(e[lab], g["tet_relabel_energy"][lab], rtol=RTOL, atol=1e-12)
+    assert np.all(e[~lab] == -1.0)
+    # the decision relabel_tetrahedra takes from these numbers (Jacobi form: labels untouched) must agree too
+    assert np.array_equal(np.argmin(e[lab], axis=1), np.argmin(g["tet_relabel_energy"][lab], axis=1)) or \
+        np.allclose(np.sort(e[lab], axis=1)[:, 0], np.sort(g["tet_relabel_energy"][lab], axis=1)[:, 0], rtol=RTOL)

@@ -86,3 +86,10 @@ def test_multithreaded_oracle_matches_single_thread(flat):
     F1 = flat.face_forces(g["volume"], s, 3, g["mean"], threads=1)
     F4 = flat.face_forces(g["volume"], s, 3, g["mean"], threads=4)
     np.testing.assert_allclose(F4, F1, rtol=1e-9, atol=1e-12)
+
+
+def test_relabel_energies_bit_exact(case, flat):
+    g, s = case
+    e = flat.relabel_energies(g["volume"], s, g["tet_face_nodes"], g["tet_face_tets"], g["meta"]["nb_phase"], g["mean"], g["meta"]["alpha"])
+    lab = g["tet_label"] != 0
+    assert np.array_equal(e[lab], g["tet_relabel_energy"][lab])

@@ -66,12 +66,15 @@ def interface_faces(tets, labels, n_nodes):
     tri = np.sort(tets[:, loc].reshape(-1, 3), axis=1)
     owner = np.repeat(np.arange(m, dtype=np.int64), 4)
     N = np.int64(n_nodes)
-    assert float(N) ** 3 < 9e18, "node count too large for the 63-bit face key"
-    key = (tri[:, 0] * N + tri[:, 1]) * N + tri[:, 2]
-    order = np.argsort(key, kind="stable")
-    key, tri, owner = key[order], tri[order], owner[order]
-    first = np.ones(len(key), bool)
-    first[1:] = key[1:] != key[:-1]
+    if float(N) ** 3 < 9e18:
+        key = (tri[:, 0] * N + tri[:, 1]) * N + tri[:, 2]
+        order = np.argsort(key, kind="stable")
+    else:  # > 2 M nodes: the triple no longer fits one 63-bit key
+        order = np.lexsort((tri[:, 2], tri[:, 1], tri[:, 0]))
+    tri, owner = tri[order], owner[order]
+    first = np.ones(len(tri), bool)
+    first[1:] = (tri[1:] != tri[:-1]).any(axis=1)
+    key = tri  # only its length is used below
     start = np.flatnonzero(first)
     count = np.diff(np.append(start, len(key)))
     assert count.max() <= 2, "non-manifold face"

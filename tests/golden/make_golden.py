@@ -62,6 +62,9 @@ CASES = {
     # float sphere (BASELINE config #2 scaled down), 2 phases
     "sph48_f32": dict(vol=lambda: sphere_f32(48, 15.0, 0.2, 0.8), dtype="f32", edge=4.3, nb_phase=2, alpha=0.001, labels="thres",
                       thres="0.5", jitter=0.25),
+    # non-cubic volume (X=100, Y=72, Z=56: a crop of the reference's data), 4 phases by fixed thresholds, jittered mesh
+    "c1_crop_xyz": dict(vol=lambda: np.ascontiguousarray(png_stack("square_round_2_0.1")[22:78, 14:86, :]), dtype="u8", edge=7.3, nb_phase=4,
+                        alpha=0.005, labels="thres", thres="0.08,0.3,0.6", jitter=0.2, iters=1),
     # uint16 nested shells + noise (BASELINE config #3 scaled down), coarse mesh => higher sample levels
     "sh40_u16": dict(vol=lambda: shells_u16(40, 1234, 0.05), dtype="u16", edge=10, nb_phase=3, alpha=0.001, labels="thres",
                      thres="0.3,0.7", jitter=0.2),

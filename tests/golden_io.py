@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["c1_e6", "c1_e8_it2", "c1n_e9_j", "sph48_f32", "sh40_u16"]
+CASES = ["c1_e6", "c1_e8_it2", "c1n_e9_j", "sph48_f32", "sh40_u16", "c1_crop_xyz"]
 
 
 def load(name):

@@ -310,3 +310,46 @@ def test_relabel_energies(case):
     # the decision relabel_tetrahedra takes from these numbers (Jacobi form: labels untouched) must agree too
     assert np.array_equal(np.argmin(e[lab], axis=1), np.argmin(g["tet_relabel_energy"][lab], axis=1)) or \
         np.allclose(np.sort(e[lab], axis=1)[:, 0], np.sort(g["tet_relabel_energy"][lab], axis=1)[:, 0], rtol=RTOL)
+
+
+@pytest.mark.parametrize("dtype,P", [(np.float32, 6), (np.uint16, 8), (np.uint8, 5)])
+def test_non_cubic_volume_and_many_phases(pkg, flat, dtype, P):
+    """X != Y != Z and more than four phases (label-indexed lanes / accumulators up to DSCGPU_MAX_PHASE)."""
+    syn = pkg.synthetic
+    vol = np.ascontiguousarray(syn.shells_phantom(48, levels=(0.05, 0.35, 0.65, 0.95), radii=(0.45, 0.3, 0.15), sigma=0.08, seed=21, dtype=dtype)[5:41, 0:30, 3:48])
+    assert vol.shape == (36, 30, 45)
+    thr = tuple(np.linspace(0.1, 0.9, P - 1))
+    snap = syn.build_case(vol, 5.5, P, thr, lambda pos, tets, base: flat.tet_integrate(vol, tets, pos, want_hash=False)["mean"], jitter=0.25, seed=3)
+    assert len(np.unique(snap["tet_label"])) >= P  # every phase (and the boundary layer) is populated
+    img = pkg.Image3D(vol)
+    seg = pkg.SegmentFunction(img, P, 0.01)
+    seg.set_snapshot(snap)
+    ref = flat.tet_integrate(vol, snap["tet_nodes"], snap["pos"], c=[0.0])
+    h, ns = seg.tet_sample_hash()
+    assert np.array_equal(h, ref["hash"]) and np.array_equal(ns, ref["nsamp"])
+    lab = snap["tet_label"]
+    for variant in (0, 40, 128):
+        seg.set_tet_variant(variant)
+        o = seg.tet_integrate()
+        m = lab != 0
+        assert np.array_equal(o["vol"][m], ref["vol"][m])
+        np.testing.assert_allclose(o["total"][m], ref["total"][m], rtol=RTOL, atol=1e-12)
+        tot, volu, mean = flat.phase_reduce(lab, ref["total"], ref["vol"], P)
+        np.testing.assert_allclose(o["phase_total"], tot, rtol=RTOL)
+        np.testing.assert_allclose(o["phase_volume"], volu, rtol=RTOL)
+        sq, _, _ = flat.phase_reduce(lab, ref["sq"][:, 0], ref["vol"], P)
+        np.testing.assert_allclose(o["phase_sumsq"], sq, rtol=RTOL)
+    z = flat.zray(vol, snap, P, mode=0)
+    seg.update_average_intensity()
+    assert np.array_equal(seg._phase_volume, z["count"])
+    ok = z["count"] > 0
+    np.testing.assert_allclose(seg._total_intensities[ok], z["total"][ok], rtol=RTOL)
+    mvals = np.where(ok, z["mean"], 0.5)
+    assert np.array_equal(seg.compute_external_force(mean=mvals), flat.face_forces(vol, snap, P, mvals))
+    np.testing.assert_allclose(seg.compute_external_force(mode=pkg.FORCE_ATOMIC, mean=mvals), flat.face_forces(vol, snap, P, mvals), rtol=RTOL,
+                               atol=RTOL * 10)
+    e = flat.zray(vol, snap, P, mode=1, mean=mvals, alpha=0.01)
+    d, a = seg.compute_energy(mean=mvals)
+    np.testing.assert_allclose([d, a], [e["energy_data"], e["energy_area"]], rtol=RTOL)
+    assert np.array_equal(img.sum_table(), flat.build_sum_table(vol))
+    img.close()

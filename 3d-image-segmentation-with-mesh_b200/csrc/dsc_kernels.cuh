@@ -783,6 +783,275 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
 }
 
 // -------------------------------------------------------------------------------------------------
+// w4 (variant 512): w2 with a software-pipelined phase B -- the index computation and the gathers of the next batch (which
+// may belong to the group's next tet) are issued before the pending batch is accumulated, so two batches (8 gathers per
+// lane) are in flight and the accumulation no longer waits on the loads it has just issued.
+// -------------------------------------------------------------------------------------------------
+template <typename VoxT, bool WANT_SQ, bool PER_TET>
+__global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w4_kernel(const TetArgs a)
+{
+    constexpr int G = 8, U = 4;
+    __shared__ float4 s_lat[kSmemRows];        // (a1, a2, a3, eps) per table row
+    __shared__ double2 s_tabd[2 * kSmemRows];  // exact rows for the fallback
+    __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0-.5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
+    __shared__ int2 w_m[8][32];                // meta, (O_linear - fold)
+    __shared__ double w_v[8][32];
+    __shared__ uint4 w_nd[8][32];
+    for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
+    for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_lat[i] = a.tet_lat[i];
+    __syncthreads();
+
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const int XYi = X * Y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane_g = lane & (G - 1), grp = lane >> 3;
+    const unsigned gmask = 0xFFu << (grp * 8);
+    const unsigned n_work = a.tet_end - a.tet_begin;
+    const unsigned n_tiles = (n_work + 31) / 32;
+    const unsigned total_warps = gridDim.x * 8;
+    const float MAGIC = 12582912.0f; // 1.5 * 2^23
+    const unsigned fold = 0x4B400000u * (unsigned)(XYi + X + 1);
+
+    double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane_g + 1
+    unsigned long long nsamp = 0;
+
+    for (unsigned tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += total_warps) {
+        const unsigned base_t = a.tet_begin + tile * 32;
+        const int nb = (int)min(32u, a.tet_end - base_t);
+        __syncwarp();
+        // ---------------- phase A: lane <-> tet ----------------
+        // Records are stored in a permuted order: tets with at most 32 samples first, then the larger ones, inactive tets
+        // last -- the four groups of a phase-B round then mostly run the same number of batches (a 27-sample tet next to a
+        // 64-sample one would idle for a batch) and rounds past the last active tet are skipped.
+        int n_act = 0;
+        {
+            int meta = 0, olin = 0;
+            bool active = false, big = false, fast = false;
+            float4 rq0 = make_float4(0, 0, 0, 0), re1 = rq0, re2 = rq0, re3 = rq0;
+            double rv = 0;
+            uint4 rnd = make_uint4(0, 0, 0, 0);
+            if (lane < nb) {
+                const unsigned t = base_t + lane;
+                const int label = __ldg(a.mesh.tet_label + t);
+                active = a.include_bound || label != 0;
+                meta = (label & 0xff) | (lane << 16);
+                if (active) {
+                    const uint4 nd = __ldg(a.mesh.tet_nodes + t);
+                    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                    const double v = tet_volume(p0, p1, p2, p3);
+                    const int L = tet_level(v);
+                    big = (L + 1) * (L + 1) * (L + 1) > G * U;
+                    const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
+                    const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
+                    const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
+                    // strictly inside the volume with a margin: no sample can leave [1, dim-1), so no bounds checks, no negatives
+                    const bool interior = lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5;
+                    const double ox = floor(lox), oy = floor(loy), oz = floor(loz);
+                    const double rmax = fmax(fmax(hix - ox, hiy - oy), hiz - oz);
+                    fast = interior && L < kSmemLevels && rmax < 100.0;
+                    meta |= (L << 8) | (1 << 12);
+                    if (fast) {
+                        const double inv4n = 1.0 / (double)(4 * (L + 1));
+                        rq0 = make_float4((float)((p0.x - ox) - 0.5), (float)((p0.y - oy) - 0.5), (float)((p0.z - oz) - 0.5),
+                                          0.5f - (48.0f * (float)rmax + 8.0f) * 5.9604644775390625e-08f);
+                        re1 = make_float4((float)((p1.x - p0.x) * inv4n), (float)((p1.y - p0.y) * inv4n), (float)((p1.z - p0.z) * inv4n), (float)ox);
+                        re2 = make_float4((float)((p2.x - p0.x) * inv4n), (float)((p2.y - p0.y) * inv4n), (float)((p2.z - p0.z) * inv4n), (float)oy);
+                        re3 = make_float4((float)((p3.x - p0.x) * inv4n), (float)((p3.y - p0.y) * inv4n), (float)((p3.z - p0.z) * inv4n), (float)oz);
+                        olin = (int)((unsigned)((int)oz * XYi + (int)oy * X + (int)ox) - fold);
+                        meta |= 1 << 13;
+                    }
+                    rv = v;
+                    rnd = nd;
+                } else {
+                    if (a.tet_total) a.tet_total[t] = -1.0;
+                    if (a.tet_vol) a.tet_vol[t] = -1.0;
+                    if (a.tet_mean) a.tet_mean[t] = -1.0;
+                }
+            }
+            const unsigned m_small = __ballot_sync(0xffffffffu, active && !big);
+            const unsigned m_big = __ballot_sync(0xffffffffu, active && big);
+            const unsigned lt = (1u << lane) - 1u;
+            n_act = __popc(m_small) + __popc(m_big);
+            const int slot = active ? (big ? __popc(m_small) + __popc(m_big & lt) : __popc(m_small & lt))
+                                    : n_act + __popc(~(m_small | m_big) & lt);
+            w_m[warp][slot] = make_int2(meta, olin);
+            if (active) {
+                w_v[warp][slot] = rv;
+                w_nd[warp][slot] = rnd;
+                if (fast) { w_q0[warp][slot] = rq0; w_e1[warp][slot] = re1; w_e2[warp][slot] = re2; w_e3[warp][slot] = re3; }
+            }
+        }
+        __syncwarp();
+        // ---------------- phase B, software-pipelined: the gathers of batch k+1 are issued before batch k is consumed ------
+        VoxT pval[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) pval[u] = (VoxT)0;
+        bool pending = false, p_last = false;
+        int p_meta = 0, p_n3 = 1;
+        double p_v = 0;
+        double s = 0, sq = 0;
+        unsigned long long isum = 0, isq = 0;
+        auto consume = [&]() {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if constexpr (VoxTraits<VoxT>::integral) {
+                    const unsigned q = (unsigned)pval[u];
+                    isum += q;
+                    if (WANT_SQ) isq += (unsigned long long)q * q;
+                } else {
+                    double I;
+                    if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)pval[u]);
+                    else I = (double)pval[u];
+                    s += I;
+                    if (WANT_SQ) sq = fma(I, I, sq);
+                }
+            }
+            if (p_last) { // last batch of its tet: group reduction and bookkeeping (the 8 lanes of the group are converged)
+                if constexpr (VoxTraits<VoxT>::integral) {
+                    const double dn = VoxTraits<VoxT>::denom();
+                    s = (double)isum / dn;
+                    if (WANT_SQ) sq = (double)isq / (dn * dn);
+                }
+#pragma unroll
+                for (int m = G / 2; m >= 1; m >>= 1) {
+                    s += __shfl_xor_sync(gmask, s, m);
+                    if (WANT_SQ) sq += __shfl_xor_sync(gmask, sq, m);
+                }
+                const int label = p_meta & 0xff;
+                const double tot = s * p_v / (double)p_n3; // total = total * v / a.size()  (image3d.cpp:371)
+                const double tsq = WANT_SQ ? sq * p_v / (double)p_n3 : 0.0;
+                if (lane_g == 0) {
+                    nsamp += (unsigned long long)p_n3;
+                    if (PER_TET) {
+                        const unsigned t = base_t + ((p_meta >> 16) & 31);
+                        if (a.tet_total) a.tet_total[t] = tot;
+                        if (a.tet_vol) a.tet_vol[t] = p_v;
+                        if (a.tet_mean) a.tet_mean[t] = tot / p_v;
+                    }
+                }
+                if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
+                    acc_tot += tot;
+                    acc_sq += tsq;
+                    acc_vol += p_v;
+                }
+                s = 0; sq = 0; isum = 0; isq = 0;
+            }
+        };
+        for (int r = 0; r * 4 < n_act; r++) {
+            const int j = r * 4 + grp;
+            const int2 mm = w_m[warp][j];
+            const int meta = mm.x;
+            if (!(meta & (1 << 12))) continue;
+            const int L = (meta >> 8) & 0xf;
+            const int n3 = (L + 1) * (L + 1) * (L + 1);
+            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+            const double v_j = w_v[warp][j];
+            if (meta & (1 << 13)) {
+                const float4 q0 = w_q0[warp][j], e1 = w_e1[warp][j], e2 = w_e2[warp][j], e3 = w_e3[warp][j];
+                const float thr = q0.w;
+                const unsigned obase = (unsigned)mm.y;
+                const float4 *__restrict__ tl = s_lat + off;
+                const int last = n3 - 1;
+                for (int b0 = 0; b0 < n3; b0 += G * U) { // uniform trip count over the group (consume() shuffles inside)
+                    const int base = b0 + lane_g;
+                    int idx[U];
+                    unsigned unsafe = 0;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = base + u * G;
+                        const bool ok = i <= last;
+                        const float4 c = tl[min(i, last)];
+                        const float qx = fmaf(c.z, e3.x, fmaf(c.y, e2.x, fmaf(c.x, e1.x, fmaf(c.w, e1.w, q0.x))));
+                        const float qy = fmaf(c.z, e3.y, fmaf(c.y, e2.y, fmaf(c.x, e1.y, fmaf(c.w, e2.w, q0.y))));
+                        const float qz = fmaf(c.z, e3.z, fmaf(c.y, e2.z, fmaf(c.x, e1.z, fmaf(c.w, e3.w, q0.z))));
+                        const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
+                        const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
+                        const int lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) + obase);
+                        idx[u] = ok ? lin : -1;
+                        if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) unsafe |= 1u << u;
+                    }
+                    if (unsafe) { // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
+                        const uint4 nd = w_nd[warp][j];
+                        const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                        const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+#pragma unroll
+                        for (int u = 0; u < U; u++)
+                            if (unsafe & (1u << u)) {
+                                const int i = base + u * G;
+                                const double2 b01 = s_tabd[2 * (off + i)], b23 = s_tabd[2 * (off + i) + 1];
+                                const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                                const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                                const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                                idx[u] = iz * XYi + iy * X + ix; // interior tet: always in range
+                            }
+                    }
+                    VoxT nval[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) nval[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
+                    if (pending) consume();
+#pragma unroll
+                    for (int u = 0; u < U; u++) pval[u] = nval[u];
+                    pending = true; p_last = b0 + G * U >= n3; p_meta = meta; p_n3 = n3; p_v = v_j;
+                }
+            } else {
+                // exact path (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491)
+                const uint4 nd = w_nd[warp][j];
+                const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+                for (int b0 = 0; b0 < n3; b0 += G * U) { // uniform trip count over the group (consume() shuffles inside)
+                    const int base = b0 + lane_g;
+                    int idx[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = base + u * G;
+                        idx[u] = -1;
+                        if (i < n3) {
+                            const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
+                            const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+                            const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+                            const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+                            if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) idx[u] = iz * XYi + iy * X + ix;
+                        }
+                    }
+                    VoxT nval[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) nval[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
+                    if (pending) consume();
+#pragma unroll
+                    for (int u = 0; u < U; u++) pval[u] = nval[u];
+                    pending = true; p_last = b0 + G * U >= n3; p_meta = meta; p_n3 = n3; p_v = v_j;
+                }
+            }
+        }
+        if (pending) consume();
+    }
+#pragma unroll
+    for (int m = 16; m >= G; m >>= 1) {
+        acc_tot += shfl_xor_d(acc_tot, m);
+        acc_sq += shfl_xor_d(acc_sq, m);
+        acc_vol += shfl_xor_d(acc_vol, m);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
+    __shared__ double sm[8][3 * kMaxPhase];
+    if (lane < kMaxPhase) {
+        sm[warp][lane] = acc_tot;
+        sm[warp][kMaxPhase + lane] = acc_sq;
+        sm[warp][2 * kMaxPhase + lane] = acc_vol;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * kMaxPhase) {
+        double r = 0;
+        for (int wdx = 0; wdx < 8; wdx++) r += sm[wdx][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
+    }
+    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+}
+
+// -------------------------------------------------------------------------------------------------
 // w3 (variant 256): w2 with the per-sample instruction count cut further.
 //   * the float chain starts at Q0 + 128 with O = floor(min corner) - 1, so the result t lies in [128, 256): its
 //     mantissa IS the fixed-point relative coordinate with 16 fraction bits.  floor = byte 2 of the bit pattern (one

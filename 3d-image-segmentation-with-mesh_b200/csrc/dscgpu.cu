@@ -275,6 +275,32 @@ template <typename VoxT> int launch_w3(dscgpu_ctx *ctx, TetArgs &a)
     return per_tet ? launch_w3_t<VoxT, false, true>(ctx, a) : launch_w3_t<VoxT, false, false>(ctx, a);
 }
 
+template <typename VoxT, bool WANT_SQ, bool PER_TET> int launch_w4_t(dscgpu_ctx *ctx, TetArgs &a)
+{
+    auto kern = tet_integrate_w4_kernel<VoxT, WANT_SQ, PER_TET>;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+    if (occ < 1) occ = 1;
+    unsigned n_work = a.tet_end - a.tet_begin;
+    unsigned need = (n_work + 255) / 256;
+    unsigned grid = (unsigned)(ctx->num_sms * occ);
+    if (need < grid) grid = need ? need : 1;
+    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)grid;
+    kern<<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT> int launch_w4(dscgpu_ctx *ctx, TetArgs &a)
+{
+    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
+    if (a.want_sq) return per_tet ? launch_w4_t<VoxT, true, true>(ctx, a) : launch_w4_t<VoxT, true, false>(ctx, a);
+    return per_tet ? launch_w4_t<VoxT, false, true>(ctx, a) : launch_w4_t<VoxT, false, false>(ctx, a);
+}
+
 template <typename VoxT, int PMAX, bool PER_TET> int launch_ab_t(dscgpu_ctx *ctx, TetArgs &a)
 {
     auto kern = tet_integrate_ab_kernel<VoxT, PMAX, PER_TET>;
@@ -355,6 +381,14 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
     }
     int G = ctx->lanes_per_tet ? ctx->lanes_per_tet : ctx->auto_lanes;
     const bool fits32 = (double)ctx->dims[0] * ctx->dims[1] * ctx->dims[2] < 2147483648.0;
+    if ((ctx->tet_variant & 512) && !with_c && fits32) { // w4: w2 with software-pipelined gathers
+        switch (ctx->dtype) {
+        case DSCGPU_U8: return launch_w4<unsigned char>(ctx, a);
+        case DSCGPU_U16: return launch_w4<unsigned short>(ctx, a);
+        case DSCGPU_F32: return launch_w4<float>(ctx, a);
+        default: return launch_w4<double>(ctx, a);
+        }
+    }
     if ((ctx->tet_variant & 256) && !with_c && fits32) { // w3: lattice coordinates, fixed-point floor, independent groups
         switch (ctx->dtype) {
         case DSCGPU_U8: return launch_w3<unsigned char>(ctx, a);
@@ -1445,7 +1479,7 @@ int dscgpu_build_texture(dscgpu_ctx *ctx)
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 512, "variant is a 9-bit field");
+    ARG(variant >= 0 && variant < 1024, "variant is a 10-bit field");
     if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
         int r = dscgpu_build_texture(ctx);
         if (r) return r;

@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--config", default="C4")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mean-mode", default="tet", choices=["tet", "zray"])
-    ap.add_argument("--force-mode", default="gather", choices=["gather", "atomic"])
+    ap.add_argument("--force-mode", default="auto", choices=["auto", "gather", "atomic"],
+                    help="auto: the bit-exact ordered gather on one GPU, the face-partitioned atomic scatter when the forces are all-reduced anyway")
     ap.add_argument("--jitter", type=float, default=0.2)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -259,6 +260,8 @@ def main_b200(args):
     units = n_tets + n_faces
     build_s = time.time() - t0
     mean_mode = pkg.MEAN_TET if args.mean_mode == "tet" else pkg.MEAN_ZRAY
+    if args.force_mode == "auto":
+        args.force_mode = "gather" if world == 1 else "atomic"
     force_mode = pkg.FORCE_GATHER if args.force_mode == "gather" else pkg.FORCE_ATOMIC
 
     # all launches go to one explicit (non-default) torch stream so that torch.cuda.Event brackets them;

@@ -34,7 +34,7 @@ def main():
     ref = None
     import torch
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
-    cases = [(0, 8, "v1 group G=8"), (40, 8, "g4 G=8 u=4 f=0"), (128, 0, "w2 lattice"), (256, 0, "w3 fixed-point")]
+    cases = [(0, 8, "v1 group G=8"), (128, 0, "w2 lattice"), (512, 0, "w4 pipelined")]
     for variant, lanes, label in cases:
         seg.set_tet_variant(variant)
         seg.set_lanes_per_tet(lanes)

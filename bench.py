@@ -317,9 +317,15 @@ def main_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # samples clocks / throttle reasons from the warm-up to the end of the end-to-end loop
+    t_warm = time.time()
     for _ in range(max(3, args.warmup)):
         flush_l2(torch, l2_buf)
         step_device()
+    # keep the device busy for ~0.7 s of extra untimed steps so that the 20 ms clock sampler sees it under load
+    while rank == 0 and world == 1 and time.time() - t_warm < 0.7:
+        flush_l2(torch, l2_buf)
+        step_device()
+        torch.cuda.synchronize(dev)
     barrier()
     # ---- per-kernel durations (library CUDA events on the launching stream), eager launches ----
     tet_ms, force_ms = [], []

@@ -12,6 +12,7 @@
 
 #include "../../include/dscgpu.h"
 #include "dsc_kernels.cuh"
+#include "dsc_tet_g32.cuh"
 #include "dsc_tables.h"
 
 using namespace dsc;
@@ -76,7 +77,14 @@ struct dscgpu_ctx {
     cudaTextureObject_t vol_tex = 0;
     int force_thread_gather = 0; // 1: thread-per-node gather (first implementation) instead of warp-per-node
     int hot_want_sq = 0; // dscgpu_image_force_eval / dscgpu_tet_phase_sums_dev skip the second moment unless asked
-    int tet_variant = 128; // see dscgpu_set_tet_variant; default = batched group kernel, 4 gathers in flight per lane
+    int tet_variant = 1024 | 128; // see dscgpu_set_tet_variant; default = warp-per-tet kernel over the bricked volume, w2 for what it does not cover
+    // bricked, padded copy of the volume for tet_sums_g32_kernel (dsc_tet_g32.cuh); rebuilt when the volume may have changed
+    void *d_brick = nullptr;
+    bool brick_valid = false;
+    bool brick_simple = true; // float volume holds only +0 and positive normal numbers
+    int brick_nb[3] = {0, 0, 0};
+    float4 *d_lat32 = nullptr;
+    unsigned *d_brick_flags = nullptr;
 
     bool has_snapshot = false;
     uint32_t n_nodes = 0, n_tets = 0, n_faces = 0;
@@ -367,8 +375,113 @@ template <typename VoxT> int launch_tet_v(dscgpu_ctx *ctx, TetArgs &a, int G, bo
     return with_c ? launch_tet_t<VoxT, 8, true>(ctx, a) : launch_tet_t<VoxT, 8, false>(ctx, a);
 }
 
+
+// ---- warp-per-tet kernel over the bricked volume (dsc_tet_g32.cuh) ----
+size_t brick_elems(const dscgpu_ctx *ctx) { return (size_t)ctx->brick_nb[0] * ctx->brick_nb[1] * ctx->brick_nb[2] * 32; }
+
+template <typename VoxT> int build_bricks_t(dscgpu_ctx *ctx)
+{
+    const size_t n = brick_elems(ctx);
+    unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 32);
+    brick_volume_kernel<VoxT><<<grid, 256, 0, ctx->stream>>>(static_cast<const VoxT *>(ctx->d_vol), static_cast<VoxT *>(ctx->d_brick), ctx->dims[0], ctx->dims[1],
+                                                               ctx->dims[2], ctx->brick_nb[0], ctx->brick_nb[1], ctx->brick_nb[2], ctx->d_brick_flags);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+// (re)builds the bricked copy if the volume may have changed since the last build; one pass over the volume, like the sum table
+int ensure_bricks(dscgpu_ctx *ctx)
+{
+    if (ctx->brick_valid) return DSCGPU_OK;
+    ctx->brick_nb[0] = (ctx->dims[0] + 2 * kBrickPad + 3) / 4;
+    ctx->brick_nb[1] = (ctx->dims[1] + 2 * kBrickPad + 1) / 2;
+    ctx->brick_nb[2] = (ctx->dims[2] + 2 * kBrickPad + 3) / 4;
+    if (!ctx->d_brick) CK(cudaMalloc(&ctx->d_brick, brick_elems(ctx) * dtype_size(ctx->dtype)));
+    if (!ctx->d_brick_flags) CK(cudaMalloc(&ctx->d_brick_flags, sizeof(unsigned)));
+    CK(cudaMemsetAsync(ctx->d_brick_flags, 0, sizeof(unsigned), ctx->stream));
+    int r;
+    switch (ctx->dtype) {
+    case DSCGPU_U8: r = build_bricks_t<unsigned char>(ctx); break;
+    case DSCGPU_U16: r = build_bricks_t<unsigned short>(ctx); break;
+    case DSCGPU_F32: r = build_bricks_t<float>(ctx); break;
+    default: r = build_bricks_t<double>(ctx); break;
+    }
+    if (r) return r;
+    unsigned flags = 0;
+    CK(cudaMemcpyAsync(&flags, ctx->d_brick_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->brick_simple = (flags & 1u) == 0;
+    ctx->brick_valid = true;
+    return DSCGPU_OK;
+}
+
+bool g32_fits(const dscgpu_ctx *ctx)
+{
+    const double n = ((double)ctx->dims[0] + 2 * kBrickPad + 3) * ((double)ctx->dims[1] + 2 * kBrickPad + 1) * ((double)ctx->dims[2] + 2 * kBrickPad + 3);
+    return n < 2147483648.0;
+}
+
+template <typename VoxT, bool SIMPLE, bool WANT_SQ, bool PER_TET> int launch_g32_t(dscgpu_ctx *ctx, const TetArgs &t)
+{
+    auto kern = tet_sums_g32_kernel<VoxT, SIMPLE, WANT_SQ, PER_TET>;
+    static bool attr_set = false; // per instantiation
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG32SmemBytes));
+        attr_set = true;
+    }
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, kG32SmemBytes));
+    if (occ < 1) occ = 1;
+    TetG32Args a;
+    a.mesh = t.mesh;
+    a.tet_bary = t.tet_bary;
+    a.lat32 = ctx->d_lat32;
+    a.brick = ctx->d_brick;
+    a.Sy = 32u * (unsigned)ctx->brick_nb[0];
+    a.Sz = a.Sy * (unsigned)ctx->brick_nb[1];
+    a.X = ctx->dims[0]; a.Y = ctx->dims[1]; a.Z = ctx->dims[2];
+    a.tet_begin = t.tet_begin; a.tet_end = t.tet_end;
+    a.nb_phase = t.nb_phase;
+    a.tet_total = t.tet_total; a.tet_vol = t.tet_vol; a.tet_mean = t.tet_mean;
+    a.sample_count = t.sample_count;
+    unsigned n_work = a.tet_end - a.tet_begin;
+    unsigned need = (n_work + 255) / 256;
+    unsigned grid = (unsigned)(ctx->num_sms * occ);
+    if (need < grid) grid = need ? need : 1;
+    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)grid;
+    kern<<<grid, 256, kG32SmemBytes, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT, bool SIMPLE> int launch_g32_s(dscgpu_ctx *ctx, const TetArgs &a)
+{
+    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
+    if (a.want_sq) return per_tet ? launch_g32_t<VoxT, SIMPLE, true, true>(ctx, a) : launch_g32_t<VoxT, SIMPLE, true, false>(ctx, a);
+    return per_tet ? launch_g32_t<VoxT, SIMPLE, false, true>(ctx, a) : launch_g32_t<VoxT, SIMPLE, false, false>(ctx, a);
+}
+
+int launch_g32(dscgpu_ctx *ctx, const TetArgs &a)
+{
+    switch (ctx->dtype) {
+    case DSCGPU_U8: return launch_g32_s<unsigned char, true>(ctx, a);
+    case DSCGPU_U16: return launch_g32_s<unsigned short, true>(ctx, a);
+    case DSCGPU_F32: return ctx->brick_simple ? launch_g32_s<float, true>(ctx, a) : launch_g32_s<float, false>(ctx, a);
+    default: return launch_g32_s<double, true>(ctx, a);
+    }
+}
+
 int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
 {
+    if ((ctx->tet_variant & 1024) && !with_c && !a.include_bound && g32_fits(ctx)) { // warp-per-tet kernel over the bricked volume
+        int r = ensure_bricks(ctx);
+        if (r) return r;
+        return launch_g32(ctx, a);
+    }
     if ((ctx->tet_variant & 1) && !with_c) {
         const bool tex = (ctx->tet_variant & 2) && ctx->vol_tex != 0;
         const bool filter = (ctx->tet_variant & 4) != 0;
@@ -878,8 +991,24 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
         }
         CK(cudaMalloc(&ctx->d_tet_lat, tl.size() * sizeof(float)));
         CK(cudaMemcpy(ctx->d_tet_lat, tl.data(), tl.size() * sizeof(float), cudaMemcpyHostToDevice));
+        // the same rows with every level padded to a multiple of 32 (padding = the level's first row; masked in the kernel)
+        std::vector<float> t32(4 * (size_t)kG32Rows, 0.f);
+        for (int L = 0; L < DSC_TET_LEVELS; L++) {
+            const int first = DSC_TET_LEVEL_OFFSET[L], cnt = DSC_TET_LEVEL_OFFSET[L + 1] - first;
+            ARG(g32_slot_off(L + 1) - g32_slot_off(L) == (cnt + 31) / 32, "sample table does not match the slot layout of the warp-per-tet kernel");
+            for (int i = 0; i < (g32_slot_off(L + 1) - g32_slot_off(L)) * 32; i++) {
+                const int src = first + (i < cnt ? i : 0);
+                for (int k = 0; k < 4; k++) t32[4 * ((size_t)g32_slot_off(L) * 32 + i) + k] = tl[4 * (size_t)src + k];
+            }
+        }
+        CK(cudaMalloc(&ctx->d_lat32, t32.size() * sizeof(float)));
+        CK(cudaMemcpy(ctx->d_lat32, t32.data(), t32.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (const char *ev = getenv("DSCGPU_TET_VARIANT")) ctx->tet_variant = atoi(ev);
+    if (voxels_host && (ctx->tet_variant & 1024) && g32_fits(ctx)) { // bricked copy for the warp-per-tet kernel, once per volume
+        int rb = ensure_bricks(ctx);
+        if (rb) return rb;
+    }
     if (const char *ev = getenv("DSCGPU_FORCE_THREAD_GATHER")) ctx->force_thread_gather = atoi(ev);
     CK(cudaMemcpyToSymbolAsync(c_gauss, DSC_GAUSS, sizeof(DSC_GAUSS), 0, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyToSymbolAsync(c_gauss_off, DSC_GAUSS_SET_OFFSET, sizeof(DSC_GAUSS_SET_OFFSET), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -906,6 +1035,9 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
     if (ctx->d_tet_bary) cudaFree(ctx->d_tet_bary);
     if (ctx->d_tet_bary_f) cudaFree(ctx->d_tet_bary_f);
     if (ctx->d_tet_lat) cudaFree(ctx->d_tet_lat);
+    if (ctx->d_lat32) cudaFree(ctx->d_lat32);
+    if (ctx->d_brick) cudaFree(ctx->d_brick);
+    if (ctx->d_brick_flags) cudaFree(ctx->d_brick_flags);
     if (ctx->vol_tex) cudaDestroyTextureObject(ctx->vol_tex);
     if (ctx->vol_array) cudaFreeArray(ctx->vol_array);
     for (int i = 0; i < DSCGPU_T_COUNT; i++) {
@@ -934,7 +1066,31 @@ int dscgpu_synchronize(dscgpu_ctx *ctx)
     return sync_and_check(ctx);
 }
 
-void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx) { return ctx ? ctx->d_vol : nullptr; }
+void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx)
+{
+    if (!ctx) return nullptr;
+    ctx->brick_valid = false; // the caller may write the volume through this pointer
+    return ctx->d_vol;
+}
+
+int dscgpu_volume_modified(dscgpu_ctx *ctx)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ctx->brick_valid = false;
+    return DSCGPU_OK;
+}
+
+int dscgpu_volume_upload(dscgpu_ctx *ctx, const void *voxels_host)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(voxels_host, "voxels_host is NULL");
+    const size_t n = (size_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2];
+    CK(cudaMemcpyAsync(ctx->d_vol, voxels_host, n * dtype_size(ctx->dtype), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->brick_valid = false;
+    ctx->has_sum_table = false;
+    return DSCGPU_OK;
+}
 double *dscgpu_sum_table_ptr_dev(dscgpu_ctx *ctx) { return ctx ? ctx->d_sum_table : nullptr; }
 
 int dscgpu_build_sum_table(dscgpu_ctx *ctx)
@@ -1479,7 +1635,7 @@ int dscgpu_build_texture(dscgpu_ctx *ctx)
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 1024, "variant is a 10-bit field");
+    ARG(variant >= 0 && variant < 2048, "variant is an 11-bit field");
     if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
         int r = dscgpu_build_texture(ctx);
         if (r) return r;

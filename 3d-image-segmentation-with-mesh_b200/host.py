@@ -149,6 +149,14 @@ class Image3D:
     def volume_ptr_dev(self):
         return self.lib.dscgpu_volume_ptr_dev(self._ctx)
 
+    def write_volume(self, volume):
+        """Replaces the voxels (same shape and dtype): image3d::load on a live object."""
+        volume = np.ascontiguousarray(volume)
+        if volume.shape != self.shape or volume.dtype != self.dtype:
+            raise ValueError("volume must keep its shape and dtype")
+        self._check(self.lib.dscgpu_volume_upload(self._ctx, _ptr(volume)), "dscgpu_volume_upload")
+        self._has_table = False
+
     def close(self):
         if getattr(self, "_ctx", None):
             self.lib.dscgpu_ctx_destroy(self._ctx)

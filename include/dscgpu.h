@@ -94,6 +94,13 @@ int dscgpu_set_stream(dscgpu_ctx *ctx, void *cuda_stream);
 int dscgpu_synchronize(dscgpu_ctx *ctx);
 /* Device pointer of the voxel volume (dtype as created) and of the z prefix-sum table (FP64). */
 void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx);
+/* The tet pass gathers from a bricked copy of the volume (4x2x4-voxel bricks, built once per volume like the sum table).
+ * Call this after writing the volume through dscgpu_volume_ptr_dev so that the copy is rebuilt at the next tet pass
+ * (fetching the pointer marks it stale as well). */
+int dscgpu_volume_modified(dscgpu_ctx *ctx);
+/* Replaces the voxels of an existing context (same dims and dtype as at creation): image3d::load on a live object.  The
+ * sum table has to be rebuilt afterwards (dscgpu_build_sum_table). */
+int dscgpu_volume_upload(dscgpu_ctx *ctx, const void *voxels_host);
 double *dscgpu_sum_table_ptr_dev(dscgpu_ctx *ctx);
 
 /* image3d::build_sum_table (DEMO/image3d.cpp:143-177): S[x,y,z] = S[x,y,z-1] + V[x,y,z], bit-exact. */
@@ -222,7 +229,10 @@ int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes);
  *   bit 0 (1)    one thread per tet;  + bit 1 (2): gather through a 3-D texture;  + bit 2 (4): FP32 filter
  *   bit 3 (8)    batched G-lanes-per-tet kernel: bits 4-5 = log2(gathers in flight per lane), bit 2 (4) = FP32 filter
  *   bit 6 (64)   two-phase CTA kernel (setup per thread, sampling per warp, FP32 filter)
- * Default 40 (= 8 | 2<<4).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
+ *   bit 7 (128)  w2: warp-level two-phase kernel, origin-relative lattice coordinates;  256: w3 fixed-point floor;  512: w4 pipelined w2
+ *   bit 10 (1024) warp-per-tet kernel over the bricked volume, packed FP32 (FFMA2) position arithmetic; serves every call
+ *                without candidates and with include_bound == 0, the remaining bits choose the kernel for the other calls
+ * Default 1152 (= 1024 | 128).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
  * Per-candidate outputs (tet_energy / tet_variation) always use the v1 kernel. */
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant);
 int dscgpu_build_texture(dscgpu_ctx *ctx);

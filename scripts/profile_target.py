@@ -37,6 +37,14 @@ def main():
     snap = syn.build_case(vol, edge, P, cfg["thresholds"], tet_mean, jitter=0.2, seed=5)
     seg.set_snapshot(snap)
     seg.enable_timers(True)
+    if what == "hot":  # the instantiation of the per-iteration hot path: no per-tet outputs, no second moment
+        import torch
+        d_sums = torch.zeros(3 * P, dtype=torch.float64, device="cuda")
+        for i in range(reps):
+            seg.tet_phase_sums_dev(d_sums.data_ptr())
+            img.synchronize()
+            print("tet ms", seg.timer_ms("tet"), d_sums.cpu().numpy())
+        return
     for i in range(reps):
         if what in ("all", "tet"):
             o = seg.tet_integrate(per_tet=False)

@@ -38,7 +38,7 @@ namespace dsc {
 constexpr int kBrickPad = 8;                      // voxels of padding on every side (multiple of every brick extent)
 constexpr int kG32Slots = 66;                     // sum over n = 1..9 of ceil(n^3 / 32)
 constexpr int kG32Rows = kG32Slots * 32;          // padded table rows
-constexpr int kG32WarpBytes = 2048 + 256 + 256 + 512 + 256 + 128; // rec, w, base/meta, nd, v, slow meta
+constexpr int kG32WarpBytes = 2048 + 256 + 256 + 512 + 256 + 128 + 128 + 256 + 128; // rec, w, control words, nd, v, meta, base, slow w, slow meta
 constexpr int kG32SmemBytes = kG32Rows * 16 + 8 * kG32WarpBytes;
 
 // first 32-row slot of level L (n = L + 1) in the padded table
@@ -55,8 +55,8 @@ DSC_HD unsigned brick_index(int x, int y, int z, unsigned Sy, unsigned Sz)
     return (zp >> 2) * Sz + (yp >> 1) * Sy + ((xp >> 2) << 5) + ((zp & 3u) << 3) + ((yp & 1u) << 2) + (xp & 3u);
 }
 
-// Builds the bricked copy.  flags bit 0 is raised when a float volume holds anything but +0 and positive normal numbers
-// (negative values, denormals, infinities, NaNs): the kernel then widens voxels with the general routine.
+// Builds the bricked copy.  flags bit 0 is raised when a float volume holds anything but non-negative finite numbers
+// (negative values incl. -0, infinities, NaNs): the kernel then widens voxels with the general routine.
 template <typename VoxT>
 __global__ void brick_volume_kernel(const VoxT *__restrict__ vol, VoxT *__restrict__ out, int X, int Y, int Z, int NBX, int NBY, int NBZ, unsigned *flags)
 {
@@ -75,7 +75,7 @@ __global__ void brick_volume_kernel(const VoxT *__restrict__ vol, VoxT *__restri
             v = vol[((size_t)max(z, 0) * Y + max(y, 0)) * X + max(x, 0)];
             if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
                 const unsigned bits = __float_as_uint((float)v);
-                if (bits != 0u && (bits - 0x00800000u) >= 0x7f000000u) f = 1;
+                if (bits >= 0x7f800000u) f = 1; // negative (sign bit), infinite or NaN
             }
         }
         out[i] = v;
@@ -119,15 +119,6 @@ DSC_D f32x2 add2(f32x2 a, f32x2 b)
     return r;
 }
 
-// float -> double for +0 and positive normal numbers, three integer ops and a select (no F2F: the XU pipe is slow)
-DSC_D double widen_simple(float f)
-{
-    const unsigned b = __float_as_uint(f);
-    unsigned hi = (b >> 3) + 0x38000000u;
-    hi = b ? hi : 0u;
-    return __hiloint2double((int)hi, (int)(b << 29));
-}
-
 DSC_D double warp_sum_d(double v)
 {
 #pragma unroll
@@ -148,7 +139,16 @@ DSC_D unsigned g32_exact_index(const TetG32Args &a, V3 p0, V3 p1, V3 p2, V3 p3, 
     return 0u;
 }
 
-// meta word of a tet record: label 0-7 | level L 8-11 | active 12 | lane in tile 13-17 | first table slot 18-24
+// meta word of a tet record: label 0-7 | level L 8-11 | active 12 | lane in tile 13-17
+// pair control words (one int4 per pair, made lane-parallel at the end of phase A):
+//   x, y  brick index of the two origins minus the folded magic bits
+//   z     rowA 0-11 | rowB 12-23 | labelA 24-31          (first table row of each tet's level)
+//   w     nfull 0-4 | nall 5-9 | eps 10 | same level 11 | B active 12 | LA 13-16 | LB 17-20 | labelB 21-28 | same label as the previous pair 29
+//
+// Voxel widening: a non-negative finite float with bits b is the double with words (b >> 3, b << 29) times 2^896 (zeros
+// and denormals included), so sums are kept scaled by 2^-896 -- two shifts per voxel, no conversion instruction, no
+// special cases -- and the tet weight v/n^3 carries the factor 2^896 (an exact scaling).  Volumes that hold negative
+// values, infinities or NaNs (flag raised when the bricked copy is built) use the general routine and no scaling.
 template <typename VoxT, bool SIMPLE, bool WANT_SQ, bool PER_TET>
 __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const TetG32Args a)
 {
@@ -156,16 +156,20 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
     float4 *s_lat = reinterpret_cast<float4 *>(g32_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wb = g32_smem + kG32Rows * 16 + warp * kG32WarpBytes;
-    ulonglong2 *w_rec = reinterpret_cast<ulonglong2 *>(wb);        // [16 pairs][8]: 16 float fields x (half A, half B)
-    double *w_w = reinterpret_cast<double *>(wb + 2048);           // [32 slots] v / n^3 (/ denominator for integer voxels)
-    int *w_bm = reinterpret_cast<int *>(wb + 2304);                // [16 pairs] (baseA, baseB, metaA, metaB)
+    ulonglong2 *w_rec = reinterpret_cast<ulonglong2 *>(wb);        // [8 field pairs][16 tet pairs]: (f A, f B, f+1 A, f+1 B)
+    double *w_w = reinterpret_cast<double *>(wb + 2048);           // [32 slots] v / n^3 (times the widening scale, over the integer denominator)
+    int4 *w_ctl = reinterpret_cast<int4 *>(wb + 2304);             // [16 pairs] control words
     uint4 *w_nd = reinterpret_cast<uint4 *>(wb + 2560);            // [32 slots] node ids
-    double *w_v = reinterpret_cast<double *>(wb + 3072);           // [32 slots] volume
-    int *w_smeta = reinterpret_cast<int *>(wb + 3328);             // [32 slots] meta of slow tets (stored from the end)
+    double *w_v = reinterpret_cast<double *>(wb + 3072);           // [32 slots] volume (per-tet outputs only)
+    int *w_meta = reinterpret_cast<int *>(wb + 3328);              // [32 slots] meta
+    unsigned *w_base = reinterpret_cast<unsigned *>(wb + 3456);    // [32 slots] origin index
+    double *w_sw = reinterpret_cast<double *>(wb + 3584);          // slow tets (stored from the end): weight
+    int *w_smeta = reinterpret_cast<int *>(wb + 3840);             // ... meta
     __shared__ double sm[8][3 * kMaxPhase];
     for (int i = threadIdx.x; i < kG32Rows; i += blockDim.x) s_lat[i] = a.lat32[i];
     __syncthreads();
 
+    constexpr bool F32S = sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral && SIMPLE; // scaled widening in use
     const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.brick);
     const unsigned Sy = a.Sy, Sz = a.Sz;
     const unsigned Ky = Sy - 8u, Kz = Sz - 32u;
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
     const f32x2 C4 = pk2(37748736.0f, 37748736.0f);                                 // 1.5*2^25 - 1.5*2^23
     const f32x2 K2 = pk2(0.999999940395355224609375f, 0.999999940395355224609375f); // 1 - 2^-24
     const double dn = VoxTraits<VoxT>::denom();
+    const double UNSCALE = F32S ? 0x1p+896 : 1.0, INV_UNSCALE = F32S ? 0x1p-896 : 1.0;
     const unsigned full = 0xffffffffu;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned n_work = a.tet_end - a.tet_begin;
@@ -205,9 +210,80 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
         if (WANT_SQ) cur_sq += xs;
     };
 
+    // ---- the pair in flight: its gathers have been issued, its sums are not final yet ----
+    // Accumulation is deferred: the voxels gathered by one step are added after the NEXT step has computed its indices and
+    // just before it issues its own gathers, so the index arithmetic of a step overlaps the memory latency of the previous one.
+    double sA = 0, sB = 0, sqA = 0, sqB = 0;   // sums of the open pair (float / double voxels)
+    unsigned isA = 0, isB = 0;                 // ... integer voxels
+    unsigned long long iqA = 0, iqB = 0;
+    VoxT pendA[2], pendB[2];
+    pendA[0] = pendA[1] = pendB[0] = pendB[1] = (VoxT)0;
+    int pend_n = 0;
+    bool open_pair = false, close_pending = false;
+    double cl_wA = 0, cl_wB = 0;               // of the pair waiting to be closed
+    int cl_labA = 0, cl_labB = 0;
+    bool cl_fast = false;
+
+    auto add_voxel = [&](VoxT val, double &s, double &sq, unsigned &is, unsigned long long &iq) {
+        if constexpr (VoxTraits<VoxT>::integral) {
+            const unsigned q = (unsigned)val;
+            is += q;
+            if (WANT_SQ) iq += (unsigned long long)q * q;
+        } else {
+            double I;
+            if constexpr (sizeof(VoxT) == 4) {
+                if (SIMPLE) {
+                    const unsigned b = __float_as_uint((float)val);
+                    I = __hiloint2double((int)(b >> 3), (int)(b << 29)); // val * 2^-896, exact
+                } else {
+                    I = widen_exact((float)val);
+                }
+            } else {
+                I = (double)val;
+            }
+            s += I;
+            if (WANT_SQ) {
+                const double Iu = I * UNSCALE; // exact
+                sq = fma(Iu, Iu, sq); // second moment: tolerance quantity, fused on purpose
+            }
+        }
+    };
+    // adds the gathered voxels of the previous step; closes the previous pair if that step was its last
+    auto drain = [&]() {
+        if (pend_n) {
+            add_voxel(pendA[0], sA, sqA, isA, iqA);
+            add_voxel(pendB[0], sB, sqB, isB, iqB);
+            if (pend_n == 2) {
+                add_voxel(pendA[1], sA, sqA, isA, iqA);
+                add_voxel(pendB[1], sB, sqB, isB, iqB);
+            }
+            pend_n = 0;
+        }
+        if (close_pending) {
+            if constexpr (VoxTraits<VoxT>::integral) {
+                sA = (double)isA; sB = (double)isB;
+                if (WANT_SQ) { sqA = (double)iqA / dn; sqB = (double)iqB / dn; } // the weight carries the other 1/dn
+            }
+            double xsA = 0, xsB = 0;
+            if (WANT_SQ) { xsA = sqA * (cl_wA * INV_UNSCALE); xsB = sqB * (cl_wB * INV_UNSCALE); } // the weight carries 2^896
+            if (cl_fast) { // both labels are the running label
+                cur_acc += sA * cl_wA + sB * cl_wB;
+                if (WANT_SQ) cur_sq += xsA + xsB;
+            } else {
+                contribute(cl_labA, sA * cl_wA, xsA);
+                if (cl_labB) contribute(cl_labB, sB * cl_wB, xsB);
+            }
+            sA = sB = sqA = sqB = 0;
+            isA = isB = 0;
+            iqA = iqB = 0;
+            close_pending = false;
+        }
+    };
+
     for (unsigned tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += total_warps) {
         const unsigned base_t = a.tet_begin + tile * 32;
         const int nb = (int)min(32u, a.tet_end - base_t);
+        if (PER_TET) drain();
         __syncwarp();
         // ---------------- phase A: lane <-> tet ----------------
         int nfast = 0, nslow = 0;
@@ -235,12 +311,13 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                     big = n3 > 32;
                     w = v / (double)n3;
                     if (VoxTraits<VoxT>::integral) w = w / dn;
+                    w = w * UNSCALE;
                     const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
                     const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
                     const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
                     // the whole tet inside the padded copy, with a margin of two voxels
                     const bool inside = lox >= -6.0 && loy >= -6.0 && loz >= -6.0 && hix < (double)a.X + 6.0 && hiy < (double)a.Y + 6.0 && hiz < (double)a.Z + 6.0;
-                    meta = ((label >= 1 && label < 255) ? label : 255) | (L << 8) | (1 << 12) | (lane << 13) | (g32_slot_off(L) << 18);
+                    meta = ((label >= 1 && label < 255) ? label : 255) | (L << 8) | (1 << 12) | (lane << 13);
                     if (inside) {
                         // origin: floor(min corner) rounded down to a brick corner (the padding is a multiple of the brick)
                         const int oxi = (((int)floor(lox) + kBrickPad) & ~3) - kBrickPad;
@@ -287,65 +364,78 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
             const unsigned m_slow = __ballot_sync(full, act && !fast);
             nslow = __popc(m_slow);
             if (act && fast) {
-                const int p = slot >> 1, h = slot & 1;
+                // field pair i = k / 2 of tet pair p sits at w_rec[i * 16 + p] as (f_k A, f_k B, f_k+1 A, f_k+1 B):
+                // consecutive slots write consecutive words (2-way conflicts at worst), a pair reads 8 broadcast LDS.128
                 float *recf = reinterpret_cast<float *>(w_rec);
+                const int p = slot >> 1, h = slot & 1;
 #pragma unroll
-                for (int k = 0; k < 16; k++) recf[(p * 16 + k) * 2 + h] = f[k];
-                w_bm[p * 4 + h] = (int)base;
-                w_bm[p * 4 + 2 + h] = meta;
+                for (int k = 0; k < 16; k++) recf[((k >> 1) * 16 + p) * 4 + (k & 1) * 2 + h] = f[k];
+                w_base[slot] = base;
+                w_meta[slot] = meta;
                 w_w[slot] = w;
                 w_nd[slot] = nd;
                 if (PER_TET) w_v[slot] = v;
                 if (slot == nfast - 1 && h == 0) { // odd count: the last pair's second half mirrors the first, inactive
 #pragma unroll
-                    for (int k = 0; k < 16; k++) recf[(p * 16 + k) * 2 + 1] = f[k];
-                    w_bm[p * 4 + 1] = (int)base;
-                    w_bm[p * 4 + 3] = meta & ~(1 << 12);
+                    for (int k = 0; k < 16; k++) recf[((k >> 1) * 16 + p) * 4 + (k & 1) * 2 + 1] = f[k];
+                    w_base[slot + 1] = base;
+                    w_meta[slot + 1] = meta & ~(1 << 12);
+                    w_w[slot + 1] = 0.0;
                 }
-            } else if (act) {
+            }
+            if (act && !fast) { // node ids and volumes share the slot arrays (nfast + nslow <= 32); weight and meta have their own
                 const int ss = 31 - __popc(m_slow & lt);
                 w_smeta[ss] = meta;
-                w_w[ss] = w;
+                w_sw[ss] = w * INV_UNSCALE;
                 w_nd[ss] = nd;
                 if (PER_TET) w_v[ss] = v;
             }
         }
+        // pair control words, lane <-> pair
+        const int npairs = (nfast + 1) >> 1;
+        __syncwarp();
+        {
+            int4 c = make_int4(0, 0, 0, 0);
+            int labA = 0, labBe = 0;
+            if (lane < npairs) {
+                const int mA = w_meta[2 * lane], mB = w_meta[2 * lane + 1];
+                const int LA = (mA >> 8) & 15, LB = (mB >> 8) & 15;
+                const bool actB = (mB >> 12) & 1;
+                const int n3A = (LA + 1) * (LA + 1) * (LA + 1), n3B = actB ? (LB + 1) * (LB + 1) * (LB + 1) : 0;
+                const int rowA = g32_slot_off(LA) * 32, rowB = g32_slot_off(LB) * 32;
+                const int nfull = min(n3A, n3B) >> 5, nall = (max(n3A, n3B) + 31) >> 5;
+                const int eps = ((0x164 >> LA) | (0x164 >> LB)) & 1; // rows of n = 3, 6, 7, 9 do not sum to exactly one
+                labA = mA & 0xff;
+                const int labB = actB ? (mB & 0xff) : 0;
+                labBe = actB ? labB : labA;
+                c.x = (int)w_base[2 * lane];
+                c.y = (int)w_base[2 * lane + 1];
+                c.z = rowA | (rowB << 12) | (labA << 24);
+                c.w = nfull | (nall << 5) | (eps << 10) | ((rowA == rowB ? 1 : 0) << 11) | ((actB ? 1 : 0) << 12) | (LA << 13) | (LB << 17) | (labB << 21);
+            }
+            const int prevB = __shfl_up_sync(full, labBe, 1);
+            if (lane < npairs) {
+                if (lane > 0 && labA == labBe && labA == prevB) c.w |= 1 << 29; // the running label is already this pair's
+                w_ctl[lane] = c;
+            }
+        }
         __syncwarp();
         // ---------------- phase B: the warp walks pairs of tets; lane <-> table row, the two halves of a packed register <-> the two tets ----------------
-        const int npairs = (nfast + 1) >> 1;
         for (int p = 0; p < npairs; p++) {
-            const ulonglong2 r0 = w_rec[p * 8 + 0], r1 = w_rec[p * 8 + 1], r2 = w_rec[p * 8 + 2], r3 = w_rec[p * 8 + 3];
-            const ulonglong2 r4 = w_rec[p * 8 + 4], r5 = w_rec[p * 8 + 5], r6 = w_rec[p * 8 + 6], r7 = w_rec[p * 8 + 7];
+            const ulonglong2 r0 = w_rec[0 * 16 + p], r1 = w_rec[1 * 16 + p], r2 = w_rec[2 * 16 + p], r3 = w_rec[3 * 16 + p];
+            const ulonglong2 r4 = w_rec[4 * 16 + p], r5 = w_rec[5 * 16 + p], r6 = w_rec[6 * 16 + p], r7 = w_rec[7 * 16 + p];
             const f32x2 q0x = r0.x, q0y = r0.y, q0z = r1.x, thr2 = r1.y, e1x = r2.x, e1y = r2.y, e1z = r3.x, e2x = r3.y;
             const f32x2 e2y = r4.x, e2z = r4.y, e3x = r5.x, e3y = r5.y, e3z = r6.x, o_x = r6.y, o_y = r7.x, o_z = r7.y;
-            const int4 bm = reinterpret_cast<const int4 *>(w_bm)[p];
-            const unsigned baseA = (unsigned)bm.x, baseB = (unsigned)bm.y;
-            const int metaA = bm.z, metaB = bm.w;
-            const int LA = (metaA >> 8) & 15, LB = (metaB >> 8) & 15;
-            const bool actB = (metaB >> 12) & 1;
+            const int4 ctl = w_ctl[p];
+            const unsigned baseA = (unsigned)ctl.x, baseB = (unsigned)ctl.y;
+            const int rowA = (ctl.z & 0xfff) + lane, rowB = ((ctl.z >> 12) & 0xfff) + lane;
+            const int nfull = ctl.w & 31, nall = (ctl.w >> 5) & 31;
+            const int LA = (ctl.w >> 13) & 15, LB = (ctl.w >> 17) & 15;
+            const bool actB = (ctl.w >> 12) & 1;
             const int n3A = (LA + 1) * (LA + 1) * (LA + 1), n3B = actB ? (LB + 1) * (LB + 1) * (LB + 1) : 0;
-            const int rowA = ((metaA >> 18) & 127) * 32 + lane, rowB = ((metaB >> 18) & 127) * 32 + lane;
-            const int nfull = min(n3A, n3B) >> 5, nall = (max(n3A, n3B) + 31) >> 5;
-            const bool has_eps = (((0x164 >> LA) | (0x164 >> LB)) & 1) != 0; // rows of n = 3, 6, 7, 9 do not sum to exactly one
             float thrA, thrB;
             upk2(thr2, thrA, thrB);
 
-            double sA = 0, sB = 0, sqA = 0, sqB = 0;
-            unsigned isA = 0, isB = 0;
-            unsigned long long iqA = 0, iqB = 0;
-            auto add_voxel = [&](VoxT val, double &s, double &sq, unsigned &is, unsigned long long &iq) {
-                if constexpr (VoxTraits<VoxT>::integral) {
-                    const unsigned q = (unsigned)val;
-                    is += q;
-                    if (WANT_SQ) iq += (unsigned long long)q * q;
-                } else {
-                    double I;
-                    if constexpr (sizeof(VoxT) == 4) I = SIMPLE ? widen_simple((float)val) : widen_exact((float)val);
-                    else I = (double)val;
-                    s += I;
-                    if (WANT_SQ) sq = fma(I, I, sq); // second moment: tolerance quantity, fused on purpose
-                }
-            };
             // NS consecutive 32-row slots starting at s; TAIL: rows past the end of either tet are masked
             // SAME: both tets on the same level, one table row serves both halves (broadcast operand, no second LDS)
             auto body = [&](auto ns_c, auto tail_c, auto eps_c, auto same_c, int s) {
@@ -417,11 +507,10 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                         if ((s + u) * 32 + lane >= n3B) idxB[u] = 0u;
                     }
                 }
-                VoxT valA[NS], valB[NS];
+                drain(); // the previous step's voxels (and, if that step ended a pair, the pair itself)
 #pragma unroll
-                for (int u = 0; u < NS; u++) { valA[u] = __ldg(vol + idxA[u]); valB[u] = __ldg(vol + idxB[u]); }
-#pragma unroll
-                for (int u = 0; u < NS; u++) { add_voxel(valA[u], sA, sqA, isA, iqA); add_voxel(valB[u], sB, sqB, isB, iqB); }
+                for (int u = 0; u < NS; u++) { pendA[u] = __ldg(vol + idxA[u]); pendB[u] = __ldg(vol + idxB[u]); }
+                pend_n = NS;
             };
             using I1 = std::integral_constant<int, 1>;
             using I2 = std::integral_constant<int, 2>;
@@ -431,26 +520,35 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                 for (; s < nfull; s++) body(I1{}, std::false_type{}, eps_c, same_c, s);
                 for (; s < nall; s++) body(I1{}, std::true_type{}, eps_c, same_c, s);
             };
-            if (rowA == rowB) {
-                if (has_eps) run(std::true_type{}, std::true_type{});
+            if (ctl.w & (1 << 11)) {
+                if (ctl.w & (1 << 10)) run(std::true_type{}, std::true_type{});
                 else run(std::false_type{}, std::true_type{});
             } else {
-                if (has_eps) run(std::true_type{}, std::false_type{});
+                if (ctl.w & (1 << 10)) run(std::true_type{}, std::false_type{});
                 else run(std::false_type{}, std::false_type{});
             }
-            if constexpr (VoxTraits<VoxT>::integral) {
-                sA = (double)isA; sB = (double)isB;
-                if (WANT_SQ) { sqA = (double)iqA / dn; sqB = (double)iqB / dn; } // w carries the other 1/dn
+            // the pair is closed by the next drain(), once its last gathers have landed
+            {
+                const double2 ww = reinterpret_cast<const double2 *>(w_w)[p];
+                cl_wA = ww.x; cl_wB = ww.y;
+                cl_labA = (ctl.z >> 24) & 0xff; cl_labB = (ctl.w >> 21) & 0xff;
+                cl_fast = (ctl.w >> 29) & 1;
+                close_pending = true;
             }
             if (PER_TET) { // per-tet outputs: the exact sum of the tet's voxels, then the reference's own expression
+                if (pend_n) {
+                    add_voxel(pendA[0], sA, sqA, isA, iqA); add_voxel(pendB[0], sB, sqB, isB, iqB);
+                    if (pend_n == 2) { add_voxel(pendA[1], sA, sqA, isA, iqA); add_voxel(pendB[1], sB, sqB, isB, iqB); }
+                    pend_n = 0;
+                }
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     if (h == 1 && !actB) break;
-                    double st = warp_sum_d(h ? sB : sA);
-                    if (VoxTraits<VoxT>::integral) st = st / dn;
+                    double st;
+                    if constexpr (VoxTraits<VoxT>::integral) st = warp_sum_d((double)(h ? isB : isA)) / dn;
+                    else st = warp_sum_d(h ? sB : sA) * UNSCALE;
                     if (lane == 0) {
-                        const int meta = h ? metaB : metaA;
-                        const unsigned t = base_t + ((meta >> 13) & 31);
+                        const unsigned t = base_t + ((w_meta[2 * p + h] >> 13) & 31);
                         const double vv = w_v[2 * p + h];
                         const double tot = st * vv / (double)(h ? n3B : n3A); // total = total * v / a.size()  (image3d.cpp:371)
                         if (a.tet_total) a.tet_total[t] = tot;
@@ -458,12 +556,11 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                         if (a.tet_mean) a.tet_mean[t] = tot / vv;
                     }
                 }
+                drain();
             }
-            const double2 ww = reinterpret_cast<const double2 *>(w_w)[p];
-            contribute(metaA & 0xff, sA * ww.x, WANT_SQ ? sqA * ww.x : 0.0);
-            if (actB) contribute(metaB & 0xff, sB * ww.y, WANT_SQ ? sqB * ww.y : 0.0);
         }
         // ---------------- slow tets: outside the padded copy or wider than 100 voxels; exact arithmetic, the whole warp on one tet ----------------
+        if (nslow) drain();
         for (int k = 0; k < nslow; k++) {
             const int ss = 31 - k;
             const int meta = w_smeta[ss];
@@ -503,10 +600,11 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                     if (a.tet_mean) a.tet_mean[t] = tot / vv;
                 }
             }
-            const double w = w_w[ss];
+            const double w = w_sw[ss]; // true doubles here
             contribute(meta & 0xff, s * w, WANT_SQ ? sq * w : 0.0);
         }
     }
+    drain();
     flush();
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(full, nsamp, m);

@@ -17,8 +17,8 @@
 //  * tet-local origins are aligned to brick corners, so the brick index and the offset inside the brick are both linear
 //    in r and floor(r / brick): idx = base + rx + 28 hx + 4 ry + (Sy-8) hy + 8 rz + (Sz-32) hz.
 //  * packed FP32 (Blackwell FFMA2 / FADD2, PTX fma.rn.f32x2): one lane evaluates two samples per instruction -- the two
-//    halves of a pair of tets (pairs are formed in phase A from tets of the same label and sample count) -- which halves
-//    the issue slots of the position arithmetic.  floor() is the 1.5*2^23 trick; floor(r/4) and floor(r/2) come from one
+//    halves of a pair of tets (pairs are formed in phase A from tets of the same label and sample level, so both halves
+//    use the same table row) -- which halves the issue slots of the position arithmetic.  floor() is the 1.5*2^23 trick; floor(r/4) and floor(r/2) come from one
 //    more FFMA2 each on the already rounded value: fma(t, 1-2^-23, 4.5*2^23) rounds M4 + r - 1.5 - r 2^-23 at ulp 4.
 //  * no per-tet cross-lane reduction: each lane multiplies its partial sum by the tet's v/n^3 and keeps a running sum for
 //    the current label; a warp reduction happens only when the label changes (tets are sorted by label inside a tile).
@@ -38,7 +38,8 @@ namespace dsc {
 constexpr int kBrickPad = 8;                      // voxels of padding on every side (multiple of every brick extent)
 constexpr int kG32Slots = 66;                     // sum over n = 1..9 of ceil(n^3 / 32)
 constexpr int kG32Rows = kG32Slots * 32;          // padded table rows
-constexpr int kG32WarpBytes = 2048 + 256 + 256 + 512 + 256 + 128 + 128 + 256 + 128; // rec, w, control words, nd, v, meta, base, slow w, slow meta
+constexpr int kG32Pairs = 24;                     // tet pairs a tile can hold (32 tets plus the odd member of each label/level class)
+constexpr int kG32WarpBytes = 8 * kG32Pairs * 16 + 2 * kG32Pairs * 8 + kG32Pairs * 16 + 512 + 256 + 2 * kG32Pairs * 4 + 2 * kG32Pairs * 4 + 128 + 256;
 constexpr int kG32SmemBytes = kG32Rows * 16 + 8 * kG32WarpBytes;
 
 // first 32-row slot of level L (n = L + 1) in the padded table
@@ -139,11 +140,11 @@ DSC_D unsigned g32_exact_index(const TetG32Args &a, V3 p0, V3 p1, V3 p2, V3 p3, 
     return 0u;
 }
 
-// meta word of a tet record: label 0-7 | level L 8-11 | active 12 | lane in tile 13-17
+// meta word of a tet: label 0-7 | level L 8-11 | active 12 | lane in tile 13-17
 // pair control words (one int4 per pair, made lane-parallel at the end of phase A):
 //   x, y  brick index of the two origins minus the folded magic bits
-//   z     rowA 0-11 | rowB 12-23 | labelA 24-31          (first table row of each tet's level)
-//   w     nfull 0-4 | nall 5-9 | eps 10 | same level 11 | B active 12 | LA 13-16 | LB 17-20 | labelB 21-28 | same label as the previous pair 29
+//   z     first table row of the level 0-11 | label 12-19 | tile lane of A 20-24 | tile lane of B 25-29
+//   w     nfull 0-4 | nall 5-9 | eps 10 | B active 12 | L 13-16 | label equals the previous pair's 29
 //
 // Voxel widening: a non-negative finite float with bits b is the double with words (b >> 3, b << 29) times 2^896 (zeros
 // and denormals included), so sums are kept scaled by 2^-896 -- two shifts per voxel, no conversion instruction, no
@@ -156,15 +157,16 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
     float4 *s_lat = reinterpret_cast<float4 *>(g32_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wb = g32_smem + kG32Rows * 16 + warp * kG32WarpBytes;
-    ulonglong2 *w_rec = reinterpret_cast<ulonglong2 *>(wb);        // [8 field pairs][16 tet pairs]: (f A, f B, f+1 A, f+1 B)
-    double *w_w = reinterpret_cast<double *>(wb + 2048);           // [32 slots] v / n^3 (times the widening scale, over the integer denominator)
-    int4 *w_ctl = reinterpret_cast<int4 *>(wb + 2304);             // [16 pairs] control words
-    uint4 *w_nd = reinterpret_cast<uint4 *>(wb + 2560);            // [32 slots] node ids
-    double *w_v = reinterpret_cast<double *>(wb + 3072);           // [32 slots] volume (per-tet outputs only)
-    int *w_meta = reinterpret_cast<int *>(wb + 3328);              // [32 slots] meta
-    unsigned *w_base = reinterpret_cast<unsigned *>(wb + 3456);    // [32 slots] origin index
-    double *w_sw = reinterpret_cast<double *>(wb + 3584);          // slow tets (stored from the end): weight
-    int *w_smeta = reinterpret_cast<int *>(wb + 3840);             // ... meta
+    constexpr int NP = kG32Pairs;
+    ulonglong2 *w_rec = reinterpret_cast<ulonglong2 *>(wb);                 // [8 field pairs][NP tet pairs]: (f A, f B, f+1 A, f+1 B)
+    double *w_w = reinterpret_cast<double *>(wb + 128 * NP);                // [2 NP slots] v / n^3 (times the widening scale, over the integer denominator)
+    int4 *w_ctl = reinterpret_cast<int4 *>(wb + 144 * NP);                  // [NP pairs] control words
+    uint4 *w_nd = reinterpret_cast<uint4 *>(wb + 160 * NP);                 // [32 tile lanes] node ids
+    double *w_v = reinterpret_cast<double *>(wb + 160 * NP + 512);          // [32 tile lanes] volume (per-tet outputs only)
+    int *w_meta = reinterpret_cast<int *>(wb + 160 * NP + 768);             // [2 NP slots] meta
+    unsigned *w_base = reinterpret_cast<unsigned *>(wb + 168 * NP + 768);   // [2 NP slots] origin index
+    int *w_slow = reinterpret_cast<int *>(wb + 176 * NP + 768);             // [32] meta of the slow tets
+    double *w_sw = reinterpret_cast<double *>(wb + 176 * NP + 896);         // [32] their weights (unscaled)
     __shared__ double sm[8][3 * kMaxPhase];
     for (int i = threadIdx.x; i < kG32Rows; i += blockDim.x) s_lat[i] = a.lat32[i];
     __syncthreads();
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
     unsigned long long nsamp = 0;
 
     auto flush = [&]() {
-        if (cur_label) {
+        if (__any_sync(full, cur_label != 0)) {
             const double r = warp_sum_d(cur_acc);
             double rs = 0;
             if (WANT_SQ) rs = warp_sum_d(cur_sq);
@@ -203,25 +205,25 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
             cur_sq = 0;
         }
     };
-    // adds one tet's contribution (this lane's partial sum times the tet weight) to the running sum of its label
+    // adds a contribution (this lane's partial sum times the tet weight) to the running sum of its label
     auto contribute = [&](int label, double x, double xs) {
         if (label != cur_label) { flush(); cur_label = label; }
         cur_acc += x;
         if (WANT_SQ) cur_sq += xs;
     };
 
-    // ---- the pair in flight: its gathers have been issued, its sums are not final yet ----
+    // ---- the pair in flight ----
     // Accumulation is deferred: the voxels gathered by one step are added after the NEXT step has computed its indices and
-    // just before it issues its own gathers, so the index arithmetic of a step overlaps the memory latency of the previous one.
+    // just before it issues its own gathers, so the index arithmetic of a step overlaps the memory latency of the previous
+    // one; a pair is closed (sum times weight added to the running label sum) by the drain that follows its last step.
     double sA = 0, sB = 0, sqA = 0, sqB = 0;   // sums of the open pair (float / double voxels)
     unsigned isA = 0, isB = 0;                 // ... integer voxels
     unsigned long long iqA = 0, iqB = 0;
-    VoxT pendA[2], pendB[2];
-    pendA[0] = pendA[1] = pendB[0] = pendB[1] = (VoxT)0;
-    int pend_n = 0;
-    bool open_pair = false, close_pending = false;
+    VoxT pend[4];                              // A0, B0, A1, B1 of the last step (element 0 of the copy, a zero, when unused)
+    pend[0] = pend[1] = pend[2] = pend[3] = (VoxT)0;
+    bool close_pending = false;
     double cl_wA = 0, cl_wB = 0;               // of the pair waiting to be closed
-    int cl_labA = 0, cl_labB = 0;
+    int cl_lab = 0;
     bool cl_fast = false;
 
     auto add_voxel = [&](VoxT val, double &s, double &sq, unsigned &is, unsigned long long &iq) {
@@ -248,31 +250,23 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
             }
         }
     };
-    // adds the gathered voxels of the previous step; closes the previous pair if that step was its last
+    auto add_pending = [&]() {
+        add_voxel(pend[0], sA, sqA, isA, iqA);
+        add_voxel(pend[1], sB, sqB, isB, iqB);
+        add_voxel(pend[2], sA, sqA, isA, iqA);
+        add_voxel(pend[3], sB, sqB, isB, iqB);
+        pend[0] = pend[1] = pend[2] = pend[3] = (VoxT)0;
+    };
     auto drain = [&]() {
-        if (pend_n) {
-            add_voxel(pendA[0], sA, sqA, isA, iqA);
-            add_voxel(pendB[0], sB, sqB, isB, iqB);
-            if (pend_n == 2) {
-                add_voxel(pendA[1], sA, sqA, isA, iqA);
-                add_voxel(pendB[1], sB, sqB, isB, iqB);
-            }
-            pend_n = 0;
-        }
-        if (close_pending) {
+        add_pending();
+        if (__any_sync(full, close_pending)) {
             if constexpr (VoxTraits<VoxT>::integral) {
                 sA = (double)isA; sB = (double)isB;
                 if (WANT_SQ) { sqA = (double)iqA / dn; sqB = (double)iqB / dn; } // the weight carries the other 1/dn
             }
-            double xsA = 0, xsB = 0;
-            if (WANT_SQ) { xsA = sqA * (cl_wA * INV_UNSCALE); xsB = sqB * (cl_wB * INV_UNSCALE); } // the weight carries 2^896
-            if (cl_fast) { // both labels are the running label
-                cur_acc += sA * cl_wA + sB * cl_wB;
-                if (WANT_SQ) cur_sq += xsA + xsB;
-            } else {
-                contribute(cl_labA, sA * cl_wA, xsA);
-                if (cl_labB) contribute(cl_labB, sB * cl_wB, xsB);
-            }
+            if (__any_sync(full, !cl_fast && cl_lab != cur_label)) { flush(); cur_label = cl_lab; }
+            cur_acc += sA * cl_wA + sB * cl_wB;
+            if (WANT_SQ) cur_sq += sqA * (cl_wA * INV_UNSCALE) + sqB * (cl_wB * INV_UNSCALE); // the weight carries 2^896
             sA = sB = sqA = sqB = 0;
             isA = isB = 0;
             iqA = iqB = 0;
@@ -283,14 +277,13 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
     for (unsigned tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += total_warps) {
         const unsigned base_t = a.tet_begin + tile * 32;
         const int nb = (int)min(32u, a.tet_end - base_t);
-        if (PER_TET) drain();
         __syncwarp();
         // ---------------- phase A: lane <-> tet ----------------
-        int nfast = 0, nslow = 0;
+        int nslots = 0, nslow = 0;
         {
             int label = 0, L = 0, n3 = 0, meta = 0;
             unsigned base = 0;
-            bool act = false, fast = false, big = false;
+            bool act = false, fast = false;
             float f[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) f[k] = 0.f;
@@ -308,16 +301,15 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                     L = tet_level(v);
                     n3 = (L + 1) * (L + 1) * (L + 1);
                     nsamp += (unsigned long long)n3;
-                    big = n3 > 32;
                     w = v / (double)n3;
                     if (VoxTraits<VoxT>::integral) w = w / dn;
-                    w = w * UNSCALE;
                     const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
                     const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
                     const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
                     // the whole tet inside the padded copy, with a margin of two voxels
                     const bool inside = lox >= -6.0 && loy >= -6.0 && loz >= -6.0 && hix < (double)a.X + 6.0 && hiy < (double)a.Y + 6.0 && hiz < (double)a.Z + 6.0;
-                    meta = ((label >= 1 && label < 255) ? label : 255) | (L << 8) | (1 << 12) | (lane << 13);
+                    label = (label >= 1 && label < 255) ? label : 255; // labels beyond nb_phase are processed but belong to no phase
+                    meta = label | (L << 8) | (1 << 12) | (lane << 13);
                     if (inside) {
                         // origin: floor(min corner) rounded down to a brick corner (the padding is a multiple of the brick)
                         const int oxi = (((int)floor(lox) + kBrickPad) & ~3) - kBrickPad;
@@ -343,119 +335,130 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                     if (a.tet_mean) a.tet_mean[t] = -1.0;
                 }
             }
-            // order the fast tets by label (first occurrence), tets of at most 32 samples first; sum volumes per label
+            // Order the fast tets by label (first occurrence) and, inside a label, by level; every (label, level) class
+            // starts on an even slot so that the two tets of a pair always share label and table rows.  Volumes are
+            // summed per label on the way.
             int slot = -1;
+            bool mirror = false; // this tet is the odd one of its class: it also fills the second half of its pair, inactive
             unsigned todo = __ballot_sync(full, act);
             while (todo) {
-                const int src = __ffs(todo) - 1;
-                const int lab = __shfl_sync(full, label, src);
-                const bool mine = act && label == lab;
-                const unsigned m = __ballot_sync(full, mine);
-                const unsigned ms = __ballot_sync(full, mine && fast && !big);
-                const unsigned mbg = __ballot_sync(full, mine && fast && big);
-                if (mine && fast) slot = nfast + (big ? __popc(ms) + __popc(mbg & lt) : __popc(ms & lt));
-                nfast += __popc(ms) + __popc(mbg);
-                if (lab >= 1 && lab <= a.nb_phase) {
-                    const double vs = warp_sum_d(mine ? v : 0.0);
+                const int lab = __shfl_sync(full, label, __ffs(todo) - 1);
+                const bool in_lab = act && label == lab;
+                const unsigned m = __ballot_sync(full, in_lab);
+                unsigned todo_l = __ballot_sync(full, in_lab && fast);
+                while (todo_l) {
+                    const int lev = __shfl_sync(full, L, __ffs(todo_l) - 1);
+                    const bool mine = in_lab && fast && L == lev;
+                    const unsigned mc = __ballot_sync(full, mine);
+                    const int cnt = __popc(mc);
+                    if (mine) {
+                        slot = nslots + __popc(mc & lt);
+                        mirror = (cnt & 1) && slot == nslots + cnt - 1;
+                    }
+                    nslots += (cnt + 1) & ~1;
+                    todo_l &= ~mc;
+                }
+                if (lab <= a.nb_phase) {
+                    const double vs = warp_sum_d(in_lab ? v : 0.0);
                     if (lane == lab - 1) acc_vol += vs;
                 }
                 todo &= ~m;
             }
+            if (slot >= 2 * NP) { fast = false; slot = -1; } // more classes than the tile record can hold: the exact path takes the rest
+            if (nslots > 2 * NP) nslots = 2 * NP;
             const unsigned m_slow = __ballot_sync(full, act && !fast);
             nslow = __popc(m_slow);
+            if (act) {
+                w_nd[lane] = nd;
+                if (PER_TET) w_v[lane] = v;
+            }
             if (act && fast) {
-                // field pair i = k / 2 of tet pair p sits at w_rec[i * 16 + p] as (f_k A, f_k B, f_k+1 A, f_k+1 B):
-                // consecutive slots write consecutive words (2-way conflicts at worst), a pair reads 8 broadcast LDS.128
+                // field pair i = k / 2 of tet pair p sits at w_rec[i * NP + p] as (f_k A, f_k B, f_k+1 A, f_k+1 B):
+                // consecutive slots write consecutive words, a pair reads 8 broadcast LDS.128
                 float *recf = reinterpret_cast<float *>(w_rec);
                 const int p = slot >> 1, h = slot & 1;
 #pragma unroll
-                for (int k = 0; k < 16; k++) recf[((k >> 1) * 16 + p) * 4 + (k & 1) * 2 + h] = f[k];
+                for (int k = 0; k < 16; k++) recf[((k >> 1) * NP + p) * 4 + (k & 1) * 2 + h] = f[k];
                 w_base[slot] = base;
                 w_meta[slot] = meta;
-                w_w[slot] = w;
-                w_nd[slot] = nd;
-                if (PER_TET) w_v[slot] = v;
-                if (slot == nfast - 1 && h == 0) { // odd count: the last pair's second half mirrors the first, inactive
+                w_w[slot] = w * UNSCALE;
+                if (mirror) {
 #pragma unroll
-                    for (int k = 0; k < 16; k++) recf[((k >> 1) * 16 + p) * 4 + (k & 1) * 2 + 1] = f[k];
+                    for (int k = 0; k < 16; k++) recf[((k >> 1) * NP + p) * 4 + (k & 1) * 2 + 1] = f[k];
                     w_base[slot + 1] = base;
                     w_meta[slot + 1] = meta & ~(1 << 12);
                     w_w[slot + 1] = 0.0;
                 }
-            }
-            if (act && !fast) { // node ids and volumes share the slot arrays (nfast + nslow <= 32); weight and meta have their own
-                const int ss = 31 - __popc(m_slow & lt);
-                w_smeta[ss] = meta;
-                w_sw[ss] = w * INV_UNSCALE;
-                w_nd[ss] = nd;
-                if (PER_TET) w_v[ss] = v;
+            } else if (act) {
+                const int ss = __popc(m_slow & lt);
+                w_slow[ss] = meta;
+                w_sw[ss] = w;
             }
         }
         // pair control words, lane <-> pair
-        const int npairs = (nfast + 1) >> 1;
+        const int npairs = nslots >> 1;
         __syncwarp();
         {
             int4 c = make_int4(0, 0, 0, 0);
-            int labA = 0, labBe = 0;
+            int lab = 0;
             if (lane < npairs) {
                 const int mA = w_meta[2 * lane], mB = w_meta[2 * lane + 1];
-                const int LA = (mA >> 8) & 15, LB = (mB >> 8) & 15;
+                const int L = (mA >> 8) & 15;
                 const bool actB = (mB >> 12) & 1;
-                const int n3A = (LA + 1) * (LA + 1) * (LA + 1), n3B = actB ? (LB + 1) * (LB + 1) * (LB + 1) : 0;
-                const int rowA = g32_slot_off(LA) * 32, rowB = g32_slot_off(LB) * 32;
-                const int nfull = min(n3A, n3B) >> 5, nall = (max(n3A, n3B) + 31) >> 5;
-                const int eps = ((0x164 >> LA) | (0x164 >> LB)) & 1; // rows of n = 3, 6, 7, 9 do not sum to exactly one
-                labA = mA & 0xff;
-                const int labB = actB ? (mB & 0xff) : 0;
-                labBe = actB ? labB : labA;
+                const int n3 = (L + 1) * (L + 1) * (L + 1);
+                const int nfull = actB ? n3 >> 5 : 0, nall = (n3 + 31) >> 5;
+                const int eps = (0x164 >> L) & 1; // rows of n = 3, 6, 7, 9 do not sum to exactly one
+                lab = mA & 0xff;
                 c.x = (int)w_base[2 * lane];
                 c.y = (int)w_base[2 * lane + 1];
-                c.z = rowA | (rowB << 12) | (labA << 24);
-                c.w = nfull | (nall << 5) | (eps << 10) | ((rowA == rowB ? 1 : 0) << 11) | ((actB ? 1 : 0) << 12) | (LA << 13) | (LB << 17) | (labB << 21);
+                c.z = (g32_slot_off(L) * 32) | (lab << 12) | (((mA >> 13) & 31) << 20) | (((mB >> 13) & 31) << 25);
+                c.w = nfull | (nall << 5) | (eps << 10) | ((actB ? 1 : 0) << 12) | (L << 13);
             }
-            const int prevB = __shfl_up_sync(full, labBe, 1);
+            const int prev = __shfl_up_sync(full, lab, 1);
             if (lane < npairs) {
-                if (lane > 0 && labA == labBe && labA == prevB) c.w |= 1 << 29; // the running label is already this pair's
+                if (lane > 0 && lab == prev) c.w |= 1 << 29; // the running label is already this pair's
                 w_ctl[lane] = c;
             }
         }
         __syncwarp();
         // ---------------- phase B: the warp walks pairs of tets; lane <-> table row, the two halves of a packed register <-> the two tets ----------------
-        for (int p = 0; p < npairs; p++) {
-            const ulonglong2 r0 = w_rec[0 * 16 + p], r1 = w_rec[1 * 16 + p], r2 = w_rec[2 * 16 + p], r3 = w_rec[3 * 16 + p];
-            const ulonglong2 r4 = w_rec[4 * 16 + p], r5 = w_rec[5 * 16 + p], r6 = w_rec[6 * 16 + p], r7 = w_rec[7 * 16 + p];
-            const f32x2 q0x = r0.x, q0y = r0.y, q0z = r1.x, thr2 = r1.y, e1x = r2.x, e1y = r2.y, e1z = r3.x, e2x = r3.y;
-            const f32x2 e2y = r4.x, e2z = r4.y, e3x = r5.x, e3y = r5.y, e3z = r6.x, o_x = r6.y, o_y = r7.x, o_z = r7.y;
-            const int4 ctl = w_ctl[p];
-            const unsigned baseA = (unsigned)ctl.x, baseB = (unsigned)ctl.y;
-            const int rowA = (ctl.z & 0xfff) + lane, rowB = ((ctl.z >> 12) & 0xfff) + lane;
-            const int nfull = ctl.w & 31, nall = (ctl.w >> 5) & 31;
-            const int LA = (ctl.w >> 13) & 15, LB = (ctl.w >> 17) & 15;
-            const bool actB = (ctl.w >> 12) & 1;
-            const int n3A = (LA + 1) * (LA + 1) * (LA + 1), n3B = actB ? (LB + 1) * (LB + 1) * (LB + 1) : 0;
-            float thrA, thrB;
-            upk2(thr2, thrA, thrB);
-
-            // NS consecutive 32-row slots starting at s; TAIL: rows past the end of either tet are masked
-            // SAME: both tets on the same level, one table row serves both halves (broadcast operand, no second LDS)
-            auto body = [&](auto ns_c, auto tail_c, auto eps_c, auto same_c, int s) {
-                constexpr int NS = decltype(ns_c)::value;
-                constexpr bool TAIL = decltype(tail_c)::value;
-                constexpr bool EPS = decltype(eps_c)::value;
-                constexpr bool SAME = decltype(same_c)::value;
-                unsigned idxA[NS], idxB[NS];
-                bool unsafeA[NS], unsafeB[NS];
-                bool any_unsafe = false;
-#pragma unroll
-                for (int u = 0; u < NS; u++) {
-                    const int ra_i = rowA + (s + u) * 32, rb_i = rowB + (s + u) * 32;
-                    const float4 ra = s_lat[ra_i];
-                    float4 rb = ra;
-                    if (!SAME) rb = s_lat[rb_i];
-                    const f32x2 a1 = pk2(ra.x, rb.x), a2 = pk2(ra.y, rb.y), a3 = pk2(ra.z, rb.z);
+        // One flat loop over the steps of all pairs (a step = one or two 32-row slots of one pair), so that the gathers of a
+        // step stay in flight across the loop's back edge while the next step computes its indices.
+        {
+            f32x2 q0x = 0, q0y = 0, q0z = 0, e1x = 0, e1y = 0, e1z = 0, e2x = 0, e2y = 0, e2z = 0, e3x = 0, e3y = 0, e3z = 0, o_x = 0, o_y = 0, o_z = 0;
+            float thrA = 0, thrB = 0;
+            unsigned baseA = 0, baseB = 0;
+            int row0 = 0, nfull = 0, nall = 0, L = 0, n3 = 0, ctl_z = 0, ctl_w = 0;
+            bool actB = false, has_eps = false;
+            int p = 0, s = 0;
+            bool need_record = true;
+            // Every condition that steers this loop is warp-uniform by construction; UNI() (a warp vote, a no-op on equal
+            // values) tells the compiler so.  A branch it must treat as divergent makes it wait for every gather in flight,
+            // which undoes the deferred accumulation (ncu: a long-scoreboard stall on that branch, a third of all stalls).
+#define UNI(c) __any_sync(full, (c))
+            while (UNI(p < npairs)) {
+                if (UNI(need_record)) {
+                    const ulonglong2 r0 = w_rec[0 * NP + p], r1 = w_rec[1 * NP + p], r2 = w_rec[2 * NP + p], r3 = w_rec[3 * NP + p];
+                    const ulonglong2 r4 = w_rec[4 * NP + p], r5 = w_rec[5 * NP + p], r6 = w_rec[6 * NP + p], r7 = w_rec[7 * NP + p];
+                    q0x = r0.x; q0y = r0.y; q0z = r1.x; upk2(r1.y, thrA, thrB); e1x = r2.x; e1y = r2.y; e1z = r3.x; e2x = r3.y;
+                    e2y = r4.x; e2z = r4.y; e3x = r5.x; e3y = r5.y; e3z = r6.x; o_x = r6.y; o_y = r7.x; o_z = r7.y;
+                    const int4 ctl = w_ctl[p];
+                    baseA = (unsigned)ctl.x; baseB = (unsigned)ctl.y;
+                    ctl_z = ctl.z; ctl_w = ctl.w;
+                    row0 = (ctl_z & 0xfff) + lane;
+                    nfull = ctl_w & 31; nall = (ctl_w >> 5) & 31;
+                    L = (ctl_w >> 13) & 15;
+                    actB = (ctl_w >> 12) & 1; has_eps = (ctl_w >> 10) & 1;
+                    n3 = (L + 1) * (L + 1) * (L + 1);
+                    need_record = false;
+                }
+                // one 32-row slot: packed position, floor, guard-band test and brick index of this lane's row for both tets
+                auto compute = [&](int sl, unsigned &iA, unsigned &iB, bool &uA, bool &uB) {
+                    const float4 r = s_lat[row0 + sl * 32];
+                    const f32x2 a1 = pk2(r.x, r.x), a2 = pk2(r.y, r.y), a3 = pk2(r.z, r.z);
                     f32x2 qx = q0x, qy = q0y, qz = q0z;
-                    if (EPS) {
-                        const f32x2 ep = pk2(ra.w, rb.w);
+                    if (UNI(has_eps)) {
+                        const f32x2 ep = pk2(r.w, r.w);
                         qx = fma2(ep, o_x, qx); qy = fma2(ep, o_y, qy); qz = fma2(ep, o_z, qz);
                     }
                     qx = fma2(a1, e1x, qx); qy = fma2(a1, e1y, qy); qz = fma2(a1, e1z, qz);
@@ -469,103 +472,79 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                     float txA, txB, tyA, tyB, tzA, tzB, hxA, hxB, hyA, hyB, hzA, hzB;
                     upk2(tx, txA, txB); upk2(ty, tyA, tyB); upk2(tz, tzA, tzB);
                     upk2(hx, hxA, hxB); upk2(hy, hyA, hyB); upk2(hz, hzA, hzB);
-                    idxA[u] = __float_as_uint(txA) + 28u * __float_as_uint(hxA) + 4u * __float_as_uint(tyA) + Ky * __float_as_uint(hyA) +
-                              8u * __float_as_uint(tzA) + Kz * __float_as_uint(hzA) + baseA;
-                    idxB[u] = __float_as_uint(txB) + 28u * __float_as_uint(hxB) + 4u * __float_as_uint(tyB) + Ky * __float_as_uint(hyB) +
-                              8u * __float_as_uint(tzB) + Kz * __float_as_uint(hzB) + baseB;
-                    unsafeA[u] = fmaxf(fmaxf(fabsf(exA), fabsf(eyA)), fabsf(ezA)) >= thrA;
-                    unsafeB[u] = fmaxf(fmaxf(fabsf(exB), fabsf(eyB)), fabsf(ezB)) >= thrB;
-                    if (TAIL) {
-                        unsafeA[u] = unsafeA[u] && (s + u) * 32 + lane < n3A;
-                        unsafeB[u] = unsafeB[u] && (s + u) * 32 + lane < n3B;
-                    }
-                    any_unsafe = any_unsafe || unsafeA[u] || unsafeB[u];
+                    iA = __float_as_uint(txA) + 28u * __float_as_uint(hxA) + 4u * __float_as_uint(tyA) + Ky * __float_as_uint(hyA) +
+                         8u * __float_as_uint(tzA) + Kz * __float_as_uint(hzA) + baseA;
+                    iB = __float_as_uint(txB) + 28u * __float_as_uint(hxB) + 4u * __float_as_uint(tyB) + Ky * __float_as_uint(hyB) +
+                         8u * __float_as_uint(tzB) + Kz * __float_as_uint(hzB) + baseB;
+                    uA = fmaxf(fmaxf(fabsf(exA), fabsf(eyA)), fabsf(ezA)) >= thrA;
+                    uB = fmaxf(fmaxf(fabsf(exB), fabsf(eyB)), fabsf(ezB)) >= thrB;
+                };
+                unsigned i0A = 0u, i0B = 0u, i1A = 0u, i1B = 0u; // element 0 is padding: reads 0
+                bool u0A = false, u0B = false, u1A = false, u1B = false;
+                const bool two = UNI(s + 2 <= nfull);
+                if (two) { // two full slots: no masks
+                    compute(s, i0A, i0B, u0A, u0B);
+                    compute(s + 1, i1A, i1B, u1A, u1B);
+                } else { // one slot; rows past the end of the level (and the whole second half of an odd pair) are masked
+                    compute(s, i0A, i0B, u0A, u0B);
+                    const bool in = s * 32 + lane < n3;
+                    if (!in) { i0A = 0u; u0A = false; }
+                    if (!in || !actB) { i0B = 0u; u0B = false; }
                 }
-                if (any_unsafe) { // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        bool need = false;
-#pragma unroll
-                        for (int u = 0; u < NS; u++) need = need || (h ? unsafeB[u] : unsafeA[u]);
-                        if (need) {
-                            const uint4 nd = w_nd[2 * p + h];
-                            const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                            const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-#pragma unroll
-                            for (int u = 0; u < NS; u++)
-                                if (h ? unsafeB[u] : unsafeA[u]) {
-                                    const unsigned e = g32_exact_index(a, p0, p1, p2, p3, h ? LB : LA, (s + u) * 32 + lane);
-                                    if (h) idxB[u] = e; else idxA[u] = e;
-                                }
-                        }
-                    }
-                }
-                if (TAIL) {
-#pragma unroll
-                    for (int u = 0; u < NS; u++) {
-                        if ((s + u) * 32 + lane >= n3A) idxA[u] = 0u; // element 0 is padding: reads 0
-                        if ((s + u) * 32 + lane >= n3B) idxB[u] = 0u;
-                    }
+                if (__any_sync(full, u0A || u0B || u1A || u1B)) { // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
+                    auto fix = [&](int tl, bool u0, bool u1, unsigned &i0, unsigned &i1) {
+                        if (!(u0 || u1)) return;
+                        const uint4 nd = w_nd[tl];
+                        const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+                        const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+                        if (u0) i0 = g32_exact_index(a, p0, p1, p2, p3, L, s * 32 + lane);
+                        if (u1) i1 = g32_exact_index(a, p0, p1, p2, p3, L, (s + 1) * 32 + lane);
+                    };
+                    fix((ctl_z >> 20) & 31, u0A, u1A, i0A, i1A);
+                    fix((ctl_z >> 25) & 31, u0B, u1B, i0B, i1B);
                 }
                 drain(); // the previous step's voxels (and, if that step ended a pair, the pair itself)
+                pend[0] = __ldg(vol + i0A); pend[1] = __ldg(vol + i0B); pend[2] = __ldg(vol + i1A); pend[3] = __ldg(vol + i1B);
+                s += two ? 2 : 1;
+                if (UNI(s >= nall)) { // last step of the pair: it is closed by the next drain(), once these gathers have landed
+                    if (PER_TET) { // per-tet outputs: the exact sum of the tet's voxels, then the reference's own expression
+                        add_pending();
 #pragma unroll
-                for (int u = 0; u < NS; u++) { pendA[u] = __ldg(vol + idxA[u]); pendB[u] = __ldg(vol + idxB[u]); }
-                pend_n = NS;
-            };
-            using I1 = std::integral_constant<int, 1>;
-            using I2 = std::integral_constant<int, 2>;
-            auto run = [&](auto eps_c, auto same_c) {
-                int s = 0;
-                for (; s + 2 <= nfull; s += 2) body(I2{}, std::false_type{}, eps_c, same_c, s);
-                for (; s < nfull; s++) body(I1{}, std::false_type{}, eps_c, same_c, s);
-                for (; s < nall; s++) body(I1{}, std::true_type{}, eps_c, same_c, s);
-            };
-            if (ctl.w & (1 << 11)) {
-                if (ctl.w & (1 << 10)) run(std::true_type{}, std::true_type{});
-                else run(std::false_type{}, std::true_type{});
-            } else {
-                if (ctl.w & (1 << 10)) run(std::true_type{}, std::false_type{});
-                else run(std::false_type{}, std::false_type{});
-            }
-            // the pair is closed by the next drain(), once its last gathers have landed
-            {
-                const double2 ww = reinterpret_cast<const double2 *>(w_w)[p];
-                cl_wA = ww.x; cl_wB = ww.y;
-                cl_labA = (ctl.z >> 24) & 0xff; cl_labB = (ctl.w >> 21) & 0xff;
-                cl_fast = (ctl.w >> 29) & 1;
-                close_pending = true;
-            }
-            if (PER_TET) { // per-tet outputs: the exact sum of the tet's voxels, then the reference's own expression
-                if (pend_n) {
-                    add_voxel(pendA[0], sA, sqA, isA, iqA); add_voxel(pendB[0], sB, sqB, isB, iqB);
-                    if (pend_n == 2) { add_voxel(pendA[1], sA, sqA, isA, iqA); add_voxel(pendB[1], sB, sqB, isB, iqB); }
-                    pend_n = 0;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    if (h == 1 && !actB) break;
-                    double st;
-                    if constexpr (VoxTraits<VoxT>::integral) st = warp_sum_d((double)(h ? isB : isA)) / dn;
-                    else st = warp_sum_d(h ? sB : sA) * UNSCALE;
-                    if (lane == 0) {
-                        const unsigned t = base_t + ((w_meta[2 * p + h] >> 13) & 31);
-                        const double vv = w_v[2 * p + h];
-                        const double tot = st * vv / (double)(h ? n3B : n3A); // total = total * v / a.size()  (image3d.cpp:371)
-                        if (a.tet_total) a.tet_total[t] = tot;
-                        if (a.tet_vol) a.tet_vol[t] = vv;
-                        if (a.tet_mean) a.tet_mean[t] = tot / vv;
+                        for (int h = 0; h < 2; h++) {
+                            if (h == 1 && !actB) break;
+                            double st;
+                            if constexpr (VoxTraits<VoxT>::integral) st = warp_sum_d((double)(h ? isB : isA)) / dn;
+                            else st = warp_sum_d(h ? sB : sA) * UNSCALE;
+                            if (lane == 0) {
+                                const int tl = (ctl_z >> (20 + 5 * h)) & 31;
+                                const unsigned t = base_t + tl;
+                                const double vv = w_v[tl];
+                                const double tot = st * vv / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
+                                if (a.tet_total) a.tet_total[t] = tot;
+                                if (a.tet_vol) a.tet_vol[t] = vv;
+                                if (a.tet_mean) a.tet_mean[t] = tot / vv;
+                            }
+                        }
                     }
+                    const double2 ww = reinterpret_cast<const double2 *>(w_w)[p];
+                    cl_wA = ww.x; cl_wB = ww.y;
+                    cl_lab = (ctl_z >> 12) & 0xff;
+                    cl_fast = (ctl_w >> 29) & 1;
+                    close_pending = true;
+                    p++;
+                    s = 0;
+                    need_record = true;
                 }
-                drain();
             }
+#undef UNI
         }
         // ---------------- slow tets: outside the padded copy or wider than 100 voxels; exact arithmetic, the whole warp on one tet ----------------
         if (nslow) drain();
         for (int k = 0; k < nslow; k++) {
-            const int ss = 31 - k;
-            const int meta = w_smeta[ss];
+            const int meta = w_slow[k];
             const int L = (meta >> 8) & 15, n3 = (L + 1) * (L + 1) * (L + 1);
-            const uint4 nd = w_nd[ss];
+            const int tl = (meta >> 13) & 31;
+            const uint4 nd = w_nd[tl];
             const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
             const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
             double s = 0, sq = 0;
@@ -592,15 +571,15 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                 double st = warp_sum_d(s);
                 if (VoxTraits<VoxT>::integral) st = st / dn;
                 if (lane == 0) {
-                    const unsigned t = base_t + ((meta >> 13) & 31);
-                    const double vv = w_v[ss];
+                    const unsigned t = base_t + tl;
+                    const double vv = w_v[tl];
                     const double tot = st * vv / (double)n3;
                     if (a.tet_total) a.tet_total[t] = tot;
                     if (a.tet_vol) a.tet_vol[t] = vv;
                     if (a.tet_mean) a.tet_mean[t] = tot / vv;
                 }
             }
-            const double w = w_sw[ss]; // true doubles here
+            const double w = w_sw[k]; // true doubles here
             contribute(meta & 0xff, s * w, WANT_SQ ? sq * w : 0.0);
         }
     }

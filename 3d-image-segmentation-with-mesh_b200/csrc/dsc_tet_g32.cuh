@@ -212,19 +212,10 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
         if (WANT_SQ) cur_sq += xs;
     };
 
-    // ---- the pair in flight ----
-    // Accumulation is deferred: the voxels gathered by one step are added after the NEXT step has computed its indices and
-    // just before it issues its own gathers, so the index arithmetic of a step overlaps the memory latency of the previous
-    // one; a pair is closed (sum times weight added to the running label sum) by the drain that follows its last step.
-    double sA = 0, sB = 0, sqA = 0, sqB = 0;   // sums of the open pair (float / double voxels)
-    unsigned isA = 0, isB = 0;                 // ... integer voxels
+    // sums of the open pair (this lane's rows): float / double voxels, integer voxels
+    double sA = 0, sB = 0, sqA = 0, sqB = 0;
+    unsigned isA = 0, isB = 0;
     unsigned long long iqA = 0, iqB = 0;
-    VoxT pend[4];                              // A0, B0, A1, B1 of the last step (element 0 of the copy, a zero, when unused)
-    pend[0] = pend[1] = pend[2] = pend[3] = (VoxT)0;
-    bool close_pending = false;
-    double cl_wA = 0, cl_wB = 0;               // of the pair waiting to be closed
-    int cl_lab = 0;
-    bool cl_fast = false;
 
     auto add_voxel = [&](VoxT val, double &s, double &sq, unsigned &is, unsigned long long &iq) {
         if constexpr (VoxTraits<VoxT>::integral) {
@@ -248,29 +239,6 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
                 const double Iu = I * UNSCALE; // exact
                 sq = fma(Iu, Iu, sq); // second moment: tolerance quantity, fused on purpose
             }
-        }
-    };
-    auto add_pending = [&]() {
-        add_voxel(pend[0], sA, sqA, isA, iqA);
-        add_voxel(pend[1], sB, sqB, isB, iqB);
-        add_voxel(pend[2], sA, sqA, isA, iqA);
-        add_voxel(pend[3], sB, sqB, isB, iqB);
-        pend[0] = pend[1] = pend[2] = pend[3] = (VoxT)0;
-    };
-    auto drain = [&]() {
-        add_pending();
-        if (__any_sync(full, close_pending)) {
-            if constexpr (VoxTraits<VoxT>::integral) {
-                sA = (double)isA; sB = (double)isB;
-                if (WANT_SQ) { sqA = (double)iqA / dn; sqB = (double)iqB / dn; } // the weight carries the other 1/dn
-            }
-            if (__any_sync(full, !cl_fast && cl_lab != cur_label)) { flush(); cur_label = cl_lab; }
-            cur_acc += sA * cl_wA + sB * cl_wB;
-            if (WANT_SQ) cur_sq += sqA * (cl_wA * INV_UNSCALE) + sqB * (cl_wB * INV_UNSCALE); // the weight carries 2^896
-            sA = sB = sqA = sqB = 0;
-            isA = isB = 0;
-            iqA = iqB = 0;
-            close_pending = false;
         }
     };
 
@@ -422,124 +390,169 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
         }
         __syncwarp();
         // ---------------- phase B: the warp walks pairs of tets; lane <-> table row, the two halves of a packed register <-> the two tets ----------------
-        // One flat loop over the steps of all pairs (a step = one or two 32-row slots of one pair), so that the gathers of a
-        // step stay in flight across the loop's back edge while the next step computes its indices.
-        {
+        // A step is one or two 32-row slots of one pair.  Software pipeline, one step deep: an iteration issues the gathers of
+        // the CURRENT step (its indices were computed by the previous iteration), computes the indices of the NEXT step and
+        // only then adds the gathered voxels -- all in one straight-line block, because the compiler drains every load in
+        // flight at the first branch it meets (ncu: a third of all stalls sat on such a branch).  Everything branchy (loading
+        // the next pair's record, the exact re-evaluation inside the guard band, closing a pair) happens between blocks.
+        if (npairs > 0) {
+#define UNI(c) __any_sync(full, (c))
             f32x2 q0x = 0, q0y = 0, q0z = 0, e1x = 0, e1y = 0, e1z = 0, e2x = 0, e2y = 0, e2z = 0, e3x = 0, e3y = 0, e3z = 0, o_x = 0, o_y = 0, o_z = 0;
             float thrA = 0, thrB = 0;
             unsigned baseA = 0, baseB = 0;
             int row0 = 0, nfull = 0, nall = 0, L = 0, n3 = 0, ctl_z = 0, ctl_w = 0;
-            bool actB = false, has_eps = false;
-            int p = 0, s = 0;
-            bool need_record = true;
-            // Every condition that steers this loop is warp-uniform by construction; UNI() (a warp vote, a no-op on equal
-            // values) tells the compiler so.  A branch it must treat as divergent makes it wait for every gather in flight,
-            // which undoes the deferred accumulation (ncu: a long-scoreboard stall on that branch, a third of all stalls).
-#define UNI(c) __any_sync(full, (c))
-            while (UNI(p < npairs)) {
-                if (UNI(need_record)) {
-                    const ulonglong2 r0 = w_rec[0 * NP + p], r1 = w_rec[1 * NP + p], r2 = w_rec[2 * NP + p], r3 = w_rec[3 * NP + p];
-                    const ulonglong2 r4 = w_rec[4 * NP + p], r5 = w_rec[5 * NP + p], r6 = w_rec[6 * NP + p], r7 = w_rec[7 * NP + p];
-                    q0x = r0.x; q0y = r0.y; q0z = r1.x; upk2(r1.y, thrA, thrB); e1x = r2.x; e1y = r2.y; e1z = r3.x; e2x = r3.y;
-                    e2y = r4.x; e2z = r4.y; e3x = r5.x; e3y = r5.y; e3z = r6.x; o_x = r6.y; o_y = r7.x; o_z = r7.y;
-                    const int4 ctl = w_ctl[p];
-                    baseA = (unsigned)ctl.x; baseB = (unsigned)ctl.y;
-                    ctl_z = ctl.z; ctl_w = ctl.w;
-                    row0 = (ctl_z & 0xfff) + lane;
-                    nfull = ctl_w & 31; nall = (ctl_w >> 5) & 31;
-                    L = (ctl_w >> 13) & 15;
-                    actB = (ctl_w >> 12) & 1; has_eps = (ctl_w >> 10) & 1;
-                    n3 = (L + 1) * (L + 1) * (L + 1);
-                    need_record = false;
+            bool actB = false;
+            auto load_record = [&](int p) {
+                const ulonglong2 r0 = w_rec[0 * NP + p], r1 = w_rec[1 * NP + p], r2 = w_rec[2 * NP + p], r3 = w_rec[3 * NP + p];
+                const ulonglong2 r4 = w_rec[4 * NP + p], r5 = w_rec[5 * NP + p], r6 = w_rec[6 * NP + p], r7 = w_rec[7 * NP + p];
+                q0x = r0.x; q0y = r0.y; q0z = r1.x; upk2(r1.y, thrA, thrB); e1x = r2.x; e1y = r2.y; e1z = r3.x; e2x = r3.y;
+                e2y = r4.x; e2z = r4.y; e3x = r5.x; e3y = r5.y; e3z = r6.x; o_x = r6.y; o_y = r7.x; o_z = r7.y;
+                const int4 ctl = w_ctl[p];
+                baseA = (unsigned)ctl.x; baseB = (unsigned)ctl.y;
+                ctl_z = ctl.z; ctl_w = ctl.w;
+                row0 = (ctl.z & 0xfff) + lane;
+                nfull = ctl.w & 31; nall = (ctl.w >> 5) & 31;
+                L = (ctl.w >> 13) & 15;
+                actB = (ctl.w >> 12) & 1;
+                n3 = (L + 1) * (L + 1) * (L + 1);
+            };
+            // one 32-row slot: packed position, floor, guard-band test and brick index of this lane's row for both tets
+            auto compute = [&](auto eps_c, int sl, unsigned &iA, unsigned &iB, bool &uA, bool &uB) {
+                const float4 r = s_lat[row0 + sl * 32];
+                const f32x2 a1 = pk2(r.x, r.x), a2 = pk2(r.y, r.y), a3 = pk2(r.z, r.z);
+                f32x2 qx = q0x, qy = q0y, qz = q0z;
+                if (decltype(eps_c)::value) {
+                    const f32x2 ep = pk2(r.w, r.w);
+                    qx = fma2(ep, o_x, qx); qy = fma2(ep, o_y, qy); qz = fma2(ep, o_z, qz);
                 }
-                // one 32-row slot: packed position, floor, guard-band test and brick index of this lane's row for both tets
-                auto compute = [&](int sl, unsigned &iA, unsigned &iB, bool &uA, bool &uB) {
-                    const float4 r = s_lat[row0 + sl * 32];
-                    const f32x2 a1 = pk2(r.x, r.x), a2 = pk2(r.y, r.y), a3 = pk2(r.z, r.z);
-                    f32x2 qx = q0x, qy = q0y, qz = q0z;
-                    if (UNI(has_eps)) {
-                        const f32x2 ep = pk2(r.w, r.w);
-                        qx = fma2(ep, o_x, qx); qy = fma2(ep, o_y, qy); qz = fma2(ep, o_z, qz);
-                    }
-                    qx = fma2(a1, e1x, qx); qy = fma2(a1, e1y, qy); qz = fma2(a1, e1z, qz);
-                    qx = fma2(a2, e2x, qx); qy = fma2(a2, e2y, qy); qz = fma2(a2, e2z, qz);
-                    qx = fma2(a3, e3x, qx); qy = fma2(a3, e3y, qy); qz = fma2(a3, e3z, qz);
-                    const f32x2 tx = add2(qx, M2), ty = add2(qy, M2), tz = add2(qz, M2);
-                    const f32x2 ex = fma2(add2(tx, NM2), NEG1, qx), ey = fma2(add2(ty, NM2), NEG1, qy), ez = fma2(add2(tz, NM2), NEG1, qz);
-                    const f32x2 hx = fma2(tx, K4, C4), hy = fma2(ty, K2, M2), hz = fma2(tz, K4, C4);
-                    float exA, exB, eyA, eyB, ezA, ezB;
-                    upk2(ex, exA, exB); upk2(ey, eyA, eyB); upk2(ez, ezA, ezB);
-                    float txA, txB, tyA, tyB, tzA, tzB, hxA, hxB, hyA, hyB, hzA, hzB;
-                    upk2(tx, txA, txB); upk2(ty, tyA, tyB); upk2(tz, tzA, tzB);
-                    upk2(hx, hxA, hxB); upk2(hy, hyA, hyB); upk2(hz, hzA, hzB);
-                    iA = __float_as_uint(txA) + 28u * __float_as_uint(hxA) + 4u * __float_as_uint(tyA) + Ky * __float_as_uint(hyA) +
-                         8u * __float_as_uint(tzA) + Kz * __float_as_uint(hzA) + baseA;
-                    iB = __float_as_uint(txB) + 28u * __float_as_uint(hxB) + 4u * __float_as_uint(tyB) + Ky * __float_as_uint(hyB) +
-                         8u * __float_as_uint(tzB) + Kz * __float_as_uint(hzB) + baseB;
-                    uA = fmaxf(fmaxf(fabsf(exA), fabsf(eyA)), fabsf(ezA)) >= thrA;
-                    uB = fmaxf(fmaxf(fabsf(exB), fabsf(eyB)), fabsf(ezB)) >= thrB;
-                };
-                unsigned i0A = 0u, i0B = 0u, i1A = 0u, i1B = 0u; // element 0 is padding: reads 0
-                bool u0A = false, u0B = false, u1A = false, u1B = false;
-                const bool two = UNI(s + 2 <= nfull);
-                if (two) { // two full slots: no masks
-                    compute(s, i0A, i0B, u0A, u0B);
-                    compute(s + 1, i1A, i1B, u1A, u1B);
+                qx = fma2(a1, e1x, qx); qy = fma2(a1, e1y, qy); qz = fma2(a1, e1z, qz);
+                qx = fma2(a2, e2x, qx); qy = fma2(a2, e2y, qy); qz = fma2(a2, e2z, qz);
+                qx = fma2(a3, e3x, qx); qy = fma2(a3, e3y, qy); qz = fma2(a3, e3z, qz);
+                const f32x2 tx = add2(qx, M2), ty = add2(qy, M2), tz = add2(qz, M2);
+                const f32x2 ex = fma2(add2(tx, NM2), NEG1, qx), ey = fma2(add2(ty, NM2), NEG1, qy), ez = fma2(add2(tz, NM2), NEG1, qz);
+                const f32x2 hx = fma2(tx, K4, C4), hy = fma2(ty, K2, M2), hz = fma2(tz, K4, C4);
+                float exA, exB, eyA, eyB, ezA, ezB;
+                upk2(ex, exA, exB); upk2(ey, eyA, eyB); upk2(ez, ezA, ezB);
+                float txA, txB, tyA, tyB, tzA, tzB, hxA, hxB, hyA, hyB, hzA, hzB;
+                upk2(tx, txA, txB); upk2(ty, tyA, tyB); upk2(tz, tzA, tzB);
+                upk2(hx, hxA, hxB); upk2(hy, hyA, hyB); upk2(hz, hzA, hzB);
+                iA = __float_as_uint(txA) + 28u * __float_as_uint(hxA) + 4u * __float_as_uint(tyA) + Ky * __float_as_uint(hyA) +
+                     8u * __float_as_uint(tzA) + Kz * __float_as_uint(hzA) + baseA;
+                iB = __float_as_uint(txB) + 28u * __float_as_uint(hxB) + 4u * __float_as_uint(tyB) + Ky * __float_as_uint(hyB) +
+                     8u * __float_as_uint(tzB) + Kz * __float_as_uint(hzB) + baseB;
+                uA = fmaxf(fmaxf(fabsf(exA), fabsf(eyA)), fabsf(ezA)) >= thrA;
+                uB = fmaxf(fmaxf(fabsf(exB), fabsf(eyB)), fabsf(ezB)) >= thrB;
+            };
+            // indices of the step (record in registers, slot s): A0, B0, A1, B1; element 0 of the copy is padding and reads 0
+            unsigned n_i[4];
+            bool n_u[4];
+            auto compute_step = [&](auto two_c, auto eps_c, int s) {
+                n_i[2] = n_i[3] = 0u;
+                n_u[2] = n_u[3] = false;
+                compute(eps_c, s, n_i[0], n_i[1], n_u[0], n_u[1]);
+                if (decltype(two_c)::value) { // two full slots: no masks
+                    compute(eps_c, s + 1, n_i[2], n_i[3], n_u[2], n_u[3]);
                 } else { // one slot; rows past the end of the level (and the whole second half of an odd pair) are masked
-                    compute(s, i0A, i0B, u0A, u0B);
                     const bool in = s * 32 + lane < n3;
-                    if (!in) { i0A = 0u; u0A = false; }
-                    if (!in || !actB) { i0B = 0u; u0B = false; }
+                    if (!in) { n_i[0] = 0u; n_u[0] = false; }
+                    if (!in || !actB) { n_i[1] = 0u; n_u[1] = false; }
                 }
-                if (__any_sync(full, u0A || u0B || u1A || u1B)) { // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
+            };
+            // the current step
+            unsigned c_i[4] = {0u, 0u, 0u, 0u};
+            bool c_u[4] = {false, false, false, false};
+            int c_L = 0, c_s = 0, c_z = 0, c_w = 0, c_p = 0;
+            bool c_last = false;
+            // the next step: pair p, slot s, record of pair p in registers
+            int p = 0, s = 0;
+            load_record(0);
+            bool have_next = true;
+            {   // prologue: the first step's indices
+                const bool two = UNI(2 <= nfull), eps = UNI((ctl_w >> 10) & 1);
+                if (two) { if (eps) compute_step(std::true_type{}, std::true_type{}, 0); else compute_step(std::true_type{}, std::false_type{}, 0); }
+                else { if (eps) compute_step(std::false_type{}, std::true_type{}, 0); else compute_step(std::false_type{}, std::false_type{}, 0); }
+            }
+            while (true) {
+                // ---- next becomes current; find the step after it and, if it opens a new pair, load that pair's record ----
+#pragma unroll
+                for (int k = 0; k < 4; k++) { c_i[k] = n_i[k]; c_u[k] = n_u[k]; }
+                c_L = L; c_s = s; c_z = ctl_z; c_w = ctl_w; c_p = p;
+                s += UNI(s + 2 <= nfull) ? 2 : 1;
+                c_last = s >= nall;
+                if (UNI(c_last)) {
+                    p++;
+                    s = 0;
+                    have_next = p < npairs;
+                    if (UNI(have_next)) load_record(p);
+                }
+                if (UNI(c_u[0] || c_u[1] || c_u[2] || c_u[3])) { // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
                     auto fix = [&](int tl, bool u0, bool u1, unsigned &i0, unsigned &i1) {
                         if (!(u0 || u1)) return;
                         const uint4 nd = w_nd[tl];
                         const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
                         const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-                        if (u0) i0 = g32_exact_index(a, p0, p1, p2, p3, L, s * 32 + lane);
-                        if (u1) i1 = g32_exact_index(a, p0, p1, p2, p3, L, (s + 1) * 32 + lane);
+                        if (u0) i0 = g32_exact_index(a, p0, p1, p2, p3, c_L, c_s * 32 + lane);
+                        if (u1) i1 = g32_exact_index(a, p0, p1, p2, p3, c_L, (c_s + 1) * 32 + lane);
                     };
-                    fix((ctl_z >> 20) & 31, u0A, u1A, i0A, i1A);
-                    fix((ctl_z >> 25) & 31, u0B, u1B, i0B, i1B);
+                    fix((c_z >> 20) & 31, c_u[0], c_u[2], c_i[0], c_i[2]);
+                    fix((c_z >> 25) & 31, c_u[1], c_u[3], c_i[1], c_i[3]);
                 }
-                drain(); // the previous step's voxels (and, if that step ended a pair, the pair itself)
-                pend[0] = __ldg(vol + i0A); pend[1] = __ldg(vol + i0B); pend[2] = __ldg(vol + i1A); pend[3] = __ldg(vol + i1B);
-                s += two ? 2 : 1;
-                if (UNI(s >= nall)) { // last step of the pair: it is closed by the next drain(), once these gathers have landed
+                // ---- straight-line block: gathers of the current step, indices of the next one, then the accumulation ----
+                const bool two = UNI(s + 2 <= nfull), eps = UNI((ctl_w >> 10) & 1);
+                auto block = [&](auto next_c, auto two_c, auto eps_c) {
+                    const VoxT v0 = __ldg(vol + c_i[0]), v1 = __ldg(vol + c_i[1]), v2 = __ldg(vol + c_i[2]), v3 = __ldg(vol + c_i[3]);
+                    if (decltype(next_c)::value) compute_step(two_c, eps_c, s);
+                    add_voxel(v0, sA, sqA, isA, iqA);
+                    add_voxel(v1, sB, sqB, isB, iqB);
+                    add_voxel(v2, sA, sqA, isA, iqA);
+                    add_voxel(v3, sB, sqB, isB, iqB);
+                };
+                if (UNI(have_next)) {
+                    if (two) { if (eps) block(std::true_type{}, std::true_type{}, std::true_type{}); else block(std::true_type{}, std::true_type{}, std::false_type{}); }
+                    else { if (eps) block(std::true_type{}, std::false_type{}, std::true_type{}); else block(std::true_type{}, std::false_type{}, std::false_type{}); }
+                } else {
+                    block(std::false_type{}, std::false_type{}, std::false_type{});
+                }
+                // ---- the current step was the last of its pair: close the pair ----
+                if (UNI(c_last)) {
+                    const int cn3 = (c_L + 1) * (c_L + 1) * (c_L + 1);
+                    const bool c_actB = (c_w >> 12) & 1, c_fastlab = (c_w >> 29) & 1;
                     if (PER_TET) { // per-tet outputs: the exact sum of the tet's voxels, then the reference's own expression
-                        add_pending();
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
-                            if (h == 1 && !actB) break;
+                            if (h == 1 && !UNI(c_actB)) break;
                             double st;
                             if constexpr (VoxTraits<VoxT>::integral) st = warp_sum_d((double)(h ? isB : isA)) / dn;
                             else st = warp_sum_d(h ? sB : sA) * UNSCALE;
                             if (lane == 0) {
-                                const int tl = (ctl_z >> (20 + 5 * h)) & 31;
+                                const int tl = (c_z >> (20 + 5 * h)) & 31;
                                 const unsigned t = base_t + tl;
                                 const double vv = w_v[tl];
-                                const double tot = st * vv / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
+                                const double tot = st * vv / (double)cn3; // total = total * v / a.size()  (image3d.cpp:371)
                                 if (a.tet_total) a.tet_total[t] = tot;
                                 if (a.tet_vol) a.tet_vol[t] = vv;
                                 if (a.tet_mean) a.tet_mean[t] = tot / vv;
                             }
                         }
                     }
-                    const double2 ww = reinterpret_cast<const double2 *>(w_w)[p];
-                    cl_wA = ww.x; cl_wB = ww.y;
-                    cl_lab = (ctl_z >> 12) & 0xff;
-                    cl_fast = (ctl_w >> 29) & 1;
-                    close_pending = true;
-                    p++;
-                    s = 0;
-                    need_record = true;
+                    const double2 ww = reinterpret_cast<const double2 *>(w_w)[c_p];
+                    const int lab = (c_z >> 12) & 0xff;
+                    if constexpr (VoxTraits<VoxT>::integral) {
+                        sA = (double)isA; sB = (double)isB;
+                        if (WANT_SQ) { sqA = (double)iqA / dn; sqB = (double)iqB / dn; } // the weight carries the other 1/dn
+                    }
+                    if (UNI(!c_fastlab && lab != cur_label)) { flush(); cur_label = lab; }
+                    cur_acc += sA * ww.x + sB * ww.y;
+                    if (WANT_SQ) cur_sq += sqA * (ww.x * INV_UNSCALE) + sqB * (ww.y * INV_UNSCALE); // the weight carries 2^896
+                    sA = sB = sqA = sqB = 0;
+                    isA = isB = 0;
+                    iqA = iqB = 0;
                 }
+                if (!UNI(have_next)) break;
             }
 #undef UNI
         }
         // ---------------- slow tets: outside the padded copy or wider than 100 voxels; exact arithmetic, the whole warp on one tet ----------------
-        if (nslow) drain();
         for (int k = 0; k < nslow; k++) {
             const int meta = w_slow[k];
             const int L = (meta >> 8) & 15, n3 = (L + 1) * (L + 1) * (L + 1);
@@ -583,7 +596,6 @@ __global__ void __launch_bounds__(256, G32_MIN_BLOCKS) tet_sums_g32_kernel(const
             contribute(meta & 0xff, s * w, WANT_SQ ? sq * w : 0.0);
         }
     }
-    drain();
     flush();
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(full, nsamp, m);

@@ -104,6 +104,19 @@ template <typename T> DSC_D T tex_fetch(cudaTextureObject_t tex, int x, int y, i
     return tex3D<T>(tex, (float)x + 0.5f, (float)y + 0.5f, (float)z + 0.5f);
 }
 
+// ---- bricked, padded copy of the volume (built by brick_volume_kernel, dsc_tet_g32.cuh) ----
+// 4x2x4-voxel bricks (32 voxels; 128 B for float), padded by kBrickPad voxels on every side.  The padding holds what
+// image3d::get_value returns outside the volume (0, DEMO/image3d.cpp:480-491) and, in the layer at -1, a replica of layer 0:
+// the reference truncates toward zero (image3d.cpp:366), so a coordinate in (-1,0) reads voxel 0.  Element 0 is padding (0).
+constexpr int kBrickPad = 8; // a multiple of every brick extent
+
+// element index of voxel (x, y, z) (volume coordinates, -kBrickPad <= x < X + pad ...) in the bricked, padded copy
+DSC_HD unsigned brick_index(int x, int y, int z, unsigned Sy, unsigned Sz)
+{
+    const unsigned xp = (unsigned)(x + kBrickPad), yp = (unsigned)(y + kBrickPad), zp = (unsigned)(z + kBrickPad);
+    return (zp >> 2) * Sz + (yp >> 1) * Sy + ((xp >> 2) << 5) + ((zp & 3u) << 3) + ((yp & 1u) << 2) + (xp & 3u);
+}
+
 DSC_D V3 load_pos(const double4 *__restrict__ pos4, unsigned n)
 {
     const double2 *p = reinterpret_cast<const double2 *>(pos4 + n);
@@ -162,6 +175,8 @@ struct TetArgs {
     cudaTextureObject_t tex;         // 3-D texture over the volume (0 when unavailable)
     double *partials;                // [gridDim.x][3*kMaxPhase]: total, sumsq, volume
     unsigned long long *sample_count; // algorithmic samples processed (for the roofline figure)
+    const void *brick;               // bricked, padded copy of the volume (w2 BRICK form), strides in elements
+    unsigned brick_sy, brick_sz;
 };
 
 template <typename VoxT, int G, bool WITH_C>
@@ -536,7 +551,12 @@ __global__ void __launch_bounds__(256) tet_integrate_g_kernel(const TetArgs a)
 // floor() uses the 1.5*2^23 trick (no F2I), the voxel is widened with integer ops (no F2F): the XU pipe stays idle.
 // Tets touching the volume border, very large tets (n > kSmemLevels) and tets wider than 100 voxels use the exact path.
 // -------------------------------------------------------------------------------------------------
-template <typename VoxT, bool WANT_SQ, bool PER_TET>
+// BRICK (variant bit 2048): the same kernel gathering from the bricked, padded copy of the volume.  Origins are rounded down
+// to brick corners, so idx = base + rx + 28 hx + 4 ry + (Sy-8) hy + 8 rz + (Sz-32) hz with hx = floor(rx/4), hy = floor(ry/2),
+// hz = floor(rz/4), each from one more FFMA on the rounded value (dsc_tet_g32.cuh explains the trick).  A gather then touches
+// 9.4 distinct 128 B lines instead of 16.8 (scripts/line_sim.py), and every tet inside the padded region -- including the
+// layer of tets along the volume border -- takes the filtered path.
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false>
 __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(const TetArgs a)
 {
     constexpr int G = 8, U = 4;
@@ -550,7 +570,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
     for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_lat[i] = a.tet_lat[i];
     __syncthreads();
 
-    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(BRICK ? a.brick : a.vol.data);
     const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
     const int XYi = X * Y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -559,7 +579,15 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
     const unsigned n_tiles = (n_work + 31) / 32;
     const unsigned total_warps = gridDim.x * 8;
     const float MAGIC = 12582912.0f; // 1.5 * 2^23
-    const unsigned fold = 0x4B400000u * (unsigned)(XYi + X + 1);
+    const unsigned bSy = a.brick_sy, bSz = a.brick_sz, bKy = bSy - 8u, bKz = bSz - 32u;
+    // bits of 1.5*2^23, 1.5*2^24, 1.5*2^25 times the coefficients they enter the index with
+    const unsigned fold = BRICK ? 0x4B400000u * 13u + 0x4C400000u * (28u + bKz) + 0x4BC00000u * bKy : 0x4B400000u * (unsigned)(XYi + X + 1);
+    // exact sample voxel as an element index of the volume this kernel reads; -1: outside (linear form only)
+    auto exact_index = [&](int ix, int iy, int iz) -> int {
+        const bool inb = (unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z;
+        if (BRICK) return inb ? (int)brick_index(ix, iy, iz, bSy, bSz) : 0; // element 0 is padding: reads 0
+        return inb ? iz * XYi + iy * X + ix : -1;
+    };
 
     double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane_g + 1
     unsigned long long nsamp = 0;
@@ -595,8 +623,15 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
                     const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
                     // strictly inside the volume with a margin: no sample can leave [1, dim-1), so no bounds checks, no negatives
-                    const bool interior = lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5;
-                    const double ox = floor(lox), oy = floor(loy), oz = floor(loz);
+                    // (BRICK: inside the padded copy with a margin of two voxels; the padding stands in for the bounds test)
+                    const bool interior = BRICK ? (lox >= -6.0 && loy >= -6.0 && loz >= -6.0 && hix < (double)X + 6.0 && hiy < (double)Y + 6.0 && hiz < (double)Z + 6.0)
+                                                : (lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5);
+                    double ox = floor(lox), oy = floor(loy), oz = floor(loz);
+                    if (BRICK && interior) { // round the origin down to a brick corner (the padding is a multiple of the brick)
+                        ox = (double)((((int)ox + kBrickPad) & ~3) - kBrickPad);
+                        oy = (double)((((int)oy + kBrickPad) & ~1) - kBrickPad);
+                        oz = (double)((((int)oz + kBrickPad) & ~3) - kBrickPad);
+                    }
                     const double rmax = fmax(fmax(hix - ox, hiy - oy), hiz - oz);
                     fast = interior && L < kSmemLevels && rmax < 100.0;
                     meta |= (L << 8) | (1 << 12);
@@ -607,7 +642,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                         re1 = make_float4((float)((p1.x - p0.x) * inv4n), (float)((p1.y - p0.y) * inv4n), (float)((p1.z - p0.z) * inv4n), (float)ox);
                         re2 = make_float4((float)((p2.x - p0.x) * inv4n), (float)((p2.y - p0.y) * inv4n), (float)((p2.z - p0.z) * inv4n), (float)oy);
                         re3 = make_float4((float)((p3.x - p0.x) * inv4n), (float)((p3.y - p0.y) * inv4n), (float)((p3.z - p0.z) * inv4n), (float)oz);
-                        olin = (int)((unsigned)((int)oz * XYi + (int)oy * X + (int)ox) - fold);
+                        olin = BRICK ? (int)(brick_index((int)ox, (int)oy, (int)oz, bSy, bSz) - fold) : (int)((unsigned)((int)oz * XYi + (int)oy * X + (int)ox) - fold);
                         meta |= 1 << 13;
                     }
                     rv = v;
@@ -676,7 +711,15 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                         const float qz = fmaf(c.z, e3.z, fmaf(c.y, e2.z, fmaf(c.x, e1.z, fmaf(c.w, e3.w, q0.z))));
                         const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
                         const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
-                        const int lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) + obase);
+                        int lin;
+                        if (BRICK) {
+                            const float hx = fmaf(tx, 0.99999988079071044921875f, 37748736.0f), hy = fmaf(ty, 0.999999940395355224609375f, MAGIC);
+                            const float hz = fmaf(tz, 0.99999988079071044921875f, 37748736.0f);
+                            lin = (int)(__float_as_uint(tx) + 28u * __float_as_uint(hx) + 4u * __float_as_uint(ty) + bKy * __float_as_uint(hy) +
+                                        8u * __float_as_uint(tz) + bKz * __float_as_uint(hz) + obase);
+                        } else {
+                            lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) + obase);
+                        }
                         idx[u] = ok ? lin : -1;
                         if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) unsafe |= 1u << u;
                     }
@@ -692,7 +735,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                                 const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
                                 const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
                                 const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                                idx[u] = iz * XYi + iy * X + ix; // interior tet: always in range
+                                idx[u] = BRICK ? exact_index(ix, iy, iz) : iz * XYi + iy * X + ix; // linear form: interior tet, always in range
                             }
                     }
                     VoxT val[U];
@@ -718,7 +761,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                             const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
                             const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
                             const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                            if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) idx[u] = iz * XYi + iy * X + ix;
+                            idx[u] = exact_index(ix, iy, iz);
                         }
                     }
                     VoxT val[U];

@@ -1,27 +1,34 @@
-// dsc_tet_g32.cuh -- per-tet integration, warp-per-tet form over a bricked copy of the volume (variant 1024, the default
-// of the per-iteration hot path).
+// dsc_tet_g32.cuh -- per-tet integration, warp-per-tet form over a bricked copy of the volume (tet variant bit 1024).
 //
 // Same arithmetic contract as tet_integrate_w2_kernel (dsc_kernels.cuh): image3d::get_tetra_intensity
 // (DEMO/image3d.cpp:351-382) batched over all tets and fused with the per-label reduction; the sample -> voxel
 // classification is bit-identical to the reference (FP32 lattice filter with a rigorous guard band, exact FP64 re-evaluation
-// inside the band), sums are FP64.  What changes is everything the profile of w2 showed to be the limit
-// (profiles/README.md: the L1 data pipe at one wavefront per distinct 128 B line touched by a gather -- 16.8 lines per
-// 32-lane gather on the x-fastest volume -- and instruction issue at ~52 instructions per sample):
+// inside the band), sums are FP64.  It attacks the two limits the profile of w2 shows (profiles/README.md: the L1 data pipe
+// at one wavefront per distinct 128 B line touched by a gather -- 16.8 lines per 32-lane gather on the x-fastest volume --
+// and instruction issue at ~52 instructions per sample):
 //
-//  * bricked volume: the kernel gathers from a copy of the volume laid out in 4x2x4-voxel bricks (32 voxels; 128 B for
-//    float), padded by 8 voxels on every side.  A tet's samples fall into few bricks, and with all 32 lanes on ONE tet a
-//    gather touches 8.0 lines instead of 16.8 (scripts/line_sim.py reproduces both figures on the C4 mesh).  The padding
-//    holds what image3d::get_value returns outside the volume (0, DEMO/image3d.cpp:480-491) and, in the layer at -1, a
-//    replica of layer 0: the reference truncates toward zero (image3d.cpp:366), so a coordinate in (-1,0) reads voxel 0.
-//    Every tet whose bounding box lies inside the padded region therefore takes the fast path without bounds checks.
+//  * bricked volume: gathers go to a copy of the volume laid out in 4x2x4-voxel bricks (32 voxels; 128 B for float), padded
+//    by 8 voxels on every side (dsc_kernels.cuh: brick_index).  With all 32 lanes on ONE tet a gather touches 8.0 lines
+//    instead of 16.8 (scripts/line_sim.py reproduces both figures on the C4 mesh; ncu confirms).  The padding replaces the
+//    bounds test of image3d::get_value, so every tet inside the padded region takes the fast path.
 //  * tet-local origins are aligned to brick corners, so the brick index and the offset inside the brick are both linear
 //    in r and floor(r / brick): idx = base + rx + 28 hx + 4 ry + (Sy-8) hy + 8 rz + (Sz-32) hz.
 //  * packed FP32 (Blackwell FFMA2 / FADD2, PTX fma.rn.f32x2): one lane evaluates two samples per instruction -- the two
 //    halves of a pair of tets (pairs are formed in phase A from tets of the same label and sample level, so both halves
-//    use the same table row) -- which halves the issue slots of the position arithmetic.  floor() is the 1.5*2^23 trick; floor(r/4) and floor(r/2) come from one
-//    more FFMA2 each on the already rounded value: fma(t, 1-2^-23, 4.5*2^23) rounds M4 + r - 1.5 - r 2^-23 at ulp 4.
+//    use the same table row) -- which halves the issue slots of the position arithmetic.  floor() is the 1.5*2^23 trick;
+//    floor(r/4) and floor(r/2) come from one more FFMA2 each on the already rounded value: fma(t, 1-2^-23, 4.5*2^23)
+//    rounds M4 + r - 1.5 - r 2^-23 at ulp 4 (tests/test_brick_index.py emulates all of this on the host).
 //  * no per-tet cross-lane reduction: each lane multiplies its partial sum by the tet's v/n^3 and keeps a running sum for
 //    the current label; a warp reduction happens only when the label changes (tets are sorted by label inside a tile).
+//
+// MEASURED (C4, B200): 0.47 ms against 0.39 ms of w2, so w2 stays the default.  The index arithmetic is down to 24
+// instructions per sample (w2: 52) and the L1 wavefronts of the gathers are halved, but the packed pair records cost 126
+// registers (16 warps per SM), and with four gathers in flight per warp the kernel is bound by memory latency: 31 % of the
+// stall samples sit on the first use of the gathered voxels although the next step's indices are computed between the
+// loads and that use.  Register-destination loads cannot be kept in flight any longer than that: ptxas drains every pending
+// load at the first branch it meets, warp-uniform or not.  cp.async gathers (4 B per lane) lift that limit but load the L1
+// pipe to 79 % (0.54 ms); L2 prefetches of the next step's addresses cost more than they hide (0.79 ms).  DESIGN.md
+// section 9 has the table.
 //
 // Lattice form of the sample position and the guard band: see tet_integrate_w2_kernel; the only difference is that the
 // origin O is floor(min corner) rounded DOWN to a brick corner, so Rmax is up to 3 voxels larger.
@@ -35,7 +42,6 @@
 
 namespace dsc {
 
-constexpr int kBrickPad = 8;                      // voxels of padding on every side (multiple of every brick extent)
 constexpr int kG32Slots = 66;                     // sum over n = 1..9 of ceil(n^3 / 32)
 constexpr int kG32Rows = kG32Slots * 32;          // padded table rows
 constexpr int kG32Pairs = 24;                     // tet pairs a tile can hold (32 tets plus the odd member of each label/level class)
@@ -45,15 +51,9 @@ constexpr int kG32SmemBytes = kG32Rows * 16 + 8 * kG32WarpBytes;
 // first 32-row slot of level L (n = L + 1) in the padded table
 DSC_HD int g32_slot_off(int L)
 {
-    const int off[10] = {0, 1, 2, 3, 5, 9, 16, 27, 43, 66};
-    return off[L];
-}
-
-// element index of voxel (x, y, z) (volume coordinates, -kBrickPad <= x < X + pad ...) in the bricked, padded copy
-DSC_HD unsigned brick_index(int x, int y, int z, unsigned Sy, unsigned Sz)
-{
-    const unsigned xp = (unsigned)(x + kBrickPad), yp = (unsigned)(y + kBrickPad), zp = (unsigned)(z + kBrickPad);
-    return (zp >> 2) * Sz + (yp >> 1) * Sy + ((xp >> 2) << 5) + ((zp & 3u) << 3) + ((yp & 1u) << 2) + (xp & 3u);
+    // {0, 1, 2, 3, 5, 9, 16, 27, 43, 66} packed in bytes (a local array would live on the stack)
+    const unsigned w = L < 4 ? 0x03020100u : (L < 8 ? 0x1B100905u : 0x0000422Bu);
+    return (int)((w >> (8 * (L & 3))) & 0xffu);
 }
 
 // Builds the bricked copy.  flags bit 0 is raised when a float volume holds anything but non-negative finite numbers

@@ -77,7 +77,7 @@ struct dscgpu_ctx {
     cudaTextureObject_t vol_tex = 0;
     int force_thread_gather = 0; // 1: thread-per-node gather (first implementation) instead of warp-per-node
     int hot_want_sq = 0; // dscgpu_image_force_eval / dscgpu_tet_phase_sums_dev skip the second moment unless asked
-    int tet_variant = 1024 | 128; // see dscgpu_set_tet_variant; default = warp-per-tet kernel over the bricked volume, w2 for what it does not cover
+    int tet_variant = 128; // see dscgpu_set_tet_variant; default = w2 (the fastest measured form: DESIGN.md section 9)
     // bricked, padded copy of the volume for tet_sums_g32_kernel (dsc_tet_g32.cuh); rebuilt when the volume may have changed
     void *d_brick = nullptr;
     bool brick_valid = false;
@@ -231,9 +231,9 @@ template <typename VoxT> int launch_tpt_v(dscgpu_ctx *ctx, TetArgs &a, bool tex,
     return filter ? launch_tpt_t<VoxT, kFetchLdg, true>(ctx, a) : launch_tpt_t<VoxT, kFetchLdg, false>(ctx, a);
 }
 
-template <typename VoxT, bool WANT_SQ, bool PER_TET> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
 {
-    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET>;
+    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET, BRICK>;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     if (occ < 1) occ = 1;
@@ -253,6 +253,10 @@ template <typename VoxT, bool WANT_SQ, bool PER_TET> int launch_w2_t(dscgpu_ctx 
 template <typename VoxT> int launch_w2(dscgpu_ctx *ctx, TetArgs &a)
 {
     const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
+    if (a.brick) { // bricked volume (variant bit 2048)
+        if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true, true>(ctx, a) : launch_w2_t<VoxT, true, false, true>(ctx, a);
+        return per_tet ? launch_w2_t<VoxT, false, true, true>(ctx, a) : launch_w2_t<VoxT, false, false, true>(ctx, a);
+    }
     if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true>(ctx, a) : launch_w2_t<VoxT, true, false>(ctx, a);
     return per_tet ? launch_w2_t<VoxT, false, true>(ctx, a) : launch_w2_t<VoxT, false, false>(ctx, a);
 }
@@ -511,6 +515,14 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
         }
     }
     if ((ctx->tet_variant & 128) && !with_c && fits32) { // warp-level two-phase kernel with lattice coordinates
+        a.brick = nullptr;
+        if ((ctx->tet_variant & 2048) && g32_fits(ctx)) { // ... gathering from the bricked, padded copy of the volume
+            int r = ensure_bricks(ctx);
+            if (r) return r;
+            a.brick = ctx->d_brick;
+            a.brick_sy = 32u * (unsigned)ctx->brick_nb[0];
+            a.brick_sz = a.brick_sy * (unsigned)ctx->brick_nb[1];
+        }
         switch (ctx->dtype) {
         case DSCGPU_U8: return launch_w2<unsigned char>(ctx, a);
         case DSCGPU_U16: return launch_w2<unsigned short>(ctx, a);
@@ -568,6 +580,7 @@ int tet_pass_range(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, con
     for (int k = 0; k < kMaxPhase; k++) a.c[k] = (c && k < nc) ? c[k] : 0.0;
     a.tet_total = o.d_total; a.tet_vol = o.d_vol; a.tet_mean = o.d_mean; a.tet_energy = o.d_energy; a.tet_variation = o.d_variation;
     a.sample_count = ctr(ctx, 0);
+    a.brick = nullptr; a.brick_sy = a.brick_sz = 0;
     return launch_tet(ctx, a, nc > 0 && (o.d_energy || o.d_variation));
 }
 
@@ -1005,7 +1018,7 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
         CK(cudaMemcpy(ctx->d_lat32, t32.data(), t32.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (const char *ev = getenv("DSCGPU_TET_VARIANT")) ctx->tet_variant = atoi(ev);
-    if (voxels_host && (ctx->tet_variant & 1024) && g32_fits(ctx)) { // bricked copy for the warp-per-tet kernel, once per volume
+    if (voxels_host && (ctx->tet_variant & (1024 | 2048)) && g32_fits(ctx)) { // bricked copy for the warp-per-tet kernel, once per volume
         int rb = ensure_bricks(ctx);
         if (rb) return rb;
     }
@@ -1635,7 +1648,7 @@ int dscgpu_build_texture(dscgpu_ctx *ctx)
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 2048, "variant is an 11-bit field");
+    ARG(variant >= 0 && variant < 4096, "variant is a 12-bit field");
     if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
         int r = dscgpu_build_texture(ctx);
         if (r) return r;

@@ -230,9 +230,10 @@ int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes);
  *   bit 3 (8)    batched G-lanes-per-tet kernel: bits 4-5 = log2(gathers in flight per lane), bit 2 (4) = FP32 filter
  *   bit 6 (64)   two-phase CTA kernel (setup per thread, sampling per warp, FP32 filter)
  *   bit 7 (128)  w2: warp-level two-phase kernel, origin-relative lattice coordinates;  256: w3 fixed-point floor;  512: w4 pipelined w2
- *   bit 10 (1024) warp-per-tet kernel over the bricked volume, packed FP32 (FFMA2) position arithmetic; serves every call
- *                without candidates and with include_bound == 0, the remaining bits choose the kernel for the other calls
- * Default 1152 (= 1024 | 128).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
+ *   bit 10 (1024) warp-per-tet kernel over a bricked copy of the volume, packed FP32 (FFMA2) position arithmetic; serves every
+ *                call without candidates and with include_bound == 0, the remaining bits choose the kernel for the other calls
+ *   bit 11 (2048) with bit 7: w2 gathering from the bricked, padded copy of the volume
+ * Default 128 (w2, the fastest measured form; DESIGN.md section 9 has the numbers of the others).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
  * Per-candidate outputs (tet_energy / tet_variation) always use the v1 kernel. */
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant);
 int dscgpu_build_texture(dscgpu_ctx *ctx);

@@ -13,6 +13,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 RTOL = 1e-6
 G32 = 1024 | 128
+W2B = 2048 | 128  # w2 gathering from the bricked copy
 
 
 def _random_tets(rng, dims_xyz, n_tets, size_lo, size_hi, margin):
@@ -37,7 +38,7 @@ def _check(pkg, flat, vol, pos, tets, labels, P, exact=True):
     ref = flat.tet_integrate(vol, tets, pos, c=[0.0], want_hash=False)
     m = labels != 0
     outs = {}
-    for variant in (G32, 128):
+    for variant in (G32, W2B, 128):
         seg.set_tet_variant(variant)
         o = seg.tet_integrate()
         assert np.array_equal(o["vol"][m], ref["vol"][m])
@@ -57,11 +58,12 @@ def _check(pkg, flat, vol, pos, tets, labels, P, exact=True):
         np.testing.assert_allclose(o2["phase_volume"], volu, rtol=RTOL)
         outs[variant] = o
     # the hot path proper (dscgpu_tet_phase_sums_dev: no second moment, no per-tet outputs) through the fused evaluation
-    seg.set_tet_variant(G32)
-    mean, _ = seg.image_force_eval(_snap(pos, tets, labels), mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_ATOMIC)
-    ok = volu > 0
-    np.testing.assert_allclose(np.asarray(mean)[ok], (tot / np.where(ok, volu, 1))[ok], rtol=RTOL, atol=1e-12)
-    assert seg.last_sample_count() == int(ref["nsamp"][m].sum())
+    for variant in (G32, W2B):
+        seg.set_tet_variant(variant)
+        mean, _ = seg.image_force_eval(_snap(pos, tets, labels), mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_ATOMIC)
+        ok = volu > 0
+        np.testing.assert_allclose(np.asarray(mean)[ok], (tot / np.where(ok, volu, 1))[ok], rtol=RTOL, atol=1e-12)
+        assert seg.last_sample_count() == int(ref["nsamp"][m].sum())
     img.close()
     return outs
 

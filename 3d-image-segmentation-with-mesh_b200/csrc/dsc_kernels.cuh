@@ -137,6 +137,25 @@ DSC_D double widen_exact(float f)
     return __hiloint2double((int)hi, (int)lo);
 }
 
+// A non-negative finite float with bits b is the double with words (b >> 3, b << 29) times 2^896 -- zeros and denormals
+// included -- so sums of such values can be kept scaled by 2^-896: two shifts per voxel, no conversion instruction, no
+// special cases, and one exact multiplication by 2^896 when the sum is used.  Volumes that hold negative values (incl. -0),
+// infinities or NaNs (volume_flags_kernel) use widen_exact.
+DSC_D double widen_scaled(float f)
+{
+    const unsigned b = __float_as_uint(f);
+    return __hiloint2double((int)(b >> 3), (int)(b << 29));
+}
+
+// flags bit 0: the float volume holds something other than non-negative finite numbers
+__global__ void volume_flags_kernel(const float *__restrict__ vol, size_t n, unsigned *flags)
+{
+    unsigned f = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (__float_as_uint(__ldg(vol + i)) >= 0x7f800000u) f = 1;
+    if (__any_sync(0xffffffffu, f) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+}
+
 __global__ void pos_to_float_kernel(const double4 *__restrict__ pos4, float4 *__restrict__ pos4f, unsigned n)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,6 +196,7 @@ struct TetArgs {
     unsigned long long *sample_count; // algorithmic samples processed (for the roofline figure)
     const void *brick;               // bricked, padded copy of the volume (w2 BRICK form), strides in elements
     unsigned brick_sy, brick_sz;
+    int vol_simple;                  // float volume: only non-negative finite values (scaled widening allowed)
 };
 
 template <typename VoxT, int G, bool WITH_C>
@@ -556,10 +576,11 @@ __global__ void __launch_bounds__(256) tet_integrate_g_kernel(const TetArgs a)
 // hz = floor(rz/4), each from one more FFMA on the rounded value (dsc_tet_g32.cuh explains the trick).  A gather then touches
 // 9.4 distinct 128 B lines instead of 16.8 (scripts/line_sim.py), and every tet inside the padded region -- including the
 // layer of tets along the volume border -- takes the filtered path.
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false>
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false>
 __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(const TetArgs a)
 {
     constexpr int G = 8, U = 4;
+    constexpr bool F32S = SIMPLE && sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral; // sums scaled by 2^-896 (widen_scaled)
     __shared__ float4 s_lat[kSmemRows];        // (a1, a2, a3, eps) per table row
     __shared__ double2 s_tabd[2 * kSmemRows];  // exact rows for the fallback
     __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0-.5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
@@ -686,10 +707,14 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     if (WANT_SQ) isq += (unsigned long long)q * q;
                 } else {
                     double I;
-                    if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val);
+                    if constexpr (F32S) I = widen_scaled((float)val);
+                    else if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val);
                     else I = (double)val;
                     s += I;
-                    if (WANT_SQ) sq = fma(I, I, sq); // second moment: tolerance quantity, fused on purpose
+                    if (WANT_SQ) {
+                        const double Iu = F32S ? I * 0x1p+896 : I; // exact
+                        sq = fma(Iu, Iu, sq); // second moment: tolerance quantity, fused on purpose
+                    }
                 }
             };
             if (meta & (1 << 13)) {
@@ -781,6 +806,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                 s += shfl_xor_d(s, m);
                 if (WANT_SQ) sq += shfl_xor_d(sq, m);
             }
+            if (F32S) s = s * 0x1p+896; // exact: back to the true sum
             if (active) {
                 const double v = w_v[warp][j];
                 const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)

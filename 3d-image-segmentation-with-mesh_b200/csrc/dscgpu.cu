@@ -81,7 +81,8 @@ struct dscgpu_ctx {
     // bricked, padded copy of the volume for tet_sums_g32_kernel (dsc_tet_g32.cuh); rebuilt when the volume may have changed
     void *d_brick = nullptr;
     bool brick_valid = false;
-    bool brick_simple = true; // float volume holds only +0 and positive normal numbers
+    bool brick_simple = true; // float volume holds only non-negative finite numbers (flag of the bricked copy's build)
+    bool vol_flags_valid = false, vol_simple = false; // the same property from a scan of the volume (volume_flags_kernel)
     int brick_nb[3] = {0, 0, 0};
     float4 *d_lat32 = nullptr;
     unsigned *d_brick_flags = nullptr;
@@ -231,9 +232,30 @@ template <typename VoxT> int launch_tpt_v(dscgpu_ctx *ctx, TetArgs &a, bool tex,
     return filter ? launch_tpt_t<VoxT, kFetchLdg, true>(ctx, a) : launch_tpt_t<VoxT, kFetchLdg, false>(ctx, a);
 }
 
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
+// float volumes: one pass that tells whether every voxel is a non-negative finite number (scaled widening, dsc_kernels.cuh)
+int ensure_volume_flags(dscgpu_ctx *ctx)
 {
-    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET, BRICK>;
+    if (ctx->vol_flags_valid) return DSCGPU_OK;
+    ctx->vol_simple = false;
+    if (ctx->dtype == DSCGPU_F32) {
+        if (!ctx->d_brick_flags) CK(cudaMalloc(&ctx->d_brick_flags, sizeof(unsigned)));
+        CK(cudaMemsetAsync(ctx->d_brick_flags, 0, sizeof(unsigned), ctx->stream));
+        const size_t n = (size_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2];
+        volume_flags_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(static_cast<const float *>(ctx->d_vol), n, ctx->d_brick_flags);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        unsigned flags = 1;
+        CK(cudaMemcpyAsync(&flags, ctx->d_brick_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->vol_simple = (flags & 1u) == 0;
+    }
+    ctx->vol_flags_valid = true;
+    return DSCGPU_OK;
+}
+
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
+{
+    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET, BRICK, SIMPLE>;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     if (occ < 1) occ = 1;
@@ -256,6 +278,12 @@ template <typename VoxT> int launch_w2(dscgpu_ctx *ctx, TetArgs &a)
     if (a.brick) { // bricked volume (variant bit 2048)
         if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true, true>(ctx, a) : launch_w2_t<VoxT, true, false, true>(ctx, a);
         return per_tet ? launch_w2_t<VoxT, false, true, true>(ctx, a) : launch_w2_t<VoxT, false, false, true>(ctx, a);
+    }
+    if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
+        if (a.vol_simple) { // non-negative finite floats: scaled widening
+            if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true, false, true>(ctx, a) : launch_w2_t<VoxT, true, false, false, true>(ctx, a);
+            return per_tet ? launch_w2_t<VoxT, false, true, false, true>(ctx, a) : launch_w2_t<VoxT, false, false, false, true>(ctx, a);
+        }
     }
     if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true>(ctx, a) : launch_w2_t<VoxT, true, false>(ctx, a);
     return per_tet ? launch_w2_t<VoxT, false, true>(ctx, a) : launch_w2_t<VoxT, false, false>(ctx, a);
@@ -516,6 +544,11 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
     }
     if ((ctx->tet_variant & 128) && !with_c && fits32) { // warp-level two-phase kernel with lattice coordinates
         a.brick = nullptr;
+        if (!(ctx->tet_variant & 4096)) { // bit 12: keep the general float widening (A/B switch)
+            int rf = ensure_volume_flags(ctx);
+            if (rf) return rf;
+            a.vol_simple = ctx->vol_simple ? 1 : 0;
+        }
         if ((ctx->tet_variant & 2048) && g32_fits(ctx)) { // ... gathering from the bricked, padded copy of the volume
             int r = ensure_bricks(ctx);
             if (r) return r;
@@ -581,6 +614,7 @@ int tet_pass_range(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, con
     a.tet_total = o.d_total; a.tet_vol = o.d_vol; a.tet_mean = o.d_mean; a.tet_energy = o.d_energy; a.tet_variation = o.d_variation;
     a.sample_count = ctr(ctx, 0);
     a.brick = nullptr; a.brick_sy = a.brick_sz = 0;
+    a.vol_simple = 0;
     return launch_tet(ctx, a, nc > 0 && (o.d_energy || o.d_variation));
 }
 
@@ -1018,6 +1052,10 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
         CK(cudaMemcpy(ctx->d_lat32, t32.data(), t32.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (const char *ev = getenv("DSCGPU_TET_VARIANT")) ctx->tet_variant = atoi(ev);
+    if (voxels_host) { // one scan of a float volume: are all voxels non-negative finite numbers?
+        int rf = ensure_volume_flags(ctx);
+        if (rf) return rf;
+    }
     if (voxels_host && (ctx->tet_variant & (1024 | 2048)) && g32_fits(ctx)) { // bricked copy for the warp-per-tet kernel, once per volume
         int rb = ensure_bricks(ctx);
         if (rb) return rb;
@@ -1083,6 +1121,7 @@ void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx)
 {
     if (!ctx) return nullptr;
     ctx->brick_valid = false; // the caller may write the volume through this pointer
+    ctx->vol_flags_valid = false;
     return ctx->d_vol;
 }
 
@@ -1090,6 +1129,7 @@ int dscgpu_volume_modified(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
     ctx->brick_valid = false;
+    ctx->vol_flags_valid = false;
     return DSCGPU_OK;
 }
 
@@ -1101,6 +1141,7 @@ int dscgpu_volume_upload(dscgpu_ctx *ctx, const void *voxels_host)
     CK(cudaMemcpyAsync(ctx->d_vol, voxels_host, n * dtype_size(ctx->dtype), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->brick_valid = false;
+    ctx->vol_flags_valid = false;
     ctx->has_sum_table = false;
     return DSCGPU_OK;
 }
@@ -1648,7 +1689,7 @@ int dscgpu_build_texture(dscgpu_ctx *ctx)
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 4096, "variant is a 12-bit field");
+    ARG(variant >= 0 && variant < 8192, "variant is a 13-bit field");
     if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
         int r = dscgpu_build_texture(ctx);
         if (r) return r;

@@ -197,6 +197,7 @@ struct TetArgs {
     const void *brick;               // bricked, padded copy of the volume (w2 BRICK form), strides in elements
     unsigned brick_sy, brick_sz;
     int vol_simple;                  // float volume: only non-negative finite values (scaled widening allowed)
+    int pack;                        // w2: packed FP32 position arithmetic
 };
 
 template <typename VoxT, int G, bool WITH_C>
@@ -553,6 +554,36 @@ __global__ void __launch_bounds__(256) tet_integrate_g_kernel(const TetArgs a)
     if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
 }
 
+// ---- packed FP32 pairs (Blackwell FFMA2 / FADD2, PTX fma.rn.f32x2 / add.rn.f32x2): two IEEE operations per issue slot ----
+typedef unsigned long long f32x2;
+DSC_D f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+DSC_D void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+DSC_D f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+DSC_D f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// first 32-row slot of level L (n = L + 1) when every level is padded to a multiple of 32 rows
+DSC_HD int g32_slot_off(int L)
+{
+    // {0, 1, 2, 3, 5, 9, 16, 27, 43, 66} packed in bytes (a local array would live on the stack)
+    const unsigned w = L < 4 ? 0x03020100u : (L < 8 ? 0x1B100905u : 0x0000422Bu);
+    return (int)((w >> (8 * (L & 3))) & 0xffu);
+}
+
 // -------------------------------------------------------------------------------------------------
 // Warp-level two-phase form with origin-relative lattice coordinates (variant 128).
 //
@@ -576,19 +607,37 @@ __global__ void __launch_bounds__(256) tet_integrate_g_kernel(const TetArgs a)
 // hz = floor(rz/4), each from one more FFMA on the rounded value (dsc_tet_g32.cuh explains the trick).  A gather then touches
 // 9.4 distinct 128 B lines instead of 16.8 (scripts/line_sim.py), and every tet inside the padded region -- including the
 // layer of tets along the volume border -- takes the filtered path.
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false>
+// PACK (variant bit 8192): the position arithmetic of a lane's four samples runs as two packed pairs (FFMA2 / FADD2), from a
+// copy of the lattice table laid out in pairs of rows (i, i + 8).
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false>
 __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(const TetArgs a)
 {
     constexpr int G = 8, U = 4;
     constexpr bool F32S = SIMPLE && sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral; // sums scaled by 2^-896 (widen_scaled)
-    __shared__ float4 s_lat[kSmemRows];        // (a1, a2, a3, eps) per table row
+    constexpr int kPairEntries = 9 * 2 * 8;    // levels n <= 5: 1+1+1+2+4 iterations of 32 rows, two row pairs per lane and iteration
+    __shared__ float4 s_lat[PACK ? (2 * kPairEntries) : kSmemRows]; // (a1, a2, a3, eps) per table row; PACK: pairs, see below
     __shared__ double2 s_tabd[2 * kSmemRows];  // exact rows for the fallback
     __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0-.5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
     __shared__ int2 w_m[8][32];                // meta, (O_linear - fold)
     __shared__ double w_v[8][32];
     __shared__ uint4 w_nd[8][32];
     for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
-    for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_lat[i] = a.tet_lat[i];
+    if (PACK) {
+        // entry e = (iteration slot * 2 + p) * 8 + g holds rows i = 32 it + 16 p + g and j = i + 8 of its level (clamped to the last
+        // row) as (a1_i, a1_j, a2_i, a2_j), (a3_i, a3_j, eps_i, eps_j): each LDS.128 yields two register pairs ready for FFMA2
+        for (int e = threadIdx.x; e < kPairEntries; e += blockDim.x) {
+            const int slot = e >> 4, pp = (e >> 3) & 1, g = e & 7;
+            int L = 0;
+            while (L < kSmemLevels - 1 && g32_slot_off(L + 1) <= slot) L++;
+            const int it = slot - g32_slot_off(L), n3 = (L + 1) * (L + 1) * (L + 1), off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+            const int i = min(32 * it + 16 * pp + g, n3 - 1), j = min(32 * it + 16 * pp + g + 8, n3 - 1);
+            const float4 ri = a.tet_lat[off + i], rj = a.tet_lat[off + j];
+            s_lat[2 * e] = make_float4(ri.x, rj.x, ri.y, rj.y);
+            s_lat[2 * e + 1] = make_float4(ri.z, rj.z, ri.w, rj.w);
+        }
+    } else {
+        for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_lat[i] = a.tet_lat[i];
+    }
     __syncthreads();
 
     const VoxT *__restrict__ vol = static_cast<const VoxT *>(BRICK ? a.brick : a.vol.data);
@@ -722,10 +771,38 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                 const float thr = q0.w;
                 const unsigned obase = (unsigned)mm.y;
                 const float4 *__restrict__ tl = s_lat + off;
+                const ulonglong2 *__restrict__ tl2 = reinterpret_cast<const ulonglong2 *>(s_lat) + (size_t)g32_slot_off(L) * 32 + 2 * lane_g;
                 const int last = n3 - 1;
-                for (int base = lane_g; base < n3; base += G * U) {
+                for (int base = lane_g, it = 0; base < n3; base += G * U, it++) {
                     int idx[U];
                     unsigned unsafe = 0;
+                    if constexpr (PACK) {
+                        const f32x2 M2 = pk2(MAGIC, MAGIC), NM2 = pk2(-MAGIC, -MAGIC), NEG1 = pk2(-1.0f, -1.0f);
+#pragma unroll
+                        for (int pp = 0; pp < 2; pp++) { // rows (i, i + 8) in the two halves of a packed register
+                            const ulonglong2 A = tl2[(it * 2 + pp) * 16], B = tl2[(it * 2 + pp) * 16 + 1];
+                            const int i0 = base + 16 * pp;
+                            const bool ok0 = i0 <= last, ok1 = i0 + 8 <= last;
+                            const f32x2 a1 = A.x, a2 = A.y, a3 = B.x, ep = B.y;
+                            f32x2 qx = fma2(ep, pk2(e1.w, e1.w), pk2(q0.x, q0.x)), qy = fma2(ep, pk2(e2.w, e2.w), pk2(q0.y, q0.y));
+                            f32x2 qz = fma2(ep, pk2(e3.w, e3.w), pk2(q0.z, q0.z));
+                            qx = fma2(a1, pk2(e1.x, e1.x), qx); qy = fma2(a1, pk2(e1.y, e1.y), qy); qz = fma2(a1, pk2(e1.z, e1.z), qz);
+                            qx = fma2(a2, pk2(e2.x, e2.x), qx); qy = fma2(a2, pk2(e2.y, e2.y), qy); qz = fma2(a2, pk2(e2.z, e2.z), qz);
+                            qx = fma2(a3, pk2(e3.x, e3.x), qx); qy = fma2(a3, pk2(e3.y, e3.y), qy); qz = fma2(a3, pk2(e3.z, e3.z), qz);
+                            const f32x2 tx2 = add2(qx, M2), ty2 = add2(qy, M2), tz2 = add2(qz, M2);
+                            const f32x2 ex2 = fma2(add2(tx2, NM2), NEG1, qx), ey2 = fma2(add2(ty2, NM2), NEG1, qy), ez2 = fma2(add2(tz2, NM2), NEG1, qz);
+                            float tx[2], ty[2], tz[2], ex[2], ey[2], ez[2];
+                            upk2(tx2, tx[0], tx[1]); upk2(ty2, ty[0], ty[1]); upk2(tz2, tz[0], tz[1]);
+                            upk2(ex2, ex[0], ex[1]); upk2(ey2, ey[0], ey[1]); upk2(ez2, ez[0], ez[1]);
+#pragma unroll
+                            for (int k = 0; k < 2; k++) {
+                                const bool ok = k ? ok1 : ok0;
+                                const int lin = (int)(__float_as_uint(tz[k]) * (unsigned)XYi + __float_as_uint(ty[k]) * (unsigned)X + __float_as_uint(tx[k]) + obase);
+                                idx[2 * pp + k] = ok ? lin : -1;
+                                if (ok && fmaxf(fmaxf(fabsf(ex[k]), fabsf(ey[k])), fabsf(ez[k])) >= thr) unsafe |= 1u << (2 * pp + k);
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const int i = base + u * G;
@@ -747,6 +824,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                         }
                         idx[u] = ok ? lin : -1;
                         if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) unsafe |= 1u << u;
+                    }
                     }
                     if (unsafe) { // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
                         const uint4 nd = w_nd[warp][j];

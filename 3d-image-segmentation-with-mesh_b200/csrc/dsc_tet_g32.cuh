@@ -48,14 +48,6 @@ constexpr int kG32Pairs = 24;                     // tet pairs a tile can hold (
 constexpr int kG32WarpBytes = 8 * kG32Pairs * 16 + 2 * kG32Pairs * 8 + kG32Pairs * 16 + 512 + 256 + 2 * kG32Pairs * 4 + 2 * kG32Pairs * 4 + 128 + 256;
 constexpr int kG32SmemBytes = kG32Rows * 16 + 8 * kG32WarpBytes;
 
-// first 32-row slot of level L (n = L + 1) in the padded table
-DSC_HD int g32_slot_off(int L)
-{
-    // {0, 1, 2, 3, 5, 9, 16, 27, 43, 66} packed in bytes (a local array would live on the stack)
-    const unsigned w = L < 4 ? 0x03020100u : (L < 8 ? 0x1B100905u : 0x0000422Bu);
-    return (int)((w >> (8 * (L & 3))) & 0xffu);
-}
-
 // Builds the bricked copy.  flags bit 0 is raised when a float volume holds anything but non-negative finite numbers
 // (negative values incl. -0, infinities, NaNs): the kernel then widens voxels with the general routine.
 template <typename VoxT>
@@ -97,28 +89,6 @@ struct TetG32Args {
     double *partials;
     unsigned long long *sample_count;
 };
-
-// ---- packed FP32 pairs (Blackwell FFMA2 / FADD2) ----
-typedef unsigned long long f32x2;
-DSC_D f32x2 pk2(float lo, float hi)
-{
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-DSC_D void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-DSC_D f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-DSC_D f32x2 add2(f32x2 a, f32x2 b)
-{
-    f32x2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
 
 DSC_D double warp_sum_d(double v)
 {

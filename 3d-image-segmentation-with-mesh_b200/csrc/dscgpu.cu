@@ -253,9 +253,9 @@ int ensure_volume_flags(dscgpu_ctx *ctx)
     return DSCGPU_OK;
 }
 
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
 {
-    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET, BRICK, SIMPLE>;
+    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET, BRICK, SIMPLE, PACK>;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     if (occ < 1) occ = 1;
@@ -278,6 +278,14 @@ template <typename VoxT> int launch_w2(dscgpu_ctx *ctx, TetArgs &a)
     if (a.brick) { // bricked volume (variant bit 2048)
         if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true, true>(ctx, a) : launch_w2_t<VoxT, true, false, true>(ctx, a);
         return per_tet ? launch_w2_t<VoxT, false, true, true>(ctx, a) : launch_w2_t<VoxT, false, false, true>(ctx, a);
+    }
+    if (a.pack) { // packed FP32 position arithmetic (variant bit 8192); hot-path instantiations only
+        if (!a.want_sq && !per_tet) {
+            if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
+                if (a.vol_simple) return launch_w2_t<VoxT, false, false, false, true, true>(ctx, a);
+            }
+            return launch_w2_t<VoxT, false, false, false, false, true>(ctx, a);
+        }
     }
     if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
         if (a.vol_simple) { // non-negative finite floats: scaled widening
@@ -544,6 +552,7 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
     }
     if ((ctx->tet_variant & 128) && !with_c && fits32) { // warp-level two-phase kernel with lattice coordinates
         a.brick = nullptr;
+        a.pack = (ctx->tet_variant & 8192) ? 1 : 0;
         if (!(ctx->tet_variant & 4096)) { // bit 12: keep the general float widening (A/B switch)
             int rf = ensure_volume_flags(ctx);
             if (rf) return rf;
@@ -615,6 +624,7 @@ int tet_pass_range(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, con
     a.sample_count = ctr(ctx, 0);
     a.brick = nullptr; a.brick_sy = a.brick_sz = 0;
     a.vol_simple = 0;
+    a.pack = 0;
     return launch_tet(ctx, a, nc > 0 && (o.d_energy || o.d_variation));
 }
 
@@ -1689,7 +1699,7 @@ int dscgpu_build_texture(dscgpu_ctx *ctx)
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 8192, "variant is a 13-bit field");
+    ARG(variant >= 0 && variant < 16384, "variant is a 14-bit field");
     if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
         int r = dscgpu_build_texture(ctx);
         if (r) return r;

@@ -233,6 +233,8 @@ int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes);
  *   bit 10 (1024) warp-per-tet kernel over a bricked copy of the volume, packed FP32 (FFMA2) position arithmetic; serves every
  *                call without candidates and with include_bound == 0, the remaining bits choose the kernel for the other calls
  *   bit 11 (2048) with bit 7: w2 gathering from the bricked, padded copy of the volume
+ *   bit 12 (4096) with bit 7: keep the general float widening (off: scaled widening when the volume allows it)
+ *   bit 13 (8192) with bit 7: packed FP32 (FFMA2) position arithmetic in the hot-path instantiation
  * Default 128 (w2, the fastest measured form; DESIGN.md section 9 has the numbers of the others).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
  * Per-candidate outputs (tet_energy / tet_variation) always use the v1 kernel. */
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant);

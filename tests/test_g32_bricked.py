@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-6
 G32 = 1024 | 128
 W2B = 2048 | 128  # w2 gathering from the bricked copy
+W2P = 8192 | 128  # w2 with packed FP32 position arithmetic (hot-path instantiation only)
 
 
 def _random_tets(rng, dims_xyz, n_tets, size_lo, size_hi, margin):
@@ -58,7 +59,7 @@ def _check(pkg, flat, vol, pos, tets, labels, P, exact=True):
         np.testing.assert_allclose(o2["phase_volume"], volu, rtol=RTOL)
         outs[variant] = o
     # the hot path proper (dscgpu_tet_phase_sums_dev: no second moment, no per-tet outputs) through the fused evaluation
-    for variant in (G32, W2B):
+    for variant in (G32, W2B, W2P, 128 | 4096):
         seg.set_tet_variant(variant)
         mean, _ = seg.image_force_eval(_snap(pos, tets, labels), mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_ATOMIC)
         ok = volu > 0

@@ -1,0 +1,185 @@
+// dsc_comm.cuh -- the two exchange steps of a multi-GPU image-force evaluation as kernels over NVLink peer memory.
+//
+// every GPU holds the whole volume and snapshot and a partition of the tets and interface faces; the only
+// cross-GPU data are 3*nb_phase per-phase sums (needed by the force pass) and the force rows of the nodes that have
+// interface faces (14 % of the nodes at C4: 1.15 MB).  Both are far below the size where NCCL's bandwidth matters; what a
+// step pays is NCCL's launch and synchronisation latency, twice, plus the pack / unpack kernels around the second call --
+// about 0.1 ms of a 0.19 ms step at 8 GPUs.  Here each exchange is ONE kernel that also does the neighbouring compute:
+//
+//   comm_phase_allreduce_kernel  adds this rank's per-CTA partial rows of the tet pass (what tet_finalize_kernel does),
+//                                publishes the 3*nb_phase sums in this rank's window, waits for every peer's flag, adds
+//                                the peers' sums in rank order (the same order on every rank: identical results) and
+//                                writes sums and means.
+//   force_scatter_rows_kernel    force_atomic_kernel scattering into compact rows (one per active node) of this rank's window.
+//   comm_force_allreduce_kernel  raises this rank's flag, waits for the peers', then every thread adds one row of all
+//                                ranks' windows in rank order (16-byte loads over NVLink, L1 bypassed) and stores it into
+//                                the full force array; it also clears the row of the OTHER window half for the next step.
+//
+// Windows are cudaMalloc'ed per rank and mapped into the peers with CUDA IPC (dscgpu_comm_create / dscgpu_comm_connect).
+// Each window has two halves used by alternating steps (epoch parity): a rank can be one exchange ahead of a slow peer, never
+// two, because it cannot pass exchange e+1 before that peer has published its flag e+1, which it does after its reads of
+// exchange e.  Flags carry the epoch (monotonic), so nothing is ever reset.  The epoch lives in device memory and is advanced
+// by the kernel itself: the step can be captured in a CUDA graph and replayed.
+// A spin that sees no progress for ~2 s sets an error word instead of hanging the device.
+#pragma once
+#include "dsc_kernels.cuh"
+
+namespace dsc {
+
+constexpr int kCommMaxWorld = 8;
+constexpr size_t kCommFlagSums = 0, kCommFlagForce = 128, kCommEpoch = 256, kCommError = 320, kCommUsedRows = 384, kCommSums = 512, kCommRows = 1024;
+// [0,64) [64,128) flag of the sums exchange, one per half; [128,256) flags of the force exchange; 256 epoch; 320 error;
+// 384 rows written into each half by its last use (2 x unsigned); [512,896) 2 x 24 doubles; from 1024 on: 2 x cap_rows x 3 doubles
+
+struct CommView {
+    unsigned char *win[kCommMaxWorld]; // window of every rank as mapped here; win[rank] is this rank's own
+    int rank, world;
+    unsigned cap_rows;
+};
+
+DSC_D unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+DSC_D void st_release_sys(unsigned long long *p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+// waits until the flag at p reaches epoch e; false (and the error word set) after ~2 s without success
+DSC_D bool comm_wait(const unsigned long long *p, unsigned long long e, int *err)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < e) {
+        if (clock64() - t0 > 4000000000ll) {
+            *err = 1;
+            return false;
+        }
+        __nanosleep(64);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kernel(CommView c, const double *__restrict__ partials, int n_rows, int nb_phase, double *sums,
+                                                                                  double *mean)
+{
+    const int col = threadIdx.x >> 5, lane = threadIdx.x & 31; // 24 warps, one per column of the partial rows
+    unsigned char *mine = c.win[c.rank];
+    __shared__ unsigned long long s_epoch;
+    __shared__ double tot[kMaxPhase], vol[kMaxPhase];
+    if (threadIdx.x == 0) {
+        unsigned long long *ep = reinterpret_cast<unsigned long long *>(mine + kCommEpoch);
+        s_epoch = *ep + 1; // one epoch per evaluation; the force exchange of the same evaluation reads it back
+        *ep = s_epoch;
+    }
+    double r = 0;
+    for (int i = lane; i < n_rows; i += 32) r += partials[(size_t)i * 3 * kMaxPhase + col];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) r += shfl_xor_d(r, m);
+    __syncthreads();
+    const unsigned long long e = s_epoch;
+    const int half = (int)(e & 1);
+    if (lane == 0) reinterpret_cast<double *>(mine + kCommSums)[half * 3 * kMaxPhase + col] = r;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned long long *>(mine + kCommFlagSums + 64 * half), e);
+    if (threadIdx.x < c.world) comm_wait(reinterpret_cast<const unsigned long long *>(c.win[threadIdx.x] + kCommFlagSums + 64 * half), e,
+                                         reinterpret_cast<int *>(mine + kCommError));
+    __syncthreads();
+    if (lane == 0) {
+        double t = 0;
+        for (int k = 0; k < c.world; k++) t += __ldcv(reinterpret_cast<const double *>(c.win[k] + kCommSums) + half * 3 * kMaxPhase + col);
+        const int which = col / kMaxPhase, ph = col % kMaxPhase;
+        if (ph < nb_phase) sums[which * nb_phase + ph] = t;
+        if (which == 0) tot[ph] = t;
+        if (which == 2) vol[ph] = t;
+    }
+    __syncthreads();
+    if (mean && threadIdx.x < nb_phase) mean[threadIdx.x] = tot[threadIdx.x] / vol[threadIdx.x];
+}
+
+struct ForceRowsArgs {
+    VolumeView vol;
+    MeshView mesh;
+    int nb_phase;
+    const double *mean;
+    const unsigned *apos;       // node -> row (exclusive scan of "has interface faces")
+    unsigned char *window;      // this rank's window
+    unsigned cap_rows;
+    unsigned begin, end;        // faces of this rank
+};
+
+// force_atomic_kernel with compact destination rows in the half of the window that belongs to the current epoch
+template <typename VoxT> __global__ void __launch_bounds__(128) force_scatter_rows_kernel(const ForceRowsArgs a)
+{
+    const unsigned f = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.end) return;
+    const unsigned long long e = *reinterpret_cast<const unsigned long long *>(a.window + kCommEpoch);
+    double *rows = reinterpret_cast<double *>(a.window + kCommRows) + (size_t)(e & 1) * 3 * a.cap_rows;
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    FaceGeom g;
+    unsigned n[3];
+    if (!face_setup(a.mesh, f, a.nb_phase, a.mean, g, n)) return;
+    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int q = c_gauss_off[g.gs]; q < c_gauss_off[g.gs + 1]; q++) {
+        const double w = c_gauss[4 * q];
+        const double b[3] = {c_gauss[4 * q + 1], c_gauss[4 * q + 2], c_gauss[4 * q + 3]};
+        const V3 p = add(add(mul(g.p[0], b[0]), mul(g.p[1], b[1])), mul(g.p[2], b[2]));
+        const double I = fetch_trilinear(vol, a.vol.X, a.vol.Y, a.vol.Z, p);
+        const V3 fv = mul(g.norm, (2 * I - g.c0 - g.c1) * (g.c0 - g.c1) * w * g.area);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { acc[k][0] += fv.x * b[k]; acc[k][1] += fv.y * b[k]; acc[k][2] += fv.z * b[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        double *dst = rows + 3 * (size_t)a.apos[n[k]];
+        atomicAdd(dst, acc[k][0]);
+        atomicAdd(dst + 1, acc[k][1]);
+        atomicAdd(dst + 2, acc[k][2]);
+    }
+}
+
+// rows of all ranks added in rank order into the full force array (which is zero everywhere else)
+__global__ void __launch_bounds__(256) comm_force_allreduce_kernel(CommView c, const unsigned *__restrict__ active_nodes, const unsigned *__restrict__ n_active_ptr,
+                                                                   double *__restrict__ forces)
+{
+    unsigned char *mine = c.win[c.rank];
+    const unsigned long long e = *reinterpret_cast<const unsigned long long *>(mine + kCommEpoch);
+    const int half = (int)(e & 1);
+    // every block raises the flag (same value: idempotent) so that no block depends on another block being scheduled
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long *>(mine + kCommFlagForce + 64 * half), e);
+    }
+    if (threadIdx.x < c.world) comm_wait(reinterpret_cast<const unsigned long long *>(c.win[threadIdx.x] + kCommFlagForce + 64 * half), e,
+                                         reinterpret_cast<int *>(mine + kCommError));
+    __syncthreads();
+    const unsigned n_active = min(*n_active_ptr, c.cap_rows);
+    unsigned *used = reinterpret_cast<unsigned *>(mine + kCommUsedRows);
+    const unsigned n_clear = used[half ^ 1]; // rows the other half received when it was last used (a different snapshot, possibly)
+    const size_t off_cur = kCommRows + (size_t)half * 3 * c.cap_rows * sizeof(double);
+    double *next = reinterpret_cast<double *>(mine + kCommRows) + (size_t)(half ^ 1) * 3 * c.cap_rows;
+    const unsigned n_loop = max(n_active, n_clear);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_loop; i += gridDim.x * blockDim.x) {
+        if (i < n_active) {
+            double x = 0, y = 0, z = 0;
+            for (int k = 0; k < c.world; k++) {
+                const double *src = reinterpret_cast<const double *>(c.win[k] + off_cur) + 3 * (size_t)i;
+                x += __ldcv(src);
+                y += __ldcv(src + 1);
+                z += __ldcv(src + 2);
+            }
+            const size_t node = active_nodes[i];
+            forces[3 * node] = x;
+            forces[3 * node + 1] = y;
+            forces[3 * node + 2] = z;
+        }
+        if (i < n_clear) { // the other half is idle until the next evaluation: clear it for its next use
+            next[3 * (size_t)i] = 0.0;
+            next[3 * (size_t)i + 1] = 0.0;
+            next[3 * (size_t)i + 2] = 0.0;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) used[half] = n_active; // read by the next evaluation (as its "other half")
+}
+
+} // namespace dsc

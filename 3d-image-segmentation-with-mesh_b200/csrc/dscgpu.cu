@@ -13,6 +13,7 @@
 #include "../../include/dscgpu.h"
 #include "dsc_kernels.cuh"
 #include "dsc_tet_g32.cuh"
+#include "dsc_comm.cuh"
 #include "dsc_tables.h"
 
 using namespace dsc;
@@ -86,6 +87,12 @@ struct dscgpu_ctx {
     int brick_nb[3] = {0, 0, 0};
     float4 *d_lat32 = nullptr;
     unsigned *d_brick_flags = nullptr;
+    // peer-memory exchange (dsc_comm.cuh): this rank's window, the peers' windows as mapped here
+    unsigned char *comm_win[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool comm_ipc[8] = {false, false, false, false, false, false, false, false}; // mapped with cudaIpcOpenMemHandle (to be closed)
+    int comm_rank = 0, comm_world = 0;
+    unsigned comm_cap_rows = 0;
+    bool comm_connected = false;
 
     bool has_snapshot = false;
     uint32_t n_nodes = 0, n_tets = 0, n_faces = 0;
@@ -988,6 +995,28 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
 
 } // namespace
 
+namespace {
+
+CommView comm_view(const dscgpu_ctx *ctx)
+{
+    CommView c;
+    for (int k = 0; k < kCommMaxWorld; k++) c.win[k] = ctx->comm_win[k];
+    c.rank = ctx->comm_rank; c.world = ctx->comm_world; c.cap_rows = ctx->comm_cap_rows;
+    return c;
+}
+
+template <typename VoxT> int launch_force_rows_t(dscgpu_ctx *ctx, const ForceRowsArgs &a)
+{
+    const unsigned n = a.end - a.begin;
+    if (n == 0) return DSCGPU_OK;
+    force_scatter_rows_kernel<VoxT><<<(n + 127) / 128, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+} // namespace
+
 extern "C" {
 
 int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype, const void *voxels_host)
@@ -1096,6 +1125,11 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
     if (ctx->d_tet_bary) cudaFree(ctx->d_tet_bary);
     if (ctx->d_tet_bary_f) cudaFree(ctx->d_tet_bary_f);
     if (ctx->d_tet_lat) cudaFree(ctx->d_tet_lat);
+    for (int k = 0; k < 8; k++) {
+        if (!ctx->comm_win[k]) continue;
+        if (ctx->comm_ipc[k]) cudaIpcCloseMemHandle(ctx->comm_win[k]);
+        else if (k == ctx->comm_rank && ctx->comm_world) cudaFree(ctx->comm_win[k]);
+    }
     if (ctx->d_lat32) cudaFree(ctx->d_lat32);
     if (ctx->d_brick) cudaFree(ctx->d_brick);
     if (ctx->d_brick_flags) cudaFree(ctx->d_brick_flags);
@@ -1646,6 +1680,125 @@ int dscgpu_face_forces_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, 
     NEED_SNAPSHOT();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_mean && d_forces, "bad arguments");
     return run_forces(ctx, nb_phase, d_mean, mode, d_forces);
+}
+
+// ---- peer-memory exchange (dsc_comm.cuh) -------------------------------------------------------------------------------
+
+int dscgpu_comm_create(dscgpu_ctx *ctx, int rank, int world, uint32_t cap_rows, unsigned char handle_out[64])
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(world >= 1 && world <= kCommMaxWorld && rank >= 0 && rank < world, "rank / world out of range (at most 8 ranks)");
+    ARG(cap_rows > 0, "cap_rows must be positive");
+    ARG(!ctx->comm_win[rank] && ctx->comm_world == 0, "the exchange window exists already");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    const size_t bytes = kCommRows + 2 * 3 * (size_t)cap_rows * sizeof(double);
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    CK(cudaMemset(p, 0, bytes));
+    ctx->comm_win[rank] = static_cast<unsigned char *>(p);
+    ctx->comm_rank = rank; ctx->comm_world = world; ctx->comm_cap_rows = cap_rows;
+    ctx->comm_connected = world == 1;
+    if (handle_out) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, p));
+        memcpy(handle_out, &h, 64);
+    }
+    return DSCGPU_OK;
+}
+
+int dscgpu_comm_connect(dscgpu_ctx *ctx, const unsigned char *handles)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(ctx->comm_world >= 1 && handles, "dscgpu_comm_create first");
+    for (int k = 0; k < ctx->comm_world; k++) {
+        if (k == ctx->comm_rank || ctx->comm_win[k]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)k, 64);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->comm_win[k] = static_cast<unsigned char *>(p);
+        ctx->comm_ipc[k] = true;
+    }
+    ctx->comm_connected = true;
+    return DSCGPU_OK;
+}
+
+int dscgpu_comm_connect_local(dscgpu_ctx *ctx, void *const *windows)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(ctx->comm_world >= 1 && windows, "dscgpu_comm_create first");
+    for (int k = 0; k < ctx->comm_world; k++)
+        if (k != ctx->comm_rank) ctx->comm_win[k] = static_cast<unsigned char *>(windows[k]);
+    ctx->comm_connected = true;
+    return DSCGPU_OK;
+}
+
+void *dscgpu_comm_window_dev(dscgpu_ctx *ctx) { return (ctx && ctx->comm_world) ? ctx->comm_win[ctx->comm_rank] : nullptr; }
+
+int dscgpu_comm_error(dscgpu_ctx *ctx)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(ctx->comm_world >= 1, "no exchange window");
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, ctx->comm_win[ctx->comm_rank] + kCommError, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (e) { ctx->err = "peer exchange timed out: a rank did not reach the exchange within 2 s"; return DSCGPU_ERR_CUDA; }
+    return DSCGPU_OK;
+}
+
+int dscgpu_tet_phase_sums_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums, double *d_mean)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_sums, "bad arguments");
+    ARG(ctx->comm_connected, "dscgpu_comm_create / dscgpu_comm_connect first");
+    int r = tet_pass_begin(ctx);
+    if (r) return r;
+    TetPassOut none;
+    {
+        TimerScope ts(ctx, DSCGPU_T_TET);
+        r = tet_pass_range(ctx, nb_phase, 0, 0, nullptr, none, ctx->tet_b, ctx->tet_e, ctx->hot_want_sq);
+        if (r) return r;
+    }
+    TimerScope ts(ctx, DSCGPU_T_PHASE_FINAL);
+    comm_phase_allreduce_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(comm_view(ctx), ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums, d_mean);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+int dscgpu_face_forces_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, double *d_forces)
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_mean && d_forces, "bad arguments");
+    ARG(ctx->comm_connected, "dscgpu_comm_create / dscgpu_comm_connect first");
+    ARG(ctx->n_nodes <= ctx->comm_cap_rows, "the exchange window is too small for this snapshot (cap_rows < n_nodes_buffer)");
+    TimerScope ts(ctx, DSCGPU_T_FORCE);
+    ForceRowsArgs a;
+    a.vol = vol_view(ctx);
+    a.mesh = mesh_view(ctx);
+    a.nb_phase = nb_phase;
+    a.mean = d_mean;
+    a.apos = ctx->csr_apos.as<unsigned>();
+    a.window = ctx->comm_win[ctx->comm_rank];
+    a.cap_rows = ctx->comm_cap_rows;
+    a.begin = ctx->face_b; a.end = ctx->face_e;
+    int r;
+    switch (ctx->dtype) {
+    case DSCGPU_U8: r = launch_force_rows_t<unsigned char>(ctx, a); break;
+    case DSCGPU_U16: r = launch_force_rows_t<unsigned short>(ctx, a); break;
+    case DSCGPU_F32: r = launch_force_rows_t<float>(ctx, a); break;
+    default: r = launch_force_rows_t<double>(ctx, a); break;
+    }
+    if (r) return r;
+    // rows of nodes without interface faces are never written by the exchange kernel: they must read as zero
+    CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
+    const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * ctx->n_faces);
+    unsigned grid = (std::max<unsigned>(max_active, 1u) + 255) / 256;
+    if (grid > (unsigned)ctx->num_sms * 4) grid = (unsigned)ctx->num_sms * 4;
+    comm_force_allreduce_kernel<<<grid, 256, 0, ctx->stream>>>(comm_view(ctx), ctx->node_active.as<unsigned>(), reinterpret_cast<const unsigned *>(ctr(ctx, 5)), d_forces);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
 }
 
 int dscgpu_enable_timers(dscgpu_ctx *ctx, int on)

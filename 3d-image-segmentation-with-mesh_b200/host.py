@@ -74,6 +74,8 @@ def load_library():
     lib.dscgpu_volume_ptr_dev.restype = C.c_void_p
     lib.dscgpu_sum_table_ptr_dev.restype = C.c_void_p
     lib.dscgpu_forces_pinned.restype = C.POINTER(C.c_double)
+    lib.dscgpu_comm_window_dev.restype = C.c_void_p
+    lib.dscgpu_comm_window_dev.argtypes = [C.c_void_p]
     for name in ("dscgpu_ctx_destroy", "dscgpu_last_error", "dscgpu_set_stream", "dscgpu_synchronize", "dscgpu_build_sum_table",
                  "dscgpu_commit_snapshot", "dscgpu_launch_count", "dscgpu_last_sample_count", "dscgpu_last_gauss_count",
                  "dscgpu_volume_ptr_dev", "dscgpu_sum_table_ptr_dev"):
@@ -373,6 +375,38 @@ class SegmentFunction:
     def face_forces_dev(self, d_mean_ptr, d_forces_ptr, mode=FORCE_GATHER):
         self._img._check(self.lib.dscgpu_face_forces_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_mean_ptr), C.c_int(mode),
                                                          C.c_void_p(d_forces_ptr)), "dscgpu_face_forces_dev")
+
+    # -- exchange over NVLink peer memory (csrc/dsc_comm.cuh) -------------------------------------------------------
+    def comm_create(self, rank, world, cap_rows=None):
+        """Allocates this rank's exchange window (snapshots of up to cap_rows nodes) and returns its CUDA IPC handle (64 bytes)."""
+        cap = int(cap_rows if cap_rows is not None else max(self.n_nodes_buffer, 1))
+        h = (C.c_ubyte * 64)()
+        self._img._check(self.lib.dscgpu_comm_create(self._img._ctx, C.c_int(rank), C.c_int(world), C.c_uint32(cap), h), "dscgpu_comm_create")
+        return bytes(h)
+
+    def comm_connect(self, handles):
+        """handles: the 64-byte IPC handles of all ranks, in rank order (exchanged by the caller)."""
+        buf = b"".join(handles)
+        self._img._check(self.lib.dscgpu_comm_connect(self._img._ctx, C.c_char_p(buf)), "dscgpu_comm_connect")
+
+    def comm_connect_local(self, windows):
+        """Contexts of several ranks inside one process (tests): windows[k] = comm_window() of rank k."""
+        arr = (C.c_void_p * len(windows))(*windows)
+        self._img._check(self.lib.dscgpu_comm_connect_local(self._img._ctx, arr), "dscgpu_comm_connect_local")
+
+    def comm_window(self):
+        return self.lib.dscgpu_comm_window_dev(self._img._ctx)
+
+    def comm_error(self):
+        self._img._check(self.lib.dscgpu_comm_error(self._img._ctx), "dscgpu_comm_error")
+
+    def tet_phase_sums_allreduce_dev(self, d_sums_ptr, d_mean_ptr=None):
+        self._img._check(self.lib.dscgpu_tet_phase_sums_allreduce_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_sums_ptr),
+                                                                      C.c_void_p(d_mean_ptr) if d_mean_ptr else None), "dscgpu_tet_phase_sums_allreduce_dev")
+
+    def face_forces_allreduce_dev(self, d_mean_ptr, d_forces_ptr):
+        self._img._check(self.lib.dscgpu_face_forces_allreduce_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_mean_ptr),
+                                                                   C.c_void_p(d_forces_ptr)), "dscgpu_face_forces_allreduce_dev")
 
     # -- instrumentation --------------------------------------------------------------------------
     def enable_timers(self, on=True):

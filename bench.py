@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: exchange kernels over NVLink peer memory (csrc/dsc_comm.cuh) or two NCCL all-reduces")
     return ap.parse_args()
 
 
@@ -277,6 +279,14 @@ def main_b200(args):
     rng = lambda n: (n * rank // world, n * (rank + 1) // world)
     if world > 1:
         seg.set_partition(rng(n_tets), rng(n_faces), rng(n_nodes))
+    p2p = world > 1 and args.comm == "p2p" and mean_mode == pkg.MEAN_TET
+    if p2p:
+        def gather_handles(h):
+            out = [None] * world
+            dist.all_gather_object(out, h)
+            return out
+        pkg.distributed.connect_peers(seg, rank, world, n_nodes, gather_handles)
+        dist.barrier()  # every window exists and is mapped before the first exchange kernel runs
     d_sums = torch.zeros(3 * P, dtype=torch.float64, device=dev)
     d_mean = torch.zeros(P, dtype=torch.float64, device=dev)
     d_forces = torch.zeros(3 * n_nodes, dtype=torch.float64, device=dev)
@@ -296,6 +306,11 @@ def main_b200(args):
 
     def step_device():
         n0 = seg.launch_count()
+        if p2p:  # tet pass + fused sums exchange, force scatter + fused row exchange: no NCCL, no pack / unpack kernels
+            seg.tet_phase_sums_allreduce_dev(d_sums.data_ptr(), d_mean.data_ptr())
+            seg.face_forces_allreduce_dev(d_mean.data_ptr(), d_forces.data_ptr())
+            launches_per_step[0] = seg.launch_count() - n0
+            return
         if mean_mode == pkg.MEAN_TET:
             seg.tet_phase_sums_dev(d_sums.data_ptr())
         else:
@@ -343,7 +358,7 @@ def main_b200(args):
         try:
             seg.enable_timers(False)
             torch.cuda.synchronize(dev)
-            if world == 1:
+            if world == 1 or p2p:
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1, stream=stream):
                     step_device()
@@ -364,7 +379,7 @@ def main_b200(args):
             seg.enable_timers(True)
 
     def step_graph():
-        if world == 1:
+        if world == 1 or p2p:
             graph[0].replay()
         else:
             graph[0].replay()
@@ -389,6 +404,8 @@ def main_b200(args):
     barrier()
     if graph is not None:
         seg.enable_timers(True)
+    if p2p:
+        seg.comm_error()  # a timed-out exchange would have produced garbage: fail loudly
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     n_samples = seg.last_sample_count()
     n_gauss = seg.last_gauss_count()
@@ -497,6 +514,7 @@ def main_b200(args):
             args.config, cfg["n"], vol.dtype.name, P, n_tets, int((snap["tet_label"] != 0).sum()), n_faces, n_nodes, edge, args.jitter),
             "mean_mode": args.mean_mode, "force_mode": args.force_mode, "launch": "cuda graph replay" if graph is not None else "eager", "l2": "flushed between timed steps (256 MB write)",
             "partition": "tets/faces/nodes split in %d contiguous ranges, volume+snapshot replicated" % world,
+            "comm": ("none" if world == 1 else ("fused exchange kernels over NVLink peer memory (CUDA IPC windows)" if p2p else "2 NCCL all-reduces")),
             "samples_per_step": n_samples_all, "gauss_points_per_step": n_gauss_all},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
                 "steps": e2e_steps},

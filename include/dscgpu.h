@@ -210,6 +210,32 @@ int dscgpu_zray_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums);
 int dscgpu_means_from_sums_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_sums, double *d_mean);
 int dscgpu_face_forces_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, double *d_forces);
 
+/* -- multi-GPU exchange over NVLink peer memory ------------------------------------------------------------------------ */
+
+/* One process per GPU.  The two exchanges of an evaluation (3*nb_phase per-phase sums after the tet pass; the force rows of
+ * the nodes that have interface faces) run as kernels that read the peers' windows directly (csrc/dsc_comm.cuh) instead of
+ * two NCCL all-reduces: same results on every rank (peers are added in rank order), no pack / unpack kernels, and the whole
+ * evaluation can be captured in one CUDA graph.
+ *   dscgpu_comm_create   allocates this rank's window for snapshots of up to cap_rows nodes (n_nodes_buffer) and returns its
+ *                        64-byte CUDA IPC handle; world <= 8
+ *   dscgpu_comm_connect  maps the peers' windows: handles = world x 64 bytes in rank order (exchange them with any host-side
+ *                        all-gather); every rank must have created its window before any rank runs an exchange
+ *   dscgpu_comm_connect_local   the same for contexts that live in ONE process (tests): windows[k] = dscgpu_comm_window_dev
+ *                        of rank k's context
+ *   dscgpu_comm_error    synchronises and reports a timed-out exchange (a peer that never arrived within 2 s) */
+int dscgpu_comm_create(dscgpu_ctx *ctx, int rank, int world, uint32_t cap_rows, unsigned char handle_out[64]);
+int dscgpu_comm_connect(dscgpu_ctx *ctx, const unsigned char *handles);
+int dscgpu_comm_connect_local(dscgpu_ctx *ctx, void *const *windows);
+void *dscgpu_comm_window_dev(dscgpu_ctx *ctx);
+int dscgpu_comm_error(dscgpu_ctx *ctx);
+/* dscgpu_tet_phase_sums_dev over this context's tet partition fused with the all-reduce: d_sums (3*nb_phase) and d_mean
+ * (nb_phase, may be NULL) hold the totals over ALL ranks.  Must be followed by dscgpu_face_forces_allreduce_dev on every rank
+ * (one exchange epoch per evaluation). */
+int dscgpu_tet_phase_sums_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums, double *d_mean);
+/* External forces of this context's face partition (atomic scatter into compact rows) fused with the all-reduce:
+ * d_forces (3*n_nodes_buffer) holds the forces of ALL ranks' faces; 1e-6 parity like DSCGPU_FORCE_ATOMIC. */
+int dscgpu_face_forces_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, double *d_forces);
+
 /* -- instrumentation -------------------------------------------------------------------------- */
 
 enum dscgpu_timer {

@@ -61,6 +61,28 @@ def _worker(rank, world, port, out_dir):
         return t.numpy()
 
     mean, F = pkg.distributed.evaluate(phase_sums, forces, P, all_reduce)
+
+    # handle exchange of the peer-memory path (connect_peers) with a stand-in for the CUDA side: every rank must end up with
+    # all windows in rank order and map exactly the other ranks'
+    class FakeSeg:
+        def __init__(self):
+            self.connected = None
+
+        def comm_create(self, r, w, cap):
+            assert (r, w, cap) == (rank, world, 123)
+            return bytes([r]) * 64
+
+        def comm_connect(self, handles):
+            self.connected = handles
+
+    def all_gather_object(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    fake = FakeSeg()
+    handles = pkg.distributed.connect_peers(fake, rank, world, 123, all_gather_object)
+    assert handles == [bytes([r]) * 64 for r in range(world)] and fake.connected == handles
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), mean=mean, F=F)
     dist.destroy_process_group()
 

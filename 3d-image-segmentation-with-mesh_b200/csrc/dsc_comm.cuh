@@ -4,38 +4,45 @@
 // cross-GPU data are 3*nb_phase per-phase sums (needed by the force pass) and the force rows of the nodes that have
 // interface faces (14 % of the nodes at C4: 1.15 MB).  Both are far below the size where NCCL's bandwidth matters; what a
 // step pays is NCCL's launch and synchronisation latency, twice, plus the pack / unpack kernels around the second call --
-// about 0.1 ms of a 0.19 ms step at 8 GPUs.  Here each exchange is ONE kernel that also does the neighbouring compute:
+// about 0.1 ms of a 0.19 ms step at 8 GPUs.  Here the exchanges are PUSHES: a rank stores its contribution into a slot of
+// every peer's window (posted writes over NVLink: no round trip), then stores its flag there; a rank only ever polls and reads
+// its OWN memory.  (The first form pulled: every thread read eight peers' rows with dependent remote loads and every block
+// polled remote flags -- 0.09 ms for the force exchange at 8 GPUs, slower than NCCL.)
 //
 //   comm_phase_allreduce_kernel  adds this rank's per-CTA partial rows of the tet pass (what tet_finalize_kernel does),
-//                                publishes the 3*nb_phase sums in this rank's window, waits for every peer's flag, adds
-//                                the peers' sums in rank order (the same order on every rank: identical results) and
+//                                pushes the 3*nb_phase sums and the flag to every peer, waits for all flags in its own
+//                                window, adds the slots in rank order (same order on every rank: identical results) and
 //                                writes sums and means.
-//   force_scatter_rows_kernel    force_atomic_kernel scattering into compact rows (one per active node) of this rank's window.
-//   comm_force_allreduce_kernel  raises this rank's flag, waits for the peers', then every thread adds one row of all
-//                                ranks' windows in rank order (16-byte loads over NVLink, L1 bypassed) and stores it into
-//                                the full force array; it also clears the row of the OTHER window half for the next step.
+//   force_scatter_rows_kernel    force_atomic_kernel scattering into compact local rows (one per node with interface faces).
+//   comm_force_push_kernel       copies the local rows into this rank's slot of every window and clears them; the last block
+//                                to finish stores the flags.
+//   comm_force_reduce_kernel     waits for all flags (local polling), then every thread adds one row of all slots in rank
+//                                order and stores it into the full force array.
 //
 // Windows are cudaMalloc'ed per rank and mapped into the peers with CUDA IPC (dscgpu_comm_create / dscgpu_comm_connect).
-// Each window has two halves used by alternating steps (epoch parity): a rank can be one exchange ahead of a slow peer, never
-// two, because it cannot pass exchange e+1 before that peer has published its flag e+1, which it does after its reads of
+// Each window has two halves used by alternating evaluations (epoch parity): a rank can be one exchange ahead of a slow peer,
+// never two, because it cannot pass exchange e+1 before that peer has pushed its flag e+1, which it does after its reads of
 // exchange e.  Flags carry the epoch (monotonic), so nothing is ever reset.  The epoch lives in device memory and is advanced
 // by the kernel itself: the step can be captured in a CUDA graph and replayed.
-// A spin that sees no progress for ~2 s sets an error word instead of hanging the device.
+// A wait that sees no progress for ~2 s sets an error word instead of hanging the device.
 #pragma once
 #include "dsc_kernels.cuh"
 
 namespace dsc {
 
 constexpr int kCommMaxWorld = 8;
-constexpr size_t kCommFlagSums = 0, kCommFlagForce = 128, kCommEpoch = 256, kCommError = 320, kCommUsedRows = 384, kCommSums = 512, kCommRows = 1024;
-// [0,64) [64,128) flag of the sums exchange, one per half; [128,256) flags of the force exchange; 256 epoch; 320 error;
-// 384 rows written into each half by its last use (2 x unsigned); [512,896) 2 x 24 doubles; from 1024 on: 2 x cap_rows x 3 doubles
+// window layout (bytes): flags of the sums exchange [2 halves][8 ranks] x 8 B at 0; of the force exchange at 128; epoch 256;
+// error 264; push-kernel block counter 272; sums slots [2][8][24] doubles at 512 (3072 B); rows slots [2][world][3 cap_rows] at 4096
+constexpr size_t kCommFlagSums = 0, kCommFlagForce = 128, kCommEpoch = 256, kCommError = 264, kCommDone = 272, kCommSums = 512, kCommRows = 4096;
 
 struct CommView {
     unsigned char *win[kCommMaxWorld]; // window of every rank as mapped here; win[rank] is this rank's own
     int rank, world;
     unsigned cap_rows;
 };
+
+DSC_HD size_t comm_window_bytes(int world, unsigned cap_rows) { return kCommRows + 2 * (size_t)world * 3 * cap_rows * sizeof(double); }
+DSC_HD size_t comm_rows_offset(int half, int slot, int world, unsigned cap_rows) { return kCommRows + ((size_t)half * world + slot) * 3 * cap_rows * sizeof(double); }
 
 DSC_D unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
@@ -45,7 +52,7 @@ DSC_D unsigned long long ld_acquire_sys(const unsigned long long *p)
 }
 DSC_D void st_release_sys(unsigned long long *p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
-// waits until the flag at p reaches epoch e; false (and the error word set) after ~2 s without success
+// waits until the (local) flag at p reaches epoch e; false (and the error word set) after ~2 s without success
 DSC_D bool comm_wait(const unsigned long long *p, unsigned long long e, int *err)
 {
     const long long t0 = clock64();
@@ -54,7 +61,6 @@ DSC_D bool comm_wait(const unsigned long long *p, unsigned long long e, int *err
             *err = 1;
             return false;
         }
-        __nanosleep(64);
     }
     return true;
 }
@@ -78,16 +84,18 @@ __global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kerne
     __syncthreads();
     const unsigned long long e = s_epoch;
     const int half = (int)(e & 1);
-    if (lane == 0) reinterpret_cast<double *>(mine + kCommSums)[half * 3 * kMaxPhase + col] = r;
+    // push: lane k of every column warp stores the column's sum into this rank's slot of rank k's window
+    if (lane < c.world) reinterpret_cast<double *>(c.win[lane] + kCommSums)[((size_t)half * kCommMaxWorld + c.rank) * 3 * kMaxPhase + col] = r;
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned long long *>(mine + kCommFlagSums + 64 * half), e);
-    if (threadIdx.x < c.world) comm_wait(reinterpret_cast<const unsigned long long *>(c.win[threadIdx.x] + kCommFlagSums + 64 * half), e,
-                                         reinterpret_cast<int *>(mine + kCommError));
+    if (threadIdx.x < c.world) {
+        st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommFlagSums) + half * kCommMaxWorld + c.rank, e);
+        comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommFlagSums) + half * kCommMaxWorld + threadIdx.x, e, reinterpret_cast<int *>(mine + kCommError));
+    }
     __syncthreads();
     if (lane == 0) {
         double t = 0;
-        for (int k = 0; k < c.world; k++) t += __ldcv(reinterpret_cast<const double *>(c.win[k] + kCommSums) + half * 3 * kMaxPhase + col);
+        for (int k = 0; k < c.world; k++) t += __ldcv(reinterpret_cast<const double *>(mine + kCommSums) + ((size_t)half * kCommMaxWorld + k) * 3 * kMaxPhase + col);
         const int which = col / kMaxPhase, ph = col % kMaxPhase;
         if (ph < nb_phase) sums[which * nb_phase + ph] = t;
         if (which == 0) tot[ph] = t;
@@ -103,18 +111,15 @@ struct ForceRowsArgs {
     int nb_phase;
     const double *mean;
     const unsigned *apos;       // node -> row (exclusive scan of "has interface faces")
-    unsigned char *window;      // this rank's window
-    unsigned cap_rows;
+    double *rows;               // local rows, 3 per active node, zero on entry
     unsigned begin, end;        // faces of this rank
 };
 
-// force_atomic_kernel with compact destination rows in the half of the window that belongs to the current epoch
+// force_atomic_kernel with compact destination rows
 template <typename VoxT> __global__ void __launch_bounds__(128) force_scatter_rows_kernel(const ForceRowsArgs a)
 {
     const unsigned f = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= a.end) return;
-    const unsigned long long e = *reinterpret_cast<const unsigned long long *>(a.window + kCommEpoch);
-    double *rows = reinterpret_cast<double *>(a.window + kCommRows) + (size_t)(e & 1) * 3 * a.cap_rows;
     const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
     FaceGeom g;
     unsigned n[3];
@@ -131,55 +136,62 @@ template <typename VoxT> __global__ void __launch_bounds__(128) force_scatter_ro
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        double *dst = rows + 3 * (size_t)a.apos[n[k]];
+        double *dst = a.rows + 3 * (size_t)a.apos[n[k]];
         atomicAdd(dst, acc[k][0]);
         atomicAdd(dst + 1, acc[k][1]);
         atomicAdd(dst + 2, acc[k][2]);
     }
 }
 
-// rows of all ranks added in rank order into the full force array (which is zero everywhere else)
-__global__ void __launch_bounds__(256) comm_force_allreduce_kernel(CommView c, const unsigned *__restrict__ active_nodes, const unsigned *__restrict__ n_active_ptr,
-                                                                   double *__restrict__ forces)
+// local rows -> this rank's slot in every window (and cleared for the next evaluation); the last block stores the flags
+__global__ void __launch_bounds__(256) comm_force_push_kernel(CommView c, double *__restrict__ rows, const unsigned *__restrict__ n_active_ptr)
 {
     unsigned char *mine = c.win[c.rank];
     const unsigned long long e = *reinterpret_cast<const unsigned long long *>(mine + kCommEpoch);
     const int half = (int)(e & 1);
-    // every block raises the flag (same value: idempotent) so that no block depends on another block being scheduled
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned long long *>(mine + kCommFlagForce + 64 * half), e);
+    const size_t n = 3 * (size_t)min(*n_active_ptr, c.cap_rows);
+    const size_t off = comm_rows_offset(half, c.rank, c.world, c.cap_rows);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = rows[i];
+        rows[i] = 0.0;
+        for (int k = 0; k < c.world; k++) reinterpret_cast<double *>(c.win[k] + off)[i] = v;
     }
-    if (threadIdx.x < c.world) comm_wait(reinterpret_cast<const unsigned long long *>(c.win[threadIdx.x] + kCommFlagForce + 64 * half), e,
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned *>(mine + kCommDone), 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *reinterpret_cast<unsigned *>(mine + kCommDone) = 0u;
+        __threadfence_system();
+        if (threadIdx.x < c.world) st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommFlagForce) + half * kCommMaxWorld + c.rank, e);
+    }
+}
+
+// slots of all ranks added in rank order into the full force array (which is zero everywhere else)
+__global__ void __launch_bounds__(256) comm_force_reduce_kernel(CommView c, const unsigned *__restrict__ active_nodes, const unsigned *__restrict__ n_active_ptr,
+                                                                double *__restrict__ forces)
+{
+    unsigned char *mine = c.win[c.rank];
+    const unsigned long long e = *reinterpret_cast<const unsigned long long *>(mine + kCommEpoch);
+    const int half = (int)(e & 1);
+    if (threadIdx.x < c.world) comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommFlagForce) + half * kCommMaxWorld + threadIdx.x, e,
                                          reinterpret_cast<int *>(mine + kCommError));
     __syncthreads();
     const unsigned n_active = min(*n_active_ptr, c.cap_rows);
-    unsigned *used = reinterpret_cast<unsigned *>(mine + kCommUsedRows);
-    const unsigned n_clear = used[half ^ 1]; // rows the other half received when it was last used (a different snapshot, possibly)
-    const size_t off_cur = kCommRows + (size_t)half * 3 * c.cap_rows * sizeof(double);
-    double *next = reinterpret_cast<double *>(mine + kCommRows) + (size_t)(half ^ 1) * 3 * c.cap_rows;
-    const unsigned n_loop = max(n_active, n_clear);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_loop; i += gridDim.x * blockDim.x) {
-        if (i < n_active) {
-            double x = 0, y = 0, z = 0;
-            for (int k = 0; k < c.world; k++) {
-                const double *src = reinterpret_cast<const double *>(c.win[k] + off_cur) + 3 * (size_t)i;
-                x += __ldcv(src);
-                y += __ldcv(src + 1);
-                z += __ldcv(src + 2);
-            }
-            const size_t node = active_nodes[i];
-            forces[3 * node] = x;
-            forces[3 * node + 1] = y;
-            forces[3 * node + 2] = z;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_active; i += gridDim.x * blockDim.x) {
+        double x = 0, y = 0, z = 0;
+        for (int k = 0; k < c.world; k++) {
+            const double *src = reinterpret_cast<const double *>(mine + comm_rows_offset(half, k, c.world, c.cap_rows)) + 3 * (size_t)i;
+            x += __ldcv(src);
+            y += __ldcv(src + 1);
+            z += __ldcv(src + 2);
         }
-        if (i < n_clear) { // the other half is idle until the next evaluation: clear it for its next use
-            next[3 * (size_t)i] = 0.0;
-            next[3 * (size_t)i + 1] = 0.0;
-            next[3 * (size_t)i + 2] = 0.0;
-        }
+        const size_t node = active_nodes[i];
+        forces[3 * node] = x;
+        forces[3 * node + 1] = y;
+        forces[3 * node + 2] = z;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) used[half] = n_active; // read by the next evaluation (as its "other half")
 }
 
 } // namespace dsc

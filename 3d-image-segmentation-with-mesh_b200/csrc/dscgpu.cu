@@ -93,6 +93,7 @@ struct dscgpu_ctx {
     int comm_rank = 0, comm_world = 0;
     unsigned comm_cap_rows = 0;
     bool comm_connected = false;
+    double *comm_rows = nullptr; // local scatter target of the force exchange: 3 doubles per active node, zero between evaluations
 
     bool has_snapshot = false;
     uint32_t n_nodes = 0, n_tets = 0, n_faces = 0;
@@ -1130,6 +1131,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
         if (ctx->comm_ipc[k]) cudaIpcCloseMemHandle(ctx->comm_win[k]);
         else if (k == ctx->comm_rank && ctx->comm_world) cudaFree(ctx->comm_win[k]);
     }
+    if (ctx->comm_rows) cudaFree(ctx->comm_rows);
     if (ctx->d_lat32) cudaFree(ctx->d_lat32);
     if (ctx->d_brick) cudaFree(ctx->d_brick);
     if (ctx->d_brick_flags) cudaFree(ctx->d_brick_flags);
@@ -1691,10 +1693,12 @@ int dscgpu_comm_create(dscgpu_ctx *ctx, int rank, int world, uint32_t cap_rows, 
     ARG(cap_rows > 0, "cap_rows must be positive");
     ARG(!ctx->comm_win[rank] && ctx->comm_world == 0, "the exchange window exists already");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    const size_t bytes = kCommRows + 2 * 3 * (size_t)cap_rows * sizeof(double);
+    const size_t bytes = comm_window_bytes(world, cap_rows);
     void *p = nullptr;
     CK(cudaMalloc(&p, bytes));
     CK(cudaMemset(p, 0, bytes));
+    CK(cudaMalloc(&ctx->comm_rows, 3 * (size_t)cap_rows * sizeof(double)));
+    CK(cudaMemset(ctx->comm_rows, 0, 3 * (size_t)cap_rows * sizeof(double)));
     ctx->comm_win[rank] = static_cast<unsigned char *>(p);
     ctx->comm_rank = rank; ctx->comm_world = world; ctx->comm_cap_rows = cap_rows;
     ctx->comm_connected = world == 1;
@@ -1779,8 +1783,7 @@ int dscgpu_face_forces_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, const double
     a.nb_phase = nb_phase;
     a.mean = d_mean;
     a.apos = ctx->csr_apos.as<unsigned>();
-    a.window = ctx->comm_win[ctx->comm_rank];
-    a.cap_rows = ctx->comm_cap_rows;
+    a.rows = ctx->comm_rows;
     a.begin = ctx->face_b; a.end = ctx->face_e;
     int r;
     switch (ctx->dtype) {
@@ -1793,9 +1796,14 @@ int dscgpu_face_forces_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, const double
     // rows of nodes without interface faces are never written by the exchange kernel: they must read as zero
     CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
     const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * ctx->n_faces);
-    unsigned grid = (std::max<unsigned>(max_active, 1u) + 255) / 256;
+    const unsigned *n_active = reinterpret_cast<const unsigned *>(ctr(ctx, 5));
+    unsigned grid = (3 * std::max<unsigned>(max_active, 1u) + 255) / 256;
     if (grid > (unsigned)ctx->num_sms * 4) grid = (unsigned)ctx->num_sms * 4;
-    comm_force_allreduce_kernel<<<grid, 256, 0, ctx->stream>>>(comm_view(ctx), ctx->node_active.as<unsigned>(), reinterpret_cast<const unsigned *>(ctr(ctx, 5)), d_forces);
+    comm_force_push_kernel<<<grid, 256, 0, ctx->stream>>>(comm_view(ctx), ctx->comm_rows, n_active);
+    ctx->launches++;
+    grid = (std::max<unsigned>(max_active, 1u) + 255) / 256;
+    if (grid > (unsigned)ctx->num_sms * 4) grid = (unsigned)ctx->num_sms * 4;
+    comm_force_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(comm_view(ctx), ctx->node_active.as<unsigned>(), n_active, d_forces);
     ctx->launches++;
     CK(cudaGetLastError());
     return DSCGPU_OK;

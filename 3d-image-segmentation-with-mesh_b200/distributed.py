@@ -16,6 +16,25 @@ def partition(n, world, rank):
     return n * rank // world, n * (rank + 1) // world
 
 
+def balanced_cuts(cost, world):
+    """Cut points [0, c1, ..., n] of `world` contiguous ranges with (nearly) equal total cost: range r is [cuts[r], cuts[r+1]).
+    `cost` is a non-negative array with one entry per item (e.g. the sample count of a tet, ~0 for label-0 tets)."""
+    cost = np.asarray(cost, np.float64)
+    n = len(cost)
+    if world < 1:
+        raise ValueError("bad world")
+    total = cost.sum()
+    if n == 0 or total <= 0:
+        return [n * r // world for r in range(world + 1)]
+    cum = np.cumsum(cost)
+    cuts = [0]
+    for r in range(1, world):
+        c = int(np.searchsorted(cum, total * r / world, side="left")) + 1
+        cuts.append(min(max(c, cuts[-1]), n))
+    cuts.append(n)
+    return cuts
+
+
 def partitions(n_tets, n_faces, n_nodes, world, rank):
     return partition(n_tets, world, rank), partition(n_faces, world, rank), partition(n_nodes, world, rank)
 

@@ -249,7 +249,7 @@ def main_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, where exactly one JSON line is expected
+            del os.environ["NCCL_DEBUG"]  # the image's default prints a version banner to stdout, where exactly one JSON line is expected
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
@@ -279,8 +279,16 @@ def main_b200(args):
     seg.set_snapshot(snap)
     # weak scaling is not what north_star asks for C4 (fixed 2M-tet mesh split over N GPUs): strong scaling
     rng = lambda n: (n * rank // world, n * (rank + 1) // world)
+    tet_range = rng(n_tets)
     if world > 1:
-        seg.set_partition(rng(n_tets), rng(n_faces), rng(n_nodes))
+        # tets are cut by work, not by count: label-0 tets (the boundary layer, 8 % here, clustered at the ends and sides of the
+        # tet array) cost almost nothing and a tet's cost is its sample count n^3 (DEMO/image3d.cpp:355-357: n = floor(cbrt(volume)))
+        vol_t = seg.tet_integrate(include_bound=True)["vol"]
+        n_lvl = np.clip(np.floor(np.cbrt(np.maximum(vol_t, 0.0)) + 1e-9), 1, 9)
+        cost = np.where(snap["tet_label"] != 0, n_lvl ** 3 + 20.0, 0.5)
+        cuts = pkg.distributed.balanced_cuts(cost, world)
+        tet_range = (cuts[rank], cuts[rank + 1])
+        seg.set_partition(tet_range, rng(n_faces), rng(n_nodes))
     p2p = world > 1 and args.comm == "p2p" and mean_mode == pkg.MEAN_TET
     if p2p:
         def gather_handles(h):
@@ -448,7 +456,7 @@ def main_b200(args):
         else:
             seg.staging(n_nodes, n_tets, n_faces)
             seg.commit_snapshot()
-            seg.set_partition(rng(n_tets), rng(n_faces), rng(n_nodes))
+            seg.set_partition(tet_range, rng(n_faces), rng(n_nodes))
             step_device()
             pinned_forces.copy_(d_forces, non_blocking=True)
             pinned_mean.copy_(d_mean, non_blocking=True)
@@ -515,7 +523,7 @@ def main_b200(args):
         "config": {"workload": "%s: %d^3 %s %d-phase phantom, %d tets (%d labelled), %d interface faces, %d nodes, grid mesh edge %.3f jitter %.2f" % (
             args.config, cfg["n"], vol.dtype.name, P, n_tets, int((snap["tet_label"] != 0).sum()), n_faces, n_nodes, edge, args.jitter),
             "mean_mode": args.mean_mode, "force_mode": args.force_mode, "launch": "cuda graph replay" if graph is not None else "eager", "l2": "flushed between timed steps (256 MB write)",
-            "partition": "tets/faces/nodes split in %d contiguous ranges, volume+snapshot replicated" % world,
+            "partition": "tets (cut by sample count) / faces / nodes split in %d contiguous ranges, volume+snapshot replicated" % world,
             "comm": ("none" if world == 1 else ("fused exchange kernels over NVLink peer memory (CUDA IPC windows)" if p2p else "2 NCCL all-reduces")),
             "samples_per_step": n_samples_all, "gauss_points_per_step": n_gauss_all},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,

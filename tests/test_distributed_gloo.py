@@ -100,6 +100,21 @@ def test_partition_covers_everything(pkg):
         pkg.distributed.partition(10, 2, 2)
 
 
+def test_balanced_cuts(pkg):
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 5, 1000, 100000):
+        cost = rng.integers(0, 730, n).astype(float)
+        cost[rng.uniform(size=n) < 0.1] = 0.0
+        for world in (1, 2, 3, 8):
+            cuts = pkg.distributed.balanced_cuts(cost, world)
+            assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == n
+            assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+            if n >= 1000:
+                loads = [cost[a:b].sum() for a, b in zip(cuts, cuts[1:])]
+                assert max(loads) - min(loads) <= 2 * 729 + 1e-9
+    assert pkg.distributed.balanced_cuts(np.zeros(10), 2) == [0, 5, 10]
+
+
 def test_two_rank_evaluation_equals_single_rank(pkg, flat, tmp_path):
     world = 2
     port = _free_port()

@@ -2621,6 +2621,73 @@ __global__ void vertex_bound_kernel(MeshView m, unsigned char *vb)
     }
 }
 
+// =================================================================================================
+// Internal (curvature) force: segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232), SURVEY 8(f) row 3.
+// Two kernels like the external force, so that every node adds its terms in the reference's order (faces ascending) without
+// atomics:
+//   iforce_face_kernel  thread per interface face: the three corner terms -h |l2 - l1|, h = normalize(l0 - proj(l0 on l1 l2))
+//                       (is_mesh/util.h:395-399), skipped when all three nodes are vertex-bound (segment_function::is_boundary(
+//                       FaceKey), :2186-2196), and the face normal get_normal(fid) (src/DSC.h:3129-3133) for the node normals;
+//   iforce_node_kernel  thread per node that has interface faces: ordered sums over its CSR entries, then for interface,
+//                       non-crossing nodes with |f| > EPSILON the projection f = n dot(n, f) on the node normal
+//                       (DSC::get_normal(node), src/DSC.h:3138-3159; the reference adds the face normals in get_faces(node)
+//                       order, here ascending faces: the unprojected sums are bit-identical, the projected ones agree to rounding).
+// =================================================================================================
+__global__ void __launch_bounds__(128) iforce_face_kernel(MeshView m, const unsigned char *__restrict__ vb, double *__restrict__ fterm, double *__restrict__ fnorm,
+                                                          unsigned char *__restrict__ fskip)
+{
+    const unsigned f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.n_faces) return;
+    const unsigned n0 = __ldg(m.face_nodes + 3 * (size_t)f), n1 = __ldg(m.face_nodes + 3 * (size_t)f + 1), n2 = __ldg(m.face_nodes + 3 * (size_t)f + 2);
+    const unsigned t0 = __ldg(m.face_tets + 2 * (size_t)f), t1 = __ldg(m.face_tets + 2 * (size_t)f + 1);
+    // get_normal(fid): sorted w.r.t. the co-boundary tet with the highest label, first wins (is_mesh/is_mesh.h:639-663)
+    unsigned tid = t0;
+    if (t0 == kNoTet) tid = t1;
+    else if (t1 != kNoTet && __ldg(m.tet_label + t1) > __ldg(m.tet_label + t0)) tid = t1;
+    V3 N = {0, 0, 0};
+    if (tid != kNoTet) N = face_normal_wrt(m, n0, n1, n2, __ldg(m.tet_nodes + tid));
+    fnorm[3 * (size_t)f] = N.x; fnorm[3 * (size_t)f + 1] = N.y; fnorm[3 * (size_t)f + 2] = N.z;
+    const bool skip = vb[n0] && vb[n1] && vb[n2];
+    fskip[f] = skip ? 1 : 0;
+    if (skip) return;
+    const V3 p[3] = {load_pos(m.pos4, n0), load_pos(m.pos4, n1), load_pos(m.pos4, n2)};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const V3 l0 = p[i], l1 = p[(i + 1) % 3], l2 = p[(i + 2) % 3];
+        const V3 v = sub(l2, l1), v1 = sub(l0, l1);
+        const V3 proj = add(l1, divs(mul(v, dot(v1, v)), dot(v, v))); // a + v * dot(v1,v) / dot(v,v)
+        const V3 h = normalize(sub(l0, proj));
+        const V3 t = mul(mul(h, -1.0), length(v)); // -h * (l2 - l1).length()
+        double *o = fterm + 9 * (size_t)f + 3 * i;
+        o[0] = t.x; o[1] = t.y; o[2] = t.z;
+    }
+}
+
+__global__ void __launch_bounds__(128) iforce_node_kernel(MeshView m, const unsigned *__restrict__ active_nodes, const unsigned *__restrict__ n_active,
+                                                          const unsigned char *__restrict__ node_flags, const double *__restrict__ fterm,
+                                                          const double *__restrict__ fnorm, const unsigned char *__restrict__ fskip, double *__restrict__ out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_active) return;
+    const unsigned n = active_nodes[i];
+    V3 F = {0, 0, 0}, S = {0, 0, 0};
+    for (unsigned k = m.node_off[n]; k < m.node_off[n + 1]; k++) {
+        const unsigned e = m.node_inc[k], f = e >> 2, c = e & 3u;
+        S = add(S, V3{fnorm[3 * (size_t)f], fnorm[3 * (size_t)f + 1], fnorm[3 * (size_t)f + 2]});
+        if (!fskip[f]) {
+            const double *t = fterm + 9 * (size_t)f + 3 * c;
+            F = add(F, V3{t[0], t[1], t[2]});
+        }
+    }
+    const unsigned char fl = node_flags[n];
+    if ((fl & 1) && !(fl & 2) && length(F) > 1e-8) { // is_interface && !is_crossing && |f| > EPSILON (is_mesh/util.h:43)
+        V3 norm = {0, 0, 0};
+        if (!(length(S) < 1e-8)) norm = normalize(S);
+        F = mul(norm, dot(norm, F));
+    }
+    out[3 * (size_t)n] = F.x; out[3 * (size_t)n + 1] = F.y; out[3 * (size_t)n + 2] = F.z;
+}
+
 // alpha * sum of areas of interface faces whose nodes are not all vertex-bound (:2482-2489);
 // one partial per CTA, added in CTA order by the caller's finalize.
 __global__ void __launch_bounds__(256) area_term_kernel(MeshView m, const unsigned char *vb, double alpha, double *partials)

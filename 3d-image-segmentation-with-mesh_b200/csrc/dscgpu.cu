@@ -109,7 +109,7 @@ struct dscgpu_ctx {
 
     DevBuf partials, sums, mean, forces, counters;
     DevBuf o_total, o_vol, o_mean, o_energy, o_variation, o_hash, o_nsamp;
-    DevBuf ray_count, ray_offset, ray_cursor, hits, block_sums, ray_psum, ray_pcnt, misc, vbound, pit;
+    DevBuf ray_count, ray_offset, ray_cursor, hits, block_sums, ray_psum, ray_pcnt, misc, vbound, pit, nflags, iterm, inorm, iskip, iforce;
 
     cudaEvent_t ev[DSCGPU_T_COUNT][2];
     bool ev_used[DSCGPU_T_COUNT];
@@ -1113,7 +1113,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_OK;
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    DevBuf *bufs[] = {&ctx->tet_face_nodes, &ctx->tet_face_tets, &ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
+    DevBuf *bufs[] = {&ctx->nflags, &ctx->iterm, &ctx->inorm, &ctx->iskip, &ctx->iforce, &ctx->tet_face_nodes, &ctx->tet_face_tets, &ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
                       &ctx->partials, &ctx->sums, &ctx->mean, &ctx->forces, &ctx->counters, &ctx->o_total, &ctx->o_vol, &ctx->o_mean, &ctx->o_energy,
                       &ctx->o_variation, &ctx->o_hash, &ctx->o_nsamp, &ctx->ray_count, &ctx->ray_offset, &ctx->ray_cursor, &ctx->hits, &ctx->block_sums,
                       &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
@@ -1555,6 +1555,41 @@ int dscgpu_zray_energy(dscgpu_ctx *ctx, int nb_phase, const double *mean, double
     }
     if (energy_area) *energy_area = area;
     return DSCGPU_OK;
+}
+
+int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uint8_t *vertex_bound, double *internal_forces)
+{
+    NEED_SNAPSHOT();
+    ARG(node_flags && internal_forces, "node_flags and internal_forces are required");
+    const size_t nn = ctx->n_nodes, nf = ctx->n_faces;
+    int r;
+    if (vertex_bound) {
+        CK(ctx->vbound.ensure(nn + 1));
+        CK(cudaMemcpyAsync(ctx->vbound.p, vertex_bound, nn, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        r = dscgpu_vertex_bound(ctx, nullptr);
+        if (r) return r;
+    }
+    CK(ctx->nflags.ensure(nn + 1));
+    CK(ctx->iforce.ensure(3 * nn * sizeof(double) + 8));
+    CK(ctx->iterm.ensure(9 * nf * sizeof(double) + 8));
+    CK(ctx->inorm.ensure(3 * nf * sizeof(double) + 8));
+    CK(ctx->iskip.ensure(nf + 1));
+    if (nn) CK(cudaMemcpyAsync(ctx->nflags.p, node_flags, nn, cudaMemcpyHostToDevice, ctx->stream));
+    // nodes without interface faces keep a zero force (the reference's vector is zero-initialised, :2199)
+    if (nn) CK(cudaMemsetAsync(ctx->iforce.p, 0, 3 * nn * sizeof(double), ctx->stream));
+    if (nf) {
+        iforce_face_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, ctx->stream>>>(mesh_view(ctx), ctx->vbound.as<unsigned char>(), ctx->iterm.as<double>(),
+                                                                                ctx->inorm.as<double>(), ctx->iskip.as<unsigned char>());
+        const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * ctx->n_faces);
+        iforce_node_kernel<<<(max_active + 127) / 128, 128, 0, ctx->stream>>>(mesh_view(ctx), ctx->node_active.as<unsigned>(), reinterpret_cast<const unsigned *>(ctr(ctx, 5)),
+                                                                             ctx->nflags.as<unsigned char>(), ctx->iterm.as<double>(), ctx->inorm.as<double>(),
+                                                                             ctx->iskip.as<unsigned char>(), ctx->iforce.as<double>());
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+    }
+    if (nn) CK(cudaMemcpyAsync(internal_forces, ctx->iforce.p, 3 * nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_and_check(ctx);
 }
 
 int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mode, double *forces)

@@ -186,6 +186,7 @@ class SegmentFunction:
         self._phase_volume = None
         self._phase_sumsq = None
         self._forces = None
+        self._internal_forces = None
         self.n_nodes_buffer = self.n_tets = self.n_faces = 0
         self._keep = None
 
@@ -313,6 +314,24 @@ class SegmentFunction:
         self._img._check(self.lib.dscgpu_face_forces(self._img._ctx, C.c_int(self.NB_PHASE), _ptr(m), C.c_int(mode), _ptr(f)), "dscgpu_face_forces")
         self._forces = f
         return f
+
+    def compute_internal_force_2(self, node_flags, vertex_bound=None):
+        """segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232).  node_flags: bit 0 is_interface,
+        bit 1 is_crossing per node (is_mesh attributes)."""
+        nf = np.ascontiguousarray(node_flags, np.uint8)
+        if len(nf) != self.n_nodes_buffer:
+            raise ValueError("node_flags must have one byte per node of the buffer")
+        vb = None if vertex_bound is None else np.ascontiguousarray(vertex_bound, np.uint8)
+        f = np.empty((self.n_nodes_buffer, 3))
+        self._img._check(self.lib.dscgpu_internal_forces(self._img._ctx, _ptr(nf), _ptr(vb), _ptr(f)), "dscgpu_internal_forces")
+        self._internal_forces = f
+        return f
+
+    def get_node_displacements(self, dt, forces=None, internal_forces=None):
+        """segment_function::get_node_displacement for every node (DEMO/segment_function.cpp:581-584)."""
+        F = self._forces if forces is None else forces
+        Fi = self._internal_forces if internal_forces is None else internal_forces
+        return (F + self.m_alpha * Fi) * dt
 
     def compute_energy(self, mean=None, vertex_bound=None):
         """segment_function::compute_energy (DEMO/segment_function.cpp:2331-2492): (data, alpha*area)."""

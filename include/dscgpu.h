@@ -186,6 +186,17 @@ enum dscgpu_force_mode {
  * 3*n_nodes_buffer doubles indexed by raw node key (= _forces). */
 int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mode, double *forces);
 
+/* SURVEY 8(f) row 3 -- segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232), the curvature force
+ * segment() evaluates next to the external force every iteration (:2246): internal_forces is 3*n_nodes_buffer doubles indexed by
+ * raw node key (= _internal_forces); get_node_displacement is (forces + alpha*internal_forces)*dt (:581-584).
+ *   node_flags    n_nodes_buffer bytes: bit 0 NodeAttributes::is_interface(), bit 1 is_crossing() (is_mesh/attributes.h:84-102).
+ *                 is_crossing comes from connected components of the tets around a node (is_mesh/is_mesh.h:523-573): topology,
+ *                 kept by the host; reading the attribute is free.
+ *   vertex_bound  n_nodes_buffer bytes (m_vertex_bound) or NULL to derive it from the snapshot like dscgpu_vertex_bound.
+ * Nodes that are not projected (crossing, or not interface) are bit-identical to the reference; projected ones agree to
+ * rounding (the node normal adds the face normals in ascending face order, the reference in get_faces(node) order). */
+int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uint8_t *vertex_bound, double *internal_forces);
+
 /* -- fused evaluation and device-resident variants ------------------------------------------- */
 
 enum dscgpu_mean_mode { DSCGPU_MEAN_TET = 0, DSCGPU_MEAN_ZRAY = 1 };

@@ -10,7 +10,9 @@
 //       segment_function::update_average_intensity   (DEMO/segment_function.cpp:1600-1764)
 //       segment_function::compute_external_force     (DEMO/segment_function.cpp:1425-1473)
 //       segment_function::compute_energy             (DEMO/segment_function.cpp:2331-2492)
-//     that write the reference's public result members (_mean_intensities, _total_intensities, _phase_volume, _forces).
+//       segment_function::compute_internal_force_2   (DEMO/segment_function.cpp:2197-2232)
+//     that write the reference's public result members (_mean_intensities, _total_intensities, _phase_volume, _forces,
+//     _internal_forces).
 // INTEGRATION.md shows the three-line patch to DEMO/segment_function.cpp that routes segment() through it.
 #pragma once
 #include <cstdint>
@@ -31,6 +33,7 @@ struct Snapshot {
     std::vector<uint32_t> face_nodes;   // 3 per face, get_nodes(f) order
     std::vector<uint32_t> face_tets;    // 2 per face: indices into the tet arrays, get_tets(f) order
     std::vector<uint8_t> face_is_boundary;
+    std::vector<uint8_t> node_flags;    // per node of the buffer: bit 0 is_interface(), bit 1 is_crossing() (is_mesh/attributes.h:84-102)
 
     dscgpu_snapshot view() const
     {
@@ -53,10 +56,12 @@ template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s)
 {
     const unsigned nnb = dsc.get_no_nodes_buffer();
     s.pos.assign(3 * (size_t)nnb, 0.0);
+    s.node_flags.assign(nnb, 0);
     for (auto nit = dsc.nodes_begin(); nit != dsc.nodes_end(); nit++) {
         const unsigned k = nit.key();
         const auto p = dsc.get_pos(nit.key());
         s.pos[3 * (size_t)k] = p[0]; s.pos[3 * (size_t)k + 1] = p[1]; s.pos[3 * (size_t)k + 2] = p[2];
+        s.node_flags[k] = (uint8_t)((nit->is_interface() ? 1 : 0) | (nit->is_crossing() ? 2 : 0));
     }
     std::vector<int32_t> tet_index(dsc.get_no_tets_buffer(), -1);
     s.tet_key.clear(); s.tet_nodes.clear(); s.tet_label.clear();
@@ -126,6 +131,20 @@ public:
         seg._forces.resize(nnb);
         for (size_t i = 0; i < nnb; i++) {
             seg._forces[i][0] = forces_[3 * i]; seg._forces[i][1] = forces_[3 * i + 1]; seg._forces[i][2] = forces_[3 * i + 2];
+        }
+    }
+
+    // Body of segment_function::compute_internal_force_2; m_vertex_bound is read from seg (update_vertex_boundary ran before).
+    void compute_internal_force_2(SEG &seg)
+    {
+        const size_t nnb = snap_.pos.size() / 3;
+        forces_.resize(3 * nnb);
+        std::vector<uint8_t> vb(nnb, 0);
+        for (size_t i = 0; i < nnb && i < seg.m_vertex_bound.size(); i++) vb[i] = seg.m_vertex_bound[i] ? 1 : 0;
+        check(dscgpu_internal_forces(ctx_, snap_.node_flags.data(), vb.data(), forces_.data()), "dscgpu_internal_forces");
+        seg._internal_forces.resize(nnb);
+        for (size_t i = 0; i < nnb; i++) {
+            seg._internal_forces[i][0] = forces_[3 * i]; seg._internal_forces[i][1] = forces_[3 * i + 1]; seg._internal_forces[i][2] = forces_[3 * i + 2];
         }
     }
 

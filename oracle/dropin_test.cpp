@@ -3,7 +3,7 @@
 // The drop-in demonstration: the UNMODIFIED reference sources (same objects as oracle/_ref/dsc_ref) and the product's
 // C ABI (libdscgpu.so, through include/dscgpu_adapter.hpp) in ONE process, on the same live is_mesh/DSC complex.
 // For the initial mesh and after every segment() iteration (deform + relabel + adapt make the mesh irregular) it runs
-//     reference: update_vertex_boundary(); update_average_intensity(); compute_external_force(); compute_energy()
+//     reference: update_vertex_boundary(); update_average_intensity(); compute_external_force(); compute_internal_force_2(); compute_energy()
 //     GPU      : adapter.refresh(); adapter.update_average_intensity(); adapter.compute_external_force(); compute_energy()
 // on the same segment_function object and compares the public result members:
 //     _phase_volume bit-exact, _total_intensities/_mean_intensities 1e-6 relative, _forces bit-exact when fed the
@@ -109,6 +109,7 @@ int main(int argc, char **argv)
                 seg.update_vertex_boundary();
                 seg.update_average_intensity();
                 seg.compute_external_force();
+                seg.compute_internal_force_2();
                 seg.compute_energy();
                 log = q.ss.str();
             }
@@ -116,9 +117,17 @@ int main(int argc, char **argv)
             size_t p = log.rfind("=== Energy; area = ");
             if (p != std::string::npos) sscanf(log.c_str() + p, "=== Energy; area = %lf - %lf", &e_data_ref, &e_area_ref);
             const std::vector<double> mean_ref = seg._mean_intensities, total_ref = seg._total_intensities, vol_ref = seg._phase_volume;
-            const std::vector<vec3> forces_ref = seg._forces;
+            const std::vector<vec3> forces_ref = seg._forces, internal_ref = seg._internal_forces;
             // ---- GPU, same object, same mesh ----
             gpu.refresh(seg);
+            gpu.compute_internal_force_2(seg); // unprojected nodes bit for bit, projected ones to rounding
+            double imax = 0, idmax = 0;
+            size_t bad_i = seg._internal_forces.size() != internal_ref.size() ? 1 : 0;
+            for (size_t i = 0; i < internal_ref.size() && !bad_i; i++) for (int c = 0; c < 3; c++) {
+                imax = std::max(imax, std::fabs(internal_ref[i][c]));
+                idmax = std::max(idmax, std::fabs(internal_ref[i][c] - seg._internal_forces[i][c]));
+            }
+            seg._internal_forces = internal_ref;
             gpu.compute_external_force(seg); // with the reference's means still in seg._mean_intensities: bit-exact bar
             size_t bad_f = 0;
             if (seg._forces.size() != forces_ref.size()) bad_f = 1;
@@ -140,6 +149,8 @@ int main(int argc, char **argv)
             double e_data = 0, e_area = 0;
             gpu.compute_energy(seg, &e_data, &e_area);
             if (!close_rel(e_data, e_data_ref, 1e-6) || !close_rel(e_area, e_area_ref, 1e-6)) ok = false;
+            if (bad_i || idmax > 1e-9 * std::max(imax, 1e-300)) ok = false;
+            printf("iter %d: internal forces max abs diff %.3g of %.3g\n", it, idmax, imax);
             printf("iter %d: %zu tets %zu interface faces | phase_volume %s | forces(ref means) %zu mismatching components | "
                    "forces(gpu means) max abs diff %.3g of %.3g | energy %.10g/%.10g vs %.10g/%.10g | %s\n",
                    it, gpu.snapshot().tet_label.size(), gpu.snapshot().face_is_boundary.size(),

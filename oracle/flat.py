@@ -103,6 +103,21 @@ def face_forces(vol, snap, nb_phase, mean, threads=1):
     return forces.reshape(-1, 3)
 
 
+def internal_forces(snap, node_flags, vb=None):
+    """segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232) over a flat snapshot."""
+    pos = _c(snap["pos"], np.float64)
+    nnb = pos.size // 3
+    fn = _c(snap["face_nodes"], np.uint32)
+    ft = _c(snap["face_tets"], np.uint32)
+    tn = _c(snap["tet_nodes"], np.uint32)
+    tl = _c(snap["tet_label"], np.int32)
+    vb = vertex_bound(snap) if vb is None else _c(vb, np.uint8)
+    nf = _c(node_flags, np.uint8)
+    out = np.zeros(3 * nnb)
+    lib().fo_internal_forces(C.c_uint32(nnb), _p(pos), _p(tn), _p(tl), C.c_uint32(fn.size // 3), _p(fn), _p(ft), _p(vb), _p(nf), _p(out))
+    return out.reshape(-1, 3)
+
+
 def build_sum_table(vol):
     vol = np.ascontiguousarray(vol)
     table = np.empty(vol.shape, np.float64)

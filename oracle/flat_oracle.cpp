@@ -260,6 +260,59 @@ int fo_face_forces(const int dims[3], int dtype, const void *voxels, uint32_t n_
 }
 
 // image3d::build_sum_table, DEMO/image3d.cpp:166-176: S[x,y,z] = S[x,y,z-1] + V[x,y,z].
+// segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232).
+//   pass 1, interface faces in ascending key order that are not all-vertex-bound (segment_function::is_boundary(FaceKey),
+//           :2186-2196): corner i receives -h * |l2 - l1| with h = normalize(l0 - project_point_line(l0, l1, l2 - l1))
+//           (is_mesh/util.h:395-399), l0/l1/l2 = corners i, i+1, i+2 in get_nodes(f) order;
+//   pass 2, nodes that are interface and not crossing (node_flags bit 0 / bit 1, is_mesh/attributes.h:84-102) with
+//           |f| > EPSILON (1e-8, is_mesh/util.h:43): f = n * dot(n, f), n = DSC::get_normal(node) (src/DSC.h:3138-3159):
+//           the normalised sum of get_normal(face) over the node's interface faces, 0 when that sum is shorter than EPSILON.
+// The reference adds the face normals in get_faces(node) order, which a flat snapshot does not carry: here ascending face
+// order; the projected forces agree to rounding (1e-12), the unprojected sums bit for bit.
+int fo_internal_forces(uint32_t n_nodes_buffer, const double *pos, const uint32_t *tet_nodes, const int32_t *tet_label, uint32_t n_faces,
+                       const uint32_t *face_nodes, const uint32_t *face_tets, const uint8_t *vertex_bound, const uint8_t *node_flags,
+                       double *internal_forces)
+{
+    const double EPS = 1e-8;
+    memset(internal_forces, 0, sizeof(double) * 3 * (size_t)n_nodes_buffer);
+    std::vector<double> nsum(3 * (size_t)n_nodes_buffer, 0.0);
+    for (uint32_t f = 0; f < n_faces; f++) {
+        const uint32_t *fn = face_nodes + 3 * (size_t)f;
+        uint32_t t0 = face_tets[2 * f], t1 = face_tets[2 * f + 1];
+        // get_normal(fid): sorted w.r.t. the co-boundary tet with the highest label, first wins (is_mesh/is_mesh.h:639-663)
+        uint32_t tid = t0;
+        if (t0 == 0xFFFFFFFFu) tid = t1;
+        else if (t1 != 0xFFFFFFFFu && tet_label[t1] > tet_label[t0]) tid = t1;
+        if (tid != 0xFFFFFFFFu) {
+            V3 N = face_normal_wrt(pos, fn, tet_nodes + 4 * (size_t)tid);
+            for (int k = 0; k < 3; k++) { double *o = nsum.data() + 3 * (size_t)fn[k]; o[0] += N.x; o[1] += N.y; o[2] += N.z; }
+        }
+        if (vertex_bound[fn[0]] && vertex_bound[fn[1]] && vertex_bound[fn[2]]) continue;
+        V3 p[3] = {P(pos, fn[0]), P(pos, fn[1]), P(pos, fn[2])};
+        for (int i = 0; i < 3; i++) {
+            V3 l0 = p[i], l1 = p[(i + 1) % 3], l2 = p[(i + 2) % 3];
+            V3 v = sub(l2, l1), v1 = sub(l0, l1);
+            V3 proj = add(l1, divs(mul(v, dot(v1, v)), dot(v, v))); // a + v * dot(v1,v) / dot(v,v)
+            V3 h = normalize(sub(l0, proj));
+            V3 t = mul(mul(h, -1.0), length(v)); // -h * (l2 - l1).length()
+            double *o = internal_forces + 3 * (size_t)fn[i];
+            o[0] += t.x; o[1] += t.y; o[2] += t.z;
+        }
+    }
+    for (uint32_t n = 0; n < n_nodes_buffer; n++) {
+        if (!(node_flags[n] & 1) || (node_flags[n] & 2)) continue;
+        double *o = internal_forces + 3 * (size_t)n;
+        V3 F{o[0], o[1], o[2]};
+        if (!(length(F) > EPS)) continue;
+        V3 S{nsum[3 * (size_t)n], nsum[3 * (size_t)n + 1], nsum[3 * (size_t)n + 2]};
+        V3 norm{0, 0, 0};
+        if (!(length(S) < EPS)) norm = normalize(S);
+        V3 r = mul(norm, dot(norm, F));
+        o[0] = r.x; o[1] = r.y; o[2] = r.z;
+    }
+    return 0;
+}
+
 int fo_build_sum_table(const int dims[3], int dtype, const void *voxels, double *table)
 {
     Vol V{dims[0], dims[1], dims[2], dtype, voxels};

@@ -249,6 +249,7 @@ static void dump_state(const Args &a, segment_function &seg, const std::string &
         seg.update_vertex_boundary();
         seg.update_average_intensity();
         seg.compute_external_force();
+        seg.compute_internal_force_2();
         seg.compute_energy();
         log = cap.ss.str();
     }
@@ -379,6 +380,16 @@ static void dump_state(const Args &a, segment_function &seg, const std::string &
     // --- outputs of the reference members ---------------------------------------------------
     std::vector<double> forces(3 * (size_t)nnb, 0.0);
     for (size_t i = 0; i < seg._forces.size() && i < nnb; i++) { forces[3 * i] = seg._forces[i][0]; forces[3 * i + 1] = seg._forces[i][1]; forces[3 * i + 2] = seg._forces[i][2]; }
+
+    // compute_internal_force_2 and the node attributes it reads (is_mesh/attributes.h:84-102)
+    std::vector<double> internal_forces(3 * (size_t)nnb, 0.0);
+    for (size_t i = 0; i < seg._internal_forces.size() && i < nnb; i++)
+        for (int d = 0; d < 3; d++) internal_forces[3 * i + d] = seg._internal_forces[i][d];
+    std::vector<uint8_t> node_flags(nnb, 0);
+    for (auto nit = dsc->nodes_begin(); nit != dsc->nodes_end(); nit++)
+        node_flags[(unsigned)nit.key()] = (uint8_t)((nit->is_interface() ? 1 : 0) | (nit->is_crossing() ? 2 : 0) | (nit->is_boundary() ? 4 : 0));
+    write_bin(dir, "internal_forces.f64", internal_forces);
+    write_bin(dir, "node_flags.u8", node_flags);
 
     write_bin(dir, "pos.f64", pos);
     write_bin(dir, "node_valid.u8", node_valid);

@@ -95,6 +95,7 @@ def run_case(name, spec):
     P = meta["nb_phase"]
     arrs["pos"] = arrs["pos"].reshape(-1, 3)
     arrs["forces"] = arrs["forces"].reshape(-1, 3)
+    arrs["internal_forces"] = arrs["internal_forces"].reshape(-1, 3)
     arrs["tet_nodes"] = arrs["tet_nodes"].reshape(-1, 4)
     arrs["face_nodes"] = arrs["face_nodes"].reshape(-1, 3)
     arrs["face_tets"] = arrs["face_tets"].reshape(-1, 2)

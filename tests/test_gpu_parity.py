@@ -105,6 +105,27 @@ def test_compute_energy(case):
     assert d2 == d and a2 == a
 
 
+def test_internal_force(case, flat):
+    """compute_internal_force_2 against the reference's own _internal_forces."""
+    g, img, seg = case
+    fl = g["node_flags"]
+    ref = g["internal_forces"]
+    F = seg.compute_internal_force_2(fl)  # m_vertex_bound derived on the device
+    unprojected = ((fl & 1) == 0) | ((fl & 2) != 0)
+    assert np.array_equal(F[unprojected], ref[unprojected])  # ordered sums, reference arithmetic: bit for bit
+    np.testing.assert_allclose(F, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    F2 = seg.compute_internal_force_2(fl, vertex_bound=g["vertex_bound"])
+    assert np.array_equal(F2, F)
+    assert np.array_equal(F, flat.internal_forces(golden_io.snapshot_of(g), fl, g["vertex_bound"]))  # same order as the flat oracle
+    # get_node_displacement (DEMO/segment_function.cpp:581-584)
+    Fe = seg.compute_external_force(mean=g["mean"])
+    d = seg.get_node_displacements(0.5)
+    assert np.array_equal(d, (g["forces"] + g["meta"]["alpha"] * F) * 0.5)
+    # flags decide the projection: with every node marked crossing nothing is projected
+    F3 = seg.compute_internal_force_2(fl | 2)
+    assert np.array_equal(F3[unprojected], F[unprojected]) and not np.array_equal(F3, F)
+
+
 def test_points_in_tets_bit_exact(case):
     g, img, seg = case
     assert np.array_equal(seg.points_in_tets(g["pit_tet"], g["pit_pts"]), g["pit_inside"])

@@ -93,3 +93,19 @@ def test_relabel_energies_bit_exact(case, flat):
     e = flat.relabel_energies(g["volume"], s, g["tet_face_nodes"], g["tet_face_tets"], g["meta"]["nb_phase"], g["mean"], g["meta"]["alpha"])
     lab = g["tet_label"] != 0
     assert np.array_equal(e[lab], g["tet_relabel_energy"][lab])
+
+
+def test_internal_forces_match_the_reference(flat):
+    """compute_internal_force_2.  Nodes that are not projected on their normal (crossing or not interface) are
+    bit-identical; projected ones differ by the order in which the face normals of a node are added (rounding)."""
+    for name in golden_io.CASES:
+        g = golden_io.load(name)
+        s = golden_io.snapshot_of(g)
+        F = flat.internal_forces(s, g["node_flags"], g["vertex_bound"])
+        ref = g["internal_forces"]
+        fl = g["node_flags"]
+        unprojected = ((fl & 1) == 0) | ((fl & 2) != 0)
+        assert np.array_equal(F[unprojected], ref[unprojected])
+        np.testing.assert_allclose(F, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+        assert np.abs(ref).max() > 1.0  # the fixture exercises the path
+        assert np.array_equal(flat.internal_forces(s, fl), F)  # vertex_bound derived from the snapshot

@@ -2622,6 +2622,41 @@ __global__ void vertex_bound_kernel(MeshView m, unsigned char *vb)
 }
 
 // =================================================================================================
+// Initialisation pass of segment_function::initialization_discrete_opt (DEMO/segment_function.cpp:165-262), SURVEY 8(f) row 2:
+// histogram of the per-tet mean intensities (bin (int)(mean*256), clamped to 255, :219-226) for Otsu's multi-level
+// thresholding (host: DEMO/otsu_multi.h), then label = 1 + lower_bound(thresholds, min((int)(mean*255), 255)) (:250-260).
+// Label-0 (boundary layer) tets are skipped by both (:167-168, :245-248).
+// =================================================================================================
+__global__ void __launch_bounds__(256) init_hist_kernel(const int *__restrict__ tet_label, const double *__restrict__ tet_mean, unsigned n_tets, int *hist)
+{
+    __shared__ int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tets; t += gridDim.x * blockDim.x) {
+        if (tet_label[t] == 0) continue;
+        int idx = (int)(tet_mean[t] * 256);
+        if (idx > 255) idx = 255;
+        if (idx < 0) idx = 0; // a negative mean (negative voxels) would index out of bounds in the reference
+        atomicAdd(&sh[idx], 1);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void init_label_kernel(const int *__restrict__ tet_label, const double *__restrict__ tet_mean, unsigned n_tets, int n_thres, const int *__restrict__ thres,
+                                  int *__restrict__ out)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tets) return;
+    if (tet_label[t] == 0) { out[t] = 0; return; }
+    int m = (int)(tet_mean[t] * 255);
+    if (m >= 255) m = 255;
+    int k = 0;
+    while (k < n_thres && thres[k] < m) k++; // std::lower_bound on the ascending thresholds
+    out[t] = k + 1;
+}
+
+// =================================================================================================
 // Internal (curvature) force: segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232), SURVEY 8(f) row 3.
 // Two kernels like the external force, so that every node adds its terms in the reference's order (faces ascending) without
 // atomics:

@@ -93,6 +93,7 @@ struct dscgpu_ctx {
     int comm_rank = 0, comm_world = 0;
     unsigned comm_cap_rows = 0;
     bool comm_connected = false;
+    bool init_means_valid = false; // o_mean holds the per-tet means of the current snapshot (dscgpu_init_histogram)
     double *comm_rows = nullptr; // local scatter target of the force exchange: 3 doubles per active node, zero between evaluations
 
     bool has_snapshot = false;
@@ -943,6 +944,7 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
+    ctx->init_means_valid = false;
     ctx->has_tet_faces = false;
     CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ks));
     CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[16], 0));
@@ -1303,6 +1305,7 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     }
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
+    ctx->init_means_valid = false;
     ctx->has_tet_faces = false;
 
     // choose lanes per tet from a sample of tet volumes (heuristic only; never affects results)
@@ -1555,6 +1558,52 @@ int dscgpu_zray_energy(dscgpu_ctx *ctx, int nb_phase, const double *mean, double
     }
     if (energy_area) *energy_area = area;
     return DSCGPU_OK;
+}
+
+int dscgpu_init_histogram(dscgpu_ctx *ctx, int nb_phase, int32_t hist[256])
+{
+    NEED_SNAPSHOT();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && hist, "bad arguments");
+    const size_t nt = ctx->n_tets;
+    memset(hist, 0, 256 * sizeof(int32_t));
+    ctx->init_means_valid = false;
+    if (!nt) { ctx->init_means_valid = true; return DSCGPU_OK; }
+    CK(ctx->o_mean.ensure(nt * 8));
+    CK(ctx->misc.ensure(256 * sizeof(int) + 64));
+    // per-tet means of the whole mesh, whatever partition is set (the histogram is a property of the mesh)
+    const uint32_t tb = ctx->tet_b, te = ctx->tet_e;
+    ctx->tet_b = 0; ctx->tet_e = ctx->n_tets;
+    int r = run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, ctx->o_mean.as<double>(), nullptr, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), 0);
+    ctx->tet_b = tb; ctx->tet_e = te;
+    if (r) return r;
+    CK(cudaMemsetAsync(ctx->misc.p, 0, 256 * sizeof(int), ctx->stream));
+    unsigned grid = (unsigned)std::min<size_t>((nt + 255) / 256, (size_t)ctx->num_sms * 8);
+    init_hist_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->tet_label.as<int>(), ctx->o_mean.as<double>(), (unsigned)nt, ctx->misc.as<int>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hist, ctx->misc.p, 256 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    r = sync_and_check(ctx);
+    if (r) return r;
+    ctx->init_means_valid = true;
+    return DSCGPU_OK;
+}
+
+int dscgpu_init_labels(dscgpu_ctx *ctx, int n_thresholds, const int32_t *thresholds, int32_t *tet_label_out)
+{
+    NEED_SNAPSHOT();
+    ARG(n_thresholds >= 0 && n_thresholds < DSCGPU_MAX_PHASE && (n_thresholds == 0 || thresholds) && tet_label_out, "bad arguments");
+    ARG(ctx->init_means_valid, "dscgpu_init_histogram must run on this snapshot first");
+    const size_t nt = ctx->n_tets;
+    if (!nt) return DSCGPU_OK;
+    CK(ctx->misc.ensure(256 * sizeof(int) + 64));
+    CK(ctx->o_nsamp.ensure(nt * sizeof(int)));
+    if (n_thresholds) CK(cudaMemcpyAsync(ctx->misc.p, thresholds, n_thresholds * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    init_label_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ctx->tet_label.as<int>(), ctx->o_mean.as<double>(), (unsigned)nt, n_thresholds,
+                                                                          ctx->misc.as<int>(), ctx->o_nsamp.as<int>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(tet_label_out, ctx->o_nsamp.p, nt * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_and_check(ctx);
 }
 
 int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uint8_t *vertex_bound, double *internal_forces)

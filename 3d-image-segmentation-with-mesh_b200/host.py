@@ -315,6 +315,19 @@ class SegmentFunction:
         self._forces = f
         return f
 
+    def init_histogram(self):
+        """Histogram of the per-tet means for Otsu's thresholding (DEMO/segment_function.cpp:165-226)."""
+        h = np.zeros(256, np.int32)
+        self._img._check(self.lib.dscgpu_init_histogram(self._img._ctx, C.c_int(self.NB_PHASE), _ptr(h)), "dscgpu_init_histogram")
+        return h
+
+    def init_labels(self, thresholds):
+        """Labels of initialization_discrete_opt for the given Otsu thresholds (DEMO/segment_function.cpp:245-261)."""
+        t = np.ascontiguousarray(thresholds, np.int32)
+        out = np.zeros(self.n_tets, np.int32)
+        self._img._check(self.lib.dscgpu_init_labels(self._img._ctx, C.c_int(len(t)), _ptr(t) if len(t) else None, _ptr(out)), "dscgpu_init_labels")
+        return out
+
     def compute_internal_force_2(self, node_flags, vertex_bound=None):
         """segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232).  node_flags: bit 0 is_interface,
         bit 1 is_crossing per node (is_mesh attributes)."""

@@ -186,6 +186,16 @@ enum dscgpu_force_mode {
  * 3*n_nodes_buffer doubles indexed by raw node key (= _forces). */
 int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mode, double *forces);
 
+/* SURVEY 8(f) row 2 -- the initialisation pass, segment_function::initialization_discrete_opt (DEMO/segment_function.cpp:165-262):
+ *   dscgpu_init_histogram  per-tet mean intensities of all labelled tets (kept on the device) and their 256-bin histogram,
+ *                          bin = (int)(mean*256) clamped to 255 (:219-226).  Label-0 tets are skipped; the reference's loop also
+ *                          visits the -1 entries of its key-indexed buffer and writes bin -256 for them, out of bounds.
+ *   (host)                 thresholds = otsu_muti(hist, NB_PHASE), DEMO/otsu_multi.h:105-129 -- sequential scalar code
+ *   dscgpu_init_labels     label = 1 + lower_bound(thresholds, min((int)(mean*255), 255)) for labelled tets, 0 for label-0 tets
+ *                          (:245-261); the host applies them with set_label. */
+int dscgpu_init_histogram(dscgpu_ctx *ctx, int nb_phase, int32_t hist[256]);
+int dscgpu_init_labels(dscgpu_ctx *ctx, int n_thresholds, const int32_t *thresholds, int32_t *tet_label_out);
+
 /* SURVEY 8(f) row 3 -- segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232), the curvature force
  * segment() evaluates next to the external force every iteration (:2246): internal_forces is 3*n_nodes_buffer doubles indexed by
  * raw node key (= _internal_forces); get_node_displacement is (forces + alpha*internal_forces)*dt (:581-584).

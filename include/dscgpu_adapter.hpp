@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "dscgpu.h"
@@ -132,6 +133,20 @@ public:
         for (size_t i = 0; i < nnb; i++) {
             seg._forces[i][0] = forces_[3 * i]; seg._forces[i][1] = forces_[3 * i + 1]; seg._forces[i][2] = forces_[3 * i + 2];
         }
+    }
+
+    // Body of segment_function::initialization_discrete_opt (DEMO/segment_function.cpp:143-262): per-tet means and their
+    // histogram on the device, the reference's own otsu_muti (pass it in: DEMO/otsu_multi.h defines it in a header) on the
+    // host, the label rule on the device, set_label on the host.  Call refresh() first (labels: boundary layer = 0).
+    template <class OTSU> void initialization_discrete_opt(SEG &seg, OTSU otsu_muti)
+    {
+        std::vector<int32_t> hist(256, 0);
+        check(dscgpu_init_histogram(ctx_, seg.NB_PHASE, hist.data()), "dscgpu_init_histogram");
+        const std::vector<int> thres = otsu_muti(std::vector<int>(hist.begin(), hist.end()), seg.NB_PHASE);
+        std::vector<int32_t> t32(thres.begin(), thres.end()), labels(snap_.tet_label.size(), 0);
+        check(dscgpu_init_labels(ctx_, (int)t32.size(), t32.data(), labels.data()), "dscgpu_init_labels");
+        for (size_t i = 0; i < labels.size(); i++)
+            if (labels[i] != 0) seg._dsc->set_label(typename std::decay<decltype(seg._dsc->tetrahedra_begin().key())>::type(snap_.tet_key[i]), labels[i]);
     }
 
     // Body of segment_function::compute_internal_force_2; m_vertex_bound is read from seg (update_vertex_boundary ran before).

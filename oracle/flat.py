@@ -103,6 +103,20 @@ def face_forces(vol, snap, nb_phase, mean, threads=1):
     return forces.reshape(-1, 3)
 
 
+def init_histogram(tet_label, tet_mean):
+    """Histogram of initialization_discrete_opt (DEMO/segment_function.cpp:219-226) over the labelled tets."""
+    m = np.asarray(tet_label) != 0
+    idx = np.minimum(np.trunc(np.asarray(tet_mean, np.float64)[m] * 256).astype(np.int64), 255)
+    return np.bincount(idx, minlength=256).astype(np.int32)
+
+
+def init_labels(tet_label, tet_mean, thresholds):
+    """Label rule of initialization_discrete_opt (DEMO/segment_function.cpp:245-261): 0 stays 0."""
+    m255 = np.minimum(np.trunc(np.asarray(tet_mean, np.float64) * 255).astype(np.int64), 255)
+    lab = 1 + np.searchsorted(np.asarray(thresholds, np.int64), m255, side="left")
+    return np.where(np.asarray(tet_label) != 0, lab, 0).astype(np.int32)
+
+
 def internal_forces(snap, node_flags, vb=None):
     """segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232) over a flat snapshot."""
     pos = _c(snap["pos"], np.float64)

@@ -29,10 +29,14 @@
 #include <sstream>
 #include <random>
 #include <memory>
+#include <algorithm>
 
 #include "segment_function.h"
 #include "tet_dis_coord.hpp"
 #include "gaussian_points.h"
+
+// DEMO/otsu_multi.h defines (not declares) its functions; the definition comes from the reference's segment_function.o
+std::vector<int> otsu_muti(std::vector<int> histogram_in, int classes);
 
 // globals the reference expects the (GUI) driver to define
 // (DEMO/demo.cpp:22,27 and DEMO/user_interface.cpp:187)
@@ -318,6 +322,28 @@ static void dump_state(const Args &a, segment_function &seg, const std::string &
             tet_energy[i * P + k] = seg._img.get_energy(p, seg._mean_intensities[k]);
         }
     }
+    // --- the initialisation pass (segment_function.cpp:165-262) on the current mesh: the 256-bin histogram of
+    //     the per-tet means (labelled tets; the reference's loop also visits the -1 entries of its key-indexed buffer and writes
+    //     bin -256 for them, out of bounds: there is nothing to match for those), the reference's own otsu_muti on it
+    //     (DEMO/otsu_multi.h:105-129) and the labels the rule at :250-260 assigns
+    std::vector<int> init_hist(256, 0);
+    for (size_t i = 0; i < nt; i++) {
+        if (tet_label[i] == BOUND_LABEL) continue;
+        int idx = (int)(tet_mean[i] * 256);
+        if (idx > 255) idx = 255;
+        init_hist[idx]++;
+    }
+    std::vector<int> init_thres = otsu_muti(init_hist, P);
+    std::vector<int32_t> init_labels(nt, 0);
+    for (size_t i = 0; i < nt; i++) {
+        if (tet_label[i] == BOUND_LABEL) continue;
+        int m255 = (int)(tet_mean[i] * 255);
+        if (m255 >= 255) m255 = 255;
+        auto v_pos = std::lower_bound(init_thres.begin(), init_thres.end(), m255);
+        int label = (int)(v_pos == init_thres.end()) ? init_thres.size() : int(v_pos - init_thres.begin());
+        init_labels[i] = label + 1;
+    }
+
     // relabel energies with the neighbour-area term (segment_function.cpp:618-643), labels unchanged
     std::vector<double> tet_relabel_energy(nt * (size_t)P, -1.0);
     for (size_t i = 0; i < nt; i++) {
@@ -388,6 +414,9 @@ static void dump_state(const Args &a, segment_function &seg, const std::string &
     std::vector<uint8_t> node_flags(nnb, 0);
     for (auto nit = dsc->nodes_begin(); nit != dsc->nodes_end(); nit++)
         node_flags[(unsigned)nit.key()] = (uint8_t)((nit->is_interface() ? 1 : 0) | (nit->is_crossing() ? 2 : 0) | (nit->is_boundary() ? 4 : 0));
+    write_bin(dir, "init_hist.i32", init_hist);
+    write_bin(dir, "init_thres.i32", init_thres);
+    write_bin(dir, "init_labels.i32", init_labels);
     write_bin(dir, "internal_forces.f64", internal_forces);
     write_bin(dir, "node_flags.u8", node_flags);
 

@@ -105,6 +105,27 @@ def test_compute_energy(case):
     assert d2 == d and a2 == a
 
 
+def test_initialisation_pass(case, flat):
+    """histogram of the per-tet means and the label rule against the reference-derived fixture values."""
+    g, img, seg = case
+    h = seg.init_histogram()
+    ref = g["init_hist"]
+    assert h.sum() == ref.sum() == int((g["tet_label"] != 0).sum())
+    # a tet moves to the neighbouring bin only if its mean*256 sits within rounding of an integer (u8 voxels: the kernel adds the
+    # integer voxel values and divides once, the reference divides every voxel by 255 first)
+    m = g["tet_mean"][g["tet_label"] != 0] * 256
+    fragile = int((np.abs(m - np.rint(m)) < 1e-9).sum())
+    assert np.abs(h.astype(np.int64) - ref).sum() <= 2 * fragile
+    if fragile == 0:
+        assert np.array_equal(h, ref)
+    lab = seg.init_labels(g["init_thres"])
+    m255 = g["tet_mean"] * 255
+    stable = np.abs(m255 - np.rint(m255)) > 1e-9
+    assert np.array_equal(lab[stable], g["init_labels"][stable])
+    assert np.all(lab[g["tet_label"] == 0] == 0)
+    assert np.array_equal(seg.init_labels([]), np.where(g["tet_label"] != 0, 1, 0))  # one phase: no threshold
+
+
 def test_internal_force(case, flat):
     """compute_internal_force_2 against the reference's own _internal_forces."""
     g, img, seg = case

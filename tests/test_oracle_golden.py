@@ -109,3 +109,15 @@ def test_internal_forces_match_the_reference(flat):
         np.testing.assert_allclose(F, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
         assert np.abs(ref).max() > 1.0  # the fixture exercises the path
         assert np.array_equal(flat.internal_forces(s, fl), F)  # vertex_bound derived from the snapshot
+
+
+def test_initialisation_pass_matches_the_reference(flat):
+    """histogram of per-tet means, label rule.  c1_e6 carries the labels the reference's own
+    initialization_discrete_opt assigned (labels=otsu, no iteration): they pin histogram, thresholds and rule together."""
+    for name in golden_io.CASES:
+        g = golden_io.load(name)
+        lab = g["tet_label"]
+        assert np.array_equal(flat.init_histogram(lab, g["tet_mean"]), g["init_hist"])
+        assert np.array_equal(flat.init_labels(lab, g["tet_mean"], g["init_thres"]), g["init_labels"])
+    g = golden_io.load("c1_e6")
+    assert np.array_equal(g["init_labels"], g["tet_label"])

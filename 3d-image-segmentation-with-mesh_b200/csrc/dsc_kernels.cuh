@@ -2607,6 +2607,32 @@ __global__ void validate_snapshot_kernel(unsigned *tet_nodes, size_t n_tn, unsig
     if (bad) atomicExch(flag, 1);
 }
 
+// Incremental snapshot: moved nodes and changed tets scattered into the resident arrays.  Entries with a
+// key / index out of range are dropped and *flag is raised, like validate_snapshot_kernel.
+__global__ void scatter_positions_kernel(const unsigned *__restrict__ keys, const double *__restrict__ pos3, unsigned n, double4 *pos4, float4 *pos4f,
+                                         unsigned n_nodes, int *flag)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = keys ? keys[i] : i;
+    if (k >= n_nodes) { atomicExch(flag, 1); return; }
+    const double x = pos3[3 * (size_t)i], y = pos3[3 * (size_t)i + 1], z = pos3[3 * (size_t)i + 2];
+    pos4[k] = make_double4(x, y, z, 0.0);
+    pos4f[k] = make_float4((float)x, (float)y, (float)z, 0.f);
+}
+
+__global__ void scatter_tets_kernel(const unsigned *__restrict__ idx, const uint4 *__restrict__ nodes, const int *__restrict__ labels, unsigned n, uint4 *tet_nodes,
+                                    int *tet_label, unsigned n_tets, unsigned n_nodes, int *flag)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned t = idx[i];
+    const uint4 nd = nodes[i];
+    if (t >= n_tets || nd.x >= n_nodes || nd.y >= n_nodes || nd.z >= n_nodes || nd.w >= n_nodes) { atomicExch(flag, 1); return; }
+    tet_nodes[t] = nd;
+    tet_label[t] = labels[i];
+}
+
 // m_vertex_bound of update_vertex_boundary (DEMO/segment_function.cpp:2158-2171) from the snapshot
 __global__ void vertex_bound_kernel(MeshView m, unsigned char *vb)
 {

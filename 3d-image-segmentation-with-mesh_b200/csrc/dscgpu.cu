@@ -110,7 +110,8 @@ struct dscgpu_ctx {
 
     DevBuf partials, sums, mean, forces, counters;
     DevBuf o_total, o_vol, o_mean, o_energy, o_variation, o_hash, o_nsamp;
-    DevBuf ray_count, ray_offset, ray_cursor, hits, block_sums, ray_psum, ray_pcnt, misc, vbound, pit, nflags, iterm, inorm, iskip, iforce;
+    DevBuf ray_count, ray_offset, ray_cursor, hits, block_sums, ray_psum, ray_pcnt, misc, vbound, pit, nflags, iterm, inorm, iskip, iforce, upd;
+    PinBuf h_upd;
 
     cudaEvent_t ev[DSCGPU_T_COUNT][2];
     bool ev_used[DSCGPU_T_COUNT];
@@ -139,6 +140,15 @@ struct dscgpu_ctx {
             ctx->err = msg;             \
             return DSCGPU_ERR_ARG;      \
         }                               \
+    } while (0)
+
+#define NEED_SNAPSHOT()                                              \
+    do {                                                             \
+        if (!ctx) return DSCGPU_ERR_ARG;                             \
+        if (!ctx->has_snapshot) {                                    \
+            ctx->err = "dscgpu_set_snapshot has not been called";    \
+            return DSCGPU_ERR_NO_SNAPSHOT;                           \
+        }                                                            \
     } while (0)
 
 namespace {
@@ -1330,6 +1340,81 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     return DSCGPU_OK;
 }
 
+int dscgpu_update_snapshot(dscgpu_ctx *ctx, uint32_t n_pos, const uint32_t *node_keys, const double *pos, uint32_t n_tet_upd, const uint32_t *tet_index,
+                           const uint32_t *tet_nodes, const int32_t *tet_label, int replace_faces, uint32_t n_faces, const uint32_t *face_nodes,
+                           const uint32_t *face_tets, const uint8_t *face_is_boundary)
+{
+    NEED_SNAPSHOT();
+    ARG(n_pos == 0 || pos, "pos is null");
+    ARG(n_tet_upd == 0 || (tet_index && tet_nodes && tet_label), "tet update arrays are null");
+    ARG(!replace_faces || n_faces == 0 || (face_nodes && face_tets && face_is_boundary), "face arrays are null");
+    ARG(!replace_faces || n_faces < (1u << 30), "too many interface faces");
+    const uint32_t nn = ctx->n_nodes, nt = ctx->n_tets;
+    // one pinned staging block, one H2D copy: [keys | pos | tet idx | tet nodes | tet labels]
+    const size_t o_keys = 0, o_pos = o_keys + (node_keys ? (((size_t)n_pos * 4 + 15) & ~(size_t)15) : 0), o_tidx = o_pos + (size_t)n_pos * 24 + 8;
+    const size_t o_tidx_a = (o_tidx + 15) & ~(size_t)15, o_tn = o_tidx_a + (((size_t)n_tet_upd * 4 + 15) & ~(size_t)15), o_tl = o_tn + (size_t)n_tet_upd * 16;
+    const size_t total = o_tl + (size_t)n_tet_upd * 4 + 16;
+    CK(ctx->h_upd.ensure(total));
+    CK(ctx->upd.ensure(total));
+    CK(ctx->h_flag.ensure(sizeof(int)));
+    unsigned char *h = ctx->h_upd.as<unsigned char>();
+    CK(cudaStreamSynchronize(ctx->stream)); // the staging block may still feed the previous update
+    if (node_keys && n_pos) memcpy(h + o_keys, node_keys, (size_t)n_pos * 4);
+    if (n_pos) memcpy(h + o_pos, pos, (size_t)n_pos * 24);
+    if (n_tet_upd) {
+        memcpy(h + o_tidx_a, tet_index, (size_t)n_tet_upd * 4);
+        memcpy(h + o_tn, tet_nodes, (size_t)n_tet_upd * 16);
+        memcpy(h + o_tl, tet_label, (size_t)n_tet_upd * 4);
+    }
+    TimerScope ts(ctx, DSCGPU_T_H2D);
+    if (n_pos || n_tet_upd) CK(cudaMemcpyAsync(ctx->upd.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->validation_pending) CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ctx->stream));
+    unsigned char *d = ctx->upd.as<unsigned char>();
+    if (n_pos) {
+        scatter_positions_kernel<<<(n_pos + 255) / 256, 256, 0, ctx->stream>>>(node_keys ? reinterpret_cast<const unsigned *>(d + o_keys) : nullptr,
+                                                                              reinterpret_cast<const double *>(d + o_pos), n_pos, ctx->pos4.as<double4>(),
+                                                                              ctx->pos4f.as<float4>(), nn, reinterpret_cast<int *>(ctr(ctx, 4)));
+        ctx->launches++;
+    }
+    if (n_tet_upd) {
+        scatter_tets_kernel<<<(n_tet_upd + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const unsigned *>(d + o_tidx_a), reinterpret_cast<const uint4 *>(d + o_tn),
+                                                                             reinterpret_cast<const int *>(d + o_tl), n_tet_upd, ctx->tet_nodes.as<uint4>(),
+                                                                             ctx->tet_label.as<int>(), nt, nn, reinterpret_cast<int *>(ctr(ctx, 4)));
+        ctx->launches++;
+        ctx->has_tet_faces = false;
+    }
+    CK(cudaGetLastError());
+    if (replace_faces) {
+        const uint32_t nf = n_faces;
+        CK(ctx->face_nodes.ensure((size_t)nf * 12));
+        CK(ctx->face_tets.ensure((size_t)nf * 8));
+        CK(ctx->face_isb.ensure((size_t)nf));
+        CK(ctx->node_inc.ensure((size_t)nf * 12));
+        if (nf) {
+            CK(cudaMemcpyAsync(ctx->face_nodes.p, face_nodes, (size_t)nf * 12, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->face_tets.p, face_tets, (size_t)nf * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->face_isb.p, face_is_boundary, (size_t)nf, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        ctx->n_faces = nf;
+        ctx->face_b = 0; ctx->face_e = nf;
+        int rs = build_csr_device(ctx);
+        if (rs) return rs;
+        if (nf) {
+            const size_t n_ids = 5 * (size_t)nf;
+            unsigned grid = (unsigned)std::min<size_t>((n_ids + 255) / 256, (size_t)ctx->num_sms * 16);
+            validate_snapshot_kernel<<<grid, 256, 0, ctx->stream>>>(nullptr, 0, ctx->face_nodes.as<unsigned>(), 3 * (size_t)nf, ctx->face_tets.as<unsigned>(),
+                                                                  2 * (size_t)nf, nn, nt, reinterpret_cast<int *>(ctr(ctx, 4)));
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->h_flag.p, ctr(ctx, 4), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->validation_pending = true;
+    ctx->init_means_valid = false;
+    ctx->staging_valid = false; // the pinned staging of the last full snapshot is stale: dscgpu_image_force_eval(ctx, NULL, ...) must not re-upload it
+    return DSCGPU_OK;
+}
+
 int dscgpu_set_snapshot(dscgpu_ctx *ctx, const dscgpu_snapshot *s)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
@@ -1366,14 +1451,6 @@ int dscgpu_set_partition(dscgpu_ctx *ctx, uint32_t tb, uint32_t te, uint32_t fb,
     return DSCGPU_OK;
 }
 
-#define NEED_SNAPSHOT()                                              \
-    do {                                                             \
-        if (!ctx) return DSCGPU_ERR_ARG;                             \
-        if (!ctx->has_snapshot) {                                    \
-            ctx->err = "dscgpu_set_snapshot has not been called";    \
-            return DSCGPU_ERR_NO_SNAPSHOT;                           \
-        }                                                            \
-    } while (0)
 
 int dscgpu_tet_integrate(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, double *tet_total, double *tet_vol,
                          double *tet_mean, double *tet_energy, double *tet_variation, dscgpu_phase_stats *stats)

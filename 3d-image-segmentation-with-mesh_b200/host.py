@@ -206,6 +206,34 @@ class SegmentFunction:
         self._img._check(self.lib.dscgpu_set_snapshot(self._img._ctx, C.byref(s)), "dscgpu_set_snapshot")
         self.n_nodes_buffer, self.n_tets, self.n_faces = len(pos), len(tn), len(fn)
 
+    def update_snapshot(self, node_keys=None, pos=None, tet_index=None, tet_nodes=None, tet_label=None, faces=None):
+        """Edits the snapshot resident on the device: moved nodes (keys + positions; keys None = nodes 0..n-1), tets replaced in
+        place (index, 4 node keys, label), and -- faces = dict(face_nodes, face_tets, face_is_boundary) -- a new interface-face list."""
+        n_pos = 0 if pos is None else len(pos)
+        p = None if pos is None else np.ascontiguousarray(pos, np.float64).reshape(-1, 3)
+        k = None if node_keys is None else np.ascontiguousarray(node_keys, np.uint32)
+        if k is not None and len(k) != n_pos:
+            raise ValueError("node_keys and pos differ in length")
+        n_t = 0 if tet_index is None else len(tet_index)
+        ti = None if tet_index is None else np.ascontiguousarray(tet_index, np.uint32)
+        tn = None if tet_nodes is None else np.ascontiguousarray(tet_nodes, np.uint32).reshape(-1, 4)
+        tl = None if tet_label is None else np.ascontiguousarray(tet_label, np.int32)
+        if n_t and (tn is None or tl is None or len(tn) != n_t or len(tl) != n_t):
+            raise ValueError("tet_index, tet_nodes and tet_label differ in length")
+        fn = ft = fb = None
+        nf = 0
+        if faces is not None:
+            fn = np.ascontiguousarray(faces["face_nodes"], np.uint32).reshape(-1, 3)
+            ft = np.ascontiguousarray(faces["face_tets"], np.uint32).reshape(-1, 2)
+            fb = np.ascontiguousarray(faces["face_is_boundary"], np.uint8).reshape(-1)
+            nf = len(fn)
+        r = self.lib.dscgpu_update_snapshot(self._img._ctx, C.c_uint32(n_pos), _ptr(k), _ptr(p), C.c_uint32(n_t), _ptr(ti), _ptr(tn), _ptr(tl),
+                                            C.c_int(0 if faces is None else 1), C.c_uint32(nf), _ptr(fn) if nf else None, _ptr(ft) if nf else None,
+                                            _ptr(fb) if nf else None)
+        self._img._check(r, "dscgpu_update_snapshot")
+        if faces is not None:
+            self.n_faces = nf
+
     def staging(self, n_nodes_buffer, n_tets, n_faces):
         """Pinned host arrays to flatten a mesh into without an extra copy; follow with commit_snapshot()."""
         st = _Staging()

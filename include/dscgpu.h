@@ -124,6 +124,19 @@ typedef struct dscgpu_snapshot_staging {
 } dscgpu_snapshot_staging;
 int dscgpu_snapshot_staging_get(dscgpu_ctx *ctx, uint32_t n_nodes_buffer, uint32_t n_tets, uint32_t n_faces, dscgpu_snapshot_staging *out);
 int dscgpu_commit_snapshot(dscgpu_ctx *ctx);
+/* SURVEY 8(f) row 4 -- incremental snapshot.  Between two evaluations of segment() every interface node moves but only the tets
+ * that deform()/adapt() touched change (the reference tracks them, src/cache.hpp:82-115); re-sending 52 MB of an otherwise
+ * unchanged 2 M-tet snapshot is what bounds the end-to-end step.  This call edits the snapshot resident on the device:
+ *   n_pos positions (3 doubles each) for the node keys in node_keys (NULL: keys 0 .. n_pos-1),
+ *   n_tet_upd tets replaced in place: tet_index[i] (index into the snapshot's tet arrays) gets tet_nodes[4i..] and tet_label[i],
+ *   replace_faces != 0: the interface-face list is replaced as a whole (it is small and depends on every label) and the
+ *   node -> face table rebuilt; otherwise it is kept.
+ * n_nodes_buffer and n_tets stay what dscgpu_set_snapshot established (a mesh that grew needs a full snapshot).  Out-of-range
+ * keys / indices are dropped and reported by the next synchronising call.  Afterwards dscgpu_image_force_eval(ctx, NULL, ...)
+ * evaluates the resident snapshot without any upload. */
+int dscgpu_update_snapshot(dscgpu_ctx *ctx, uint32_t n_pos, const uint32_t *node_keys, const double *pos, uint32_t n_tet_upd, const uint32_t *tet_index,
+                           const uint32_t *tet_nodes, const int32_t *tet_label, int replace_faces, uint32_t n_faces, const uint32_t *face_nodes,
+                           const uint32_t *face_tets, const uint8_t *face_is_boundary);
 /* Multi-GPU: restrict the work of this context to tets [tet_begin,tet_end), interface faces
  * [face_begin,face_end) and (for the gather force kernel) nodes [node_begin,node_end); the
  * snapshot itself stays whole.  Reset by dscgpu_set_snapshot. */

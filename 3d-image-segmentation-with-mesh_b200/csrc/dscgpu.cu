@@ -484,11 +484,7 @@ bool g32_fits(const dscgpu_ctx *ctx)
 template <typename VoxT, bool SIMPLE, bool WANT_SQ, bool PER_TET> int launch_g32_t(dscgpu_ctx *ctx, const TetArgs &t)
 {
     auto kern = tet_sums_g32_kernel<VoxT, SIMPLE, WANT_SQ, PER_TET>;
-    static bool attr_set = false; // per instantiation
-    if (!attr_set) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG32SmemBytes));
-        attr_set = true;
-    }
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG32SmemBytes)); // per device: set it every time
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, kG32SmemBytes));
     if (occ < 1) occ = 1;

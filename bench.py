@@ -476,6 +476,30 @@ def main_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = te.item() / e2e_steps * 1e3
     e2e_value = units / (e2e_ms * 1e-3)
+    # ---- the same with an incremental snapshot: every node position re-sent, 2 % of the tets replaced, the
+    # interface-face list re-sent; reported next to e2e, never instead of it
+    e2e_incr = None
+    if world == 1:
+        idx = np.arange(0, n_tets, 50, dtype=np.uint32)
+        upd = dict(pos=np.ascontiguousarray(snap["pos"], np.float64), tet_index=idx, tet_nodes=np.ascontiguousarray(snap["tet_nodes"][idx]),
+                   tet_label=np.ascontiguousarray(snap["tet_label"][idx]),
+                   faces={k: snap[k] for k in ("face_nodes", "face_tets", "face_is_boundary")})
+
+        def step_incr():
+            seg.update_snapshot(**upd)
+            seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode, want_forces="pinned")
+
+        for _ in range(3):
+            step_incr()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_incr()
+        torch.cuda.synchronize(dev)
+        incr_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+        e2e_incr = {"value": units / (incr_ms * 1e-3), "unit": UNIT, "ms_per_step": incr_ms,
+                    "h2d_bytes_per_step": int(n_nodes * 24 + len(idx) * 24 + n_faces * 21), "d2h_bytes_per_step": d2h_bytes,
+                    "what": "dscgpu_update_snapshot: all node positions, 2 % of the tets, the interface-face list; then the evaluation on the resident snapshot"}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -528,6 +552,7 @@ def main_b200(args):
             "samples_per_step": n_samples_all, "gauss_points_per_step": n_gauss_all},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
                 "steps": e2e_steps},
+        "e2e_incremental": e2e_incr,
         "gpu_launches": int(launches_per_step[0] * args.steps),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "kernel_ms": {"tet_or_zray": float(np.mean(tet_ms)), "force": float(np.mean(force_ms)), "step_min": float(step_ms.min()),

@@ -93,6 +93,8 @@ struct dscgpu_ctx {
     int comm_rank = 0, comm_world = 0;
     unsigned comm_cap_rows = 0;
     bool comm_connected = false;
+    uint32_t upd_n_pos = 0, upd_n_tet = 0, upd_n_faces = 0; // the staged update (dscgpu_update_staging_get)
+    bool upd_keys = false, upd_staged = false;
     bool init_means_valid = false; // o_mean holds the per-tet means of the current snapshot (dscgpu_init_histogram)
     double *comm_rows = nullptr; // local scatter target of the force exchange: 3 doubles per active node, zero between evaluations
 
@@ -1336,45 +1338,75 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     return DSCGPU_OK;
 }
 
-int dscgpu_update_snapshot(dscgpu_ctx *ctx, uint32_t n_pos, const uint32_t *node_keys, const double *pos, uint32_t n_tet_upd, const uint32_t *tet_index,
-                           const uint32_t *tet_nodes, const int32_t *tet_label, int replace_faces, uint32_t n_faces, const uint32_t *face_nodes,
-                           const uint32_t *face_tets, const uint8_t *face_is_boundary)
+// layout of the pinned update block: [keys | pos | tet idx | tet nodes | tet labels | face nodes | face tets | face flags]
+namespace {
+struct UpdLayout {
+    size_t keys, pos, tidx, tn, tl, fn, ft, fb, total;
+};
+UpdLayout upd_layout(uint32_t n_pos, bool with_keys, uint32_t n_tet, uint32_t n_faces)
+{
+    auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    UpdLayout L;
+    L.keys = 0;
+    L.pos = up(with_keys ? (size_t)n_pos * 4 : 0);
+    L.tidx = up(L.pos + (size_t)n_pos * 24);
+    L.tn = up(L.tidx + (size_t)n_tet * 4);
+    L.tl = up(L.tn + (size_t)n_tet * 16);
+    L.fn = up(L.tl + (size_t)n_tet * 4);
+    L.ft = up(L.fn + (size_t)n_faces * 12);
+    L.fb = up(L.ft + (size_t)n_faces * 8);
+    L.total = up(L.fb + (size_t)n_faces) + 16;
+    return L;
+}
+} // namespace
+
+int dscgpu_update_staging_get(dscgpu_ctx *ctx, uint32_t n_pos, int with_keys, uint32_t n_tet_upd, uint32_t n_faces, dscgpu_update_staging *out)
 {
     NEED_SNAPSHOT();
-    ARG(n_pos == 0 || pos, "pos is null");
-    ARG(n_tet_upd == 0 || (tet_index && tet_nodes && tet_label), "tet update arrays are null");
-    ARG(!replace_faces || n_faces == 0 || (face_nodes && face_tets && face_is_boundary), "face arrays are null");
-    ARG(!replace_faces || n_faces < (1u << 30), "too many interface faces");
-    const uint32_t nn = ctx->n_nodes, nt = ctx->n_tets;
-    // one pinned staging block, one H2D copy: [keys | pos | tet idx | tet nodes | tet labels]
-    const size_t o_keys = 0, o_pos = o_keys + (node_keys ? (((size_t)n_pos * 4 + 15) & ~(size_t)15) : 0), o_tidx = o_pos + (size_t)n_pos * 24 + 8;
-    const size_t o_tidx_a = (o_tidx + 15) & ~(size_t)15, o_tn = o_tidx_a + (((size_t)n_tet_upd * 4 + 15) & ~(size_t)15), o_tl = o_tn + (size_t)n_tet_upd * 16;
-    const size_t total = o_tl + (size_t)n_tet_upd * 4 + 16;
-    CK(ctx->h_upd.ensure(total));
-    CK(ctx->upd.ensure(total));
-    CK(ctx->h_flag.ensure(sizeof(int)));
+    ARG(out, "out is null");
+    ARG(n_faces < (1u << 30), "too many interface faces");
+    const UpdLayout L = upd_layout(n_pos, with_keys != 0, n_tet_upd, n_faces);
+    CK(cudaStreamSynchronize(ctx->stream)); // the block may still feed the previous update
+    CK(ctx->h_upd.ensure(L.total));
     unsigned char *h = ctx->h_upd.as<unsigned char>();
-    CK(cudaStreamSynchronize(ctx->stream)); // the staging block may still feed the previous update
-    if (node_keys && n_pos) memcpy(h + o_keys, node_keys, (size_t)n_pos * 4);
-    if (n_pos) memcpy(h + o_pos, pos, (size_t)n_pos * 24);
-    if (n_tet_upd) {
-        memcpy(h + o_tidx_a, tet_index, (size_t)n_tet_upd * 4);
-        memcpy(h + o_tn, tet_nodes, (size_t)n_tet_upd * 16);
-        memcpy(h + o_tl, tet_label, (size_t)n_tet_upd * 4);
-    }
+    out->node_keys = with_keys ? reinterpret_cast<uint32_t *>(h + L.keys) : nullptr;
+    out->pos = reinterpret_cast<double *>(h + L.pos);
+    out->tet_index = reinterpret_cast<uint32_t *>(h + L.tidx);
+    out->tet_nodes = reinterpret_cast<uint32_t *>(h + L.tn);
+    out->tet_label = reinterpret_cast<int32_t *>(h + L.tl);
+    out->face_nodes = reinterpret_cast<uint32_t *>(h + L.fn);
+    out->face_tets = reinterpret_cast<uint32_t *>(h + L.ft);
+    out->face_is_boundary = h + L.fb;
+    ctx->upd_n_pos = n_pos; ctx->upd_keys = with_keys != 0; ctx->upd_n_tet = n_tet_upd; ctx->upd_n_faces = n_faces;
+    ctx->upd_staged = true;
+    return DSCGPU_OK;
+}
+
+int dscgpu_update_commit(dscgpu_ctx *ctx, int replace_faces)
+{
+    NEED_SNAPSHOT();
+    ARG(ctx->upd_staged, "dscgpu_update_staging_get was not called");
+    const uint32_t nn = ctx->n_nodes, nt = ctx->n_tets;
+    const uint32_t n_pos = ctx->upd_n_pos, n_tet_upd = ctx->upd_n_tet, n_faces = replace_faces ? ctx->upd_n_faces : 0;
+    const UpdLayout L = upd_layout(n_pos, ctx->upd_keys, n_tet_upd, ctx->upd_n_faces);
+    CK(ctx->upd.ensure(L.total));
+    CK(ctx->h_flag.ensure(sizeof(int)));
     TimerScope ts(ctx, DSCGPU_T_H2D);
-    if (n_pos || n_tet_upd) CK(cudaMemcpyAsync(ctx->upd.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    // one H2D copy for everything that is scattered; the face arrays go straight to their place
+    const size_t scatter_bytes = L.fn;
+    if (n_pos || n_tet_upd) CK(cudaMemcpyAsync(ctx->upd.p, ctx->h_upd.p, scatter_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (!ctx->validation_pending) CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ctx->stream));
     unsigned char *d = ctx->upd.as<unsigned char>();
+    const unsigned char *h = ctx->h_upd.as<unsigned char>();
     if (n_pos) {
-        scatter_positions_kernel<<<(n_pos + 255) / 256, 256, 0, ctx->stream>>>(node_keys ? reinterpret_cast<const unsigned *>(d + o_keys) : nullptr,
-                                                                              reinterpret_cast<const double *>(d + o_pos), n_pos, ctx->pos4.as<double4>(),
+        scatter_positions_kernel<<<(n_pos + 255) / 256, 256, 0, ctx->stream>>>(ctx->upd_keys ? reinterpret_cast<const unsigned *>(d + L.keys) : nullptr,
+                                                                              reinterpret_cast<const double *>(d + L.pos), n_pos, ctx->pos4.as<double4>(),
                                                                               ctx->pos4f.as<float4>(), nn, reinterpret_cast<int *>(ctr(ctx, 4)));
         ctx->launches++;
     }
     if (n_tet_upd) {
-        scatter_tets_kernel<<<(n_tet_upd + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const unsigned *>(d + o_tidx_a), reinterpret_cast<const uint4 *>(d + o_tn),
-                                                                             reinterpret_cast<const int *>(d + o_tl), n_tet_upd, ctx->tet_nodes.as<uint4>(),
+        scatter_tets_kernel<<<(n_tet_upd + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const unsigned *>(d + L.tidx), reinterpret_cast<const uint4 *>(d + L.tn),
+                                                                             reinterpret_cast<const int *>(d + L.tl), n_tet_upd, ctx->tet_nodes.as<uint4>(),
                                                                              ctx->tet_label.as<int>(), nt, nn, reinterpret_cast<int *>(ctr(ctx, 4)));
         ctx->launches++;
         ctx->has_tet_faces = false;
@@ -1387,9 +1419,9 @@ int dscgpu_update_snapshot(dscgpu_ctx *ctx, uint32_t n_pos, const uint32_t *node
         CK(ctx->face_isb.ensure((size_t)nf));
         CK(ctx->node_inc.ensure((size_t)nf * 12));
         if (nf) {
-            CK(cudaMemcpyAsync(ctx->face_nodes.p, face_nodes, (size_t)nf * 12, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->face_tets.p, face_tets, (size_t)nf * 8, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->face_isb.p, face_is_boundary, (size_t)nf, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->face_nodes.p, h + L.fn, (size_t)nf * 12, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->face_tets.p, h + L.ft, (size_t)nf * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->face_isb.p, h + L.fb, (size_t)nf, cudaMemcpyHostToDevice, ctx->stream));
         }
         ctx->n_faces = nf;
         ctx->face_b = 0; ctx->face_e = nf;
@@ -1409,6 +1441,32 @@ int dscgpu_update_snapshot(dscgpu_ctx *ctx, uint32_t n_pos, const uint32_t *node
     ctx->init_means_valid = false;
     ctx->staging_valid = false; // the pinned staging of the last full snapshot is stale: dscgpu_image_force_eval(ctx, NULL, ...) must not re-upload it
     return DSCGPU_OK;
+}
+
+int dscgpu_update_snapshot(dscgpu_ctx *ctx, uint32_t n_pos, const uint32_t *node_keys, const double *pos, uint32_t n_tet_upd, const uint32_t *tet_index,
+                           const uint32_t *tet_nodes, const int32_t *tet_label, int replace_faces, uint32_t n_faces, const uint32_t *face_nodes,
+                           const uint32_t *face_tets, const uint8_t *face_is_boundary)
+{
+    NEED_SNAPSHOT();
+    ARG(n_pos == 0 || pos, "pos is null");
+    ARG(n_tet_upd == 0 || (tet_index && tet_nodes && tet_label), "tet update arrays are null");
+    ARG(!replace_faces || n_faces == 0 || (face_nodes && face_tets && face_is_boundary), "face arrays are null");
+    dscgpu_update_staging st;
+    int r = dscgpu_update_staging_get(ctx, n_pos, node_keys != nullptr, n_tet_upd, replace_faces ? n_faces : 0, &st);
+    if (r) return r;
+    if (node_keys && n_pos) memcpy(st.node_keys, node_keys, (size_t)n_pos * 4);
+    if (n_pos) memcpy(st.pos, pos, (size_t)n_pos * 24);
+    if (n_tet_upd) {
+        memcpy(st.tet_index, tet_index, (size_t)n_tet_upd * 4);
+        memcpy(st.tet_nodes, tet_nodes, (size_t)n_tet_upd * 16);
+        memcpy(st.tet_label, tet_label, (size_t)n_tet_upd * 4);
+    }
+    if (replace_faces && n_faces) {
+        memcpy(st.face_nodes, face_nodes, (size_t)n_faces * 12);
+        memcpy(st.face_tets, face_tets, (size_t)n_faces * 8);
+        memcpy(st.face_is_boundary, face_is_boundary, (size_t)n_faces);
+    }
+    return dscgpu_update_commit(ctx, replace_faces);
 }
 
 int dscgpu_set_snapshot(dscgpu_ctx *ctx, const dscgpu_snapshot *s)

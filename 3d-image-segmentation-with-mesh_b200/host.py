@@ -45,6 +45,11 @@ class _Staging(C.Structure):
                 ("face_tets", C.c_void_p), ("face_is_boundary", C.c_void_p)]
 
 
+class _UpdateStaging(C.Structure):
+    _fields_ = [("node_keys", C.c_void_p), ("pos", C.c_void_p), ("tet_index", C.c_void_p), ("tet_nodes", C.c_void_p), ("tet_label", C.c_void_p),
+                ("face_nodes", C.c_void_p), ("face_tets", C.c_void_p), ("face_is_boundary", C.c_void_p)]
+
+
 class _PhaseStats(C.Structure):
     _fields_ = [("total", C.c_double * MAX_PHASE), ("sumsq", C.c_double * MAX_PHASE), ("volume", C.c_double * MAX_PHASE),
                 ("mean", C.c_double * MAX_PHASE)]
@@ -233,6 +238,32 @@ class SegmentFunction:
         self._img._check(r, "dscgpu_update_snapshot")
         if faces is not None:
             self.n_faces = nf
+
+    def update_staging(self, n_pos, with_keys, n_tet_upd, n_faces):
+        """Pinned host arrays of an incremental update (zero-copy); fill them, then update_commit()."""
+        st = _UpdateStaging()
+        self._img._check(self.lib.dscgpu_update_staging_get(self._img._ctx, C.c_uint32(n_pos), C.c_int(1 if with_keys else 0), C.c_uint32(n_tet_upd),
+                                                            C.c_uint32(n_faces), C.byref(st)), "dscgpu_update_staging_get")
+
+        def view(ptr, ctype, n, shape):
+            if n == 0 or not ptr:
+                return np.zeros(shape, dtype=ctype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).reshape(shape)
+
+        self._upd_faces = n_faces
+        return {"node_keys": view(st.node_keys, C.c_uint32, n_pos if with_keys else 0, (n_pos if with_keys else 0,)),
+                "pos": view(st.pos, C.c_double, 3 * n_pos, (n_pos, 3)),
+                "tet_index": view(st.tet_index, C.c_uint32, n_tet_upd, (n_tet_upd,)),
+                "tet_nodes": view(st.tet_nodes, C.c_uint32, 4 * n_tet_upd, (n_tet_upd, 4)),
+                "tet_label": view(st.tet_label, C.c_int32, n_tet_upd, (n_tet_upd,)),
+                "face_nodes": view(st.face_nodes, C.c_uint32, 3 * n_faces, (n_faces, 3)),
+                "face_tets": view(st.face_tets, C.c_uint32, 2 * n_faces, (n_faces, 2)),
+                "face_is_boundary": view(st.face_is_boundary, C.c_uint8, n_faces, (n_faces,))}
+
+    def update_commit(self, replace_faces=True):
+        self._img._check(self.lib.dscgpu_update_commit(self._img._ctx, C.c_int(1 if replace_faces else 0)), "dscgpu_update_commit")
+        if replace_faces:
+            self.n_faces = self._upd_faces
 
     def staging(self, n_nodes_buffer, n_tets, n_faces):
         """Pinned host arrays to flatten a mesh into without an extra copy; follow with commit_snapshot()."""

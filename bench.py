@@ -481,12 +481,17 @@ def main_b200(args):
     e2e_incr = None
     if world == 1:
         idx = np.arange(0, n_tets, 50, dtype=np.uint32)
-        upd = dict(pos=np.ascontiguousarray(snap["pos"], np.float64), tet_index=idx, tet_nodes=np.ascontiguousarray(snap["tet_nodes"][idx]),
-                   tet_label=np.ascontiguousarray(snap["tet_label"][idx]),
-                   faces={k: snap[k] for k in ("face_nodes", "face_tets", "face_is_boundary")})
+        # like the full snapshot above: the host has flattened the update straight into the library's pinned arrays
+        ust = seg.update_staging(n_nodes, False, len(idx), n_faces)
+        ust["pos"][...] = snap["pos"]
+        ust["tet_index"][...] = idx
+        ust["tet_nodes"][...] = snap["tet_nodes"][idx]
+        ust["tet_label"][...] = snap["tet_label"][idx]
+        for k in ("face_nodes", "face_tets", "face_is_boundary"):
+            ust[k][...] = snap[k]
 
         def step_incr():
-            seg.update_snapshot(**upd)
+            seg.update_commit(True)
             seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode, want_forces="pinned")
 
         for _ in range(3):
@@ -499,7 +504,7 @@ def main_b200(args):
         incr_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
         e2e_incr = {"value": units / (incr_ms * 1e-3), "unit": UNIT, "ms_per_step": incr_ms,
                     "h2d_bytes_per_step": int(n_nodes * 24 + len(idx) * 24 + n_faces * 21), "d2h_bytes_per_step": d2h_bytes,
-                    "what": "dscgpu_update_snapshot: all node positions, 2 % of the tets, the interface-face list; then the evaluation on the resident snapshot"}
+                    "what": "dscgpu_update_commit from pinned staging: all node positions, 2 % of the tets, the interface-face list; then the evaluation on the resident snapshot"}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:

@@ -137,6 +137,20 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx);
 int dscgpu_update_snapshot(dscgpu_ctx *ctx, uint32_t n_pos, const uint32_t *node_keys, const double *pos, uint32_t n_tet_upd, const uint32_t *tet_index,
                            const uint32_t *tet_nodes, const int32_t *tet_label, int replace_faces, uint32_t n_faces, const uint32_t *face_nodes,
                            const uint32_t *face_tets, const uint8_t *face_is_boundary);
+/* Zero-copy variant: PINNED host arrays sized for the given counts (node_keys NULL when with_keys == 0); fill them, then commit.
+ * The arrays stay valid -- and may be committed again -- until the next dscgpu_update_staging_get. */
+typedef struct dscgpu_update_staging {
+    uint32_t *node_keys;
+    double *pos;            /* 3 per updated node */
+    uint32_t *tet_index;
+    uint32_t *tet_nodes;    /* 4 per updated tet */
+    int32_t *tet_label;
+    uint32_t *face_nodes;   /* the whole new interface-face list, used when dscgpu_update_commit(ctx, 1) */
+    uint32_t *face_tets;
+    uint8_t *face_is_boundary;
+} dscgpu_update_staging;
+int dscgpu_update_staging_get(dscgpu_ctx *ctx, uint32_t n_pos, int with_keys, uint32_t n_tet_upd, uint32_t n_faces, dscgpu_update_staging *out);
+int dscgpu_update_commit(dscgpu_ctx *ctx, int replace_faces);
 /* Multi-GPU: restrict the work of this context to tets [tet_begin,tet_end), interface faces
  * [face_begin,face_end) and (for the gather force kernel) nodes [node_begin,node_end); the
  * snapshot itself stays whole.  Reset by dscgpu_set_snapshot. */

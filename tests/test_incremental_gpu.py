@@ -66,6 +66,21 @@ def test_update_equals_full_snapshot(pkg, flat):
     seg_b.set_snapshot(dict(s1, pos=s0["pos"]))
     assert np.array_equal(seg_a.tet_integrate()["total"], seg_b.tet_integrate()["total"])
     assert np.array_equal(seg_a.compute_external_force(mean=[0.1, 0.5, 0.9]), seg_b.compute_external_force(mean=[0.1, 0.5, 0.9]))
+    # zero-copy staging: fill the pinned arrays, commit (twice: the staged update may be committed again)
+    st = seg_a.update_staging(len(moved), True, len(changed), len(fn))
+    st["node_keys"][...] = moved
+    st["pos"][...] = pos1[moved]
+    st["tet_index"][...] = changed
+    st["tet_nodes"][...] = tn1[changed]
+    st["tet_label"][...] = lab1[changed]
+    st["face_nodes"][...] = fn
+    st["face_tets"][...] = ft
+    st["face_is_boundary"][...] = fb
+    seg_a.update_commit(True)
+    seg_a.update_commit(True)
+    seg_b.set_snapshot(s1)
+    for g, w in zip(_outputs(pkg, seg_a, P), _outputs(pkg, seg_b, P)):
+        assert np.array_equal(np.asarray(g), np.asarray(w))
     # bad keys are rejected loudly
     seg_a.update_snapshot(node_keys=np.array([n_nodes + 5], np.uint32), pos=np.zeros((1, 3)))
     with pytest.raises(pkg.DscGpuError):

@@ -13,6 +13,7 @@
 // bounded by HBM/L2 bandwidth and, for the tet pass, the FP64 pipe (21 non-fused DMUL/DADD per
 // sample position, which must not be contracted -- see dsc_device.cuh).
 #pragma once
+#include <type_traits>
 #include "dsc_device.cuh"
 
 #ifndef W2_MIN_BLOCKS
@@ -198,6 +199,7 @@ struct TetArgs {
     unsigned brick_sy, brick_sz;
     int vol_simple;                  // float volume: only non-negative finite values (scaled widening allowed)
     int pack;                        // w2: packed FP32 position arithmetic
+    int lean;                        // w2: full/tail batch split, per-tet weight from phase A
 };
 
 template <typename VoxT, int G, bool WITH_C>
@@ -609,7 +611,10 @@ DSC_HD int g32_slot_off(int L)
 // layer of tets along the volume border -- takes the filtered path.
 // PACK (variant bit 8192): the position arithmetic of a lane's four samples runs as two packed pairs (FFMA2 / FADD2), from a
 // copy of the lattice table laid out in pairs of rows (i, i + 8).
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false>
+// LEAN (variant bit 16384): full batches run without row clamps and masks, and the hot-path instantiation takes v / n^3 from
+// phase A instead of dividing once per round.  LEAN == 2 (bit 32768 as well): two full batches at a time -- eight gathers in
+// flight per lane, one wait instead of two for a 64-sample tet.
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false, int LEAN = 0>
 __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(const TetArgs a)
 {
     constexpr int G = 8, U = 4;
@@ -620,6 +625,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
     __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0-.5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
     __shared__ int2 w_m[8][32];                // meta, (O_linear - fold)
     __shared__ double w_v[8][32];
+    __shared__ double w_rw[LEAN ? 8 : 1][32]; // v / n^3 from phase A (one division per tet, lanes in parallel)
     __shared__ uint4 w_nd[8][32];
     for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
     if (PACK) {
@@ -732,6 +738,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
             w_m[warp][slot] = make_int2(meta, olin);
             if (active) {
                 w_v[warp][slot] = rv;
+                if (LEAN) { const int Lr = (meta >> 8) & 0xf; w_rw[warp][slot] = rv / (double)((Lr + 1) * (Lr + 1) * (Lr + 1)); }
                 w_nd[warp][slot] = rnd;
                 if (fast) { w_q0[warp][slot] = rq0; w_e1[warp][slot] = re1; w_e2[warp][slot] = re2; w_e3[warp][slot] = re3; }
             }
@@ -773,7 +780,10 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                 const float4 *__restrict__ tl = s_lat + off;
                 const ulonglong2 *__restrict__ tl2 = reinterpret_cast<const ulonglong2 *>(s_lat) + (size_t)g32_slot_off(L) * 32 + 2 * lane_g;
                 const int last = n3 - 1;
-                for (int base = lane_g, it = 0; base < n3; base += G * U, it++) {
+                // one batch of 4 samples per lane; TAIL: the batch may reach past the last row of the level (rows are clamped and masked)
+                auto batch = [&](auto tail_c, auto nb_c, int base, int it) {
+                    constexpr bool TAIL = decltype(tail_c)::value;
+                    constexpr int U = 4 * decltype(nb_c)::value; // samples per lane in this call (shadows the kernel's U)
                     int idx[U];
                     unsigned unsafe = 0;
                     if constexpr (PACK) {
@@ -806,8 +816,8 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const int i = base + u * G;
-                        const bool ok = i <= last;
-                        const float4 c = tl[min(i, last)];
+                        const bool ok = !TAIL || i <= last;
+                        const float4 c = tl[TAIL ? min(i, last) : i];
                         const float qx = fmaf(c.z, e3.x, fmaf(c.y, e2.x, fmaf(c.x, e1.x, fmaf(c.w, e1.w, q0.x))));
                         const float qy = fmaf(c.z, e3.y, fmaf(c.y, e2.y, fmaf(c.x, e1.y, fmaf(c.w, e2.w, q0.y))));
                         const float qz = fmaf(c.z, e3.z, fmaf(c.y, e2.z, fmaf(c.x, e1.z, fmaf(c.w, e3.w, q0.z))));
@@ -843,9 +853,20 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     }
                     VoxT val[U];
 #pragma unroll
-                    for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
+                    for (int u = 0; u < U; u++) val[u] = (!TAIL || idx[u] >= 0) ? __ldg(vol + idx[u]) : (VoxT)0;
 #pragma unroll
                     for (int u = 0; u < U; u++) add_voxel(val[u]);
+                };
+                using N1 = std::integral_constant<int, 1>;
+                using N2 = std::integral_constant<int, 2>;
+                if (LEAN && !PACK) { // full batches first: no clamps, no masks
+                    int base = lane_g, it = 0;
+                    if (LEAN == 2)
+                        for (; base - lane_g + 2 * G * U <= n3; base += 2 * G * U, it += 2) batch(std::false_type{}, N2{}, base, it);
+                    for (; base - lane_g + G * U <= n3; base += G * U, it++) batch(std::false_type{}, N1{}, base, it);
+                    for (; base < n3; base += G * U, it++) batch(std::true_type{}, N1{}, base, it);
+                } else {
+                    for (int base = lane_g, it = 0; base < n3; base += G * U, it++) batch(std::true_type{}, N1{}, base, it);
                 }
             } else if (active) {
                 // exact path (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491)
@@ -887,7 +908,8 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
             if (F32S) s = s * 0x1p+896; // exact: back to the true sum
             if (active) {
                 const double v = w_v[warp][j];
-                const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
+                // total = total * v / a.size()  (image3d.cpp:371); LEAN without per-tet outputs: v / n^3 comes from phase A (sums: 1e-6 quantities)
+                const double tot = (LEAN && !PER_TET) ? s * w_rw[warp][j] : s * v / (double)n3;
                 const double tsq = WANT_SQ ? sq * v / (double)n3 : 0.0;
                 if (lane_g == 0) {
                     nsamp += (unsigned long long)n3;

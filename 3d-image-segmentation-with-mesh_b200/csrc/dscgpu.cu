@@ -274,9 +274,9 @@ int ensure_volume_flags(dscgpu_ctx *ctx)
     return DSCGPU_OK;
 }
 
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false, int LEAN = 0> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
 {
-    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET, BRICK, SIMPLE, PACK>;
+    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET, BRICK, SIMPLE, PACK, LEAN>;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     if (occ < 1) occ = 1;
@@ -299,6 +299,12 @@ template <typename VoxT> int launch_w2(dscgpu_ctx *ctx, TetArgs &a)
     if (a.brick) { // bricked volume (variant bit 2048)
         if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true, true>(ctx, a) : launch_w2_t<VoxT, true, false, true>(ctx, a);
         return per_tet ? launch_w2_t<VoxT, false, true, true>(ctx, a) : launch_w2_t<VoxT, false, false, true>(ctx, a);
+    }
+    if (a.lean && !a.want_sq && !per_tet && !a.brick && !a.pack) { // variant bit 16384; hot-path instantiations only
+        if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
+            if (a.vol_simple) return a.lean == 2 ? launch_w2_t<VoxT, false, false, false, true, false, 2>(ctx, a) : launch_w2_t<VoxT, false, false, false, true, false, 1>(ctx, a);
+        }
+        return a.lean == 2 ? launch_w2_t<VoxT, false, false, false, false, false, 2>(ctx, a) : launch_w2_t<VoxT, false, false, false, false, false, 1>(ctx, a);
     }
     if (a.pack) { // packed FP32 position arithmetic (variant bit 8192); hot-path instantiations only
         if (!a.want_sq && !per_tet) {
@@ -570,6 +576,7 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
     if ((ctx->tet_variant & 128) && !with_c && fits32) { // warp-level two-phase kernel with lattice coordinates
         a.brick = nullptr;
         a.pack = (ctx->tet_variant & 8192) ? 1 : 0;
+        a.lean = (ctx->tet_variant & 16384) ? ((ctx->tet_variant & 32768) ? 2 : 1) : 0;
         if (!(ctx->tet_variant & 4096)) { // bit 12: keep the general float widening (A/B switch)
             int rf = ensure_volume_flags(ctx);
             if (rf) return rf;
@@ -642,6 +649,7 @@ int tet_pass_range(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, con
     a.brick = nullptr; a.brick_sy = a.brick_sz = 0;
     a.vol_simple = 0;
     a.pack = 0;
+    a.lean = 0;
     return launch_tet(ctx, a, nc > 0 && (o.d_energy || o.d_variation));
 }
 
@@ -2075,7 +2083,7 @@ int dscgpu_build_texture(dscgpu_ctx *ctx)
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 16384, "variant is a 14-bit field");
+    ARG(variant >= 0 && variant < 65536, "variant is a 16-bit field");
     if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
         int r = dscgpu_build_texture(ctx);
         if (r) return r;

@@ -309,6 +309,7 @@ int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes);
  *   bit 11 (2048) with bit 7: w2 gathering from the bricked, padded copy of the volume
  *   bit 12 (4096) with bit 7: keep the general float widening (off: scaled widening when the volume allows it)
  *   bit 13 (8192) with bit 7: packed FP32 (FFMA2) position arithmetic in the hot-path instantiation
+ *   bit 14 (16384) with bit 7: full batches without row clamps, per-tet weight from phase A; + bit 15 (32768): two batches per wait
  * Default 128 (w2, the fastest measured form; DESIGN.md section 9 has the numbers of the others).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
  * Per-candidate outputs (tet_energy / tet_variation) always use the v1 kernel. */
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant);

@@ -300,7 +300,7 @@ def test_ray_overflow_is_reported(pkg):
     img.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 5, 7, 8, 12, 24, 40, 44, 56, 60, 64, 128, 256, 512, 1152, 2176, 8320, 4224])
+@pytest.mark.parametrize("variant", [0, 1, 3, 5, 7, 8, 12, 24, 40, 44, 56, 60, 64, 128, 256, 512, 1152, 2176, 8320, 4224, 16512, 49280])
 def test_every_kernel_variant_classifies_identically(pkg, variant):
     """All implementations of the tet pass (incl. the FP32-filtered ones) must put every sample in the same voxel:
     per-tet sums of noisy data agree to rounding, and the volumes bit for bit."""
@@ -370,7 +370,7 @@ def test_non_cubic_volume_and_many_phases(pkg, flat, dtype, P):
     h, ns = seg.tet_sample_hash()
     assert np.array_equal(h, ref["hash"]) and np.array_equal(ns, ref["nsamp"])
     lab = snap["tet_label"]
-    for variant in (0, 40, 128, 512, 1152, 2176, 8320):
+    for variant in (0, 40, 128, 512, 1152, 2176, 8320, 16512, 49280):
         seg.set_tet_variant(variant)
         o = seg.tet_integrate()
         m = lab != 0

@@ -2186,9 +2186,12 @@ __global__ void __launch_bounds__(128) force_node_kernel(const ForceNodeArgs a)
     __shared__ signed char ngs[16][8];
     const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3;
     const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
-    const unsigned item = blockIdx.x * 16 + grp;
-    const unsigned v = item < __ldg(a.n_active) ? __ldg(a.active_nodes + item) : 0xFFFFFFFFu;
-    const bool live = v != 0xFFFFFFFFu && v >= a.begin && v < a.end;
+    const unsigned n_active = __ldg(a.n_active);
+    // grid-stride over the active nodes: the host only knows an upper bound of their number (3 per face), and a grid sized
+    // for that bound is five blocks in six that exit at once
+    for (unsigned item = blockIdx.x * 16 + grp; item < n_active; item += gridDim.x * 16) {
+    const unsigned v = __ldg(a.active_nodes + item);
+    const bool live = v >= a.begin && v < a.end;
     unsigned e0 = 0, e1 = 0;
     if (live) { e0 = __ldg(a.mesh.node_off + v); e1 = __ldg(a.mesh.node_off + v + 1); }
     double acc = 0; // lanes 0..2 of the group: x, y, z
@@ -2223,6 +2226,7 @@ __global__ void __launch_bounds__(128) force_node_kernel(const ForceNodeArgs a)
         __syncwarp(gmask);
     }
     if (live && lane8 < 3) a.forces[3 * (size_t)v + lane8] = acc;
+    }
 }
 
 // Instrumentation only (bench roofline bytes): number of Gauss points the force pass evaluates, recomputed on demand so

@@ -746,7 +746,8 @@ int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, do
         CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
         const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * nf);
         if (na.end > na.begin && max_active) {
-            force_node_kernel<<<(max_active + 15) / 16, 128, 0, ctx->stream>>>(na);
+            const unsigned grid = std::min<unsigned>((max_active + 15) / 16, (unsigned)ctx->num_sms * 16);
+            force_node_kernel<<<grid, 128, 0, ctx->stream>>>(na);
             ctx->launches++;
         }
         CK(cudaGetLastError());

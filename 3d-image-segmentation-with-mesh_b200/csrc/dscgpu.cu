@@ -1132,13 +1132,13 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_OK;
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    DevBuf *bufs[] = {&ctx->nflags, &ctx->iterm, &ctx->inorm, &ctx->iskip, &ctx->iforce, &ctx->tet_face_nodes, &ctx->tet_face_tets, &ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
+    DevBuf *bufs[] = {&ctx->upd, &ctx->nflags, &ctx->iterm, &ctx->inorm, &ctx->iskip, &ctx->iforce, &ctx->tet_face_nodes, &ctx->tet_face_tets, &ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
                       &ctx->partials, &ctx->sums, &ctx->mean, &ctx->forces, &ctx->counters, &ctx->o_total, &ctx->o_vol, &ctx->o_mean, &ctx->o_energy,
                       &ctx->o_variation, &ctx->o_hash, &ctx->o_nsamp, &ctx->ray_count, &ctx->ray_offset, &ctx->ray_cursor, &ctx->hits, &ctx->block_sums,
                       &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
     for (DevBuf *b : bufs) b->release();
     PinBuf *pins[] = {&ctx->h_pos4, &ctx->h_tet_nodes, &ctx->h_tet_label, &ctx->h_face_nodes, &ctx->h_face_tets, &ctx->h_face_isb, &ctx->h_node_off,
-                      &ctx->h_node_inc, &ctx->h_node_active, &ctx->h_out, &ctx->h_flag};
+                      &ctx->h_node_inc, &ctx->h_node_active, &ctx->h_out, &ctx->h_flag, &ctx->h_upd};
     for (PinBuf *b : pins) b->release();
     if (ctx->d_vol) cudaFree(ctx->d_vol);
     if (ctx->d_sum_table) cudaFree(ctx->d_sum_table);

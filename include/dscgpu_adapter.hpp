@@ -15,6 +15,7 @@
 //     _internal_forces).
 // INTEGRATION.md shows the three-line patch to DEMO/segment_function.cpp that routes segment() through it.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -36,6 +37,12 @@ struct Snapshot {
     std::vector<uint8_t> face_is_boundary;
     std::vector<uint8_t> node_flags;    // per node of the buffer: bit 0 is_interface(), bit 1 is_crossing() (is_mesh/attributes.h:84-102)
 
+    void swap(Snapshot &o)
+    {
+        pos.swap(o.pos); tet_key.swap(o.tet_key); tet_nodes.swap(o.tet_nodes); tet_label.swap(o.tet_label); face_key.swap(o.face_key);
+        face_nodes.swap(o.face_nodes); face_tets.swap(o.face_tets); face_is_boundary.swap(o.face_is_boundary); node_flags.swap(o.node_flags);
+    }
+
     dscgpu_snapshot view() const
     {
         dscgpu_snapshot s;
@@ -53,7 +60,11 @@ struct Snapshot {
 };
 
 // DSC is DSC::DeformableSimplicialComplex<> (or any ISMesh with the same getters).
-template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s)
+// key_indexed: the tet arrays have one entry per slot of the tet buffer (get_no_tets_buffer(), index = raw key; free slots
+// carry label 0 and are skipped by every kernel) instead of one per valid tet.  deform() collapses and splits simplices in
+// every iteration, so a dense list shifts all the time; with key-indexed arrays an unchanged tet keeps its place and
+// ImageEnergy::refresh can send differences only.
+template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s, bool key_indexed = false)
 {
     const unsigned nnb = dsc.get_no_nodes_buffer();
     s.pos.assign(3 * (size_t)nnb, 0.0);
@@ -66,6 +77,20 @@ template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s)
     }
     std::vector<int32_t> tet_index(dsc.get_no_tets_buffer(), -1);
     s.tet_key.clear(); s.tet_nodes.clear(); s.tet_label.clear();
+    if (key_indexed) {
+        const size_t ntb = dsc.get_no_tets_buffer();
+        s.tet_key.resize(ntb);
+        s.tet_nodes.assign(4 * ntb, 0u);
+        s.tet_label.assign(ntb, 0);
+        for (size_t k = 0; k < ntb; k++) s.tet_key[k] = (uint32_t)k;
+        for (auto tit = dsc.tetrahedra_begin(); tit != dsc.tetrahedra_end(); tit++) {
+            const size_t k = (size_t)(unsigned)tit.key();
+            tet_index[k] = (int32_t)k;
+            const auto nids = dsc.get_nodes(tit.key());
+            for (int c = 0; c < 4; c++) s.tet_nodes[4 * k + c] = nids[c];
+            s.tet_label[k] = dsc.get_label(tit.key());
+        }
+    } else
     for (auto tit = dsc.tetrahedra_begin(); tit != dsc.tetrahedra_end(); tit++) {
         tet_index[tit.key()] = (int32_t)s.tet_key.size();
         s.tet_key.push_back(tit.key());
@@ -106,12 +131,48 @@ public:
     ImageEnergy &operator=(const ImageEnergy &) = delete;
 
     // Call after anything that changed the mesh (deform, relabel, adapt) and after update_vertex_boundary().
+    // When the buffers kept their sizes (no key was added: the usual case between two deformations) only what differs from
+    // the snapshot resident on the device is sent -- moved nodes, tets whose nodes or label changed, and the (small)
+    // interface-face list -- through dscgpu_update_snapshot; otherwise the whole snapshot.
     void refresh(SEG &seg)
     {
-        snapshot_from_dsc(*seg._dsc, snap_);
-        dscgpu_snapshot v = snap_.view();
-        check(dscgpu_set_snapshot(ctx_, &v), "dscgpu_set_snapshot");
+        Snapshot next;
+        snapshot_from_dsc(*seg._dsc, next, /*key_indexed=*/true);
+        const bool same_shape = have_snapshot_ && next.pos.size() == snap_.pos.size() && next.tet_label.size() == snap_.tet_label.size();
+        if (!same_shape) {
+            snap_.swap(next);
+            dscgpu_snapshot v = snap_.view();
+            check(dscgpu_set_snapshot(ctx_, &v), "dscgpu_set_snapshot");
+            have_snapshot_ = true;
+            last_refresh_incremental_ = false;
+            return;
+        }
+        std::vector<uint32_t> keys, tidx, tnodes;
+        std::vector<double> pos;
+        std::vector<int32_t> tlabel;
+        const size_t nn = next.pos.size() / 3, nt = next.tet_label.size();
+        for (size_t k = 0; k < nn; k++)
+            if (next.pos[3 * k] != snap_.pos[3 * k] || next.pos[3 * k + 1] != snap_.pos[3 * k + 1] || next.pos[3 * k + 2] != snap_.pos[3 * k + 2]) {
+                keys.push_back((uint32_t)k);
+                pos.insert(pos.end(), next.pos.begin() + 3 * k, next.pos.begin() + 3 * k + 3);
+            }
+        for (size_t t = 0; t < nt; t++)
+            if (next.tet_label[t] != snap_.tet_label[t] || !std::equal(next.tet_nodes.begin() + 4 * t, next.tet_nodes.begin() + 4 * t + 4, snap_.tet_nodes.begin() + 4 * t)) {
+                tidx.push_back((uint32_t)t);
+                tnodes.insert(tnodes.end(), next.tet_nodes.begin() + 4 * t, next.tet_nodes.begin() + 4 * t + 4);
+                tlabel.push_back(next.tet_label[t]);
+            }
+        check(dscgpu_update_snapshot(ctx_, (uint32_t)keys.size(), keys.data(), pos.data(), (uint32_t)tidx.size(), tidx.data(), tnodes.data(), tlabel.data(), 1,
+                                     (uint32_t)next.face_is_boundary.size(), next.face_nodes.data(), next.face_tets.data(), next.face_is_boundary.data()),
+              "dscgpu_update_snapshot");
+        snap_.swap(next);
+        last_refresh_incremental_ = true;
+        last_moved_nodes_ = keys.size();
+        last_changed_tets_ = tidx.size();
     }
+    bool last_refresh_incremental() const { return last_refresh_incremental_; }
+    size_t last_moved_nodes() const { return last_moved_nodes_; }
+    size_t last_changed_tets() const { return last_changed_tets_; }
 
     // Body of segment_function::update_average_intensity.
     void update_average_intensity(SEG &seg)
@@ -145,7 +206,7 @@ public:
         const std::vector<int> thres = otsu_muti(std::vector<int>(hist.begin(), hist.end()), seg.NB_PHASE);
         std::vector<int32_t> t32(thres.begin(), thres.end()), labels(snap_.tet_label.size(), 0);
         check(dscgpu_init_labels(ctx_, (int)t32.size(), t32.data(), labels.data()), "dscgpu_init_labels");
-        for (size_t i = 0; i < labels.size(); i++)
+        for (size_t i = 0; i < labels.size(); i++) // (free slots of a key-indexed snapshot carry label 0: never touched)
             if (labels[i] != 0) seg._dsc->set_label(typename std::decay<decltype(seg._dsc->tetrahedra_begin().key())>::type(snap_.tet_key[i]), labels[i]);
     }
 
@@ -179,6 +240,8 @@ private:
     }
     dscgpu_ctx *ctx_ = nullptr;
     Snapshot snap_;
+    bool have_snapshot_ = false, last_refresh_incremental_ = false;
+    size_t last_moved_nodes_ = 0, last_changed_tets_ = 0;
     std::vector<double> forces_;
     int force_mode_;
 };

@@ -1986,7 +1986,8 @@ DSC_D V3 tet_barycenter(const MeshView &m, uint4 tn)
     return mul(add(add(add(a, b), c), d), 0.25);
 }
 
-DSC_D bool face_setup(const MeshView &m, unsigned f, int nb_phase, const double *__restrict__ mean, FaceGeom &g, unsigned n[3])
+// the part of face_setup that does not depend on the phase means: nodes, positions, normal, area, Gauss set, the two labels
+DSC_D bool face_geometry(const MeshView &m, unsigned f, FaceGeom &g, unsigned n[3], int &l0, int &l1)
 {
     const unsigned t0 = __ldg(m.face_tets + 2 * (size_t)f), t1 = __ldg(m.face_tets + 2 * (size_t)f + 1);
     if (t0 == kNoTet || t1 == kNoTet) return false; // the reference would read tets[1] out of range here
@@ -1994,10 +1995,9 @@ DSC_D bool face_setup(const MeshView &m, unsigned f, int nb_phase, const double 
     n[1] = __ldg(m.face_nodes + 3 * (size_t)f + 1);
     n[2] = __ldg(m.face_nodes + 3 * (size_t)f + 2);
     g.p[0] = load_pos(m.pos4, n[0]); g.p[1] = load_pos(m.pos4, n[1]); g.p[2] = load_pos(m.pos4, n[2]);
-    const int l0 = __ldg(m.tet_label + t0), l1 = __ldg(m.tet_label + t1);
-    // phase_intensity (DEMO/segment_function.h:149-156): -0.3 for the label-0 side
-    g.c0 = (l0 >= 1 && l0 <= nb_phase) ? mean[l0 - 1] : -0.3;
-    g.c1 = (l1 >= 1 && l1 <= nb_phase) ? mean[l1 - 1] : -0.3;
+    l0 = __ldg(m.tet_label + t0);
+    l1 = __ldg(m.tet_label + t1);
+    g.c0 = g.c1 = 0.0;
     const uint4 tn0 = __ldg(m.tet_nodes + t0), tn1 = __ldg(m.tet_nodes + t1);
     // get_normal(fid): sorted w.r.t. the co-boundary tet with the highest label, first wins (is_mesh.h:639-663)
     V3 N = face_normal_wrt(m, n[0], n[1], n[2], l1 > l0 ? tn1 : tn0);
@@ -2006,6 +2006,18 @@ DSC_D bool face_setup(const MeshView &m, unsigned f, int nb_phase, const double 
     g.norm = divs(N, length(N)); // Vec3d::normalize
     g.area = tri_area(g.p[0], g.p[1], g.p[2]);
     g.gs = gauss_set(g.area);
+    return true;
+}
+
+// phase_intensity (DEMO/segment_function.h:149-156): -0.3 for the label-0 side
+DSC_D double phase_intensity(int label, int nb_phase, const double *__restrict__ mean) { return (label >= 1 && label <= nb_phase) ? mean[label - 1] : -0.3; }
+
+DSC_D bool face_setup(const MeshView &m, unsigned f, int nb_phase, const double *__restrict__ mean, FaceGeom &g, unsigned n[3])
+{
+    int l0, l1;
+    if (!face_geometry(m, f, g, n, l0, l1)) return false;
+    g.c0 = phase_intensity(l0, nb_phase, mean);
+    g.c1 = phase_intensity(l1, nb_phase, mean);
     return true;
 }
 
@@ -2164,6 +2176,117 @@ template <typename VoxT> __global__ void __launch_bounds__(128) force_face_kerne
         const V3 fv = mul(g.norm, (2 * I - g.c0 - g.c1) * (g.c0 - g.c1) * w * g.area);
         double *out = a.fbuf + (size_t)f * 36 + 3 * k;
         out[0] = fv.x; out[1] = fv.y; out[2] = fv.z;
+    }
+}
+
+// ---- the same pass split at the only place the phase means enter -------------------------------------------------------------
+// f = Norm * ((2I - c0 - c1)(c0 - c1) w area): everything but c0, c1 is known before the means are -- the normal, the area,
+// the Gauss set and, per Gauss point, the trilinear sample I, which is where the time goes.  force_geom_kernel computes those
+// (it can run next to the tet pass that produces the means, on a second stream), force_node2_kernel forms the vectors with
+// the reference's operation order and adds them like force_node_kernel: the forces are bit-identical to the reference's.
+struct ForceGeomArgs {
+    VolumeView vol;
+    MeshView mesh;
+    double *fgeo;        // [n_faces][4]: unit normal (tet0 -> tet1), area
+    int *flab;           // [n_faces][2]: labels of the two tets
+    double *fint;        // [n_faces][12]: trilinear sample per Gauss point
+    signed char *fset;   // [n_faces] Gauss set index, -1 = face skipped
+    unsigned begin, end; // face range
+};
+
+template <typename VoxT> __global__ void __launch_bounds__(128) force_geom_kernel(const ForceGeomArgs a)
+{
+    const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned f = a.begin + gt / kFaceLanes;
+    const int slot = (int)(gt % kFaceLanes);
+    if (f >= a.end) return;
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    FaceGeom g;
+    unsigned n[3];
+    int l0, l1;
+    if (!face_geometry(a.mesh, f, g, n, l0, l1)) {
+        if (slot == 0) a.fset[f] = -1;
+        return;
+    }
+    const int q0 = c_gauss_off[g.gs], ng = c_gauss_off[g.gs + 1] - q0;
+    if (slot == 0) {
+        a.fset[f] = (signed char)g.gs;
+        double *o = a.fgeo + 4 * (size_t)f;
+        o[0] = g.norm.x; o[1] = g.norm.y; o[2] = g.norm.z; o[3] = g.area;
+        a.flab[2 * (size_t)f] = l0;
+        a.flab[2 * (size_t)f + 1] = l1;
+    }
+    for (int k = slot; k < ng; k += kFaceLanes) {
+        const int q = q0 + k;
+        const double b0 = c_gauss[4 * q + 1], b1 = c_gauss[4 * q + 2], b2 = c_gauss[4 * q + 3];
+        const V3 p = add(add(mul(g.p[0], b0), mul(g.p[1], b1)), mul(g.p[2], b2)); // get_coord_tri
+        a.fint[12 * (size_t)f + k] = fetch_trilinear(vol, a.vol.X, a.vol.Y, a.vol.Z, p);
+    }
+}
+
+struct ForceNode2Args {
+    MeshView mesh;
+    const double *fgeo;
+    const int *flab;
+    const double *fint;
+    const signed char *fset;
+    int nb_phase;
+    const double *mean;
+    double *forces;
+    unsigned begin, end;          // node range handled by this context
+    const unsigned *active_nodes; // nodes that have interface faces, ascending (built with the CSR)
+    const unsigned *n_active;     // device-resident length of that list
+};
+
+__global__ void __launch_bounds__(128) force_node2_kernel(const ForceNode2Args a)
+{
+    __shared__ double slab[16][8][12][3]; // [group in CTA][entry lane][gauss][component]
+    __shared__ signed char ngs[16][8];
+    const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+    const unsigned n_active = __ldg(a.n_active);
+    for (unsigned item = blockIdx.x * 16 + grp; item < n_active; item += gridDim.x * 16) {
+        const unsigned v = __ldg(a.active_nodes + item);
+        const bool live = v >= a.begin && v < a.end;
+        unsigned e0 = 0, e1 = 0;
+        if (live) { e0 = __ldg(a.mesh.node_off + v); e1 = __ldg(a.mesh.node_off + v + 1); }
+        double acc = 0; // lanes 0..2 of the group: x, y, z
+        for (unsigned eb = e0; eb < e1; eb += 8) {
+            const unsigned e = eb + lane8;
+            int ng = 0;
+            if (e < e1) {
+                const unsigned inc = __ldg(a.mesh.node_inc + e);
+                const unsigned f = inc >> 2, corner = inc & 3u;
+                const int gs = a.fset[f];
+                if (gs >= 0) {
+                    const double *ge = a.fgeo + 4 * (size_t)f;
+                    const V3 norm = {ge[0], ge[1], ge[2]};
+                    const double area = ge[3];
+                    const double c0 = phase_intensity(a.flab[2 * (size_t)f], a.nb_phase, a.mean), c1 = phase_intensity(a.flab[2 * (size_t)f + 1], a.nb_phase, a.mean);
+                    const double *fi = a.fint + 12 * (size_t)f;
+                    const int q0 = c_gauss_off[gs];
+                    ng = c_gauss_off[gs + 1] - q0;
+                    for (int k = 0; k < ng; k++) {
+                        const double w = c_gauss[4 * (q0 + k)], bc = c_gauss[4 * (q0 + k) + 1 + corner];
+                        const V3 fv = mul(norm, (2 * fi[k] - c0 - c1) * (c0 - c1) * w * area); // DEMO/segment_function.cpp:1463-1465
+                        slab[grp][lane8][k][0] = fv.x * bc;
+                        slab[grp][lane8][k][1] = fv.y * bc;
+                        slab[grp][lane8][k][2] = fv.z * bc;
+                    }
+                }
+            }
+            ngs[grp][lane8] = (signed char)ng;
+            __syncwarp(gmask);
+            if (lane8 < 3) {
+                const int cnt = (int)min(8u, e1 - eb);
+                for (int l = 0; l < cnt; l++) {
+                    const int m = ngs[grp][l];
+                    for (int k = 0; k < m; k++) acc += slab[grp][l][k][lane8];
+                }
+            }
+            __syncwarp(gmask);
+        }
+        if (live && lane8 < 3) a.forces[3 * (size_t)v + lane8] = acc;
     }
 }
 

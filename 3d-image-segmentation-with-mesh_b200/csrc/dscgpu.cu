@@ -112,6 +112,8 @@ struct dscgpu_ctx {
 
     DevBuf partials, sums, mean, forces, counters;
     DevBuf o_total, o_vol, o_mean, o_energy, o_variation, o_hash, o_nsamp;
+    DevBuf fgeo, flab, fint; // mean-independent part of the external force (force_geom_kernel)
+    bool geom_async = false;  // force_geom_kernel of the current snapshot is running / has run on copy_stream (join on ev_chunk[19])
     DevBuf ray_count, ray_offset, ray_cursor, hits, block_sums, ray_psum, ray_pcnt, misc, vbound, pit, nflags, iterm, inorm, iskip, iforce, upd;
     PinBuf h_upd;
 
@@ -697,6 +699,35 @@ template <typename VoxT> int launch_force_t(dscgpu_ctx *ctx, ForceArgs &a, int m
     return DSCGPU_OK;
 }
 
+// mean-independent half of the external force (force_geom_kernel) of this context's face range on stream st
+int launch_force_geom(dscgpu_ctx *ctx, cudaStream_t st)
+{
+    const unsigned nf = ctx->n_faces;
+    CK(ctx->fgeo.ensure((size_t)nf * 4 * sizeof(double) + 8));
+    CK(ctx->flab.ensure((size_t)nf * 2 * sizeof(int) + 8));
+    CK(ctx->fint.ensure((size_t)nf * 12 * sizeof(double) + 8));
+    CK(ctx->fset.ensure((size_t)nf + 8));
+    ForceGeomArgs fa;
+    fa.vol = vol_view(ctx); fa.mesh = mesh_view(ctx);
+    fa.fgeo = ctx->fgeo.as<double>(); fa.flab = ctx->flab.as<int>(); fa.fint = ctx->fint.as<double>(); fa.fset = ctx->fset.as<signed char>();
+    // multi-GPU: this context evaluates the faces of its partition only; faces outside keep set -1 and contribute on another rank
+    const bool whole_faces = ctx->face_b == 0 && ctx->face_e == nf;
+    fa.begin = ctx->face_b; fa.end = ctx->face_e;
+    if (!whole_faces && nf) CK(cudaMemsetAsync(ctx->fset.p, 0xFF, nf, st));
+    if (fa.end > fa.begin) {
+        const unsigned grid = (unsigned)(((size_t)(fa.end - fa.begin) * kFaceLanes + 127) / 128);
+        switch (ctx->dtype) {
+        case DSCGPU_U8: force_geom_kernel<unsigned char><<<grid, 128, 0, st>>>(fa); break;
+        case DSCGPU_U16: force_geom_kernel<unsigned short><<<grid, 128, 0, st>>>(fa); break;
+        case DSCGPU_F32: force_geom_kernel<float><<<grid, 128, 0, st>>>(fa); break;
+        default: force_geom_kernel<double><<<grid, 128, 0, st>>>(fa); break;
+        }
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
 int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, double *d_forces)
 {
     ForceArgs a;
@@ -710,29 +741,20 @@ int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, do
     TimerScope ts(ctx, DSCGPU_T_FORCE);
     const bool whole_nodes = ctx->node_b == 0 && ctx->node_e == ctx->n_nodes;
     if (mode == DSCGPU_FORCE_GATHER && !ctx->force_thread_gather) {
-        // two kernels: per-face Gauss vectors (all faces, on every rank: it is a few tens of microseconds), then per-node ordered sums
+        // two kernels: per-face geometry and samples (mean-independent: it may already be running on the side stream, see
+        // dscgpu_face_geometry_async), then per-node ordered sums with the means
         const unsigned nf = ctx->n_faces;
-        CK(ctx->fbuf.ensure((size_t)nf * 36 * sizeof(double) + 8));
-        CK(ctx->fset.ensure((size_t)nf + 8));
-        ForceFaceArgs fa;
-        fa.vol = a.vol; fa.mesh = a.mesh; fa.nb_phase = nb_phase; fa.mean = d_mean; fa.gauss_count = a.gauss_count;
-        fa.fbuf = ctx->fbuf.as<double>(); fa.fset = ctx->fset.as<signed char>();
-        // multi-GPU: this context evaluates the faces of its partition only; faces outside keep set -1 and contribute on another rank
-        const bool whole_faces = ctx->face_b == 0 && ctx->face_e == nf;
-        fa.begin = ctx->face_b; fa.end = ctx->face_e;
-        if (!whole_faces && nf) CK(cudaMemsetAsync(ctx->fset.p, 0xFF, nf, ctx->stream));
-        if (fa.end > fa.begin) {
-            const unsigned grid = (unsigned)(((size_t)(fa.end - fa.begin) * kFaceLanes + 127) / 128);
-            switch (ctx->dtype) {
-            case DSCGPU_U8: force_face_kernel<unsigned char><<<grid, 128, 0, ctx->stream>>>(fa); break;
-            case DSCGPU_U16: force_face_kernel<unsigned short><<<grid, 128, 0, ctx->stream>>>(fa); break;
-            case DSCGPU_F32: force_face_kernel<float><<<grid, 128, 0, ctx->stream>>>(fa); break;
-            default: force_face_kernel<double><<<grid, 128, 0, ctx->stream>>>(fa); break;
-            }
-            ctx->launches++;
+        if (ctx->geom_async) {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[19], 0));
+            ctx->geom_async = false;
+        } else {
+            int rg = launch_force_geom(ctx, ctx->stream);
+            if (rg) return rg;
         }
-        ForceNodeArgs na;
-        na.mesh = a.mesh; na.fbuf = fa.fbuf; na.fset = fa.fset; na.forces = d_forces;
+        const bool whole_faces = ctx->face_b == 0 && ctx->face_e == nf;
+        ForceNode2Args na;
+        na.mesh = a.mesh; na.fgeo = ctx->fgeo.as<double>(); na.flab = ctx->flab.as<int>(); na.fint = ctx->fint.as<double>();
+        na.fset = ctx->fset.as<signed char>(); na.nb_phase = nb_phase; na.mean = d_mean; na.forces = d_forces;
         // with a face partition every node may receive a contribution from this rank; with all faces present the node
         // range of the partition is enough (and the result is the reference's, bit for bit)
         if (whole_faces) {
@@ -747,7 +769,7 @@ int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, do
         const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * nf);
         if (na.end > na.begin && max_active) {
             const unsigned grid = std::min<unsigned>((max_active + 15) / 16, (unsigned)ctx->num_sms * 16);
-            force_node_kernel<<<grid, 128, 0, ctx->stream>>>(na);
+            force_node2_kernel<<<grid, 128, 0, ctx->stream>>>(na);
             ctx->launches++;
         }
         CK(cudaGetLastError());
@@ -961,6 +983,7 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
+    ctx->geom_async = false;
     ctx->init_means_valid = false;
     ctx->has_tet_faces = false;
     CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ks));
@@ -1132,7 +1155,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_OK;
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    DevBuf *bufs[] = {&ctx->upd, &ctx->nflags, &ctx->iterm, &ctx->inorm, &ctx->iskip, &ctx->iforce, &ctx->tet_face_nodes, &ctx->tet_face_tets, &ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
+    DevBuf *bufs[] = {&ctx->fgeo, &ctx->flab, &ctx->fint, &ctx->upd, &ctx->nflags, &ctx->iterm, &ctx->inorm, &ctx->iskip, &ctx->iforce, &ctx->tet_face_nodes, &ctx->tet_face_tets, &ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
                       &ctx->partials, &ctx->sums, &ctx->mean, &ctx->forces, &ctx->counters, &ctx->o_total, &ctx->o_vol, &ctx->o_mean, &ctx->o_energy,
                       &ctx->o_variation, &ctx->o_hash, &ctx->o_nsamp, &ctx->ray_count, &ctx->ray_offset, &ctx->ray_cursor, &ctx->hits, &ctx->block_sums,
                       &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
@@ -1322,6 +1345,7 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     }
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
+    ctx->geom_async = false;
     ctx->init_means_valid = false;
     ctx->has_tet_faces = false;
 
@@ -1448,6 +1472,7 @@ int dscgpu_update_commit(dscgpu_ctx *ctx, int replace_faces)
     CK(cudaMemcpyAsync(ctx->h_flag.p, ctr(ctx, 4), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->validation_pending = true;
     ctx->init_means_valid = false;
+    ctx->geom_async = false;
     ctx->staging_valid = false; // the pinned staging of the last full snapshot is stale: dscgpu_image_force_eval(ctx, NULL, ...) must not re-upload it
     return DSCGPU_OK;
 }
@@ -1898,6 +1923,20 @@ int dscgpu_means_from_sums_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_su
     means_from_sums_kernel<<<1, 32, 0, ctx->stream>>>(d_sums, nb_phase, d_mean);
     ctx->launches++;
     CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+int dscgpu_face_geometry_async(dscgpu_ctx *ctx)
+{
+    NEED_SNAPSHOT();
+    // fork: the side stream picks up where the main stream is now (snapshot in place), runs the kernel, and the next
+    // gather-mode force call joins it; both edges are events, so the pattern can be captured in a CUDA graph
+    CK(cudaEventRecord(ctx->ev_chunk[18], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[18], 0));
+    int r = launch_force_geom(ctx, ctx->copy_stream);
+    if (r) return r;
+    CK(cudaEventRecord(ctx->ev_chunk[19], ctx->copy_stream));
+    ctx->geom_async = true;
     return DSCGPU_OK;
 }
 

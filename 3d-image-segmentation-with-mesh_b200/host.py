@@ -463,6 +463,10 @@ class SegmentFunction:
         self._img._check(self.lib.dscgpu_means_from_sums_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_sums_ptr), C.c_void_p(d_mean_ptr)),
                          "dscgpu_means_from_sums_dev")
 
+    def face_geometry_async(self):
+        """Starts the mean-independent half of the external force on the context's second stream (joined by the next gather-mode force call)."""
+        self._img._check(self.lib.dscgpu_face_geometry_async(self._img._ctx), "dscgpu_face_geometry_async")
+
     def face_forces_dev(self, d_mean_ptr, d_forces_ptr, mode=FORCE_GATHER):
         self._img._check(self.lib.dscgpu_face_forces_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_mean_ptr), C.c_int(mode),
                                                          C.c_void_p(d_forces_ptr)), "dscgpu_face_forces_dev")

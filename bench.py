@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
+    ap.add_argument("--overlap-forces", action="store_true",
+                    help="start the mean-independent half of the force pass on a second stream next to the tet pass (measured: no gain, the tet kernel fills every SM)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: exchange kernels over NVLink peer memory (csrc/dsc_comm.cuh) or two NCCL all-reduces")
     return ap.parse_args()
@@ -321,6 +323,8 @@ def main_b200(args):
             seg.face_forces_allreduce_dev(d_mean.data_ptr(), d_forces.data_ptr())
             launches_per_step[0] = seg.launch_count() - n0
             return
+        if args.overlap_forces and world == 1 and force_mode == pkg.FORCE_GATHER:
+            seg.face_geometry_async()  # normals, areas, trilinear samples of the Gauss points: next to the tet pass, on the second stream
         if mean_mode == pkg.MEAN_TET:
             seg.tet_phase_sums_dev(d_sums.data_ptr())
         else:

@@ -256,6 +256,11 @@ const double *dscgpu_forces_pinned(dscgpu_ctx *ctx, uint32_t *n_nodes_buffer);
 int dscgpu_tet_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums);
 int dscgpu_zray_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums);
 int dscgpu_means_from_sums_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_sums, double *d_mean);
+/* Starts the part of the external force that does not depend on the phase means -- face normals, areas, Gauss sets and the
+ * trilinear sample of every Gauss point -- on the context's second stream, so that it runs next to the tet pass that produces
+ * the means; the next DSCGPU_FORCE_GATHER force call (dscgpu_face_forces[_dev]) joins it and only forms and adds the vectors.
+ * Optional: without it the force call computes that part itself.  Call it after the snapshot (and partition) is in place. */
+int dscgpu_face_geometry_async(dscgpu_ctx *ctx);
 int dscgpu_face_forces_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, double *d_forces);
 
 /* -- multi-GPU exchange over NVLink peer memory ------------------------------------------------------------------------ */

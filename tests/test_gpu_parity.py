@@ -85,6 +85,11 @@ def test_compute_external_force_gather_bit_exact(case, pkg):
     g, img, seg = case
     F = seg.compute_external_force(mode=pkg.FORCE_GATHER, mean=g["mean"])
     assert np.array_equal(F, g["forces"])
+    # the mean-independent half started ahead on the second stream (as next to the tet pass), joined by the force call
+    seg.face_geometry_async()
+    seg.tet_integrate(per_tet=False)
+    F2 = seg.compute_external_force(mode=pkg.FORCE_GATHER, mean=g["mean"])
+    assert np.array_equal(F2, g["forces"])
 
 
 def test_compute_external_force_atomic(case, pkg):

@@ -13,6 +13,7 @@
 // bounded by HBM/L2 bandwidth and, for the tet pass, the FP64 pipe (21 non-fused DMUL/DADD per
 // sample position, which must not be contracted -- see dsc_device.cuh).
 #pragma once
+#include <climits>
 #include <type_traits>
 #include "dsc_device.cuh"
 
@@ -179,6 +180,8 @@ DSC_D double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v
 // reduced per CTA and written as one partial row per CTA; tet_finalize_kernel adds the rows in CTA
 // order, so the result is bit-reproducible run to run (no atomics on doubles anywhere).
 // =================================================================================================
+struct alignas(64) TmapBlob { unsigned long long v[16]; }; // a CUtensorMap by value (kernel parameter space, __grid_constant__)
+
 struct TetArgs {
     VolumeView vol;
     MeshView mesh;
@@ -200,6 +203,8 @@ struct TetArgs {
     int vol_simple;                  // float volume: only non-negative finite values (scaled widening allowed)
     int pack;                        // w2: packed FP32 position arithmetic
     int lean;                        // w2: full/tail batch split, per-tet weight from phase A
+    const int4 *tile_box;            // w2 PF: voxel box of every 32-tet tile of [tet_begin, tet_end) (tile_box_kernel)
+    TmapBlob tmap;                   // w2 PF: CUtensorMap of the volume (box kPfBoxX x kPfBoxY x kPfBoxZ), valid when tile_box is set
 };
 
 template <typename VoxT, int G, bool WITH_C>
@@ -586,6 +591,54 @@ DSC_HD int g32_slot_off(int L)
     return (int)((w >> (8 * (L & 3))) & 0xffu);
 }
 
+// ---- L2 prefetch of a tile's voxels (w2 PF, variant bit 65536) ---------------------------------------------------------------
+// The gathers of a tile touch a box of about 52 x 11 x 11 voxels (C4) that nobody has read before about 40 % of the time: those
+// first touches pay the DRAM latency inside the sample loop.  tile_box_kernel records, per 32-tet tile of the launch range, the
+// integer voxel box of its active tets (once per snapshot and range); the integration kernel then has ONE lane ask the TMA unit
+// to pull the box of the warp's NEXT tile into L2 (cp.async.bulk.prefetch.tensor, a handful of instructions per tile -- the
+// per-lane prefetch instructions cost an L1 wavefront per line, as much as the gathers they would help).  A hint only: results
+// cannot depend on it.
+constexpr int kPfBoxX = 64, kPfBoxY = 4, kPfBoxZ = 4; // box of the tensor map (elements)
+
+__global__ void __launch_bounds__(256) tile_box_kernel(MeshView m, unsigned tet_begin, unsigned tet_end, int include_bound, int X, int Y, int Z, int x_align, int4 *__restrict__ box)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const unsigned n_tiles = (tet_end - tet_begin + 31) / 32;
+    if (tile >= n_tiles) return;
+    const unsigned t = tet_begin + tile * 32 + lane;
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    if (t < tet_end && (include_bound || __ldg(m.tet_label + t) != 0)) {
+        const uint4 nd = __ldg(m.tet_nodes + t);
+        const float4 p0 = __ldg(m.pos4f + nd.x), p1 = __ldg(m.pos4f + nd.y), p2 = __ldg(m.pos4f + nd.z), p3 = __ldg(m.pos4f + nd.w);
+        lo[0] = (int)floorf(fminf(fminf(p0.x, p1.x), fminf(p2.x, p3.x))); hi[0] = (int)floorf(fmaxf(fmaxf(p0.x, p1.x), fmaxf(p2.x, p3.x)));
+        lo[1] = (int)floorf(fminf(fminf(p0.y, p1.y), fminf(p2.y, p3.y))); hi[1] = (int)floorf(fmaxf(fmaxf(p0.y, p1.y), fmaxf(p2.y, p3.y)));
+        lo[2] = (int)floorf(fminf(fminf(p0.z, p1.z), fminf(p2.z, p3.z))); hi[2] = (int)floorf(fmaxf(fmaxf(p0.z, p1.z), fmaxf(p2.z, p3.z)));
+    }
+    const int dim[3] = {X, Y, Z};
+    int ext[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        lo[k] = max(__reduce_min_sync(0xffffffffu, lo[k]), 0);
+        hi[k] = min(__reduce_max_sync(0xffffffffu, hi[k]), dim[k] - 1);
+        // the TMA unit faults ("illegal instruction") on a box whose first element is not 16-byte aligned (scripts/tma_prefetch_probe.cu)
+        if (k == 0) lo[0] &= ~(x_align - 1);
+        ext[k] = hi[k] >= lo[k] ? hi[k] - lo[k] + 1 : 0;
+    }
+    // tiles that wrap around a row of the mesh span the whole volume in x: not worth prefetching
+    const bool ok = ext[0] > 0 && ext[1] > 0 && ext[2] > 0 && ext[0] <= 4 * kPfBoxX && ext[1] <= 8 * kPfBoxY && ext[2] <= 8 * kPfBoxZ;
+    if (lane == 0) box[tile] = make_int4(lo[0], lo[1], lo[2], ok ? (ext[0] | (ext[1] << 10) | (ext[2] << 20)) : 0);
+}
+
+DSC_D void tile_prefetch_l2(const TmapBlob *tmap, int4 b)
+{
+    const int ex = b.w & 1023, ey = (b.w >> 10) & 1023, ez = (b.w >> 20) & 1023;
+    for (int z = 0; z < ez; z += kPfBoxZ)
+        for (int y = 0; y < ey; y += kPfBoxY)
+            for (int x = 0; x < ex; x += kPfBoxX)
+                asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(b.x + x), "r"(b.y + y), "r"(b.z + z) : "memory");
+}
+
 // -------------------------------------------------------------------------------------------------
 // Warp-level two-phase form with origin-relative lattice coordinates (variant 128).
 //
@@ -614,8 +667,8 @@ DSC_HD int g32_slot_off(int L)
 // LEAN (variant bit 16384): full batches run without row clamps and masks, and the hot-path instantiation takes v / n^3 from
 // phase A instead of dividing once per round.  LEAN == 2 (bit 32768 as well): two full batches at a time -- eight gathers in
 // flight per lane, one wait instead of two for a 64-sample tet.
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false, int LEAN = 0>
-__global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(const TetArgs a)
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false, int LEAN = 0, bool PF = false>
+__global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(const __grid_constant__ TetArgs a)
 {
     constexpr int G = 8, U = 4;
     constexpr bool F32S = SIMPLE && sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral; // sums scaled by 2^-896 (widen_scaled)
@@ -926,6 +979,11 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     acc_vol += v;
                 }
             }
+        }
+        if constexpr (PF) {
+            // The box of this warp's next tile -> L2 while its phase A (ids -> positions -> records: two dependent DRAM round trips)
+            // runs.  Asked for a whole tile earlier (22 us at C4) the boxes of all resident warps overflow the L2: measured slower.
+            if (lane == 0 && tile + total_warps < n_tiles) tile_prefetch_l2(&a.tmap, __ldg(a.tile_box + tile + total_warps));
         }
     }
 #pragma unroll

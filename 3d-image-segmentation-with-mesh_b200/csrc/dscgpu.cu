@@ -9,6 +9,7 @@
 #include <vector>
 #include <algorithm>
 #include <new>
+#include <cuda.h> // CUtensorMap; the encoder is fetched with cudaGetDriverEntryPoint (no link against libcuda)
 
 #include "../../include/dscgpu.h"
 #include "dsc_kernels.cuh"
@@ -79,6 +80,14 @@ struct dscgpu_ctx {
     int force_thread_gather = 0; // 1: thread-per-node gather (first implementation) instead of warp-per-node
     int hot_want_sq = 0; // dscgpu_image_force_eval / dscgpu_tet_phase_sums_dev skip the second moment unless asked
     int tet_variant = 128; // see dscgpu_set_tet_variant; default = w2 (the fastest measured form: DESIGN.md section 9)
+    // w2 PF (variant bit 65536): tensor map of the volume (passed by value in the kernel arguments), voxel boxes of the 32-tet tiles of one launch range
+    TmapBlob tmap_host;
+    int tmap_state = 0; // 0 not tried, 1 ready, -1 unavailable (layout not expressible / no driver entry point)
+    int4 *d_tile_box = nullptr;
+    size_t tile_box_cap = 0;
+    unsigned tb_begin = 0, tb_end = 0;
+    int tb_bound = -1;
+    bool tb_valid = false;
     // bricked, padded copy of the volume for tet_sums_g32_kernel (dsc_tet_g32.cuh); rebuilt when the volume may have changed
     void *d_brick = nullptr;
     bool brick_valid = false;
@@ -255,6 +264,59 @@ template <typename VoxT> int launch_tpt_v(dscgpu_ctx *ctx, TetArgs &a, bool tex,
     return filter ? launch_tpt_t<VoxT, kFetchLdg, true>(ctx, a) : launch_tpt_t<VoxT, kFetchLdg, false>(ctx, a);
 }
 
+// w2 PF: a CUtensorMap over the volume (3-D, x fastest, box kPfBoxX x kPfBoxY x kPfBoxZ) for cp.async.bulk.prefetch.tensor.
+// Volumes whose row pitch is not a multiple of 16 bytes cannot be described: the kernel then runs without the prefetch.
+int ensure_tmap(dscgpu_ctx *ctx)
+{
+    if (ctx->tmap_state != 0) return DSCGPU_OK;
+    ctx->tmap_state = -1;
+    const size_t es = dtype_size(ctx->dtype);
+    const cuuint64_t X = (cuuint64_t)ctx->dims[0], Y = (cuuint64_t)ctx->dims[1], Z = (cuuint64_t)ctx->dims[2];
+    if ((X * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(ctx->d_vol) & 15) != 0) return DSCGPU_OK;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return DSCGPU_OK;
+    }
+    const CUtensorMapDataType dt = ctx->dtype == DSCGPU_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : ctx->dtype == DSCGPU_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                   : ctx->dtype == DSCGPU_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t gdim[3] = {X, Y, Z}, gstr[2] = {X * es, X * Y * es};
+    const cuuint32_t box[3] = {(cuuint32_t)kPfBoxX, (cuuint32_t)kPfBoxY, (cuuint32_t)kPfBoxZ}, estr[3] = {1, 1, 1};
+    if (reinterpret_cast<encode_fn>(fn)(&tm, dt, 3, ctx->d_vol, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return DSCGPU_OK;
+    static_assert(sizeof(CUtensorMap) == sizeof(TmapBlob), "CUtensorMap is 128 bytes");
+    memcpy(&ctx->tmap_host, &tm, sizeof(CUtensorMap));
+    ctx->tmap_state = 1;
+    return DSCGPU_OK;
+}
+
+// w2 PF: voxel boxes of the 32-tet tiles of [begin, end), once per snapshot and range
+int ensure_tile_boxes(dscgpu_ctx *ctx, const TetArgs &a)
+{
+    if (ctx->tb_valid && ctx->tb_begin == a.tet_begin && ctx->tb_end == a.tet_end && ctx->tb_bound == a.include_bound) return DSCGPU_OK;
+    const unsigned n_tiles = (a.tet_end - a.tet_begin + 31) / 32;
+    if (!n_tiles) return DSCGPU_OK;
+    if ((size_t)n_tiles > ctx->tile_box_cap) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(ctx->stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { ctx->tb_valid = false; return DSCGPU_OK; }
+        if (ctx->d_tile_box) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_tile_box); ctx->d_tile_box = nullptr; ctx->tile_box_cap = 0; }
+        const size_t want = (size_t)n_tiles + n_tiles / 4 + 64;
+        CK(cudaMalloc(&ctx->d_tile_box, want * sizeof(int4)));
+        ctx->tile_box_cap = want;
+    }
+    tile_box_kernel<<<(n_tiles + 7) / 8, 256, 0, ctx->stream>>>(a.mesh, a.tet_begin, a.tet_end, a.include_bound, ctx->dims[0], ctx->dims[1], ctx->dims[2], (int)(16 / dtype_size(ctx->dtype)), ctx->d_tile_box);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->tb_begin = a.tet_begin; ctx->tb_end = a.tet_end; ctx->tb_bound = a.include_bound;
+    ctx->tb_valid = true;
+    return DSCGPU_OK;
+}
+
 // float volumes: one pass that tells whether every voxel is a non-negative finite number (scaled widening, dsc_kernels.cuh)
 int ensure_volume_flags(dscgpu_ctx *ctx)
 {
@@ -276,9 +338,9 @@ int ensure_volume_flags(dscgpu_ctx *ctx)
     return DSCGPU_OK;
 }
 
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false, int LEAN = 0> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false, int LEAN = 0, bool PF = false> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
 {
-    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET, BRICK, SIMPLE, PACK, LEAN>;
+    auto kern = tet_integrate_w2_kernel<VoxT, WANT_SQ, PER_TET, BRICK, SIMPLE, PACK, LEAN, PF>;
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     if (occ < 1) occ = 1;
@@ -301,6 +363,12 @@ template <typename VoxT> int launch_w2(dscgpu_ctx *ctx, TetArgs &a)
     if (a.brick) { // bricked volume (variant bit 2048)
         if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true, true>(ctx, a) : launch_w2_t<VoxT, true, false, true>(ctx, a);
         return per_tet ? launch_w2_t<VoxT, false, true, true>(ctx, a) : launch_w2_t<VoxT, false, false, true>(ctx, a);
+    }
+    if (a.tile_box && !a.want_sq && !per_tet) { // L2 prefetch of the next tile's voxels (variant bit 65536); hot-path instantiations only
+        if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
+            if (a.vol_simple) return launch_w2_t<VoxT, false, false, false, true, false, 0, true>(ctx, a);
+        }
+        return launch_w2_t<VoxT, false, false, false, false, false, 0, true>(ctx, a);
     }
     if (a.lean && !a.want_sq && !per_tet && !a.brick && !a.pack) { // variant bit 16384; hot-path instantiations only
         if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
@@ -584,6 +652,16 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
             if (rf) return rf;
             a.vol_simple = ctx->vol_simple ? 1 : 0;
         }
+        a.tile_box = nullptr;
+        if ((ctx->tet_variant & 65536) && !(ctx->tet_variant & (2048 | 8192 | 16384)) && !a.want_sq && !(a.tet_total || a.tet_vol || a.tet_mean)) {
+            int rt = ensure_tmap(ctx);
+            if (rt) return rt;
+            if (ctx->tmap_state == 1) {
+                rt = ensure_tile_boxes(ctx, a);
+                if (rt) return rt;
+                if (ctx->tb_valid) { a.tile_box = ctx->d_tile_box; a.tmap = ctx->tmap_host; }
+            }
+        }
         if ((ctx->tet_variant & 2048) && g32_fits(ctx)) { // ... gathering from the bricked, padded copy of the volume
             int r = ensure_bricks(ctx);
             if (r) return r;
@@ -652,6 +730,8 @@ int tet_pass_range(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, con
     a.vol_simple = 0;
     a.pack = 0;
     a.lean = 0;
+    a.tile_box = nullptr;
+    memset(&a.tmap, 0, sizeof(a.tmap));
     return launch_tet(ctx, a, nc > 0 && (o.d_energy || o.d_variation));
 }
 
@@ -984,6 +1064,7 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
     ctx->geom_async = false;
+    ctx->tb_valid = false;
     ctx->init_means_valid = false;
     ctx->has_tet_faces = false;
     CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ks));
@@ -1164,6 +1245,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
                       &ctx->h_node_inc, &ctx->h_node_active, &ctx->h_out, &ctx->h_flag, &ctx->h_upd};
     for (PinBuf *b : pins) b->release();
     if (ctx->d_vol) cudaFree(ctx->d_vol);
+    if (ctx->d_tile_box) cudaFree(ctx->d_tile_box);
     if (ctx->d_sum_table) cudaFree(ctx->d_sum_table);
     if (ctx->d_tet_bary) cudaFree(ctx->d_tet_bary);
     if (ctx->d_tet_bary_f) cudaFree(ctx->d_tet_bary_f);
@@ -1346,6 +1428,7 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
     ctx->geom_async = false;
+    ctx->tb_valid = false;
     ctx->init_means_valid = false;
     ctx->has_tet_faces = false;
 
@@ -1473,6 +1556,7 @@ int dscgpu_update_commit(dscgpu_ctx *ctx, int replace_faces)
     ctx->validation_pending = true;
     ctx->init_means_valid = false;
     ctx->geom_async = false;
+    ctx->tb_valid = false;
     ctx->staging_valid = false; // the pinned staging of the last full snapshot is stale: dscgpu_image_force_eval(ctx, NULL, ...) must not re-upload it
     return DSCGPU_OK;
 }
@@ -2123,7 +2207,7 @@ int dscgpu_build_texture(dscgpu_ctx *ctx)
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 65536, "variant is a 16-bit field");
+    ARG(variant >= 0 && variant < 131072, "variant is a 17-bit field");
     if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
         int r = dscgpu_build_texture(ctx);
         if (r) return r;

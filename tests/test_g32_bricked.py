@@ -15,6 +15,7 @@ RTOL = 1e-6
 G32 = 1024 | 128
 W2B = 2048 | 128  # w2 gathering from the bricked copy
 W2P = 8192 | 128  # w2 with packed FP32 position arithmetic (hot-path instantiation only)
+W2PF = 65536 | 128  # w2 with the TMA L2 prefetch of the next tile's voxel box (hot-path instantiation only; a hint: same results)
 
 
 def _random_tets(rng, dims_xyz, n_tets, size_lo, size_hi, margin):
@@ -59,7 +60,7 @@ def _check(pkg, flat, vol, pos, tets, labels, P, exact=True):
         np.testing.assert_allclose(o2["phase_volume"], volu, rtol=RTOL)
         outs[variant] = o
     # the hot path proper (dscgpu_tet_phase_sums_dev: no second moment, no per-tet outputs) through the fused evaluation
-    for variant in (G32, W2B, W2P, 128 | 4096, 128 | 16384, 128 | 16384 | 32768):
+    for variant in (G32, W2B, W2P, W2PF, 128 | 4096, 128 | 16384, 128 | 16384 | 32768):
         seg.set_tet_variant(variant)
         mean, _ = seg.image_force_eval(_snap(pos, tets, labels), mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_ATOMIC)
         ok = volu > 0
@@ -205,4 +206,28 @@ def test_volume_modified_rebuilds_the_bricked_copy(pkg, flat):
     ref = flat.tet_integrate(vol2, tets, pos, want_hash=False)
     assert np.array_equal(b["total"], ref["total"])
     assert not np.array_equal(a["total"], b["total"])
+    img.close()
+
+
+def test_l2_prefetch_variant_on_many_tiles(pkg, flat):
+    """Variant bit 65536 only adds TMA L2 prefetches of the next tile's voxel box (a hint).  It engages when a launch has
+    more 32-tet tiles than resident warps, i.e. above ~114 K tets: the sums must be bit-identical to plain w2's."""
+    syn = pkg.synthetic
+    vol = syn.shells_phantom(160, sigma=0.05, seed=5, dtype=np.float32)
+    pos, tets, n_grid = syn.grid_mesh(vol.shape[::-1], 5.9, jitter=0.25, seed=9)
+    assert len(tets) > 130000
+    labels = syn.boundary_layer_labels(tets, n_grid) * (1 + (np.arange(len(tets)) % 3))
+    img = pkg.Image3D(vol)
+    seg = pkg.SegmentFunction(img, 3)
+    seg.set_snapshot(_snap(pos, tets, labels))
+    outs = {}
+    for variant in (128, W2PF):
+        seg.set_tet_variant(variant)
+        for _ in range(2):  # second pass: tile boxes cached
+            mean, _ = seg.image_force_eval(None, mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_ATOMIC)
+        outs[variant] = (np.array(mean), seg.last_sample_count())
+    assert np.array_equal(outs[128][0], outs[W2PF][0]) and outs[128][1] == outs[W2PF][1]
+    ref = flat.tet_integrate(vol, tets, pos, want_hash=False)
+    tot, volu, _ = flat.phase_reduce(labels, ref["total"], ref["vol"], 3)
+    np.testing.assert_allclose(outs[W2PF][0], tot / volu, rtol=RTOL)
     img.close()

@@ -906,7 +906,13 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     }
                     VoxT val[U];
 #pragma unroll
+#if defined(W2_FAKE) && W2_FAKE == 1 // measurement only (scripts/w2_gather_bound.sh): wrong voxels, never defined by build.py
+                    for (int u = 0; u < U; u++) val[u] = __ldg(vol + (idx[u] & 4095));
+#elif defined(W2_FAKE) && W2_FAKE == 2
+                    for (int u = 0; u < U; u++) val[u] = reinterpret_cast<const VoxT *>(s_tabd)[idx[u] & 1023];
+#else
                     for (int u = 0; u < U; u++) val[u] = (!TAIL || idx[u] >= 0) ? __ldg(vol + idx[u]) : (VoxT)0;
+#endif
 #pragma unroll
                     for (int u = 0; u < U; u++) add_voxel(val[u]);
                 };

@@ -678,9 +678,12 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
     __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0-.5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
     __shared__ int2 w_m[8][32];                // meta, (O_linear - fold)
     __shared__ double w_v[8][32];
-    __shared__ double w_rw[LEAN ? 8 : 1][32]; // v / n^3 from phase A (one division per tet, lanes in parallel)
+    constexpr bool RW = LEAN != 0 || !PER_TET; // sums only: v / n^3 once per tet in phase A (lanes in parallel) instead of a division per round
+    __shared__ double w_rw[RW ? 8 : 1][32];
+    __shared__ unsigned long long w_ns[8];     // samples processed by each warp (kept out of the registers of phase B)
     __shared__ uint4 w_nd[8][32];
     for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
+    if (threadIdx.x < 8) w_ns[threadIdx.x] = 0;
     if (PACK) {
         // entry e = (iteration slot * 2 + p) * 8 + g holds rows i = 32 it + 16 p + g and j = i + 8 of its level (clamped to the last
         // row) as (a1_i, a1_j, a2_i, a2_j), (a3_i, a3_j, eps_i, eps_j): each LDS.128 yields two register pairs ready for FFMA2
@@ -719,7 +722,6 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
     };
 
     double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane_g + 1
-    unsigned long long nsamp = 0;
 
     for (unsigned tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += total_warps) {
         const unsigned base_t = a.tet_begin + tile * 32;
@@ -733,6 +735,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
         {
             int meta = 0, olin = 0;
             bool active = false, big = false, fast = false;
+            int n3_lane = 0;
             float4 rq0 = make_float4(0, 0, 0, 0), re1 = rq0, re2 = rq0, re3 = rq0;
             double rv = 0;
             uint4 rnd = make_uint4(0, 0, 0, 0);
@@ -747,7 +750,8 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
                     const double v = tet_volume(p0, p1, p2, p3);
                     const int L = tet_level(v);
-                    big = (L + 1) * (L + 1) * (L + 1) > G * U;
+                    n3_lane = (L + 1) * (L + 1) * (L + 1);
+                    big = n3_lane > G * U;
                     const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
                     const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
                     const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
@@ -786,12 +790,16 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
             const unsigned m_big = __ballot_sync(0xffffffffu, active && big);
             const unsigned lt = (1u << lane) - 1u;
             n_act = __popc(m_small) + __popc(m_big);
+            {
+                const unsigned tile_ns = __reduce_add_sync(0xffffffffu, (unsigned)n3_lane);
+                if (lane == 0) w_ns[warp] += tile_ns;
+            }
             const int slot = active ? (big ? __popc(m_small) + __popc(m_big & lt) : __popc(m_small & lt))
                                     : n_act + __popc(~(m_small | m_big) & lt);
             w_m[warp][slot] = make_int2(meta, olin);
             if (active) {
                 w_v[warp][slot] = rv;
-                if (LEAN) { const int Lr = (meta >> 8) & 0xf; w_rw[warp][slot] = rv / (double)((Lr + 1) * (Lr + 1) * (Lr + 1)); }
+                if (RW) w_rw[warp][slot] = rv / (double)n3_lane;
                 w_nd[warp][slot] = rnd;
                 if (fast) { w_q0[warp][slot] = rq0; w_e1[warp][slot] = re1; w_e2[warp][slot] = re2; w_e3[warp][slot] = re3; }
             }
@@ -967,11 +975,10 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
             if (F32S) s = s * 0x1p+896; // exact: back to the true sum
             if (active) {
                 const double v = w_v[warp][j];
-                // total = total * v / a.size()  (image3d.cpp:371); LEAN without per-tet outputs: v / n^3 comes from phase A (sums: 1e-6 quantities)
-                const double tot = (LEAN && !PER_TET) ? s * w_rw[warp][j] : s * v / (double)n3;
-                const double tsq = WANT_SQ ? sq * v / (double)n3 : 0.0;
+                // total = total * v / a.size()  (image3d.cpp:371) when per-tet values go out; the per-label sums alone are 1e-6 quantities
+                const double tot = (RW && !PER_TET) ? s * w_rw[warp][j] : s * v / (double)n3;
+                const double tsq = WANT_SQ ? ((RW && !PER_TET) ? sq * w_rw[warp][j] : sq * v / (double)n3) : 0.0;
                 if (lane_g == 0) {
-                    nsamp += (unsigned long long)n3;
                     if (PER_TET) {
                         const unsigned t = base_t + ((meta >> 16) & 31);
                         if (a.tet_total) a.tet_total[t] = tot;
@@ -998,8 +1005,6 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
         acc_sq += shfl_xor_d(acc_sq, m);
         acc_vol += shfl_xor_d(acc_vol, m);
     }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
     __shared__ double sm[8][3 * kMaxPhase];
     if (lane < kMaxPhase) {
         sm[warp][lane] = acc_tot;
@@ -1012,7 +1017,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
         for (int wdx = 0; wdx < 8; wdx++) r += sm[wdx][threadIdx.x];
         a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
     }
-    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+    if (lane == 0 && w_ns[warp]) atomicAdd(a.sample_count, w_ns[warp]);
 }
 
 // -------------------------------------------------------------------------------------------------

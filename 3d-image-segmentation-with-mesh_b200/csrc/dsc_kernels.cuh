@@ -667,6 +667,16 @@ DSC_D void tile_prefetch_l2(const TmapBlob *tmap, int4 b)
 // LEAN (variant bit 16384): full batches run without row clamps and masks, and the hot-path instantiation takes v / n^3 from
 // phase A instead of dividing once per round.  LEAN == 2 (bit 32768 as well): two full batches at a time -- eight gathers in
 // flight per lane, one wait instead of two for a 64-sample tet.
+// per-tet record of the w2 kernel: 112 bytes = 28 words, so the four records a round reads (and the records eight lanes write) fall in distinct banks
+struct alignas(16) W2Rec {
+    float4 q0, e1, e2, e3; // (Q0 - .5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
+    uint4 nd;              // node ids (exact fallback)
+    int2 m;                // meta, (O_linear - fold)
+    double v, rw;          // volume, v / n^3
+    double pad;
+};
+static_assert(sizeof(W2Rec) == 112, "W2Rec layout");
+
 template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false, int LEAN = 0, bool PF = false>
 __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(const __grid_constant__ TetArgs a)
 {
@@ -675,13 +685,11 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
     constexpr int kPairEntries = 9 * 2 * 8;    // levels n <= 5: 1+1+1+2+4 iterations of 32 rows, two row pairs per lane and iteration
     __shared__ float4 s_lat[PACK ? (2 * kPairEntries) : kSmemRows]; // (a1, a2, a3, eps) per table row; PACK: pairs, see below
     __shared__ double2 s_tabd[2 * kSmemRows];  // exact rows for the fallback
-    __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0-.5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
-    __shared__ int2 w_m[8][32];                // meta, (O_linear - fold)
-    __shared__ double w_v[8][32];
+    // one record per tet of the warp's tile, written in phase A (lane <-> tet), read in phase B (8 lanes <-> tet): a single array, so a
+    // round addresses all its fields from one base (eight separate arrays cost ~40 address instructions per round under the register cap)
+    __shared__ W2Rec w_rec[8][32];
     constexpr bool RW = LEAN != 0 || !PER_TET; // sums only: v / n^3 once per tet in phase A (lanes in parallel) instead of a division per round
-    __shared__ double w_rw[RW ? 8 : 1][32];
     __shared__ unsigned long long w_ns[8];     // samples processed by each warp (kept out of the registers of phase B)
-    __shared__ uint4 w_nd[8][32];
     for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
     if (threadIdx.x < 8) w_ns[threadIdx.x] = 0;
     if (PACK) {
@@ -796,19 +804,19 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
             }
             const int slot = active ? (big ? __popc(m_small) + __popc(m_big & lt) : __popc(m_small & lt))
                                     : n_act + __popc(~(m_small | m_big) & lt);
-            w_m[warp][slot] = make_int2(meta, olin);
+            w_rec[warp][slot].m = make_int2(meta, olin);
             if (active) {
-                w_v[warp][slot] = rv;
-                if (RW) w_rw[warp][slot] = rv / (double)n3_lane;
-                w_nd[warp][slot] = rnd;
-                if (fast) { w_q0[warp][slot] = rq0; w_e1[warp][slot] = re1; w_e2[warp][slot] = re2; w_e3[warp][slot] = re3; }
+                w_rec[warp][slot].v = rv;
+                if (RW) w_rec[warp][slot].rw = rv / (double)n3_lane;
+                w_rec[warp][slot].nd = rnd;
+                if (fast) { w_rec[warp][slot].q0 = rq0; w_rec[warp][slot].e1 = re1; w_rec[warp][slot].e2 = re2; w_rec[warp][slot].e3 = re3; }
             }
         }
         __syncwarp();
         // ---------------- phase B: 8 lanes <-> tet; group grp walks tets grp, grp+4, ... of the tile ----------------
         for (int r = 0; r * 4 < n_act; r++) {
             const int j = r * 4 + grp;
-            const int2 mm = w_m[warp][j];
+            const int2 mm = w_rec[warp][j].m;
             const int meta = mm.x;
             const bool active = (meta & (1 << 12)) != 0;
             const int label = meta & 0xff;
@@ -835,7 +843,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                 }
             };
             if (meta & (1 << 13)) {
-                const float4 q0 = w_q0[warp][j], e1 = w_e1[warp][j], e2 = w_e2[warp][j], e3 = w_e3[warp][j];
+                const float4 q0 = w_rec[warp][j].q0, e1 = w_rec[warp][j].e1, e2 = w_rec[warp][j].e2, e3 = w_rec[warp][j].e3;
                 const float thr = q0.w;
                 const unsigned obase = (unsigned)mm.y;
                 const float4 *__restrict__ tl = s_lat + off;
@@ -847,6 +855,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     constexpr int U = 4 * decltype(nb_c)::value; // samples per lane in this call (shadows the kernel's U)
                     int idx[U];
                     unsigned unsafe = 0;
+                    [[maybe_unused]] float emax[U]; // scalar path: largest |q - round(q)| of each sample; one test per batch on the common path
                     if constexpr (PACK) {
                         const f32x2 M2 = pk2(MAGIC, MAGIC), NM2 = pk2(-MAGIC, -MAGIC), NEG1 = pk2(-1.0f, -1.0f);
 #pragma unroll
@@ -894,11 +903,21 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                             lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) + obase);
                         }
                         idx[u] = ok ? lin : -1;
-                        if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) unsafe |= 1u << u;
+                        emax[u] = fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)); // rows past the last one repeat it: harmless in the batch-wide test
                     }
+                    }
+                    if constexpr (!PACK) {
+                        float eall = emax[0];
+#pragma unroll
+                        for (int u = 1; u < U; u++) eall = fmaxf(eall, emax[u]);
+                        if (eall >= thr) {
+#pragma unroll
+                            for (int u = 0; u < U; u++)
+                                if (idx[u] >= 0 && emax[u] >= thr) unsafe |= 1u << u;
+                        }
                     }
                     if (unsafe) { // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
-                        const uint4 nd = w_nd[warp][j];
+                        const uint4 nd = w_rec[warp][j].nd;
                         const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
                         const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
 #pragma unroll
@@ -937,7 +956,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                 }
             } else if (active) {
                 // exact path (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491)
-                const uint4 nd = w_nd[warp][j];
+                const uint4 nd = w_rec[warp][j].nd;
                 const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
                 const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
                 const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
@@ -974,10 +993,10 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
             }
             if (F32S) s = s * 0x1p+896; // exact: back to the true sum
             if (active) {
-                const double v = w_v[warp][j];
+                const double v = w_rec[warp][j].v;
                 // total = total * v / a.size()  (image3d.cpp:371) when per-tet values go out; the per-label sums alone are 1e-6 quantities
-                const double tot = (RW && !PER_TET) ? s * w_rw[warp][j] : s * v / (double)n3;
-                const double tsq = WANT_SQ ? ((RW && !PER_TET) ? sq * w_rw[warp][j] : sq * v / (double)n3) : 0.0;
+                const double tot = (RW && !PER_TET) ? s * w_rec[warp][j].rw : s * v / (double)n3;
+                const double tsq = WANT_SQ ? ((RW && !PER_TET) ? sq * w_rec[warp][j].rw : sq * v / (double)n3) : 0.0;
                 if (lane_g == 0) {
                     if (PER_TET) {
                         const unsigned t = base_t + ((meta >> 16) & 31);

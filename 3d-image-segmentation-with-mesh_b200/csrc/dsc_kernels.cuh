@@ -763,10 +763,17 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
                     const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
                     const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
-                    // strictly inside the volume with a margin: no sample can leave [1, dim-1), so no bounds checks, no negatives
+                    // Inside the volume: no sample can leave [0, dim), so no bounds checks and no negative coordinates (trunc == floor).
+                    // With a margin that is plain.  Without one -- the first layer of tets of a DSC mesh has nodes exactly on the faces of
+                    // the volume -- it still holds when the tet is not a sliver along that axis: every weight of every row is at least
+                    // b_min = 1/(4n) - 5e-7 >= 0.05 (a_k >= 1 for n <= 5, checked when the table is built) and the weights sum to 1 + eps,
+                    // |eps| <= 2.1e-6, so  lo (1 + eps) + b_min (hi - lo) <= sum_k b_k p_k <= hi (1 + eps) - b_min (hi - lo):  with
+                    // -1e-7 <= lo, hi <= dim + 1e-7 and hi - lo >= 1e-4 dim the sample coordinate lies in (0, dim).
                     // (BRICK: inside the padded copy with a margin of two voxels; the padding stands in for the bounds test)
+                    auto axis_in = [](double lo, double hi, int dim) { return lo >= -1.0e-7 && hi <= (double)dim + 1.0e-7 && hi - lo >= 1.0e-4 * (double)dim; };
                     const bool interior = BRICK ? (lox >= -6.0 && loy >= -6.0 && loz >= -6.0 && hix < (double)X + 6.0 && hiy < (double)Y + 6.0 && hiz < (double)Z + 6.0)
-                                                : (lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5);
+                                                : ((lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5) ||
+                                                   (axis_in(lox, hix, X) && axis_in(loy, hiy, Y) && axis_in(loz, hiz, Z)));
                     double ox = floor(lox), oy = floor(loy), oz = floor(loz);
                     if (BRICK && interior) { // round the origin down to a brick corner (the padding is a multiple of the brick)
                         ox = (double)((((int)ox + kBrickPad) & ~3) - kBrickPad);

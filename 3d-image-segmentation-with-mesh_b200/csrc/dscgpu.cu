@@ -79,7 +79,7 @@ struct dscgpu_ctx {
     cudaTextureObject_t vol_tex = 0;
     int force_thread_gather = 0; // 1: thread-per-node gather (first implementation) instead of warp-per-node
     int hot_want_sq = 0; // dscgpu_image_force_eval / dscgpu_tet_phase_sums_dev skip the second moment unless asked
-    int tet_variant = 128; // see dscgpu_set_tet_variant; default = w2 (the fastest measured form: DESIGN.md section 9)
+    int tet_variant = 128 | 16384; // see dscgpu_set_tet_variant; default = w2, full batches without clamps on the sums-only path (the fastest measured form: DESIGN.md section 9)
     // w2 PF (variant bit 65536): tensor map of the volume (passed by value in the kernel arguments), voxel boxes of the 32-tet tiles of one launch range
     TmapBlob tmap_host;
     int tmap_state = 0; // 0 not tried, 1 ready, -1 unavailable (layout not expressible / no driver entry point)
@@ -1192,6 +1192,7 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
                     av[k] = (double)lrint(4.0 * n * b[k]);
                     asum += (long)av[k];
                     ARG(fabs(b[k] - av[k] / (4.0 * n)) <= 5.0e-7, "sample table is not the expected 6-decimal lattice");
+                    ARG(av[k] >= 1.0, "sample table row on the boundary of the tet"); // w2's in-volume argument needs every weight >= 1/(4n) - 5e-7
                 }
                 ARG(asum == 4 * n, "sample table row does not sum to one on the lattice");
                 const double eps = ((b[0] + b[1]) + b[2]) + b[3] - 1.0;

@@ -535,7 +535,7 @@ def main_b200(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("tet_sums_g32_kernel" if int(os.environ.get("DSCGPU_TET_VARIANT", "128")) & 1024 else "tet_integrate_w2_kernel") if mean_mode == pkg.MEAN_TET else "zray pass", "kernel_ms": kernel_ms,
+                "kernel": ("tet_sums_g32_kernel" if int(os.environ.get("DSCGPU_TET_VARIANT", "16512")) & 1024 else "tet_integrate_w2_kernel") if mean_mode == pkg.MEAN_TET else "zray pass", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": tet_bytes_rank, "peak_source": peak_src,
                 "whole_step": {"algorithmic_bytes": tet_bytes + face_bytes, "achieved": (tet_bytes + face_bytes) / world / (ms_per_step * 1e-3) / 1e9}}
 

@@ -317,7 +317,7 @@ int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes);
  *   bit 14 (16384) with bit 7: full batches without row clamps, per-tet weight from phase A; + bit 15 (32768): two batches per wait
  *   bit 16 (65536) with bit 7 alone: one lane asks the TMA unit to pull the voxel box of the warp's next 32-tet tile into L2 (a hint:
  *                results identical; volumes whose row pitch is not a multiple of 16 bytes run without it)
- * Default 128 (w2, the fastest measured form; DESIGN.md section 9 has the numbers of the others).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
+ * Default 128 + 16384 (w2 with clamp-free full batches on the sums-only path, the fastest measured form; DESIGN.md section 9 has the numbers of the others).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
  * Per-candidate outputs (tet_energy / tet_variation) always use the v1 kernel. */
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant);
 int dscgpu_build_texture(dscgpu_ctx *ctx);

@@ -231,3 +231,24 @@ def test_l2_prefetch_variant_on_many_tiles(pkg, flat):
     tot, volu, _ = flat.phase_reduce(labels, ref["total"], ref["vol"], 3)
     np.testing.assert_allclose(outs[W2PF][0], tot / volu, rtol=RTOL)
     img.close()
+
+
+def test_nodes_exactly_on_the_volume_faces(pkg, flat):
+    """The first layer of tets of a DSC mesh has nodes exactly on the faces of the volume (coordinate 0.0 or dim).  w2 takes
+    such tets on its FP32-filtered path when no sample can leave the volume; slivers along a face stay on the exact path.
+    Every sample must still land in the reference's voxel (bit-equal per-tet totals), whichever path a tet took."""
+    rng = np.random.default_rng(77)
+    dims = (48, 40, 56)
+    vol = rng.uniform(0.05, 1.0, dims[::-1]).astype(np.float32)
+    pos, tets = _random_tets(rng, dims, 6000, 2.0, 9.0, margin=0.0)
+    pos = np.clip(pos, 0.0, np.array(dims, dtype=np.float64))  # many corners land exactly on a face
+    # slivers: all four corners within 1e-3 (or exactly on) of the top face of one axis
+    for k in range(600):
+        ax = k % 3
+        t = tets[k]
+        pos[t, ax] = dims[ax] - rng.uniform(0.0, 1.0e-3, 4) * (k % 2)
+    # and a negative-zero / tiny negative corner, which truncates to voxel 0
+    pos[tets[600:700, 0], 0] = -1.0e-15
+    labels = rng.integers(1, 4, len(tets))
+    outs = _check(pkg, flat, vol, pos, tets, labels, 3)
+    assert np.array_equal(outs[128]["total"], outs[W2B]["total"])

@@ -750,10 +750,10 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
             if (lane < nb) {
                 const unsigned t = base_t + lane;
                 const int label = __ldg(a.mesh.tet_label + t);
+                const uint4 nd = __ldg(a.mesh.tet_nodes + t); // with the label, not after it: one dependent round trip less per tile
                 active = a.include_bound || label != 0;
                 meta = (label & 0xff) | (lane << 16);
                 if (active) {
-                    const uint4 nd = __ldg(a.mesh.tet_nodes + t);
                     const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
                     const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
                     const double v = tet_volume(p0, p1, p2, p3);

@@ -862,14 +862,14 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     constexpr int U = 4 * decltype(nb_c)::value; // samples per lane in this call (shadows the kernel's U)
                     int idx[U];
                     unsigned unsafe = 0;
-                    [[maybe_unused]] float emax[U]; // scalar path: largest |q - round(q)| of each sample; one test per batch on the common path
+                    float emax[U]; // largest |q - round(q)| of each sample; one test per batch on the common path
                     if constexpr (PACK) {
                         const f32x2 M2 = pk2(MAGIC, MAGIC), NM2 = pk2(-MAGIC, -MAGIC), NEG1 = pk2(-1.0f, -1.0f);
 #pragma unroll
                         for (int pp = 0; pp < 2; pp++) { // rows (i, i + 8) in the two halves of a packed register
                             const ulonglong2 A = tl2[(it * 2 + pp) * 16], B = tl2[(it * 2 + pp) * 16 + 1];
                             const int i0 = base + 16 * pp;
-                            const bool ok0 = i0 <= last, ok1 = i0 + 8 <= last;
+                            const bool ok0 = !TAIL || i0 <= last, ok1 = !TAIL || i0 + 8 <= last;
                             const f32x2 a1 = A.x, a2 = A.y, a3 = B.x, ep = B.y;
                             f32x2 qx = fma2(ep, pk2(e1.w, e1.w), pk2(q0.x, q0.x)), qy = fma2(ep, pk2(e2.w, e2.w), pk2(q0.y, q0.y));
                             f32x2 qz = fma2(ep, pk2(e3.w, e3.w), pk2(q0.z, q0.z));
@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                                 const bool ok = k ? ok1 : ok0;
                                 const int lin = (int)(__float_as_uint(tz[k]) * (unsigned)XYi + __float_as_uint(ty[k]) * (unsigned)X + __float_as_uint(tx[k]) + obase);
                                 idx[2 * pp + k] = ok ? lin : -1;
-                                if (ok && fmaxf(fmaxf(fabsf(ex[k]), fabsf(ey[k])), fabsf(ez[k])) >= thr) unsafe |= 1u << (2 * pp + k);
+                                emax[2 * pp + k] = fmaxf(fmaxf(fabsf(ex[k]), fabsf(ey[k])), fabsf(ez[k]));
                             }
                         }
                     } else {
@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                         emax[u] = fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)); // rows past the last one repeat it: harmless in the batch-wide test
                     }
                     }
-                    if constexpr (!PACK) {
+                    {
                         float eall = emax[0];
 #pragma unroll
                         for (int u = 1; u < U; u++) eall = fmaxf(eall, emax[u]);
@@ -952,9 +952,9 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                 };
                 using N1 = std::integral_constant<int, 1>;
                 using N2 = std::integral_constant<int, 2>;
-                if (LEAN && !PACK) { // full batches first: no clamps, no masks
+                if (LEAN) { // full batches first: no clamps, no masks
                     int base = lane_g, it = 0;
-                    if (LEAN == 2)
+                    if (LEAN == 2 && !PACK)
                         for (; base - lane_g + 2 * G * U <= n3; base += 2 * G * U, it += 2) batch(std::false_type{}, N2{}, base, it);
                     for (; base - lane_g + G * U <= n3; base += G * U, it++) batch(std::false_type{}, N1{}, base, it);
                     for (; base < n3; base += G * U, it++) batch(std::true_type{}, N1{}, base, it);

@@ -370,6 +370,12 @@ template <typename VoxT> int launch_w2(dscgpu_ctx *ctx, TetArgs &a)
         }
         return launch_w2_t<VoxT, false, false, false, false, false, 0, true>(ctx, a);
     }
+    if (a.lean && a.pack && !a.want_sq && !per_tet && !a.brick) { // bits 8192 + 16384: packed arithmetic in clamp-free batches
+        if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
+            if (a.vol_simple) return launch_w2_t<VoxT, false, false, false, true, true, 1>(ctx, a);
+        }
+        return launch_w2_t<VoxT, false, false, false, false, true, 1>(ctx, a);
+    }
     if (a.lean && !a.want_sq && !per_tet && !a.brick && !a.pack) { // variant bit 16384; hot-path instantiations only
         if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
             if (a.vol_simple) return a.lean == 2 ? launch_w2_t<VoxT, false, false, false, true, false, 2>(ctx, a) : launch_w2_t<VoxT, false, false, false, true, false, 1>(ctx, a);

@@ -313,7 +313,7 @@ int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes);
  *                call without candidates and with include_bound == 0, the remaining bits choose the kernel for the other calls
  *   bit 11 (2048) with bit 7: w2 gathering from the bricked, padded copy of the volume
  *   bit 12 (4096) with bit 7: keep the general float widening (off: scaled widening when the volume allows it)
- *   bit 13 (8192) with bit 7: packed FP32 (FFMA2) position arithmetic in the hot-path instantiation
+ *   bit 13 (8192) with bit 7: packed FP32 (FFMA2) position arithmetic in the hot-path instantiation (also together with bit 14)
  *   bit 14 (16384) with bit 7: full batches without row clamps, per-tet weight from phase A; + bit 15 (32768): two batches per wait
  *   bit 16 (65536) with bit 7 alone: one lane asks the TMA unit to pull the voxel box of the warp's next 32-tet tile into L2 (a hint:
  *                results identical; volumes whose row pitch is not a multiple of 16 bytes run without it)

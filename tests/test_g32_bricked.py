@@ -60,7 +60,7 @@ def _check(pkg, flat, vol, pos, tets, labels, P, exact=True):
         np.testing.assert_allclose(o2["phase_volume"], volu, rtol=RTOL)
         outs[variant] = o
     # the hot path proper (dscgpu_tet_phase_sums_dev: no second moment, no per-tet outputs) through the fused evaluation
-    for variant in (G32, W2B, W2P, W2PF, 128 | 4096, 128 | 16384, 128 | 16384 | 32768):
+    for variant in (G32, W2B, W2P, W2PF, 128 | 4096, 128 | 16384, 128 | 16384 | 32768, 128 | 8192 | 16384):
         seg.set_tet_variant(variant)
         mean, _ = seg.image_force_eval(_snap(pos, tets, labels), mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_ATOMIC)
         ok = volu > 0

@@ -655,7 +655,10 @@ DSC_D void tile_prefetch_l2(const TmapBlob *tmap, int4 b)
 // the error bound -- and with it the fraction of samples that must be re-evaluated exactly -- by two orders of magnitude:
 //     |q - r| <= (41 Rmax + 5) * 2^-24 ;  delta = (48 Rmax + 8) * 2^-24.
 // floor() uses the 1.5*2^23 trick (no F2I), the voxel is widened with integer ops (no F2F): the XU pipe stays idle.
-// Tets touching the volume border, very large tets (n > kSmemLevels) and tets wider than 100 voxels use the exact path.
+// One guard-band test per batch (largest |q - round(q)| of the lane's four samples against 1/2 - delta); only when it fires are the
+// samples looked at one by one and the unsafe ones re-evaluated with the reference's FP64 sequence.
+// Tets reaching outside the volume, slivers along one of its faces (phase A has the rule and the argument), very large tets
+// (n > kSmemLevels) and tets wider than 100 voxels use the exact path.
 // -------------------------------------------------------------------------------------------------
 // BRICK (variant bit 2048): the same kernel gathering from the bricked, padded copy of the volume.  Origins are rounded down
 // to brick corners, so idx = base + rx + 28 hx + 4 ry + (Sy-8) hy + 8 rz + (Sz-32) hz with hx = floor(rx/4), hy = floor(ry/2),
@@ -664,9 +667,11 @@ DSC_D void tile_prefetch_l2(const TmapBlob *tmap, int4 b)
 // layer of tets along the volume border -- takes the filtered path.
 // PACK (variant bit 8192): the position arithmetic of a lane's four samples runs as two packed pairs (FFMA2 / FADD2), from a
 // copy of the lattice table laid out in pairs of rows (i, i + 8).
-// LEAN (variant bit 16384): full batches run without row clamps and masks, and the hot-path instantiation takes v / n^3 from
-// phase A instead of dividing once per round.  LEAN == 2 (bit 32768 as well): two full batches at a time -- eight gathers in
-// flight per lane, one wait instead of two for a 64-sample tet.
+// LEAN (variant bit 16384, part of the default): full batches run without row clamps and masks; only the last, partial batch of a
+// tet carries them.  LEAN == 2 (bit 32768 as well): two full batches at a time -- eight gathers in flight per lane, one wait
+// instead of two for a 64-sample tet.  Sums-only instantiations (no per-tet outputs) take v / n^3 from phase A instead of
+// dividing once per round, whatever LEAN is.
+// PF (variant bit 65536): one lane asks the TMA unit to pull the voxel box of the warp's next tile into L2 (tile_prefetch_l2).
 // per-tet record of the w2 kernel: 112 bytes = 28 words, so the four records a round reads (and the records eight lanes write) fall in distinct banks
 struct alignas(16) W2Rec {
     float4 q0, e1, e2, e3; // (Q0 - .5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)

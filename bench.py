@@ -14,6 +14,7 @@ processed per second, whole job.
   roofline   dominant kernel (per-tet integration): algorithmic bytes / CUDA-event duration vs the measured
              HBM copy peak in MEASURED_PEAKS.json.
   cpu_baseline  the reference's CPU path on this box's host cores, on a bounded sample of the same workload.
+  cpu_baseline_port  the flat restatement of that path (oracle/flat_oracle.cpp) on all host threads, same kind of sample.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref/dsc_ref, the unmodified
 reference sources built by oracle/Makefile; falls back to the flat oracle port when that binary is absent)
@@ -152,13 +153,13 @@ def reference_binary():
     return p if os.path.exists(p) else None
 
 
-def run_reference_sample(pkg, cfg_name, target_seconds, jitter):
+def run_reference_sample(pkg, cfg_name, target_seconds, jitter, force_port=False):
     """Times the reference CPU path on a bounded sample of the workload: the same phantom family and the same mesh
     edge length, on a sub-volume sized so that one pass takes roughly `target_seconds`.  Returns dict."""
     syn = pkg.synthetic
     cfg = syn.CONFIGS[cfg_name]
     edge = syn.edge_for_cells(cfg["n"], cfg["cells"])
-    binp = reference_binary()
+    binp = None if force_port else reference_binary()
     # the reference builds an is_mesh complex (std::map based, ~6 us/tet) and samples ~1 us/tet: keep ~150 K tets
     n_sub = min(cfg["n"], 192 if target_seconds >= 10 else 128)
     if cfg_name == "C2":
@@ -546,6 +547,14 @@ def main_b200(args):
             cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # the baseline is a reported extra; never fail the bench for it
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    # next to the reference on one core, the flat restatement on all host threads (a reported figure, never the target)
+    cpu_port = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_port = run_reference_sample(pkg, args.config, 10.0, args.jitter, force_port=True)
+            cpu_port = {k: cpu_port[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # noqa: BLE001 -- never fail the bench line over the second baseline
+            cpu_port = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
     check = {"mean": [float(x) for x in d_mean.cpu().tolist()], "force_l2": float(torch.linalg.vector_norm(d_forces).item()),
              "force_sum": [float(x) for x in forces_rows.sum(dim=0).cpu().tolist()]}
@@ -563,7 +572,7 @@ def main_b200(args):
                 "steps": e2e_steps},
         "e2e_incremental": e2e_incr,
         "gpu_launches": int(launches_per_step[0] * args.steps),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_baseline_port": cpu_port, "clocks": clocks,
         "kernel_ms": {"tet_or_zray": float(np.mean(tet_ms)), "force": float(np.mean(force_ms)), "step_min": float(step_ms.min()),
                       "step_max": float(step_ms.max())},
         "setup_s": build_s, "check": check,

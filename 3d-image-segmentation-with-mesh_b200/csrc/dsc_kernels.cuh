@@ -149,13 +149,19 @@ DSC_D double widen_scaled(float f)
     return __hiloint2double((int)(b >> 3), (int)(b << 29));
 }
 
-// flags bit 0: the float volume holds something other than non-negative finite numbers
+// flags[0] bit 0: the float volume holds something other than non-negative finite numbers; flags[1]: the largest bit pattern
+// (for non-negative finite floats: the bit pattern of the largest voxel)
 __global__ void volume_flags_kernel(const float *__restrict__ vol, size_t n, unsigned *flags)
 {
-    unsigned f = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        if (__float_as_uint(__ldg(vol + i)) >= 0x7f800000u) f = 1;
+    unsigned f = 0, mx = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned b = __float_as_uint(__ldg(vol + i));
+        if (b >= 0x7f800000u) f = 1;
+        else mx = max(mx, b);
+    }
     if (__any_sync(0xffffffffu, f) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(flags + 1, mx);
 }
 
 __global__ void pos_to_float_kernel(const double4 *__restrict__ pos4, float4 *__restrict__ pos4f, unsigned n)
@@ -205,6 +211,12 @@ struct TetArgs {
     int lean;                        // w2: full/tail batch split, per-tet weight from phase A
     const int4 *tile_box;            // w2 PF: voxel box of every 32-tet tile of [tet_begin, tet_end) (tile_box_kernel)
     TmapBlob tmap;                   // w2 PF: CUtensorMap of the volume (box kPfBoxX x kPfBoxY x kPfBoxZ), valid when tile_box is set
+    // staged kernel (dsc_tet_staged.cuh)
+    const TmapBlob *stg_maps;        // [16][16] tensor maps of the volume in device memory: box = (u+1) x 16 bytes by (r+1) rows by 1 slice
+    int stg_slot_bytes;              // shared-memory slot of one warp (multiple of 1024)
+    unsigned *stg_counter;           // tile fetch counter, zero at launch
+    long long *stg_partials;         // [gridDim.x][3*kMaxPhase] fixed-point rows: total, sumsq, volume
+    double stg_scale[3];             // fixed-point scales (powers of two) of total, sumsq, volume
 };
 
 template <typename VoxT, int G, bool WITH_C>

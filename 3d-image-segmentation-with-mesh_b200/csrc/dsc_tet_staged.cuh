@@ -1,0 +1,568 @@
+// dsc_tet_staged.cuh -- per-tet voxel integration with the tile's voxel box staged in shared memory by TMA.
+//
+// image3d::get_tetra_intensity (DEMO/image3d.cpp:351-382) over all tets, fused with the per-label reduction, as the hot path of
+// the image-energy evaluation.  What is different from tet_integrate_w2_kernel (dsc_kernels.cuh):
+//
+//  * lane <-> tet for the whole tile of 32 consecutive tets.  The sample table of the reference is a lattice
+//    (tools/gen_tables.py restates its generator, DEMO/image3d.cpp:256-306): the unit cube is cut into n^3 cells, every cell
+//    into six tets, and the centroids with x+y+z < 1 are kept.  In barycentric numerators a_k = 4n b_k (exact up to the
+//    6-decimal rounding eta_k of the printed literals) a row is
+//         a1 = 4j + oy,  a2 = 4i + ox,  a3 = 4k + oz,   (ox,oy,oz) one of the six kOff vectors, (i,j,k) the cell,
+//    so with D_k = (P_k - P0)/n and E_k = D_k/4 the sample position is
+//         P0 + j D1 + i D2 + k D3  +  (oy E1 + ox E2 + oz E3)   (+ eps P0 + tau, see below).
+//    With the row index a compile-time constant (every lane of the warp is at the same row of its own tet) the cell corner is
+//    shared by up to six samples and a sample costs ONE packed add for x,y and half a packed add for z, instead of twelve FMAs
+//    and a table row from shared memory.  The rows of level n-1 are a subset of the (cell, offset) slots of level n
+//    (scripts/lattice_structure.py), so tets of level NB-1 ride the level-NB instruction stream with their own D, E.
+//  * the voxels a tile can touch form a small box (32 consecutive tets of a DSC grid mesh: ~52 x 10 x 10 voxels).  One lane
+//    per z slice asks the TMA unit for it (cp.async.bulk.tensor.3d, one tensor map per (row bytes, rows) pair), the warp waits
+//    on its mbarrier and every gather is an LDS: no L1 tags, no sectors, no DRAM latency inside the sample loop.
+//  * one CTA per SM, eight warps, one box slot per warp; tiles are fetched dynamically (one atomicAdd per tile).
+//  * per-label sums are accumulated as 64-bit fixed point (exact integer adds of per-tet contributions rounded to 2^-k), so
+//    the result does not depend on which warp took which tile, nor on the number of GPUs the tets are partitioned over.
+//
+// FP32 filter (what feeds an integer decision must equal the reference's FP64 result): with O the integer
+// origin of the tet, q = (P0 - O - 1/2) + lattice terms evaluated in float, t = q + 1.5*2^23 holds round(q) = floor(sample - O)
+// in its mantissa unless q is within delta of a half-integer.  delta bounds |q_float - q_reference| (derivation at stg_delta);
+// a tet with any |q - round(q)| >= 1/2 - delta is recomputed with the reference's exact FP64 sequence (coop_exact), as are
+// tets of level n >= 5, tets reaching outside the volume, and tets whose box does not fit a slot.
+#pragma once
+#include "dsc_kernels.cuh"
+
+namespace dsc {
+
+constexpr int kStgWarps = 8;
+constexpr int kStgMaxUnits = 16; // tensor-map family: box rows of 1..16 units of 16 bytes, 1..16 rows per slice
+constexpr int kStgMaxRows = 16;
+
+// the six centroid offsets (ox, oy, oz) of the reference's cube split, in table order (DEMO/image3d.cpp:274-291)
+__host__ __device__ constexpr int stg_off(int t, int c)
+{
+    constexpr int o[6][3] = {{1, 1, 1}, {2, 1, 2}, {1, 2, 3}, {3, 2, 1}, {2, 3, 2}, {3, 3, 3}};
+    return o[t][c];
+}
+// lowest level whose table holds slot (cell sum s = i+j+k, offset t): the outermost layer of cells keeps one tet, the next five
+__host__ __device__ constexpr int stg_need(int s, int t) { return s + (t == 0 ? 1 : (t <= 4 ? 2 : 3)); }
+// sign of eps = sum_k eta_k for a level-3 row, in units of 1e-6: a_k = 1 mod 3 was printed rounded down, 2 mod 3 rounded up
+__host__ __device__ constexpr int stg_eps3(int i, int j, int k, int t)
+{
+    const int a1 = 4 * j + stg_off(t, 1), a2 = 4 * i + stg_off(t, 0), a3 = 4 * k + stg_off(t, 2), a0 = 12 - a1 - a2 - a3;
+    int c = 0;
+    const int a[4] = {a0, a1, a2, a3};
+    for (int m = 0; m < 4; m++) c += (a[m] % 3 == 2) - (a[m] % 3 == 1);
+    return c / 3; // -1, 0 or +1 (the sum of the four is 0 mod 3)
+}
+
+DSC_D unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+DSC_D f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+DSC_D float fmax3abs(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c)));
+    return r;
+}
+template <typename VoxT> DSC_D VoxT lds_vox(unsigned addr);
+template <> DSC_D float lds_vox<float>(unsigned addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <> DSC_D unsigned short lds_vox<unsigned short>(unsigned addr)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+template <> DSC_D unsigned char lds_vox<unsigned char>(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (unsigned char)v;
+}
+
+// per-lane state of the block path
+struct StgLane {
+    f32x2 q0xy, q0zz;                               // P0 - O - 1/2 (z in both halves)
+    f32x2 d1xy, d1zz, d2xy, d2zz, d3xy, d3zz;       // (P_k - P0)/n
+    f32x2 oxy[6], ozz[3];                           // centroid offsets; z of offsets (0,1) (2,3) (4,5) paired
+    f32x2 epxy, epzz;                               // 1e-6 * P0 (level 3 only: the 6-decimal literals of n = 3 do not sum to 1)
+    unsigned base;                                  // shared address of voxel O in the box, minus the folded 1.5*2^23 bit patterns
+    unsigned bx, bxy;                               // byte pitch of a box row / slice
+    unsigned zero_addr;                             // shared address of a zero word (slots of level NB a level NB-1 tet does not have)
+    float thr;                                      // 1/2 - delta
+};
+
+template <typename VoxT, bool WANT_SQ, bool F32S> struct StgAcc {
+    double s = 0, sq = 0;
+    unsigned isum = 0;
+    unsigned long long isq = 0;
+    float emax = 0.f;
+    DSC_D void add(VoxT val)
+    {
+        if constexpr (VoxTraits<VoxT>::integral) {
+            const unsigned q = (unsigned)val;
+            isum += q;
+            if (WANT_SQ) isq += (unsigned long long)q * q;
+        } else {
+            double I;
+            if constexpr (F32S) I = widen_scaled((float)val);
+            else if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val);
+            else I = (double)val;
+            s += I;
+            if (WANT_SQ) {
+                const double Iu = F32S ? I * 0x1p+896 : I; // exact
+                sq = fma(Iu, Iu, sq);                      // second moment: tolerance quantity, fused on purpose
+            }
+        }
+    }
+    // the true sums
+    DSC_D void result(double &sum, double &sumsq) const
+    {
+        if constexpr (VoxTraits<VoxT>::integral) {
+            const double dn = VoxTraits<VoxT>::denom();
+            sum = (double)isum / dn;
+            sumsq = WANT_SQ ? (double)isq / (dn * dn) : 0.0;
+        } else {
+            sum = F32S ? s * 0x1p+896 : s;
+            sumsq = sq;
+        }
+    }
+};
+
+// one sample: position bits -> shared address -> voxel
+template <typename VoxT, bool SEL> DSC_D unsigned stg_addr(const StgLane &r, float tx, float ty, float tz, bool full)
+{
+    constexpr int SH = sizeof(VoxT) == 4 ? 2 : (sizeof(VoxT) == 2 ? 1 : 0);
+    const unsigned addr = r.base + (__float_as_uint(tx) << SH) + __float_as_uint(ty) * r.bx + __float_as_uint(tz) * r.bxy;
+    return SEL ? (full ? addr : r.zero_addr) : addr;
+}
+
+// The level-NB instruction stream.  `full`: this lane's tet is of level NB (else NB-1, or the lane is idle with an all-zero
+// record whose reads hit the first voxel of the slot and whose sums are never looked at).
+template <int NB, typename VoxT, bool WANT_SQ, bool F32S> DSC_D void stg_block(const StgLane &r, bool full, StgAcc<VoxT, WANT_SQ, F32S> &acc)
+{
+    const float MAGIC = 12582912.0f; // 1.5 * 2^23
+    const f32x2 M2 = pk2(MAGIC, MAGIC);
+    float em = 0.f;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        const f32x2 cjxy = j ? fma2(pk2((float)j, (float)j), r.d1xy, r.q0xy) : r.q0xy;
+        const f32x2 cjzz = j ? fma2(pk2((float)j, (float)j), r.d1zz, r.q0zz) : r.q0zz;
+#pragma unroll
+        for (int i = 0; i < NB - j; i++) {
+            const f32x2 cixy = i ? fma2(pk2((float)i, (float)i), r.d2xy, cjxy) : cjxy;
+            const f32x2 cizz = i ? fma2(pk2((float)i, (float)i), r.d2zz, cjzz) : cjzz;
+#pragma unroll
+            for (int k = 0; k < NB - j - i; k++) {
+                const f32x2 cxy = k ? fma2(pk2((float)k, (float)k), r.d3xy, cixy) : cixy;
+                const f32x2 czz = k ? fma2(pk2((float)k, (float)k), r.d3zz, cizz) : cizz;
+                const int s = i + j + k;
+                const int m = (NB - s >= 3) ? 6 : (NB - s == 2 ? 5 : 1); // offsets kept in this cell
+#pragma unroll
+                for (int t = 0; t < m; t += 2) {
+                    const bool two = t + 1 < m;
+                    // z of the two samples in one packed add; x,y one packed add per sample
+                    f32x2 qzz = add2(czz, r.ozz[t >> 1]);
+                    f32x2 qa = add2(cxy, r.oxy[t]);
+                    f32x2 qb = two ? add2(cxy, r.oxy[t + 1]) : qa;
+                    if (NB >= 3) { // level-3 rows whose literals sum to 1 -/+ 1e-6 (every other level: eps = 0)
+                        const int ea = (NB == 3 || stg_need(s, t) <= 3) ? stg_eps3(i, j, k, t) : 0;
+                        const int eb = (two && (NB == 3 || stg_need(s, t + 1) <= 3)) ? stg_eps3(i, j, k, t + 1) : 0;
+                        if (ea > 0) qa = add2(qa, r.epxy);
+                        if (ea < 0) qa = sub2(qa, r.epxy);
+                        if (eb > 0) qb = add2(qb, r.epxy);
+                        if (eb < 0) qb = sub2(qb, r.epxy);
+                        if (ea != 0 || eb != 0) {
+                            float ez0, ez1;
+                            upk2(r.epzz, ez0, ez1);
+                            qzz = add2(qzz, pk2(ea > 0 ? ez0 : (ea < 0 ? -ez0 : 0.f), eb > 0 ? ez1 : (eb < 0 ? -ez1 : 0.f)));
+                        }
+                    }
+                    const f32x2 ta = add2(qa, M2), tz2 = add2(qzz, M2);
+                    const f32x2 ea2 = sub2(qa, sub2(ta, M2)), ez2 = sub2(qzz, sub2(tz2, M2));
+                    float tax, tay, tz0, tz1, eax, eay, ez0, ez1;
+                    upk2(ta, tax, tay); upk2(tz2, tz0, tz1); upk2(ea2, eax, eay); upk2(ez2, ez0, ez1);
+                    em = fmax3abs(em, eax, eay);
+                    const bool sel_a = NB > 1 && stg_need(s, t) == NB;
+                    const unsigned addr_a = sel_a ? stg_addr<VoxT, true>(r, tax, tay, tz0, full) : stg_addr<VoxT, false>(r, tax, tay, tz0, full);
+                    const VoxT va = lds_vox<VoxT>(addr_a);
+                    if (two) {
+                        const f32x2 tb = add2(qb, M2);
+                        const f32x2 eb2 = sub2(qb, sub2(tb, M2));
+                        float tbx, tby, ebx, eby;
+                        upk2(tb, tbx, tby); upk2(eb2, ebx, eby);
+                        em = fmax3abs(em, ebx, eby);
+                        em = fmax3abs(em, ez0, ez1);
+                        const bool sel_b = NB > 1 && stg_need(s, t + 1) == NB;
+                        const unsigned addr_b = sel_b ? stg_addr<VoxT, true>(r, tbx, tby, tz1, full) : stg_addr<VoxT, false>(r, tbx, tby, tz1, full);
+                        const VoxT vb = lds_vox<VoxT>(addr_b);
+                        acc.add(va);
+                        acc.add(vb);
+                    } else {
+                        em = fmax3abs(em, ez0, ez0);
+                        acc.add(va);
+                    }
+                }
+            }
+        }
+    }
+    acc.emax = em;
+}
+
+// The reference's exact sequence for one tet, 32 lanes over its rows (get_coord, DEMO/tet_dis_coord.hpp:27; truncation
+// image3d.cpp:366; bounds image3d.cpp:480-491).  Every lane gets the tet's sums.
+template <typename VoxT, bool WANT_SQ, bool F32S> DSC_D void coop_exact(const TetArgs &a, const VoxT *__restrict__ vol, uint4 nd, int L, int lane, double &sum, double &sumsq)
+{
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
+    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+    const int n3 = (L + 1) * (L + 1) * (L + 1);
+    const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+    StgAcc<VoxT, WANT_SQ, F32S> acc;
+    for (int i = lane; i < n3; i += 32) {
+        const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
+        const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+        const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+        const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+        const bool inb = (unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z;
+        if (inb) acc.add(__ldg(vol + ((size_t)iz * Y + iy) * X + ix));
+    }
+    double s, q;
+    if constexpr (VoxTraits<VoxT>::integral) {
+        unsigned is = __reduce_add_sync(0xffffffffu, acc.isum); // <= 729 * 65535
+        unsigned long long iq = acc.isq;
+        if (WANT_SQ) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) iq += __shfl_xor_sync(0xffffffffu, iq, m);
+        }
+        const double dn = VoxTraits<VoxT>::denom();
+        s = (double)is / dn;
+        q = WANT_SQ ? (double)iq / (dn * dn) : 0.0;
+    } else {
+        s = acc.s;
+        q = acc.sq;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            s += shfl_xor_d(s, m);
+            if (WANT_SQ) q += shfl_xor_d(q, m);
+        }
+        if (F32S) s = s * 0x1p+896;
+    }
+    sum = s;
+    sumsq = q;
+}
+
+// |q_float - q_reference| per coordinate, for a tet whose origin-relative coordinates are below R and whose edge vectors
+// from P0 are below diam (both in voxels):
+//   q* = (P0 - O - 1/2) + j D1 + i D2 + k D3 + (oy E1 + ox E2 + oz E3) + eps P0 + tau,   tau = sum_{k>=1} eta_k (P_k - P0)
+//   float: Q0, D_k, E_k = D_k/4 rounded once (2^-24 relative each); three FMAs for the cell corner (each rounds a number
+//   below R + 1); the offset vector from three float operations on numbers below (9/4n) diam; one add for the sample and, at
+//   level 3, one more for eps P0.  Sum: 2^-24 (6 R + 6 + 10 diam).  eta: the literals of levels 1, 2, 4 are exact binary
+//   fractions; level 3 has |eta_k| <= 3.34e-7, so |tau| <= 1.01e-6 diam.  The reference's own FP64 rounding (4 products and 3
+//   sums of numbers below the volume size) and the FP64 set-up of Q0, D_k add less than 1e-9.
+DSC_D float stg_threshold(double R, double diam, int n)
+{
+    const double delta = 5.9604644775390625e-08 * (6.0 * R + 6.0 + 10.0 * diam) + (n == 3 ? 1.01e-6 * diam : 0.0) + 1.0e-9;
+    return (float)(0.5 - delta) * 0.99999988079071044921875f; // rounded towards the safe side
+}
+
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S>
+__global__ void __launch_bounds__(kStgWarps * 32, 1) tet_staged_kernel(const __grid_constant__ TetArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char s_dyn[];
+    __shared__ __align__(8) unsigned long long s_bar[kStgWarps];
+    __shared__ long long s_red[kStgWarps][3 * kMaxPhase];
+    __shared__ unsigned s_zero[4];
+    constexpr int ESZ = (int)sizeof(VoxT);
+    constexpr int AL = 16 / ESZ; // elements per 16-byte unit
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned slot_a = smem_u32(s_dyn) + (unsigned)warp * (unsigned)a.stg_slot_bytes;
+    const unsigned bar_a = smem_u32(&s_bar[warp]);
+    if (threadIdx.x < 4) s_zero[threadIdx.x] = 0u;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned phase = 0;
+    const unsigned n_work = a.tet_end - a.tet_begin;
+    const unsigned n_tiles = (n_work + 31) / 32;
+
+    long long acc_tot[kMaxPhase], acc_sq[kMaxPhase], acc_vol[kMaxPhase];
+#pragma unroll
+    for (int k = 0; k < kMaxPhase; k++) acc_tot[k] = acc_sq[k] = acc_vol[k] = 0;
+    unsigned long long nsamp = 0;
+
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(a.stg_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < n_tiles) {
+        unsigned next = 0;
+        if (lane == 0) next = atomicAdd(a.stg_counter, 1u);
+        const unsigned base_t = a.tet_begin + tile * 32;
+        const unsigned t = base_t + lane;
+        // ---------------- phase A: lane <-> tet ----------------
+        bool active = false, cand = false;
+        int label = 0, L = 0, n3 = 0;
+        uint4 nd = make_uint4(0, 0, 0, 0);
+        V3 p0 = {0, 0, 0}, p1 = p0, p2 = p0, p3 = p0;
+        double v = 0;
+        int blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0}, org[3] = {0, 0, 0};
+        double rmax = 0, diam = 0;
+        if (t < a.tet_end) {
+            label = __ldg(a.mesh.tet_label + t);
+            nd = __ldg(a.mesh.tet_nodes + t);
+            active = a.include_bound || label != 0;
+        }
+        if (active) {
+            p0 = load_pos(a.mesh.pos4, nd.x); p1 = load_pos(a.mesh.pos4, nd.y);
+            p2 = load_pos(a.mesh.pos4, nd.z); p3 = load_pos(a.mesh.pos4, nd.w);
+            v = tet_volume(p0, p1, p2, p3);
+            L = tet_level(v);
+            n3 = (L + 1) * (L + 1) * (L + 1);
+            const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
+            const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
+            const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
+            // Inside the volume: no sample can leave [0, dim), so truncation equals floor and no bounds test is needed -- with a
+            // margin that is plain; for tets with nodes on the faces of the volume see the argument at tet_integrate_w2_kernel
+            // (minimum weight 1/(4n) - 5e-7 of every table row, checked when the table is built).
+            auto axis_in = [](double lo, double hi, int dim) { return lo >= -1.0e-7 && hi <= (double)dim + 1.0e-7 && hi - lo >= 1.0e-4 * (double)dim; };
+            const bool interior = (lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5) ||
+                                  (axis_in(lox, hix, X) && axis_in(loy, hiy, Y) && axis_in(loz, hiz, Z));
+            const double ox = floor(lox), oy = floor(loy), oz = floor(loz);
+            rmax = fmax(fmax(hix - ox, hiy - oy), hiz - oz);
+            diam = fmax(fmax(hix - lox, hiy - loy), hiz - loz);
+            cand = interior && L < 4 && rmax < 60.0;
+            if (cand) {
+                // voxels the samples can touch: every weight is at least 1/(4n) - 5e-7, so a sample keeps (hi-lo)/(4n) away from the
+                // faces of the tet's bounding box; 0.9 of that and 1e-3 absolute cover eps * coordinate and the filter's own error
+                const double f = 0.9 / (double)(4 * (L + 1));
+                org[0] = (int)ox; org[1] = (int)oy; org[2] = (int)oz;
+                blo[0] = max((int)floor(lox + f * (hix - lox) - 1.0e-3), 0); bhi[0] = min((int)floor(hix - f * (hix - lox) + 1.0e-3), X - 1);
+                blo[1] = max((int)floor(loy + f * (hiy - loy) - 1.0e-3), 0); bhi[1] = min((int)floor(hiy - f * (hiy - loy) + 1.0e-3), Y - 1);
+                blo[2] = max((int)floor(loz + f * (hiz - loz) - 1.0e-3), 0); bhi[2] = min((int)floor(hiz - f * (hiz - loz) + 1.0e-3), Z - 1);
+            }
+            nsamp += (unsigned)n3;
+        }
+        double t_sum = 0, t_sq = 0; // this lane's tet: true sum of the sampled intensities and of their squares
+        unsigned pending = __ballot_sync(0xffffffffu, cand);
+        unsigned coop = __ballot_sync(0xffffffffu, active && !cand);
+        // ---------------- staged block path: candidate sets whose box fits the slot ----------------
+        while (pending) {
+            unsigned set = pending;
+            int x0 = 0, y0 = 0, z0 = 0, exu = 0, ey = 0, ez = 0;
+            unsigned zstride = 0;
+            bool fits = false;
+            for (;;) {
+                const bool in = (set >> lane) & 1u;
+                x0 = __reduce_min_sync(0xffffffffu, in ? blo[0] : INT_MAX);
+                y0 = __reduce_min_sync(0xffffffffu, in ? blo[1] : INT_MAX);
+                z0 = __reduce_min_sync(0xffffffffu, in ? blo[2] : INT_MAX);
+                const int x1 = __reduce_max_sync(0xffffffffu, in ? bhi[0] : INT_MIN);
+                const int y1 = __reduce_max_sync(0xffffffffu, in ? bhi[1] : INT_MIN);
+                const int z1 = __reduce_max_sync(0xffffffffu, in ? bhi[2] : INT_MIN);
+                x0 &= ~(AL - 1); // a TMA box starts on a 16-byte boundary (scripts/tma_prefetch_probe.cu)
+                exu = (x1 - x0 + AL) / AL;
+                ey = y1 - y0 + 1;
+                ez = z1 - z0 + 1;
+                zstride = ((unsigned)(exu * 16 * ey) + 127u) & ~127u; // a slice starts on a 128-byte boundary of the slot
+                fits = exu <= kStgMaxUnits && ey <= kStgMaxRows && ez <= 32 && (unsigned)ez * zstride <= (unsigned)a.stg_slot_bytes;
+                const int cnt = __popc(set);
+                if (fits || cnt == 1) break;
+                set &= (1u << __fns(set, 0, cnt / 2 + 1)) - 1u; // keep the lower half of the set's lanes
+            }
+            pending &= ~set;
+            if (!fits) { coop |= set; continue; }
+            const bool in = (set >> lane) & 1u;
+            // level of the instruction stream: the one that costs least (block + the tets it leaves to the exact path)
+            int NB;
+            {
+                const unsigned m1 = __ballot_sync(0xffffffffu, in && L == 0), m2 = __ballot_sync(0xffffffffu, in && L == 1);
+                const unsigned m3 = __ballot_sync(0xffffffffu, in && L == 2), m4 = __ballot_sync(0xffffffffu, in && L == 3);
+                const int c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3), c4 = __popc(m4);
+                const int k1 = 180, k4 = 260; // instruction estimates: exact path per tet (levels 1-3, level 4), blocks below
+                const int cost1 = 40 + k1 * (c2 + c3) + k4 * c4, cost2 = 150 + k1 * c3 + k4 * c4, cost3 = 450 + k1 * c1 + k4 * c4, cost4 = 1000 + k1 * (c1 + c2);
+                NB = 1;
+                int best = c1 ? cost1 : INT_MAX;
+                if ((c2 || c1) && cost2 < best) { best = cost2; NB = 2; }
+                if ((c3 || c2) && cost3 < best) { best = cost3; NB = 3; }
+                if ((c4 || c3) && cost4 < best) { best = cost4; NB = 4; }
+            }
+            const bool ride = in && (L + 1 == NB || L + 2 == NB);
+            coop |= __ballot_sync(0xffffffffu, in && !ride);
+            if (!__any_sync(0xffffffffu, ride)) continue;
+            // the box -> this warp's slot
+            __syncwarp();
+            const unsigned bytes = (unsigned)(exu * 16 * ey) * (unsigned)ez;
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+            __syncwarp();
+            if (lane < ez) {
+                const TmapBlob *map = a.stg_maps + ((exu - 1) * kStgMaxRows + (ey - 1));
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(slot_a + (unsigned)lane * zstride),
+                             "l"(map), "r"(x0), "r"(y0), "r"(z0 + lane), "r"(bar_a)
+                             : "memory");
+            }
+            // per-lane record while the box is on its way
+            StgLane r;
+            r.bx = (unsigned)(exu * 16);
+            r.bxy = zstride;
+            r.zero_addr = smem_u32(&s_zero[0]);
+            {
+                const int n = L + 1;
+                const double inv = 1.0 / (double)n;
+                const float q0x = ride ? (float)((p0.x - (double)org[0]) - 0.5) : 0.f, q0y = ride ? (float)((p0.y - (double)org[1]) - 0.5) : 0.f;
+                const float q0z = ride ? (float)((p0.z - (double)org[2]) - 0.5) : 0.f;
+                const float d1x = ride ? (float)((p1.x - p0.x) * inv) : 0.f, d1y = ride ? (float)((p1.y - p0.y) * inv) : 0.f, d1z = ride ? (float)((p1.z - p0.z) * inv) : 0.f;
+                const float d2x = ride ? (float)((p2.x - p0.x) * inv) : 0.f, d2y = ride ? (float)((p2.y - p0.y) * inv) : 0.f, d2z = ride ? (float)((p2.z - p0.z) * inv) : 0.f;
+                const float d3x = ride ? (float)((p3.x - p0.x) * inv) : 0.f, d3y = ride ? (float)((p3.y - p0.y) * inv) : 0.f, d3z = ride ? (float)((p3.z - p0.z) * inv) : 0.f;
+                r.q0xy = pk2(q0x, q0y); r.q0zz = pk2(q0z, q0z);
+                r.d1xy = pk2(d1x, d1y); r.d1zz = pk2(d1z, d1z);
+                r.d2xy = pk2(d2x, d2y); r.d2zz = pk2(d2z, d2z);
+                r.d3xy = pk2(d3x, d3y); r.d3zz = pk2(d3z, d3z);
+                const float e1x = 0.25f * d1x, e1y = 0.25f * d1y, e1z = 0.25f * d1z, e2x = 0.25f * d2x, e2y = 0.25f * d2y, e2z = 0.25f * d2z;
+                const float e3x = 0.25f * d3x, e3y = 0.25f * d3y, e3z = 0.25f * d3z;
+                float ofz[6];
+#pragma unroll
+                for (int o = 0; o < 6; o++) {
+                    const float fx = (float)stg_off(o, 0), fy = (float)stg_off(o, 1), fz = (float)stg_off(o, 2);
+                    r.oxy[o] = pk2(fmaf(fz, e3x, fmaf(fx, e2x, fy * e1x)), fmaf(fz, e3y, fmaf(fx, e2y, fy * e1y)));
+                    ofz[o] = fmaf(fz, e3z, fmaf(fx, e2z, fy * e1z));
+                }
+                r.ozz[0] = pk2(ofz[0], ofz[1]); r.ozz[1] = pk2(ofz[2], ofz[3]); r.ozz[2] = pk2(ofz[4], ofz[5]);
+                const bool l3 = ride && n == 3;
+                const float epx = l3 ? (float)(1.0e-6 * p0.x) : 0.f, epy = l3 ? (float)(1.0e-6 * p0.y) : 0.f, epz = l3 ? (float)(1.0e-6 * p0.z) : 0.f;
+                r.epxy = pk2(epx, epy); r.epzz = pk2(epz, epz);
+                r.thr = ride ? stg_threshold(rmax + 1.0, diam, n) : 1.0e30f;
+                // address of voxel O + m: base + (bits(tx) << SH) + bits(ty) bx + bits(tz) bxy, the bits being 0x4B400000 + m
+                constexpr unsigned SHM = ESZ;
+                const unsigned fold = 0x4B400000u * (SHM + r.bx + r.bxy);
+                const unsigned rel = ride ? (unsigned)((org[0] - x0) * ESZ) + (unsigned)(org[1] - y0) * r.bx + (unsigned)(org[2] - z0) * r.bxy : 0u;
+                r.base = slot_a + rel - fold;
+            }
+            {
+                unsigned done = 0;
+                while (!done)
+                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+                phase ^= 1u;
+            }
+            StgAcc<VoxT, WANT_SQ, F32S> acc;
+            const bool full = ride && L + 1 == NB;
+            switch (NB) {
+            case 1: stg_block<1, VoxT, WANT_SQ, F32S>(r, full, acc); break;
+            case 2: stg_block<2, VoxT, WANT_SQ, F32S>(r, full, acc); break;
+            case 3: stg_block<3, VoxT, WANT_SQ, F32S>(r, full, acc); break;
+            default: stg_block<4, VoxT, WANT_SQ, F32S>(r, full, acc); break;
+            }
+            const bool flagged = ride && !(acc.emax < r.thr);
+            coop |= __ballot_sync(0xffffffffu, flagged);
+            if (ride && !flagged) acc.result(t_sum, t_sq);
+        }
+        // ---------------- exact path: one tet at a time, 32 lanes over its rows ----------------
+        while (coop) {
+            const int src = __ffs(coop) - 1;
+            coop &= coop - 1u;
+            uint4 snd;
+            snd.x = __shfl_sync(0xffffffffu, nd.x, src); snd.y = __shfl_sync(0xffffffffu, nd.y, src);
+            snd.z = __shfl_sync(0xffffffffu, nd.z, src); snd.w = __shfl_sync(0xffffffffu, nd.w, src);
+            const int sL = __shfl_sync(0xffffffffu, L, src);
+            double s, q;
+            coop_exact<VoxT, WANT_SQ, F32S>(a, vol, snd, sL, lane, s, q);
+            if (lane == src) { t_sum = s; t_sq = q; }
+        }
+        // ---------------- per-tet result, per-label fixed-point sums ----------------
+        if (t < a.tet_end) {
+            if (active) {
+                const double tot = PER_TET ? t_sum * v / (double)n3 : t_sum * (v / (double)n3); // total * v / a.size() (image3d.cpp:371)
+                if (PER_TET) {
+                    if (a.tet_total) a.tet_total[t] = tot;
+                    if (a.tet_vol) a.tet_vol[t] = v;
+                    if (a.tet_mean) a.tet_mean[t] = tot / v;
+                }
+                const long long ftot = __double2ll_rn(tot * a.stg_scale[0]);
+                const long long fvol = __double2ll_rn(v * a.stg_scale[2]);
+                long long fsq = 0;
+                if (WANT_SQ) fsq = __double2ll_rn(t_sq * (v / (double)n3) * a.stg_scale[1]);
+#pragma unroll
+                for (int k = 0; k < kMaxPhase; k++)
+                    if (label == k + 1 && k < a.nb_phase) {
+                        acc_tot[k] += ftot;
+                        acc_vol[k] += fvol;
+                        if (WANT_SQ) acc_sq[k] += fsq;
+                    }
+            } else if (PER_TET) {
+                if (a.tet_total) a.tet_total[t] = -1.0;
+                if (a.tet_vol) a.tet_vol[t] = -1.0;
+                if (a.tet_mean) a.tet_mean[t] = -1.0;
+            }
+        }
+        tile = __shfl_sync(0xffffffffu, next, 0);
+    }
+    // ---------------- per-CTA partial row (integers: any order gives the same sums) ----------------
+#pragma unroll
+    for (int k = 0; k < kMaxPhase; k++) {
+        long long x = acc_tot[k], y = acc_sq[k], z = acc_vol[k];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            x += __shfl_xor_sync(0xffffffffu, x, m);
+            if (WANT_SQ) y += __shfl_xor_sync(0xffffffffu, y, m);
+            z += __shfl_xor_sync(0xffffffffu, z, m);
+        }
+        if (lane == 0) {
+            s_red[warp][k] = x;
+            s_red[warp][kMaxPhase + k] = y;
+            s_red[warp][2 * kMaxPhase + k] = z;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
+    __syncthreads();
+    if (threadIdx.x < 3 * kMaxPhase) {
+        long long rsum = 0;
+        for (int w = 0; w < kStgWarps; w++) rsum += s_red[w][threadIdx.x];
+        a.stg_partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = rsum;
+    }
+    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+}
+
+// Adds the per-CTA fixed-point rows (exact) and converts: out[0..P) total, [P..2P) sumsq, [2P..3P) volume, mean = total/volume.
+// A sum that left the 62-bit range (a mesh far larger than the volume the scale was chosen for) raises bit 1 of *flags.
+__global__ void __launch_bounds__(32 * 3 * kMaxPhase) tet_finalize_fixed_kernel(const long long *__restrict__ partials, int n_rows, int nb_phase, double s_tot, double s_sq,
+                                                                                  double s_vol, double *sums, double *mean, unsigned *flags)
+{
+    const int col = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long r = 0;
+    double approx = 0;
+    for (int i = lane; i < n_rows; i += 32) {
+        const long long p = partials[(size_t)i * 3 * kMaxPhase + col];
+        r += p;
+        approx += fabs((double)p);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        r += __shfl_xor_sync(0xffffffffu, r, m);
+        approx += shfl_xor_d(approx, m);
+    }
+    const int which = col / kMaxPhase, ph = col % kMaxPhase;
+    const double scale = which == 0 ? s_tot : (which == 1 ? s_sq : s_vol);
+    const double val = (double)r / scale; // scale is a power of two: one rounding, of the integer
+    __shared__ double tot[kMaxPhase], vol[kMaxPhase];
+    if (lane == 0) {
+        if (approx >= 4.0e18 && flags) atomicOr(flags, 2u);
+        if (ph < nb_phase) sums[which * nb_phase + ph] = val;
+        if (which == 0) tot[ph] = val;
+        if (which == 2) vol[ph] = val;
+    }
+    __syncthreads();
+    if (mean && threadIdx.x < nb_phase) mean[threadIdx.x] = tot[threadIdx.x] / vol[threadIdx.x];
+}
+
+} // namespace dsc

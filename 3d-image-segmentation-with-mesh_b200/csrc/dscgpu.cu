@@ -14,6 +14,7 @@
 #include "../../include/dscgpu.h"
 #include "dsc_kernels.cuh"
 #include "dsc_tet_g32.cuh"
+#include "dsc_tet_staged.cuh"
 #include "dsc_comm.cuh"
 #include "dsc_tables.h"
 
@@ -83,6 +84,14 @@ struct dscgpu_ctx {
     // w2 PF (variant bit 65536): tensor map of the volume (passed by value in the kernel arguments), voxel boxes of the 32-tet tiles of one launch range
     TmapBlob tmap_host;
     int tmap_state = 0; // 0 not tried, 1 ready, -1 unavailable (layout not expressible / no driver entry point)
+    // staged kernel (variant bit 131072, dsc_tet_staged.cuh): tensor-map family in device memory, tile counter, fixed-point scales
+    TmapBlob *d_stg_maps = nullptr;
+    unsigned *d_stg_counter = nullptr;
+    int stg_state = 0;          // 0 not tried, 1 ready, -1 unavailable
+    int stg_slot_bytes = 27 * 1024;
+    double stg_scale[3] = {1.0, 1.0, 1.0};
+    bool tet_rows_fixed = false; // the partial rows of the running tet pass are fixed-point integers (staged kernel)
+    float vol_max = 1.0f;        // largest voxel of a float volume (volume_flags_kernel)
     int4 *d_tile_box = nullptr;
     size_t tile_box_cap = 0;
     unsigned tb_begin = 0, tb_end = 0;
@@ -323,19 +332,119 @@ int ensure_volume_flags(dscgpu_ctx *ctx)
     if (ctx->vol_flags_valid) return DSCGPU_OK;
     ctx->vol_simple = false;
     if (ctx->dtype == DSCGPU_F32) {
-        if (!ctx->d_brick_flags) CK(cudaMalloc(&ctx->d_brick_flags, sizeof(unsigned)));
-        CK(cudaMemsetAsync(ctx->d_brick_flags, 0, sizeof(unsigned), ctx->stream));
+        if (!ctx->d_brick_flags) { CK(cudaMalloc(&ctx->d_brick_flags, 4 * sizeof(unsigned))); CK(cudaMemset(ctx->d_brick_flags, 0, 4 * sizeof(unsigned))); }
+        CK(cudaMemsetAsync(ctx->d_brick_flags, 0, 2 * sizeof(unsigned), ctx->stream));
         const size_t n = (size_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2];
         volume_flags_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(static_cast<const float *>(ctx->d_vol), n, ctx->d_brick_flags);
         ctx->launches++;
         CK(cudaGetLastError());
-        unsigned flags = 1;
-        CK(cudaMemcpyAsync(&flags, ctx->d_brick_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned flags[2] = {1, 0};
+        CK(cudaMemcpyAsync(flags, ctx->d_brick_flags, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        ctx->vol_simple = (flags & 1u) == 0;
+        ctx->vol_simple = (flags[0] & 1u) == 0;
+        memcpy(&ctx->vol_max, &flags[1], sizeof(float)); // bit pattern order = value order for non-negative floats
     }
     ctx->vol_flags_valid = true;
     return DSCGPU_OK;
+}
+
+// Staged kernel: one tensor map per (row bytes, rows) pair of a z slice of a voxel box -- 16 x 16 maps of 128 bytes in device
+// memory, picked per tile by the kernel -- plus the tile counter and the fixed-point scales of the per-label sums.
+// Unavailable (the w2 kernel runs instead): row pitch of the volume not a multiple of 16 bytes, FP64 volumes, float volumes with
+// negative / non-finite voxels, no driver entry point.
+int ensure_staged(dscgpu_ctx *ctx)
+{
+    if (ctx->stg_state != 0) return DSCGPU_OK;
+    ctx->stg_state = -1;
+    const size_t es = dtype_size(ctx->dtype);
+    const cuuint64_t X = (cuuint64_t)ctx->dims[0], Y = (cuuint64_t)ctx->dims[1], Z = (cuuint64_t)ctx->dims[2];
+    if (ctx->dtype == DSCGPU_F64 || (X * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(ctx->d_vol) & 15) != 0) return DSCGPU_OK;
+    double vmax = 1.0;
+    if (ctx->dtype == DSCGPU_F32) {
+        int rf = ensure_volume_flags(ctx);
+        if (rf) return rf;
+        if (!ctx->vol_simple) return DSCGPU_OK;
+        vmax = (double)ctx->vol_max;
+    }
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return DSCGPU_OK;
+    }
+    const CUtensorMapDataType dt = ctx->dtype == DSCGPU_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : ctx->dtype == DSCGPU_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    std::vector<TmapBlob> maps((size_t)kStgMaxUnits * kStgMaxRows);
+    const cuuint64_t gdim[3] = {X, Y, Z}, gstr[2] = {X * es, X * Y * es};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int u = 0; u < kStgMaxUnits; u++)
+        for (int r = 0; r < kStgMaxRows; r++) {
+            alignas(64) CUtensorMap tm;
+            const cuuint32_t box[3] = {(cuuint32_t)((u + 1) * 16 / es), (cuuint32_t)(r + 1), 1};
+            if (reinterpret_cast<encode_fn>(fn)(&tm, dt, 3, ctx->d_vol, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return DSCGPU_OK;
+            memcpy(&maps[(size_t)u * kStgMaxRows + r], &tm, sizeof(CUtensorMap));
+        }
+    if (!ctx->d_stg_maps) CK(cudaMalloc(&ctx->d_stg_maps, maps.size() * sizeof(TmapBlob)));
+    if (!ctx->d_stg_counter) CK(cudaMalloc(&ctx->d_stg_counter, sizeof(unsigned)));
+    CK(cudaMemcpy(ctx->d_stg_maps, maps.data(), maps.size() * sizeof(TmapBlob), cudaMemcpyHostToDevice));
+    // fixed point: per-label sums stay below 64 x (voxels of the volume) x (largest intensity) -- tets cover the volume once, a
+    // DSC mesh pads it by one edge -- and must stay below 2^62; tet_finalize_fixed_kernel reports a sum that did not
+    const double nvox = (double)X * (double)Y * (double)Z;
+    auto scale_for = [](double bound) { int e = 0; frexp(bound, &e); int k = 62 - e; if (k > 60) k = 60; if (k < -60) k = -60; return ldexp(1.0, k); };
+    const double vm = vmax > 1.0e-30 ? vmax : 1.0e-30;
+    ctx->stg_scale[0] = scale_for(64.0 * nvox * vm);
+    ctx->stg_scale[1] = scale_for(64.0 * nvox * vm * vm);
+    ctx->stg_scale[2] = scale_for(64.0 * nvox);
+    ctx->stg_state = 1;
+    return DSCGPU_OK;
+}
+
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S> int launch_staged_t(dscgpu_ctx *ctx, TetArgs &a)
+{
+    auto kern = tet_staged_kernel<VoxT, WANT_SQ, PER_TET, F32S>;
+    const int smem = kStgWarps * ctx->stg_slot_bytes;
+    static bool attr_set = false; // per instantiation
+    static int attr_dev = -1;
+    if (!attr_set || attr_dev != ctx->device) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        attr_set = true; attr_dev = ctx->device;
+    }
+    const unsigned n_tiles = (a.tet_end - a.tet_begin + 31) / 32;
+    unsigned grid = (unsigned)ctx->num_sms;
+    const unsigned need = (n_tiles + kStgWarps - 1) / kStgWarps;
+    if (need < grid) grid = need ? need : 1;
+    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    a.stg_partials = ctx->partials.as<long long>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)grid;
+    ctx->tet_rows_fixed = true;
+    a.stg_maps = ctx->d_stg_maps;
+    a.stg_slot_bytes = ctx->stg_slot_bytes;
+    a.stg_counter = ctx->d_stg_counter;
+    for (int k = 0; k < 3; k++) a.stg_scale[k] = ctx->stg_scale[k];
+    CK(cudaMemsetAsync(ctx->d_stg_counter, 0, sizeof(unsigned), ctx->stream));
+    kern<<<grid, kStgWarps * 32, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return DSCGPU_OK;
+}
+
+template <typename VoxT, bool F32S> int launch_staged_v(dscgpu_ctx *ctx, TetArgs &a)
+{
+    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
+    if (a.want_sq) return per_tet ? launch_staged_t<VoxT, true, true, F32S>(ctx, a) : launch_staged_t<VoxT, true, false, F32S>(ctx, a);
+    return per_tet ? launch_staged_t<VoxT, false, true, F32S>(ctx, a) : launch_staged_t<VoxT, false, false, F32S>(ctx, a);
+}
+
+int launch_staged(dscgpu_ctx *ctx, TetArgs &a)
+{
+    switch (ctx->dtype) {
+    case DSCGPU_U8: return launch_staged_v<unsigned char, false>(ctx, a);
+    case DSCGPU_U16: return launch_staged_v<unsigned short, false>(ctx, a);
+    default: return launch_staged_v<float, true>(ctx, a);
+    }
 }
 
 template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SIMPLE = false, bool PACK = false, int LEAN = 0, bool PF = false> int launch_w2_t(dscgpu_ctx *ctx, TetArgs &a)
@@ -541,7 +650,7 @@ int ensure_bricks(dscgpu_ctx *ctx)
     ctx->brick_nb[1] = (ctx->dims[1] + 2 * kBrickPad + 1) / 2;
     ctx->brick_nb[2] = (ctx->dims[2] + 2 * kBrickPad + 3) / 4;
     if (!ctx->d_brick) CK(cudaMalloc(&ctx->d_brick, brick_elems(ctx) * dtype_size(ctx->dtype)));
-    if (!ctx->d_brick_flags) CK(cudaMalloc(&ctx->d_brick_flags, sizeof(unsigned)));
+    if (!ctx->d_brick_flags) { CK(cudaMalloc(&ctx->d_brick_flags, 4 * sizeof(unsigned))); CK(cudaMemset(ctx->d_brick_flags, 0, 4 * sizeof(unsigned))); }
     CK(cudaMemsetAsync(ctx->d_brick_flags, 0, sizeof(unsigned), ctx->stream));
     int r;
     switch (ctx->dtype) {
@@ -633,6 +742,11 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
     }
     int G = ctx->lanes_per_tet ? ctx->lanes_per_tet : ctx->auto_lanes;
     const bool fits32 = (double)ctx->dims[0] * ctx->dims[1] * ctx->dims[2] < 2147483648.0;
+    if ((ctx->tet_variant & 131072) && !with_c && fits32) { // staged kernel: lane per tet, voxel boxes in shared memory by TMA
+        int rs = ensure_staged(ctx);
+        if (rs) return rs;
+        if (ctx->stg_state == 1 && (ctx->tet_grid == 0 || ctx->tet_rows_fixed)) return launch_staged(ctx, a);
+    }
     if ((ctx->tet_variant & 512) && !with_c && fits32) { // w4: w2 with software-pipelined gathers
         switch (ctx->dtype) {
         case DSCGPU_U8: return launch_w4<unsigned char>(ctx, a);
@@ -744,6 +858,7 @@ int tet_pass_range(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, con
 int tet_pass_begin(dscgpu_ctx *ctx)
 {
     ctx->tet_grid = 0;
+    ctx->tet_rows_fixed = false;
     CK(cudaMemsetAsync(ctr(ctx, 0), 0, sizeof(unsigned long long), ctx->stream));
     return DSCGPU_OK;
 }
@@ -751,7 +866,11 @@ int tet_pass_begin(dscgpu_ctx *ctx)
 int tet_pass_finish(dscgpu_ctx *ctx, int nb_phase, double *d_sums_out, double *d_mean_out)
 {
     TimerScope ts(ctx, DSCGPU_T_PHASE_FINAL);
-    tet_finalize_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums_out, d_mean_out);
+    if (ctx->tet_rows_fixed)
+        tet_finalize_fixed_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<long long>(), ctx->tet_grid, nb_phase, ctx->stg_scale[0], ctx->stg_scale[1], ctx->stg_scale[2],
+                                                                              d_sums_out, d_mean_out, ctx->d_brick_flags ? ctx->d_brick_flags + 2 : nullptr);
+    else
+        tet_finalize_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums_out, d_mean_out);
     ctx->launches++;
     CK(cudaGetLastError());
     return DSCGPU_OK;
@@ -1222,6 +1341,10 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
         CK(cudaMemcpy(ctx->d_lat32, t32.data(), t32.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (const char *ev = getenv("DSCGPU_TET_VARIANT")) ctx->tet_variant = atoi(ev);
+    if (const char *ev = getenv("DSCGPU_STG_SLOT_KB")) { // development knob: shared-memory slot of one warp of the staged kernel
+        const int kb = atoi(ev);
+        if (kb >= 4 && kb * kStgWarps <= 222) ctx->stg_slot_bytes = kb * 1024;
+    }
     if (voxels_host) { // one scan of a float volume: are all voxels non-negative finite numbers?
         int rf = ensure_volume_flags(ctx);
         if (rf) return rf;
@@ -1266,6 +1389,8 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
     if (ctx->d_lat32) cudaFree(ctx->d_lat32);
     if (ctx->d_brick) cudaFree(ctx->d_brick);
     if (ctx->d_brick_flags) cudaFree(ctx->d_brick_flags);
+    if (ctx->d_stg_maps) cudaFree(ctx->d_stg_maps);
+    if (ctx->d_stg_counter) cudaFree(ctx->d_stg_counter);
     if (ctx->vol_tex) cudaDestroyTextureObject(ctx->vol_tex);
     if (ctx->vol_array) cudaFreeArray(ctx->vol_array);
     for (int i = 0; i < DSCGPU_T_COUNT; i++) {
@@ -1299,6 +1424,7 @@ void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx)
     if (!ctx) return nullptr;
     ctx->brick_valid = false; // the caller may write the volume through this pointer
     ctx->vol_flags_valid = false;
+    ctx->stg_state = 0; // the fixed-point scales depend on the largest voxel
     return ctx->d_vol;
 }
 
@@ -1307,6 +1433,7 @@ int dscgpu_volume_modified(dscgpu_ctx *ctx)
     if (!ctx) return DSCGPU_ERR_ARG;
     ctx->brick_valid = false;
     ctx->vol_flags_valid = false;
+    ctx->stg_state = 0; // the fixed-point scales depend on the largest voxel
     return DSCGPU_OK;
 }
 
@@ -1319,6 +1446,7 @@ int dscgpu_volume_upload(dscgpu_ctx *ctx, const void *voxels_host)
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->brick_valid = false;
     ctx->vol_flags_valid = false;
+    ctx->stg_state = 0; // the fixed-point scales depend on the largest voxel
     ctx->has_sum_table = false;
     return DSCGPU_OK;
 }
@@ -2214,7 +2342,7 @@ int dscgpu_build_texture(dscgpu_ctx *ctx)
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 131072, "variant is a 17-bit field");
+    ARG(variant >= 0 && variant < 262144, "variant is an 18-bit field");
     if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
         int r = dscgpu_build_texture(ctx);
         if (r) return r;

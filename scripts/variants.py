@@ -34,7 +34,7 @@ def main():
     ref = None
     import torch
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
-    cases = [(0, 8, "v1 group G=8"), (128, 0, "w2 lattice"), (512, 0, "w4 pipelined")]
+    cases = [(128 | 16384, 0, "w2 default"), (131072 | 128 | 16384, 0, "staged")]
     for variant, lanes, label in cases:
         seg.set_tet_variant(variant)
         seg.set_lanes_per_tet(lanes)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdscgpu.so")
 SOURCES = ["dscgpu.cu"]
-DEPS = ["dscgpu.cu", "dsc_kernels.cuh", "dsc_tet_g32.cuh", "dsc_comm.cuh", "dsc_device.cuh", "dsc_tables.h", os.path.join("..", "..", "include", "dscgpu.h")]
+DEPS = ["dscgpu.cu", "dsc_kernels.cuh", "dsc_tet_staged.cuh", "dsc_comm.cuh", "dsc_device.cuh", "dsc_tables.h", os.path.join("..", "..", "include", "dscgpu.h")]
 
 
 def nvcc_path():

@@ -201,7 +201,6 @@ struct TetArgs {
     const float4 *tet_bary_f;        // the same table rounded to float (FP32 filter path)
     const float4 *tet_lat;           // lattice form of the table: (a1, a2, a3, eps) per row, see tet_integrate_w2_kernel
     int want_sq;                     // fill the per-label second moment (costs one DFMA per sample)
-    cudaTextureObject_t tex;         // 3-D texture over the volume (0 when unavailable)
     double *partials;                // [gridDim.x][3*kMaxPhase]: total, sumsq, volume
     unsigned long long *sample_count; // algorithmic samples processed (for the roofline figure)
     const void *brick;               // bricked, padded copy of the volume (w2 BRICK form), strides in elements
@@ -209,8 +208,6 @@ struct TetArgs {
     int vol_simple;                  // float volume: only non-negative finite values (scaled widening allowed)
     int pack;                        // w2: packed FP32 position arithmetic
     int lean;                        // w2: full/tail batch split, per-tet weight from phase A
-    const int4 *tile_box;            // w2 PF: voxel box of every 32-tet tile of [tet_begin, tet_end) (tile_box_kernel)
-    TmapBlob tmap;                   // w2 PF: CUtensorMap of the volume (box kPfBoxX x kPfBoxY x kPfBoxZ), valid when tile_box is set
     // staged kernel (dsc_tet_staged.cuh)
     const TmapBlob *stg_maps;        // [16][16] tensor maps of the volume in device memory: box = (u+1) x 16 bytes by (r+1) rows by 1 slice
     int stg_slot_bytes;              // shared-memory slot of one warp (multiple of 1024)
@@ -370,208 +367,9 @@ __global__ void __launch_bounds__(256) tet_integrate_kernel(const TetArgs a)
     if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
 }
 
-// -------------------------------------------------------------------------------------------------
-// Optimised G-lanes-per-tet form (hot path without per-c outputs): as tet_integrate_kernel, plus
-//   * the barycentric table rows of levels n <= kSmemLevels are staged in shared memory once per CTA
-//     (float4 rows for the FP32 filter, double rows for the exact path), so the L1 only serves voxel gathers;
-//   * samples are processed in batches of UNROLL per lane: indices first, then UNROLL gathers back to back;
-//   * FILTER: FP32 position + error bound in front of the exact FP64 position (see the thread-per-tet kernel
-//     below for the bound); tets that are not strictly inside the volume take the exact path.
-// Lanes of a group take consecutive table rows, which are spatially adjacent sample points (the table is
-// generated sub-cube by sub-cube), so the G gathers of one step fall into 2-3 cache lines.
-// -------------------------------------------------------------------------------------------------
+// levels whose table rows the w2 kernel stages in shared memory
 constexpr int kSmemLevels = 5;                                                        // n = 1..5
 constexpr int kSmemRows = (kSmemLevels * (kSmemLevels + 1) / 2) * (kSmemLevels * (kSmemLevels + 1) / 2); // 225 rows
-
-template <typename VoxT, int G, int UNROLL, bool FILTER>
-__global__ void __launch_bounds__(256) tet_integrate_g_kernel(const TetArgs a)
-{
-    __shared__ float4 s_tabf[FILTER ? kSmemRows : 1];
-    __shared__ double2 s_tabd[2 * kSmemRows];
-    for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
-    if (FILTER)
-        for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_tabf[i] = a.tet_bary_f[i];
-    __syncthreads();
-
-    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
-    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
-    const size_t XY = (size_t)X * Y;
-    const int lane_g = threadIdx.x & (G - 1);
-    const unsigned groups_per_block = blockDim.x / G;
-    const unsigned total_groups = gridDim.x * groups_per_block;
-    const unsigned gid = blockIdx.x * groups_per_block + threadIdx.x / G;
-    const unsigned n_work = a.tet_end - a.tet_begin;
-    const unsigned iters = (n_work + total_groups - 1) / total_groups;
-    const float MAGIC = 12582912.0f; // 1.5 * 2^23
-    const int MAGIC_BITS = 0x4B400000;
-
-    double acc_tot = 0, acc_sq = 0, acc_vol = 0;
-    unsigned long long nsamp = 0;
-
-    for (unsigned it = 0; it < iters; it++) {
-        const unsigned w = it * total_groups + gid;
-        const bool valid = w < n_work;
-        const unsigned t = a.tet_begin + (valid ? w : 0);
-        int label = 0;
-        bool active = false;
-        double s = 0, sq = 0, v = 0;
-        int n3 = 0;
-        if (valid) {
-            label = __ldg(a.mesh.tet_label + t);
-            active = a.include_bound || label != 0;
-        }
-        if (active) {
-            const uint4 nd = __ldg(a.mesh.tet_nodes + t);
-            const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-            const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-            v = tet_volume(p0, p1, p2, p3);
-            const int L = tet_level(v);
-            n3 = (L + 1) * (L + 1) * (L + 1);
-            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
-            // float copies of the vertices come from HBM (pos4f): converting per lane would saturate the XU pipe
-            const float4 f0 = __ldg(a.mesh.pos4f + nd.x), f1 = __ldg(a.mesh.pos4f + nd.y), f2 = __ldg(a.mesh.pos4f + nd.z), f3 = __ldg(a.mesh.pos4f + nd.w);
-            const float ax = f0.x, ay = f0.y, az = f0.z, bx = f1.x, by = f1.y, bz = f1.z;
-            const float cx = f2.x, cy = f2.y, cz = f2.z, dx = f3.x, dy = f3.y, dz = f3.z;
-            // conservative interior test on the float copies (they are within 2^-24 relative of the doubles; margin 0.5):
-            // every vertex, hence every sample point (a convex combination up to 1e-5), lies in [1, dim-1) on each axis
-            const float lo = fminf(fminf(fminf(fminf(ax, ay), az), fminf(fminf(bx, by), bz)), fminf(fminf(fminf(cx, cy), cz), fminf(fminf(dx, dy), dz)));
-            const float hx = fmaxf(fmaxf(ax, bx), fmaxf(cx, dx)), hy = fmaxf(fmaxf(ay, by), fmaxf(cy, dy)), hz = fmaxf(fmaxf(az, bz), fmaxf(cz, dz));
-            const bool interior = lo >= 1.5f && hx < (float)X - 1.5f && hy < (float)Y - 1.5f && hz < (float)Z - 1.5f;
-            const float M = fmaxf(fmaxf(hx, hy), hz);
-            const bool in_smem = L < kSmemLevels;
-            unsigned long long isum = 0, isq = 0;
-            // Samples are processed in batches of UNROLL per lane: all voxel indices of a batch are computed first
-            // (branch-free), then all gathers are issued back to back, then accumulated -- UNROLL loads in flight per
-            // lane instead of one (the gather latency, not bandwidth, bounds this kernel otherwise).  Indices are 32-bit
-            // (the host only selects this kernel when X*Y*Z < 2^31); -1 marks "reads as 0".
-            const double2 *__restrict__ tbg = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
-            const int XYi = X * Y;
-            auto exact_index = [&](int i) -> int {
-                // get_coord: ((p0*b0 + p1*b1) + p2*b2) + p3*b3 per component (DEMO/tet_dis_coord.hpp:27), truncated (image3d.cpp:366)
-                double2 b01, b23;
-                if (in_smem) { b01 = s_tabd[2 * (off + i)]; b23 = s_tabd[2 * (off + i) + 1]; }
-                else { b01 = __ldg(tbg + 2 * i); b23 = __ldg(tbg + 2 * i + 1); }
-                const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-                const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-                const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                const bool inb = (unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z;
-                return inb ? iz * XYi + iy * X + ix : -1;
-            };
-            auto gather_and_accumulate = [&](const int (&idx)[UNROLL]) {
-                VoxT val[UNROLL];
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++) {
-                    if constexpr (VoxTraits<VoxT>::integral) {
-                        const unsigned q = (unsigned)val[u];
-                        isum += q;
-                        isq += (unsigned long long)q * q;
-                    } else {
-                        double I;
-                        if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val[u]);
-                        else I = (double)val[u];
-                        s += I;
-                        sq = fma(I, I, sq); // second moment: tolerance quantity, fused on purpose
-                    }
-                }
-            };
-            if (FILTER && interior && in_smem && M < 65536.0f) {
-                const float thr = 0.5f - (M + 1.0f) * 9.5367431640625e-07f; // 0.5 - delta, delta = 2^-20 (M + 1)
-                const int last = n3 - 1;
-                const unsigned fold = (unsigned)MAGIC_BITS * (unsigned)(XYi + X + 1); // wraps, as intended
-                const float4 *__restrict__ tf = s_tabf + off;
-                for (int base = lane_g; base < n3; base += G * UNROLL) {
-                    int idx[UNROLL];
-                    unsigned unsafe = 0;
-#pragma unroll
-                    for (int u = 0; u < UNROLL; u++) {
-                        const int i = base + u * G;
-                        const bool ok = i <= last;
-                        const float4 b = tf[min(i, last)];
-                        const float qx = fmaf(b.w, dx, fmaf(b.z, cx, fmaf(b.y, bx, fmaf(b.x, ax, -0.5f))));
-                        const float qy = fmaf(b.w, dy, fmaf(b.z, cy, fmaf(b.y, by, fmaf(b.x, ay, -0.5f))));
-                        const float qz = fmaf(b.w, dz, fmaf(b.z, cz, fmaf(b.y, bz, fmaf(b.x, az, -0.5f))));
-                        const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
-                        const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
-                        // (iz*XY + iy*X + ix) with the three MAGIC_BITS offsets folded into one constant
-                        const int lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) - fold);
-                        idx[u] = ok ? lin : -1;
-                        if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) unsafe |= 1u << u;
-                    }
-                    if (unsafe) { // a coordinate within delta of a voxel boundary: exact reference arithmetic for those samples
-#pragma unroll
-                        for (int u = 0; u < UNROLL; u++)
-                            if (unsafe & (1u << u)) idx[u] = exact_index(base + u * G);
-                    }
-                    gather_and_accumulate(idx);
-                }
-            } else {
-                for (int base = lane_g; base < n3; base += G * UNROLL) {
-                    int idx[UNROLL];
-#pragma unroll
-                    for (int u = 0; u < UNROLL; u++) {
-                        const int i = base + u * G;
-                        idx[u] = i < n3 ? exact_index(i) : -1;
-                    }
-                    gather_and_accumulate(idx);
-                }
-            }
-            if (VoxTraits<VoxT>::integral) {
-                const double dn = VoxTraits<VoxT>::denom();
-                s = (double)isum / dn;
-                sq = (double)isq / (dn * dn);
-            }
-        }
-#pragma unroll
-        for (int m = G / 2; m >= 1; m >>= 1) {
-            s += shfl_xor_d(s, m);
-            sq += shfl_xor_d(sq, m);
-        }
-        if (active) {
-            const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
-            const double tsq = sq * v / (double)n3;
-            if (lane_g == 0) {
-                nsamp += (unsigned long long)n3;
-                if (a.tet_total) a.tet_total[t] = tot;
-                if (a.tet_vol) a.tet_vol[t] = v;
-                if (a.tet_mean) a.tet_mean[t] = tot / v;
-            }
-            if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
-                acc_tot += tot;
-                acc_sq += tsq;
-                acc_vol += v;
-            }
-        } else if (valid && lane_g == 0) {
-            if (a.tet_total) a.tet_total[t] = -1.0;
-            if (a.tet_vol) a.tet_vol[t] = -1.0;
-            if (a.tet_mean) a.tet_mean[t] = -1.0;
-        }
-    }
-#pragma unroll
-    for (int m = 16; m >= G; m >>= 1) {
-        acc_tot += shfl_xor_d(acc_tot, m);
-        acc_sq += shfl_xor_d(acc_sq, m);
-        acc_vol += shfl_xor_d(acc_vol, m);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
-    __shared__ double sm[8][3 * kMaxPhase];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane < kMaxPhase && lane < G) {
-        sm[warp][lane] = acc_tot;
-        sm[warp][kMaxPhase + lane] = acc_sq;
-        sm[warp][2 * kMaxPhase + lane] = acc_vol;
-    }
-    __syncthreads();
-    if (threadIdx.x < 3 * kMaxPhase) {
-        double r = 0;
-        const int nw = blockDim.x >> 5;
-        for (int wdx = 0; wdx < nw; wdx++) r += sm[wdx][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
-    }
-    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
-}
 
 // ---- packed FP32 pairs (Blackwell FFMA2 / FADD2, PTX fma.rn.f32x2 / add.rn.f32x2): two IEEE operations per issue slot ----
 typedef unsigned long long f32x2;
@@ -601,54 +399,6 @@ DSC_HD int g32_slot_off(int L)
     // {0, 1, 2, 3, 5, 9, 16, 27, 43, 66} packed in bytes (a local array would live on the stack)
     const unsigned w = L < 4 ? 0x03020100u : (L < 8 ? 0x1B100905u : 0x0000422Bu);
     return (int)((w >> (8 * (L & 3))) & 0xffu);
-}
-
-// ---- L2 prefetch of a tile's voxels (w2 PF, variant bit 65536) ---------------------------------------------------------------
-// The gathers of a tile touch a box of about 52 x 11 x 11 voxels (C4) that nobody has read before about 40 % of the time: those
-// first touches pay the DRAM latency inside the sample loop.  tile_box_kernel records, per 32-tet tile of the launch range, the
-// integer voxel box of its active tets (once per snapshot and range); the integration kernel then has ONE lane ask the TMA unit
-// to pull the box of the warp's NEXT tile into L2 (cp.async.bulk.prefetch.tensor, a handful of instructions per tile -- the
-// per-lane prefetch instructions cost an L1 wavefront per line, as much as the gathers they would help).  A hint only: results
-// cannot depend on it.
-constexpr int kPfBoxX = 64, kPfBoxY = 4, kPfBoxZ = 4; // box of the tensor map (elements)
-
-__global__ void __launch_bounds__(256) tile_box_kernel(MeshView m, unsigned tet_begin, unsigned tet_end, int include_bound, int X, int Y, int Z, int x_align, int4 *__restrict__ box)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned tile = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const unsigned n_tiles = (tet_end - tet_begin + 31) / 32;
-    if (tile >= n_tiles) return;
-    const unsigned t = tet_begin + tile * 32 + lane;
-    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
-    if (t < tet_end && (include_bound || __ldg(m.tet_label + t) != 0)) {
-        const uint4 nd = __ldg(m.tet_nodes + t);
-        const float4 p0 = __ldg(m.pos4f + nd.x), p1 = __ldg(m.pos4f + nd.y), p2 = __ldg(m.pos4f + nd.z), p3 = __ldg(m.pos4f + nd.w);
-        lo[0] = (int)floorf(fminf(fminf(p0.x, p1.x), fminf(p2.x, p3.x))); hi[0] = (int)floorf(fmaxf(fmaxf(p0.x, p1.x), fmaxf(p2.x, p3.x)));
-        lo[1] = (int)floorf(fminf(fminf(p0.y, p1.y), fminf(p2.y, p3.y))); hi[1] = (int)floorf(fmaxf(fmaxf(p0.y, p1.y), fmaxf(p2.y, p3.y)));
-        lo[2] = (int)floorf(fminf(fminf(p0.z, p1.z), fminf(p2.z, p3.z))); hi[2] = (int)floorf(fmaxf(fmaxf(p0.z, p1.z), fmaxf(p2.z, p3.z)));
-    }
-    const int dim[3] = {X, Y, Z};
-    int ext[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        lo[k] = max(__reduce_min_sync(0xffffffffu, lo[k]), 0);
-        hi[k] = min(__reduce_max_sync(0xffffffffu, hi[k]), dim[k] - 1);
-        // the TMA unit faults ("illegal instruction") on a box whose first element is not 16-byte aligned (scripts/tma_prefetch_probe.cu)
-        if (k == 0) lo[0] &= ~(x_align - 1);
-        ext[k] = hi[k] >= lo[k] ? hi[k] - lo[k] + 1 : 0;
-    }
-    // tiles that wrap around a row of the mesh span the whole volume in x: not worth prefetching
-    const bool ok = ext[0] > 0 && ext[1] > 0 && ext[2] > 0 && ext[0] <= 4 * kPfBoxX && ext[1] <= 8 * kPfBoxY && ext[2] <= 8 * kPfBoxZ;
-    if (lane == 0) box[tile] = make_int4(lo[0], lo[1], lo[2], ok ? (ext[0] | (ext[1] << 10) | (ext[2] << 20)) : 0);
-}
-
-DSC_D void tile_prefetch_l2(const TmapBlob *tmap, int4 b)
-{
-    const int ex = b.w & 1023, ey = (b.w >> 10) & 1023, ez = (b.w >> 20) & 1023;
-    for (int z = 0; z < ez; z += kPfBoxZ)
-        for (int y = 0; y < ey; y += kPfBoxY)
-            for (int x = 0; x < ex; x += kPfBoxX)
-                asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(b.x + x), "r"(b.y + y), "r"(b.z + z) : "memory");
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -957,13 +707,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                     }
                     VoxT val[U];
 #pragma unroll
-#if defined(W2_FAKE) && W2_FAKE == 1 // measurement only (scripts/w2_gather_bound.sh): wrong voxels, never defined by build.py
-                    for (int u = 0; u < U; u++) val[u] = __ldg(vol + (idx[u] & 4095));
-#elif defined(W2_FAKE) && W2_FAKE == 2
-                    for (int u = 0; u < U; u++) val[u] = reinterpret_cast<const VoxT *>(s_tabd)[idx[u] & 1023];
-#else
                     for (int u = 0; u < U; u++) val[u] = (!TAIL || idx[u] >= 0) ? __ldg(vol + idx[u]) : (VoxT)0;
-#endif
 #pragma unroll
                     for (int u = 0; u < U; u++) add_voxel(val[u]);
                 };
@@ -1036,11 +780,6 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                 }
             }
         }
-        if constexpr (PF) {
-            // The box of this warp's next tile -> L2 while its phase A (ids -> positions -> records: two dependent DRAM round trips)
-            // runs.  Asked for a whole tile earlier (22 us at C4) the boxes of all resident warps overflow the L2: measured slower.
-            if (lane == 0 && tile + total_warps < n_tiles) tile_prefetch_l2(&a.tmap, __ldg(a.tile_box + tile + total_warps));
-        }
     }
 #pragma unroll
     for (int m = 16; m >= G; m >>= 1) {
@@ -1061,910 +800,6 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
         a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
     }
     if (lane == 0 && w_ns[warp]) atomicAdd(a.sample_count, w_ns[warp]);
-}
-
-// -------------------------------------------------------------------------------------------------
-// w4 (variant 512): w2 with a software-pipelined phase B -- the index computation and the gathers of the next batch (which
-// may belong to the group's next tet) are issued before the pending batch is accumulated, so two batches (8 gathers per
-// lane) are in flight and the accumulation no longer waits on the loads it has just issued.
-// -------------------------------------------------------------------------------------------------
-template <typename VoxT, bool WANT_SQ, bool PER_TET>
-__global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w4_kernel(const TetArgs a)
-{
-    constexpr int G = 8, U = 4;
-    __shared__ float4 s_lat[kSmemRows];        // (a1, a2, a3, eps) per table row
-    __shared__ double2 s_tabd[2 * kSmemRows];  // exact rows for the fallback
-    __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0-.5 xyz, thr) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
-    __shared__ int2 w_m[8][32];                // meta, (O_linear - fold)
-    __shared__ double w_v[8][32];
-    __shared__ uint4 w_nd[8][32];
-    for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
-    for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_lat[i] = a.tet_lat[i];
-    __syncthreads();
-
-    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
-    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
-    const int XYi = X * Y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lane_g = lane & (G - 1), grp = lane >> 3;
-    const unsigned gmask = 0xFFu << (grp * 8);
-    const unsigned n_work = a.tet_end - a.tet_begin;
-    const unsigned n_tiles = (n_work + 31) / 32;
-    const unsigned total_warps = gridDim.x * 8;
-    const float MAGIC = 12582912.0f; // 1.5 * 2^23
-    const unsigned fold = 0x4B400000u * (unsigned)(XYi + X + 1);
-
-    double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane_g + 1
-    unsigned long long nsamp = 0;
-
-    for (unsigned tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += total_warps) {
-        const unsigned base_t = a.tet_begin + tile * 32;
-        const int nb = (int)min(32u, a.tet_end - base_t);
-        __syncwarp();
-        // ---------------- phase A: lane <-> tet ----------------
-        // Records are stored in a permuted order: tets with at most 32 samples first, then the larger ones, inactive tets
-        // last -- the four groups of a phase-B round then mostly run the same number of batches (a 27-sample tet next to a
-        // 64-sample one would idle for a batch) and rounds past the last active tet are skipped.
-        int n_act = 0;
-        {
-            int meta = 0, olin = 0;
-            bool active = false, big = false, fast = false;
-            float4 rq0 = make_float4(0, 0, 0, 0), re1 = rq0, re2 = rq0, re3 = rq0;
-            double rv = 0;
-            uint4 rnd = make_uint4(0, 0, 0, 0);
-            if (lane < nb) {
-                const unsigned t = base_t + lane;
-                const int label = __ldg(a.mesh.tet_label + t);
-                active = a.include_bound || label != 0;
-                meta = (label & 0xff) | (lane << 16);
-                if (active) {
-                    const uint4 nd = __ldg(a.mesh.tet_nodes + t);
-                    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-                    const double v = tet_volume(p0, p1, p2, p3);
-                    const int L = tet_level(v);
-                    big = (L + 1) * (L + 1) * (L + 1) > G * U;
-                    const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
-                    const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
-                    const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
-                    // strictly inside the volume with a margin: no sample can leave [1, dim-1), so no bounds checks, no negatives
-                    const bool interior = lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5;
-                    const double ox = floor(lox), oy = floor(loy), oz = floor(loz);
-                    const double rmax = fmax(fmax(hix - ox, hiy - oy), hiz - oz);
-                    fast = interior && L < kSmemLevels && rmax < 100.0;
-                    meta |= (L << 8) | (1 << 12);
-                    if (fast) {
-                        const double inv4n = 1.0 / (double)(4 * (L + 1));
-                        rq0 = make_float4((float)((p0.x - ox) - 0.5), (float)((p0.y - oy) - 0.5), (float)((p0.z - oz) - 0.5),
-                                          0.5f - (48.0f * (float)rmax + 8.0f) * 5.9604644775390625e-08f);
-                        re1 = make_float4((float)((p1.x - p0.x) * inv4n), (float)((p1.y - p0.y) * inv4n), (float)((p1.z - p0.z) * inv4n), (float)ox);
-                        re2 = make_float4((float)((p2.x - p0.x) * inv4n), (float)((p2.y - p0.y) * inv4n), (float)((p2.z - p0.z) * inv4n), (float)oy);
-                        re3 = make_float4((float)((p3.x - p0.x) * inv4n), (float)((p3.y - p0.y) * inv4n), (float)((p3.z - p0.z) * inv4n), (float)oz);
-                        olin = (int)((unsigned)((int)oz * XYi + (int)oy * X + (int)ox) - fold);
-                        meta |= 1 << 13;
-                    }
-                    rv = v;
-                    rnd = nd;
-                } else {
-                    if (a.tet_total) a.tet_total[t] = -1.0;
-                    if (a.tet_vol) a.tet_vol[t] = -1.0;
-                    if (a.tet_mean) a.tet_mean[t] = -1.0;
-                }
-            }
-            const unsigned m_small = __ballot_sync(0xffffffffu, active && !big);
-            const unsigned m_big = __ballot_sync(0xffffffffu, active && big);
-            const unsigned lt = (1u << lane) - 1u;
-            n_act = __popc(m_small) + __popc(m_big);
-            const int slot = active ? (big ? __popc(m_small) + __popc(m_big & lt) : __popc(m_small & lt))
-                                    : n_act + __popc(~(m_small | m_big) & lt);
-            w_m[warp][slot] = make_int2(meta, olin);
-            if (active) {
-                w_v[warp][slot] = rv;
-                w_nd[warp][slot] = rnd;
-                if (fast) { w_q0[warp][slot] = rq0; w_e1[warp][slot] = re1; w_e2[warp][slot] = re2; w_e3[warp][slot] = re3; }
-            }
-        }
-        __syncwarp();
-        // ---------------- phase B, software-pipelined: the gathers of batch k+1 are issued before batch k is consumed ------
-        VoxT pval[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) pval[u] = (VoxT)0;
-        bool pending = false, p_last = false;
-        int p_meta = 0, p_n3 = 1;
-        double p_v = 0;
-        double s = 0, sq = 0;
-        unsigned long long isum = 0, isq = 0;
-        auto consume = [&]() {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                if constexpr (VoxTraits<VoxT>::integral) {
-                    const unsigned q = (unsigned)pval[u];
-                    isum += q;
-                    if (WANT_SQ) isq += (unsigned long long)q * q;
-                } else {
-                    double I;
-                    if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)pval[u]);
-                    else I = (double)pval[u];
-                    s += I;
-                    if (WANT_SQ) sq = fma(I, I, sq);
-                }
-            }
-            if (p_last) { // last batch of its tet: group reduction and bookkeeping (the 8 lanes of the group are converged)
-                if constexpr (VoxTraits<VoxT>::integral) {
-                    const double dn = VoxTraits<VoxT>::denom();
-                    s = (double)isum / dn;
-                    if (WANT_SQ) sq = (double)isq / (dn * dn);
-                }
-#pragma unroll
-                for (int m = G / 2; m >= 1; m >>= 1) {
-                    s += __shfl_xor_sync(gmask, s, m);
-                    if (WANT_SQ) sq += __shfl_xor_sync(gmask, sq, m);
-                }
-                const int label = p_meta & 0xff;
-                const double tot = s * p_v / (double)p_n3; // total = total * v / a.size()  (image3d.cpp:371)
-                const double tsq = WANT_SQ ? sq * p_v / (double)p_n3 : 0.0;
-                if (lane_g == 0) {
-                    nsamp += (unsigned long long)p_n3;
-                    if (PER_TET) {
-                        const unsigned t = base_t + ((p_meta >> 16) & 31);
-                        if (a.tet_total) a.tet_total[t] = tot;
-                        if (a.tet_vol) a.tet_vol[t] = p_v;
-                        if (a.tet_mean) a.tet_mean[t] = tot / p_v;
-                    }
-                }
-                if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
-                    acc_tot += tot;
-                    acc_sq += tsq;
-                    acc_vol += p_v;
-                }
-                s = 0; sq = 0; isum = 0; isq = 0;
-            }
-        };
-        for (int r = 0; r * 4 < n_act; r++) {
-            const int j = r * 4 + grp;
-            const int2 mm = w_m[warp][j];
-            const int meta = mm.x;
-            if (!(meta & (1 << 12))) continue;
-            const int L = (meta >> 8) & 0xf;
-            const int n3 = (L + 1) * (L + 1) * (L + 1);
-            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
-            const double v_j = w_v[warp][j];
-            if (meta & (1 << 13)) {
-                const float4 q0 = w_q0[warp][j], e1 = w_e1[warp][j], e2 = w_e2[warp][j], e3 = w_e3[warp][j];
-                const float thr = q0.w;
-                const unsigned obase = (unsigned)mm.y;
-                const float4 *__restrict__ tl = s_lat + off;
-                const int last = n3 - 1;
-                for (int b0 = 0; b0 < n3; b0 += G * U) { // uniform trip count over the group (consume() shuffles inside)
-                    const int base = b0 + lane_g;
-                    int idx[U];
-                    unsigned unsafe = 0;
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int i = base + u * G;
-                        const bool ok = i <= last;
-                        const float4 c = tl[min(i, last)];
-                        const float qx = fmaf(c.z, e3.x, fmaf(c.y, e2.x, fmaf(c.x, e1.x, fmaf(c.w, e1.w, q0.x))));
-                        const float qy = fmaf(c.z, e3.y, fmaf(c.y, e2.y, fmaf(c.x, e1.y, fmaf(c.w, e2.w, q0.y))));
-                        const float qz = fmaf(c.z, e3.z, fmaf(c.y, e2.z, fmaf(c.x, e1.z, fmaf(c.w, e3.w, q0.z))));
-                        const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
-                        const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
-                        const int lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) + obase);
-                        idx[u] = ok ? lin : -1;
-                        if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) unsafe |= 1u << u;
-                    }
-                    if (unsafe) { // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
-                        const uint4 nd = w_nd[warp][j];
-                        const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                        const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-#pragma unroll
-                        for (int u = 0; u < U; u++)
-                            if (unsafe & (1u << u)) {
-                                const int i = base + u * G;
-                                const double2 b01 = s_tabd[2 * (off + i)], b23 = s_tabd[2 * (off + i) + 1];
-                                const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-                                const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-                                const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                                idx[u] = iz * XYi + iy * X + ix; // interior tet: always in range
-                            }
-                    }
-                    VoxT nval[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) nval[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
-                    if (pending) consume();
-#pragma unroll
-                    for (int u = 0; u < U; u++) pval[u] = nval[u];
-                    pending = true; p_last = b0 + G * U >= n3; p_meta = meta; p_n3 = n3; p_v = v_j;
-                }
-            } else {
-                // exact path (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491)
-                const uint4 nd = w_nd[warp][j];
-                const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
-                for (int b0 = 0; b0 < n3; b0 += G * U) { // uniform trip count over the group (consume() shuffles inside)
-                    const int base = b0 + lane_g;
-                    int idx[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int i = base + u * G;
-                        idx[u] = -1;
-                        if (i < n3) {
-                            const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
-                            const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-                            const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-                            const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                            if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) idx[u] = iz * XYi + iy * X + ix;
-                        }
-                    }
-                    VoxT nval[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) nval[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
-                    if (pending) consume();
-#pragma unroll
-                    for (int u = 0; u < U; u++) pval[u] = nval[u];
-                    pending = true; p_last = b0 + G * U >= n3; p_meta = meta; p_n3 = n3; p_v = v_j;
-                }
-            }
-        }
-        if (pending) consume();
-    }
-#pragma unroll
-    for (int m = 16; m >= G; m >>= 1) {
-        acc_tot += shfl_xor_d(acc_tot, m);
-        acc_sq += shfl_xor_d(acc_sq, m);
-        acc_vol += shfl_xor_d(acc_vol, m);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
-    __shared__ double sm[8][3 * kMaxPhase];
-    if (lane < kMaxPhase) {
-        sm[warp][lane] = acc_tot;
-        sm[warp][kMaxPhase + lane] = acc_sq;
-        sm[warp][2 * kMaxPhase + lane] = acc_vol;
-    }
-    __syncthreads();
-    if (threadIdx.x < 3 * kMaxPhase) {
-        double r = 0;
-        for (int wdx = 0; wdx < 8; wdx++) r += sm[wdx][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
-    }
-    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
-}
-
-// -------------------------------------------------------------------------------------------------
-// w3 (variant 256): w2 with the per-sample instruction count cut further.
-//   * the float chain starts at Q0 + 128 with O = floor(min corner) - 1, so the result t lies in [128, 256): its
-//     mantissa IS the fixed-point relative coordinate with 16 fraction bits.  floor = byte 2 of the bit pattern (one
-//     PRMT), the distance to the nearest voxel boundary is the low 16 bits: no FADD/F2I at all.  A sample is "unsafe"
-//     when its fraction is within K units of 2^-16 of an integer; K covers the c0 rounding (0.5), four FFMA roundings
-//     at ulp(t) = 2^-16 (2.0), the float rounding of E_k (6*2^-24*R) and the lattice perturbation tau (4*4.45e-7*R),
-//     R = Rmax + 1:  K = ceil(3 + 0.141 R).
-//   * the widened voxel uses one special-value test per batch; the second moment is optional.
-// -------------------------------------------------------------------------------------------------
-template <typename VoxT, bool WANT_SQ, bool PER_TET>
-__global__ void __launch_bounds__(256, 3) tet_integrate_w3_kernel(const TetArgs a)
-{
-    constexpr int G = 8, U = 4;
-    __shared__ float4 s_lat[kSmemRows];
-    __shared__ double2 s_tabd[2 * kSmemRows];
-    __shared__ float4 w_q0[8][32], w_e1[8][32], w_e2[8][32], w_e3[8][32]; // (Q0+128 xyz, K<<16 as bits) (E1 xyz, Ox) (E2 xyz, Oy) (E3 xyz, Oz)
-    __shared__ int2 w_m[8][32];               // meta, O_linear
-    __shared__ double w_v[8][32];
-    __shared__ uint4 w_nd[8][32];
-    for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
-    for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_lat[i] = a.tet_lat[i];
-    __syncthreads();
-
-    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
-    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
-    const int XYi = X * Y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lane_g = lane & (G - 1), grp = lane >> 3;
-    const unsigned gmask = 0xFFu << (grp * 8);
-    const unsigned n_work = a.tet_end - a.tet_begin;
-    const unsigned n_tiles = (n_work + 31) / 32;
-    const unsigned total_warps = gridDim.x * 8;
-
-    double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane_g + 1
-    unsigned long long nsamp = 0;
-
-    for (unsigned tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += total_warps) {
-        const unsigned base_t = a.tet_begin + tile * 32;
-        const int nb = (int)min(32u, a.tet_end - base_t);
-        __syncwarp();
-        // ---------------- phase A: lane <-> tet ----------------
-        {
-            int meta = 0;
-            int olin = 0;
-            if (lane < nb) {
-                const unsigned t = base_t + lane;
-                const int label = __ldg(a.mesh.tet_label + t);
-                const bool active = a.include_bound || label != 0;
-                meta = label & 0xff;
-                if (active) {
-                    const uint4 nd = __ldg(a.mesh.tet_nodes + t);
-                    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-                    const double v = tet_volume(p0, p1, p2, p3);
-                    const int L = tet_level(v);
-                    const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
-                    const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
-                    const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
-                    const bool interior = lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5;
-                    const double ox = floor(lox) - 1.0, oy = floor(loy) - 1.0, oz = floor(loz) - 1.0; // relative coordinates >= 1
-                    const double R = fmax(fmax(hix - ox, hiy - oy), hiz - oz) + 1.0;
-                    const bool fast = interior && L < kSmemLevels && R < 120.0;
-                    meta |= (L << 8) | (1 << 12);
-                    if (fast) {
-                        const double inv4n = 1.0 / (double)(4 * (L + 1));
-                        const unsigned K = (unsigned)ceil(3.0 + 0.141 * R);
-                        w_q0[warp][lane] = make_float4((float)((p0.x - ox) + 128.0), (float)((p0.y - oy) + 128.0), (float)((p0.z - oz) + 128.0), __uint_as_float(K << 16));
-                        w_e1[warp][lane] = make_float4((float)((p1.x - p0.x) * inv4n), (float)((p1.y - p0.y) * inv4n), (float)((p1.z - p0.z) * inv4n), (float)ox);
-                        w_e2[warp][lane] = make_float4((float)((p2.x - p0.x) * inv4n), (float)((p2.y - p0.y) * inv4n), (float)((p2.z - p0.z) * inv4n), (float)oy);
-                        w_e3[warp][lane] = make_float4((float)((p3.x - p0.x) * inv4n), (float)((p3.y - p0.y) * inv4n), (float)((p3.z - p0.z) * inv4n), (float)oz);
-                        olin = (int)oz * XYi + (int)oy * X + (int)ox;
-                        meta |= 1 << 13;
-                    }
-                    w_v[warp][lane] = v;
-                    w_nd[warp][lane] = nd;
-                } else {
-                    if (a.tet_total) a.tet_total[t] = -1.0;
-                    if (a.tet_vol) a.tet_vol[t] = -1.0;
-                    if (a.tet_mean) a.tet_mean[t] = -1.0;
-                }
-            }
-            w_m[warp][lane] = make_int2(meta, olin);
-        }
-        __syncwarp();
-        // ---------------- phase B: 8 lanes <-> tet; group grp takes tets grp, grp+4, ... of the tile ----------------
-        for (int r = 0; r < 8; r++) {
-            const int j = r * 4 + grp;
-            const int2 mm = w_m[warp][j];
-            const int meta = mm.x;
-            const bool active = (meta & (1 << 12)) != 0;
-            const int label = meta & 0xff;
-            const int L = (meta >> 8) & 0xf;
-            const int n3 = active ? (L + 1) * (L + 1) * (L + 1) : 0;
-            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
-            double s = 0, sq = 0;
-            unsigned long long isum = 0, isq = 0;
-            auto add_voxel = [&](VoxT val) {
-                if constexpr (VoxTraits<VoxT>::integral) {
-                    const unsigned q = (unsigned)val;
-                    isum += q;
-                    if (WANT_SQ) isq += (unsigned long long)q * q;
-                } else {
-                    double I;
-                    if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val);
-                    else I = (double)val;
-                    s += I;
-                    if (WANT_SQ) sq = fma(I, I, sq);
-                }
-            };
-            if (meta & (1 << 13)) {
-                const float4 q0 = w_q0[warp][j], e1 = w_e1[warp][j], e2 = w_e2[warp][j], e3 = w_e3[warp][j];
-                const unsigned kk = __float_as_uint(q0.w); // K << 16
-                const int obase = mm.y;
-                const float4 *__restrict__ tl = s_lat + off;
-                const int last = n3 - 1;
-                for (int base = lane_g; base < n3; base += G * U) {
-                    int idx[U];
-                    unsigned worst = 0xffffffffu;
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int i = base + u * G;
-                        const float4 c = tl[min(i, last)];
-                        const float tx = fmaf(c.z, e3.x, fmaf(c.y, e2.x, fmaf(c.x, e1.x, fmaf(c.w, e1.w, q0.x))));
-                        const float ty = fmaf(c.z, e3.y, fmaf(c.y, e2.y, fmaf(c.x, e1.y, fmaf(c.w, e2.w, q0.y))));
-                        const float tz = fmaf(c.z, e3.z, fmaf(c.y, e2.z, fmaf(c.x, e1.z, fmaf(c.w, e3.w, q0.z))));
-                        const unsigned ux = __float_as_uint(tx), uy = __float_as_uint(ty), uz = __float_as_uint(tz);
-                        // fraction field (16 bits) moved to the top and biased by K: a small value <=> within K*2^-16 of an integer
-                        const unsigned m = min(min(ux * 65536u + kk, uy * 65536u + kk), uz * 65536u + kk);
-                        const int lin = (int)(__byte_perm(uz, 0, 0x4442) * (unsigned)XYi + __byte_perm(uy, 0, 0x4442) * (unsigned)X + __byte_perm(ux, 0, 0x4442)) + obase;
-                        const bool ok = i <= last;
-                        idx[u] = ok ? lin : -1;
-                        worst = ok ? min(worst, m) : worst;
-                    }
-                    if (worst < 2u * kk) { // some coordinate within K*2^-16 of a voxel boundary: exact reference arithmetic decides
-                        const uint4 nd = w_nd[warp][j];
-                        const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                        const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-#pragma unroll
-                        for (int u = 0; u < U; u++) {
-                            const int i = base + u * G;
-                            if (i <= last) {
-                                const double2 b01 = s_tabd[2 * (off + i)], b23 = s_tabd[2 * (off + i) + 1];
-                                const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-                                const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-                                const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                                idx[u] = iz * XYi + iy * X + ix; // interior tet: always in range
-                            }
-                        }
-                    }
-                    VoxT val[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
-#pragma unroll
-                    for (int u = 0; u < U; u++) add_voxel(val[u]);
-                }
-            } else if (active) {
-                // exact path (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491)
-                const uint4 nd = w_nd[warp][j];
-                const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
-                for (int base = lane_g; base < n3; base += G * U) {
-                    int idx[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int i = base + u * G;
-                        idx[u] = -1;
-                        if (i < n3) {
-                            const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
-                            const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-                            const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-                            const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                            if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) idx[u] = iz * XYi + iy * X + ix;
-                        }
-                    }
-                    VoxT val[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) val[u] = idx[u] >= 0 ? __ldg(vol + idx[u]) : (VoxT)0;
-#pragma unroll
-                    for (int u = 0; u < U; u++) add_voxel(val[u]);
-                }
-            }
-            if constexpr (VoxTraits<VoxT>::integral) {
-                const double dn = VoxTraits<VoxT>::denom();
-                s = (double)isum / dn;
-                if (WANT_SQ) sq = (double)isq / (dn * dn);
-            }
-#pragma unroll
-            for (int m = G / 2; m >= 1; m >>= 1) {
-                s += shfl_xor_d(s, m);
-                if (WANT_SQ) sq += shfl_xor_d(sq, m);
-            }
-            if (active) {
-                const double v = w_v[warp][j];
-                const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
-                const double tsq = WANT_SQ ? sq * v / (double)n3 : 0.0;
-                if (lane_g == 0) {
-                    nsamp += (unsigned long long)n3;
-                    if (PER_TET) {
-                        const unsigned t = base_t + j;
-                        if (a.tet_total) a.tet_total[t] = tot;
-                        if (a.tet_vol) a.tet_vol[t] = v;
-                        if (a.tet_mean) a.tet_mean[t] = tot / v;
-                    }
-                }
-                if (label >= 1 && label <= a.nb_phase && lane_g == label - 1) {
-                    acc_tot += tot;
-                    acc_sq += tsq;
-                    acc_vol += v;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int m = 16; m >= G; m >>= 1) {
-        acc_tot += shfl_xor_d(acc_tot, m);
-        acc_sq += shfl_xor_d(acc_sq, m);
-        acc_vol += shfl_xor_d(acc_vol, m);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
-    __shared__ double sm[8][3 * kMaxPhase];
-    if (lane < kMaxPhase) {
-        sm[warp][lane] = acc_tot;
-        sm[warp][kMaxPhase + lane] = acc_sq;
-        sm[warp][2 * kMaxPhase + lane] = acc_vol;
-    }
-    __syncthreads();
-    if (threadIdx.x < 3 * kMaxPhase) {
-        double rr = 0;
-        for (int wdx = 0; wdx < 8; wdx++) rr += sm[wdx][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = rr;
-    }
-    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
-}
-
-// -------------------------------------------------------------------------------------------------
-// Two-phase CTA form (the default hot path): setup once per tet, sampling with a warp per tet.
-//
-// Each CTA walks batches of kBatch consecutive tets:
-//   phase A  one THREAD per tet: label, node ids, FP64 positions -> exact volume, sample level, float copies of the
-//            vertices, FP32-filter threshold; the record goes to shared memory.  The three dependent global loads of
-//            a tet are issued by 256 threads at once and overlap with phase B of the other CTAs on the SM, instead of
-//            sitting on every warp's critical path, and the setup arithmetic is no longer replicated per lane.
-//   phase B  one WARP per tet: lane j takes samples j, j+32, ... (consecutive table rows = spatially adjacent points,
-//            so a 32-lane gather touches only a few cache lines); positions come from the shared record (broadcast
-//            LDS), the barycentric rows from shared memory.  The voxel index uses the FP32 filter with exact FP64
-//            fallback (see below); two 32-sample chunks are indexed before their gathers are issued.
-// Per-label sums: the label is warp-uniform in phase B, so each lane adds its partial (sum_lane * v / n^3) straight into
-// per-label registers (no per-tet shuffle reduction on the hot path); PER_TET additionally reduces per tet and writes
-// tet_total / tet_vol / tet_mean with the reference's (sum * v) / n^3 rounding.  One partial row per CTA, added in CTA
-// order by tet_finalize_kernel: bit-reproducible.
-// No conversion instruction remains in the per-sample path: F2I/F2F run on the XU pipe, which they saturated in the
-// earlier forms (ncu: xu_realtime 84 %); floor() is taken with the 1.5*2^23 trick on the FP32 pipe and the gathered
-// float is widened to double with integer ops.
-// -------------------------------------------------------------------------------------------------
-constexpr int kBatch = 256;
-#ifndef W2_MIN_BLOCKS
-#define W2_MIN_BLOCKS 3
-#endif
-
-template <typename VoxT, int PMAX, bool PER_TET>
-__global__ void __launch_bounds__(256) tet_integrate_ab_kernel(const TetArgs a)
-{
-    __shared__ float4 s_tabf[kSmemRows];
-    __shared__ double2 s_tabd[2 * kSmemRows];
-    __shared__ float4 r_pa[kBatch], r_pb[kBatch], r_pc[kBatch]; // (ax,ay,az,bx) (by,bz,cx,cy) (cz,dx,dy,dz)
-    __shared__ double r_v[kBatch];
-    __shared__ uint4 r_nd[kBatch];
-    __shared__ float r_thr[kBatch];
-    __shared__ int r_meta[kBatch]; // bits 0-7 label, 8-11 level, 12 active, 13 fast path allowed
-    for (int i = threadIdx.x; i < 2 * kSmemRows; i += blockDim.x) s_tabd[i] = reinterpret_cast<const double2 *>(a.tet_bary)[i];
-    for (int i = threadIdx.x; i < kSmemRows; i += blockDim.x) s_tabf[i] = a.tet_bary_f[i];
-
-    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
-    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
-    const int XYi = X * Y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned n_work = a.tet_end - a.tet_begin;
-    const unsigned n_batches = (n_work + kBatch - 1) / kBatch;
-    const float MAGIC = 12582912.0f; // 1.5 * 2^23
-    const unsigned fold = 0x4B400000u * (unsigned)(XYi + X + 1); // the three MAGIC_BITS offsets of (iz*XY + iy*X + ix); wraps, as intended
-
-    double acc_tot[PMAX], acc_sq[PMAX], acc_vol[PMAX];
-#pragma unroll
-    for (int k = 0; k < PMAX; k++) acc_tot[k] = acc_sq[k] = acc_vol[k] = 0.0;
-    unsigned long long nsamp = 0;
-
-    for (unsigned bt = blockIdx.x; bt < n_batches; bt += gridDim.x) {
-        const unsigned base_t = a.tet_begin + bt * kBatch;
-        const int nb = (int)min((unsigned)kBatch, a.tet_end - base_t);
-        __syncthreads(); // previous batch fully consumed (also covers the table staging on the first pass)
-        // ---------------- phase A: one thread per tet ----------------
-        if ((int)threadIdx.x < nb) {
-            const unsigned t = base_t + threadIdx.x;
-            const int label = __ldg(a.mesh.tet_label + t);
-            const bool active = a.include_bound || label != 0;
-            int meta = label & 0xff;
-            if (active) {
-                const uint4 nd = __ldg(a.mesh.tet_nodes + t);
-                const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-                const double v = tet_volume(p0, p1, p2, p3);
-                const int L = tet_level(v);
-                const float ax = (float)p0.x, ay = (float)p0.y, az = (float)p0.z, bx = (float)p1.x, by = (float)p1.y, bz = (float)p1.z;
-                const float cx = (float)p2.x, cy = (float)p2.y, cz = (float)p2.z, dx = (float)p3.x, dy = (float)p3.y, dz = (float)p3.z;
-                // conservative interior test on the float copies (within 2^-24 relative of the doubles; margin 0.5): every
-                // vertex, hence every sample point (a convex combination up to 1e-5), lies in [1, dim-1) on each axis
-                const float lo = fminf(fminf(fminf(fminf(ax, ay), az), fminf(fminf(bx, by), bz)), fminf(fminf(fminf(cx, cy), cz), fminf(fminf(dx, dy), dz)));
-                const float hx = fmaxf(fmaxf(ax, bx), fmaxf(cx, dx)), hy = fmaxf(fmaxf(ay, by), fmaxf(cy, dy)), hz = fmaxf(fmaxf(az, bz), fmaxf(cz, dz));
-                const bool interior = lo >= 1.5f && hx < (float)X - 1.5f && hy < (float)Y - 1.5f && hz < (float)Z - 1.5f;
-                const float M = fmaxf(fmaxf(hx, hy), hz);
-                const bool fast = interior && L < kSmemLevels && M < 65536.0f;
-                r_pa[threadIdx.x] = make_float4(ax, ay, az, bx);
-                r_pb[threadIdx.x] = make_float4(by, bz, cx, cy);
-                r_pc[threadIdx.x] = make_float4(cz, dx, dy, dz);
-                r_v[threadIdx.x] = v;
-                r_nd[threadIdx.x] = nd;
-                r_thr[threadIdx.x] = 0.5f - (M + 1.0f) * 9.5367431640625e-07f; // 0.5 - delta, delta = 2^-20 (M + 1)
-                meta |= (L << 8) | (1 << 12) | (fast ? (1 << 13) : 0);
-            } else {
-                if (a.tet_total) a.tet_total[t] = -1.0;
-                if (a.tet_vol) a.tet_vol[t] = -1.0;
-                if (a.tet_mean) a.tet_mean[t] = -1.0;
-            }
-            r_meta[threadIdx.x] = meta;
-        }
-        __syncthreads();
-        // ---------------- phase B: one warp per tet ----------------
-        for (int j = warp; j < nb; j += 8) {
-            const int meta = r_meta[j];
-            if (!(meta & (1 << 12))) continue;
-            const int label = meta & 0xff;
-            const int L = (meta >> 8) & 0xf;
-            const int n3 = (L + 1) * (L + 1) * (L + 1);
-            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
-            double s = 0, sq = 0;
-            unsigned long long isum = 0, isq = 0;
-            auto add_voxel = [&](VoxT val) {
-                if constexpr (VoxTraits<VoxT>::integral) {
-                    const unsigned q = (unsigned)val;
-                    isum += q;
-                    isq += (unsigned long long)q * q;
-                } else {
-                    double I;
-                    if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val);
-                    else I = (double)val;
-                    s += I;
-                    sq = fma(I, I, sq); // second moment: tolerance quantity, fused on purpose
-                }
-            };
-            if (meta & (1 << 13)) {
-                const float4 pa = r_pa[j], pb = r_pb[j], pc = r_pc[j];
-                const float thr = r_thr[j];
-                const float4 *__restrict__ tf = s_tabf + off;
-                const int last = n3 - 1;
-                auto exact_index = [&](int i) -> int {
-                    // a coordinate within delta of a voxel boundary: the reference's FP64 arithmetic decides
-                    // (get_coord, DEMO/tet_dis_coord.hpp:27; truncation, image3d.cpp:366)
-                    const uint4 nd = r_nd[j];
-                    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-                    const double2 b01 = s_tabd[2 * (off + i)], b23 = s_tabd[2 * (off + i) + 1];
-                    const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-                    const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-                    const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                    return iz * XYi + iy * X + ix; // interior tet: always in range
-                };
-                auto fast_index = [&](int i, bool ok) -> int {
-                    const float4 b = tf[min(i, last)];
-                    const float qx = fmaf(b.w, pc.y, fmaf(b.z, pb.z, fmaf(b.y, pa.w, fmaf(b.x, pa.x, -0.5f))));
-                    const float qy = fmaf(b.w, pc.z, fmaf(b.z, pb.w, fmaf(b.y, pb.x, fmaf(b.x, pa.y, -0.5f))));
-                    const float qz = fmaf(b.w, pc.w, fmaf(b.z, pc.x, fmaf(b.y, pb.y, fmaf(b.x, pa.z, -0.5f))));
-                    const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
-                    const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
-                    int lin = (int)(__float_as_uint(tz) * (unsigned)XYi + __float_as_uint(ty) * (unsigned)X + __float_as_uint(tx) - fold);
-                    if (ok && fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) lin = exact_index(i);
-                    return ok ? lin : -1;
-                };
-                for (int c0 = lane; c0 < n3; c0 += 64) {
-                    const int i1 = c0 + 32;
-                    const int idx0 = fast_index(c0, true);
-                    const int idx1 = fast_index(i1, i1 < n3);
-                    const VoxT v0 = __ldg(vol + idx0);
-                    const VoxT v1 = idx1 >= 0 ? __ldg(vol + idx1) : (VoxT)0;
-                    add_voxel(v0);
-                    add_voxel(v1);
-                }
-            } else {
-                // exact path: tets touching the volume border (bounds-checked reads, negative coordinates) or very large tets
-                const uint4 nd = r_nd[j];
-                const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-                const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
-                for (int i = lane; i < n3; i += 32) {
-                    const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
-                    const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-                    const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-                    const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                    VoxT val = (VoxT)0;
-                    if ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z) val = __ldg(vol + (iz * XYi + iy * X + ix));
-                    add_voxel(val);
-                }
-            }
-            if constexpr (VoxTraits<VoxT>::integral) {
-                const double dn = VoxTraits<VoxT>::denom();
-                s = (double)isum / dn;
-                sq = (double)isq / (dn * dn);
-            }
-            const double v = r_v[j];
-            if (PER_TET) {
-#pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) {
-                    s += shfl_xor_d(s, m);
-                    sq += shfl_xor_d(sq, m);
-                }
-                const double tot = s * v / (double)n3; // total = total * v / a.size()  (image3d.cpp:371)
-                const double tsq = sq * v / (double)n3;
-                if (lane == 0) {
-                    const unsigned t = base_t + j;
-                    if (a.tet_total) a.tet_total[t] = tot;
-                    if (a.tet_vol) a.tet_vol[t] = v;
-                    if (a.tet_mean) a.tet_mean[t] = tot / v;
-                }
-                s = lane == 0 ? tot : 0.0;
-                sq = lane == 0 ? tsq : 0.0;
-            } else {
-                const double wgt = v / (double)n3;
-                s *= wgt;
-                sq *= wgt;
-            }
-            const double vl = lane == 0 ? v : 0.0;
-#pragma unroll
-            for (int k = 0; k < PMAX; k++)
-                if (label == k + 1 && k < a.nb_phase) { acc_tot[k] += s; acc_sq[k] += sq; acc_vol[k] += vl; }
-            if (lane == 0) nsamp += (unsigned long long)n3;
-        }
-    }
-    // ---- CTA reduction: warp trees, then one row per CTA
-#pragma unroll
-    for (int k = 0; k < PMAX; k++)
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            acc_tot[k] += shfl_xor_d(acc_tot[k], m);
-            acc_sq[k] += shfl_xor_d(acc_sq[k], m);
-            acc_vol[k] += shfl_xor_d(acc_vol[k], m);
-        }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
-    __shared__ double sm[8][3 * kMaxPhase];
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < kMaxPhase; k++) {
-            sm[warp][k] = k < PMAX ? acc_tot[k < PMAX ? k : 0] : 0.0;
-            sm[warp][kMaxPhase + k] = k < PMAX ? acc_sq[k < PMAX ? k : 0] : 0.0;
-            sm[warp][2 * kMaxPhase + k] = k < PMAX ? acc_vol[k < PMAX ? k : 0] : 0.0;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < 3 * kMaxPhase) {
-        double r = 0;
-        for (int wdx = 0; wdx < 8; wdx++) r += sm[wdx][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
-    }
-    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
-}
-
-// -------------------------------------------------------------------------------------------------
-// Thread-per-tet form with an FP32 filter in front of the exact FP64 position.
-//
-// One thread owns one tet: setup (ids, positions, volume, level) is done once per tet instead of once per
-// lane, and the sample loop is unrolled so that several voxel gathers are in flight per thread.
-//
-// FILTER: the voxel a sample falls into only depends on floor() of its position, so the position is first
-// evaluated in FP32 (12 FFMA) with a rigorous error bound delta; when every coordinate is further than delta
-// from an integer, floor of the FP32 value equals floor of the reference's FP64 value and the exact 21-op
-// FP64 evaluation is skipped.  Otherwise (about 0.3 % of the samples at 512^3) the sample is re-evaluated with
-// the exact reference arithmetic.  Bound: inputs rounded to float (2^-24 relative each), 4 FMA roundings on
-// partial sums of magnitude <= M + 0.5 (M = largest |vertex coordinate| of the tet; the weights are >= 0 and sum
-// to ~1):  |q - r| <= 7 * 2^-24 * (M + 0.5); delta = 2^-20 * (M + 1) keeps a 2x margin.  The filter is only
-// used for tets whose vertices lie inside [1, dim-1) on every axis (no negative coordinates, no bounds checks
-// needed for any sample because samples are convex combinations of the vertices up to 1e-5).
-// floor via the 1.5*2^23 trick: the FMA chain starts at -0.5, t = q' + MAGIC rounds to the nearest integer n,
-// d = q' - n in [-0.5, 0.5], and floor(q) = n whenever |d| < 0.5 - delta.  No F2I conversion (XU pipe) needed.
-// -------------------------------------------------------------------------------------------------
-constexpr int kFetchLdg = 0, kFetchTex = 1;
-
-template <typename VoxT, int FETCH, bool FILTER>
-__global__ void __launch_bounds__(128) tet_integrate_tpt_kernel(const TetArgs a)
-{
-    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
-    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
-    const size_t XY = (size_t)X * Y;
-    const int lane = threadIdx.x & 31;
-    const unsigned total_threads = gridDim.x * blockDim.x;
-    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned n_work = a.tet_end - a.tet_begin;
-    const unsigned iters = (n_work + total_threads - 1) / total_threads;
-    const float MAGIC = 12582912.0f; // 1.5 * 2^23
-    const int MAGIC_BITS = 0x4B400000;
-
-    double acc_tot = 0, acc_sq = 0, acc_vol = 0; // per-label sums of label == lane + 1
-    unsigned long long nsamp = 0;
-
-    for (unsigned it = 0; it < iters; it++) {
-        const unsigned w = it * total_threads + tid;
-        const bool valid = w < n_work;
-        const unsigned t = a.tet_begin + (valid ? w : 0);
-        int label = 0;
-        bool active = false;
-        double tot = 0, tsq = 0, v = 0;
-        if (valid) {
-            label = __ldg(a.mesh.tet_label + t);
-            active = a.include_bound || label != 0;
-        }
-        if (active) {
-            const uint4 nd = __ldg(a.mesh.tet_nodes + t);
-            const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-            const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-            v = tet_volume(p0, p1, p2, p3);
-            const int L = tet_level(v);
-            const int n3 = (L + 1) * (L + 1) * (L + 1);
-            const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
-            const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
-            const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
-            const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
-            const bool interior = lox >= 1.0 && loy >= 1.0 && loz >= 1.0 && hix < (double)(X - 1) && hiy < (double)(Y - 1) && hiz < (double)(Z - 1);
-            double s = 0, sq = 0;
-            unsigned long long isum = 0, isq = 0;
-            auto accumulate = [&](int ix, int iy, int iz, bool checked) {
-                if constexpr (VoxTraits<VoxT>::integral) {
-                    unsigned q;
-                    if constexpr (FETCH == kFetchTex) q = (unsigned)tex_fetch<VoxT>(a.tex, ix, iy, iz);
-                    else if (checked || ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z))
-                        q = (unsigned)__ldg(vol + (size_t)iz * XY + (size_t)iy * X + ix);
-                    else q = 0;
-                    isum += q;
-                    isq += (unsigned long long)q * q;
-                } else {
-                    double I;
-                    if constexpr (FETCH == kFetchTex) I = (double)tex_fetch<VoxT>(a.tex, ix, iy, iz);
-                    else if (checked || ((unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z))
-                        I = (double)__ldg(vol + (size_t)iz * XY + (size_t)iy * X + ix);
-                    else I = 0.0;
-                    s += I;
-                    sq = fma(I, I, sq); // second moment: tolerance quantity, fused on purpose
-                }
-            };
-            const double M = fmax(fmax(hix, hiy), hiz);
-            if (FILTER && interior && M < 65536.0) {
-                const float delta = (float)((M + 1.0) * 9.5367431640625e-07); // 2^-20
-                const float thr = 0.5f - delta;
-                const float ax = (float)p0.x, ay = (float)p0.y, az = (float)p0.z, bx = (float)p1.x, by = (float)p1.y, bz = (float)p1.z;
-                const float cx = (float)p2.x, cy = (float)p2.y, cz = (float)p2.z, dx = (float)p3.x, dy = (float)p3.y, dz = (float)p3.z;
-                const float4 *__restrict__ tf = a.tet_bary_f + off;
-                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
-#pragma unroll 4
-                for (int i = 0; i < n3; i++) {
-                    const float4 b = __ldg(tf + i);
-                    const float qx = fmaf(b.w, dx, fmaf(b.z, cx, fmaf(b.y, bx, fmaf(b.x, ax, -0.5f))));
-                    const float qy = fmaf(b.w, dy, fmaf(b.z, cy, fmaf(b.y, by, fmaf(b.x, ay, -0.5f))));
-                    const float qz = fmaf(b.w, dz, fmaf(b.z, cz, fmaf(b.y, bz, fmaf(b.x, az, -0.5f))));
-                    const float tx = qx + MAGIC, ty = qy + MAGIC, tz = qz + MAGIC;
-                    const float ex = qx - (tx - MAGIC), ey = qy - (ty - MAGIC), ez = qz - (tz - MAGIC);
-                    int ix = __float_as_int(tx) - MAGIC_BITS, iy = __float_as_int(ty) - MAGIC_BITS, iz = __float_as_int(tz) - MAGIC_BITS;
-                    if (fmaxf(fmaxf(fabsf(ex), fabsf(ey)), fabsf(ez)) >= thr) {
-                        // too close to a voxel boundary for FP32: exact reference arithmetic
-                        const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
-                        ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-                        iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-                        iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                    }
-                    accumulate(ix, iy, iz, true);
-                }
-            } else {
-                const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
-#pragma unroll 2
-                for (int i = 0; i < n3; i++) {
-                    const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
-                    const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-                    const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-                    const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-                    accumulate(ix, iy, iz, interior);
-                }
-            }
-            if (VoxTraits<VoxT>::integral) {
-                const double dn = VoxTraits<VoxT>::denom();
-                s = (double)isum / dn;
-                sq = (double)isq / (dn * dn);
-            }
-            tot = s * v / (double)n3;
-            tsq = sq * v / (double)n3;
-            nsamp += (unsigned long long)n3;
-            if (a.tet_total) a.tet_total[t] = tot;
-            if (a.tet_vol) a.tet_vol[t] = v;
-            if (a.tet_mean) a.tet_mean[t] = tot / v;
-        } else if (valid) {
-            if (a.tet_total) a.tet_total[t] = -1.0;
-            if (a.tet_vol) a.tet_vol[t] = -1.0;
-            if (a.tet_mean) a.tet_mean[t] = -1.0;
-        }
-        // per-label warp reduction: lane k keeps the sums of label k+1
-        for (int k = 0; k < a.nb_phase; k++) {
-            const bool m = active && label == k + 1;
-            double x = m ? tot : 0.0, y = m ? tsq : 0.0, z = m ? v : 0.0;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                x += shfl_xor_d(x, o);
-                y += shfl_xor_d(y, o);
-                z += shfl_xor_d(z, o);
-            }
-            if (lane == k) { acc_tot += x; acc_sq += y; acc_vol += z; }
-        }
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
-    __shared__ double sm[4][3 * kMaxPhase];
-    const int warp = threadIdx.x >> 5;
-    if (lane < kMaxPhase) {
-        sm[warp][lane] = acc_tot;
-        sm[warp][kMaxPhase + lane] = acc_sq;
-        sm[warp][2 * kMaxPhase + lane] = acc_vol;
-    }
-    __syncthreads();
-    if (threadIdx.x < 3 * kMaxPhase) {
-        double r = 0;
-        const int nw = blockDim.x >> 5;
-        for (int wdx = 0; wdx < nw; wdx++) r += sm[wdx][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = r;
-    }
-    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
 }
 
 // Adds the per-CTA partial rows and derives the means: out[0..P) total, [P..2P) sumsq, [2P..3P) volume (P = nb_phase),

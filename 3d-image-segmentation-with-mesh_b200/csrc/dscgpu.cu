@@ -13,7 +13,6 @@
 
 #include "../../include/dscgpu.h"
 #include "dsc_kernels.cuh"
-#include "dsc_tet_g32.cuh"
 #include "dsc_tet_staged.cuh"
 #include "dsc_comm.cuh"
 #include "dsc_tables.h"
@@ -76,14 +75,9 @@ struct dscgpu_ctx {
     double *d_tet_bary = nullptr;
     float4 *d_tet_bary_f = nullptr;
     float4 *d_tet_lat = nullptr;
-    cudaArray_t vol_array = nullptr;
-    cudaTextureObject_t vol_tex = 0;
     int force_thread_gather = 0; // 1: thread-per-node gather (first implementation) instead of warp-per-node
     int hot_want_sq = 0; // dscgpu_image_force_eval / dscgpu_tet_phase_sums_dev skip the second moment unless asked
     int tet_variant = 128 | 16384; // see dscgpu_set_tet_variant; default = w2, full batches without clamps on the sums-only path (the fastest measured form: DESIGN.md section 9)
-    // w2 PF (variant bit 65536): tensor map of the volume (passed by value in the kernel arguments), voxel boxes of the 32-tet tiles of one launch range
-    TmapBlob tmap_host;
-    int tmap_state = 0; // 0 not tried, 1 ready, -1 unavailable (layout not expressible / no driver entry point)
     // staged kernel (variant bit 131072, dsc_tet_staged.cuh): tensor-map family in device memory, tile counter, fixed-point scales
     TmapBlob *d_stg_maps = nullptr;
     unsigned *d_stg_counter = nullptr;
@@ -92,19 +86,8 @@ struct dscgpu_ctx {
     double stg_scale[3] = {1.0, 1.0, 1.0};
     bool tet_rows_fixed = false; // the partial rows of the running tet pass are fixed-point integers (staged kernel)
     float vol_max = 1.0f;        // largest voxel of a float volume (volume_flags_kernel)
-    int4 *d_tile_box = nullptr;
-    size_t tile_box_cap = 0;
-    unsigned tb_begin = 0, tb_end = 0;
-    int tb_bound = -1;
-    bool tb_valid = false;
-    // bricked, padded copy of the volume for tet_sums_g32_kernel (dsc_tet_g32.cuh); rebuilt when the volume may have changed
-    void *d_brick = nullptr;
-    bool brick_valid = false;
-    bool brick_simple = true; // float volume holds only non-negative finite numbers (flag of the bricked copy's build)
     bool vol_flags_valid = false, vol_simple = false; // the same property from a scan of the volume (volume_flags_kernel)
-    int brick_nb[3] = {0, 0, 0};
-    float4 *d_lat32 = nullptr;
-    unsigned *d_brick_flags = nullptr;
+    unsigned *d_vol_flags = nullptr;
     // peer-memory exchange (dsc_comm.cuh): this rank's window, the peers' windows as mapped here
     unsigned char *comm_win[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool comm_ipc[8] = {false, false, false, false, false, false, false, false}; // mapped with cudaIpcOpenMemHandle (to be closed)
@@ -248,98 +231,20 @@ template <typename VoxT, int G, bool WITH_C> int launch_tet_t(dscgpu_ctx *ctx, T
     return DSCGPU_OK;
 }
 
-template <typename VoxT, int FETCH, bool FILTER> int launch_tpt_t(dscgpu_ctx *ctx, TetArgs &a)
-{
-    auto kern = tet_integrate_tpt_kernel<VoxT, FETCH, FILTER>;
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
-    if (occ < 1) occ = 1;
-    unsigned n_work = a.tet_end - a.tet_begin;
-    unsigned need = (n_work + 127) / 128;
-    unsigned grid = (unsigned)(ctx->num_sms * occ);
-    if (need < grid) grid = need ? need : 1;
-    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
-    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
-    ctx->tet_grid += (int)grid;
-    kern<<<grid, 128, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return DSCGPU_OK;
-}
-
-template <typename VoxT> int launch_tpt_v(dscgpu_ctx *ctx, TetArgs &a, bool tex, bool filter)
-{
-    if (tex) return filter ? launch_tpt_t<VoxT, kFetchTex, true>(ctx, a) : launch_tpt_t<VoxT, kFetchTex, false>(ctx, a);
-    return filter ? launch_tpt_t<VoxT, kFetchLdg, true>(ctx, a) : launch_tpt_t<VoxT, kFetchLdg, false>(ctx, a);
-}
-
-// w2 PF: a CUtensorMap over the volume (3-D, x fastest, box kPfBoxX x kPfBoxY x kPfBoxZ) for cp.async.bulk.prefetch.tensor.
-// Volumes whose row pitch is not a multiple of 16 bytes cannot be described: the kernel then runs without the prefetch.
-int ensure_tmap(dscgpu_ctx *ctx)
-{
-    if (ctx->tmap_state != 0) return DSCGPU_OK;
-    ctx->tmap_state = -1;
-    const size_t es = dtype_size(ctx->dtype);
-    const cuuint64_t X = (cuuint64_t)ctx->dims[0], Y = (cuuint64_t)ctx->dims[1], Z = (cuuint64_t)ctx->dims[2];
-    if ((X * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(ctx->d_vol) & 15) != 0) return DSCGPU_OK;
-    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-        cudaGetLastError();
-        return DSCGPU_OK;
-    }
-    const CUtensorMapDataType dt = ctx->dtype == DSCGPU_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : ctx->dtype == DSCGPU_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
-                                   : ctx->dtype == DSCGPU_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
-    alignas(64) CUtensorMap tm;
-    const cuuint64_t gdim[3] = {X, Y, Z}, gstr[2] = {X * es, X * Y * es};
-    const cuuint32_t box[3] = {(cuuint32_t)kPfBoxX, (cuuint32_t)kPfBoxY, (cuuint32_t)kPfBoxZ}, estr[3] = {1, 1, 1};
-    if (reinterpret_cast<encode_fn>(fn)(&tm, dt, 3, ctx->d_vol, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return DSCGPU_OK;
-    static_assert(sizeof(CUtensorMap) == sizeof(TmapBlob), "CUtensorMap is 128 bytes");
-    memcpy(&ctx->tmap_host, &tm, sizeof(CUtensorMap));
-    ctx->tmap_state = 1;
-    return DSCGPU_OK;
-}
-
-// w2 PF: voxel boxes of the 32-tet tiles of [begin, end), once per snapshot and range
-int ensure_tile_boxes(dscgpu_ctx *ctx, const TetArgs &a)
-{
-    if (ctx->tb_valid && ctx->tb_begin == a.tet_begin && ctx->tb_end == a.tet_end && ctx->tb_bound == a.include_bound) return DSCGPU_OK;
-    const unsigned n_tiles = (a.tet_end - a.tet_begin + 31) / 32;
-    if (!n_tiles) return DSCGPU_OK;
-    if ((size_t)n_tiles > ctx->tile_box_cap) {
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(ctx->stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { ctx->tb_valid = false; return DSCGPU_OK; }
-        if (ctx->d_tile_box) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_tile_box); ctx->d_tile_box = nullptr; ctx->tile_box_cap = 0; }
-        const size_t want = (size_t)n_tiles + n_tiles / 4 + 64;
-        CK(cudaMalloc(&ctx->d_tile_box, want * sizeof(int4)));
-        ctx->tile_box_cap = want;
-    }
-    tile_box_kernel<<<(n_tiles + 7) / 8, 256, 0, ctx->stream>>>(a.mesh, a.tet_begin, a.tet_end, a.include_bound, ctx->dims[0], ctx->dims[1], ctx->dims[2], (int)(16 / dtype_size(ctx->dtype)), ctx->d_tile_box);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    ctx->tb_begin = a.tet_begin; ctx->tb_end = a.tet_end; ctx->tb_bound = a.include_bound;
-    ctx->tb_valid = true;
-    return DSCGPU_OK;
-}
-
 // float volumes: one pass that tells whether every voxel is a non-negative finite number (scaled widening, dsc_kernels.cuh)
 int ensure_volume_flags(dscgpu_ctx *ctx)
 {
     if (ctx->vol_flags_valid) return DSCGPU_OK;
     ctx->vol_simple = false;
     if (ctx->dtype == DSCGPU_F32) {
-        if (!ctx->d_brick_flags) { CK(cudaMalloc(&ctx->d_brick_flags, 4 * sizeof(unsigned))); CK(cudaMemset(ctx->d_brick_flags, 0, 4 * sizeof(unsigned))); }
-        CK(cudaMemsetAsync(ctx->d_brick_flags, 0, 2 * sizeof(unsigned), ctx->stream));
+        if (!ctx->d_vol_flags) { CK(cudaMalloc(&ctx->d_vol_flags, 4 * sizeof(unsigned))); CK(cudaMemset(ctx->d_vol_flags, 0, 4 * sizeof(unsigned))); }
+        CK(cudaMemsetAsync(ctx->d_vol_flags, 0, 2 * sizeof(unsigned), ctx->stream));
         const size_t n = (size_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2];
-        volume_flags_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(static_cast<const float *>(ctx->d_vol), n, ctx->d_brick_flags);
+        volume_flags_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(static_cast<const float *>(ctx->d_vol), n, ctx->d_vol_flags);
         ctx->launches++;
         CK(cudaGetLastError());
         unsigned flags[2] = {1, 0};
-        CK(cudaMemcpyAsync(flags, ctx->d_brick_flags, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(flags, ctx->d_vol_flags, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->vol_simple = (flags[0] & 1u) == 0;
         memcpy(&ctx->vol_max, &flags[1], sizeof(float)); // bit pattern order = value order for non-negative floats
@@ -469,35 +374,11 @@ template <typename VoxT, bool WANT_SQ, bool PER_TET, bool BRICK = false, bool SI
 template <typename VoxT> int launch_w2(dscgpu_ctx *ctx, TetArgs &a)
 {
     const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
-    if (a.brick) { // bricked volume (variant bit 2048)
-        if (a.want_sq) return per_tet ? launch_w2_t<VoxT, true, true, true>(ctx, a) : launch_w2_t<VoxT, true, false, true>(ctx, a);
-        return per_tet ? launch_w2_t<VoxT, false, true, true>(ctx, a) : launch_w2_t<VoxT, false, false, true>(ctx, a);
-    }
-    if (a.tile_box && !a.want_sq && !per_tet) { // L2 prefetch of the next tile's voxels (variant bit 65536); hot-path instantiations only
+    if (a.lean && !a.want_sq && !per_tet) { // sums only: full batches without row clamps and masks
         if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
-            if (a.vol_simple) return launch_w2_t<VoxT, false, false, false, true, false, 0, true>(ctx, a);
+            if (a.vol_simple) return launch_w2_t<VoxT, false, false, false, true, false, 1>(ctx, a);
         }
-        return launch_w2_t<VoxT, false, false, false, false, false, 0, true>(ctx, a);
-    }
-    if (a.lean && a.pack && !a.want_sq && !per_tet && !a.brick) { // bits 8192 + 16384: packed arithmetic in clamp-free batches
-        if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
-            if (a.vol_simple) return launch_w2_t<VoxT, false, false, false, true, true, 1>(ctx, a);
-        }
-        return launch_w2_t<VoxT, false, false, false, false, true, 1>(ctx, a);
-    }
-    if (a.lean && !a.want_sq && !per_tet && !a.brick && !a.pack) { // variant bit 16384; hot-path instantiations only
-        if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
-            if (a.vol_simple) return a.lean == 2 ? launch_w2_t<VoxT, false, false, false, true, false, 2>(ctx, a) : launch_w2_t<VoxT, false, false, false, true, false, 1>(ctx, a);
-        }
-        return a.lean == 2 ? launch_w2_t<VoxT, false, false, false, false, false, 2>(ctx, a) : launch_w2_t<VoxT, false, false, false, false, false, 1>(ctx, a);
-    }
-    if (a.pack) { // packed FP32 position arithmetic (variant bit 8192); hot-path instantiations only
-        if (!a.want_sq && !per_tet) {
-            if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
-                if (a.vol_simple) return launch_w2_t<VoxT, false, false, false, true, true>(ctx, a);
-            }
-            return launch_w2_t<VoxT, false, false, false, false, true>(ctx, a);
-        }
+        return launch_w2_t<VoxT, false, false, false, false, false, 1>(ctx, a);
     }
     if constexpr (sizeof(VoxT) == 4 && !VoxTraits<VoxT>::integral) {
         if (a.vol_simple) { // non-negative finite floats: scaled widening
@@ -509,118 +390,6 @@ template <typename VoxT> int launch_w2(dscgpu_ctx *ctx, TetArgs &a)
     return per_tet ? launch_w2_t<VoxT, false, true>(ctx, a) : launch_w2_t<VoxT, false, false>(ctx, a);
 }
 
-template <typename VoxT, bool WANT_SQ, bool PER_TET> int launch_w3_t(dscgpu_ctx *ctx, TetArgs &a)
-{
-    auto kern = tet_integrate_w3_kernel<VoxT, WANT_SQ, PER_TET>;
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-    if (occ < 1) occ = 1;
-    unsigned n_work = a.tet_end - a.tet_begin;
-    unsigned need = (n_work + 255) / 256;
-    unsigned grid = (unsigned)(ctx->num_sms * occ);
-    if (need < grid) grid = need ? need : 1;
-    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
-    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
-    ctx->tet_grid += (int)grid;
-    kern<<<grid, 256, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return DSCGPU_OK;
-}
-
-template <typename VoxT> int launch_w3(dscgpu_ctx *ctx, TetArgs &a)
-{
-    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
-    if (a.want_sq) return per_tet ? launch_w3_t<VoxT, true, true>(ctx, a) : launch_w3_t<VoxT, true, false>(ctx, a);
-    return per_tet ? launch_w3_t<VoxT, false, true>(ctx, a) : launch_w3_t<VoxT, false, false>(ctx, a);
-}
-
-template <typename VoxT, bool WANT_SQ, bool PER_TET> int launch_w4_t(dscgpu_ctx *ctx, TetArgs &a)
-{
-    auto kern = tet_integrate_w4_kernel<VoxT, WANT_SQ, PER_TET>;
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-    if (occ < 1) occ = 1;
-    unsigned n_work = a.tet_end - a.tet_begin;
-    unsigned need = (n_work + 255) / 256;
-    unsigned grid = (unsigned)(ctx->num_sms * occ);
-    if (need < grid) grid = need ? need : 1;
-    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
-    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
-    ctx->tet_grid += (int)grid;
-    kern<<<grid, 256, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return DSCGPU_OK;
-}
-
-template <typename VoxT> int launch_w4(dscgpu_ctx *ctx, TetArgs &a)
-{
-    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
-    if (a.want_sq) return per_tet ? launch_w4_t<VoxT, true, true>(ctx, a) : launch_w4_t<VoxT, true, false>(ctx, a);
-    return per_tet ? launch_w4_t<VoxT, false, true>(ctx, a) : launch_w4_t<VoxT, false, false>(ctx, a);
-}
-
-template <typename VoxT, int PMAX, bool PER_TET> int launch_ab_t(dscgpu_ctx *ctx, TetArgs &a)
-{
-    auto kern = tet_integrate_ab_kernel<VoxT, PMAX, PER_TET>;
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-    if (occ < 1) occ = 1;
-    unsigned n_work = a.tet_end - a.tet_begin;
-    unsigned need = (n_work + kBatch - 1) / kBatch;
-    unsigned grid = (unsigned)(ctx->num_sms * occ);
-    if (need < grid) grid = need ? need : 1;
-    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
-    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
-    ctx->tet_grid += (int)grid;
-    kern<<<grid, 256, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return DSCGPU_OK;
-}
-
-template <typename VoxT> int launch_ab(dscgpu_ctx *ctx, TetArgs &a)
-{
-    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
-    if (a.nb_phase <= 4) return per_tet ? launch_ab_t<VoxT, 4, true>(ctx, a) : launch_ab_t<VoxT, 4, false>(ctx, a);
-    return per_tet ? launch_ab_t<VoxT, 8, true>(ctx, a) : launch_ab_t<VoxT, 8, false>(ctx, a);
-}
-
-template <typename VoxT, int G, int UNROLL, bool FILTER> int launch_g_t(dscgpu_ctx *ctx, TetArgs &a)
-{
-    auto kern = tet_integrate_g_kernel<VoxT, G, UNROLL, FILTER>;
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-    if (occ < 1) occ = 1;
-    unsigned n_work = a.tet_end - a.tet_begin;
-    unsigned groups_per_block = 256 / G;
-    unsigned need = (n_work + groups_per_block - 1) / groups_per_block;
-    unsigned grid = (unsigned)(ctx->num_sms * occ);
-    if (need < grid) grid = need ? need : 1;
-    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
-    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
-    ctx->tet_grid += (int)grid;
-    kern<<<grid, 256, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return DSCGPU_OK;
-}
-
-template <typename VoxT, int G> int launch_g_v(dscgpu_ctx *ctx, TetArgs &a, int unroll, bool filter)
-{
-    if (unroll >= 4) return filter ? launch_g_t<VoxT, G, 4, true>(ctx, a) : launch_g_t<VoxT, G, 4, false>(ctx, a);
-    if (unroll >= 2) return filter ? launch_g_t<VoxT, G, 2, true>(ctx, a) : launch_g_t<VoxT, G, 2, false>(ctx, a);
-    return filter ? launch_g_t<VoxT, G, 1, true>(ctx, a) : launch_g_t<VoxT, G, 1, false>(ctx, a);
-}
-
-template <typename VoxT> int launch_g(dscgpu_ctx *ctx, TetArgs &a, int G, int unroll, bool filter)
-{
-    if (G == 32) return launch_g_v<VoxT, 32>(ctx, a, unroll, filter);
-    if (G == 16) return launch_g_v<VoxT, 16>(ctx, a, unroll, filter);
-    return launch_g_v<VoxT, 8>(ctx, a, unroll, filter);
-}
-
 template <typename VoxT> int launch_tet_v(dscgpu_ctx *ctx, TetArgs &a, int G, bool with_c)
 {
     if (G == 32) return with_c ? launch_tet_t<VoxT, 32, true>(ctx, a) : launch_tet_t<VoxT, 32, false>(ctx, a);
@@ -628,118 +397,11 @@ template <typename VoxT> int launch_tet_v(dscgpu_ctx *ctx, TetArgs &a, int G, bo
 }
 
 
-// ---- warp-per-tet kernel over the bricked volume (dsc_tet_g32.cuh) ----
-size_t brick_elems(const dscgpu_ctx *ctx) { return (size_t)ctx->brick_nb[0] * ctx->brick_nb[1] * ctx->brick_nb[2] * 32; }
-
-template <typename VoxT> int build_bricks_t(dscgpu_ctx *ctx)
-{
-    const size_t n = brick_elems(ctx);
-    unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 32);
-    brick_volume_kernel<VoxT><<<grid, 256, 0, ctx->stream>>>(static_cast<const VoxT *>(ctx->d_vol), static_cast<VoxT *>(ctx->d_brick), ctx->dims[0], ctx->dims[1],
-                                                               ctx->dims[2], ctx->brick_nb[0], ctx->brick_nb[1], ctx->brick_nb[2], ctx->d_brick_flags);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return DSCGPU_OK;
-}
-
-// (re)builds the bricked copy if the volume may have changed since the last build; one pass over the volume, like the sum table
-int ensure_bricks(dscgpu_ctx *ctx)
-{
-    if (ctx->brick_valid) return DSCGPU_OK;
-    ctx->brick_nb[0] = (ctx->dims[0] + 2 * kBrickPad + 3) / 4;
-    ctx->brick_nb[1] = (ctx->dims[1] + 2 * kBrickPad + 1) / 2;
-    ctx->brick_nb[2] = (ctx->dims[2] + 2 * kBrickPad + 3) / 4;
-    if (!ctx->d_brick) CK(cudaMalloc(&ctx->d_brick, brick_elems(ctx) * dtype_size(ctx->dtype)));
-    if (!ctx->d_brick_flags) { CK(cudaMalloc(&ctx->d_brick_flags, 4 * sizeof(unsigned))); CK(cudaMemset(ctx->d_brick_flags, 0, 4 * sizeof(unsigned))); }
-    CK(cudaMemsetAsync(ctx->d_brick_flags, 0, sizeof(unsigned), ctx->stream));
-    int r;
-    switch (ctx->dtype) {
-    case DSCGPU_U8: r = build_bricks_t<unsigned char>(ctx); break;
-    case DSCGPU_U16: r = build_bricks_t<unsigned short>(ctx); break;
-    case DSCGPU_F32: r = build_bricks_t<float>(ctx); break;
-    default: r = build_bricks_t<double>(ctx); break;
-    }
-    if (r) return r;
-    unsigned flags = 0;
-    CK(cudaMemcpyAsync(&flags, ctx->d_brick_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->brick_simple = (flags & 1u) == 0;
-    ctx->brick_valid = true;
-    return DSCGPU_OK;
-}
-
-bool g32_fits(const dscgpu_ctx *ctx)
-{
-    const double n = ((double)ctx->dims[0] + 2 * kBrickPad + 3) * ((double)ctx->dims[1] + 2 * kBrickPad + 1) * ((double)ctx->dims[2] + 2 * kBrickPad + 3);
-    return n < 2147483648.0;
-}
-
-template <typename VoxT, bool SIMPLE, bool WANT_SQ, bool PER_TET> int launch_g32_t(dscgpu_ctx *ctx, const TetArgs &t)
-{
-    auto kern = tet_sums_g32_kernel<VoxT, SIMPLE, WANT_SQ, PER_TET>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG32SmemBytes)); // per device: set it every time
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, kG32SmemBytes));
-    if (occ < 1) occ = 1;
-    TetG32Args a;
-    a.mesh = t.mesh;
-    a.tet_bary = t.tet_bary;
-    a.lat32 = ctx->d_lat32;
-    a.brick = ctx->d_brick;
-    a.Sy = 32u * (unsigned)ctx->brick_nb[0];
-    a.Sz = a.Sy * (unsigned)ctx->brick_nb[1];
-    a.X = ctx->dims[0]; a.Y = ctx->dims[1]; a.Z = ctx->dims[2];
-    a.tet_begin = t.tet_begin; a.tet_end = t.tet_end;
-    a.nb_phase = t.nb_phase;
-    a.tet_total = t.tet_total; a.tet_vol = t.tet_vol; a.tet_mean = t.tet_mean;
-    a.sample_count = t.sample_count;
-    unsigned n_work = a.tet_end - a.tet_begin;
-    unsigned need = (n_work + 255) / 256;
-    unsigned grid = (unsigned)(ctx->num_sms * occ);
-    if (need < grid) grid = need ? need : 1;
-    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
-    a.partials = ctx->partials.as<double>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
-    ctx->tet_grid += (int)grid;
-    kern<<<grid, 256, kG32SmemBytes, ctx->stream>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return DSCGPU_OK;
-}
-
-template <typename VoxT, bool SIMPLE> int launch_g32_s(dscgpu_ctx *ctx, const TetArgs &a)
-{
-    const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
-    if (a.want_sq) return per_tet ? launch_g32_t<VoxT, SIMPLE, true, true>(ctx, a) : launch_g32_t<VoxT, SIMPLE, true, false>(ctx, a);
-    return per_tet ? launch_g32_t<VoxT, SIMPLE, false, true>(ctx, a) : launch_g32_t<VoxT, SIMPLE, false, false>(ctx, a);
-}
-
-int launch_g32(dscgpu_ctx *ctx, const TetArgs &a)
-{
-    switch (ctx->dtype) {
-    case DSCGPU_U8: return launch_g32_s<unsigned char, true>(ctx, a);
-    case DSCGPU_U16: return launch_g32_s<unsigned short, true>(ctx, a);
-    case DSCGPU_F32: return ctx->brick_simple ? launch_g32_s<float, true>(ctx, a) : launch_g32_s<float, false>(ctx, a);
-    default: return launch_g32_s<double, true>(ctx, a);
-    }
-}
-
+// Which kernel runs a tet pass (dscgpu_set_tet_variant): bit 131072 the staged kernel (dsc_tet_staged.cuh), bit 128 the w2 kernel
+// (bit 16384: clamp-free full batches on the sums-only path; bit 4096: general float widening), otherwise -- and whenever candidate
+// values c are given -- the plain G-lanes-per-tet kernel, which is the reference's sequence verbatim.
 int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
 {
-    if ((ctx->tet_variant & 1024) && !with_c && !a.include_bound && g32_fits(ctx)) { // warp-per-tet kernel over the bricked volume
-        int r = ensure_bricks(ctx);
-        if (r) return r;
-        return launch_g32(ctx, a);
-    }
-    if ((ctx->tet_variant & 1) && !with_c) {
-        const bool tex = (ctx->tet_variant & 2) && ctx->vol_tex != 0;
-        const bool filter = (ctx->tet_variant & 4) != 0;
-        switch (ctx->dtype) {
-        case DSCGPU_U8: return launch_tpt_v<unsigned char>(ctx, a, tex, filter);
-        case DSCGPU_U16: return launch_tpt_v<unsigned short>(ctx, a, tex, filter);
-        case DSCGPU_F32: return launch_tpt_v<float>(ctx, a, tex, filter);
-        default: return launch_tpt_t<double, kFetchLdg, false>(ctx, a); // no double textures; filter pointless without FP32 data
-        }
-    }
     int G = ctx->lanes_per_tet ? ctx->lanes_per_tet : ctx->auto_lanes;
     const bool fits32 = (double)ctx->dims[0] * ctx->dims[1] * ctx->dims[2] < 2147483648.0;
     if ((ctx->tet_variant & 131072) && !with_c && fits32) { // staged kernel: lane per tet, voxel boxes in shared memory by TMA
@@ -747,71 +409,18 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
         if (rs) return rs;
         if (ctx->stg_state == 1 && (ctx->tet_grid == 0 || ctx->tet_rows_fixed)) return launch_staged(ctx, a);
     }
-    if ((ctx->tet_variant & 512) && !with_c && fits32) { // w4: w2 with software-pipelined gathers
-        switch (ctx->dtype) {
-        case DSCGPU_U8: return launch_w4<unsigned char>(ctx, a);
-        case DSCGPU_U16: return launch_w4<unsigned short>(ctx, a);
-        case DSCGPU_F32: return launch_w4<float>(ctx, a);
-        default: return launch_w4<double>(ctx, a);
-        }
-    }
-    if ((ctx->tet_variant & 256) && !with_c && fits32) { // w3: lattice coordinates, fixed-point floor, independent groups
-        switch (ctx->dtype) {
-        case DSCGPU_U8: return launch_w3<unsigned char>(ctx, a);
-        case DSCGPU_U16: return launch_w3<unsigned short>(ctx, a);
-        case DSCGPU_F32: return launch_w3<float>(ctx, a);
-        default: return launch_w3<double>(ctx, a);
-        }
-    }
     if ((ctx->tet_variant & 128) && !with_c && fits32) { // warp-level two-phase kernel with lattice coordinates
-        a.brick = nullptr;
-        a.pack = (ctx->tet_variant & 8192) ? 1 : 0;
-        a.lean = (ctx->tet_variant & 16384) ? ((ctx->tet_variant & 32768) ? 2 : 1) : 0;
+        a.lean = (ctx->tet_variant & 16384) ? 1 : 0;
         if (!(ctx->tet_variant & 4096)) { // bit 12: keep the general float widening (A/B switch)
             int rf = ensure_volume_flags(ctx);
             if (rf) return rf;
             a.vol_simple = ctx->vol_simple ? 1 : 0;
-        }
-        a.tile_box = nullptr;
-        if ((ctx->tet_variant & 65536) && !(ctx->tet_variant & (2048 | 8192 | 16384)) && !a.want_sq && !(a.tet_total || a.tet_vol || a.tet_mean)) {
-            int rt = ensure_tmap(ctx);
-            if (rt) return rt;
-            if (ctx->tmap_state == 1) {
-                rt = ensure_tile_boxes(ctx, a);
-                if (rt) return rt;
-                if (ctx->tb_valid) { a.tile_box = ctx->d_tile_box; a.tmap = ctx->tmap_host; }
-            }
-        }
-        if ((ctx->tet_variant & 2048) && g32_fits(ctx)) { // ... gathering from the bricked, padded copy of the volume
-            int r = ensure_bricks(ctx);
-            if (r) return r;
-            a.brick = ctx->d_brick;
-            a.brick_sy = 32u * (unsigned)ctx->brick_nb[0];
-            a.brick_sz = a.brick_sy * (unsigned)ctx->brick_nb[1];
         }
         switch (ctx->dtype) {
         case DSCGPU_U8: return launch_w2<unsigned char>(ctx, a);
         case DSCGPU_U16: return launch_w2<unsigned short>(ctx, a);
         case DSCGPU_F32: return launch_w2<float>(ctx, a);
         default: return launch_w2<double>(ctx, a);
-        }
-    }
-    if ((ctx->tet_variant & 64) && !with_c && fits32) { // two-phase CTA kernel (32-bit voxel indices)
-        switch (ctx->dtype) {
-        case DSCGPU_U8: return launch_ab<unsigned char>(ctx, a);
-        case DSCGPU_U16: return launch_ab<unsigned short>(ctx, a);
-        case DSCGPU_F32: return launch_ab<float>(ctx, a);
-        default: return launch_ab<double>(ctx, a);
-        }
-    }
-    if ((ctx->tet_variant & 8) && !with_c && fits32) { // optimised group kernel (32-bit voxel indices): bits 4-5 = log2(unroll), bit 2 = FP32 filter
-        const int unroll = 1 << ((ctx->tet_variant >> 4) & 3);
-        const bool filter = (ctx->tet_variant & 4) != 0;
-        switch (ctx->dtype) {
-        case DSCGPU_U8: return launch_g<unsigned char>(ctx, a, G, unroll, filter);
-        case DSCGPU_U16: return launch_g<unsigned short>(ctx, a, G, unroll, filter);
-        case DSCGPU_F32: return launch_g<float>(ctx, a, G, unroll, filter);
-        default: return launch_g<double>(ctx, a, G, unroll, false);
         }
     }
     if (G != 32) G = 8;
@@ -836,7 +445,6 @@ int tet_pass_range(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, con
     a.mesh = mesh_view(ctx);
     a.tet_bary = ctx->d_tet_bary;
     a.tet_bary_f = ctx->d_tet_bary_f;
-    a.tex = ctx->vol_tex;
     a.tet_lat = ctx->d_tet_lat;
     a.want_sq = want_sq;
     a.tet_begin = begin; a.tet_end = end;
@@ -846,12 +454,8 @@ int tet_pass_range(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, con
     for (int k = 0; k < kMaxPhase; k++) a.c[k] = (c && k < nc) ? c[k] : 0.0;
     a.tet_total = o.d_total; a.tet_vol = o.d_vol; a.tet_mean = o.d_mean; a.tet_energy = o.d_energy; a.tet_variation = o.d_variation;
     a.sample_count = ctr(ctx, 0);
-    a.brick = nullptr; a.brick_sy = a.brick_sz = 0;
     a.vol_simple = 0;
-    a.pack = 0;
     a.lean = 0;
-    a.tile_box = nullptr;
-    memset(&a.tmap, 0, sizeof(a.tmap));
     return launch_tet(ctx, a, nc > 0 && (o.d_energy || o.d_variation));
 }
 
@@ -868,7 +472,7 @@ int tet_pass_finish(dscgpu_ctx *ctx, int nb_phase, double *d_sums_out, double *d
     TimerScope ts(ctx, DSCGPU_T_PHASE_FINAL);
     if (ctx->tet_rows_fixed)
         tet_finalize_fixed_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<long long>(), ctx->tet_grid, nb_phase, ctx->stg_scale[0], ctx->stg_scale[1], ctx->stg_scale[2],
-                                                                              d_sums_out, d_mean_out, ctx->d_brick_flags ? ctx->d_brick_flags + 2 : nullptr);
+                                                                              d_sums_out, d_mean_out, ctx->d_vol_flags ? ctx->d_vol_flags + 2 : nullptr);
     else
         tet_finalize_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums_out, d_mean_out);
     ctx->launches++;
@@ -1189,7 +793,6 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
     ctx->geom_async = false;
-    ctx->tb_valid = false;
     ctx->init_means_valid = false;
     ctx->has_tet_faces = false;
     CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ks));
@@ -1327,18 +930,6 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
         }
         CK(cudaMalloc(&ctx->d_tet_lat, tl.size() * sizeof(float)));
         CK(cudaMemcpy(ctx->d_tet_lat, tl.data(), tl.size() * sizeof(float), cudaMemcpyHostToDevice));
-        // the same rows with every level padded to a multiple of 32 (padding = the level's first row; masked in the kernel)
-        std::vector<float> t32(4 * (size_t)kG32Rows, 0.f);
-        for (int L = 0; L < DSC_TET_LEVELS; L++) {
-            const int first = DSC_TET_LEVEL_OFFSET[L], cnt = DSC_TET_LEVEL_OFFSET[L + 1] - first;
-            ARG(g32_slot_off(L + 1) - g32_slot_off(L) == (cnt + 31) / 32, "sample table does not match the slot layout of the warp-per-tet kernel");
-            for (int i = 0; i < (g32_slot_off(L + 1) - g32_slot_off(L)) * 32; i++) {
-                const int src = first + (i < cnt ? i : 0);
-                for (int k = 0; k < 4; k++) t32[4 * ((size_t)g32_slot_off(L) * 32 + i) + k] = tl[4 * (size_t)src + k];
-            }
-        }
-        CK(cudaMalloc(&ctx->d_lat32, t32.size() * sizeof(float)));
-        CK(cudaMemcpy(ctx->d_lat32, t32.data(), t32.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (const char *ev = getenv("DSCGPU_TET_VARIANT")) ctx->tet_variant = atoi(ev);
     if (const char *ev = getenv("DSCGPU_STG_SLOT_KB")) { // development knob: shared-memory slot of one warp of the staged kernel
@@ -1348,10 +939,6 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
     if (voxels_host) { // one scan of a float volume: are all voxels non-negative finite numbers?
         int rf = ensure_volume_flags(ctx);
         if (rf) return rf;
-    }
-    if (voxels_host && (ctx->tet_variant & (1024 | 2048)) && g32_fits(ctx)) { // bricked copy for the warp-per-tet kernel, once per volume
-        int rb = ensure_bricks(ctx);
-        if (rb) return rb;
     }
     if (const char *ev = getenv("DSCGPU_FORCE_THREAD_GATHER")) ctx->force_thread_gather = atoi(ev);
     CK(cudaMemcpyToSymbolAsync(c_gauss, DSC_GAUSS, sizeof(DSC_GAUSS), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -1375,7 +962,6 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
                       &ctx->h_node_inc, &ctx->h_node_active, &ctx->h_out, &ctx->h_flag, &ctx->h_upd};
     for (PinBuf *b : pins) b->release();
     if (ctx->d_vol) cudaFree(ctx->d_vol);
-    if (ctx->d_tile_box) cudaFree(ctx->d_tile_box);
     if (ctx->d_sum_table) cudaFree(ctx->d_sum_table);
     if (ctx->d_tet_bary) cudaFree(ctx->d_tet_bary);
     if (ctx->d_tet_bary_f) cudaFree(ctx->d_tet_bary_f);
@@ -1386,13 +972,9 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
         else if (k == ctx->comm_rank && ctx->comm_world) cudaFree(ctx->comm_win[k]);
     }
     if (ctx->comm_rows) cudaFree(ctx->comm_rows);
-    if (ctx->d_lat32) cudaFree(ctx->d_lat32);
-    if (ctx->d_brick) cudaFree(ctx->d_brick);
-    if (ctx->d_brick_flags) cudaFree(ctx->d_brick_flags);
+    if (ctx->d_vol_flags) cudaFree(ctx->d_vol_flags);
     if (ctx->d_stg_maps) cudaFree(ctx->d_stg_maps);
     if (ctx->d_stg_counter) cudaFree(ctx->d_stg_counter);
-    if (ctx->vol_tex) cudaDestroyTextureObject(ctx->vol_tex);
-    if (ctx->vol_array) cudaFreeArray(ctx->vol_array);
     for (int i = 0; i < DSCGPU_T_COUNT; i++) {
         if (ctx->ev[i][0]) cudaEventDestroy(ctx->ev[i][0]);
         if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]);
@@ -1422,7 +1004,6 @@ int dscgpu_synchronize(dscgpu_ctx *ctx)
 void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx)
 {
     if (!ctx) return nullptr;
-    ctx->brick_valid = false; // the caller may write the volume through this pointer
     ctx->vol_flags_valid = false;
     ctx->stg_state = 0; // the fixed-point scales depend on the largest voxel
     return ctx->d_vol;
@@ -1431,7 +1012,6 @@ void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx)
 int dscgpu_volume_modified(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ctx->brick_valid = false;
     ctx->vol_flags_valid = false;
     ctx->stg_state = 0; // the fixed-point scales depend on the largest voxel
     return DSCGPU_OK;
@@ -1444,7 +1024,6 @@ int dscgpu_volume_upload(dscgpu_ctx *ctx, const void *voxels_host)
     const size_t n = (size_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2];
     CK(cudaMemcpyAsync(ctx->d_vol, voxels_host, n * dtype_size(ctx->dtype), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->brick_valid = false;
     ctx->vol_flags_valid = false;
     ctx->stg_state = 0; // the fixed-point scales depend on the largest voxel
     ctx->has_sum_table = false;
@@ -1563,7 +1142,6 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->has_snapshot = true;
     ctx->geom_async = false;
-    ctx->tb_valid = false;
     ctx->init_means_valid = false;
     ctx->has_tet_faces = false;
 
@@ -1691,7 +1269,6 @@ int dscgpu_update_commit(dscgpu_ctx *ctx, int replace_faces)
     ctx->validation_pending = true;
     ctx->init_means_valid = false;
     ctx->geom_async = false;
-    ctx->tb_valid = false;
     ctx->staging_valid = false; // the pinned staging of the last full snapshot is stale: dscgpu_image_force_eval(ctx, NULL, ...) must not re-upload it
     return DSCGPU_OK;
 }
@@ -2309,45 +1886,20 @@ int dscgpu_get_timer(dscgpu_ctx *ctx, int which, float *ms)
     return DSCGPU_OK;
 }
 
-int dscgpu_build_texture(dscgpu_ctx *ctx)
-{
-    if (!ctx) return DSCGPU_ERR_ARG;
-    if (ctx->vol_tex) return DSCGPU_OK;
-    ARG(ctx->dtype != DSCGPU_F64, "no texture path for float64 volumes");
-    cudaChannelFormatDesc desc;
-    if (ctx->dtype == DSCGPU_U8) desc = cudaCreateChannelDesc<unsigned char>();
-    else if (ctx->dtype == DSCGPU_U16) desc = cudaCreateChannelDesc<unsigned short>();
-    else desc = cudaCreateChannelDesc<float>();
-    cudaExtent ext = make_cudaExtent((size_t)ctx->dims[0], (size_t)ctx->dims[1], (size_t)ctx->dims[2]);
-    CK(cudaMalloc3DArray(&ctx->vol_array, &desc, ext));
-    cudaMemcpy3DParms cp = {};
-    cp.srcPtr = make_cudaPitchedPtr(ctx->d_vol, (size_t)ctx->dims[0] * dtype_size(ctx->dtype), (size_t)ctx->dims[0], (size_t)ctx->dims[1]);
-    cp.dstArray = ctx->vol_array;
-    cp.extent = ext;
-    cp.kind = cudaMemcpyDeviceToDevice;
-    CK(cudaMemcpy3DAsync(&cp, ctx->stream));
-    cudaResourceDesc rd = {};
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = ctx->vol_array;
-    cudaTextureDesc td = {};
-    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
-    td.filterMode = cudaFilterModePoint;
-    td.readMode = cudaReadModeElementType;
-    td.normalizedCoords = 0;
-    CK(cudaCreateTextureObject(&ctx->vol_tex, &rd, &td, nullptr));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return DSCGPU_OK;
-}
-
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(variant >= 0 && variant < 262144, "variant is an 18-bit field");
-    if ((variant & 2) && ctx->dtype != DSCGPU_F64) {
-        int r = dscgpu_build_texture(ctx);
-        if (r) return r;
-    }
+    ARG(variant >= 0 && (variant & ~(128 | 4096 | 16384 | 131072)) == 0, "unknown tet-kernel variant bit (dscgpu.h lists them)");
     ctx->tet_variant = variant;
+    return DSCGPU_OK;
+}
+
+int dscgpu_get_tet_variant(const dscgpu_ctx *ctx) { return ctx ? ctx->tet_variant : -1; }
+
+int dscgpu_set_hot_want_sq(dscgpu_ctx *ctx, int on)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ctx->hot_want_sq = on ? 1 : 0;
     return DSCGPU_OK;
 }
 
@@ -2356,7 +1908,7 @@ uint64_t dscgpu_launch_count(const dscgpu_ctx *ctx) { return ctx ? ctx->launches
 int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
-    ARG(lanes == 0 || lanes == 8 || lanes == 16 || lanes == 32, "lanes per tet must be 0, 8, 16 or 32");
+    ARG(lanes == 0 || lanes == 8 || lanes == 32, "lanes per tet must be 0, 8 or 32");
     ctx->lanes_per_tet = lanes;
     return DSCGPU_OK;
 }

@@ -522,8 +522,15 @@ class SegmentFunction:
         return int(self.lib.dscgpu_last_gauss_count(self._img._ctx))
 
     def set_tet_variant(self, variant):
-        """bit0 thread-per-tet, bit1 texture gather, bit2 FP32 filter (see include/dscgpu.h)."""
+        """0 v1, 128 w2 (+4096 general widening, +16384 clamp-free batches), 131072 staged (see include/dscgpu.h)."""
         self._img._check(self.lib.dscgpu_set_tet_variant(self._img._ctx, C.c_int(variant)), "dscgpu_set_tet_variant")
+
+    def get_tet_variant(self):
+        return int(self.lib.dscgpu_get_tet_variant(self._img._ctx))
+
+    def set_hot_want_sq(self, on):
+        """Per-label second moment on the per-iteration entry points (off by default)."""
+        self._img._check(self.lib.dscgpu_set_hot_want_sq(self._img._ctx, C.c_int(1 if on else 0)), "dscgpu_set_hot_want_sq")
 
     def set_lanes_per_tet(self, lanes):
         self._img._check(self.lib.dscgpu_set_lanes_per_tet(self._img._ctx, C.c_int(lanes)), "dscgpu_set_lanes_per_tet")

@@ -303,24 +303,23 @@ int dscgpu_get_timer(dscgpu_ctx *ctx, int which, float *ms);
 uint64_t dscgpu_launch_count(const dscgpu_ctx *ctx);
 /* Tunables: lanes per tet of the integration kernel (1, 8 or 32; 0 = choose from the mesh). */
 int dscgpu_set_lanes_per_tet(dscgpu_ctx *ctx, int lanes);
-/* Implementation of the per-tet integration kernel (results are identical up to FP64 summation order):
- *   0            v1: G lanes per tet (dscgpu_set_lanes_per_tet), one gather in flight per lane
- *   bit 0 (1)    one thread per tet;  + bit 1 (2): gather through a 3-D texture;  + bit 2 (4): FP32 filter
- *   bit 3 (8)    batched G-lanes-per-tet kernel: bits 4-5 = log2(gathers in flight per lane), bit 2 (4) = FP32 filter
- *   bit 6 (64)   two-phase CTA kernel (setup per thread, sampling per warp, FP32 filter)
- *   bit 7 (128)  w2: warp-level two-phase kernel, origin-relative lattice coordinates;  256: w3 fixed-point floor;  512: w4 pipelined w2
- *   bit 10 (1024) warp-per-tet kernel over a bricked copy of the volume, packed FP32 (FFMA2) position arithmetic; serves every
- *                call without candidates and with include_bound == 0, the remaining bits choose the kernel for the other calls
- *   bit 11 (2048) with bit 7: w2 gathering from the bricked, padded copy of the volume
+/* Implementation of the per-tet integration kernel (every one puts every sample in the reference's voxel; sums agree to rounding):
+ *   0             v1: G lanes per tet (dscgpu_set_lanes_per_tet), the reference's FP64 sequence for every sample
+ *   bit 7 (128)   w2: warp-level two-phase kernel, origin-relative lattice coordinates, FP32 filter with exact FP64 fallback
  *   bit 12 (4096) with bit 7: keep the general float widening (off: scaled widening when the volume allows it)
- *   bit 13 (8192) with bit 7: packed FP32 (FFMA2) position arithmetic in the hot-path instantiation (also together with bit 14)
- *   bit 14 (16384) with bit 7: full batches without row clamps, per-tet weight from phase A; + bit 15 (32768): two batches per wait
- *   bit 16 (65536) with bit 7 alone: one lane asks the TMA unit to pull the voxel box of the warp's next 32-tet tile into L2 (a hint:
- *                results identical; volumes whose row pitch is not a multiple of 16 bytes run without it)
- * Default 128 + 16384 (w2 with clamp-free full batches on the sums-only path, the fastest measured form; DESIGN.md section 9 has the numbers of the others).  The environment variable DSCGPU_TET_VARIANT overrides the default at context creation.
+ *   bit 14 (16384) with bit 7: full batches without row clamps, per-tet weight from phase A, on the sums-only path
+ *   bit 17 (131072) staged kernel: lane per tet, the voxel box of each 32-tet tile brought into shared memory by TMA, per-label sums
+ *                 in 64-bit fixed point (independent of the order of the tiles and of the partition); volumes it cannot describe
+ *                 (FP64 voxels, row pitch not a multiple of 16 bytes, float volumes with negative or non-finite voxels) fall
+ *                 through to the kernel the remaining bits select
+ * The environment variable DSCGPU_TET_VARIANT overrides the default at context creation; DESIGN.md section 9 has the measurements,
+ * the branch proto/round1-variants the forms that were measured and dropped.
  * Per-candidate outputs (tet_energy / tet_variation) always use the v1 kernel. */
 int dscgpu_set_tet_variant(dscgpu_ctx *ctx, int variant);
-int dscgpu_build_texture(dscgpu_ctx *ctx);
+int dscgpu_get_tet_variant(const dscgpu_ctx *ctx);
+/* The per-iteration entry points (dscgpu_image_force_eval, dscgpu_tet_phase_sums_dev and the *_allreduce_dev forms) fill the
+ * per-label second moment (sum of I^2 v/n^3, DEMO/image3d.cpp:384-404 with c = 0) only when asked: 0 (default) leaves it zero. */
+int dscgpu_set_hot_want_sq(dscgpu_ctx *ctx, int on);
 /* Algorithmic sample count of the last tet pass (sum of n^3 over processed tets). */
 uint64_t dscgpu_last_sample_count(dscgpu_ctx *ctx);
 uint64_t dscgpu_last_gauss_count(dscgpu_ctx *ctx);

@@ -305,7 +305,7 @@ def test_ray_overflow_is_reported(pkg):
     img.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 5, 7, 8, 12, 24, 40, 44, 56, 60, 64, 128, 256, 512, 1152, 2176, 8320, 4224, 16512, 49280])
+@pytest.mark.parametrize("variant", [0, 128, 4224, 16512, 131072 | 16512])
 def test_every_kernel_variant_classifies_identically(pkg, variant):
     """All implementations of the tet pass (incl. the FP32-filtered ones) must put every sample in the same voxel:
     per-tet sums of noisy data agree to rounding, and the volumes bit for bit."""
@@ -314,7 +314,7 @@ def test_every_kernel_variant_classifies_identically(pkg, variant):
         img, seg = _seg(pkg, g)
         lab = g["tet_label"] != 0
         seg.set_tet_variant(variant)
-        for lanes in ((8, 16, 32) if variant & 8 else (0,)):
+        for lanes in ((8, 32) if variant == 0 else (0,)):
             seg.set_lanes_per_tet(lanes)
             o = seg.tet_integrate()
             assert np.array_equal(o["vol"][lab], g["tet_vol"][lab])
@@ -338,7 +338,7 @@ def test_filter_variants_on_large_interior_mesh(pkg, flat):
     img = pkg.Image3D(vol)
     seg = pkg.SegmentFunction(img, 3)
     seg.set_snapshot(snap)
-    for variant in (5, 12, 44, 60, 64, 128, 256, 512, 2176):
+    for variant in (128, 4224, 16512, 131072 | 16512):
         seg.set_tet_variant(variant)
         o = seg.tet_integrate(include_bound=True)
         assert np.array_equal(o["vol"], ref["vol"])
@@ -375,7 +375,7 @@ def test_non_cubic_volume_and_many_phases(pkg, flat, dtype, P):
     h, ns = seg.tet_sample_hash()
     assert np.array_equal(h, ref["hash"]) and np.array_equal(ns, ref["nsamp"])
     lab = snap["tet_label"]
-    for variant in (0, 40, 128, 512, 1152, 2176, 8320, 16512, 49280):
+    for variant in (0, 128, 16512, 131072 | 16512):
         seg.set_tet_variant(variant)
         o = seg.tet_integrate()
         m = lab != 0

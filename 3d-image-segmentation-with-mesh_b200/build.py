@@ -45,6 +45,15 @@ def needs_build():
         return True
 
 
+def build_variant(name, defines):
+    """Development: an experimental copy of the library with extra -D flags, as lib<name>.so next to the real one (DSCGPU_LIBRARY)."""
+    out = os.path.join(HERE, "lib%s.so" % name)
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17"] + ["-D" + d for d in defines] + [
+        "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return out
+
+
 def build(force=False, verbose=False):
     """Builds the library if it is missing or older than its sources.  Safe under concurrency (one process per GPU all import
     the package at once): an exclusive file lock serialises the check, and the compiler writes to a temporary file that is

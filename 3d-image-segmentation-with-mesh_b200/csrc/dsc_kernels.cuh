@@ -209,10 +209,14 @@ struct TetArgs {
     int pack;                        // w2: packed FP32 position arithmetic
     int lean;                        // w2: full/tail batch split, per-tet weight from phase A
     // staged kernel (dsc_tet_staged.cuh)
-    const TmapBlob *stg_maps;        // [16][16] tensor maps of the volume in device memory: box = (u+1) x 16 bytes by (r+1) rows by 1 slice
-    int stg_slot_bytes;              // shared-memory slot of one warp (multiple of 1024)
+    const TmapBlob *stg_maps;        // [16][16][16] tensor maps of the volume in device memory: box = (u+1) x 16 bytes by (r+1) rows by (s+1) slices
+    int stg_slot_bytes;              // voxel box of one shared-memory slot (multiple of 1024)
+    int stg_slots;                   // slots of the ring
     unsigned *stg_counter;           // tile fetch counter, zero at launch
-    long long *stg_partials;         // [gridDim.x][3*kMaxPhase] fixed-point rows: total, sumsq, volume
+    unsigned *stg_exact_count;       // tets left to the exact path (stg_counter + 1), zero at launch
+    unsigned *stg_exact_list;        // ... and their indices, capacity tet_end - tet_begin
+    long long *stg_partials;         // [gridDim.x][3*kMaxPhase] fixed-point rows of the staged kernel: total, sumsq, volume
+    long long *stg_partials2;        // ... and of tet_exact_list_kernel
     double stg_scale[3];             // fixed-point scales (powers of two) of total, sumsq, volume
 };
 

@@ -24,16 +24,25 @@
 // FP32 filter (what feeds an integer decision must equal the reference's FP64 result): with O the integer
 // origin of the tet, q = (P0 - O - 1/2) + lattice terms evaluated in float, t = q + 1.5*2^23 holds round(q) = floor(sample - O)
 // in its mantissa unless q is within delta of a half-integer.  delta bounds |q_float - q_reference| (derivation at stg_delta);
-// a tet with any |q - round(q)| >= 1/2 - delta is recomputed with the reference's exact FP64 sequence (coop_exact), as are
+// a tet with any |q - round(q)| >= 1/2 - delta is recomputed with the reference's exact FP64 sequence (tet_exact_list_kernel), as are
 // tets of level n >= 5, tets reaching outside the volume, and tets whose box does not fit a slot.
 #pragma once
 #include "dsc_kernels.cuh"
 
 namespace dsc {
 
-constexpr int kStgWarps = 8;
-constexpr int kStgMaxUnits = 16; // tensor-map family: box rows of 1..16 units of 16 bytes, 1..16 rows per slice
+#ifndef STG_PROD
+#define STG_PROD 8
+#endif
+#ifndef STG_CONS
+#define STG_CONS 8
+#endif
+constexpr int kStgProd = STG_PROD, kStgCons = STG_CONS; // producer / consumer warps of a CTA
+constexpr int kStgMaxSlots = 16;
+constexpr int kStgChunk = 4; // tiles a producer claims with one atomic
+constexpr int kStgMaxUnits = 16; // tensor-map family: boxes of 1..16 units of 16 bytes by 1..16 rows by 1..16 slices
 constexpr int kStgMaxRows = 16;
+constexpr int kStgMaxSlices = 16;
 
 // the six centroid offsets (ox, oy, oz) of the reference's cube split, in table order (DEMO/image3d.cpp:274-291)
 __host__ __device__ constexpr int stg_off(int t, int c)
@@ -98,26 +107,28 @@ struct StgLane {
     float thr;                                      // 1/2 - delta
 };
 
+// per-tet sums of the sampled voxels: four interleaved partial sums (the adds of consecutive samples do not wait for each other;
+// float voxel sums of this length are exact in double, integer sums are exact anyway, so the split changes nothing)
 template <typename VoxT, bool WANT_SQ, bool F32S> struct StgAcc {
-    double s = 0, sq = 0;
-    unsigned isum = 0;
+    double s[4] = {0, 0, 0, 0}, sq[2] = {0, 0};
+    unsigned isum[2] = {0, 0};
     unsigned long long isq = 0;
     float emax = 0.f;
-    DSC_D void add(VoxT val)
+    DSC_D void add(VoxT val, int c)
     {
         if constexpr (VoxTraits<VoxT>::integral) {
             const unsigned q = (unsigned)val;
-            isum += q;
+            isum[c & 1] += q;
             if (WANT_SQ) isq += (unsigned long long)q * q;
         } else {
             double I;
             if constexpr (F32S) I = widen_scaled((float)val);
             else if constexpr (sizeof(VoxT) == 4) I = widen_exact((float)val);
             else I = (double)val;
-            s += I;
+            s[c & 3] += I;
             if (WANT_SQ) {
-                const double Iu = F32S ? I * 0x1p+896 : I; // exact
-                sq = fma(Iu, Iu, sq);                      // second moment: tolerance quantity, fused on purpose
+                const double Iu = F32S ? I * 0x1p+896 : I;   // exact
+                sq[c & 1] = fma(Iu, Iu, sq[c & 1]);          // second moment: tolerance quantity, fused on purpose
             }
         }
     }
@@ -126,11 +137,12 @@ template <typename VoxT, bool WANT_SQ, bool F32S> struct StgAcc {
     {
         if constexpr (VoxTraits<VoxT>::integral) {
             const double dn = VoxTraits<VoxT>::denom();
-            sum = (double)isum / dn;
+            sum = (double)(isum[0] + isum[1]) / dn;
             sumsq = WANT_SQ ? (double)isq / (dn * dn) : 0.0;
         } else {
-            sum = F32S ? s * 0x1p+896 : s;
-            sumsq = sq;
+            const double t = (s[0] + s[1]) + (s[2] + s[3]);
+            sum = F32S ? t * 0x1p+896 : t;
+            sumsq = sq[0] + sq[1];
         }
     }
 };
@@ -149,7 +161,8 @@ template <int NB, typename VoxT, bool WANT_SQ, bool F32S> DSC_D void stg_block(c
 {
     const float MAGIC = 12582912.0f; // 1.5 * 2^23
     const f32x2 M2 = pk2(MAGIC, MAGIC);
-    float em = 0.f;
+    float em = 0.f, em1 = 0.f;
+    int cnt = 0; // samples so far (a constant at every point of the unrolled stream)
 #pragma unroll
     for (int j = 0; j < NB; j++) {
         const f32x2 cjxy = j ? fma2(pk2((float)j, (float)j), r.d1xy, r.q0xy) : r.q0xy;
@@ -197,66 +210,24 @@ template <int NB, typename VoxT, bool WANT_SQ, bool F32S> DSC_D void stg_block(c
                         const f32x2 eb2 = sub2(qb, sub2(tb, M2));
                         float tbx, tby, ebx, eby;
                         upk2(tb, tbx, tby); upk2(eb2, ebx, eby);
-                        em = fmax3abs(em, ebx, eby);
-                        em = fmax3abs(em, ez0, ez1);
+                        em1 = fmax3abs(em1, ebx, eby);
+                        em1 = fmax3abs(em1, ez0, ez1);
                         const bool sel_b = NB > 1 && stg_need(s, t + 1) == NB;
                         const unsigned addr_b = sel_b ? stg_addr<VoxT, true>(r, tbx, tby, tz1, full) : stg_addr<VoxT, false>(r, tbx, tby, tz1, full);
                         const VoxT vb = lds_vox<VoxT>(addr_b);
-                        acc.add(va);
-                        acc.add(vb);
+                        acc.add(va, cnt);
+                        acc.add(vb, cnt + 1);
+                        cnt += 2;
                     } else {
-                        em = fmax3abs(em, ez0, ez0);
-                        acc.add(va);
+                        em1 = fmax3abs(em1, ez0, ez0);
+                        acc.add(va, cnt);
+                        cnt += 1;
                     }
                 }
             }
         }
     }
-    acc.emax = em;
-}
-
-// The reference's exact sequence for one tet, 32 lanes over its rows (get_coord, DEMO/tet_dis_coord.hpp:27; truncation
-// image3d.cpp:366; bounds image3d.cpp:480-491).  Every lane gets the tet's sums.
-template <typename VoxT, bool WANT_SQ, bool F32S> DSC_D void coop_exact(const TetArgs &a, const VoxT *__restrict__ vol, uint4 nd, int L, int lane, double &sum, double &sumsq)
-{
-    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
-    const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
-    const V3 p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
-    const int n3 = (L + 1) * (L + 1) * (L + 1);
-    const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
-    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
-    StgAcc<VoxT, WANT_SQ, F32S> acc;
-    for (int i = lane; i < n3; i += 32) {
-        const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
-        const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
-        const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
-        const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
-        const bool inb = (unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z;
-        if (inb) acc.add(__ldg(vol + ((size_t)iz * Y + iy) * X + ix));
-    }
-    double s, q;
-    if constexpr (VoxTraits<VoxT>::integral) {
-        unsigned is = __reduce_add_sync(0xffffffffu, acc.isum); // <= 729 * 65535
-        unsigned long long iq = acc.isq;
-        if (WANT_SQ) {
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) iq += __shfl_xor_sync(0xffffffffu, iq, m);
-        }
-        const double dn = VoxTraits<VoxT>::denom();
-        s = (double)is / dn;
-        q = WANT_SQ ? (double)iq / (dn * dn) : 0.0;
-    } else {
-        s = acc.s;
-        q = acc.sq;
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            s += shfl_xor_d(s, m);
-            if (WANT_SQ) q += shfl_xor_d(q, m);
-        }
-        if (F32S) s = s * 0x1p+896;
-    }
-    sum = s;
-    sumsq = q;
+    acc.emax = fmaxf(em, em1);
 }
 
 // |q_float - q_reference| per coordinate, for a tet whose origin-relative coordinates are below R and whose edge vectors
@@ -269,161 +240,326 @@ template <typename VoxT, bool WANT_SQ, bool F32S> DSC_D void coop_exact(const Te
 //   sums of numbers below the volume size) and the FP64 set-up of Q0, D_k add less than 1e-9.
 DSC_D float stg_threshold(double R, double diam, int n)
 {
-    const double delta = 5.9604644775390625e-08 * (6.0 * R + 6.0 + 10.0 * diam) + (n == 3 ? 1.01e-6 * diam : 0.0) + 1.0e-9;
-    return (float)(0.5 - delta) * 0.99999988079071044921875f; // rounded towards the safe side
+    // evaluated in float, every step rounded towards a larger delta
+    const float Rf = (float)R * 1.000001f, df = (float)diam * 1.000001f;
+    const float delta = (5.9604644775390625e-08f * (6.0f * Rf + 6.0f + 14.0f * df) + (n == 3 ? 1.01e-6f * df : 0.0f) + 1.0e-9f) * 1.00001f;
+    return (0.5f - delta) * 0.99999988079071044921875f;
 }
 
+DSC_D V3 load_pos_now(const double4 *pos4, unsigned node)
+{
+    const double4 *ptr = pos4 + node;
+    V3 r;
+    double pad;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%4];\n\tld.global.nc.v2.f64 {%2, %3}, [%4 + 16];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(pad) : "l"(ptr));
+    return r;
+}
+
+// ---- shared-memory pipeline: mbarrier helpers ----
+DSC_D void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+DSC_D void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+DSC_D void mbar_arrive_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+DSC_D void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+// Tets that leave the staged stream (level n >= 5, reaching outside the volume, a box that does not fit a slot, a sample inside the
+// guard band) are appended to a list; tet_exact_list_kernel runs the reference's exact sequence on them afterwards.
+DSC_D void exact_append(const TetArgs &a, bool flag, unsigned t, int lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (!m) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(a.stg_exact_count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (flag) a.stg_exact_list[base + __popc(m & ((1u << lane) - 1u))] = t;
+}
+
+// record of one tet in a slot: words [field][lane] (conflict-free), written by the producer lane, read by the consumer lane
+enum { kRecQ0 = 0, kRecD1 = 3, kRecD2 = 6, kRecD3 = 9, kRecEp = 12, kRecThr = 15, kRecBase = 16, kRecMeta = 17, kRecW = 18, kRecV = 20, kRecWords = 22 };
+constexpr int kStgRecBytes = kRecWords * 32 * 4;
+
+// The kernel.  One CTA per SM: kStgProd producer warps and kStgCons consumer warps around a ring of shared-memory slots.
+//   producer  lane <-> tet of a 32-tet tile (tiles fetched with one atomicAdd): label, ids, FP64 positions -> exact volume and level
+//             (as the reference), voxel box of the tile; takes the next slot of the ring, writes the per-tet records of the FP32
+//             lattice form, and has the TMA unit bring the box into the slot (one cp.async.bulk.tensor.3d, tensor map picked from a
+//             family indexed by the box extents); the slot's "full" mbarrier completes when the bytes have landed.
+//   consumer  takes the next filled slot, lane <-> tet again: the unrolled level-NB sample stream with every gather an LDS, the
+//             guard-band test, per-label fixed-point sums in registers; releases the slot through its "empty" mbarrier.
+// The phases of different tiles overlap: the dependent global loads of phase A, the TMA transfers and the sample streams of up to
+// `stg_slots` tiles are in flight on one SM.
 template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S>
-__global__ void __launch_bounds__(kStgWarps * 32, 1) tet_staged_kernel(const __grid_constant__ TetArgs a)
+__global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kernel(const __grid_constant__ TetArgs a)
 {
     extern __shared__ __align__(1024) unsigned char s_dyn[];
-    __shared__ __align__(8) unsigned long long s_bar[kStgWarps];
-    __shared__ long long s_red[kStgWarps][3 * kMaxPhase];
+    __shared__ __align__(8) unsigned long long s_full[kStgMaxSlots]; // completes when the records are written and the box has landed
+    __shared__ int4 s_hdr[kStgMaxSlots];         // tile base, NB (0: end of a producer's stream), row pitch, slice pitch
+    __shared__ unsigned s_fillseq[kStgMaxSlots];  // sequence number + 1 of the item a producer has put into the slot
+    __shared__ unsigned s_released[kStgMaxSlots]; // how many items of the slot the consumers are done with
+    __shared__ long long s_red[kStgCons][3 * kMaxPhase];
     __shared__ unsigned s_zero[4];
+    __shared__ unsigned s_seq[2]; // next slot sequence number of the producers / of the consumers
     constexpr int ESZ = (int)sizeof(VoxT);
     constexpr int AL = 16 / ESZ; // elements per 16-byte unit
-    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
     const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned slot_a = smem_u32(s_dyn) + (unsigned)warp * (unsigned)a.stg_slot_bytes;
-    const unsigned bar_a = smem_u32(&s_bar[warp]);
+    const int S = a.stg_slots;
+    const unsigned box0 = smem_u32(s_dyn);
+    const unsigned rec0 = box0 + (unsigned)S * (unsigned)a.stg_slot_bytes;
     if (threadIdx.x < 4) s_zero[threadIdx.x] = 0u;
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x < 2) s_seq[threadIdx.x] = 0u;
+    if (threadIdx.x < S) {
+        mbar_init(smem_u32(&s_full[threadIdx.x]), 1);
+        s_fillseq[threadIdx.x] = 0u;
+        s_released[threadIdx.x] = 0u;
     }
+    if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    unsigned phase = 0;
     const unsigned n_work = a.tet_end - a.tet_begin;
     const unsigned n_tiles = (n_work + 31) / 32;
 
-    long long acc_tot[kMaxPhase], acc_sq[kMaxPhase], acc_vol[kMaxPhase];
-#pragma unroll
-    for (int k = 0; k < kMaxPhase; k++) acc_tot[k] = acc_sq[k] = acc_vol[k] = 0;
-    unsigned long long nsamp = 0;
-
-    unsigned tile = 0;
-    if (lane == 0) tile = atomicAdd(a.stg_counter, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    while (tile < n_tiles) {
-        unsigned next = 0;
-        if (lane == 0) next = atomicAdd(a.stg_counter, 1u);
-        const unsigned base_t = a.tet_begin + tile * 32;
-        const unsigned t = base_t + lane;
-        // ---------------- phase A: lane <-> tet ----------------
-        bool active = false, cand = false;
-        int label = 0, L = 0, n3 = 0;
-        uint4 nd = make_uint4(0, 0, 0, 0);
+    if (warp < kStgProd) {
+        // ======================================= producer =======================================
+        unsigned long long nsamp = 0;
+        // Next item of the ring and its slot, once the consumers are done with the slot's previous item.  Items are handed out in
+        // sequence, but warps do not finish them in sequence, so a warp can be several rounds of the ring behind: the slot's history is
+        // kept as counts (an mbarrier phase bit alone cannot tell round u from round u + 2).
+        auto take_slot = [&](unsigned &slot, unsigned &q) {
+            q = 0;
+            if (lane == 0) q = atomicAdd(&s_seq[0], 1u);
+            q = __shfl_sync(0xffffffffu, q, 0);
+            slot = q % (unsigned)S;
+            const unsigned round = q / (unsigned)S;
+            while (*reinterpret_cast<volatile unsigned *>(&s_released[slot]) != round) __nanosleep(40);
+            __threadfence_block();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the consumers' reads of the slot precede the TMA writes into it
+        };
+        // Three tiles are in flight per producer: the index of tile k+2 (atomicAdd), label and node ids of tile k+1, the positions of
+        // tile k+1 (asked for at the top of iteration k, when its ids have arrived) -- so the dependent round trips of a tile
+        // (index -> ids -> positions) overlap with the arithmetic of the tiles before it.
+        // Tiles are claimed kStgChunk at a time: ptxas emits every returning atomic add in its warp-aggregated form, whose shuffle waits
+        // for the result on the spot (one L2 round trip), so the claim is amortised over a chunk instead of being prefetched.
+        // (inline PTX for the position loads: the compiler sinks plain loads down to their first use, an iteration later)
+        unsigned chunk_base = 0, chunk_pos = kStgChunk;
+        auto fetch_tile = [&]() {
+            if (chunk_pos == kStgChunk) {
+                unsigned x = 0;
+                if (lane == 0) x = atomicAdd(a.stg_counter, (unsigned)kStgChunk);
+                chunk_base = __shfl_sync(0xffffffffu, x, 0);
+                chunk_pos = 0;
+            }
+            return chunk_base + chunk_pos++;
+        };
+        auto load_ids = [&](unsigned tl, int &lab, uint4 &ids) {
+            lab = 0; ids = make_uint4(0, 0, 0, 0);
+            const unsigned tt = a.tet_begin + tl * 32 + lane;
+            if (tl < n_tiles && tt < a.tet_end) { lab = __ldg(a.mesh.tet_label + tt); ids = __ldg(a.mesh.tet_nodes + tt); }
+        };
+        unsigned tile = fetch_tile();
+        unsigned tile1 = fetch_tile();
+        int label = 0, label1 = 0;
+        uint4 nd, nd1;
+        load_ids(tile, label, nd);
+        load_ids(tile1, label1, nd1);
         V3 p0 = {0, 0, 0}, p1 = p0, p2 = p0, p3 = p0;
-        double v = 0;
-        int blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0}, org[3] = {0, 0, 0};
-        double rmax = 0, diam = 0;
-        if (t < a.tet_end) {
-            label = __ldg(a.mesh.tet_label + t);
-            nd = __ldg(a.mesh.tet_nodes + t);
-            active = a.include_bound || label != 0;
-        }
-        if (active) {
+        if (a.include_bound || label != 0) {
             p0 = load_pos(a.mesh.pos4, nd.x); p1 = load_pos(a.mesh.pos4, nd.y);
             p2 = load_pos(a.mesh.pos4, nd.z); p3 = load_pos(a.mesh.pos4, nd.w);
-            v = tet_volume(p0, p1, p2, p3);
-            L = tet_level(v);
-            n3 = (L + 1) * (L + 1) * (L + 1);
-            const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
-            const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
-            const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
-            // Inside the volume: no sample can leave [0, dim), so truncation equals floor and no bounds test is needed -- with a
-            // margin that is plain; for tets with nodes on the faces of the volume see the argument at tet_integrate_w2_kernel
-            // (minimum weight 1/(4n) - 5e-7 of every table row, checked when the table is built).
-            auto axis_in = [](double lo, double hi, int dim) { return lo >= -1.0e-7 && hi <= (double)dim + 1.0e-7 && hi - lo >= 1.0e-4 * (double)dim; };
-            const bool interior = (lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5) ||
-                                  (axis_in(lox, hix, X) && axis_in(loy, hiy, Y) && axis_in(loz, hiz, Z));
-            const double ox = floor(lox), oy = floor(loy), oz = floor(loz);
-            rmax = fmax(fmax(hix - ox, hiy - oy), hiz - oz);
-            diam = fmax(fmax(hix - lox, hiy - loy), hiz - loz);
-            cand = interior && L < 4 && rmax < 60.0;
-            if (cand) {
-                // voxels the samples can touch: every weight is at least 1/(4n) - 5e-7, so a sample keeps (hi-lo)/(4n) away from the
-                // faces of the tet's bounding box; 0.9 of that and 1e-3 absolute cover eps * coordinate and the filter's own error
-                const double f = 0.9 / (double)(4 * (L + 1));
-                org[0] = (int)ox; org[1] = (int)oy; org[2] = (int)oz;
-                blo[0] = max((int)floor(lox + f * (hix - lox) - 1.0e-3), 0); bhi[0] = min((int)floor(hix - f * (hix - lox) + 1.0e-3), X - 1);
-                blo[1] = max((int)floor(loy + f * (hiy - loy) - 1.0e-3), 0); bhi[1] = min((int)floor(hiy - f * (hiy - loy) + 1.0e-3), Y - 1);
-                blo[2] = max((int)floor(loz + f * (hiz - loz) - 1.0e-3), 0); bhi[2] = min((int)floor(hiz - f * (hiz - loz) + 1.0e-3), Z - 1);
-            }
-            nsamp += (unsigned)n3;
         }
-        double t_sum = 0, t_sq = 0; // this lane's tet: true sum of the sampled intensities and of their squares
-        unsigned pending = __ballot_sync(0xffffffffu, cand);
-        unsigned coop = __ballot_sync(0xffffffffu, active && !cand);
-        // ---------------- staged block path: candidate sets whose box fits the slot ----------------
-        while (pending) {
-            unsigned set = pending;
-            int x0 = 0, y0 = 0, z0 = 0, exu = 0, ey = 0, ez = 0;
-            unsigned zstride = 0;
-            bool fits = false;
-            for (;;) {
+        while (tile < n_tiles) {
+            const unsigned tile2 = fetch_tile();
+            // positions of the next tile (its ids are here by now)
+            V3 n0 = {0, 0, 0}, n1 = n0, n2 = n0, n3 = n0;
+            if (a.include_bound || label1 != 0) {
+                n0 = load_pos_now(a.mesh.pos4, nd1.x); n1 = load_pos_now(a.mesh.pos4, nd1.y);
+                n2 = load_pos_now(a.mesh.pos4, nd1.z); n3 = load_pos_now(a.mesh.pos4, nd1.w);
+            }
+            const unsigned base_t = a.tet_begin + tile * 32;
+            const unsigned t = base_t + lane;
+            const bool active = t < a.tet_end && (a.include_bound || label != 0);
+            bool cand = false;
+            int L = 0;
+            double v = 0;
+            int blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0}, org[3] = {0, 0, 0};
+            double rmax = 0, diam = 0;
+            if (active) {
+                v = tet_volume(p0, p1, p2, p3);
+                L = tet_level(v);
+                const double lox = fmin(fmin(p0.x, p1.x), fmin(p2.x, p3.x)), hix = fmax(fmax(p0.x, p1.x), fmax(p2.x, p3.x));
+                const double loy = fmin(fmin(p0.y, p1.y), fmin(p2.y, p3.y)), hiy = fmax(fmax(p0.y, p1.y), fmax(p2.y, p3.y));
+                const double loz = fmin(fmin(p0.z, p1.z), fmin(p2.z, p3.z)), hiz = fmax(fmax(p0.z, p1.z), fmax(p2.z, p3.z));
+                // Inside the volume: no sample can leave [0, dim), so truncation equals floor and no bounds test is needed -- with a
+                // margin that is plain; for tets with nodes on the faces of the volume see the argument at tet_integrate_w2_kernel
+                // (minimum weight 1/(4n) - 5e-7 of every table row, checked when the table is built).
+                auto axis_in = [](double lo, double hi, int dim) { return lo >= -1.0e-7 && hi <= (double)dim + 1.0e-7 && hi - lo >= 1.0e-4 * (double)dim; };
+                const bool interior = (lox >= 1.5 && loy >= 1.5 && loz >= 1.5 && hix < (double)X - 1.5 && hiy < (double)Y - 1.5 && hiz < (double)Z - 1.5) ||
+                                      (axis_in(lox, hix, X) && axis_in(loy, hiy, Y) && axis_in(loz, hiz, Z));
+                const double ox = floor(lox), oy = floor(loy), oz = floor(loz);
+                rmax = fmax(fmax(hix - ox, hiy - oy), hiz - oz);
+                diam = fmax(fmax(hix - lox, hiy - loy), hiz - loz);
+                cand = interior && L < 4 && rmax < 60.0;
+                if (cand) {
+                    // voxels the samples can touch: every weight is at least 1/(4n) - 5e-7, so a sample keeps (hi-lo)/(4n) away from the
+                    // faces of the tet's bounding box; 0.9 of that and 1e-3 absolute cover eps * coordinate and the filter's own error
+                    const double f = 0.9 / (double)(4 * (L + 1));
+                    org[0] = (int)ox; org[1] = (int)oy; org[2] = (int)oz;
+                    blo[0] = max((int)floor(lox + f * (hix - lox) - 1.0e-3), 0); bhi[0] = min((int)floor(hix - f * (hix - lox) + 1.0e-3), X - 1);
+                    blo[1] = max((int)floor(loy + f * (hiy - loy) - 1.0e-3), 0); bhi[1] = min((int)floor(hiy - f * (hiy - loy) + 1.0e-3), Y - 1);
+                    blo[2] = max((int)floor(loz + f * (hiz - loz) - 1.0e-3), 0); bhi[2] = min((int)floor(hiz - f * (hiz - loz) + 1.0e-3), Z - 1);
+                }
+                nsamp += (unsigned)((L + 1) * (L + 1) * (L + 1));
+            } else if (PER_TET && t < a.tet_end) {
+                if (a.tet_total) a.tet_total[t] = -1.0;
+                if (a.tet_vol) a.tet_vol[t] = -1.0;
+                if (a.tet_mean) a.tet_mean[t] = -1.0;
+            }
+            unsigned pending = __ballot_sync(0xffffffffu, cand);
+            bool exact = active && !cand;
+            while (pending) {
+                unsigned set = pending;
+                int x0 = 0, y0 = 0, z0 = 0, exu = 0, ey = 0, ez = 0;
+                bool fits = false;
+                for (;;) {
+                    const bool in = (set >> lane) & 1u;
+                    x0 = __reduce_min_sync(0xffffffffu, in ? blo[0] : INT_MAX);
+                    y0 = __reduce_min_sync(0xffffffffu, in ? blo[1] : INT_MAX);
+                    z0 = __reduce_min_sync(0xffffffffu, in ? blo[2] : INT_MAX);
+                    const int x1 = __reduce_max_sync(0xffffffffu, in ? bhi[0] : INT_MIN);
+                    const int y1 = __reduce_max_sync(0xffffffffu, in ? bhi[1] : INT_MIN);
+                    const int z1 = __reduce_max_sync(0xffffffffu, in ? bhi[2] : INT_MIN);
+                    x0 &= ~(AL - 1); // a TMA box starts on a 16-byte boundary
+                    exu = (x1 - x0 + AL) / AL;
+                    ey = y1 - y0 + 1;
+                    ez = z1 - z0 + 1;
+                    fits = exu <= kStgMaxUnits && ey <= kStgMaxRows && ez <= kStgMaxSlices && (unsigned)(exu * 16 * ey * ez) <= (unsigned)a.stg_slot_bytes;
+                    const int cnt = __popc(set);
+                    if (fits || cnt == 1) break;
+                    set &= (1u << __fns(set, 0, cnt / 2 + 1)) - 1u; // keep the lower half of the set's lanes
+                }
+                pending &= ~set;
                 const bool in = (set >> lane) & 1u;
-                x0 = __reduce_min_sync(0xffffffffu, in ? blo[0] : INT_MAX);
-                y0 = __reduce_min_sync(0xffffffffu, in ? blo[1] : INT_MAX);
-                z0 = __reduce_min_sync(0xffffffffu, in ? blo[2] : INT_MAX);
-                const int x1 = __reduce_max_sync(0xffffffffu, in ? bhi[0] : INT_MIN);
-                const int y1 = __reduce_max_sync(0xffffffffu, in ? bhi[1] : INT_MIN);
-                const int z1 = __reduce_max_sync(0xffffffffu, in ? bhi[2] : INT_MIN);
-                x0 &= ~(AL - 1); // a TMA box starts on a 16-byte boundary (scripts/tma_prefetch_probe.cu)
-                exu = (x1 - x0 + AL) / AL;
-                ey = y1 - y0 + 1;
-                ez = z1 - z0 + 1;
-                zstride = ((unsigned)(exu * 16 * ey) + 127u) & ~127u; // a slice starts on a 128-byte boundary of the slot
-                fits = exu <= kStgMaxUnits && ey <= kStgMaxRows && ez <= 32 && (unsigned)ez * zstride <= (unsigned)a.stg_slot_bytes;
-                const int cnt = __popc(set);
-                if (fits || cnt == 1) break;
-                set &= (1u << __fns(set, 0, cnt / 2 + 1)) - 1u; // keep the lower half of the set's lanes
+                if (!fits) { exact = exact || in; continue; }
+                // level of the instruction stream: the one that costs least (stream + the tets it leaves to the exact path)
+                int NB;
+                {
+                    const unsigned m1 = __ballot_sync(0xffffffffu, in && L == 0), m2 = __ballot_sync(0xffffffffu, in && L == 1);
+                    const unsigned m3 = __ballot_sync(0xffffffffu, in && L == 2), m4 = __ballot_sync(0xffffffffu, in && L == 3);
+                    const int c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3), c4 = __popc(m4);
+                    const int k1 = 180, k4 = 260; // instruction estimates: exact path per tet (levels 1-3, level 4), streams below
+                    const int cost1 = 40 + k1 * (c2 + c3) + k4 * c4, cost2 = 150 + k1 * c3 + k4 * c4, cost3 = 450 + k1 * c1 + k4 * c4, cost4 = 1000 + k1 * (c1 + c2);
+                    NB = 1;
+                    int best = c1 ? cost1 : INT_MAX;
+                    if ((c2 || c1) && cost2 < best) { best = cost2; NB = 2; }
+                    if ((c3 || c2) && cost3 < best) { best = cost3; NB = 3; }
+                    if ((c4 || c3) && cost4 < best) { best = cost4; NB = 4; }
+                }
+                const bool ride = in && (L + 1 == NB || L + 2 == NB);
+                exact = exact || (in && !ride);
+                if (!__any_sync(0xffffffffu, ride)) continue;
+                unsigned slot, q;
+                take_slot(slot, q);
+                const unsigned slot_a = box0 + slot * (unsigned)a.stg_slot_bytes;
+                const unsigned bx = (unsigned)(exu * 16), bxy = bx * (unsigned)ey;
+                {
+                    float *rec = reinterpret_cast<float *>(s_dyn + (size_t)S * a.stg_slot_bytes + (size_t)slot * kStgRecBytes) + lane;
+                    const int n = L + 1;
+                    const double inv = n == 1 ? 1.0 : (n == 2 ? 0.5 : (n == 3 ? 1.0 / 3.0 : 0.25)); // = 1.0 / n, correctly rounded
+                    rec[32 * (kRecQ0 + 0)] = ride ? (float)((p0.x - (double)org[0]) - 0.5) : 0.f;
+                    rec[32 * (kRecQ0 + 1)] = ride ? (float)((p0.y - (double)org[1]) - 0.5) : 0.f;
+                    rec[32 * (kRecQ0 + 2)] = ride ? (float)((p0.z - (double)org[2]) - 0.5) : 0.f;
+                    rec[32 * (kRecD1 + 0)] = ride ? (float)((p1.x - p0.x) * inv) : 0.f; rec[32 * (kRecD1 + 1)] = ride ? (float)((p1.y - p0.y) * inv) : 0.f;
+                    rec[32 * (kRecD1 + 2)] = ride ? (float)((p1.z - p0.z) * inv) : 0.f;
+                    rec[32 * (kRecD2 + 0)] = ride ? (float)((p2.x - p0.x) * inv) : 0.f; rec[32 * (kRecD2 + 1)] = ride ? (float)((p2.y - p0.y) * inv) : 0.f;
+                    rec[32 * (kRecD2 + 2)] = ride ? (float)((p2.z - p0.z) * inv) : 0.f;
+                    rec[32 * (kRecD3 + 0)] = ride ? (float)((p3.x - p0.x) * inv) : 0.f; rec[32 * (kRecD3 + 1)] = ride ? (float)((p3.y - p0.y) * inv) : 0.f;
+                    rec[32 * (kRecD3 + 2)] = ride ? (float)((p3.z - p0.z) * inv) : 0.f;
+                    const bool l3 = ride && n == 3;
+                    rec[32 * (kRecEp + 0)] = l3 ? (float)(1.0e-6 * p0.x) : 0.f;
+                    rec[32 * (kRecEp + 1)] = l3 ? (float)(1.0e-6 * p0.y) : 0.f;
+                    rec[32 * (kRecEp + 2)] = l3 ? (float)(1.0e-6 * p0.z) : 0.f;
+                    rec[32 * kRecThr] = ride ? stg_threshold(rmax + 1.0, diam, n) : 1.0e30f;
+                    // address of voxel O + m: base + (bits(tx) << SH) + bits(ty) bx + bits(tz) bxy, the bits being 0x4B400000 + m
+                    const unsigned fold = 0x4B400000u * ((unsigned)ESZ + bx + bxy);
+                    const unsigned rel = ride ? (unsigned)((org[0] - x0) * ESZ) + (unsigned)(org[1] - y0) * bx + (unsigned)(org[2] - z0) * bxy : 0u;
+                    unsigned *recu = reinterpret_cast<unsigned *>(rec);
+                    recu[32 * kRecBase] = slot_a + rel - fold;
+                    recu[32 * kRecMeta] = (ride ? 1u : 0u) | ((ride && L + 1 == NB) ? 2u : 0u) | ((unsigned)(label & 0xff) << 8) | ((unsigned)L << 16);
+                    const double w = v * (n == 1 ? 1.0 : (n == 2 ? 0.125 : (n == 3 ? 1.0 / 27.0 : 0.015625))); // sums-only weight v / n^3 (tolerance quantity)
+                    recu[32 * kRecW] = (unsigned)__double2loint(w); recu[32 * (kRecW + 1)] = (unsigned)__double2hiint(w);
+                    recu[32 * kRecV] = (unsigned)__double2loint(v); recu[32 * (kRecV + 1)] = (unsigned)__double2hiint(v);
+                    if (lane == 0) s_hdr[slot] = make_int4((int)base_t, NB, (int)bx, (int)bxy);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    const unsigned bar = smem_u32(&s_full[slot]);
+                    __threadfence_block();
+                    *reinterpret_cast<volatile unsigned *>(&s_fillseq[slot]) = q + 1u;
+                    mbar_arrive_tx(bar, bxy * (unsigned)ez);
+                    const TmapBlob *map = a.stg_maps + (((exu - 1) * kStgMaxRows + (ey - 1)) * kStgMaxSlices + (ez - 1));
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(slot_a), "l"(map),
+                                 "r"(x0), "r"(y0), "r"(z0), "r"(bar)
+                                 : "memory");
+                }
             }
-            pending &= ~set;
-            if (!fits) { coop |= set; continue; }
-            const bool in = (set >> lane) & 1u;
-            // level of the instruction stream: the one that costs least (block + the tets it leaves to the exact path)
-            int NB;
-            {
-                const unsigned m1 = __ballot_sync(0xffffffffu, in && L == 0), m2 = __ballot_sync(0xffffffffu, in && L == 1);
-                const unsigned m3 = __ballot_sync(0xffffffffu, in && L == 2), m4 = __ballot_sync(0xffffffffu, in && L == 3);
-                const int c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3), c4 = __popc(m4);
-                const int k1 = 180, k4 = 260; // instruction estimates: exact path per tet (levels 1-3, level 4), blocks below
-                const int cost1 = 40 + k1 * (c2 + c3) + k4 * c4, cost2 = 150 + k1 * c3 + k4 * c4, cost3 = 450 + k1 * c1 + k4 * c4, cost4 = 1000 + k1 * (c1 + c2);
-                NB = 1;
-                int best = c1 ? cost1 : INT_MAX;
-                if ((c2 || c1) && cost2 < best) { best = cost2; NB = 2; }
-                if ((c3 || c2) && cost3 < best) { best = cost3; NB = 3; }
-                if ((c4 || c3) && cost4 < best) { best = cost4; NB = 4; }
+            exact_append(a, exact, t, lane);
+            // shift the pipeline: ids of the tile after next
+            tile = tile1; label = label1; nd = nd1;
+            p0 = n0; p1 = n1; p2 = n2; p3 = n3;
+            tile1 = tile2;
+            load_ids(tile1, label1, nd1);
+        }
+        // end of this producer's stream: one END item per consumer it is responsible for
+        for (int e = warp; e < kStgCons; e += kStgProd) {
+            unsigned slot, q;
+            take_slot(slot, q);
+            if (lane == 0) {
+                s_hdr[slot] = make_int4(0, 0, 0, 0);
+                __threadfence_block();
+                *reinterpret_cast<volatile unsigned *>(&s_fillseq[slot]) = q + 1u;
+                mbar_arrive(smem_u32(&s_full[slot]));
             }
-            const bool ride = in && (L + 1 == NB || L + 2 == NB);
-            coop |= __ballot_sync(0xffffffffu, in && !ride);
-            if (!__any_sync(0xffffffffu, ride)) continue;
-            // the box -> this warp's slot
-            __syncwarp();
-            const unsigned bytes = (unsigned)(exu * 16 * ey) * (unsigned)ez;
-            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-            __syncwarp();
-            if (lane < ez) {
-                const TmapBlob *map = a.stg_maps + ((exu - 1) * kStgMaxRows + (ey - 1));
-                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(slot_a + (unsigned)lane * zstride),
-                             "l"(map), "r"(x0), "r"(y0), "r"(z0 + lane), "r"(bar_a)
-                             : "memory");
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
+        if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+    } else {
+        // ======================================= consumer =======================================
+        long long acc_tot[kMaxPhase], acc_sq[kMaxPhase], acc_vol[kMaxPhase];
+#pragma unroll
+        for (int k = 0; k < kMaxPhase; k++) acc_tot[k] = acc_sq[k] = acc_vol[k] = 0;
+        for (;;) {
+            unsigned q = 0;
+            if (lane == 0) q = atomicAdd(&s_seq[1], 1u);
+            q = __shfl_sync(0xffffffffu, q, 0);
+            const unsigned slot = q % (unsigned)S, round = q / (unsigned)S;
+            // first the producer of THIS item must have started filling the slot (then the mbarrier is in the phase of this round) ...
+            while (*reinterpret_cast<volatile unsigned *>(&s_fillseq[slot]) != q + 1u) __nanosleep(40);
+            __threadfence_block(); // the records and the header were written before the sequence number
+            // ... then its phase completes when the voxels have landed: waited for after the per-lane set-up below
+            const int4 hdr = s_hdr[slot];
+            const int NB = hdr.y;
+            if (NB == 0) { // a producer has finished
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile unsigned *>(&s_released[slot]) = round + 1u;
+                break;
             }
-            // per-lane record while the box is on its way
+            const float *rec = reinterpret_cast<const float *>(s_dyn + (size_t)S * a.stg_slot_bytes + (size_t)slot * kStgRecBytes) + lane;
+            const unsigned *recu = reinterpret_cast<const unsigned *>(rec);
             StgLane r;
-            r.bx = (unsigned)(exu * 16);
-            r.bxy = zstride;
+            r.bx = (unsigned)hdr.z;
+            r.bxy = (unsigned)hdr.w;
             r.zero_addr = smem_u32(&s_zero[0]);
+            const unsigned meta = recu[32 * kRecMeta];
+            const bool ride = meta & 1u, full = (meta & 2u) != 0;
+            const int label = (int)((meta >> 8) & 0xffu), L = (int)(meta >> 16);
             {
-                const int n = L + 1;
-                const double inv = 1.0 / (double)n;
-                const float q0x = ride ? (float)((p0.x - (double)org[0]) - 0.5) : 0.f, q0y = ride ? (float)((p0.y - (double)org[1]) - 0.5) : 0.f;
-                const float q0z = ride ? (float)((p0.z - (double)org[2]) - 0.5) : 0.f;
-                const float d1x = ride ? (float)((p1.x - p0.x) * inv) : 0.f, d1y = ride ? (float)((p1.y - p0.y) * inv) : 0.f, d1z = ride ? (float)((p1.z - p0.z) * inv) : 0.f;
-                const float d2x = ride ? (float)((p2.x - p0.x) * inv) : 0.f, d2y = ride ? (float)((p2.y - p0.y) * inv) : 0.f, d2z = ride ? (float)((p2.z - p0.z) * inv) : 0.f;
-                const float d3x = ride ? (float)((p3.x - p0.x) * inv) : 0.f, d3y = ride ? (float)((p3.y - p0.y) * inv) : 0.f, d3z = ride ? (float)((p3.z - p0.z) * inv) : 0.f;
+                const float q0x = rec[32 * (kRecQ0 + 0)], q0y = rec[32 * (kRecQ0 + 1)], q0z = rec[32 * (kRecQ0 + 2)];
+                const float d1x = rec[32 * (kRecD1 + 0)], d1y = rec[32 * (kRecD1 + 1)], d1z = rec[32 * (kRecD1 + 2)];
+                const float d2x = rec[32 * (kRecD2 + 0)], d2y = rec[32 * (kRecD2 + 1)], d2z = rec[32 * (kRecD2 + 2)];
+                const float d3x = rec[32 * (kRecD3 + 0)], d3y = rec[32 * (kRecD3 + 1)], d3z = rec[32 * (kRecD3 + 2)];
                 r.q0xy = pk2(q0x, q0y); r.q0zz = pk2(q0z, q0z);
                 r.d1xy = pk2(d1x, d1y); r.d1zz = pk2(d1z, d1z);
                 r.d2xy = pk2(d2x, d2y); r.d2zz = pk2(d2z, d2z);
@@ -438,50 +574,34 @@ __global__ void __launch_bounds__(kStgWarps * 32, 1) tet_staged_kernel(const __g
                     ofz[o] = fmaf(fz, e3z, fmaf(fx, e2z, fy * e1z));
                 }
                 r.ozz[0] = pk2(ofz[0], ofz[1]); r.ozz[1] = pk2(ofz[2], ofz[3]); r.ozz[2] = pk2(ofz[4], ofz[5]);
-                const bool l3 = ride && n == 3;
-                const float epx = l3 ? (float)(1.0e-6 * p0.x) : 0.f, epy = l3 ? (float)(1.0e-6 * p0.y) : 0.f, epz = l3 ? (float)(1.0e-6 * p0.z) : 0.f;
-                r.epxy = pk2(epx, epy); r.epzz = pk2(epz, epz);
-                r.thr = ride ? stg_threshold(rmax + 1.0, diam, n) : 1.0e30f;
-                // address of voxel O + m: base + (bits(tx) << SH) + bits(ty) bx + bits(tz) bxy, the bits being 0x4B400000 + m
-                constexpr unsigned SHM = ESZ;
-                const unsigned fold = 0x4B400000u * (SHM + r.bx + r.bxy);
-                const unsigned rel = ride ? (unsigned)((org[0] - x0) * ESZ) + (unsigned)(org[1] - y0) * r.bx + (unsigned)(org[2] - z0) * r.bxy : 0u;
-                r.base = slot_a + rel - fold;
+                const float epz = rec[32 * (kRecEp + 2)];
+                r.epxy = pk2(rec[32 * (kRecEp + 0)], rec[32 * (kRecEp + 1)]); r.epzz = pk2(epz, epz);
+                r.thr = rec[32 * kRecThr];
+                r.base = recu[32 * kRecBase];
             }
-            {
-                unsigned done = 0;
-                while (!done)
-                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
-                phase ^= 1u;
-            }
+            const double w = __hiloint2double((int)recu[32 * (kRecW + 1)], (int)recu[32 * kRecW]);
+            const double v = __hiloint2double((int)recu[32 * (kRecV + 1)], (int)recu[32 * kRecV]);
             StgAcc<VoxT, WANT_SQ, F32S> acc;
-            const bool full = ride && L + 1 == NB;
+            mbar_wait(smem_u32(&s_full[slot]), round & 1u);
             switch (NB) {
             case 1: stg_block<1, VoxT, WANT_SQ, F32S>(r, full, acc); break;
             case 2: stg_block<2, VoxT, WANT_SQ, F32S>(r, full, acc); break;
             case 3: stg_block<3, VoxT, WANT_SQ, F32S>(r, full, acc); break;
             default: stg_block<4, VoxT, WANT_SQ, F32S>(r, full, acc); break;
             }
+            __syncwarp();
+            if (lane == 0) { // every lane has read its voxels and its record
+                __threadfence_block();
+                *reinterpret_cast<volatile unsigned *>(&s_released[slot]) = round + 1u;
+            }
             const bool flagged = ride && !(acc.emax < r.thr);
-            coop |= __ballot_sync(0xffffffffu, flagged);
-            if (ride && !flagged) acc.result(t_sum, t_sq);
-        }
-        // ---------------- exact path: one tet at a time, 32 lanes over its rows ----------------
-        while (coop) {
-            const int src = __ffs(coop) - 1;
-            coop &= coop - 1u;
-            uint4 snd;
-            snd.x = __shfl_sync(0xffffffffu, nd.x, src); snd.y = __shfl_sync(0xffffffffu, nd.y, src);
-            snd.z = __shfl_sync(0xffffffffu, nd.z, src); snd.w = __shfl_sync(0xffffffffu, nd.w, src);
-            const int sL = __shfl_sync(0xffffffffu, L, src);
-            double s, q;
-            coop_exact<VoxT, WANT_SQ, F32S>(a, vol, snd, sL, lane, s, q);
-            if (lane == src) { t_sum = s; t_sq = q; }
-        }
-        // ---------------- per-tet result, per-label fixed-point sums ----------------
-        if (t < a.tet_end) {
-            if (active) {
-                const double tot = PER_TET ? t_sum * v / (double)n3 : t_sum * (v / (double)n3); // total * v / a.size() (image3d.cpp:371)
+            const unsigned t = (unsigned)hdr.x + (unsigned)lane;
+            exact_append(a, flagged, t, lane);
+            if (ride && !flagged) {
+                double t_sum, t_sq;
+                acc.result(t_sum, t_sq);
+                const int n3 = (L + 1) * (L + 1) * (L + 1);
+                const double tot = PER_TET ? t_sum * v / (double)n3 : t_sum * w; // total * v / a.size() (image3d.cpp:371)
                 if (PER_TET) {
                     if (a.tet_total) a.tet_total[t] = tot;
                     if (a.tet_vol) a.tet_vol[t] = v;
@@ -490,7 +610,7 @@ __global__ void __launch_bounds__(kStgWarps * 32, 1) tet_staged_kernel(const __g
                 const long long ftot = __double2ll_rn(tot * a.stg_scale[0]);
                 const long long fvol = __double2ll_rn(v * a.stg_scale[2]);
                 long long fsq = 0;
-                if (WANT_SQ) fsq = __double2ll_rn(t_sq * (v / (double)n3) * a.stg_scale[1]);
+                if (WANT_SQ) fsq = __double2ll_rn(t_sq * w * a.stg_scale[1]);
 #pragma unroll
                 for (int k = 0; k < kMaxPhase; k++)
                     if (label == k + 1 && k < a.nb_phase) {
@@ -498,39 +618,117 @@ __global__ void __launch_bounds__(kStgWarps * 32, 1) tet_staged_kernel(const __g
                         acc_vol[k] += fvol;
                         if (WANT_SQ) acc_sq[k] += fsq;
                     }
-            } else if (PER_TET) {
-                if (a.tet_total) a.tet_total[t] = -1.0;
-                if (a.tet_vol) a.tet_vol[t] = -1.0;
-                if (a.tet_mean) a.tet_mean[t] = -1.0;
             }
         }
-        tile = __shfl_sync(0xffffffffu, next, 0);
-    }
-    // ---------------- per-CTA partial row (integers: any order gives the same sums) ----------------
+        // per-warp rows (integers: any order gives the same sums)
 #pragma unroll
-    for (int k = 0; k < kMaxPhase; k++) {
-        long long x = acc_tot[k], y = acc_sq[k], z = acc_vol[k];
+        for (int k = 0; k < kMaxPhase; k++) {
+            long long x = acc_tot[k], y = acc_sq[k], z = acc_vol[k];
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            x += __shfl_xor_sync(0xffffffffu, x, m);
-            if (WANT_SQ) y += __shfl_xor_sync(0xffffffffu, y, m);
-            z += __shfl_xor_sync(0xffffffffu, z, m);
+            for (int m = 16; m >= 1; m >>= 1) {
+                x += __shfl_xor_sync(0xffffffffu, x, m);
+                if (WANT_SQ) y += __shfl_xor_sync(0xffffffffu, y, m);
+                z += __shfl_xor_sync(0xffffffffu, z, m);
+            }
+            if (lane == 0) {
+                s_red[warp - kStgProd][k] = x;
+                s_red[warp - kStgProd][kMaxPhase + k] = y;
+                s_red[warp - kStgProd][2 * kMaxPhase + k] = z;
+            }
         }
-        if (lane == 0) {
-            s_red[warp][k] = x;
-            s_red[warp][kMaxPhase + k] = y;
-            s_red[warp][2 * kMaxPhase + k] = z;
-        }
     }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, m);
     __syncthreads();
     if (threadIdx.x < 3 * kMaxPhase) {
         long long rsum = 0;
-        for (int w = 0; w < kStgWarps; w++) rsum += s_red[w][threadIdx.x];
+        for (int wd = 0; wd < kStgCons; wd++) rsum += s_red[wd][threadIdx.x];
         a.stg_partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = rsum;
     }
-    if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
+}
+
+// The tets the staged stream left out (exact_append), one warp per tet: the reference's exact FP64 sequence for every sample
+// (get_coord, DEMO/tet_dis_coord.hpp:27; truncation image3d.cpp:366; bounds image3d.cpp:480-491), two table rows per lane in
+// flight.  The list entry and the ids of the following tets are fetched ahead.
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S>
+__global__ void __launch_bounds__(256, 4) tet_exact_list_kernel(const __grid_constant__ TetArgs a)
+{
+    __shared__ unsigned long long s_acc[3 * kMaxPhase];
+    if (threadIdx.x < 3 * kMaxPhase) s_acc[threadIdx.x] = 0ull;
+    __syncthreads();
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
+    const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
+    const int lane = threadIdx.x & 31;
+    const unsigned n = *a.stg_exact_count;
+    const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    constexpr unsigned NONE = 0xffffffffu;
+    auto entry = [&](unsigned i) { return i < n ? __ldg(a.stg_exact_list + i) : NONE; };
+    auto ids = [&](unsigned t, int &lab, uint4 &nd) {
+        lab = 0; nd = make_uint4(0, 0, 0, 0);
+        if (t != NONE) { lab = __ldg(a.mesh.tet_label + t); nd = __ldg(a.mesh.tet_nodes + t); }
+    };
+    unsigned i = wid;
+    unsigned t = entry(i), t1 = entry(i + nw), t2 = NONE;
+    int label, label1;
+    uint4 nd, nd1;
+    ids(t, label, nd);
+    ids(t1, label1, nd1);
+    while (t != NONE) {
+        t2 = entry(i + 2 * nw);
+        const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y), p2 = load_pos(a.mesh.pos4, nd.z), p3 = load_pos(a.mesh.pos4, nd.w);
+        const double v = tet_volume(p0, p1, p2, p3);
+        const int L = tet_level(v);
+        const int rows = (L + 1) * (L + 1) * (L + 1);
+        const int off = (L * (L + 1) / 2) * (L * (L + 1) / 2);
+        const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(a.tet_bary) + 2 * (size_t)off;
+        StgAcc<VoxT, WANT_SQ, F32S> acc;
+        constexpr int U = 2; // table rows per lane in flight
+        for (int r0 = 0; r0 < rows; r0 += 32 * U) {
+            double2 b01[U], b23[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int r = min(r0 + 32 * u + lane, rows - 1);
+                b01[u] = __ldg(tb + 2 * r);
+                b23[u] = __ldg(tb + 2 * r + 1);
+            }
+            VoxT val[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int ix = (int)(((p0.x * b01[u].x + p1.x * b01[u].y) + p2.x * b23[u].x) + p3.x * b23[u].y);
+                const int iy = (int)(((p0.y * b01[u].x + p1.y * b01[u].y) + p2.y * b23[u].x) + p3.y * b23[u].y);
+                const int iz = (int)(((p0.z * b01[u].x + p1.z * b01[u].y) + p2.z * b23[u].x) + p3.z * b23[u].y);
+                const bool ok = r0 + 32 * u + lane < rows && (unsigned)ix < (unsigned)X && (unsigned)iy < (unsigned)Y && (unsigned)iz < (unsigned)Z;
+                val[u] = ok ? __ldg(vol + ((size_t)iz * Y + iy) * X + ix) : (VoxT)0; // outside the volume: BOUND_INTENSITY = 0
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) acc.add(val[u], u);
+        }
+        double s, q;
+        acc.result(s, q);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            s += shfl_xor_d(s, m);
+            if (WANT_SQ) q += shfl_xor_d(q, m);
+        }
+        if (lane == 0) {
+            const double w = v / (double)rows;
+            const double tot = PER_TET ? s * v / (double)rows : s * w;
+            if (PER_TET) {
+                if (a.tet_total) a.tet_total[t] = tot;
+                if (a.tet_vol) a.tet_vol[t] = v;
+                if (a.tet_mean) a.tet_mean[t] = tot / v;
+            }
+            if (label >= 1 && label <= a.nb_phase) {
+                atomicAdd(&s_acc[label - 1], (unsigned long long)__double2ll_rn(tot * a.stg_scale[0]));
+                if (WANT_SQ) atomicAdd(&s_acc[kMaxPhase + label - 1], (unsigned long long)__double2ll_rn(q * w * a.stg_scale[1]));
+                atomicAdd(&s_acc[2 * kMaxPhase + label - 1], (unsigned long long)__double2ll_rn(v * a.stg_scale[2]));
+            }
+        }
+        i += nw;
+        t = t1; label = label1; nd = nd1;
+        t1 = t2;
+        ids(t1, label1, nd1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * kMaxPhase) a.stg_partials2[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = (long long)s_acc[threadIdx.x];
 }
 
 // Adds the per-CTA fixed-point rows (exact) and converts: out[0..P) total, [P..2P) sumsq, [2P..3P) volume, mean = total/volume.

@@ -80,9 +80,10 @@ struct dscgpu_ctx {
     int tet_variant = 128 | 16384; // see dscgpu_set_tet_variant; default = w2, full batches without clamps on the sums-only path (the fastest measured form: DESIGN.md section 9)
     // staged kernel (variant bit 131072, dsc_tet_staged.cuh): tensor-map family in device memory, tile counter, fixed-point scales
     TmapBlob *d_stg_maps = nullptr;
-    unsigned *d_stg_counter = nullptr;
+    unsigned *d_stg_counter = nullptr; // [0] tile counter, [1] length of the exact list
+    DevBuf stg_exact;           // the exact list
     int stg_state = 0;          // 0 not tried, 1 ready, -1 unavailable
-    int stg_slot_bytes = 27 * 1024;
+    int stg_slot_bytes = 24 * 1024, stg_slots = 8;
     double stg_scale[3] = {1.0, 1.0, 1.0};
     bool tet_rows_fixed = false; // the partial rows of the running tet pass are fixed-point integers (staged kernel)
     float vol_max = 1.0f;        // largest voxel of a float volume (volume_flags_kernel)
@@ -280,20 +281,21 @@ int ensure_staged(dscgpu_ctx *ctx)
         return DSCGPU_OK;
     }
     const CUtensorMapDataType dt = ctx->dtype == DSCGPU_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : ctx->dtype == DSCGPU_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    std::vector<TmapBlob> maps((size_t)kStgMaxUnits * kStgMaxRows);
+    std::vector<TmapBlob> maps((size_t)kStgMaxUnits * kStgMaxRows * kStgMaxSlices);
     const cuuint64_t gdim[3] = {X, Y, Z}, gstr[2] = {X * es, X * Y * es};
     const cuuint32_t estr[3] = {1, 1, 1};
     for (int u = 0; u < kStgMaxUnits; u++)
-        for (int r = 0; r < kStgMaxRows; r++) {
-            alignas(64) CUtensorMap tm;
-            const cuuint32_t box[3] = {(cuuint32_t)((u + 1) * 16 / es), (cuuint32_t)(r + 1), 1};
-            if (reinterpret_cast<encode_fn>(fn)(&tm, dt, 3, ctx->d_vol, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                return DSCGPU_OK;
-            memcpy(&maps[(size_t)u * kStgMaxRows + r], &tm, sizeof(CUtensorMap));
-        }
+        for (int r = 0; r < kStgMaxRows; r++)
+            for (int sl = 0; sl < kStgMaxSlices; sl++) {
+                alignas(64) CUtensorMap tm;
+                const cuuint32_t box[3] = {(cuuint32_t)((u + 1) * 16 / es), (cuuint32_t)(r + 1), (cuuint32_t)(sl + 1)};
+                if (reinterpret_cast<encode_fn>(fn)(&tm, dt, 3, ctx->d_vol, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return DSCGPU_OK;
+                memcpy(&maps[((size_t)u * kStgMaxRows + r) * kStgMaxSlices + sl], &tm, sizeof(CUtensorMap));
+            }
     if (!ctx->d_stg_maps) CK(cudaMalloc(&ctx->d_stg_maps, maps.size() * sizeof(TmapBlob)));
-    if (!ctx->d_stg_counter) CK(cudaMalloc(&ctx->d_stg_counter, sizeof(unsigned)));
+    if (!ctx->d_stg_counter) CK(cudaMalloc(&ctx->d_stg_counter, 2 * sizeof(unsigned)));
     CK(cudaMemcpy(ctx->d_stg_maps, maps.data(), maps.size() * sizeof(TmapBlob), cudaMemcpyHostToDevice));
     // fixed point: per-label sums stay below 64 x (voxels of the volume) x (largest intensity) -- tets cover the volume once, a
     // DSC mesh pads it by one edge -- and must stay below 2^62; tet_finalize_fixed_kernel reports a sum that did not
@@ -310,28 +312,43 @@ int ensure_staged(dscgpu_ctx *ctx)
 template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S> int launch_staged_t(dscgpu_ctx *ctx, TetArgs &a)
 {
     auto kern = tet_staged_kernel<VoxT, WANT_SQ, PER_TET, F32S>;
-    const int smem = kStgWarps * ctx->stg_slot_bytes;
+    auto kern2 = tet_exact_list_kernel<VoxT, WANT_SQ, PER_TET, F32S>;
+    const int smem = ctx->stg_slots * (ctx->stg_slot_bytes + kStgRecBytes);
     static bool attr_set = false; // per instantiation
     static int attr_dev = -1;
     if (!attr_set || attr_dev != ctx->device) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
         attr_set = true; attr_dev = ctx->device;
     }
-    const unsigned n_tiles = (a.tet_end - a.tet_begin + 31) / 32;
+    const unsigned n_work = a.tet_end - a.tet_begin;
+    const unsigned n_tiles = (n_work + 31) / 32;
     unsigned grid = (unsigned)ctx->num_sms;
-    const unsigned need = (n_tiles + kStgWarps - 1) / kStgWarps;
+    const unsigned need = (n_tiles + kStgProd - 1) / kStgProd;
     if (need < grid) grid = need ? need : 1;
-    if (ctx->tet_grid + grid > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    // the exact list is worked off by warps, one tet each: enough of them to hide its dependent loads, no more than the list can feed
+    unsigned grid2 = (unsigned)ctx->num_sms * 4;
+    const unsigned need2 = (n_work / 64 + 7) / 8;
+    if (need2 < grid2) grid2 = need2 ? need2 : 1;
+    if (ctx->tet_grid + grid + grid2 > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
+    {   // growing the list buffer is not possible while the stream is being captured; sized per snapshot by ensure_scratch
+        if (ctx->stg_exact.cap < (size_t)n_work * sizeof(unsigned)) { ctx->err = "exact-list buffer smaller than the tet range"; return DSCGPU_ERR_ARG; }
+    }
     a.stg_partials = ctx->partials.as<long long>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
-    ctx->tet_grid += (int)grid;
+    a.stg_partials2 = a.stg_partials + (size_t)grid * 3 * kMaxPhase;
+    ctx->tet_grid += (int)(grid + grid2);
     ctx->tet_rows_fixed = true;
     a.stg_maps = ctx->d_stg_maps;
     a.stg_slot_bytes = ctx->stg_slot_bytes;
+    a.stg_slots = ctx->stg_slots;
     a.stg_counter = ctx->d_stg_counter;
+    a.stg_exact_count = ctx->d_stg_counter + 1;
+    a.stg_exact_list = ctx->stg_exact.as<unsigned>();
     for (int k = 0; k < 3; k++) a.stg_scale[k] = ctx->stg_scale[k];
-    CK(cudaMemsetAsync(ctx->d_stg_counter, 0, sizeof(unsigned), ctx->stream));
-    kern<<<grid, kStgWarps * 32, smem, ctx->stream>>>(a);
-    ctx->launches++;
+    CK(cudaMemsetAsync(ctx->d_stg_counter, 0, 2 * sizeof(unsigned), ctx->stream));
+    kern<<<grid, (kStgProd + kStgCons) * 32, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    kern2<<<grid2, 256, 0, ctx->stream>>>(a);
+    ctx->launches += 2;
     CK(cudaGetLastError());
     return DSCGPU_OK;
 }
@@ -771,6 +788,7 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     CK(ctx->pos4f.ensure((size_t)nn * 16));
     CK(ctx->tet_nodes.ensure((size_t)nt * 16));
     CK(ctx->tet_label.ensure((size_t)nt * 4));
+    CK(ctx->stg_exact.ensure((size_t)nt * 4)); // list of the tets the staged kernel leaves to the exact path
     CK(ctx->face_nodes.ensure((size_t)nf * 12));
     CK(ctx->face_tets.ensure((size_t)nf * 8));
     CK(ctx->face_isb.ensure((size_t)nf));
@@ -932,10 +950,19 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
         CK(cudaMemcpy(ctx->d_tet_lat, tl.data(), tl.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (const char *ev = getenv("DSCGPU_TET_VARIANT")) ctx->tet_variant = atoi(ev);
-    if (const char *ev = getenv("DSCGPU_STG_SLOT_KB")) { // development knob: shared-memory slot of one warp of the staged kernel
+    // staged kernel: voxel box of one shared-memory slot by voxel size (a 32-tet tile of a DSC mesh whose tets hold 27-64 voxels: about
+    // 52 x 11 x 11 voxels), as many slots as fit -- the more slots, the more TMA transfers in flight next to the consumers' tiles
+    ctx->stg_slot_bytes = (ctx->dtype == DSCGPU_U8 ? 8 : ctx->dtype == DSCGPU_U16 ? 14 : 24) * 1024;
+    ctx->stg_slots = kStgMaxSlots;
+    if (const char *ev = getenv("DSCGPU_STG_SLOT_KB")) { // development knobs
         const int kb = atoi(ev);
-        if (kb >= 4 && kb * kStgWarps <= 222) ctx->stg_slot_bytes = kb * 1024;
+        if (kb >= 4 && kb <= 64) ctx->stg_slot_bytes = kb * 1024;
     }
+    if (const char *ev = getenv("DSCGPU_STG_SLOTS")) {
+        const int n = atoi(ev);
+        if (n >= 2 && n <= kStgMaxSlots) ctx->stg_slots = n;
+    }
+    while (ctx->stg_slots > 2 && ctx->stg_slots * (ctx->stg_slot_bytes + kStgRecBytes) > 227 * 1024 - 4096) ctx->stg_slots--;
     if (voxels_host) { // one scan of a float volume: are all voxels non-negative finite numbers?
         int rf = ensure_volume_flags(ctx);
         if (rf) return rf;
@@ -1096,6 +1123,7 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     CK(ctx->pos4f.ensure((size_t)nn * 16));
     CK(ctx->tet_nodes.ensure((size_t)nt * 16));
     CK(ctx->tet_label.ensure((size_t)nt * 4));
+    CK(ctx->stg_exact.ensure((size_t)nt * 4)); // list of the tets the staged kernel leaves to the exact path
     CK(ctx->face_nodes.ensure((size_t)nf * 12));
     CK(ctx->face_tets.ensure((size_t)nf * 8));
     CK(ctx->face_isb.ensure((size_t)nf));

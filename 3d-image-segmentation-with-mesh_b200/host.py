@@ -67,7 +67,8 @@ def load_library():
     from . import build as _build
     path = library_path()
     try:
-        path = _build.build()
+        # development: DSCGPU_LIBRARY names an already built experimental copy of the library (kernel A/B runs)
+        path = os.environ["DSCGPU_LIBRARY"] if os.environ.get("DSCGPU_LIBRARY") else _build.build()
     except Exception as e:  # no nvcc on this machine: use a prebuilt library if it is there
         if not os.path.exists(path):
             raise DscGpuError("libdscgpu.so is missing and cannot be built (%s); there is no CPU fallback" % e)

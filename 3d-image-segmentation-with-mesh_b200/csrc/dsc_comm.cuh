@@ -65,8 +65,11 @@ DSC_D bool comm_wait(const unsigned long long *p, unsigned long long e, int *err
     return true;
 }
 
-__global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kernel(CommView c, const double *__restrict__ partials, int n_rows, int nb_phase, double *sums,
-                                                                                  double *mean)
+// FIXED: the partial rows are the 64-bit fixed-point sums of the staged tet kernel (dsc_tet_staged.cuh): integers are exchanged and
+// added, so the result does not depend on the number of ranks nor on how the tets were cut; scale[which] converts at the end.
+template <bool FIXED>
+__global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kernel(CommView c, const void *__restrict__ partials_v, int n_rows, int nb_phase, double s_tot,
+                                                                                  double s_sq, double s_vol, double *sums, double *mean)
 {
     const int col = threadIdx.x >> 5, lane = threadIdx.x & 31; // 24 warps, one per column of the partial rows
     unsigned char *mine = c.win[c.rank];
@@ -77,15 +80,27 @@ __global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kerne
         s_epoch = *ep + 1; // one epoch per evaluation; the force exchange of the same evaluation reads it back
         *ep = s_epoch;
     }
-    double r = 0;
-    for (int i = lane; i < n_rows; i += 32) r += partials[(size_t)i * 3 * kMaxPhase + col];
+    unsigned long long bits; // what is pushed: the double, or the integer, of this column
+    if (FIXED) {
+        const long long *partials = static_cast<const long long *>(partials_v);
+        long long r = 0;
+        for (int i = lane; i < n_rows; i += 32) r += partials[(size_t)i * 3 * kMaxPhase + col];
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) r += shfl_xor_d(r, m);
+        for (int m = 16; m >= 1; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+        bits = (unsigned long long)r;
+    } else {
+        const double *partials = static_cast<const double *>(partials_v);
+        double r = 0;
+        for (int i = lane; i < n_rows; i += 32) r += partials[(size_t)i * 3 * kMaxPhase + col];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) r += shfl_xor_d(r, m);
+        bits = (unsigned long long)__double_as_longlong(r);
+    }
     __syncthreads();
     const unsigned long long e = s_epoch;
     const int half = (int)(e & 1);
     // push: lane k of every column warp stores the column's sum into this rank's slot of rank k's window
-    if (lane < c.world) reinterpret_cast<double *>(c.win[lane] + kCommSums)[((size_t)half * kCommMaxWorld + c.rank) * 3 * kMaxPhase + col] = r;
+    if (lane < c.world) reinterpret_cast<unsigned long long *>(c.win[lane] + kCommSums)[((size_t)half * kCommMaxWorld + c.rank) * 3 * kMaxPhase + col] = bits;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < c.world) {
@@ -94,9 +109,16 @@ __global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kerne
     }
     __syncthreads();
     if (lane == 0) {
-        double t = 0;
-        for (int k = 0; k < c.world; k++) t += __ldcv(reinterpret_cast<const double *>(mine + kCommSums) + ((size_t)half * kCommMaxWorld + k) * 3 * kMaxPhase + col);
         const int which = col / kMaxPhase, ph = col % kMaxPhase;
+        const unsigned long long *slot = reinterpret_cast<const unsigned long long *>(mine + kCommSums) + (size_t)half * kCommMaxWorld * 3 * kMaxPhase + col;
+        double t = 0;
+        if (FIXED) {
+            long long ti = 0;
+            for (int k = 0; k < c.world; k++) ti += (long long)__ldcv(slot + (size_t)k * 3 * kMaxPhase);
+            t = (double)ti / (which == 0 ? s_tot : (which == 1 ? s_sq : s_vol)); // power of two: one rounding, of the integer
+        } else {
+            for (int k = 0; k < c.world; k++) t += __longlong_as_double((long long)__ldcv(slot + (size_t)k * 3 * kMaxPhase));
+        }
         if (ph < nb_phase) sums[which * nb_phase + ph] = t;
         if (which == 0) tot[ph] = t;
         if (which == 2) vol[ph] = t;

@@ -77,7 +77,7 @@ struct dscgpu_ctx {
     float4 *d_tet_lat = nullptr;
     int force_thread_gather = 0; // 1: thread-per-node gather (first implementation) instead of warp-per-node
     int hot_want_sq = 0; // dscgpu_image_force_eval / dscgpu_tet_phase_sums_dev skip the second moment unless asked
-    int tet_variant = 128 | 16384; // see dscgpu_set_tet_variant; default = w2, full batches without clamps on the sums-only path (the fastest measured form: DESIGN.md section 9)
+    int tet_variant = 131072 | 128 | 16384; // see dscgpu_set_tet_variant; default = the staged kernel, w2 (clamp-free full batches on the sums-only path) for volumes it cannot describe
     // staged kernel (variant bit 131072, dsc_tet_staged.cuh): tensor-map family in device memory, tile counter, fixed-point scales
     TmapBlob *d_stg_maps = nullptr;
     unsigned *d_stg_counter = nullptr; // [0] tile counter, [1] length of the exact list
@@ -1851,7 +1851,11 @@ int dscgpu_tet_phase_sums_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, double *d
         if (r) return r;
     }
     TimerScope ts(ctx, DSCGPU_T_PHASE_FINAL);
-    comm_phase_allreduce_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(comm_view(ctx), ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums, d_mean);
+    if (ctx->tet_rows_fixed)
+        comm_phase_allreduce_kernel<true><<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(comm_view(ctx), ctx->partials.p, ctx->tet_grid, nb_phase, ctx->stg_scale[0], ctx->stg_scale[1],
+                                                                                     ctx->stg_scale[2], d_sums, d_mean);
+    else
+        comm_phase_allreduce_kernel<false><<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(comm_view(ctx), ctx->partials.p, ctx->tet_grid, nb_phase, 1.0, 1.0, 1.0, d_sums, d_mean);
     ctx->launches++;
     CK(cudaGetLastError());
     return DSCGPU_OK;

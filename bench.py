@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--jitter", type=float, default=0.2)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the comparison of the step's outputs with the flat oracle (outside the timed region)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
     ap.add_argument("--overlap-forces", action="store_true",
                     help="start the mean-independent half of the force pass on a second stream next to the tet pass (measured: no gain, the tet kernel fills every SM)")
@@ -139,6 +140,37 @@ def algorithmic_bytes(snap, n_samples, n_gauss, voxel_bytes, per_tet_outputs=Fal
     tet_b = n_tets * (16 + 4 + 96 + (24 if per_tet_outputs else 0)) + n_bound * 4 + n_samples * voxel_bytes
     face_b = len(snap["face_nodes"]) * (60 + 120 + 144) + n_gauss * 8 * voxel_bytes
     return tet_b, face_b
+
+
+def parity_check(pkg, seg, vol, snap, P, sums, mean, forces, n_samples, bit_exact_forces, per_tet=True):
+    """Outside the timed region: what the timed step produced against the flat oracle (oracle/flat_oracle.cpp, bit-identical to the
+    unmodified reference on the fixtures) on the same inputs.  Integer decisions bit for bit, sums to the stated tolerance."""
+    from oracle import flat
+    thr = flat.num_threads()
+    ref = flat.tet_integrate(vol, snap["tet_nodes"], snap["pos"], threads=thr, want_hash=False)
+    lab = snap["tet_label"]
+    tot, volu, mean_ref = flat.phase_reduce(lab, ref["total"], ref["vol"], P)
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), 1e-300)))
+    out = {"oracle": "oracle/flat_oracle.cpp, %d threads" % thr,
+           "sample_count_equal": bool(int(n_samples) == int(ref["nsamp"][lab != 0].sum())),
+           "phase_total_max_rel": rel(sums[:P], tot), "phase_volume_max_rel": rel(sums[2 * P:3 * P], volu), "mean_max_rel": rel(mean, mean_ref)}
+    # per-tet outputs of the default kernel: every sample in the reference's voxel <=> bit-equal totals for float voxels
+    out["tet_volume_bit_equal"] = out["tet_total_mismatches"] = None
+    if per_tet:  # (one GPU: with a partition set the per-tet call only covers this rank's range)
+        o = seg.tet_integrate(include_bound=True, update_means=False)
+        out["tet_volume_bit_equal"] = bool(np.array_equal(o["vol"], ref["vol"]))
+        if vol.dtype == np.float32:
+            out["tet_total_mismatches"] = int(np.count_nonzero(o["total"] != ref["total"]))
+        else:  # integer voxels: the integer sum is divided at a different point, one rounding apart
+            out["tet_total_mismatches"] = int(np.count_nonzero(np.abs(o["total"] - ref["total"]) > 1e-13 * np.abs(ref["total"]) + 1e-14))
+    F_ref = flat.face_forces(vol, snap, P, np.asarray(mean, np.float64))  # one thread: the reference's order of additions
+    F = np.asarray(forces).reshape(-1, 3)
+    out["forces_bit_equal"] = bool(np.array_equal(F, F_ref))
+    out["forces_max_abs_diff"] = float(np.abs(F - F_ref).max())
+    out["forces_max_abs"] = float(np.abs(F_ref).max())
+    tol_ok = out["phase_total_max_rel"] < 1e-9 and out["phase_volume_max_rel"] < 1e-9 and out["forces_max_abs_diff"] <= 1e-6 * max(out["forces_max_abs"], 1.0)
+    out["ok"] = bool(out["sample_count_equal"] and out["tet_volume_bit_equal"] is not False and not out["tet_total_mismatches"] and tol_ok and (out["forces_bit_equal"] or not bit_exact_forces))
+    return out
 
 
 def flush_l2(torch, buf):
@@ -434,6 +466,47 @@ def main_b200(args):
     n_samples_all, n_gauss_all = [int(x) for x in cnt.tolist()]
     ms_per_step = total_ms_max / args.steps
     value = units / (ms_per_step * 1e-3)
+    # what the timed step left on the device, kept for the parity check below
+    res_sums = d_sums.cpu().numpy().copy()
+    res_mean = d_mean.cpu().numpy().copy()
+    res_forces = d_forces.cpu().numpy().copy()
+
+    # ---- the same step with the per-label second moment (north_star (a): "intensity sum, squared sum and volume"; the reference's
+    # get_tetra_intensity pass, and the reference arm, do not compute it, so `value` is quoted without it and this next to it) ----
+    with_sumsq = None
+    if mean_mode == pkg.MEAN_TET and (world == 1 or p2p):
+        try:
+            seg.set_hot_want_sq(True)
+            seg.enable_timers(False)
+            for _ in range(3):
+                step_device()
+            torch.cuda.synchronize(dev)
+            g2 = None
+            if graph is not None:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, stream=stream):
+                    step_device()
+                for _ in range(3):
+                    g2.replay()
+            ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            barrier()
+            for i in range(args.steps):
+                flush_l2(torch, l2_buf)
+                ev2[i][0].record(stream)
+                if g2 is not None:
+                    g2.replay()
+                else:
+                    step_device()
+                ev2[i][1].record(stream)
+            barrier()
+            t2 = torch.tensor([float(sum(a.elapsed_time(b) for a, b in ev2))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            ms2 = t2.item() / args.steps
+            with_sumsq = {"ms_per_step": ms2, "value": units / (ms2 * 1e-3), "unit": UNIT, "phase_sumsq": [float(x) for x in d_sums.cpu().numpy()[P:2 * P]]}
+        finally:
+            seg.set_hot_want_sq(False)
+            seg.enable_timers(True)
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------------------
     # Every step: the host flattens the mesh into the library's pinned staging arrays (here: a copy from the resident
@@ -450,7 +523,9 @@ def main_b200(args):
         st["face_tets"][...] = snap["face_tets"]
         st["face_is_boundary"][...] = snap["face_is_boundary"]
 
+    t_fill = time.perf_counter()
     fill_staging()
+    host_fill_ms = (time.perf_counter() - t_fill) * 1e3  # numpy copies into the pinned arrays; the adapter's is_mesh walk is timed in oracle/dropin_test.cpp
     h2d_bytes = n_nodes * 32 + n_tets * 20 + n_faces * (12 + 8 + 1)  # pos4, tet ids+labels, face ids/tets/flags; the CSR is built on the device
     d2h_bytes = n_nodes * 24 + 4 * P * 8
 
@@ -536,7 +611,7 @@ def main_b200(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("tet_sums_g32_kernel" if int(os.environ.get("DSCGPU_TET_VARIANT", "16512")) & 1024 else "tet_integrate_w2_kernel") if mean_mode == pkg.MEAN_TET else "zray pass", "kernel_ms": kernel_ms,
+                "kernel": ("tet_staged_kernel + tet_exact_list_kernel" if seg.get_tet_variant() & 131072 else "tet_integrate_w2_kernel") if mean_mode == pkg.MEAN_TET else "zray pass", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": tet_bytes_rank, "peak_source": peak_src,
                 "whole_step": {"algorithmic_bytes": tet_bytes + face_bytes, "achieved": (tet_bytes + face_bytes) / world / (ms_per_step * 1e-3) / 1e9}}
 
@@ -556,6 +631,12 @@ def main_b200(args):
         except Exception as e:  # noqa: BLE001 -- never fail the bench line over the second baseline
             cpu_port = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
+    parity = None
+    if not args.no_parity and mean_mode == pkg.MEAN_TET:
+        try:
+            parity = parity_check(pkg, seg, vol, snap, P, res_sums, res_mean, res_forces, n_samples_all, bit_exact_forces=(world == 1 and force_mode == pkg.FORCE_GATHER), per_tet=(world == 1))
+        except Exception as e:  # noqa: BLE001 -- report, never hide
+            parity = {"ok": False, "error": repr(e)}
     check = {"mean": [float(x) for x in d_mean.cpu().tolist()], "force_l2": float(torch.linalg.vector_norm(d_forces).item()),
              "force_sum": [float(x) for x in forces_rows.sum(dim=0).cpu().tolist()]}
     line = {
@@ -569,7 +650,8 @@ def main_b200(args):
             "comm": ("none" if world == 1 else ("fused exchange kernels over NVLink peer memory (CUDA IPC windows)" if p2p else "2 NCCL all-reduces")),
             "samples_per_step": n_samples_all, "gauss_points_per_step": n_gauss_all},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
-                "steps": e2e_steps},
+                "steps": e2e_steps, "host_fill_ms": host_fill_ms},
+        "with_sumsq": with_sumsq, "parity": parity,
         "e2e_incremental": e2e_incr,
         "gpu_launches": int(launches_per_step[0] * args.steps),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_baseline_port": cpu_port, "clocks": clocks,

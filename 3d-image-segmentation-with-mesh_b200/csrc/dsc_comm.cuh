@@ -13,11 +13,10 @@
 //                                pushes the 3*nb_phase sums and the flag to every peer, waits for all flags in its own
 //                                window, adds the slots in rank order (same order on every rank: identical results) and
 //                                writes sums and means.
-//   force_scatter_rows_kernel    force_atomic_kernel scattering into compact local rows (one per node with interface faces).
-//   comm_force_push_kernel       copies the local rows into this rank's slot of every window and clears them; the last block
-//                                to finish stores the flags.
-//   comm_force_reduce_kernel     waits for all flags (local polling), then every thread adds one row of all slots in rank
-//                                order and stores it into the full force array.
+//   comm_force_fused_kernel      the whole force exchange in one launch: forms the vectors of this rank's faces from the
+//                                mean-independent geometry and scatter-adds them into compact local rows, pushes the range of
+//                                rows it touched into its slot of every window, then its flag; waits for all flags (local
+//                                polling) and adds, row by row, the slots of the ranks that touched the row, in rank order.
 //
 // Windows are cudaMalloc'ed per rank and mapped into the peers with CUDA IPC (dscgpu_comm_create / dscgpu_comm_connect).
 // Each window has two halves used by alternating evaluations (epoch parity): a rank can be one exchange ahead of a slow peer,
@@ -34,14 +33,20 @@ constexpr int kCommMaxWorld = 8;
 // window layout (bytes): flags of the sums exchange [2 halves][8 ranks] x 8 B at 0; of the force exchange at 128; epoch 256;
 // error 264; push-kernel block counter 272; sums slots [2][8][24] doubles at 512 (3072 B); rows slots [2][world][3 cap_rows] at 4096
 constexpr size_t kCommFlagSums = 0, kCommFlagForce = 128, kCommEpoch = 256, kCommError = 264, kCommDone = 272, kCommSums = 512, kCommRows = 4096;
+// fused force exchange: row ranges pushed by the ranks [2 halves][8 ranks] x (lo, hi) at 3584; local scratch [2 halves] x (barrier 1, barrier 2, lo, hi) at 3712
+constexpr size_t kCommRanges = 3584, kCommLocal = 3712;
+// sharded snapshot commit: data flags [8] at 320, acknowledgements [8] at 384, its own epoch at 448, push-kernel block counter at 456
+constexpr size_t kCommFlagSnap = 320, kCommAckSnap = 384, kCommSnapEpoch = 448, kCommSnapDone = 456;
 
 struct CommView {
     unsigned char *win[kCommMaxWorld]; // window of every rank as mapped here; win[rank] is this rank's own
     int rank, world;
     unsigned cap_rows;
+    size_t snap_off; // byte offset of the snapshot region of a window (after the row slots)
 };
 
-DSC_HD size_t comm_window_bytes(int world, unsigned cap_rows) { return kCommRows + 2 * (size_t)world * 3 * cap_rows * sizeof(double); }
+DSC_HD size_t comm_snapshot_offset(int world, unsigned cap_rows) { return (kCommRows + 2 * (size_t)world * 3 * cap_rows * sizeof(double) + 255) & ~(size_t)255; }
+DSC_HD size_t comm_window_bytes(int world, unsigned cap_rows, size_t snap_bytes = 0) { return comm_snapshot_offset(world, cap_rows) + snap_bytes; }
 DSC_HD size_t comm_rows_offset(int half, int slot, int world, unsigned cap_rows) { return kCommRows + ((size_t)half * world + slot) * 3 * cap_rows * sizeof(double); }
 
 DSC_D unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -69,8 +74,9 @@ DSC_D bool comm_wait(const unsigned long long *p, unsigned long long e, int *err
 // added, so the result does not depend on the number of ranks nor on how the tets were cut; scale[which] converts at the end.
 template <bool FIXED>
 __global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kernel(CommView c, const void *__restrict__ partials_v, int n_rows, int nb_phase, double s_tot,
-                                                                                  double s_sq, double s_vol, double *sums, double *mean)
+                                                                                  double s_sq, double s_vol, double *sums, double *mean, unsigned *stg_counters)
 {
+    if (FIXED && threadIdx.x < 2 && stg_counters) stg_counters[threadIdx.x] = 0u; // staged kernel: tile counter, exact-list length
     const int col = threadIdx.x >> 5, lane = threadIdx.x & 31; // 24 warps, one per column of the partial rows
     unsigned char *mine = c.win[c.rank];
     __shared__ unsigned long long s_epoch;
@@ -81,13 +87,11 @@ __global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kerne
         *ep = s_epoch;
     }
     unsigned long long bits; // what is pushed: the double, or the integer, of this column
-    if (FIXED) {
-        const long long *partials = static_cast<const long long *>(partials_v);
-        long long r = 0;
-        for (int i = lane; i < n_rows; i += 32) r += partials[(size_t)i * 3 * kMaxPhase + col];
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
-        bits = (unsigned long long)r;
+    if (FIXED) { // one row of integers, the CTAs of the staged kernels have added theirs already; left zero for the next pass
+        unsigned long long *acc = static_cast<unsigned long long *>(const_cast<void *>(partials_v));
+        bits = acc[col];
+        __syncwarp();
+        if (lane == 0) acc[col] = 0ull;
     } else {
         const double *partials = static_cast<const double *>(partials_v);
         double r = 0;
@@ -127,92 +131,209 @@ __global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kerne
     if (mean && threadIdx.x < nb_phase) mean[threadIdx.x] = tot[threadIdx.x] / vol[threadIdx.x];
 }
 
-struct ForceRowsArgs {
-    VolumeView vol;
+// ---- the force exchange as ONE kernel -------------------------------------------------------------------------------------
+// comm_force_fused_kernel: (1) forms the force vectors of this rank's interface faces from the mean-independent geometry
+// (force_geom_kernel: normals, areas, trilinear samples) and the phase means, scatter-adds them into compact local rows and
+// notes the range of rows it touched; zeroes the full force array; (2) after a grid-wide barrier pushes ONLY that range into its
+// slot of every peer's window (a rank's faces touch about 1/world of the rows: the dense form pushed every row to every peer),
+// together with the range, then -- after a second barrier -- its flag; (3) waits for the peers' flags in its own window and
+// adds, for every row, the slots of the ranks whose range holds it, in rank order, into the full force array.
+// The grid must be co-resident (it spins on its own barrier counters): the host sizes it from the occupancy query.
+struct ForceFusedArgs {
+    CommView c;
     MeshView mesh;
+    const double *fgeo;
+    const int *flab;
+    const double *fint;
+    const signed char *fset;
     int nb_phase;
     const double *mean;
-    const unsigned *apos;       // node -> row (exclusive scan of "has interface faces")
-    double *rows;               // local rows, 3 per active node, zero on entry
-    unsigned begin, end;        // faces of this rank
+    const unsigned *apos;         // node -> row (exclusive scan of "has interface faces")
+    double *rows;                 // local rows, 3 per active node, zero on entry and on exit
+    unsigned begin, end;          // faces of this rank
+    const unsigned *active_nodes; // row -> node
+    const unsigned *n_active_ptr;
+    double *forces;               // full array, 3 * n_nodes
+    unsigned n_nodes;
 };
 
-// force_atomic_kernel with compact destination rows
-template <typename VoxT> __global__ void __launch_bounds__(128) force_scatter_rows_kernel(const ForceRowsArgs a)
+DSC_D void comm_grid_barrier(unsigned *counter)
 {
-    const unsigned f = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= a.end) return;
-    const VoxT *__restrict__ vol = static_cast<const VoxT *>(a.vol.data);
-    FaceGeom g;
-    unsigned n[3];
-    if (!face_setup(a.mesh, f, a.nb_phase, a.mean, g, n)) return;
-    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int q = c_gauss_off[g.gs]; q < c_gauss_off[g.gs + 1]; q++) {
-        const double w = c_gauss[4 * q];
-        const double b[3] = {c_gauss[4 * q + 1], c_gauss[4 * q + 2], c_gauss[4 * q + 3]};
-        const V3 p = add(add(mul(g.p[0], b[0]), mul(g.p[1], b[1])), mul(g.p[2], b[2]));
-        const double I = fetch_trilinear(vol, a.vol.X, a.vol.Y, a.vol.Z, p);
-        const V3 fv = mul(g.norm, (2 * I - g.c0 - g.c1) * (g.c0 - g.c1) * w * g.area);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { acc[k][0] += fv.x * b[k]; acc[k][1] += fv.y * b[k]; acc[k][2] += fv.z * b[k]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned *>(counter) < gridDim.x) { }
+        __threadfence();
     }
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        double *dst = a.rows + 3 * (size_t)a.apos[n[k]];
-        atomicAdd(dst, acc[k][0]);
-        atomicAdd(dst + 1, acc[k][1]);
-        atomicAdd(dst + 2, acc[k][2]);
-    }
+    __syncthreads();
 }
 
-// local rows -> this rank's slot in every window (and cleared for the next evaluation); the last block stores the flags
-__global__ void __launch_bounds__(256) comm_force_push_kernel(CommView c, double *__restrict__ rows, const unsigned *__restrict__ n_active_ptr)
+__global__ void __launch_bounds__(256) comm_force_fused_kernel(const ForceFusedArgs a)
 {
+    const CommView &c = a.c;
     unsigned char *mine = c.win[c.rank];
     const unsigned long long e = *reinterpret_cast<const unsigned long long *>(mine + kCommEpoch);
     const int half = (int)(e & 1);
-    const size_t n = 3 * (size_t)min(*n_active_ptr, c.cap_rows);
+    unsigned *loc = reinterpret_cast<unsigned *>(mine + kCommLocal) + 4 * half; // barrier 1, barrier 2, lo, hi
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    // (1) zero the full array, scatter this rank's faces into the local rows
+    for (size_t i = gtid; i < 3 * (size_t)a.n_nodes; i += gsz) a.forces[i] = 0.0;
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (unsigned f = a.begin + gtid; f < a.end; f += gsz) {
+        const int gs = a.fset[f];
+        if (gs < 0) continue;
+        const double *g = a.fgeo + 4 * (size_t)f;
+        const V3 norm = {g[0], g[1], g[2]};
+        const double area = g[3];
+        const double c0 = phase_intensity(a.flab[2 * (size_t)f], a.nb_phase, a.mean), c1 = phase_intensity(a.flab[2 * (size_t)f + 1], a.nb_phase, a.mean);
+        double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        const int q0 = c_gauss_off[gs], ng = c_gauss_off[gs + 1] - q0;
+        for (int k = 0; k < ng; k++) {
+            const int q = q0 + k;
+            const double w = c_gauss[4 * q];
+            const double b[3] = {c_gauss[4 * q + 1], c_gauss[4 * q + 2], c_gauss[4 * q + 3]};
+            const double I = a.fint[12 * (size_t)f + k];
+            const V3 fv = mul(norm, (2 * I - c0 - c1) * (c0 - c1) * w * area);
+#pragma unroll
+            for (int m = 0; m < 3; m++) { acc[m][0] += fv.x * b[m]; acc[m][1] += fv.y * b[m]; acc[m][2] += fv.z * b[m]; }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const unsigned row = a.apos[a.mesh.face_nodes[3 * (size_t)f + m]];
+            lo = min(lo, row); hi = max(hi, row + 1u);
+            double *dst = a.rows + 3 * (size_t)row;
+            atomicAdd(dst, acc[m][0]);
+            atomicAdd(dst + 1, acc[m][1]);
+            atomicAdd(dst + 2, acc[m][2]);
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0 && hi > lo) { atomicMin(loc + 2, lo); atomicMax(loc + 3, hi); }
+    comm_grid_barrier(loc);
+    // (2) push the touched range (and clear the local rows), then the range and the flag
+    lo = *reinterpret_cast<volatile unsigned *>(loc + 2);
+    hi = *reinterpret_cast<volatile unsigned *>(loc + 3);
+    if (hi < lo) lo = hi = 0u;
+    hi = min(hi, c.cap_rows);
     const size_t off = comm_rows_offset(half, c.rank, c.world, c.cap_rows);
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const double v = rows[i];
-        rows[i] = 0.0;
+    for (size_t i = 3 * (size_t)lo + gtid; i < 3 * (size_t)hi; i += gsz) {
+        const double v = a.rows[i];
+        a.rows[i] = 0.0;
         for (int k = 0; k < c.world; k++) reinterpret_cast<double *>(c.win[k] + off)[i] = v;
     }
+    if (blockIdx.x == 0 && threadIdx.x < c.world)
+        reinterpret_cast<uint2 *>(c.win[threadIdx.x] + kCommRanges)[half * kCommMaxWorld + c.rank] = make_uint2(lo, hi);
     __threadfence_system();
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned *>(mine + kCommDone), 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (last) {
-        if (threadIdx.x == 0) *reinterpret_cast<unsigned *>(mine + kCommDone) = 0u;
-        __threadfence_system();
-        if (threadIdx.x < c.world) st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommFlagForce) + half * kCommMaxWorld + c.rank, e);
+    comm_grid_barrier(loc + 1);
+    if (blockIdx.x == 0 && threadIdx.x < c.world)
+        st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommFlagForce) + half * kCommMaxWorld + c.rank, e);
+    // (3) wait for every rank's rows (local polling), add them in rank order
+    __shared__ uint2 s_rng[kCommMaxWorld];
+    if (threadIdx.x < c.world) {
+        comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommFlagForce) + half * kCommMaxWorld + threadIdx.x, e, reinterpret_cast<int *>(mine + kCommError));
+        const volatile uint2 *rp = reinterpret_cast<const volatile uint2 *>(mine + kCommRanges) + half * kCommMaxWorld + threadIdx.x;
+        s_rng[threadIdx.x] = make_uint2(rp->x, rp->y);
     }
-}
-
-// slots of all ranks added in rank order into the full force array (which is zero everywhere else)
-__global__ void __launch_bounds__(256) comm_force_reduce_kernel(CommView c, const unsigned *__restrict__ active_nodes, const unsigned *__restrict__ n_active_ptr,
-                                                                double *__restrict__ forces)
-{
-    unsigned char *mine = c.win[c.rank];
-    const unsigned long long e = *reinterpret_cast<const unsigned long long *>(mine + kCommEpoch);
-    const int half = (int)(e & 1);
-    if (threadIdx.x < c.world) comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommFlagForce) + half * kCommMaxWorld + threadIdx.x, e,
-                                         reinterpret_cast<int *>(mine + kCommError));
     __syncthreads();
-    const unsigned n_active = min(*n_active_ptr, c.cap_rows);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_active; i += gridDim.x * blockDim.x) {
+    const unsigned n_active = min(*a.n_active_ptr, c.cap_rows);
+    for (unsigned i = gtid; i < n_active; i += gsz) {
         double x = 0, y = 0, z = 0;
+        bool any = false;
         for (int k = 0; k < c.world; k++) {
+            if (i < s_rng[k].x || i >= s_rng[k].y) continue;
             const double *src = reinterpret_cast<const double *>(mine + comm_rows_offset(half, k, c.world, c.cap_rows)) + 3 * (size_t)i;
             x += __ldcv(src);
             y += __ldcv(src + 1);
             z += __ldcv(src + 2);
+            any = true;
         }
-        const size_t node = active_nodes[i];
-        forces[3 * node] = x;
-        forces[3 * node + 1] = y;
-        forces[3 * node + 2] = z;
+        if (any) {
+            const size_t node = a.active_nodes[i];
+            a.forces[3 * node] = x;
+            a.forces[3 * node + 1] = y;
+            a.forces[3 * node + 2] = z;
+        }
+    }
+    // scratch of the other half, for the next evaluation (nobody is looking at it now)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned *o = reinterpret_cast<unsigned *>(mine + kCommLocal) + 4 * (half ^ 1);
+        o[0] = 0u; o[1] = 0u; o[2] = 0xffffffffu; o[3] = 0u;
+    }
+}
+
+// ---- sharded snapshot commit ----------------------------------------------------------------------------------------------
+// Every rank needs the whole snapshot (positions, tets, labels, interface faces), but the host copy of it is the same on every
+// rank: rank r sends only bytes [b_r, e_r) of the flattened snapshot over PCIe, into the snapshot region of its own window, and
+// comm_snapshot_push_kernel copies that slice into the same place of every peer's window over NVLink, then its flag;
+// comm_snapshot_gather_kernel waits for the slices of all ranks (local polling), copies the assembled region into the snapshot
+// buffers and acknowledges the epoch; nobody pushes epoch e + 1 into a window whose owner has not acknowledged e.
+__global__ void __launch_bounds__(256) comm_snapshot_push_kernel(CommView c, size_t begin, size_t end)
+{
+    unsigned char *mine = c.win[c.rank];
+    __shared__ unsigned long long s_e;
+    if (threadIdx.x == 0) s_e = *reinterpret_cast<const unsigned long long *>(mine + kCommSnapEpoch) + 1; // advanced by the last block
+    __syncthreads();
+    const unsigned long long e = s_e;
+    // the owners of the windows written here must be done with the previous snapshot
+    if (threadIdx.x < c.world && threadIdx.x != c.rank)
+        comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommAckSnap) + threadIdx.x, e - 1, reinterpret_cast<int *>(mine + kCommError));
+    __syncthreads();
+    const uint4 *src = reinterpret_cast<const uint4 *>(mine + c.snap_off);
+    const size_t i0 = begin / 16, i1 = (end + 15) / 16;
+    for (size_t i = i0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < i1; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = src[i];
+        for (int k = 0; k < c.world; k++)
+            if (k != c.rank) reinterpret_cast<uint4 *>(c.win[k] + c.snap_off)[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned *>(mine + kCommSnapDone), 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) {
+            *reinterpret_cast<unsigned *>(mine + kCommSnapDone) = 0u;
+            *reinterpret_cast<unsigned long long *>(mine + kCommSnapEpoch) = e;
+        }
+        __threadfence_system();
+        if (threadIdx.x < c.world) st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommFlagSnap) + c.rank, e);
+    }
+}
+
+struct SnapshotParts {
+    unsigned char *dst[6]; // positions, tet nodes, tet labels, face nodes, face tets, face flags
+    size_t off[6], len[6]; // place in the snapshot region (256-byte aligned), bytes
+};
+
+// waits for the slices of all ranks (local polling), copies the assembled region into the snapshot buffers, acknowledges.
+// (A kernel, not copy-engine copies: those would queue behind this wait and, with several contexts on one device, in front of
+// a peer's upload.)
+__global__ void __launch_bounds__(256) comm_snapshot_gather_kernel(CommView c, SnapshotParts p)
+{
+    unsigned char *mine = c.win[c.rank];
+    // the push kernel of this commit has run (stream order): the epoch is the current one
+    const unsigned long long e = *reinterpret_cast<const unsigned long long *>(mine + kCommSnapEpoch);
+    if (threadIdx.x < c.world) comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommFlagSnap) + threadIdx.x, e, reinterpret_cast<int *>(mine + kCommError));
+    __syncthreads();
+    const unsigned char *region = mine + c.snap_off;
+    for (int k = 0; k < 6; k++) {
+        const size_t n16 = p.len[k] / 16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(region + p.off[k]);
+        uint4 *dst = reinterpret_cast<uint4 *>(p.dst[k]);
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = __ldcv(src + i);
+        for (size_t i = n16 * 16 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < p.len[k]; i += (size_t)gridDim.x * blockDim.x) p.dst[k][i] = region[p.off[k] + i];
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned *>(mine + kCommSnapDone), 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) { // every block has read the region: the peers may overwrite it with the next snapshot
+        if (threadIdx.x == 0) *reinterpret_cast<unsigned *>(mine + kCommSnapDone) = 0u;
+        __threadfence_system();
+        if (threadIdx.x < c.world) st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommAckSnap) + c.rank, e);
     }
 }
 

@@ -213,10 +213,10 @@ struct TetArgs {
     int stg_slot_bytes;              // voxel box of one shared-memory slot (multiple of 1024)
     int stg_slots;                   // slots of the ring
     unsigned *stg_counter;           // tile fetch counter, zero at launch
-    unsigned *stg_exact_count;       // tets left to the exact path (stg_counter + 1), zero at launch
+    int stg_chunk;                   // tiles a producer warp claims at a time
+    unsigned *stg_exact_count;       // tets left to the exact path (stg_counter + 1), zero at the first launch of a pass
     unsigned *stg_exact_list;        // ... and their indices, capacity tet_end - tet_begin
-    long long *stg_partials;         // [gridDim.x][3*kMaxPhase] fixed-point rows of the staged kernel: total, sumsq, volume
-    long long *stg_partials2;        // ... and of tet_exact_list_kernel
+    unsigned long long *stg_acc;     // [3*kMaxPhase] fixed-point sums (total, sumsq, volume per label) the CTAs of both staged kernels add theirs to
     double stg_scale[3];             // fixed-point scales (powers of two) of total, sumsq, volume
 };
 

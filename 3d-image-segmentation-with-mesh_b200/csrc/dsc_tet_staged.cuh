@@ -39,7 +39,7 @@ namespace dsc {
 #endif
 constexpr int kStgProd = STG_PROD, kStgCons = STG_CONS; // producer / consumer warps of a CTA
 constexpr int kStgMaxSlots = 16;
-constexpr int kStgChunk = 4; // tiles a producer claims with one atomic
+constexpr int kStgMaxChunk = 4; // most tiles a producer claims with one atomic
 constexpr int kStgMaxUnits = 16; // tensor-map family: boxes of 1..16 units of 16 bytes by 1..16 rows by 1..16 slices
 constexpr int kStgMaxRows = 16;
 constexpr int kStgMaxSlices = 16;
@@ -340,14 +340,15 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
         // Three tiles are in flight per producer: the index of tile k+2 (atomicAdd), label and node ids of tile k+1, the positions of
         // tile k+1 (asked for at the top of iteration k, when its ids have arrived) -- so the dependent round trips of a tile
         // (index -> ids -> positions) overlap with the arithmetic of the tiles before it.
-        // Tiles are claimed kStgChunk at a time: ptxas emits every returning atomic add in its warp-aggregated form, whose shuffle waits
+        // Tiles are claimed a.stg_chunk at a time (fewer when a launch has few tiles per warp: a chunk is also the grain of the tail): ptxas emits every returning atomic add in its warp-aggregated form, whose shuffle waits
         // for the result on the spot (one L2 round trip), so the claim is amortised over a chunk instead of being prefetched.
         // (inline PTX for the position loads: the compiler sinks plain loads down to their first use, an iteration later)
-        unsigned chunk_base = 0, chunk_pos = kStgChunk;
+        const unsigned chunk = (unsigned)a.stg_chunk;
+        unsigned chunk_base = 0, chunk_pos = chunk;
         auto fetch_tile = [&]() {
-            if (chunk_pos == kStgChunk) {
+            if (chunk_pos == chunk) {
                 unsigned x = 0;
-                if (lane == 0) x = atomicAdd(a.stg_counter, (unsigned)kStgChunk);
+                if (lane == 0) x = atomicAdd(a.stg_counter, chunk);
                 chunk_base = __shfl_sync(0xffffffffu, x, 0);
                 chunk_pos = 0;
             }
@@ -641,7 +642,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
     if (threadIdx.x < 3 * kMaxPhase) {
         long long rsum = 0;
         for (int wd = 0; wd < kStgCons; wd++) rsum += s_red[wd][threadIdx.x];
-        a.stg_partials[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = rsum;
+        if (rsum) atomicAdd(a.stg_acc + threadIdx.x, (unsigned long long)rsum); // integers: the order of the CTAs does not matter
     }
 }
 
@@ -728,33 +729,25 @@ __global__ void __launch_bounds__(256, 4) tet_exact_list_kernel(const __grid_con
         ids(t1, label1, nd1);
     }
     __syncthreads();
-    if (threadIdx.x < 3 * kMaxPhase) a.stg_partials2[(size_t)blockIdx.x * 3 * kMaxPhase + threadIdx.x] = (long long)s_acc[threadIdx.x];
+    if (threadIdx.x < 3 * kMaxPhase && s_acc[threadIdx.x]) atomicAdd(a.stg_acc + threadIdx.x, s_acc[threadIdx.x]);
 }
 
-// Adds the per-CTA fixed-point rows (exact) and converts: out[0..P) total, [P..2P) sumsq, [2P..3P) volume, mean = total/volume.
-// A sum that left the 62-bit range (a mesh far larger than the volume the scale was chosen for) raises bit 1 of *flags.
-__global__ void __launch_bounds__(32 * 3 * kMaxPhase) tet_finalize_fixed_kernel(const long long *__restrict__ partials, int n_rows, int nb_phase, double s_tot, double s_sq,
-                                                                                  double s_vol, double *sums, double *mean, unsigned *flags)
+// The fixed-point sums (one row of 3 * kMaxPhase integers the CTAs of the staged kernels have added their sums to) -> doubles:
+// out[0..P) total, [P..2P) sumsq, [2P..3P) volume, mean = total/volume.  Leaves the row, the tile counter and the list length zero
+// for the next pass.  A sum beyond 2^62 (a mesh far larger than the volume the scale was chosen for) raises bit 1 of *flags.
+__global__ void __launch_bounds__(32) tet_finalize_fixed_kernel(unsigned long long *acc, int nb_phase, double s_tot, double s_sq, double s_vol, double *sums, double *mean,
+                                                                unsigned *flags, unsigned *stg_counters)
 {
-    const int col = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    long long r = 0;
-    double approx = 0;
-    for (int i = lane; i < n_rows; i += 32) {
-        const long long p = partials[(size_t)i * 3 * kMaxPhase + col];
-        r += p;
-        approx += fabs((double)p);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        r += __shfl_xor_sync(0xffffffffu, r, m);
-        approx += shfl_xor_d(approx, m);
-    }
-    const int which = col / kMaxPhase, ph = col % kMaxPhase;
-    const double scale = which == 0 ? s_tot : (which == 1 ? s_sq : s_vol);
-    const double val = (double)r / scale; // scale is a power of two: one rounding, of the integer
     __shared__ double tot[kMaxPhase], vol[kMaxPhase];
-    if (lane == 0) {
-        if (approx >= 4.0e18 && flags) atomicOr(flags, 2u);
+    const int col = threadIdx.x;
+    if (col < 2 && stg_counters) stg_counters[col] = 0u;
+    if (col < 3 * kMaxPhase) {
+        const long long r = (long long)acc[col];
+        acc[col] = 0ull;
+        const int which = col / kMaxPhase, ph = col % kMaxPhase;
+        const double scale = which == 0 ? s_tot : (which == 1 ? s_sq : s_vol);
+        const double val = (double)r / scale; // scale is a power of two: one rounding, of the integer
+        if (fabs((double)r) >= 4.0e18 && flags) atomicOr(flags, 2u);
         if (ph < nb_phase) sums[which * nb_phase + ph] = val;
         if (which == 0) tot[ph] = val;
         if (which == 2) vol[ph] = val;

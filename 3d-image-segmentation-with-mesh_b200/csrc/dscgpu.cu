@@ -80,8 +80,11 @@ struct dscgpu_ctx {
     int tet_variant = 131072 | 128 | 16384; // see dscgpu_set_tet_variant; default = the staged kernel, w2 (clamp-free full batches on the sums-only path) for volumes it cannot describe
     // staged kernel (variant bit 131072, dsc_tet_staged.cuh): tensor-map family in device memory, tile counter, fixed-point scales
     TmapBlob *d_stg_maps = nullptr;
-    unsigned *d_stg_counter = nullptr; // [0] tile counter, [1] length of the exact list
+    unsigned *d_stg_counter = nullptr; // [0] tile counter, [1] length of the exact list, then (at byte 16) the row of 3 * kMaxPhase fixed-point sums
     DevBuf stg_exact;           // the exact list
+    TetArgs stg_args;           // arguments of the staged launches of the running pass (for tet_exact_list_kernel at its end)
+    int stg_list_kernel = -1;   // which instantiation works the list off: (want_sq << 1 | per_tet), -1: no staged launch in this pass
+    bool stg_counters_dirty = true; // tile counter / list length may be non-zero (first use, or a pass that did not reach its finalize)
     int stg_state = 0;          // 0 not tried, 1 ready, -1 unavailable
     int stg_slot_bytes = 24 * 1024, stg_slots = 8;
     double stg_scale[3] = {1.0, 1.0, 1.0};
@@ -94,6 +97,7 @@ struct dscgpu_ctx {
     bool comm_ipc[8] = {false, false, false, false, false, false, false, false}; // mapped with cudaIpcOpenMemHandle (to be closed)
     int comm_rank = 0, comm_world = 0;
     unsigned comm_cap_rows = 0;
+    size_t comm_snap_bytes = 0; // snapshot region of the window (sharded commit), 0: none
     bool comm_connected = false;
     uint32_t upd_n_pos = 0, upd_n_tet = 0, upd_n_faces = 0; // the staged update (dscgpu_update_staging_get)
     bool upd_keys = false, upd_staged = false;
@@ -111,6 +115,7 @@ struct dscgpu_ctx {
     bool staging_valid = false;
 
     uint32_t tet_b = 0, tet_e = 0, face_b = 0, face_e = 0, node_b = 0, node_e = 0;
+    bool partition_stale = false; // the face list changed size under a partition: the ranges must be set again before the next evaluation
 
     DevBuf partials, sums, mean, forces, counters;
     DevBuf o_total, o_vol, o_mean, o_energy, o_variation, o_hash, o_nsamp;
@@ -155,6 +160,14 @@ struct dscgpu_ctx {
             ctx->err = "dscgpu_set_snapshot has not been called";    \
             return DSCGPU_ERR_NO_SNAPSHOT;                           \
         }                                                            \
+    } while (0)
+
+#define NEED_PARTITION()                                                                                                              \
+    do {                                                                                                                              \
+        if (ctx->partition_stale) {                                                                                                   \
+            ctx->err = "the interface-face list changed size under a partition: call dscgpu_set_partition before the next evaluation"; \
+            return DSCGPU_ERR_ARG;                                                                                                    \
+        }                                                                                                                             \
     } while (0)
 
 namespace {
@@ -295,7 +308,7 @@ int ensure_staged(dscgpu_ctx *ctx)
                 memcpy(&maps[((size_t)u * kStgMaxRows + r) * kStgMaxSlices + sl], &tm, sizeof(CUtensorMap));
             }
     if (!ctx->d_stg_maps) CK(cudaMalloc(&ctx->d_stg_maps, maps.size() * sizeof(TmapBlob)));
-    if (!ctx->d_stg_counter) CK(cudaMalloc(&ctx->d_stg_counter, 2 * sizeof(unsigned)));
+    if (!ctx->d_stg_counter) CK(cudaMalloc(&ctx->d_stg_counter, 16 + 3 * kMaxPhase * sizeof(unsigned long long)));
     CK(cudaMemcpy(ctx->d_stg_maps, maps.data(), maps.size() * sizeof(TmapBlob), cudaMemcpyHostToDevice));
     // fixed point: per-label sums stay below 64 x (voxels of the volume) x (largest intensity) -- tets cover the volume once, a
     // DSC mesh pads it by one edge -- and must stay below 2^62; tet_finalize_fixed_kernel reports a sum that did not
@@ -312,7 +325,6 @@ int ensure_staged(dscgpu_ctx *ctx)
 template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S> int launch_staged_t(dscgpu_ctx *ctx, TetArgs &a)
 {
     auto kern = tet_staged_kernel<VoxT, WANT_SQ, PER_TET, F32S>;
-    auto kern2 = tet_exact_list_kernel<VoxT, WANT_SQ, PER_TET, F32S>;
     const int smem = ctx->stg_slots * (ctx->stg_slot_bytes + kStgRecBytes);
     static bool attr_set = false; // per instantiation
     static int attr_dev = -1;
@@ -325,17 +337,9 @@ template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S> int launch_stage
     unsigned grid = (unsigned)ctx->num_sms;
     const unsigned need = (n_tiles + kStgProd - 1) / kStgProd;
     if (need < grid) grid = need ? need : 1;
-    // the exact list is worked off by warps, one tet each: enough of them to hide its dependent loads, no more than the list can feed
-    unsigned grid2 = (unsigned)ctx->num_sms * 4;
-    const unsigned need2 = (n_work / 64 + 7) / 8;
-    if (need2 < grid2) grid2 = need2 ? need2 : 1;
-    if (ctx->tet_grid + grid + grid2 > kMaxPartialRows) { ctx->err = "too many partial rows"; return DSCGPU_ERR_ARG; }
-    {   // growing the list buffer is not possible while the stream is being captured; sized per snapshot by ensure_scratch
-        if (ctx->stg_exact.cap < (size_t)n_work * sizeof(unsigned)) { ctx->err = "exact-list buffer smaller than the tet range"; return DSCGPU_ERR_ARG; }
-    }
-    a.stg_partials = ctx->partials.as<long long>() + (size_t)ctx->tet_grid * 3 * kMaxPhase;
-    a.stg_partials2 = a.stg_partials + (size_t)grid * 3 * kMaxPhase;
-    ctx->tet_grid += (int)(grid + grid2);
+    // (the list buffer is sized with the snapshot: it cannot grow while the stream is being captured)
+    if (ctx->stg_exact.cap < (size_t)ctx->n_tets * sizeof(unsigned)) { ctx->err = "exact-list buffer smaller than the snapshot"; return DSCGPU_ERR_ARG; }
+    a.stg_acc = reinterpret_cast<unsigned long long *>(ctx->d_stg_counter + 4);
     ctx->tet_rows_fixed = true;
     a.stg_maps = ctx->d_stg_maps;
     a.stg_slot_bytes = ctx->stg_slot_bytes;
@@ -343,14 +347,51 @@ template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S> int launch_stage
     a.stg_counter = ctx->d_stg_counter;
     a.stg_exact_count = ctx->d_stg_counter + 1;
     a.stg_exact_list = ctx->stg_exact.as<unsigned>();
+    // tiles per claim: a chunk is also the grain of the tail, so launches with few tiles per producer warp claim them one at a time
+    const unsigned per_warp = n_tiles / (grid * kStgProd);
+    a.stg_chunk = per_warp >= 64 ? kStgMaxChunk : (per_warp >= 24 ? 2 : 1);
     for (int k = 0; k < 3; k++) a.stg_scale[k] = ctx->stg_scale[k];
-    CK(cudaMemsetAsync(ctx->d_stg_counter, 0, 2 * sizeof(unsigned), ctx->stream));
+    // the counters are zero after the finalize of the previous pass; a second range launch of one pass restarts the tile counter only
+    if (ctx->stg_counters_dirty) CK(cudaMemsetAsync(ctx->d_stg_counter, 0, 16 + 3 * kMaxPhase * sizeof(unsigned long long), ctx->stream));
+    else if (ctx->stg_list_kernel >= 0) CK(cudaMemsetAsync(ctx->d_stg_counter, 0, sizeof(unsigned), ctx->stream));
+    ctx->stg_counters_dirty = false;
     kern<<<grid, (kStgProd + kStgCons) * 32, smem, ctx->stream>>>(a);
+    ctx->launches++;
     CK(cudaGetLastError());
-    kern2<<<grid2, 256, 0, ctx->stream>>>(a);
-    ctx->launches += 2;
-    CK(cudaGetLastError());
+    ctx->stg_args = a;
+    ctx->stg_list_kernel = (WANT_SQ ? 2 : 0) | (PER_TET ? 1 : 0);
     return DSCGPU_OK;
+}
+
+// end of a pass with staged launches: the tets they left to the exact path, one launch for the whole pass
+template <typename VoxT, bool F32S> int launch_exact_list_v(dscgpu_ctx *ctx)
+{
+    TetArgs &a = ctx->stg_args;
+    // worked off by warps, one tet each: enough of them to hide the dependent loads, no more than the list can be expected to feed
+    const unsigned n_work = ctx->tet_e - ctx->tet_b;
+    unsigned grid2 = (unsigned)ctx->num_sms * 4;
+    const unsigned need2 = (n_work / 64 + 7) / 8;
+    if (need2 < grid2) grid2 = need2 ? need2 : 1;
+    switch (ctx->stg_list_kernel) {
+    case 0: tet_exact_list_kernel<VoxT, false, false, F32S><<<grid2, 256, 0, ctx->stream>>>(a); break;
+    case 1: tet_exact_list_kernel<VoxT, false, true, F32S><<<grid2, 256, 0, ctx->stream>>>(a); break;
+    case 2: tet_exact_list_kernel<VoxT, true, false, F32S><<<grid2, 256, 0, ctx->stream>>>(a); break;
+    default: tet_exact_list_kernel<VoxT, true, true, F32S><<<grid2, 256, 0, ctx->stream>>>(a); break;
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->stg_list_kernel = -1;
+    return DSCGPU_OK;
+}
+
+int launch_exact_list(dscgpu_ctx *ctx)
+{
+    if (ctx->stg_list_kernel < 0) return DSCGPU_OK;
+    switch (ctx->dtype) {
+    case DSCGPU_U8: return launch_exact_list_v<unsigned char, false>(ctx);
+    case DSCGPU_U16: return launch_exact_list_v<unsigned short, false>(ctx);
+    default: return launch_exact_list_v<float, true>(ctx);
+    }
 }
 
 template <typename VoxT, bool F32S> int launch_staged_v(dscgpu_ctx *ctx, TetArgs &a)
@@ -424,7 +465,7 @@ int launch_tet(dscgpu_ctx *ctx, TetArgs &a, bool with_c)
     if ((ctx->tet_variant & 131072) && !with_c && fits32) { // staged kernel: lane per tet, voxel boxes in shared memory by TMA
         int rs = ensure_staged(ctx);
         if (rs) return rs;
-        if (ctx->stg_state == 1 && (ctx->tet_grid == 0 || ctx->tet_rows_fixed)) return launch_staged(ctx, a);
+        if (ctx->stg_state == 1 && (ctx->tet_grid == 0 || ctx->tet_rows_fixed)) return launch_staged(ctx, a); // (a pass is all double rows or all fixed point)
     }
     if ((ctx->tet_variant & 128) && !with_c && fits32) { // warp-level two-phase kernel with lattice coordinates
         a.lean = (ctx->tet_variant & 16384) ? 1 : 0;
@@ -480,16 +521,19 @@ int tet_pass_begin(dscgpu_ctx *ctx)
 {
     ctx->tet_grid = 0;
     ctx->tet_rows_fixed = false;
+    if (ctx->stg_list_kernel >= 0) { ctx->stg_list_kernel = -1; ctx->stg_counters_dirty = true; } // a pass that never reached its finalize
     CK(cudaMemsetAsync(ctr(ctx, 0), 0, sizeof(unsigned long long), ctx->stream));
     return DSCGPU_OK;
 }
 
 int tet_pass_finish(dscgpu_ctx *ctx, int nb_phase, double *d_sums_out, double *d_mean_out)
 {
+    int rl = launch_exact_list(ctx); // (no-op when the caller has launched it inside its timer scope)
+    if (rl) return rl;
     TimerScope ts(ctx, DSCGPU_T_PHASE_FINAL);
     if (ctx->tet_rows_fixed)
-        tet_finalize_fixed_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<long long>(), ctx->tet_grid, nb_phase, ctx->stg_scale[0], ctx->stg_scale[1], ctx->stg_scale[2],
-                                                                              d_sums_out, d_mean_out, ctx->d_vol_flags ? ctx->d_vol_flags + 2 : nullptr);
+        tet_finalize_fixed_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<unsigned long long *>(ctx->d_stg_counter + 4), nb_phase, ctx->stg_scale[0], ctx->stg_scale[1],
+                                                             ctx->stg_scale[2], d_sums_out, d_mean_out, ctx->d_vol_flags ? ctx->d_vol_flags + 2 : nullptr, ctx->d_stg_counter);
     else
         tet_finalize_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums_out, d_mean_out);
     ctx->launches++;
@@ -508,6 +552,8 @@ int run_tet_pass(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const
     {
         TimerScope ts(ctx, DSCGPU_T_TET);
         r = tet_pass_range(ctx, nb_phase, include_bound, nc, c, o, ctx->tet_b, ctx->tet_e, want_sq);
+        if (r) return r;
+        r = launch_exact_list(ctx);
         if (r) return r;
     }
     return tet_pass_finish(ctx, nb_phase, d_sums_out, d_mean_out);
@@ -809,6 +855,7 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     CK(cudaEventRecord(ctx->ev_chunk[16], cs));
     ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
+    ctx->partition_stale = false;
     ctx->has_snapshot = true;
     ctx->geom_async = false;
     ctx->init_means_valid = false;
@@ -860,6 +907,8 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     }
     r = build_csr_device(ctx);
     if (r) return r;
+    ctx->staging_valid = false; // uploaded (see commit_snapshot_impl)
+    ctx->partition_stale = false;
     return tet_pass_finish(ctx, nb_phase, d_sums_out, d_mean_out);
 }
 
@@ -872,17 +921,8 @@ CommView comm_view(const dscgpu_ctx *ctx)
     CommView c;
     for (int k = 0; k < kCommMaxWorld; k++) c.win[k] = ctx->comm_win[k];
     c.rank = ctx->comm_rank; c.world = ctx->comm_world; c.cap_rows = ctx->comm_cap_rows;
+    c.snap_off = comm_snapshot_offset(ctx->comm_world, ctx->comm_cap_rows);
     return c;
-}
-
-template <typename VoxT> int launch_force_rows_t(dscgpu_ctx *ctx, const ForceRowsArgs &a)
-{
-    const unsigned n = a.end - a.begin;
-    if (n == 0) return DSCGPU_OK;
-    force_scatter_rows_kernel<VoxT><<<(n + 127) / 128, 128, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return DSCGPU_OK;
 }
 
 } // namespace
@@ -1111,9 +1151,23 @@ int dscgpu_snapshot_staging_get(dscgpu_ctx *ctx, uint32_t n_nodes, uint32_t n_te
     return DSCGPU_OK;
 }
 
+static int commit_snapshot_impl(dscgpu_ctx *ctx, bool sharded);
+
 int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
+    return commit_snapshot_impl(ctx, false);
+}
+
+int dscgpu_commit_snapshot_sharded(dscgpu_ctx *ctx)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(ctx->comm_connected && ctx->comm_snap_bytes, "dscgpu_comm_create_ex with a snapshot region, and dscgpu_comm_connect, first");
+    return commit_snapshot_impl(ctx, true);
+}
+
+static int commit_snapshot_impl(dscgpu_ctx *ctx, bool sharded)
+{
     ARG(ctx->staging_valid, "dscgpu_snapshot_staging_get was not called");
     const uint32_t nn = ctx->st_nodes, nt = ctx->st_tets, nf = ctx->st_faces;
     ARG(nf < (1u << 30), "too many interface faces");
@@ -1129,7 +1183,38 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
     CK(ctx->face_isb.ensure((size_t)nf));
     CK(ctx->node_off.ensure(((size_t)nn + 1) * 4));
     CK(ctx->node_inc.ensure((size_t)nf * 12));
-    {
+    if (sharded) {
+        // rank r sends bytes [T r / W, T (r+1) / W) of the flattened snapshot (six arrays at 256-byte aligned offsets) over PCIe into its
+        // window; the slices travel to the peers over NVLink (dsc_comm.cuh); the assembled region is copied into the snapshot buffers
+        TimerScope ts(ctx, DSCGPU_T_H2D);
+        cudaStream_t st = ctx->stream;
+        const size_t len[6] = {(size_t)nn * 32, (size_t)nt * 16, (size_t)nt * 4, (size_t)nf * 12, (size_t)nf * 8, (size_t)nf};
+        const void *hsrc[6] = {ctx->h_pos4.p, ctx->h_tet_nodes.p, ctx->h_tet_label.p, ctx->h_face_nodes.p, ctx->h_face_tets.p, ctx->h_face_isb.p};
+        void *ddst[6] = {ctx->pos4.p, ctx->tet_nodes.p, ctx->tet_label.p, ctx->face_nodes.p, ctx->face_tets.p, ctx->face_isb.p};
+        size_t off[7];
+        off[0] = 0;
+        for (int k = 0; k < 6; k++) off[k + 1] = (off[k] + len[k] + 255) & ~(size_t)255;
+        const size_t T = off[6];
+        ARG(T <= ctx->comm_snap_bytes, "the snapshot region of the exchange window is too small for this snapshot (dscgpu_comm_create_ex)");
+        const int W = ctx->comm_world, R = ctx->comm_rank;
+        const size_t b = (T / 256 * R / W) * 256, e = R == W - 1 ? T : (T / 256 * (R + 1) / W) * 256;
+        unsigned char *region = ctx->comm_win[R] + comm_snapshot_offset(W, ctx->comm_cap_rows);
+        for (int k = 0; k < 6; k++) { // the part of array k inside [b, e)
+            const size_t lo = std::max(b, off[k]), hi = std::min(e, off[k] + len[k]);
+            if (hi > lo) CK(cudaMemcpyAsync(region + lo, static_cast<const unsigned char *>(hsrc[k]) + (lo - off[k]), hi - lo, cudaMemcpyHostToDevice, st));
+        }
+        if (W > 1) {
+            unsigned grid = (unsigned)std::min<size_t>(((e - b) / 16 + 255) / 256 + 1, (size_t)ctx->num_sms * 2);
+            comm_snapshot_push_kernel<<<grid, 256, 0, st>>>(comm_view(ctx), b, e);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        SnapshotParts parts;
+        for (int k = 0; k < 6; k++) { parts.dst[k] = static_cast<unsigned char *>(ddst[k]); parts.off[k] = off[k]; parts.len[k] = len[k]; }
+        comm_snapshot_gather_kernel<<<(unsigned)std::min<size_t>((T / 16 + 255) / 256 + 1, (size_t)ctx->num_sms * 4), 256, 0, st>>>(comm_view(ctx), parts);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    } else {
         TimerScope ts(ctx, DSCGPU_T_H2D);
         cudaStream_t s = ctx->stream;
         if (nn) CK(cudaMemcpyAsync(ctx->pos4.p, ctx->h_pos4.p, (size_t)nn * 32, cudaMemcpyHostToDevice, s));
@@ -1168,6 +1253,7 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
         ctx->validation_pending = true;
     }
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
+    ctx->partition_stale = false;
     ctx->has_snapshot = true;
     ctx->geom_async = false;
     ctx->init_means_valid = false;
@@ -1192,6 +1278,7 @@ int dscgpu_commit_snapshot(dscgpu_ctx *ctx)
         }
         ctx->auto_lanes = (cnt && acc / cnt >= 200.0) ? 32 : 8;
     }
+    ctx->staging_valid = false; // uploaded: dscgpu_image_force_eval(ctx, NULL, ...) evaluates the resident snapshot until the staging is taken again
     return DSCGPU_OK;
 }
 
@@ -1280,8 +1367,12 @@ int dscgpu_update_commit(dscgpu_ctx *ctx, int replace_faces)
             CK(cudaMemcpyAsync(ctx->face_tets.p, h + L.ft, (size_t)nf * 8, cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemcpyAsync(ctx->face_isb.p, h + L.fb, (size_t)nf, cudaMemcpyHostToDevice, ctx->stream));
         }
+        // the partition is one unit (tets, faces, nodes): the full ranges follow the new face count; under a real partition an unchanged
+        // face count keeps the ranges, a changed one makes them stale -- evaluating all faces on every rank would add the forces world times
+        const bool whole = ctx->tet_b == 0 && ctx->tet_e == ctx->n_tets && ctx->node_b == 0 && ctx->node_e == ctx->n_nodes && ctx->face_b == 0 && ctx->face_e == ctx->n_faces;
+        if (whole) { ctx->face_b = 0; ctx->face_e = nf; }
+        else if (nf != ctx->n_faces) { ctx->partition_stale = true; ctx->face_b = ctx->face_e = 0; }
         ctx->n_faces = nf;
-        ctx->face_b = 0; ctx->face_e = nf;
         int rs = build_csr_device(ctx);
         if (rs) return rs;
         if (nf) {
@@ -1360,6 +1451,7 @@ int dscgpu_set_partition(dscgpu_ctx *ctx, uint32_t tb, uint32_t te, uint32_t fb,
     if (!ctx->has_snapshot) { ctx->err = "no snapshot"; return DSCGPU_ERR_NO_SNAPSHOT; }
     ARG(tb <= te && te <= ctx->n_tets && fb <= fe && fe <= ctx->n_faces && nb <= ne && ne <= ctx->n_nodes, "partition out of range");
     ctx->tet_b = tb; ctx->tet_e = te; ctx->face_b = fb; ctx->face_e = fe; ctx->node_b = nb; ctx->node_e = ne;
+    ctx->partition_stale = false;
     return DSCGPU_OK;
 }
 
@@ -1633,6 +1725,7 @@ int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uin
 int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mode, double *forces)
 {
     NEED_SNAPSHOT();
+    NEED_PARTITION();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && mean && forces, "bad arguments");
     ARG(mode == DSCGPU_FORCE_GATHER || mode == DSCGPU_FORCE_ATOMIC, "unknown force mode");
     size_t bytes = sizeof(double) * 3 * (size_t)ctx->n_nodes;
@@ -1753,6 +1846,7 @@ int dscgpu_means_from_sums_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_su
 int dscgpu_face_geometry_async(dscgpu_ctx *ctx)
 {
     NEED_SNAPSHOT();
+    NEED_PARTITION();
     // fork: the side stream picks up where the main stream is now (snapshot in place), runs the kernel, and the next
     // gather-mode force call joins it; both edges are events, so the pattern can be captured in a CUDA graph
     CK(cudaEventRecord(ctx->ev_chunk[18], ctx->stream));
@@ -1767,6 +1861,7 @@ int dscgpu_face_geometry_async(dscgpu_ctx *ctx)
 int dscgpu_face_forces_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, double *d_forces)
 {
     NEED_SNAPSHOT();
+    NEED_PARTITION();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_mean && d_forces, "bad arguments");
     return run_forces(ctx, nb_phase, d_mean, mode, d_forces);
 }
@@ -1775,15 +1870,26 @@ int dscgpu_face_forces_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, 
 
 int dscgpu_comm_create(dscgpu_ctx *ctx, int rank, int world, uint32_t cap_rows, unsigned char handle_out[64])
 {
+    return dscgpu_comm_create_ex(ctx, rank, world, cap_rows, 0, handle_out);
+}
+
+int dscgpu_comm_create_ex(dscgpu_ctx *ctx, int rank, int world, uint32_t cap_rows, uint64_t snapshot_bytes, unsigned char handle_out[64])
+{
     if (!ctx) return DSCGPU_ERR_ARG;
     ARG(world >= 1 && world <= kCommMaxWorld && rank >= 0 && rank < world, "rank / world out of range (at most 8 ranks)");
     ARG(cap_rows > 0, "cap_rows must be positive");
     ARG(!ctx->comm_win[rank] && ctx->comm_world == 0, "the exchange window exists already");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    const size_t bytes = comm_window_bytes(world, cap_rows);
+    const size_t snap = ((size_t)snapshot_bytes + 255) & ~(size_t)255;
+    const size_t bytes = comm_window_bytes(world, cap_rows, snap);
     void *p = nullptr;
     CK(cudaMalloc(&p, bytes));
-    CK(cudaMemset(p, 0, bytes));
+    CK(cudaMemset(p, 0, comm_snapshot_offset(world, cap_rows)));
+    ctx->comm_snap_bytes = snap;
+    {   // scratch of the fused force exchange, both halves: barrier counters 0, touched range empty
+        const unsigned init[8] = {0u, 0u, 0xffffffffu, 0u, 0u, 0u, 0xffffffffu, 0u};
+        CK(cudaMemcpy(static_cast<unsigned char *>(p) + kCommLocal, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&ctx->comm_rows, 3 * (size_t)cap_rows * sizeof(double)));
     CK(cudaMemset(ctx->comm_rows, 0, 3 * (size_t)cap_rows * sizeof(double)));
     ctx->comm_win[rank] = static_cast<unsigned char *>(p);
@@ -1840,6 +1946,7 @@ int dscgpu_comm_error(dscgpu_ctx *ctx)
 int dscgpu_tet_phase_sums_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums, double *d_mean)
 {
     NEED_SNAPSHOT();
+    NEED_PARTITION();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_sums, "bad arguments");
     ARG(ctx->comm_connected, "dscgpu_comm_create / dscgpu_comm_connect first");
     int r = tet_pass_begin(ctx);
@@ -1849,13 +1956,18 @@ int dscgpu_tet_phase_sums_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, double *d
         TimerScope ts(ctx, DSCGPU_T_TET);
         r = tet_pass_range(ctx, nb_phase, 0, 0, nullptr, none, ctx->tet_b, ctx->tet_e, ctx->hot_want_sq);
         if (r) return r;
+        r = launch_exact_list(ctx);
+        if (r) return r;
     }
+    // the mean-independent half of the force pass starts on the side stream now: it runs while this rank waits for the sums of the others
+    r = dscgpu_face_geometry_async(ctx);
+    if (r) return r;
     TimerScope ts(ctx, DSCGPU_T_PHASE_FINAL);
     if (ctx->tet_rows_fixed)
-        comm_phase_allreduce_kernel<true><<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(comm_view(ctx), ctx->partials.p, ctx->tet_grid, nb_phase, ctx->stg_scale[0], ctx->stg_scale[1],
-                                                                                     ctx->stg_scale[2], d_sums, d_mean);
+        comm_phase_allreduce_kernel<true><<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(comm_view(ctx), ctx->d_stg_counter + 4, 1, nb_phase, ctx->stg_scale[0], ctx->stg_scale[1],
+                                                                                     ctx->stg_scale[2], d_sums, d_mean, ctx->d_stg_counter);
     else
-        comm_phase_allreduce_kernel<false><<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(comm_view(ctx), ctx->partials.p, ctx->tet_grid, nb_phase, 1.0, 1.0, 1.0, d_sums, d_mean);
+        comm_phase_allreduce_kernel<false><<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(comm_view(ctx), ctx->partials.p, ctx->tet_grid, nb_phase, 1.0, 1.0, 1.0, d_sums, d_mean, nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     return DSCGPU_OK;
@@ -1864,37 +1976,44 @@ int dscgpu_tet_phase_sums_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, double *d
 int dscgpu_face_forces_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, double *d_forces)
 {
     NEED_SNAPSHOT();
+    NEED_PARTITION();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_mean && d_forces, "bad arguments");
     ARG(ctx->comm_connected, "dscgpu_comm_create / dscgpu_comm_connect first");
     ARG(ctx->n_nodes <= ctx->comm_cap_rows, "the exchange window is too small for this snapshot (cap_rows < n_nodes_buffer)");
     TimerScope ts(ctx, DSCGPU_T_FORCE);
-    ForceRowsArgs a;
-    a.vol = vol_view(ctx);
+    // mean-independent half (normals, areas, trilinear samples of this rank's faces): it may already be running on the side stream,
+    // started before the sums exchange (dscgpu_face_geometry_async)
+    if (ctx->geom_async) {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[19], 0));
+        ctx->geom_async = false;
+    } else {
+        int rg = launch_force_geom(ctx, ctx->stream);
+        if (rg) return rg;
+    }
+    ForceFusedArgs a;
+    a.c = comm_view(ctx);
     a.mesh = mesh_view(ctx);
+    a.fgeo = ctx->fgeo.as<double>(); a.flab = ctx->flab.as<int>(); a.fint = ctx->fint.as<double>(); a.fset = ctx->fset.as<signed char>();
     a.nb_phase = nb_phase;
     a.mean = d_mean;
     a.apos = ctx->csr_apos.as<unsigned>();
     a.rows = ctx->comm_rows;
     a.begin = ctx->face_b; a.end = ctx->face_e;
-    int r;
-    switch (ctx->dtype) {
-    case DSCGPU_U8: r = launch_force_rows_t<unsigned char>(ctx, a); break;
-    case DSCGPU_U16: r = launch_force_rows_t<unsigned short>(ctx, a); break;
-    case DSCGPU_F32: r = launch_force_rows_t<float>(ctx, a); break;
-    default: r = launch_force_rows_t<double>(ctx, a); break;
+    a.active_nodes = ctx->node_active.as<unsigned>();
+    a.n_active_ptr = reinterpret_cast<const unsigned *>(ctr(ctx, 5));
+    a.forces = d_forces;
+    a.n_nodes = ctx->n_nodes;
+    // one launch: scatter, push of the touched rows, wait, ordered sum.  The grid spins on its own barrier: it must be co-resident
+    static int occ = 0;
+    if (occ == 0) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, comm_force_fused_kernel, 256, 0));
+        if (occ < 1) occ = 1;
+        if (occ > 2) occ = 2;
     }
-    if (r) return r;
-    // rows of nodes without interface faces are never written by the exchange kernel: they must read as zero
-    CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
-    const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * ctx->n_faces);
-    const unsigned *n_active = reinterpret_cast<const unsigned *>(ctr(ctx, 5));
-    unsigned grid = (3 * std::max<unsigned>(max_active, 1u) + 255) / 256;
-    if (grid > (unsigned)ctx->num_sms * 4) grid = (unsigned)ctx->num_sms * 4;
-    comm_force_push_kernel<<<grid, 256, 0, ctx->stream>>>(comm_view(ctx), ctx->comm_rows, n_active);
-    ctx->launches++;
-    grid = (std::max<unsigned>(max_active, 1u) + 255) / 256;
-    if (grid > (unsigned)ctx->num_sms * 4) grid = (unsigned)ctx->num_sms * 4;
-    comm_force_reduce_kernel<<<grid, 256, 0, ctx->stream>>>(comm_view(ctx), ctx->node_active.as<unsigned>(), n_active, d_forces);
+    unsigned grid = (unsigned)(ctx->num_sms * occ);
+    const unsigned want = (std::max<unsigned>(std::max<unsigned>(a.end - a.begin, ctx->n_nodes / 8), 256u) + 255) / 256;
+    if (want < grid) grid = want;
+    comm_force_fused_kernel<<<grid, 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return DSCGPU_OK;

@@ -54,11 +54,12 @@ def evaluate(phase_sums_fn, forces_fn, nb_phase, all_reduce):
     return mean, forces
 
 
-def connect_peers(seg, rank, world, cap_rows, all_gather_object):
+def connect_peers(seg, rank, world, cap_rows, all_gather_object, snapshot_bytes=0):
     """Sets up the exchange over NVLink peer memory (csrc/dsc_comm.cuh) for `seg` (a SegmentFunction): creates this rank's
     window, exchanges the CUDA IPC handles with `all_gather_object(obj) -> list of every rank's obj in rank order`
-    (e.g. a wrapper of torch.distributed.all_gather_object) and maps the peers' windows.  Every rank must call it."""
-    handle = seg.comm_create(rank, world, cap_rows)
+    (e.g. a wrapper of torch.distributed.all_gather_object) and maps the peers' windows.  Every rank must call it.
+    snapshot_bytes > 0 adds the region of the sharded snapshot commit (SegmentFunction.commit_snapshot_sharded)."""
+    handle = seg.comm_create(rank, world, cap_rows, snapshot_bytes) if snapshot_bytes else seg.comm_create(rank, world, cap_rows)
     handles = all_gather_object(handle)
     if len(handles) != world or any(len(h) != 64 for h in handles):
         raise ValueError("all_gather_object must return one 64-byte handle per rank")

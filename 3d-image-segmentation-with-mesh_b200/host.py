@@ -473,12 +473,18 @@ class SegmentFunction:
                                                          C.c_void_p(d_forces_ptr)), "dscgpu_face_forces_dev")
 
     # -- exchange over NVLink peer memory (csrc/dsc_comm.cuh) -------------------------------------------------------
-    def comm_create(self, rank, world, cap_rows=None):
-        """Allocates this rank's exchange window (snapshots of up to cap_rows nodes) and returns its CUDA IPC handle (64 bytes)."""
+    def comm_create(self, rank, world, cap_rows=None, snapshot_bytes=0):
+        """Allocates this rank's exchange window (snapshots of up to cap_rows nodes; snapshot_bytes > 0 adds the region the sharded
+        snapshot commit assembles in) and returns its CUDA IPC handle (64 bytes)."""
         cap = int(cap_rows if cap_rows is not None else max(self.n_nodes_buffer, 1))
         h = (C.c_ubyte * 64)()
-        self._img._check(self.lib.dscgpu_comm_create(self._img._ctx, C.c_int(rank), C.c_int(world), C.c_uint32(cap), h), "dscgpu_comm_create")
+        self._img._check(self.lib.dscgpu_comm_create_ex(self._img._ctx, C.c_int(rank), C.c_int(world), C.c_uint32(cap), C.c_uint64(int(snapshot_bytes)), h),
+                         "dscgpu_comm_create_ex")
         return bytes(h)
+
+    def commit_snapshot_sharded(self):
+        """Collective form of commit_snapshot: every rank uploads 1/world of the staged bytes, the rest arrives over NVLink."""
+        self._img._check(self.lib.dscgpu_commit_snapshot_sharded(self._img._ctx), "dscgpu_commit_snapshot_sharded")
 
     def comm_connect(self, handles):
         """handles: the 64-byte IPC handles of all ranks, in rank order (exchanged by the caller)."""

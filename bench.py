@@ -330,7 +330,7 @@ def main_b200(args):
             out = [None] * world
             dist.all_gather_object(out, h)
             return out
-        pkg.distributed.connect_peers(seg, rank, world, n_nodes, gather_handles)
+        pkg.distributed.connect_peers(seg, rank, world, n_nodes, gather_handles, snapshot_bytes=32 * n_nodes + 20 * n_tets + 21 * n_faces + 4096)
         dist.barrier()  # every window exists and is mapped before the first exchange kernel runs
     d_sums = torch.zeros(3 * P, dtype=torch.float64, device=dev)
     d_mean = torch.zeros(P, dtype=torch.float64, device=dev)
@@ -535,7 +535,10 @@ def main_b200(args):
             seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode, want_forces="pinned")
         else:
             seg.staging(n_nodes, n_tets, n_faces)
-            seg.commit_snapshot()
+            if p2p:  # every rank sends 1/world of the snapshot over PCIe, the shares cross NVLink (dscgpu_commit_snapshot_sharded)
+                seg.commit_snapshot_sharded()
+            else:
+                seg.commit_snapshot()
             seg.set_partition(tet_range, rng(n_faces), rng(n_nodes))
             step_device()
             pinned_forces.copy_(d_forces, non_blocking=True)

@@ -277,6 +277,13 @@ int dscgpu_face_forces_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, 
  *                        of rank k's context
  *   dscgpu_comm_error    synchronises and reports a timed-out exchange (a peer that never arrived within 2 s) */
 int dscgpu_comm_create(dscgpu_ctx *ctx, int rank, int world, uint32_t cap_rows, unsigned char handle_out[64]);
+/* The same with a snapshot region of snapshot_bytes in the window, for dscgpu_commit_snapshot_sharded: size it for the largest
+ * snapshot, 32 n_nodes_buffer + 20 n_tets + 21 n_faces + 2 KB. */
+int dscgpu_comm_create_ex(dscgpu_ctx *ctx, int rank, int world, uint32_t cap_rows, uint64_t snapshot_bytes, unsigned char handle_out[64]);
+/* dscgpu_commit_snapshot when every rank holds the same snapshot in its pinned staging arrays (dscgpu_snapshot_staging_get): rank r
+ * sends only its 1/world share of the bytes over PCIe, the shares travel to the peers' windows over NVLink, and every rank ends
+ * up with the whole snapshot.  Collective: every rank must call it, with identical staging contents.  Resets the partition. */
+int dscgpu_commit_snapshot_sharded(dscgpu_ctx *ctx);
 int dscgpu_comm_connect(dscgpu_ctx *ctx, const unsigned char *handles);
 int dscgpu_comm_connect_local(dscgpu_ctx *ctx, void *const *windows);
 void *dscgpu_comm_window_dev(dscgpu_ctx *ctx);

@@ -36,6 +36,11 @@ def main():
 
     snap = syn.build_case(vol, edge, P, cfg["thresholds"], tet_mean, jitter=0.2, seed=5)
     seg.set_snapshot(snap)
+    part = int(os.environ.get("PART", "1"))
+    if part > 1:  # what one of `part` ranks sees: a contiguous 1/part of the tets (from the middle of the mesh) and of the faces
+        nt, nf, nn = len(snap["tet_nodes"]), len(snap["face_nodes"]), len(snap["pos"])
+        r = part // 2
+        seg.set_partition((nt * r // part, nt * (r + 1) // part), (nf * r // part, nf * (r + 1) // part), (0, nn))
     seg.enable_timers(True)
     if what == "hot":  # the instantiation of the per-iteration hot path: no per-tet outputs, no second moment
         import torch

@@ -1434,6 +1434,8 @@ struct RayArgs {
     unsigned *ray_offset;  // exclusive scan of ray_count
     unsigned *ray_cursor;  // zeroed before fill
     uint2 *hits;           // (face index, packed hit)
+    unsigned hits_cap;     // entries the hit buffer holds (FILL): hits beyond it are dropped and bit 1 of *overflow is raised
+    int *overflow;
 };
 
 template <bool FILL> __global__ void __launch_bounds__(128) zray_raster_kernel(const RayArgs a)
@@ -1478,15 +1480,17 @@ template <bool FILL> __global__ void __launch_bounds__(128) zray_raster_kernel(c
                 if (phase0 >= 0 && phase0 < a.nb_phase) {
                     const size_t r = (size_t)phase0 * XY + col;
                     if (FILL) {
-                        const unsigned slot = atomicAdd(a.ray_cursor + r, 1u);
-                        a.hits[a.ray_offset[r] + slot] = make_uint2(f, (unsigned)((zz << 1) | (in_1 ? 0 : 1)));
+                        const unsigned slot = a.ray_offset[r] + atomicAdd(a.ray_cursor + r, 1u);
+                        if (slot < a.hits_cap) a.hits[slot] = make_uint2(f, (unsigned)((zz << 1) | (in_1 ? 0 : 1)));
+                        else atomicOr(a.overflow, 2);
                     } else atomicAdd(a.ray_count + r, 1u);
                 }
                 if (phase1 >= 0 && phase1 < a.nb_phase) {
                     const size_t r = (size_t)phase1 * XY + col;
                     if (FILL) {
-                        const unsigned slot = atomicAdd(a.ray_cursor + r, 1u);
-                        a.hits[a.ray_offset[r] + slot] = make_uint2(f, (unsigned)((zz << 1) | (in_1 ? 1 : 0)));
+                        const unsigned slot = a.ray_offset[r] + atomicAdd(a.ray_cursor + r, 1u);
+                        if (slot < a.hits_cap) a.hits[slot] = make_uint2(f, (unsigned)((zz << 1) | (in_1 ? 1 : 0)));
+                        else atomicOr(a.overflow, 2);
                     } else atomicAdd(a.ray_count + r, 1u);
                 }
             }
@@ -1586,7 +1590,8 @@ struct ResolveArgs {
     double c[kMaxPhase];       // mode 1: phase means
     const unsigned *ray_count;
     const unsigned *ray_offset;
-    const uint2 *hits;
+    uint2 *hits;                 // rays with more than kMaxRayHits hits are sorted in place
+    unsigned hits_cap;
     unsigned col_begin, col_end; // column range of this partition
     double *partial_sum;         // [nb_phase][gridDim.x]
     long long *partial_cnt;      // [nb_phase][gridDim.x]
@@ -1605,40 +1610,51 @@ template <typename VoxT> __global__ void __launch_bounds__(128) zray_resolve_ker
     if (col < a.col_end) {
         const size_t r = (size_t)phase * XY + col;
         const unsigned n_hits = __ldg(a.ray_count + r);
-        if (n_hits > 1) { // rays with a single hit are ignored (:1701)
-            if (n_hits > (unsigned)kMaxRayHits) {
-                atomicExch(a.overflow, 1);
-            } else {
-                unsigned fidx[kMaxRayHits];
-                int h[kMaxRayHits];
-                const uint2 *src = a.hits + __ldg(a.ray_offset + r);
-                int n = (int)n_hits;
+        const unsigned off = __ldg(a.ray_offset + r);
+        if (n_hits > 1 && off + n_hits <= a.hits_cap) { // rays with a single hit are ignored (:1701); a ray past the buffer was not recorded (overflow bit 1 is up)
+            unsigned fidx[kMaxRayHits];
+            int hloc[kMaxRayHits];
+            uint2 *src = a.hits + off;
+            int n = (int)n_hits;
+            int *h = hloc;
+            if (n_hits <= (unsigned)kMaxRayHits) {
                 // restore the reference's push order = ascending face key (the fill order is arbitrary)
                 for (int i = 0; i < n; i++) {
                     const uint2 e = src[i];
                     int j = i - 1;
-                    while (j >= 0 && fidx[j] > e.x) { fidx[j + 1] = fidx[j]; h[j + 1] = h[j]; j--; }
-                    fidx[j + 1] = e.x; h[j + 1] = (int)e.y;
+                    while (j >= 0 && fidx[j] > e.x) { fidx[j + 1] = fidx[j]; hloc[j + 1] = hloc[j]; j--; }
+                    fidx[j + 1] = e.x; hloc[j + 1] = (int)e.y;
                 }
-                std_sort_hits(h, n);
-                n = erase_adjacent_duplicates(h, n);
-                if ((n & 1) == 0) { // odd rays are silently dropped (:1721, 1741)
-                    const int x = (int)(col % X), y = (int)(col / X);
-                    for (int j = 0; j < n / 2; j++) {
-                        int z1 = h[2 * j] >> 1, z2 = h[2 * j + 1] >> 1;
-                        if (z1 < 0) z1 = 0;
-                        if (z2 < z1) z2 = z1;
-                        cnt += z2 - z1;
-                        if (a.mode == 0) {
-                            int lo = z1, hi = z2; // image3d::sum_line_z clamps (image3d.cpp:193-201)
-                            if (hi >= Z) { hi = Z - 1; if (lo >= Z) lo = Z - 1; }
-                            sum += a.vol.sum_table[(size_t)hi * XY + col] - a.vol.sum_table[(size_t)lo * XY + col];
-                        } else {
-                            const double cc = a.c[phase];
-                            for (int k = z1 + 1; k < z2; k++) {
-                                const double d = fetch(vol, X, Y, Z, x, y, k) - cc;
-                                sum += d * d; // std::pow(., 2)
-                            }
+            } else {
+                // a ray through more interface faces than the local arrays hold (the reference has no limit): the same steps in place,
+                // on the ray's own stretch of the hit buffer -- slow, and rare
+                for (int i = 1; i < n; i++) {
+                    const uint2 e = src[i];
+                    int j = i - 1;
+                    while (j >= 0 && src[j].x > e.x) { src[j + 1] = src[j]; j--; }
+                    src[j + 1] = e;
+                }
+                h = reinterpret_cast<int *>(src);
+                for (int i = 0; i < n; i++) h[i] = (int)src[i].y; // entry i is read before words 2i, 2i+1 >= i are overwritten
+            }
+            std_sort_hits(h, n);
+            n = erase_adjacent_duplicates(h, n);
+            if ((n & 1) == 0) { // odd rays are silently dropped (:1721, 1741)
+                const int x = (int)(col % X), y = (int)(col / X);
+                for (int j = 0; j < n / 2; j++) {
+                    int z1 = h[2 * j] >> 1, z2 = h[2 * j + 1] >> 1;
+                    if (z1 < 0) z1 = 0;
+                    if (z2 < z1) z2 = z1;
+                    cnt += z2 - z1;
+                    if (a.mode == 0) {
+                        int lo = z1, hi = z2; // image3d::sum_line_z clamps (image3d.cpp:193-201)
+                        if (hi >= Z) { hi = Z - 1; if (lo >= Z) lo = Z - 1; }
+                        sum += a.vol.sum_table[(size_t)hi * XY + col] - a.vol.sum_table[(size_t)lo * XY + col];
+                    } else {
+                        const double cc = a.c[phase];
+                        for (int k = z1 + 1; k < z2; k++) {
+                            const double d = fetch(vol, X, Y, Z, x, y, k) - cc;
+                            sum += d * d; // std::pow(., 2)
                         }
                     }
                 }
@@ -1753,6 +1769,35 @@ __global__ void vertex_bound_kernel(MeshView m, unsigned char *vb)
 // thresholding (host: DEMO/otsu_multi.h), then label = 1 + lower_bound(thresholds, min((int)(mean*255), 255)) (:250-260).
 // Label-0 (boundary layer) tets are skipped by both (:167-168, :245-248).
 // =================================================================================================
+// Per-tet mean of the initialisation pass with the reference's own order of additions: get_tetra_intensity adds the sampled voxels one
+// after another in table order (DEMO/image3d.cpp:363-367), then total * v / n, then / v (:371, :381).  The histogram bin and the label
+// are truncations of that mean, so the sum must round like the reference's -- voxels of integer volumes (q / 255.0, q / 65535.0) do
+// not add exactly.  One thread per tet, sequential: the pass runs once per segmentation.
+template <typename VoxT>
+__global__ void __launch_bounds__(128) tet_mean_ordered_kernel(VolumeView vv, MeshView m, const double *__restrict__ tet_bary, double *__restrict__ tet_mean)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m.n_tets) return;
+    if (__ldg(m.tet_label + t) == 0) { tet_mean[t] = -1.0; return; }
+    const VoxT *__restrict__ vol = static_cast<const VoxT *>(vv.data);
+    const uint4 nd = __ldg(m.tet_nodes + t);
+    const V3 p0 = load_pos(m.pos4, nd.x), p1 = load_pos(m.pos4, nd.y), p2 = load_pos(m.pos4, nd.z), p3 = load_pos(m.pos4, nd.w);
+    const double v = tet_volume(p0, p1, p2, p3);
+    const int L = tet_level(v);
+    const int rows = (L + 1) * (L + 1) * (L + 1);
+    const double2 *__restrict__ tb = reinterpret_cast<const double2 *>(tet_bary) + 2 * (size_t)((L * (L + 1) / 2) * (L * (L + 1) / 2));
+    double total = 0;
+    for (int i = 0; i < rows; i++) {
+        const double2 b01 = __ldg(tb + 2 * i), b23 = __ldg(tb + 2 * i + 1);
+        const int ix = (int)(((p0.x * b01.x + p1.x * b01.y) + p2.x * b23.x) + p3.x * b23.y);
+        const int iy = (int)(((p0.y * b01.x + p1.y * b01.y) + p2.y * b23.x) + p3.y * b23.y);
+        const int iz = (int)(((p0.z * b01.x + p1.z * b01.y) + p2.z * b23.x) + p3.z * b23.y);
+        total += fetch(vol, vv.X, vv.Y, vv.Z, ix, iy, iz);
+    }
+    total = total * v / (double)rows;
+    tet_mean[t] = total / v;
+}
+
 __global__ void __launch_bounds__(256) init_hist_kernel(const int *__restrict__ tet_label, const double *__restrict__ tet_mean, unsigned n_tets, int *hist)
 {
     __shared__ int sh[256];
@@ -1879,6 +1924,103 @@ __global__ void sum_partials_kernel(const double *partials, int n, double *out)
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) r += shfl_xor_d(r, m);
     if (threadIdx.x == 0) *out = r;
+}
+
+// =================================================================================================
+// SURVEY 8(f) row 3, second half -- the non-topological part of segment_function::snapp_boundary (DEMO/segment_function.cpp:466-541)
+// with get_node_displacement (:581-584): the external and internal forces stay on the device until the destinations are formed.
+//   stage 1 (node_displacement_kernel): for every node with interface faces (is_interface() or is_crossing(), :475-476)
+//           dis = (F + alpha Fi) dt, destination = pos + dis; nodes of m_vertex_bound are aligned to the faces of the image domain
+//           (macro algin_pos, :59-65); node_displacement = destination - pos; the largest length over the free nodes and over the
+//           bound nodes (maxima: exact in any order).
+//   stage 2 (node_destination_kernel): scale = max_displacement / max_dis when max_dis exceeds it (:512-519); bound nodes are clipped to
+//           max_dis (:531-534); destination = pos + dis * dt_adapt (:536); _cur_dis = dis; the largest |dis| dt_adapt (:540).
+// Everything is element-wise FP64 in the reference's order: bit-identical results.
+// =================================================================================================
+struct NodeMoveArgs {
+    const double4 *pos4;
+    const double *forces, *iforces;   // 3 per node
+    const unsigned char *vbound;      // m_vertex_bound
+    const unsigned char *node_flags;  // bit 0 is_interface, bit 1 is_crossing (null: every node of active_nodes counts)
+    const double *dt_adapt;           // per node, null = 1.0
+    const unsigned *active_nodes, *n_active;
+    double alpha, dt, threshold, dom[3], max_displacement;
+    double *disp;                     // 3 per node: node_displacement, then (stage 2) _cur_dis
+    double *dest;                     // 3 per node: destinations (nodes that do not move keep their position)
+    unsigned long long *maxbits;      // [0] max_dis, [1] max_boundary_dis, [2] real_max as bit patterns of non-negative doubles
+    unsigned n_nodes;
+};
+
+__global__ void __launch_bounds__(256) node_displacement_kernel(const NodeMoveArgs a)
+{
+    const unsigned n_active = __ldg(a.n_active);
+    double m_free = 0, m_bound = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_active; i += gridDim.x * blockDim.x) {
+        const unsigned v = __ldg(a.active_nodes + i);
+        if (a.node_flags && !(a.node_flags[v] & 3)) continue;
+        const V3 pos = load_pos(a.pos4, v);
+        const double *F = a.forces + 3 * (size_t)v, *Fi = a.iforces + 3 * (size_t)v;
+        const double dis[3] = {(F[0] + a.alpha * Fi[0]) * a.dt, (F[1] + a.alpha * Fi[1]) * a.dt, (F[2] + a.alpha * Fi[2]) * a.dt};
+        const double p[3] = {pos.x, pos.y, pos.z};
+        double d[3] = {p[0] + dis[0], p[1] + dis[1], p[2] + dis[2]};
+        const bool bound = a.vbound[v] != 0;
+        if (bound) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { // algin_pos(k)
+                if (p[k] < a.threshold) d[k] = 0;
+                if (p[k] > a.dom[k] - 1 - a.threshold) d[k] = a.dom[k] - 1;
+                if (d[k] < a.threshold) d[k] = 0;
+                if (d[k] > a.dom[k] - 1 - a.threshold) d[k] = a.dom[k] - 1;
+            }
+        }
+        const V3 nd = {d[0] - p[0], d[1] - p[1], d[2] - p[2]};
+        const double len = length(nd);
+        if (bound) m_bound = fmax(m_bound, len); else m_free = fmax(m_free, len);
+        double *o = a.disp + 3 * (size_t)v;
+        o[0] = nd.x; o[1] = nd.y; o[2] = nd.z;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { m_free = fmax(m_free, shfl_xor_d(m_free, m)); m_bound = fmax(m_bound, shfl_xor_d(m_bound, m)); }
+    if ((threadIdx.x & 31) == 0) { // non-negative doubles order like their bit patterns
+        if (m_free > 0) atomicMax(a.maxbits, (unsigned long long)__double_as_longlong(m_free));
+        if (m_bound > 0) atomicMax(a.maxbits + 1, (unsigned long long)__double_as_longlong(m_bound));
+    }
+}
+
+__global__ void __launch_bounds__(256) node_destination_kernel(const NodeMoveArgs a)
+{
+    const unsigned n_active = __ldg(a.n_active);
+    double max_dis = __longlong_as_double((long long)a.maxbits[0]);
+    double scale = 1.0;
+    if (max_dis > a.max_displacement) { scale = a.max_displacement / max_dis; max_dis = a.max_displacement; }
+    double real_max = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_active; i += gridDim.x * blockDim.x) {
+        const unsigned v = __ldg(a.active_nodes + i);
+        if (a.node_flags && !(a.node_flags[v] & 1)) continue; // the second loop takes is_interface() nodes only (:527)
+        double *o = a.disp + 3 * (size_t)v;
+        V3 dis = {o[0] * scale, o[1] * scale, o[2] * scale};
+        const double len0 = length(dis);
+        if (a.vbound[v] && len0 > max_dis) dis = mul(dis, max_dis / len0);
+        const double ad = a.dt_adapt ? a.dt_adapt[v] : 1.0;
+        const V3 pos = load_pos(a.pos4, v);
+        double *dst = a.dest + 3 * (size_t)v;
+        dst[0] = pos.x + dis.x * ad; dst[1] = pos.y + dis.y * ad; dst[2] = pos.z + dis.z * ad;
+        o[0] = dis.x; o[1] = dis.y; o[2] = dis.z;
+        real_max = fmax(real_max, length(dis) * ad);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) real_max = fmax(real_max, shfl_xor_d(real_max, m));
+    if ((threadIdx.x & 31) == 0 && real_max > 0) atomicMax(a.maxbits + 2, (unsigned long long)__double_as_longlong(real_max));
+}
+
+// dest = pos for every node (the nodes stage 2 does not touch keep their position, like is_mesh's destination after deform)
+__global__ void node_dest_init_kernel(const double4 *__restrict__ pos4, double *__restrict__ dest, double *__restrict__ disp, unsigned n)
+{
+    const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const V3 p = load_pos(pos4, v);
+    dest[3 * (size_t)v] = p.x; dest[3 * (size_t)v + 1] = p.y; dest[3 * (size_t)v + 2] = p.z;
+    disp[3 * (size_t)v] = 0; disp[3 * (size_t)v + 1] = 0; disp[3 * (size_t)v + 2] = 0;
 }
 
 } // namespace dsc

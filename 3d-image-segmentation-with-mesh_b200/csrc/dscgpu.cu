@@ -101,6 +101,8 @@ struct dscgpu_ctx {
     bool comm_connected = false;
     uint32_t upd_n_pos = 0, upd_n_tet = 0, upd_n_faces = 0; // the staged update (dscgpu_update_staging_get)
     bool upd_keys = false, upd_staged = false;
+    bool forces_resident = false, iforces_resident = false; // ctx->forces / ctx->iforce (and nflags, vbound) hold the results of the last force calls on this snapshot
+    DevBuf ndisp, ndest;
     bool init_means_valid = false; // o_mean holds the per-tet means of the current snapshot (dscgpu_init_histogram)
     double *comm_rows = nullptr; // local scatter target of the force exchange: 3 doubles per active node, zero between evaluations
 
@@ -700,7 +702,7 @@ int run_zray(dscgpu_ctx *ctx, int nb_phase, int mode, const double *c_host, doub
     ra.ray_count = ctx->ray_count.as<unsigned>();
     ra.ray_offset = ctx->ray_offset.as<unsigned>();
     ra.ray_cursor = ctx->ray_cursor.as<unsigned>();
-    ra.hits = nullptr;
+    ra.hits = nullptr; ra.hits_cap = 0; ra.overflow = nullptr;
     unsigned fgrid = (ctx->n_faces + 127) / 128;
     if (fgrid) {
         zray_raster_kernel<false><<<fgrid, 128, 0, ctx->stream>>>(ra);
@@ -709,11 +711,21 @@ int run_zray(dscgpu_ctx *ctx, int nb_phase, int mode, const double *c_host, doub
     unsigned *d_total = reinterpret_cast<unsigned *>(ctr(ctx, 3));
     int r = exclusive_scan(ctx, ra.ray_count, ra.ray_offset, n_rays, d_total);
     if (r) return r;
-    unsigned total_hits = 0;
-    CK(cudaMemcpyAsync(&total_hits, d_total, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(ctx->hits.ensure(((size_t)total_hits + 1) * sizeof(uint2)));
+    // The hit buffer keeps its size from pass to pass: only a pass that finds it too small (the first one; a mesh whose interface has
+    // grown by more than the headroom) reads the total back and repeats -- check_overflow does that after the fact -- so the steady
+    // state has no host round trip in the middle of the pass and can be captured in a CUDA graph.
+    if (ctx->hits.cap == 0) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+            unsigned total_hits = 0;
+            CK(cudaMemcpyAsync(&total_hits, d_total, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(ctx->hits.ensure(((size_t)total_hits + 1) * sizeof(uint2)));
+        }
+    }
     ra.hits = ctx->hits.as<uint2>();
+    ra.hits_cap = (unsigned)std::min<size_t>(ctx->hits.cap / sizeof(uint2), 0xffffffffu);
+    ra.overflow = reinterpret_cast<int *>(ctr(ctx, 2));
     if (fgrid) {
         zray_raster_kernel<true><<<fgrid, 128, 0, ctx->stream>>>(ra);
         ctx->launches++;
@@ -723,7 +735,7 @@ int run_zray(dscgpu_ctx *ctx, int nb_phase, int mode, const double *c_host, doub
     rs.nb_phase = nb_phase;
     rs.mode = mode;
     for (int k = 0; k < kMaxPhase; k++) rs.c[k] = (c_host && k < nb_phase) ? c_host[k] : 0.0;
-    rs.ray_count = ra.ray_count; rs.ray_offset = ra.ray_offset; rs.hits = ra.hits;
+    rs.ray_count = ra.ray_count; rs.ray_offset = ra.ray_offset; rs.hits = ra.hits; rs.hits_cap = ra.hits_cap;
     // ray partition: contiguous column range derived from the tet partition fraction
     unsigned col_b = 0, col_e = (unsigned)XY;
     if (ctx->n_tets && !(ctx->tet_b == 0 && ctx->tet_e == ctx->n_tets)) {
@@ -751,16 +763,39 @@ int run_zray(dscgpu_ctx *ctx, int nb_phase, int mode, const double *c_host, doub
     return DSCGPU_OK;
 }
 
-int check_overflow(dscgpu_ctx *ctx)
+// end of a z-ray pass (synchronises): a hit buffer that was too small is grown to the size the pass has counted; the caller repeats
+// the pass when *again is set
+int check_overflow(dscgpu_ctx *ctx, bool *again = nullptr)
 {
-    int of = 0;
-    CK(cudaMemcpyAsync(&of, ctr(ctx, 2), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned of[4] = {0, 0, 0, 0}; // counters [2] (flags) and [3] (total hits) are adjacent
+    CK(cudaMemcpyAsync(of, ctr(ctx, 2), sizeof(of), cudaMemcpyDeviceToHost, ctx->stream));
     { int rs = sync_and_check(ctx); if (rs) return rs; }
-    if (of) {
-        ctx->err = "a z-ray collected more than DSCGPU_MAX_RAY_HITS interface hits";
+    if (again) *again = false;
+    if (of[0] & 2u) {
+        ctx->hits.release();
+        CK(ctx->hits.ensure(((size_t)of[2] + 1) * sizeof(uint2)));
+        if (again) { *again = true; return DSCGPU_OK; }
+        ctx->err = "the z-ray hit buffer was too small for this pass (grown now): repeat the call";
         return DSCGPU_ERR_RAY_OVERFLOW;
     }
     return DSCGPU_OK;
+}
+
+// a z-ray pass with its synchronising end; repeated once when the hit buffer had to grow.  h_sums / h_mean (may be null) receive the results.
+int run_zray_sync(dscgpu_ctx *ctx, int nb_phase, int mode, const double *c_host, double *d_sums, double *d_mean, double *h_sums, double *h_mean)
+{
+    for (int attempt = 0; attempt < 2; attempt++) {
+        int r = run_zray(ctx, nb_phase, mode, c_host, d_sums, d_mean);
+        if (r) return r;
+        if (h_sums) CK(cudaMemcpyAsync(h_sums, d_sums, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_mean && d_mean) CK(cudaMemcpyAsync(h_mean, d_mean, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        bool again = false;
+        r = check_overflow(ctx, &again);
+        if (r) return r;
+        if (!again) return DSCGPU_OK;
+    }
+    ctx->err = "the z-ray hit buffer did not settle";
+    return DSCGPU_ERR_RAY_OVERFLOW;
 }
 
 int ensure_scratch(dscgpu_ctx *ctx)
@@ -859,6 +894,7 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     ctx->has_snapshot = true;
     ctx->geom_async = false;
     ctx->init_means_valid = false;
+    ctx->forces_resident = ctx->iforces_resident = false;
     ctx->has_tet_faces = false;
     CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ks));
     CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[16], 0));
@@ -1257,6 +1293,7 @@ static int commit_snapshot_impl(dscgpu_ctx *ctx, bool sharded)
     ctx->has_snapshot = true;
     ctx->geom_async = false;
     ctx->init_means_valid = false;
+    ctx->forces_resident = ctx->iforces_resident = false;
     ctx->has_tet_faces = false;
 
     // choose lanes per tet from a sample of tet volumes (heuristic only; never affects results)
@@ -1335,6 +1372,7 @@ int dscgpu_update_commit(dscgpu_ctx *ctx, int replace_faces)
     const UpdLayout L = upd_layout(n_pos, ctx->upd_keys, n_tet_upd, ctx->upd_n_faces);
     CK(ctx->upd.ensure(L.total));
     CK(ctx->h_flag.ensure(sizeof(int)));
+    ctx->forces_resident = ctx->iforces_resident = false; // the mesh moves: forces of the previous state do not apply
     TimerScope ts(ctx, DSCGPU_T_H2D);
     // one H2D copy for everything that is scattered; the face arrays go straight to their place
     const size_t scatter_bytes = L.fn;
@@ -1576,12 +1614,8 @@ int dscgpu_zray_means(dscgpu_ctx *ctx, int nb_phase, dscgpu_phase_stats *stats)
     NEED_SNAPSHOT();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE, "nb_phase out of range");
     if (!ctx->has_sum_table) { ctx->err = "dscgpu_build_sum_table has not been called"; return DSCGPU_ERR_NO_SUMTABLE; }
-    int r = run_zray(ctx, nb_phase, 0, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>());
-    if (r) return r;
     double h_sums[3 * kMaxPhase], h_mean[kMaxPhase];
-    CK(cudaMemcpyAsync(h_sums, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_mean, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    r = check_overflow(ctx);
+    int r = run_zray_sync(ctx, nb_phase, 0, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), h_sums, h_mean);
     if (r) return r;
     if (stats) fill_stats(stats, h_sums, h_mean, nb_phase);
     return DSCGPU_OK;
@@ -1609,11 +1643,8 @@ int dscgpu_zray_energy(dscgpu_ctx *ctx, int nb_phase, const double *mean, double
 {
     NEED_SNAPSHOT();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && mean, "bad arguments");
-    int r = run_zray(ctx, nb_phase, 1, mean, ctx->sums.as<double>(), nullptr);
-    if (r) return r;
     double h_sums[3 * kMaxPhase];
-    CK(cudaMemcpyAsync(h_sums, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    r = check_overflow(ctx);
+    int r = run_zray_sync(ctx, nb_phase, 1, mean, ctx->sums.as<double>(), nullptr, h_sums, nullptr);
     if (r) return r;
     double d = 0;
     for (int k = 0; k < nb_phase; k++) d += h_sums[k]; // phases are accumulated one after another (:2449-2479)
@@ -1651,12 +1682,20 @@ int dscgpu_init_histogram(dscgpu_ctx *ctx, int nb_phase, int32_t hist[256])
     if (!nt) { ctx->init_means_valid = true; return DSCGPU_OK; }
     CK(ctx->o_mean.ensure(nt * 8));
     CK(ctx->misc.ensure(256 * sizeof(int) + 64));
-    // per-tet means of the whole mesh, whatever partition is set (the histogram is a property of the mesh)
-    const uint32_t tb = ctx->tet_b, te = ctx->tet_e;
-    ctx->tet_b = 0; ctx->tet_e = ctx->n_tets;
-    int r = run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, ctx->o_mean.as<double>(), nullptr, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), 0);
-    ctx->tet_b = tb; ctx->tet_e = te;
-    if (r) return r;
+    // per-tet means of the whole mesh, whatever partition is set (the histogram is a property of the mesh), added in the reference's order:
+    // the bins and the labels are truncations of these numbers
+    {
+        const unsigned g = (unsigned)((nt + 127) / 128);
+        switch (ctx->dtype) {
+        case DSCGPU_U8: tet_mean_ordered_kernel<unsigned char><<<g, 128, 0, ctx->stream>>>(vol_view(ctx), mesh_view(ctx), ctx->d_tet_bary, ctx->o_mean.as<double>()); break;
+        case DSCGPU_U16: tet_mean_ordered_kernel<unsigned short><<<g, 128, 0, ctx->stream>>>(vol_view(ctx), mesh_view(ctx), ctx->d_tet_bary, ctx->o_mean.as<double>()); break;
+        case DSCGPU_F32: tet_mean_ordered_kernel<float><<<g, 128, 0, ctx->stream>>>(vol_view(ctx), mesh_view(ctx), ctx->d_tet_bary, ctx->o_mean.as<double>()); break;
+        default: tet_mean_ordered_kernel<double><<<g, 128, 0, ctx->stream>>>(vol_view(ctx), mesh_view(ctx), ctx->d_tet_bary, ctx->o_mean.as<double>()); break;
+        }
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    int r;
     CK(cudaMemsetAsync(ctx->misc.p, 0, 256 * sizeof(int), ctx->stream));
     unsigned grid = (unsigned)std::min<size_t>((nt + 255) / 256, (size_t)ctx->num_sms * 8);
     init_hist_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->tet_label.as<int>(), ctx->o_mean.as<double>(), (unsigned)nt, ctx->misc.as<int>());
@@ -1718,8 +1757,74 @@ int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uin
         ctx->launches += 2;
         CK(cudaGetLastError());
     }
+    ctx->iforces_resident = true; // with the node flags and the vertex-bound flags this call used
     if (nn) CK(cudaMemcpyAsync(internal_forces, ctx->iforce.p, 3 * nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return sync_and_check(ctx);
+}
+
+
+int dscgpu_node_destinations(dscgpu_ctx *ctx, const dscgpu_move_params *mp, const double *forces, const double *internal_forces, const uint8_t *node_flags,
+                             const uint8_t *vertex_bound, const double *dt_adapt, double *destinations, double *cur_dis, dscgpu_move_stats *stats)
+{
+    NEED_SNAPSHOT();
+    ARG(mp && destinations, "params and destinations are required");
+    const size_t nn = ctx->n_nodes;
+    ARG(forces || ctx->forces_resident, "no external forces: pass them, or run dscgpu_image_force_eval / dscgpu_face_forces on this snapshot first");
+    ARG(internal_forces || ctx->iforces_resident, "no internal forces: pass them, or run dscgpu_internal_forces on this snapshot first");
+    ARG(node_flags || ctx->iforces_resident, "node_flags are required (or resident from dscgpu_internal_forces)");
+    CK(ctx->forces.ensure(3 * nn * sizeof(double) + 8));
+    CK(ctx->iforce.ensure(3 * nn * sizeof(double) + 8));
+    CK(ctx->nflags.ensure(nn + 1));
+    CK(ctx->vbound.ensure(nn + 1));
+    CK(ctx->ndisp.ensure(3 * nn * sizeof(double) + 8));
+    CK(ctx->ndest.ensure(3 * nn * sizeof(double) + 8));
+    CK(ctx->misc.ensure(256 * sizeof(int) + 64));
+    if (forces && nn) CK(cudaMemcpyAsync(ctx->forces.p, forces, 3 * nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (internal_forces && nn) CK(cudaMemcpyAsync(ctx->iforce.p, internal_forces, 3 * nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (node_flags && nn) CK(cudaMemcpyAsync(ctx->nflags.p, node_flags, nn, cudaMemcpyHostToDevice, ctx->stream));
+    if (vertex_bound) {
+        if (nn) CK(cudaMemcpyAsync(ctx->vbound.p, vertex_bound, nn, cudaMemcpyHostToDevice, ctx->stream));
+    } else if (!ctx->iforces_resident) { // (dscgpu_internal_forces leaves the flags it used)
+        int r = dscgpu_vertex_bound(ctx, nullptr);
+        if (r) return r;
+    }
+    double *d_adapt = nullptr;
+    if (dt_adapt && nn) {
+        CK(ctx->iterm.ensure(nn * sizeof(double)));
+        CK(cudaMemcpyAsync(ctx->iterm.p, dt_adapt, nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        d_adapt = ctx->iterm.as<double>();
+    }
+    unsigned long long *maxbits = reinterpret_cast<unsigned long long *>(ctx->misc.p);
+    CK(cudaMemsetAsync(maxbits, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    NodeMoveArgs a;
+    a.pos4 = ctx->pos4.as<double4>();
+    a.forces = ctx->forces.as<double>(); a.iforces = ctx->iforce.as<double>();
+    a.vbound = ctx->vbound.as<unsigned char>(); a.node_flags = ctx->nflags.as<unsigned char>();
+    a.dt_adapt = d_adapt;
+    a.active_nodes = ctx->node_active.as<unsigned>(); a.n_active = reinterpret_cast<const unsigned *>(ctr(ctx, 5));
+    a.alpha = mp->alpha; a.dt = mp->dt; a.threshold = mp->align_threshold; a.max_displacement = mp->max_displacement;
+    for (int k = 0; k < 3; k++) a.dom[k] = (double)ctx->dims[k]; // image3d::dimension_v()
+    a.disp = ctx->ndisp.as<double>(); a.dest = ctx->ndest.as<double>(); a.maxbits = maxbits; a.n_nodes = (unsigned)nn;
+    if (nn) {
+        node_dest_init_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, ctx->stream>>>(a.pos4, a.dest, a.disp, (unsigned)nn);
+        const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * ctx->n_faces);
+        const unsigned grid = std::max(1u, std::min<unsigned>((max_active + 255) / 256, (unsigned)ctx->num_sms * 4));
+        node_displacement_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+        node_destination_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(destinations, ctx->ndest.p, 3 * nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (cur_dis) CK(cudaMemcpyAsync(cur_dis, ctx->ndisp.p, 3 * nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    double h[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h, maxbits, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    int r = sync_and_check(ctx);
+    if (r) return r;
+    if (stats) {
+        stats->max_dis = h[0]; stats->max_boundary_dis = h[1]; stats->real_max = h[2];
+        stats->scale = h[0] > mp->max_displacement ? mp->max_displacement / h[0] : 1.0;
+    }
+    return DSCGPU_OK;
 }
 
 int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mode, double *forces)
@@ -1732,6 +1837,7 @@ int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mo
     CK(ctx->forces.ensure(bytes + 8));
     CK(cudaMemcpyAsync(ctx->mean.p, mean, nb_phase * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     int r = run_forces(ctx, nb_phase, ctx->mean.as<double>(), mode, ctx->forces.as<double>());
+    ctx->forces_resident = r == DSCGPU_OK;
     if (r) return r;
     {
         TimerScope ts(ctx, DSCGPU_T_D2H);
@@ -1781,7 +1887,7 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
     CK(ctx->h_out.ensure(fbytes + 4 * kMaxPhase * sizeof(double)));
     if (mean_mode == DSCGPU_MEAN_ZRAY) {
         if (!ctx->has_sum_table) { ctx->err = "dscgpu_build_sum_table has not been called"; return DSCGPU_ERR_NO_SUMTABLE; }
-        r = run_zray(ctx, nb_phase, 0, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>());
+        r = run_zray_sync(ctx, nb_phase, 0, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), nullptr, nullptr);
     } else if (!tet_done) {
         r = run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), ctx->hot_want_sq);
     } else {
@@ -1789,6 +1895,7 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
     }
     if (r) return r;
     r = run_forces(ctx, nb_phase, ctx->mean.as<double>(), force_mode, ctx->forces.as<double>());
+    ctx->forces_resident = r == DSCGPU_OK;
     if (r) return r;
     double *h = ctx->h_out.as<double>();
     {
@@ -1797,13 +1904,8 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
         CK(cudaMemcpyAsync(h + 3 * kMaxPhase, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (fbytes) CK(cudaMemcpyAsync(h + 4 * kMaxPhase, ctx->forces.p, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    if (mean_mode == DSCGPU_MEAN_ZRAY) {
-        r = check_overflow(ctx);
-        if (r) return r;
-    } else {
-        r = sync_and_check(ctx);
-        if (r) return r;
-    }
+    r = sync_and_check(ctx);
+    if (r) return r;
     if (stats) fill_stats(stats, h, h + 3 * kMaxPhase, nb_phase);
     if (forces && fbytes) memcpy(forces, h + 4 * kMaxPhase, fbytes);
     return DSCGPU_OK;
@@ -1828,9 +1930,10 @@ int dscgpu_zray_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums)
     NEED_SNAPSHOT();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_sums, "bad arguments");
     if (!ctx->has_sum_table) { ctx->err = "dscgpu_build_sum_table has not been called"; return DSCGPU_ERR_NO_SUMTABLE; }
-    int r = run_zray(ctx, nb_phase, 0, nullptr, d_sums, nullptr);
-    if (r) return r;
-    return check_overflow(ctx);
+    // under stream capture the pass is recorded as it is (no host round trip): run it once outside capture first, which sizes the hit buffer
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return run_zray(ctx, nb_phase, 0, nullptr, d_sums, nullptr);
+    return run_zray_sync(ctx, nb_phase, 0, nullptr, d_sums, nullptr, nullptr, nullptr);
 }
 
 int dscgpu_means_from_sums_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_sums, double *d_mean)

@@ -55,6 +55,14 @@ class _PhaseStats(C.Structure):
                 ("mean", C.c_double * MAX_PHASE)]
 
 
+class _MoveParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("alpha", C.c_double), ("align_threshold", C.c_double), ("max_displacement", C.c_double)]
+
+
+class _MoveStats(C.Structure):
+    _fields_ = [("max_dis", C.c_double), ("max_boundary_dis", C.c_double), ("scale", C.c_double), ("real_max", C.c_double)]
+
+
 def library_path():
     return os.path.join(_HERE, "libdscgpu.so")
 
@@ -405,6 +413,22 @@ class SegmentFunction:
         F = self._forces if forces is None else forces
         Fi = self._internal_forces if internal_forces is None else internal_forces
         return (F + self.m_alpha * Fi) * dt
+
+    def node_destinations(self, dt, align_threshold, max_displacement, forces=None, internal_forces=None, node_flags=None, vertex_bound=None, dt_adapt=None):
+        """get_node_displacement + the non-topological part of snapp_boundary (DEMO/segment_function.cpp:466-541, 581-584) on the device.
+        None for forces / internal_forces / node_flags / vertex_bound = what the last force calls left resident.
+        Returns (destinations[n,3], cur_dis[n,3], stats dict)."""
+        n = self.n_nodes_buffer
+        mp = _MoveParams(float(dt), float(self.m_alpha), float(align_threshold), float(max_displacement))
+        st = _MoveStats()
+        dest = np.empty((n, 3))
+        cur = np.empty((n, 3))
+        arr = lambda a, dt_: None if a is None else np.ascontiguousarray(a, dt_)
+        F, Fi, nf, vb, da = arr(forces, np.float64), arr(internal_forces, np.float64), arr(node_flags, np.uint8), arr(vertex_bound, np.uint8), arr(dt_adapt, np.float64)
+        self._keep_move = (F, Fi, nf, vb, da)
+        r = self.lib.dscgpu_node_destinations(self._img._ctx, C.byref(mp), _ptr(F), _ptr(Fi), _ptr(nf), _ptr(vb), _ptr(da), _ptr(dest), _ptr(cur), C.byref(st))
+        self._img._check(r, "dscgpu_node_destinations")
+        return dest, cur, {"max_dis": st.max_dis, "max_boundary_dis": st.max_boundary_dis, "scale": st.scale, "real_max": st.real_max}
 
     def compute_energy(self, mean=None, vertex_bound=None):
         """segment_function::compute_energy (DEMO/segment_function.cpp:2331-2492): (data, alpha*area)."""

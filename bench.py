@@ -541,7 +541,10 @@ def main_b200(args):
                 seg.commit_snapshot()
             seg.set_partition(tet_range, rng(n_faces), rng(n_nodes))
             step_device()
-            pinned_forces.copy_(d_forces, non_blocking=True)
+            # every rank ends up with the same forces (rank-ordered sums): the job's result crosses PCIe once, on rank 0;
+            # the other ranks read the means back (their synchronisation point)
+            if rank == 0:
+                pinned_forces.copy_(d_forces, non_blocking=True)
             pinned_mean.copy_(d_mean, non_blocking=True)
             torch.cuda.synchronize(dev)
 

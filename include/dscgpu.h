@@ -40,9 +40,10 @@ enum dscgpu_status {
     DSCGPU_ERR_ARG = -2,         /* bad argument */
     DSCGPU_ERR_NO_SNAPSHOT = -3, /* mesh snapshot not set */
     DSCGPU_ERR_NO_SUMTABLE = -4, /* dscgpu_build_sum_table not called */
-    DSCGPU_ERR_RAY_OVERFLOW = -5 /* a z-ray has more hits than DSCGPU_MAX_RAY_HITS */
+    DSCGPU_ERR_RAY_OVERFLOW = -5 /* the z-ray hit buffer could not be sized (it is grown and the pass repeated automatically; this is the give-up) */
 };
 
+/* rays with more interface hits than this are resolved in place in the hit buffer (slow path) instead of in registers / local memory */
 #define DSCGPU_MAX_RAY_HITS 96
 
 typedef struct dscgpu_ctx dscgpu_ctx;
@@ -233,6 +234,25 @@ int dscgpu_init_labels(dscgpu_ctx *ctx, int n_thresholds, const int32_t *thresho
  * Nodes that are not projected (crossing, or not interface) are bit-identical to the reference; projected ones agree to
  * rounding (the node normal adds the face normals in ascending face order, the reference in get_faces(node) order). */
 int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uint8_t *vertex_bound, double *internal_forces);
+
+/* SURVEY 8(f) row 3, second half -- get_node_displacement (DEMO/segment_function.cpp:581-584) and the non-topological part of
+ * snapp_boundary (:466-541) for every node at once, so that the forces need not leave the device before set_destination:
+ *   node_displacement = (forces + alpha internal_forces) dt, destination = pos + it; nodes of m_vertex_bound are aligned to the faces
+ *   of the image domain (macro algin_pos, :59-65, threshold align_threshold = AVG_LENGTH*0.5*0.6); the step is scaled when the largest
+ *   displacement of a free node exceeds max_displacement (= get_avg_edge_length()*0.5*0.4, :512-519), bound nodes are clipped (:531-534);
+ *   destinations[3 v] = pos + dis * dt_adapt[v] for is_interface() nodes -- what the reference hands to DSC::set_destination (:536) --
+ *   and pos for every other node; cur_dis (may be NULL) = _cur_dis.
+ * forces / internal_forces / node_flags / vertex_bound: host arrays, or NULL to use what the last dscgpu_image_force_eval /
+ * dscgpu_face_forces and dscgpu_internal_forces on this snapshot left on the device.  dt_adapt NULL = 1.0 for every node.
+ * Element-wise FP64 in the reference's order and exact maxima: bit-identical to the reference for identical forces. */
+typedef struct dscgpu_move_params {
+    double dt, alpha, align_threshold, max_displacement;
+} dscgpu_move_params;
+typedef struct dscgpu_move_stats {
+    double max_dis, max_boundary_dis, scale, real_max; /* the numbers snapp_boundary prints; _dt is multiplied by scale (:516) */
+} dscgpu_move_stats;
+int dscgpu_node_destinations(dscgpu_ctx *ctx, const dscgpu_move_params *params, const double *forces, const double *internal_forces, const uint8_t *node_flags,
+                             const uint8_t *vertex_bound, const double *dt_adapt, double *destinations, double *cur_dis, dscgpu_move_stats *stats);
 
 /* -- fused evaluation and device-resident variants ------------------------------------------- */
 

@@ -16,6 +16,8 @@
 // INTEGRATION.md shows the three-line patch to DEMO/segment_function.cpp that routes segment() through it.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -86,7 +88,13 @@ template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s, bool key_inde
         for (auto tit = dsc.tetrahedra_begin(); tit != dsc.tetrahedra_end(); tit++) {
             const size_t k = (size_t)(unsigned)tit.key();
             tet_index[k] = (int32_t)k;
+            // get_nodes(t) builds the node set by set unions on every call (is_mesh/is_mesh.h:673-679, ~0.7 us per tet); with DSC_CACHE
+            // the complex keeps it per tet and drops it when the tet changes (src/cache.hpp:107-111, src/DSC.h:290-299): same order
+#ifdef DSC_CACHE
+            const auto &nids = *dsc.get_nodes_cache(tit.key());
+#else
             const auto nids = dsc.get_nodes(tit.key());
+#endif
             for (int c = 0; c < 4; c++) s.tet_nodes[4 * k + c] = nids[c];
             s.tet_label[k] = dsc.get_label(tit.key());
         }
@@ -94,7 +102,11 @@ template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s, bool key_inde
     for (auto tit = dsc.tetrahedra_begin(); tit != dsc.tetrahedra_end(); tit++) {
         tet_index[tit.key()] = (int32_t)s.tet_key.size();
         s.tet_key.push_back(tit.key());
+#ifdef DSC_CACHE
+        const auto &nids = *dsc.get_nodes_cache(tit.key());
+#else
         const auto nids = dsc.get_nodes(tit.key());
+#endif
         for (int k = 0; k < 4; k++) s.tet_nodes.push_back(nids[k]);
         s.tet_label.push_back(dsc.get_label(tit.key()));
     }
@@ -119,13 +131,26 @@ public:
 // IMG is the reference's image3d; SEG its segment_function.
 template <class IMG, class SEG> class ImageEnergy {
 public:
-    // Uploads img._voxels (FP64, exactly the reference's values) and builds the z prefix-sum table on the device.
+    // Uploads img._voxels and builds the z prefix-sum table on the device.  image3d::load fills _voxels with byte / 255.0
+    // (DEMO/image3d.cpp:127): when every voxel is exactly such a value the volume goes up as bytes -- the device decodes q / 255.0 to
+    // the same doubles, at 1/8 of the memory and gather traffic; anything else goes up as the FP64 values themselves.
     explicit ImageEnergy(IMG &img, int device = 0, int force_mode = DSCGPU_FORCE_GATHER) : force_mode_(force_mode)
     {
         const int dims[3] = {img._dim[0], img._dim[1], img._dim[2]};
-        check(dscgpu_ctx_create(&ctx_, device, dims, DSCGPU_F64, img._voxels.data()), "dscgpu_ctx_create");
+        const size_t n = img._voxels.size();
+        std::vector<uint8_t> bytes(n);
+        bool as_bytes = true;
+        for (size_t i = 0; i < n && as_bytes; i++) {
+            const double v = img._voxels[i], q = std::nearbyint(v * 255.0);
+            if (!(q >= 0.0 && q <= 255.0) || q / 255.0 != v) as_bytes = false;
+            else bytes[i] = (uint8_t)q;
+        }
+        volume_dtype_ = as_bytes ? DSCGPU_U8 : DSCGPU_F64;
+        check(dscgpu_ctx_create(&ctx_, device, dims, volume_dtype_, as_bytes ? static_cast<const void *>(bytes.data()) : static_cast<const void *>(img._voxels.data())),
+              "dscgpu_ctx_create");
         check(dscgpu_build_sum_table(ctx_), "dscgpu_build_sum_table");
     }
+    int volume_dtype() const { return volume_dtype_; }
     ~ImageEnergy() { dscgpu_ctx_destroy(ctx_); }
     ImageEnergy(const ImageEnergy &) = delete;
     ImageEnergy &operator=(const ImageEnergy &) = delete;
@@ -136,8 +161,14 @@ public:
     // interface-face list -- through dscgpu_update_snapshot; otherwise the whole snapshot.
     void refresh(SEG &seg)
     {
+        const auto t0 = std::chrono::steady_clock::now();
+        struct Stop {
+            ImageEnergy *self; std::chrono::steady_clock::time_point t0;
+            ~Stop() { self->last_refresh_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+        } stop{this, t0};
         Snapshot next;
         snapshot_from_dsc(*seg._dsc, next, /*key_indexed=*/true);
+        last_flatten_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         const bool same_shape = have_snapshot_ && next.pos.size() == snap_.pos.size() && next.tet_label.size() == snap_.tet_label.size();
         if (!same_shape) {
             snap_.swap(next);
@@ -173,6 +204,8 @@ public:
     bool last_refresh_incremental() const { return last_refresh_incremental_; }
     size_t last_moved_nodes() const { return last_moved_nodes_; }
     size_t last_changed_tets() const { return last_changed_tets_; }
+    double last_flatten_ms() const { return last_flatten_ms_; } // the is_mesh walk of the last refresh
+    double last_refresh_ms() const { return last_refresh_ms_; } // walk + diff + upload (the upload is asynchronous: it overlaps what follows)
 
     // Body of segment_function::update_average_intensity.
     void update_average_intensity(SEG &seg)
@@ -224,6 +257,56 @@ public:
         }
     }
 
+    // Body of the non-topological part of segment_function::snapp_boundary (DEMO/segment_function.cpp:466-541): displacements from the
+    // forces, alignment of the m_vertex_bound nodes to the faces of the image, step scaling, set_destination.  The external forces are
+    // the ones the last compute_external_force left on the device, the internal ones those of compute_internal_force_2 (call both
+    // first, as segment() does, :2246-2247).  The two thresholds are function-local statics in the reference, fixed at the first call.
+    dscgpu_move_stats snapp_boundary(SEG &seg)
+    {
+        if (!move_init_) {
+            move_threshold_ = seg._dsc->AVG_LENGTH * 0.5 * 0.6;
+            move_max_displacement_ = seg._dsc->get_avg_edge_length() * 0.5 * 0.4;
+            move_init_ = true;
+        }
+        const size_t nnb = snap_.pos.size() / 3;
+        dscgpu_move_params mp;
+        mp.dt = seg._dt; mp.alpha = seg.m_alpha; mp.align_threshold = move_threshold_; mp.max_displacement = move_max_displacement_;
+        seg._dt_adapt.resize(nnb, 1.0);
+        dest_.resize(3 * nnb); forces_.resize(3 * nnb);
+        dscgpu_move_stats st;
+        check(dscgpu_node_destinations(ctx_, &mp, nullptr, nullptr, nullptr, nullptr, seg._dt_adapt.data(), dest_.data(), forces_.data(), &st), "dscgpu_node_destinations");
+        seg._dt *= st.scale; // :516
+        seg._previous_dis.resize(nnb, typename std::decay<decltype(seg._cur_dis[0])>::type(0));
+        seg._cur_dis.resize(nnb, typename std::decay<decltype(seg._cur_dis[0])>::type(0));
+        for (auto nit = seg._dsc->nodes_begin(); nit != seg._dsc->nodes_end(); nit++) {
+            if (!nit->is_interface()) continue;
+            const size_t k = (size_t)(unsigned)nit.key();
+            typename std::decay<decltype(seg._cur_dis[0])>::type d(dest_[3 * k], dest_[3 * k + 1], dest_[3 * k + 2]);
+            seg._dsc->set_destination(nit.key(), d);
+            seg._cur_dis[k][0] = forces_[3 * k]; seg._cur_dis[k][1] = forces_[3 * k + 1]; seg._cur_dis[k][2] = forces_[3 * k + 2];
+        }
+        // the per-node step factors for the next call (:545-578): host state (the is_clean marks live in the complex's cache), a few
+        // operations per interface node -- restated here so that the body is complete
+        typedef typename std::decay<decltype(seg._dsc->nodes_begin().key())>::type node_key_t;
+        static const double thres_minus = std::cos(M_PI / 180.0 * 150), thres_positive = std::cos(M_PI / 180.0 * 30);
+        for (size_t i = 0; i < seg._dt_adapt.size(); i++) {
+            node_key_t nk((unsigned)i);
+            if (!(seg._dsc->exists(nk) && seg._dsc->get(nk).is_interface() && (!seg.m_vertex_bound[i] || (seg.m_vertex_bound[i] && seg._dsc->get(nk).is_crossing())))) continue;
+            if (seg._cur_dis[i].length() > 0.0001) {
+                if (!seg._dsc->cache.is_clean[i]) {
+                    seg._dsc->cache.is_clean[i] = new bool(true);
+                    seg._dt_adapt[i] = 1.0;
+                }
+                seg._cur_dis[i].normalize();
+                const double cos_sign = dot(seg._cur_dis[i], seg._previous_dis[i]);
+                if (cos_sign < thres_minus) seg._dt_adapt[i] = std::max(seg._dt_adapt[i] * 0.9, 0.1);
+                if (cos_sign > thres_positive) seg._dt_adapt[i] = std::min(seg._dt_adapt[i] * 1.1, 3.0);
+                seg._previous_dis[i] = seg._cur_dis[i];
+            }
+        }
+        return st;
+    }
+
     // The two numbers of compute_energy's "=== Energy; area = data - area" line.
     void compute_energy(SEG &seg, double *data, double *area)
     {
@@ -242,7 +325,11 @@ private:
     Snapshot snap_;
     bool have_snapshot_ = false, last_refresh_incremental_ = false;
     size_t last_moved_nodes_ = 0, last_changed_tets_ = 0;
-    std::vector<double> forces_;
+    double last_flatten_ms_ = 0, last_refresh_ms_ = 0;
+    int volume_dtype_ = DSCGPU_F64;
+    std::vector<double> forces_, dest_;
+    bool move_init_ = false;
+    double move_threshold_ = 0, move_max_displacement_ = 0;
     int force_mode_;
 };
 

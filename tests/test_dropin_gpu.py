@@ -28,7 +28,28 @@ def test_reference_segment_loop_with_gpu_dropin():
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DROP-IN PARITY OK" in r.stdout
-    assert r.stdout.count("bit-exact") == 3
+    assert r.stdout.count("phase_volume bit-exact") == 3
+    assert r.stdout.count("destinations bit-exact") == 3  # get_node_displacement + snapp_boundary on the reference's forces
+    assert "0 labels differ" in r.stdout                  # initialisation pass: no tolerance
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref/dsc_dropin is built in the container (make -C oracle dropin)")
+def test_dropin_on_a_quarter_million_tets_with_timings():
+    """SURVEY section 6, edge-3 row: 257 250 tets / 23.5 K interface faces on a live is_mesh complex; parity as above, and the
+    wall-clock of every reference body next to its drop-in (the is_mesh walk of ImageEnergy::refresh included) in the log."""
+    g = golden_io.load("c1_e6")
+    with tempfile.TemporaryDirectory() as tmp:
+        vp = os.path.join(tmp, "vol.u8")
+        g["volume"].tofile(vp)
+        r = subprocess.run([DROPIN, vp, "100", "100", "100", "3", "1", "3", "0.001"], capture_output=True, text=True, timeout=1500)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "dropin_edge3.log"), "w") as f:
+            f.write(r.stdout)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DROP-IN PARITY OK" in r.stdout
+    assert "timing [ms] reference" in r.stdout
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/dsc_ref is built in the container (make -C oracle ref)")

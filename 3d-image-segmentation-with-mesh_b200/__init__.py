@@ -16,3 +16,4 @@ from .host import (DscGpuError, Image3D, SegmentFunction, FORCE_ATOMIC, FORCE_GA
                    host_sort_hits)  # noqa: F401
 from . import synthetic  # noqa: F401
 from . import distributed  # noqa: F401
+from . import mesh_io  # noqa: F401

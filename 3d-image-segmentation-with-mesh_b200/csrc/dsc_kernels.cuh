@@ -2023,4 +2023,43 @@ __global__ void node_dest_init_kernel(const double4 *__restrict__ pos4, double *
     disp[3 * (size_t)v] = 0; disp[3 * (size_t)v + 1] = 0; disp[3 * (size_t)v + 2] = 0;
 }
 
+// =================================================================================================
+// A9b -- the force loop of segment_function::thickenning_surface (DEMO/segment_function.cpp:1990-2051): the quadrature of
+// compute_external_force over the interface faces that are not segment_function::is_boundary (all three nodes in m_vertex_bound,
+// :2186-2196), plus, per face, the mean and the mean absolute deviation of the scalar magnitudes
+// (2I - c0 - c1)(c0 - c1) w area of its Gauss points (:2030-2043) that decide which edges get split (:2046-2049, host).
+// This kernel masks the skipped faces (fset_out = -1, so that force_node2_kernel leaves them out) and forms the statistics in the
+// reference's order: sum in Gauss-point order, divide, sum of |m - mean|, divide.
+// =================================================================================================
+__global__ void __launch_bounds__(128) face_force_stats_kernel(MeshView m, const double *__restrict__ fgeo, const int *__restrict__ flab, const double *__restrict__ fint,
+                                                               const signed char *__restrict__ fset, const unsigned char *__restrict__ vb, int nb_phase,
+                                                               const double *__restrict__ mean, signed char *__restrict__ fset_out, double *__restrict__ face_mean,
+                                                               double *__restrict__ face_dev)
+{
+    const unsigned f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.n_faces) return;
+    int gs = fset[f];
+    if (gs >= 0) {
+        const unsigned n0 = m.face_nodes[3 * (size_t)f], n1 = m.face_nodes[3 * (size_t)f + 1], n2 = m.face_nodes[3 * (size_t)f + 2];
+        if (vb[n0] && vb[n1] && vb[n2]) gs = -1;
+    }
+    fset_out[f] = (signed char)gs;
+    double mu = 0, dev = 0;
+    if (gs >= 0) {
+        const double area = fgeo[4 * (size_t)f + 3];
+        const double c0 = phase_intensity(flab[2 * (size_t)f], nb_phase, mean), c1 = phase_intensity(flab[2 * (size_t)f + 1], nb_phase, mean);
+        const int q0 = c_gauss_off[gs], ng = c_gauss_off[gs + 1] - q0;
+        double mag[12];
+        for (int k = 0; k < ng; k++) {
+            mag[k] = (2 * fint[12 * (size_t)f + k] - c0 - c1) * (c0 - c1) * c_gauss[4 * (q0 + k)] * area;
+            mu += mag[k];
+        }
+        mu /= (double)ng;
+        for (int k = 0; k < ng; k++) dev += fabs(mag[k] - mu);
+        dev /= (double)ng;
+    }
+    face_mean[f] = mu;
+    face_dev[f] = dev;
+}
+
 } // namespace dsc

@@ -1827,6 +1827,62 @@ int dscgpu_node_destinations(dscgpu_ctx *ctx, const dscgpu_move_params *mp, cons
     return DSCGPU_OK;
 }
 
+int dscgpu_thicken_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, const uint8_t *vertex_bound, double *forces, double *face_mean, double *face_dev,
+                          uint8_t *face_evaluated)
+{
+    NEED_SNAPSHOT();
+    NEED_PARTITION();
+    ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && mean && forces, "bad arguments");
+    ARG(ctx->face_b == 0 && ctx->face_e == ctx->n_faces && ctx->node_b == 0 && ctx->node_e == ctx->n_nodes, "dscgpu_thicken_forces evaluates the whole mesh: reset the partition");
+    const size_t nn = ctx->n_nodes, nf = ctx->n_faces;
+    CK(ctx->forces.ensure(3 * nn * sizeof(double) + 8));
+    CK(ctx->vbound.ensure(nn + 1));
+    CK(ctx->iskip.ensure(nf + 8));                     // masked Gauss-set indices
+    CK(ctx->iterm.ensure(2 * nf * sizeof(double) + 8)); // per-face mean and deviation
+    CK(cudaMemcpyAsync(ctx->mean.p, mean, nb_phase * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (vertex_bound) {
+        if (nn) CK(cudaMemcpyAsync(ctx->vbound.p, vertex_bound, nn, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        int r = dscgpu_vertex_bound(ctx, nullptr);
+        if (r) return r;
+    }
+    TimerScope ts(ctx, DSCGPU_T_FORCE);
+    if (ctx->geom_async) {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[19], 0));
+        ctx->geom_async = false;
+    } else {
+        int rg = launch_force_geom(ctx, ctx->stream);
+        if (rg) return rg;
+    }
+    CK(cudaMemsetAsync(ctx->forces.p, 0, 3 * nn * sizeof(double), ctx->stream));
+    if (nf) {
+        double *d_mu = ctx->iterm.as<double>(), *d_dev = d_mu + nf;
+        face_force_stats_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, ctx->stream>>>(mesh_view(ctx), ctx->fgeo.as<double>(), ctx->flab.as<int>(), ctx->fint.as<double>(),
+                                                                                    ctx->fset.as<signed char>(), ctx->vbound.as<unsigned char>(), nb_phase, ctx->mean.as<double>(),
+                                                                                    ctx->iskip.as<signed char>(), d_mu, d_dev);
+        ForceNode2Args na;
+        na.mesh = mesh_view(ctx); na.fgeo = ctx->fgeo.as<double>(); na.flab = ctx->flab.as<int>(); na.fint = ctx->fint.as<double>();
+        na.fset = ctx->iskip.as<signed char>(); na.nb_phase = nb_phase; na.mean = ctx->mean.as<double>(); na.forces = ctx->forces.as<double>();
+        na.begin = 0; na.end = ctx->n_nodes;
+        na.active_nodes = ctx->node_active.as<unsigned>();
+        na.n_active = reinterpret_cast<const unsigned *>(ctr(ctx, 5));
+        const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * ctx->n_faces);
+        const unsigned grid = std::max(1u, std::min<unsigned>((max_active + 15) / 16, (unsigned)ctx->num_sms * 16));
+        force_node2_kernel<<<grid, 128, 0, ctx->stream>>>(na);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        if (face_mean) CK(cudaMemcpyAsync(face_mean, d_mu, nf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (face_dev) CK(cudaMemcpyAsync(face_dev, d_dev, nf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (face_evaluated) CK(cudaMemcpyAsync(face_evaluated, ctx->iskip.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (nn) CK(cudaMemcpyAsync(forces, ctx->forces.p, 3 * nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    int r = sync_and_check(ctx);
+    if (r) return r;
+    if (face_evaluated) for (size_t f = 0; f < nf; f++) face_evaluated[f] = ((signed char)face_evaluated[f]) >= 0 ? 1 : 0;
+    ctx->forces_resident = true;
+    return DSCGPU_OK;
+}
+
 int dscgpu_face_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, int mode, double *forces)
 {
     NEED_SNAPSHOT();

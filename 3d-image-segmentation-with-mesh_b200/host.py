@@ -414,6 +414,17 @@ class SegmentFunction:
         Fi = self._internal_forces if internal_forces is None else internal_forces
         return (F + self.m_alpha * Fi) * dt
 
+    def thicken_forces(self, mean=None, vertex_bound=None):
+        """Force loop of segment_function::thickenning_surface (DEMO/segment_function.cpp:1990-2051):
+        returns (forces[n,3], face_mean[n_faces], face_dev[n_faces], face_evaluated[n_faces])."""
+        m = np.ascontiguousarray(self._mean_intensities if mean is None else mean, np.float64)
+        vb = None if vertex_bound is None else np.ascontiguousarray(vertex_bound, np.uint8)
+        F = np.zeros((self.n_nodes_buffer, 3))
+        mu, dev, ev = np.zeros(self.n_faces), np.zeros(self.n_faces), np.zeros(self.n_faces, np.uint8)
+        r = self.lib.dscgpu_thicken_forces(self._img._ctx, C.c_int(self.NB_PHASE), _ptr(m), _ptr(vb), _ptr(F), _ptr(mu), _ptr(dev), _ptr(ev))
+        self._img._check(r, "dscgpu_thicken_forces")
+        return F, mu, dev, ev
+
     def node_destinations(self, dt, align_threshold, max_displacement, forces=None, internal_forces=None, node_flags=None, vertex_bound=None, dt_adapt=None):
         """get_node_displacement + the non-topological part of snapp_boundary (DEMO/segment_function.cpp:466-541, 581-584) on the device.
         None for forces / internal_forces / node_flags / vertex_bound = what the last force calls left resident.

@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--force-mode", default="auto", choices=["auto", "gather", "atomic"],
                     help="auto: the bit-exact ordered gather on one GPU, the face-partitioned atomic scatter when the forces are all-reduced anyway")
     ap.add_argument("--jitter", type=float, default=0.2)
+    ap.add_argument("--dsc", default=None, help="replay a mesh saved by a reference run (iter_N.dsc, is_mesh/mesh_io.cpp:298-314) on the volume of --config instead of the generated grid mesh")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the comparison of the step's outputs with the flat oracle (outside the timed region)")
@@ -116,12 +117,15 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------
-def build_workload(pkg, cfg_name, seg_factory, jitter):
+def build_workload(pkg, cfg_name, seg_factory, jitter, dsc_path=None):
     syn = pkg.synthetic
     cfg = syn.CONFIGS[cfg_name]
     vol = syn.make_volume(cfg_name)
     img, seg = seg_factory(vol, cfg["nb_phase"])
     edge = syn.edge_for_cells(cfg["n"], cfg["cells"])
+    if dsc_path:  # a mesh the reference saved: positions, tets and labels as they are in the file
+        pos, tets, labels = pkg.mesh_io.read_dsc(dsc_path)
+        return vol, cfg, edge, pkg.mesh_io.snapshot_from_tets(pos, tets, labels), img, seg
 
     def tet_mean(pos, tets, base):
         seg.set_snapshot({"pos": pos, "tet_nodes": tets, "tet_label": base, "face_nodes": np.zeros((0, 3), np.uint32),
@@ -293,7 +297,7 @@ def main_b200(args):
         return img, pkg.SegmentFunction(img, nb_phase, 0.01)
 
     t0 = time.time()
-    vol, cfg, edge, snap, img, seg = build_workload(pkg, args.config, seg_factory, args.jitter)
+    vol, cfg, edge, snap, img, seg = build_workload(pkg, args.config, seg_factory, args.jitter, args.dsc)
     P = cfg["nb_phase"]
     n_tets, n_faces, n_nodes = len(snap["tet_nodes"]), len(snap["face_nodes"]), len(snap["pos"])
     units = n_tets + n_faces
@@ -649,8 +653,9 @@ def main_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %d^3 %s %d-phase phantom, %d tets (%d labelled), %d interface faces, %d nodes, grid mesh edge %.3f jitter %.2f" % (
-            args.config, cfg["n"], vol.dtype.name, P, n_tets, int((snap["tet_label"] != 0).sum()), n_faces, n_nodes, edge, args.jitter),
+        "config": {"workload": "%s: %d^3 %s %d-phase phantom, %d tets (%d labelled), %d interface faces, %d nodes, %s" % (
+            args.config, cfg["n"], vol.dtype.name, P, n_tets, int((snap["tet_label"] != 0).sum()), n_faces, n_nodes,
+            ("mesh replayed from " + os.path.basename(args.dsc)) if args.dsc else "grid mesh edge %.3f jitter %.2f" % (edge, args.jitter)),
             "mean_mode": args.mean_mode, "force_mode": args.force_mode, "launch": "cuda graph replay" if graph is not None else "eager", "l2": "flushed between timed steps (256 MB write)",
             "partition": "tets (cut by sample count) / faces / nodes split in %d contiguous ranges, volume+snapshot replicated" % world,
             "comm": ("none" if world == 1 else ("fused exchange kernels over NVLink peer memory (CUDA IPC windows)" if p2p else "2 NCCL all-reduces")),

@@ -235,6 +235,17 @@ int dscgpu_init_labels(dscgpu_ctx *ctx, int n_thresholds, const int32_t *thresho
  * rounding (the node normal adds the face normals in ascending face order, the reference in get_faces(node) order). */
 int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uint8_t *vertex_bound, double *internal_forces);
 
+/* A9b -- the force loop of segment_function::thickenning_surface (DEMO/segment_function.cpp:1990-2051): the external force over the
+ * interface faces whose three nodes are not all in m_vertex_bound (segment_function::is_boundary(FaceKey), :2186-2196), and per face the
+ * mean and the mean absolute deviation of the scalar magnitudes of its Gauss points (:2030-2043); the reference splits the longest
+ * edge of a face when either exceeds get_avg_edge_length()*0.5*0.01 (:2046-2049, host: topology).
+ *   vertex_bound   n_nodes_buffer bytes (m_vertex_bound) or NULL to derive it from the snapshot
+ *   forces         3*n_nodes_buffer doubles (the reference then adds compute_internal_force_2's, :2053-2054)
+ *   face_mean / face_dev / face_evaluated   n_faces entries each (may be NULL); skipped faces report 0, 0, 0
+ * Same ordered sums as DSCGPU_FORCE_GATHER: forces and statistics bit-identical to the reference. */
+int dscgpu_thicken_forces(dscgpu_ctx *ctx, int nb_phase, const double *mean, const uint8_t *vertex_bound, double *forces, double *face_mean, double *face_dev,
+                          uint8_t *face_evaluated);
+
 /* SURVEY 8(f) row 3, second half -- get_node_displacement (DEMO/segment_function.cpp:581-584) and the non-topological part of
  * snapp_boundary (:466-541) for every node at once, so that the forces need not leave the device before set_destination:
  *   node_displacement = (forces + alpha internal_forces) dt, destination = pos + it; nodes of m_vertex_bound are aligned to the faces

@@ -103,6 +103,23 @@ def face_forces(vol, snap, nb_phase, mean, threads=1):
     return forces.reshape(-1, 3)
 
 
+def thicken_forces(vol, snap, nb_phase, mean, vb):
+    """Force loop of segment_function::thickenning_surface (DEMO/segment_function.cpp:1990-2051): (forces, face_mean, face_dev, evaluated)."""
+    vol = np.ascontiguousarray(vol)
+    pos = _c(snap["pos"], np.float64)
+    nnb = pos.size // 3
+    fn = _c(snap["face_nodes"], np.uint32)
+    ft = _c(snap["face_tets"], np.uint32)
+    tn = _c(snap["tet_nodes"], np.uint32)
+    tl = _c(snap["tet_label"], np.int32)
+    nf = fn.size // 3
+    forces = np.zeros(3 * nnb)
+    mu, dev, ev = np.zeros(nf), np.zeros(nf), np.zeros(nf, np.uint8)
+    lib().fo_thicken_forces(_dims(vol), DTYPE_CODE[vol.dtype], _p(vol), C.c_uint32(nnb), _p(pos), _p(tn), _p(tl), C.c_uint32(nf), _p(fn), _p(ft),
+                            _p(_c(vb, np.uint8)), C.c_int(nb_phase), _p(_c(mean, np.float64)), _p(forces), _p(mu), _p(dev), _p(ev))
+    return forces.reshape(-1, 3), mu, dev, ev
+
+
 def init_histogram(tet_label, tet_mean):
     """Histogram of initialization_discrete_opt (DEMO/segment_function.cpp:219-226) over the labelled tets."""
     m = np.asarray(tet_label) != 0

@@ -259,6 +259,58 @@ int fo_face_forces(const int dims[3], int dtype, const void *voxels, uint32_t n_
     return 0;
 }
 
+// Force loop of segment_function::thickenning_surface, DEMO/segment_function.cpp:1990-2051: compute_external_force's quadrature over the
+// interface faces that are not segment_function::is_boundary(FaceKey) (all three nodes in m_vertex_bound, :2186-2196), and per face
+// the mean and the mean absolute deviation of the magnitudes of its Gauss points (:2030-2043).  One thread (the reference's order).
+int fo_thicken_forces(const int dims[3], int dtype, const void *voxels, uint32_t n_nodes_buffer, const double *pos, const uint32_t *tet_nodes,
+                      const int32_t *tet_label, uint32_t n_faces, const uint32_t *face_nodes, const uint32_t *face_tets, const uint8_t *vb, int nb_phase,
+                      const double *mean, double *forces, double *face_mean, double *face_dev, uint8_t *face_evaluated)
+{
+    Vol V{dims[0], dims[1], dims[2], dtype, voxels};
+    memset(forces, 0, sizeof(double) * 3 * (size_t)n_nodes_buffer);
+    for (int64_t f = 0; f < (int64_t)n_faces; f++) {
+        face_mean[f] = face_dev[f] = 0; face_evaluated[f] = 0;
+        uint32_t t0 = face_tets[2 * f], t1 = face_tets[2 * f + 1];
+        if (t0 == 0xFFFFFFFFu || t1 == 0xFFFFFFFFu) continue;
+        const uint32_t *fn = face_nodes + 3 * f;
+        if (vb[fn[0]] && vb[fn[1]] && vb[fn[2]]) continue;
+        V3 pts[3] = {P(pos, fn[0]), P(pos, fn[1]), P(pos, fn[2])};
+        int phase0 = tet_label[t0] - 1, phase1 = tet_label[t1] - 1;
+        double c0 = phase0 >= 0 ? mean[phase0] : -0.3, c1 = phase1 >= 0 ? mean[phase1] : -0.3;
+        uint32_t tid = tet_label[t1] > tet_label[t0] ? t1 : t0;
+        V3 Norm = face_normal_wrt(pos, fn, tet_nodes + 4 * (size_t)tid);
+        const uint32_t *a = tet_nodes + 4 * (size_t)t0, *b = tet_nodes + 4 * (size_t)t1;
+        V3 b0 = mul(add(add(add(P(pos, a[0]), P(pos, a[1])), P(pos, a[2])), P(pos, a[3])), 0.25);
+        V3 b1 = mul(add(add(add(P(pos, b[0]), P(pos, b[1])), P(pos, b[2])), P(pos, b[3])), 0.25);
+        Norm = mul(Norm, dot(Norm, sub(b1, b0)));
+        Norm = divs(Norm, length(Norm));
+        double ar = area(pts[0], pts[1], pts[2]);
+        int gs = gauss_set(ar);
+        std::vector<double> mags;
+        for (int g = DSC_GAUSS_SET_OFFSET[gs]; g < DSC_GAUSS_SET_OFFSET[gs + 1]; g++) {
+            const double *gp = DSC_GAUSS + 4 * g;
+            V3 p = add(add(mul(pts[0], gp[1]), mul(pts[1], gp[2])), mul(pts[2], gp[3]));
+            double I = V.at_f(p);
+            double magnitude = (2 * I - c0 - c1) * (c0 - c1) * gp[0] * ar;
+            V3 fv = mul(Norm, magnitude);
+            for (int ii = 0; ii < 3; ii++) {
+                V3 d = mul(fv, gp[1 + ii]);
+                double *o = forces + 3 * (size_t)fn[ii];
+                o[0] += d.x; o[1] += d.y; o[2] += d.z;
+            }
+            mags.push_back(magnitude);
+        }
+        double mu = 0;
+        for (double m : mags) mu += m;
+        mu /= mags.size();
+        double dev = 0;
+        for (double m : mags) dev += std::abs(m - mu);
+        dev /= mags.size();
+        face_mean[f] = mu; face_dev[f] = dev; face_evaluated[f] = 1;
+    }
+    return 0;
+}
+
 // image3d::build_sum_table, DEMO/image3d.cpp:166-176: S[x,y,z] = S[x,y,z-1] + V[x,y,z].
 // segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232).
 //   pass 1, interface faces in ascending key order that are not all-vertex-bound (segment_function::is_boundary(FaceKey),

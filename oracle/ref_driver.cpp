@@ -53,6 +53,7 @@ static double now_s()
 
 struct Args {
     std::string mode = "dump";
+    std::string save_dsc; // dump mode: also write the mesh with the reference's own writer (is_mesh::export_tet_mesh, is_mesh/mesh_io.cpp:298-314)
     std::string volume_path;
     std::string vol_dtype = "u8"; // u8 | u16 | f32 | f64
     int dims[3] = {0, 0, 0};
@@ -91,6 +92,7 @@ static Args parse(int argc, char **argv)
         else if (k == "--jitter-seed") a.jitter_seed = (unsigned)atoi(next().c_str());
         else if (k == "--iters") a.iters = atoi(next().c_str());
         else if (k == "--out") a.out = next();
+        else if (k == "--save-dsc") a.save_dsc = next();
         else if (k == "--repeat") a.repeat = atoi(next().c_str());
         else if (k == "--points-in-tet") a.n_points_in_tet = atoi(next().c_str());
         else { fprintf(stderr, "unknown arg %s\n", k.c_str()); exit(2); }
@@ -488,6 +490,12 @@ int main(int argc, char **argv)
             seg.segment();
         }
         dump_state(a, seg, a.out);
+        if (!a.save_dsc.empty()) { // what DSC "save" does: extract_tet_mesh (is_mesh/is_mesh.h:1686-1706) + export_tet_mesh
+            std::vector<vec3> points;
+            std::vector<int> tets, tet_labels;
+            dsc->extract_tet_mesh(points, tets, tet_labels);
+            is_mesh::export_tet_mesh(a.save_dsc, points, tets, tet_labels);
+        }
         return 0;
     }
     if (a.mode == "time") {

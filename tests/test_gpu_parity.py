@@ -456,3 +456,18 @@ def test_node_destinations_equal_the_restated_snapp_boundary(case):
     assert np.array_equal(cur, exp_cur)
     assert st["max_boundary_dis"] == max_b and st["scale"] == scale
     assert st["real_max"] == (length(dis2) * adapt)[act].max()
+
+
+def test_thickening_forces_and_face_statistics(case, flat):
+    """A9b: the force loop of thickenning_surface (DEMO/segment_function.cpp:1990-2051) -- forces without the faces whose nodes are all
+    vertex-bound, per-face mean and mean absolute deviation of the Gauss-point magnitudes -- against the oracle's restatement: bit for bit."""
+    g, img, seg = case
+    snap = golden_io.snapshot_of(g)
+    vb = flat.vertex_bound(snap)
+    F_ref, mu_ref, dev_ref, ev_ref = flat.thicken_forces(g["volume"], snap, g["meta"]["nb_phase"], g["mean"], vb)
+    F, mu, dev, ev = seg.thicken_forces(mean=g["mean"], vertex_bound=vb)
+    assert np.array_equal(ev, ev_ref) and 0 < ev.sum() <= len(ev)
+    assert np.array_equal(F, F_ref)
+    assert np.array_equal(mu, mu_ref) and np.array_equal(dev, dev_ref)
+    F2, _, _, ev2 = seg.thicken_forces(mean=g["mean"])  # vertex-bound flags derived on the device
+    assert np.array_equal(ev2, ev_ref) and np.array_equal(F2, F_ref)

@@ -2062,4 +2062,13 @@ __global__ void __launch_bounds__(128) face_force_stats_kernel(MeshView m, const
     face_dev[f] = dev;
 }
 
+// rows[i] = forces[active_nodes[i]]: the rows of the force array that can be non-zero, for the compact read-back
+__global__ void gather_rows_kernel(const double *__restrict__ forces, const unsigned *__restrict__ active_nodes, unsigned n, double *__restrict__ rows)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t v = active_nodes[i];
+    rows[3 * (size_t)i] = forces[3 * v]; rows[3 * (size_t)i + 1] = forces[3 * v + 1]; rows[3 * (size_t)i + 2] = forces[3 * v + 2];
+}
+
 } // namespace dsc

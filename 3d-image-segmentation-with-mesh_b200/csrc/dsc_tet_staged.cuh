@@ -488,7 +488,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
                     unsigned *recu = reinterpret_cast<unsigned *>(rec);
                     recu[32 * kRecBase] = slot_a + rel - fold;
                     recu[32 * kRecMeta] = (ride ? 1u : 0u) | ((ride && L + 1 == NB) ? 2u : 0u) | ((unsigned)(label & 0xff) << 8) | ((unsigned)L << 16);
-                    const double w = v * (n == 1 ? 1.0 : (n == 2 ? 0.125 : (n == 3 ? 1.0 / 27.0 : 0.015625))); // sums-only weight v / n^3 (tolerance quantity)
+                    const double w = v / (double)(n * n * n); // the same expression as in tet_exact_list_kernel: a tet contributes the same integer whichever path it takes
                     recu[32 * kRecW] = (unsigned)__double2loint(w); recu[32 * (kRecW + 1)] = (unsigned)__double2hiint(w);
                     recu[32 * kRecV] = (unsigned)__double2loint(v); recu[32 * (kRecV + 1)] = (unsigned)__double2hiint(v);
                     if (lane == 0) s_hdr[slot] = make_int4((int)base_t, NB, (int)bx, (int)bxy);
@@ -703,11 +703,24 @@ __global__ void __launch_bounds__(256, 4) tet_exact_list_kernel(const __grid_con
             for (int u = 0; u < U; u++) acc.add(val[u], u);
         }
         double s, q;
-        acc.result(s, q);
+        if constexpr (VoxTraits<VoxT>::integral) {
+            // integers first, one division: the same number the staged stream forms for a tet (its lane adds all samples of its tet)
+            const unsigned is = __reduce_add_sync(0xffffffffu, acc.isum[0] + acc.isum[1]); // <= 729 * 65535
+            unsigned long long iq = acc.isq;
+            if (WANT_SQ) {
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            s += shfl_xor_d(s, m);
-            if (WANT_SQ) q += shfl_xor_d(q, m);
+                for (int m = 16; m >= 1; m >>= 1) iq += __shfl_xor_sync(0xffffffffu, iq, m);
+            }
+            const double dn = VoxTraits<VoxT>::denom();
+            s = (double)is / dn;
+            q = WANT_SQ ? (double)iq / (dn * dn) : 0.0;
+        } else {
+            acc.result(s, q);
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                s += shfl_xor_d(s, m);
+                if (WANT_SQ) q += shfl_xor_d(q, m);
+            }
         }
         if (lane == 0) {
             const double w = v / (double)rows;

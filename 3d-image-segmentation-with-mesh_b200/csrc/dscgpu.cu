@@ -102,7 +102,11 @@ struct dscgpu_ctx {
     uint32_t upd_n_pos = 0, upd_n_tet = 0, upd_n_faces = 0; // the staged update (dscgpu_update_staging_get)
     bool upd_keys = false, upd_staged = false;
     bool forces_resident = false, iforces_resident = false; // ctx->forces / ctx->iforce (and nflags, vbound) hold the results of the last force calls on this snapshot
-    DevBuf ndisp, ndest;
+    DevBuf ndisp, ndest, crows;
+    int compact_forces = 0;      // dscgpu_image_force_eval(forces == NULL) reads back the rows of the nodes with interface faces only
+    PinBuf h_nact;               // their number, copied to the host when the node -> face table is built
+    cudaEvent_t ev_nact = nullptr;
+    uint32_t compact_n = 0xffffffffu; // rows of the last compact read-back (0xffffffff: the last read-back was the full array)
     bool init_means_valid = false; // o_mean holds the per-tet means of the current snapshot (dscgpu_init_histogram)
     double *comm_rows = nullptr; // local scatter target of the force exchange: 3 doubles per active node, zero between evaluations
 
@@ -855,6 +859,11 @@ int build_csr_device(dscgpu_ctx *ctx)
         ctx->launches += 2;
     }
     CK(cudaGetLastError());
+    // the number of nodes with interface faces, for the compact read-back of the forces (read on the host much later: no wait)
+    CK(ctx->h_nact.ensure(sizeof(unsigned)));
+    if (!ctx->ev_nact) CK(cudaEventCreateWithFlags(&ctx->ev_nact, cudaEventDisableTiming));
+    CK(cudaMemcpyAsync(ctx->h_nact.p, ctr(ctx, 5), sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_nact, ctx->stream));
     return DSCGPU_OK;
 }
 
@@ -1059,10 +1068,10 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
     DevBuf *bufs[] = {&ctx->fgeo, &ctx->flab, &ctx->fint, &ctx->upd, &ctx->nflags, &ctx->iterm, &ctx->inorm, &ctx->iskip, &ctx->iforce, &ctx->tet_face_nodes, &ctx->tet_face_tets, &ctx->csr_flag, &ctx->csr_apos, &ctx->node_active, &ctx->csr_count, &ctx->csr_cursor, &ctx->fbuf, &ctx->fset, &ctx->pos4, &ctx->pos4f, &ctx->tet_nodes, &ctx->tet_label, &ctx->face_nodes, &ctx->face_tets, &ctx->face_isb, &ctx->node_off, &ctx->node_inc,
                       &ctx->partials, &ctx->sums, &ctx->mean, &ctx->forces, &ctx->counters, &ctx->o_total, &ctx->o_vol, &ctx->o_mean, &ctx->o_energy,
                       &ctx->o_variation, &ctx->o_hash, &ctx->o_nsamp, &ctx->ray_count, &ctx->ray_offset, &ctx->ray_cursor, &ctx->hits, &ctx->block_sums,
-                      &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit};
+                      &ctx->ray_psum, &ctx->ray_pcnt, &ctx->misc, &ctx->vbound, &ctx->pit, &ctx->stg_exact, &ctx->ndisp, &ctx->ndest, &ctx->crows};
     for (DevBuf *b : bufs) b->release();
     PinBuf *pins[] = {&ctx->h_pos4, &ctx->h_tet_nodes, &ctx->h_tet_label, &ctx->h_face_nodes, &ctx->h_face_tets, &ctx->h_face_isb, &ctx->h_node_off,
-                      &ctx->h_node_inc, &ctx->h_node_active, &ctx->h_out, &ctx->h_flag, &ctx->h_upd};
+                      &ctx->h_node_inc, &ctx->h_node_active, &ctx->h_out, &ctx->h_flag, &ctx->h_upd, &ctx->h_nact};
     for (PinBuf *b : pins) b->release();
     if (ctx->d_vol) cudaFree(ctx->d_vol);
     if (ctx->d_sum_table) cudaFree(ctx->d_sum_table);
@@ -1083,6 +1092,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
         if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]);
     }
     for (int i = 0; i < 20; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+    if (ctx->ev_nact) cudaEventDestroy(ctx->ev_nact);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1958,7 +1968,26 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
         TimerScope ts(ctx, DSCGPU_T_D2H);
         CK(cudaMemcpyAsync(h, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h + 3 * kMaxPhase, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        if (fbytes) CK(cudaMemcpyAsync(h + 4 * kMaxPhase, ctx->forces.p, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (fbytes && !forces && ctx->compact_forces && ctx->ev_nact) {
+            // only the rows that can be non-zero cross PCIe: nodes with interface faces (about one node in seven on a DSC mesh)
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            ARG(cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone, "the compact read-back cannot be captured");
+            CK(cudaEventSynchronize(ctx->ev_nact)); // recorded when the snapshot was committed
+            const unsigned na = std::min<unsigned>(*ctx->h_nact.as<unsigned>(), ctx->n_nodes);
+            CK(ctx->crows.ensure(3 * (size_t)na * sizeof(double) + 8));
+            CK(ctx->h_node_active.ensure((size_t)na * sizeof(unsigned) + 8));
+            if (na) {
+                gather_rows_kernel<<<(na + 255) / 256, 256, 0, ctx->stream>>>(ctx->forces.as<double>(), ctx->node_active.as<unsigned>(), na, ctx->crows.as<double>());
+                ctx->launches++;
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(h + 4 * kMaxPhase, ctx->crows.p, 3 * (size_t)na * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(ctx->h_node_active.p, ctx->node_active.p, (size_t)na * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            ctx->compact_n = na;
+        } else if (fbytes) {
+            CK(cudaMemcpyAsync(h + 4 * kMaxPhase, ctx->forces.p, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->compact_n = 0xffffffffu;
+        }
     }
     r = sync_and_check(ctx);
     if (r) return r;
@@ -1967,9 +1996,27 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
     return DSCGPU_OK;
 }
 
+int dscgpu_set_compact_forces(dscgpu_ctx *ctx, int on)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ctx->compact_forces = on ? 1 : 0;
+    return DSCGPU_OK;
+}
+
+int dscgpu_forces_compact_pinned(dscgpu_ctx *ctx, uint32_t *n_rows, const uint32_t **node_keys, const double **rows)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ARG(n_rows && node_keys && rows, "null output");
+    ARG(ctx->h_out.p && ctx->compact_n != 0xffffffffu, "the last dscgpu_image_force_eval did not read the forces back in compact form");
+    *n_rows = ctx->compact_n;
+    *node_keys = ctx->h_node_active.as<uint32_t>();
+    *rows = ctx->h_out.as<double>() + 4 * kMaxPhase;
+    return DSCGPU_OK;
+}
+
 const double *dscgpu_forces_pinned(dscgpu_ctx *ctx, uint32_t *n_nodes_buffer)
 {
-    if (!ctx || !ctx->h_out.p) return nullptr;
+    if (!ctx || !ctx->h_out.p || ctx->compact_n != 0xffffffffu) return nullptr; // (compact read-back: dscgpu_forces_compact_pinned)
     if (n_nodes_buffer) *n_nodes_buffer = ctx->n_nodes;
     return ctx->h_out.as<double>() + 4 * kMaxPhase;
 }

@@ -472,13 +472,23 @@ class SegmentFunction:
             self.n_nodes_buffer, self.n_tets, self.n_faces = len(pos), len(tn), len(fn)
         if mean_mode == MEAN_ZRAY and not self._img._has_table:
             self._img.build_sum_table()
-        # want_forces: True -> copied into a fresh array; "pinned" -> zero-copy view of the context's pinned result buffer
+        # want_forces: True -> copied into a fresh array; "pinned" -> zero-copy view of the context's pinned result buffer;
+        # "compact" -> (node keys, rows) of the nodes with interface faces only, views of the pinned buffers
+        self._img._check(self.lib.dscgpu_set_compact_forces(self._img._ctx, C.c_int(1 if want_forces == "compact" else 0)), "dscgpu_set_compact_forces")
         f = np.empty((self.n_nodes_buffer, 3)) if want_forces is True else None
         st = _PhaseStats()
         r = self.lib.dscgpu_image_force_eval(self._img._ctx, C.byref(sp) if sp is not None else None, C.c_int(self.NB_PHASE), C.c_int(mean_mode),
                                              C.c_int(force_mode), C.byref(st), _ptr(f))
         self._img._check(r, "dscgpu_image_force_eval")
         self._stats_out(st)
+        if want_forces == "compact" and self.n_nodes_buffer:
+            n = C.c_uint32(0)
+            keys, rows = C.POINTER(C.c_uint32)(), C.POINTER(C.c_double)()
+            self._img._check(self.lib.dscgpu_forces_compact_pinned(self._img._ctx, C.byref(n), C.byref(keys), C.byref(rows)), "dscgpu_forces_compact_pinned")
+            k = np.ctypeslib.as_array(keys, shape=(n.value,)) if n.value else np.zeros(0, np.uint32)
+            f = (k, np.ctypeslib.as_array(rows, shape=(n.value * 3,)).reshape(-1, 3) if n.value else np.zeros((0, 3)))
+            self._forces = None
+            return self._mean_intensities, f
         if want_forces == "pinned" and self.n_nodes_buffer:
             n = C.c_uint32(0)
             ptr = self.lib.dscgpu_forces_pinned(self._img._ctx, C.byref(n))

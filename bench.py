@@ -531,12 +531,14 @@ def main_b200(args):
     fill_staging()
     host_fill_ms = (time.perf_counter() - t_fill) * 1e3  # numpy copies into the pinned arrays; the adapter's is_mesh walk is timed in oracle/dropin_test.cpp
     h2d_bytes = n_nodes * 32 + n_tets * 20 + n_faces * (12 + 8 + 1)  # pos4, tet ids+labels, face ids/tets/flags; the CSR is built on the device
-    d2h_bytes = n_nodes * 24 + 4 * P * 8
+    n_active_nodes = len(np.unique(snap["face_nodes"]))
+    # one GPU: the forces come back as the rows of the nodes that have interface faces (+ their keys), every other row is zero
+    d2h_bytes = (n_active_nodes * 28 if world == 1 else n_nodes * 24) + 4 * P * 8
 
     def step_e2e():
         if world == 1:
             seg.staging(n_nodes, n_tets, n_faces)  # same pinned arrays (already filled); marks the snapshot dirty
-            seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode, want_forces="pinned")
+            seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode, want_forces="compact")
         else:
             seg.staging(n_nodes, n_tets, n_faces)
             if p2p:  # every rank sends 1/world of the snapshot over PCIe, the shares cross NVLink (dscgpu_commit_snapshot_sharded)
@@ -582,7 +584,7 @@ def main_b200(args):
 
         def step_incr():
             seg.update_commit(True)
-            seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode, want_forces="pinned")
+            seg.image_force_eval(None, mean_mode=mean_mode, force_mode=force_mode, want_forces="compact")
 
         for _ in range(3):
             step_incr()
@@ -641,6 +643,27 @@ def main_b200(args):
         except Exception as e:  # noqa: BLE001 -- never fail the bench line over the second baseline
             cpu_port = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
+    # ---- the estimator segment() really uses for the means (update_average_intensity: interface faces rasterised into z-rays over
+    # the prefix-sum table) and the energy read-out, device-timed by the library's events; reported next to the metric, not in it ----
+    zray = None
+    if world == 1 and mean_mode == pkg.MEAN_TET:
+        try:
+            seg.set_snapshot(snap)
+            img.build_sum_table()
+            seg.enable_timers(True)
+            m_z = seg.update_average_intensity()  # sizes the hit buffer
+            means_ms, energy_ms = [], []
+            for _ in range(5):
+                flush_l2(torch, l2_buf)
+                m_z = seg.update_average_intensity()
+                means_ms.append(seg.timer_ms("zray"))
+                flush_l2(torch, l2_buf)
+                seg.compute_energy(mean=m_z)
+                energy_ms.append(seg.timer_ms("zray"))
+            zray = {"means_ms": float(np.median(means_ms)), "energy_ms": float(np.median(energy_ms)), "mean": [float(x) for x in m_z],
+                    "phase_volume": [float(x) for x in seg._phase_volume], "what": "dscgpu_zray_means / dscgpu_zray_energy on the same snapshot, L2 flushed"}
+        except Exception as e:  # noqa: BLE001
+            zray = {"error": repr(e)}
     parity = None
     if not args.no_parity and mean_mode == pkg.MEAN_TET:
         try:
@@ -662,7 +685,7 @@ def main_b200(args):
             "samples_per_step": n_samples_all, "gauss_points_per_step": n_gauss_all},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
                 "steps": e2e_steps, "host_fill_ms": host_fill_ms},
-        "with_sumsq": with_sumsq, "parity": parity,
+        "with_sumsq": with_sumsq, "parity": parity, "zray": zray,
         "e2e_incremental": e2e_incr,
         "gpu_launches": int(launches_per_step[0] * args.steps),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_baseline_port": cpu_port, "clocks": clocks,

@@ -278,6 +278,12 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
  * valid until the next call on the context).  Passing forces == NULL to dscgpu_image_force_eval and reading them here
  * avoids one host-side copy per evaluation. */
 const double *dscgpu_forces_pinned(dscgpu_ctx *ctx, uint32_t *n_nodes_buffer);
+/* Compact read-back: with dscgpu_set_compact_forces(ctx, 1), dscgpu_image_force_eval(..., forces = NULL) brings back only the rows of
+ * the nodes that have interface faces -- every other row of _forces is zero (DEMO/segment_function.cpp:1431: the vector starts at
+ * zero and only nodes of interface faces are added to) -- about one node in seven on a DSC mesh.  dscgpu_forces_compact_pinned
+ * gives the pinned result: rows[3 i .. 3 i + 2] is the force of node node_keys[i], keys ascending. */
+int dscgpu_set_compact_forces(dscgpu_ctx *ctx, int on);
+int dscgpu_forces_compact_pinned(dscgpu_ctx *ctx, uint32_t *n_rows, const uint32_t **node_keys, const double **rows);
 
 /* Device-resident pieces for multi-GPU composition (NCCL all-reduce happens between them, on
  * the caller's stream set with dscgpu_set_stream):

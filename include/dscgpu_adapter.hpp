@@ -229,6 +229,18 @@ public:
         }
     }
 
+    // Second half of segment_function::update_vertex_boundary (DEMO/segment_function.cpp:2160-2172): m_vertex_bound = nodes of the interface
+    // faces that touch a BOUND_LABEL tet, from the snapshot on the device (the first half -- set_label(BOUND_LABEL) on the tets around
+    // boundary nodes, :2149-2157 -- edits the complex and stays with the host).  Call refresh() first.
+    void update_vertex_boundary_flags(SEG &seg)
+    {
+        const size_t nnb = snap_.pos.size() / 3;
+        std::vector<uint8_t> vb(nnb, 0);
+        check(dscgpu_vertex_bound(ctx_, vb.data()), "dscgpu_vertex_bound");
+        seg.m_vertex_bound.assign(nnb, false);
+        for (size_t i = 0; i < nnb; i++) if (vb[i]) seg.m_vertex_bound[i] = true;
+    }
+
     // Body of segment_function::initialization_discrete_opt (DEMO/segment_function.cpp:143-262): per-tet means and their
     // histogram on the device, the reference's own otsu_muti (pass it in: DEMO/otsu_multi.h defines it in a header) on the
     // host, the label rule on the device, set_label on the host.  Call refresh() first (labels: boundary layer = 0).

@@ -147,6 +147,15 @@ int main(int argc, char **argv)
             const std::vector<vec3> forces_ref = seg._forces, internal_ref = seg._internal_forces;
             // ---- GPU, same object, same mesh ----
             { double t = now_ms(); gpu.refresh(seg); t_gpu[0] = now_ms() - t; }
+            {   // m_vertex_bound from the device against the reference's (update_vertex_boundary ran above)
+                const std::vector<bool> vb_ref = seg.m_vertex_bound;
+                gpu.update_vertex_boundary_flags(seg);
+                size_t bad_vb = vb_ref.size() != seg.m_vertex_bound.size() ? 1 : 0;
+                for (size_t i = 0; i < vb_ref.size() && !bad_vb; i++) if (vb_ref[i] != seg.m_vertex_bound[i]) bad_vb++;
+                printf("iter %d: m_vertex_bound %s\n", it, bad_vb ? "DIFFERENT" : "flags identical");
+                if (bad_vb) failures++;
+                seg.m_vertex_bound = vb_ref;
+            }
             { double t = now_ms(); gpu.compute_internal_force_2(seg); t_gpu[3] = now_ms() - t; } // unprojected nodes bit for bit, projected ones to rounding
             double imax = 0, idmax = 0;
             size_t bad_i = seg._internal_forces.size() != internal_ref.size() ? 1 : 0;

@@ -275,7 +275,7 @@ def test_edge_cases(pkg):
 def test_rays_with_many_hits_take_the_slow_path(pkg, flat):
     """More stacked interfaces over one column than DSCGPU_MAX_RAY_HITS (the reference has no limit): such rays are sorted in place
     in the hit buffer; counts bit for bit as for every other ray."""
-    n_layers = 120
+    n_layers = 121  # 120 interfaces per column: an even number of hits (rays with an odd number are dropped by the reference)
     rng = np.random.default_rng(5)
     vol = rng.uniform(0, 1, (n_layers + 4, 4, 4)).astype(np.float32)
     pos = []
@@ -295,7 +295,7 @@ def test_rays_with_many_hits_take_the_slow_path(pkg, flat):
     fn, ft, fb = pkg.synthetic.interface_faces(tets, labels, len(pos))
     snap = {"pos": pos, "tet_nodes": tets, "tet_label": labels, "face_nodes": fn, "face_tets": ft, "face_is_boundary": fb}
     z = flat.zray(vol, snap, 2, mode=0)
-    assert len(fn) > 2 * 96 and z["count"].sum() > 0  # every column inside the prism crosses ~119 stacked interface triangles
+    assert z["hits_hist"][63] > 0 and z["count"].sum() > 0  # every column inside the prism crosses 120 stacked interface triangles
     img = pkg.Image3D(vol)
     img.build_sum_table()
     seg = pkg.SegmentFunction(img, 2)
@@ -471,3 +471,22 @@ def test_thickening_forces_and_face_statistics(case, flat):
     assert np.array_equal(mu, mu_ref) and np.array_equal(dev, dev_ref)
     F2, _, _, ev2 = seg.thicken_forces(mean=g["mean"])  # vertex-bound flags derived on the device
     assert np.array_equal(ev2, ev_ref) and np.array_equal(F2, F_ref)
+
+
+def test_compact_force_read_back(case, pkg):
+    """dscgpu_image_force_eval with the compact read-back: the rows of the nodes with interface faces, every other row of the full
+    result is zero and the rows equal the full result's."""
+    g, img, seg = case
+    snap = golden_io.snapshot_of(g)
+    mean, F = seg.image_force_eval(snap, mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_GATHER)
+    mean2, (keys, rows) = seg.image_force_eval(None, mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_GATHER, want_forces="compact")
+    # (the first call sums the tets in the chunks of the pipelined upload, the second in one pass: identical integers with the staged
+    # kernel; volumes it cannot take -- a row pitch that is not a multiple of 16 bytes -- use the w2 kernel, whose double sums re-associate)
+    np.testing.assert_allclose(mean, mean2, rtol=1e-13)
+    assert np.array_equal(keys, np.unique(snap["face_nodes"]))
+    if np.array_equal(mean, mean2):
+        assert np.array_equal(rows, F[keys])
+    else:
+        np.testing.assert_allclose(rows, F[keys], rtol=1e-10, atol=1e-12)
+    rest = np.ones(len(F), bool); rest[keys] = False
+    assert not F[rest].any()

@@ -107,11 +107,21 @@ __global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kerne
     if (lane < c.world) reinterpret_cast<unsigned long long *>(c.win[lane] + kCommSums)[((size_t)half * kCommMaxWorld + c.rank) * 3 * kMaxPhase + col] = bits;
     __threadfence_system();
     __syncthreads();
+    __shared__ int s_failed;
+    if (threadIdx.x == 0) s_failed = 0;
+    __syncthreads();
     if (threadIdx.x < c.world) {
         st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommFlagSums) + half * kCommMaxWorld + c.rank, e);
-        comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommFlagSums) + half * kCommMaxWorld + threadIdx.x, e, reinterpret_cast<int *>(mine + kCommError));
+        if (!comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommFlagSums) + half * kCommMaxWorld + threadIdx.x, e, reinterpret_cast<int *>(mine + kCommError)))
+            s_failed = 1;
     }
     __syncthreads();
+    if (s_failed) { // a peer never arrived: no partial result may pass for a sum (dscgpu_comm_error reports the timeout)
+        const int which = col / kMaxPhase, ph = col % kMaxPhase;
+        if (lane == 0 && ph < nb_phase) sums[which * nb_phase + ph] = __longlong_as_double(0x7ff8000000000000ll);
+        if (mean && threadIdx.x < nb_phase) mean[threadIdx.x] = __longlong_as_double(0x7ff8000000000000ll);
+        return;
+    }
     if (lane == 0) {
         const int which = col / kMaxPhase, ph = col % kMaxPhase;
         const unsigned long long *slot = reinterpret_cast<const unsigned long long *>(mine + kCommSums) + (size_t)half * kCommMaxWorld * 3 * kMaxPhase + col;
@@ -231,16 +241,23 @@ __global__ void __launch_bounds__(256) comm_force_fused_kernel(const ForceFusedA
         st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommFlagForce) + half * kCommMaxWorld + c.rank, e);
     // (3) wait for every rank's rows (local polling), add them in rank order
     __shared__ uint2 s_rng[kCommMaxWorld];
+    __shared__ int s_failed;
+    if (threadIdx.x == 0) s_failed = 0;
+    __syncthreads();
     if (threadIdx.x < c.world) {
-        comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommFlagForce) + half * kCommMaxWorld + threadIdx.x, e, reinterpret_cast<int *>(mine + kCommError));
+        if (!comm_wait(reinterpret_cast<const unsigned long long *>(mine + kCommFlagForce) + half * kCommMaxWorld + threadIdx.x, e, reinterpret_cast<int *>(mine + kCommError)))
+            s_failed = 1;
         const volatile uint2 *rp = reinterpret_cast<const volatile uint2 *>(mine + kCommRanges) + half * kCommMaxWorld + threadIdx.x;
         s_rng[threadIdx.x] = make_uint2(rp->x, rp->y);
     }
     __syncthreads();
     const unsigned n_active = min(*a.n_active_ptr, c.cap_rows);
+    const bool failed = s_failed != 0; // a peer never arrived: the rows read as NaN, not as a partial sum
     for (unsigned i = gtid; i < n_active; i += gsz) {
         double x = 0, y = 0, z = 0;
         bool any = false;
+        if (failed) { x = y = z = __longlong_as_double(0x7ff8000000000000ll); any = true; }
+        else
         for (int k = 0; k < c.world; k++) {
             if (i < s_rng[k].x || i >= s_rng[k].y) continue;
             const double *src = reinterpret_cast<const double *>(mine + comm_rows_offset(half, k, c.world, c.cap_rows)) + 3 * (size_t)i;

@@ -119,6 +119,10 @@ DSC_HD unsigned brick_index(int x, int y, int z, unsigned Sy, unsigned Sz)
     return (zp >> 2) * Sz + (yp >> 1) * Sy + ((xp >> 2) << 5) + ((zp & 3u) << 3) + ((yp & 1u) << 2) + (xp & 3u);
 }
 
+// Which tets a pass integrates: phases always, the boundary layer (label 0 = BOUND_LABEL, DEMO/image3d.h:23) when asked; a negative
+// label (DSCGPU_LABEL_FREE) marks a slot of a key-indexed snapshot that holds no tet: never.
+DSC_D bool tet_active(int label, int include_bound) { return label > 0 || (label == 0 && include_bound); }
+
 DSC_D V3 load_pos(const double4 *__restrict__ pos4, unsigned n)
 {
     const double2 *p = reinterpret_cast<const double2 *>(pos4 + n);
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(256) tet_integrate_kernel(const TetArgs a)
         int n3 = 0;
         if (valid) {
             label = __ldg(a.mesh.tet_label + t);
-            active = a.include_bound || label != 0;
+            active = tet_active(label, a.include_bound);
         }
         if (active) {
             const uint4 nd = __ldg(a.mesh.tet_nodes + t);
@@ -522,7 +526,7 @@ __global__ void __launch_bounds__(256, W2_MIN_BLOCKS) tet_integrate_w2_kernel(co
                 const unsigned t = base_t + lane;
                 const int label = __ldg(a.mesh.tet_label + t);
                 const uint4 nd = __ldg(a.mesh.tet_nodes + t); // with the label, not after it: one dependent round trip less per tile
-                active = a.include_bound || label != 0;
+                active = tet_active(label, a.include_bound);
                 meta = (label & 0xff) | (lane << 16);
                 if (active) {
                     const V3 p0 = load_pos(a.mesh.pos4, nd.x), p1 = load_pos(a.mesh.pos4, nd.y);
@@ -843,7 +847,7 @@ __global__ void relabel_area_kernel(MeshView m, const unsigned *__restrict__ tet
     const unsigned t = (unsigned)(i / nb_phase);
     const int k = (int)(i % nb_phase);
     const int old_label = m.tet_label[t];
-    if (old_label == 0) { energy[i] = -1.0; return; }
+    if (old_label <= 0) { energy[i] = -1.0; return; }
     double e = energy[i];
     for (int f = 0; f < 4; f++) {
         const unsigned ta = tet_face_tets[((size_t)t * 4 + f) * 2], tb = tet_face_tets[((size_t)t * 4 + f) * 2 + 1];
@@ -1778,7 +1782,7 @@ __global__ void __launch_bounds__(128) tet_mean_ordered_kernel(VolumeView vv, Me
 {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m.n_tets) return;
-    if (__ldg(m.tet_label + t) == 0) { tet_mean[t] = -1.0; return; }
+    if (__ldg(m.tet_label + t) <= 0) { tet_mean[t] = -1.0; return; }
     const VoxT *__restrict__ vol = static_cast<const VoxT *>(vv.data);
     const uint4 nd = __ldg(m.tet_nodes + t);
     const V3 p0 = load_pos(m.pos4, nd.x), p1 = load_pos(m.pos4, nd.y), p2 = load_pos(m.pos4, nd.z), p3 = load_pos(m.pos4, nd.w);
@@ -1804,7 +1808,7 @@ __global__ void __launch_bounds__(256) init_hist_kernel(const int *__restrict__ 
     sh[threadIdx.x] = 0;
     __syncthreads();
     for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tets; t += gridDim.x * blockDim.x) {
-        if (tet_label[t] == 0) continue;
+        if (tet_label[t] <= 0) continue;
         int idx = (int)(tet_mean[t] * 256);
         if (idx > 255) idx = 255;
         if (idx < 0) idx = 0; // a negative mean (negative voxels) would index out of bounds in the reference
@@ -1819,7 +1823,7 @@ __global__ void init_label_kernel(const int *__restrict__ tet_label, const doubl
 {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tets) return;
-    if (tet_label[t] == 0) { out[t] = 0; return; }
+    if (tet_label[t] <= 0) { out[t] = tet_label[t] < 0 ? tet_label[t] : 0; return; }
     int m = (int)(tet_mean[t] * 255);
     if (m >= 255) m = 255;
     int k = 0;

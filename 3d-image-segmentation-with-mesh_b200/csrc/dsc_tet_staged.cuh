@@ -366,7 +366,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
         load_ids(tile, label, nd);
         load_ids(tile1, label1, nd1);
         V3 p0 = {0, 0, 0}, p1 = p0, p2 = p0, p3 = p0;
-        if (a.include_bound || label != 0) {
+        if (tet_active(label, a.include_bound)) {
             p0 = load_pos(a.mesh.pos4, nd.x); p1 = load_pos(a.mesh.pos4, nd.y);
             p2 = load_pos(a.mesh.pos4, nd.z); p3 = load_pos(a.mesh.pos4, nd.w);
         }
@@ -374,13 +374,13 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
             const unsigned tile2 = fetch_tile();
             // positions of the next tile (its ids are here by now)
             V3 n0 = {0, 0, 0}, n1 = n0, n2 = n0, n3 = n0;
-            if (a.include_bound || label1 != 0) {
+            if (tet_active(label1, a.include_bound)) {
                 n0 = load_pos_now(a.mesh.pos4, nd1.x); n1 = load_pos_now(a.mesh.pos4, nd1.y);
                 n2 = load_pos_now(a.mesh.pos4, nd1.z); n3 = load_pos_now(a.mesh.pos4, nd1.w);
             }
             const unsigned base_t = a.tet_begin + tile * 32;
             const unsigned t = base_t + lane;
-            const bool active = t < a.tet_end && (a.include_bound || label != 0);
+            const bool active = t < a.tet_end && tet_active(label, a.include_bound);
             bool cand = false;
             int L = 0;
             double v = 0;

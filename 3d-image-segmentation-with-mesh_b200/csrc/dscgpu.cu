@@ -103,6 +103,7 @@ struct dscgpu_ctx {
     bool upd_keys = false, upd_staged = false;
     bool forces_resident = false, iforces_resident = false; // ctx->forces / ctx->iforce (and nflags, vbound) hold the results of the last force calls on this snapshot
     DevBuf ndisp, ndest, crows;
+    int overlap_geom = 0;        // tet passes of the per-iteration entry points start the mean-independent half of the force pass next to their exact-list kernel
     int compact_forces = 0;      // dscgpu_image_force_eval(forces == NULL) reads back the rows of the nodes with interface faces only
     PinBuf h_nact;               // their number, copied to the host when the node -> face table is built
     cudaEvent_t ev_nact = nullptr;
@@ -549,7 +550,7 @@ int tet_pass_finish(dscgpu_ctx *ctx, int nb_phase, double *d_sums_out, double *d
 
 // tet pass + finalize over this context's partition; leaves sums (3*nb) and means on the device
 int run_tet_pass(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const double *c, double *d_total, double *d_vol, double *d_mean,
-                 double *d_energy, double *d_variation, double *d_sums_out, double *d_mean_out, int want_sq = 1)
+                 double *d_energy, double *d_variation, double *d_sums_out, double *d_mean_out, int want_sq = 1, bool fork_geom = false)
 {
     TetPassOut o;
     o.d_total = d_total; o.d_vol = d_vol; o.d_mean = d_mean; o.d_energy = d_energy; o.d_variation = d_variation;
@@ -559,6 +560,12 @@ int run_tet_pass(dscgpu_ctx *ctx, int nb_phase, int include_bound, int nc, const
         TimerScope ts(ctx, DSCGPU_T_TET);
         r = tet_pass_range(ctx, nb_phase, include_bound, nc, c, o, ctx->tet_b, ctx->tet_e, want_sq);
         if (r) return r;
+        // The staged kernel owns every SM (one CTA each, the whole register file); what follows it -- the exact list, the finalize -- is
+        // small: the geometry half of the force pass (normals, areas, trilinear samples; it does not need the means) runs next to them
+        if (fork_geom && ctx->overlap_geom && ctx->n_faces && !ctx->geom_async) {
+            r = dscgpu_face_geometry_async(ctx);
+            if (r) return r;
+        }
         r = launch_exact_list(ctx);
         if (r) return r;
     }
@@ -1955,7 +1962,7 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
         if (!ctx->has_sum_table) { ctx->err = "dscgpu_build_sum_table has not been called"; return DSCGPU_ERR_NO_SUMTABLE; }
         r = run_zray_sync(ctx, nb_phase, 0, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), nullptr, nullptr);
     } else if (!tet_done) {
-        r = run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), ctx->hot_want_sq);
+        r = run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->sums.as<double>(), ctx->mean.as<double>(), ctx->hot_want_sq, true);
     } else {
         r = DSCGPU_OK;
     }
@@ -1996,6 +2003,13 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
     return DSCGPU_OK;
 }
 
+int dscgpu_set_overlap_geometry(dscgpu_ctx *ctx, int on)
+{
+    if (!ctx) return DSCGPU_ERR_ARG;
+    ctx->overlap_geom = on ? 1 : 0;
+    return DSCGPU_OK;
+}
+
 int dscgpu_set_compact_forces(dscgpu_ctx *ctx, int on)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
@@ -2025,7 +2039,7 @@ int dscgpu_tet_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums)
 {
     NEED_SNAPSHOT();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && d_sums, "bad arguments");
-    return run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_sums, nullptr, ctx->hot_want_sq);
+    return run_tet_pass(ctx, nb_phase, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_sums, nullptr, ctx->hot_want_sq, true);
 }
 
 int dscgpu_zray_phase_sums_dev(dscgpu_ctx *ctx, int nb_phase, double *d_sums)
@@ -2145,7 +2159,12 @@ int dscgpu_comm_error(dscgpu_ctx *ctx)
     int e = 0;
     CK(cudaMemcpyAsync(&e, ctx->comm_win[ctx->comm_rank] + kCommError, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (e) { ctx->err = "peer exchange timed out: a rank did not reach the exchange within 2 s"; return DSCGPU_ERR_CUDA; }
+    if (e) { // reported once: the word is cleared, the results of that exchange are NaN
+        CK(cudaMemsetAsync(ctx->comm_win[ctx->comm_rank] + kCommError, 0, sizeof(int), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->err = "peer exchange timed out: a rank did not reach the exchange within 2 s";
+        return DSCGPU_ERR_CUDA;
+    }
     return DSCGPU_OK;
 }
 

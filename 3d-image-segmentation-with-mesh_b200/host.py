@@ -509,6 +509,10 @@ class SegmentFunction:
         self._img._check(self.lib.dscgpu_means_from_sums_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_sums_ptr), C.c_void_p(d_mean_ptr)),
                          "dscgpu_means_from_sums_dev")
 
+    def set_overlap_geometry(self, on=True):
+        """Tet passes of the per-iteration entry points start the geometry half of the force pass themselves (dscgpu_set_overlap_geometry)."""
+        self._img._check(self.lib.dscgpu_set_overlap_geometry(self._img._ctx, C.c_int(1 if on else 0)), "dscgpu_set_overlap_geometry")
+
     def face_geometry_async(self):
         """Starts the mean-independent half of the external force on the context's second stream (joined by the next gather-mode force call)."""
         self._img._check(self.lib.dscgpu_face_geometry_async(self._img._ctx), "dscgpu_face_geometry_async")

@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--dsc", default=None, help="replay a mesh saved by a reference run (iter_N.dsc, is_mesh/mesh_io.cpp:298-314) on the volume of --config instead of the generated grid mesh")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap-geometry", action="store_true", help="one GPU: keep the geometry half of the force pass behind the tet pass (A/B)")
     ap.add_argument("--no-parity", action="store_true", help="skip the comparison of the step's outputs with the flat oracle (outside the timed region)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
     ap.add_argument("--overlap-forces", action="store_true",
@@ -336,6 +337,8 @@ def main_b200(args):
             return out
         pkg.distributed.connect_peers(seg, rank, world, n_nodes, gather_handles, snapshot_bytes=32 * n_nodes + 20 * n_tets + 21 * n_faces + 4096)
         dist.barrier()  # every window exists and is mapped before the first exchange kernel runs
+    if world == 1 and force_mode == pkg.FORCE_GATHER and mean_mode == pkg.MEAN_TET and not args.no_overlap_geometry:
+        seg.set_overlap_geometry(True)  # the mean-independent half of the force pass runs next to the tail of the tet pass
     d_sums = torch.zeros(3 * P, dtype=torch.float64, device=dev)
     d_mean = torch.zeros(P, dtype=torch.float64, device=dev)
     d_forces = torch.zeros(3 * n_nodes, dtype=torch.float64, device=dev)

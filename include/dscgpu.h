@@ -45,6 +45,9 @@ enum dscgpu_status {
 
 /* rays with more interface hits than this are resolved in place in the hit buffer (slow path) instead of in registers / local memory */
 #define DSCGPU_MAX_RAY_HITS 96
+/* tet_label of a slot that holds no tet (key-indexed snapshots keep one slot per key of the tet buffer): skipped by every pass, whatever
+ * include_bound says; its per-tet outputs are -1 */
+#define DSCGPU_LABEL_FREE (-1)
 
 typedef struct dscgpu_ctx dscgpu_ctx;
 
@@ -298,6 +301,10 @@ int dscgpu_means_from_sums_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_su
  * the means; the next DSCGPU_FORCE_GATHER force call (dscgpu_face_forces[_dev]) joins it and only forms and adds the vectors.
  * Optional: without it the force call computes that part itself.  Call it after the snapshot (and partition) is in place. */
 int dscgpu_face_geometry_async(dscgpu_ctx *ctx);
+/* With on = 1, dscgpu_tet_phase_sums_dev and the tet pass of dscgpu_image_force_eval start dscgpu_face_geometry_async themselves, right
+ * after their main kernel: the geometry half of the force pass then runs next to the short kernels that end the tet pass.  Use it
+ * when a force call follows every tet pass (the per-iteration pattern); results are unchanged. */
+int dscgpu_set_overlap_geometry(dscgpu_ctx *ctx, int on);
 int dscgpu_face_forces_dev(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, double *d_forces);
 
 /* -- multi-GPU exchange over NVLink peer memory ------------------------------------------------------------------------ */

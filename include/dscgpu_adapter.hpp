@@ -63,7 +63,7 @@ struct Snapshot {
 
 // DSC is DSC::DeformableSimplicialComplex<> (or any ISMesh with the same getters).
 // key_indexed: the tet arrays have one entry per slot of the tet buffer (get_no_tets_buffer(), index = raw key; free slots
-// carry label 0 and are skipped by every kernel) instead of one per valid tet.  deform() collapses and splits simplices in
+// carry DSCGPU_LABEL_FREE and are skipped by every kernel) instead of one per valid tet.  deform() collapses and splits simplices in
 // every iteration, so a dense list shifts all the time; with key-indexed arrays an unchanged tet keeps its place and
 // ImageEnergy::refresh can send differences only.
 template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s, bool key_indexed = false)
@@ -83,7 +83,7 @@ template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s, bool key_inde
         const size_t ntb = dsc.get_no_tets_buffer();
         s.tet_key.resize(ntb);
         s.tet_nodes.assign(4 * ntb, 0u);
-        s.tet_label.assign(ntb, 0);
+        s.tet_label.assign(ntb, DSCGPU_LABEL_FREE);
         for (size_t k = 0; k < ntb; k++) s.tet_key[k] = (uint32_t)k;
         for (auto tit = dsc.tetrahedra_begin(); tit != dsc.tetrahedra_end(); tit++) {
             const size_t k = (size_t)(unsigned)tit.key();
@@ -251,8 +251,8 @@ public:
         const std::vector<int> thres = otsu_muti(std::vector<int>(hist.begin(), hist.end()), seg.NB_PHASE);
         std::vector<int32_t> t32(thres.begin(), thres.end()), labels(snap_.tet_label.size(), 0);
         check(dscgpu_init_labels(ctx_, (int)t32.size(), t32.data(), labels.data()), "dscgpu_init_labels");
-        for (size_t i = 0; i < labels.size(); i++) // (free slots of a key-indexed snapshot carry label 0: never touched)
-            if (labels[i] != 0) seg._dsc->set_label(typename std::decay<decltype(seg._dsc->tetrahedra_begin().key())>::type(snap_.tet_key[i]), labels[i]);
+        for (size_t i = 0; i < labels.size(); i++) // (free slots of a key-indexed snapshot carry a negative label: never touched)
+            if (labels[i] > 0) seg._dsc->set_label(typename std::decay<decltype(seg._dsc->tetrahedra_begin().key())>::type(snap_.tet_key[i]), labels[i]);
     }
 
     // Body of segment_function::compute_internal_force_2; m_vertex_bound is read from seg (update_vertex_boundary ran before).

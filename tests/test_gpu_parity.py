@@ -490,3 +490,35 @@ def test_compact_force_read_back(case, pkg):
         np.testing.assert_allclose(rows, F[keys], rtol=1e-10, atol=1e-12)
     rest = np.ones(len(F), bool); rest[keys] = False
     assert not F[rest].any()
+
+
+@pytest.mark.parametrize("variant", [0, 16512, 131072 | 16512])
+def test_free_slots_of_a_key_indexed_snapshot_are_skipped(pkg, flat, variant):
+    """Slots that hold no tet (label DSCGPU_LABEL_FREE = -1, nodes 0 0 0 0) take part in nothing, also with include_bound: the sums are
+    those of the mesh without them, their per-tet outputs are -1."""
+    g = golden_io.load("sph48_f32")
+    snap = golden_io.snapshot_of(g)
+    nt = len(snap["tet_label"])
+    free = np.arange(5, nt + 40, 97)
+    tn = np.insert(snap["tet_nodes"], np.minimum(free, nt), 0, axis=0)
+    tl = np.insert(snap["tet_label"], np.minimum(free, nt), -1)
+    # face_tets index the tet array: shift them past the inserted slots
+    is_free = tl == -1
+    new_index = np.flatnonzero(~is_free)
+    ft = snap["face_tets"].copy()
+    ok = ft != 0xFFFFFFFF
+    ft[ok] = new_index[ft[ok]].astype(np.uint32)
+    snap2 = dict(snap, tet_nodes=tn.astype(np.uint32), tet_label=tl.astype(np.int32), face_tets=ft)
+    img = pkg.Image3D(g["volume"])
+    seg = pkg.SegmentFunction(img, g["meta"]["nb_phase"])
+    seg.set_tet_variant(variant)
+    seg.set_snapshot(snap)
+    a = seg.tet_integrate(include_bound=True)
+    Fa = seg.compute_external_force(mean=a["phase_mean"])
+    seg.set_snapshot(snap2)
+    b = seg.tet_integrate(include_bound=True)
+    assert np.all(b["total"][is_free] == -1.0) and np.all(b["vol"][is_free] == -1.0)
+    assert np.array_equal(b["total"][~is_free], a["total"]) and np.array_equal(b["vol"][~is_free], a["vol"])
+    np.testing.assert_allclose(b["phase_total"], a["phase_total"], rtol=1e-12)
+    assert np.array_equal(seg.compute_external_force(mean=a["phase_mean"]), Fa)
+    img.close()

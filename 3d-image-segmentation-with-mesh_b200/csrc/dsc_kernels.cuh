@@ -1408,15 +1408,18 @@ template <typename VoxT> __global__ void __launch_bounds__(128) force_atomic_ker
 // column runs the same sequential recurrence, so the table is bit-exact; loads/stores are coalesced
 // along x.
 // =================================================================================================
-template <typename VoxT> __global__ void sum_table_kernel(const VoxT *__restrict__ vol, double *__restrict__ table, int X, int Y, int Z)
+template <typename VoxT, bool SQUARES = false> __global__ void sum_table_kernel(const VoxT *__restrict__ vol, double *__restrict__ table, int X, int Y, int Z)
 {
     const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t XY = (size_t)X * Y;
     if (col >= XY) return;
-    double s = decode<VoxT>(vol[col]);
+    // SQUARES: the same table over I^2, for the data term of compute_energy (zray_resolve_kernel, mode 1); not a reference structure
+    double v = decode<VoxT>(vol[col]);
+    double s = SQUARES ? v * v : v;
     table[col] = s;
     for (int z = 1; z < Z; z++) {
-        s = s + decode<VoxT>(vol[col + (size_t)z * XY]);
+        v = decode<VoxT>(vol[col + (size_t)z * XY]);
+        s = s + (SQUARES ? v * v : v);
         table[col + (size_t)z * XY] = s;
     }
 }
@@ -1594,6 +1597,7 @@ struct ResolveArgs {
     double c[kMaxPhase];       // mode 1: phase means
     const unsigned *ray_count;
     const unsigned *ray_offset;
+    const double *sq_table;      // mode 1: prefix sums of I^2 along z (null: add the voxels of every interval one by one)
     uint2 *hits;                 // rays with more than kMaxRayHits hits are sorted in place
     unsigned hits_cap;
     unsigned col_begin, col_end; // column range of this partition
@@ -1654,6 +1658,23 @@ template <typename VoxT> __global__ void __launch_bounds__(128) zray_resolve_ker
                         int lo = z1, hi = z2; // image3d::sum_line_z clamps (image3d.cpp:193-201)
                         if (hi >= Z) { hi = Z - 1; if (lo >= Z) lo = Z - 1; }
                         sum += a.vol.sum_table[(size_t)hi * XY + col] - a.vol.sum_table[(size_t)lo * XY + col];
+                    } else if (a.sq_table) {
+                        // sum over k in (z1, z2) of (I_k - c)^2 = S2 - 2 c S1 + c^2 n from the two prefix tables (1e-6 quantity: the
+                        // reference adds the squares one by one, :2470-2473); voxels past the last slice read 0 (image3d.cpp:480-491)
+                        const double cc = a.c[phase];
+                        const int n_all = z2 - 1 - z1; // k = z1 + 1 .. z2 - 1
+                        if (n_all > 0) {
+                            const int hi = min(z2 - 1, Z - 1);
+                            double s1 = 0, s2 = 0;
+                            int n_in = 0;
+                            if (hi > z1) {
+                                n_in = hi - z1;
+                                s1 = a.vol.sum_table[(size_t)hi * XY + col] - a.vol.sum_table[(size_t)z1 * XY + col];
+                                s2 = a.sq_table[(size_t)hi * XY + col] - a.sq_table[(size_t)z1 * XY + col];
+                            }
+                            sum += (s2 - 2.0 * cc * s1) + cc * cc * (double)n_all;
+                            (void)n_in;
+                        }
                     } else {
                         const double cc = a.c[phase];
                         for (int k = z1 + 1; k < z2; k++) {

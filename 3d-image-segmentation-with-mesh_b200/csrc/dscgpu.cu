@@ -70,8 +70,8 @@ struct dscgpu_ctx {
     int dims[3] = {0, 0, 0};
     int dtype = DSCGPU_F32;
     void *d_vol = nullptr;
-    double *d_sum_table = nullptr;
-    bool has_sum_table = false;
+    double *d_sum_table = nullptr, *d_sq_table = nullptr; // z prefix sums of I (image3d::_sum_table) and of I^2 (energy read-out)
+    bool has_sum_table = false, has_sq_table = false;
     double *d_tet_bary = nullptr;
     float4 *d_tet_bary_f = nullptr;
     float4 *d_tet_lat = nullptr;
@@ -747,6 +747,7 @@ int run_zray(dscgpu_ctx *ctx, int nb_phase, int mode, const double *c_host, doub
     rs.mode = mode;
     for (int k = 0; k < kMaxPhase; k++) rs.c[k] = (c_host && k < nb_phase) ? c_host[k] : 0.0;
     rs.ray_count = ra.ray_count; rs.ray_offset = ra.ray_offset; rs.hits = ra.hits; rs.hits_cap = ra.hits_cap;
+    rs.sq_table = (mode == 1 && ctx->has_sum_table && ctx->has_sq_table) ? ctx->d_sq_table : nullptr;
     // ray partition: contiguous column range derived from the tet partition fraction
     unsigned col_b = 0, col_e = (unsigned)XY;
     if (ctx->n_tets && !(ctx->tet_b == 0 && ctx->tet_e == ctx->n_tets)) {
@@ -1082,6 +1083,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
     for (PinBuf *b : pins) b->release();
     if (ctx->d_vol) cudaFree(ctx->d_vol);
     if (ctx->d_sum_table) cudaFree(ctx->d_sum_table);
+    if (ctx->d_sq_table) cudaFree(ctx->d_sq_table);
     if (ctx->d_tet_bary) cudaFree(ctx->d_tet_bary);
     if (ctx->d_tet_bary_f) cudaFree(ctx->d_tet_bary_f);
     if (ctx->d_tet_lat) cudaFree(ctx->d_tet_lat);
@@ -1125,6 +1127,7 @@ void *dscgpu_volume_ptr_dev(dscgpu_ctx *ctx)
 {
     if (!ctx) return nullptr;
     ctx->vol_flags_valid = false;
+    ctx->has_sq_table = false;
     ctx->stg_state = 0; // the fixed-point scales depend on the largest voxel
     return ctx->d_vol;
 }
@@ -1133,6 +1136,7 @@ int dscgpu_volume_modified(dscgpu_ctx *ctx)
 {
     if (!ctx) return DSCGPU_ERR_ARG;
     ctx->vol_flags_valid = false;
+    ctx->has_sq_table = false;
     ctx->stg_state = 0; // the fixed-point scales depend on the largest voxel
     return DSCGPU_OK;
 }
@@ -1146,7 +1150,7 @@ int dscgpu_volume_upload(dscgpu_ctx *ctx, const void *voxels_host)
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->vol_flags_valid = false;
     ctx->stg_state = 0; // the fixed-point scales depend on the largest voxel
-    ctx->has_sum_table = false;
+    ctx->has_sum_table = false; ctx->has_sq_table = false;
     return DSCGPU_OK;
 }
 double *dscgpu_sum_table_ptr_dev(dscgpu_ctx *ctx) { return ctx ? ctx->d_sum_table : nullptr; }
@@ -1168,6 +1172,7 @@ int dscgpu_build_sum_table(dscgpu_ctx *ctx)
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->has_sum_table = true;
+    ctx->has_sq_table = false; // built from the same voxels, on the next energy read-out
     return DSCGPU_OK;
 }
 
@@ -1660,6 +1665,20 @@ int dscgpu_zray_energy(dscgpu_ctx *ctx, int nb_phase, const double *mean, double
 {
     NEED_SNAPSHOT();
     ARG(nb_phase >= 1 && nb_phase <= DSCGPU_MAX_PHASE && mean, "bad arguments");
+    if (ctx->has_sum_table && !ctx->has_sq_table) { // the data term from two prefix tables instead of a loop over every interval
+        const size_t n = (size_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2], XY = (size_t)ctx->dims[0] * ctx->dims[1];
+        if (!ctx->d_sq_table) CK(cudaMalloc(&ctx->d_sq_table, n * sizeof(double)));
+        const unsigned grid = (unsigned)((XY + 127) / 128);
+        switch (ctx->dtype) {
+        case DSCGPU_U8: sum_table_kernel<unsigned char, true><<<grid, 128, 0, ctx->stream>>>((const unsigned char *)ctx->d_vol, ctx->d_sq_table, ctx->dims[0], ctx->dims[1], ctx->dims[2]); break;
+        case DSCGPU_U16: sum_table_kernel<unsigned short, true><<<grid, 128, 0, ctx->stream>>>((const unsigned short *)ctx->d_vol, ctx->d_sq_table, ctx->dims[0], ctx->dims[1], ctx->dims[2]); break;
+        case DSCGPU_F32: sum_table_kernel<float, true><<<grid, 128, 0, ctx->stream>>>((const float *)ctx->d_vol, ctx->d_sq_table, ctx->dims[0], ctx->dims[1], ctx->dims[2]); break;
+        default: sum_table_kernel<double, true><<<grid, 128, 0, ctx->stream>>>((const double *)ctx->d_vol, ctx->d_sq_table, ctx->dims[0], ctx->dims[1], ctx->dims[2]); break;
+        }
+        ctx->launches++;
+        CK(cudaGetLastError());
+        ctx->has_sq_table = true;
+    }
     double h_sums[3 * kMaxPhase];
     int r = run_zray_sync(ctx, nb_phase, 1, mean, ctx->sums.as<double>(), nullptr, h_sums, nullptr);
     if (r) return r;

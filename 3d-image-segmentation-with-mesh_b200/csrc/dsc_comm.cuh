@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kerne
 // (force_geom_kernel: normals, areas, trilinear samples) and the phase means, scatter-adds them into compact local rows and
 // notes the range of rows it touched; zeroes the full force array; (2) after a grid-wide barrier pushes ONLY that range into its
 // slot of every peer's window (a rank's faces touch about 1/world of the rows: the dense form pushed every row to every peer),
-// together with the range, then -- after a second barrier -- its flag; (3) waits for the peers' flags in its own window and
+// together with the range, then -- once its last block has pushed -- its flag; (3) waits for the peers' flags in its own window and
 // adds, for every row, the slots of the ranks whose range holds it, in rank order, into the full force array.
 // The grid must be co-resident (it spins on its own barrier counters): the host sizes it from the occupancy query.
 struct ForceFusedArgs {
@@ -228,17 +228,28 @@ __global__ void __launch_bounds__(256) comm_force_fused_kernel(const ForceFusedA
     if (hi < lo) lo = hi = 0u;
     hi = min(hi, c.cap_rows);
     const size_t off = comm_rows_offset(half, c.rank, c.world, c.cap_rows);
+    bool wrote = false;
     for (size_t i = 3 * (size_t)lo + gtid; i < 3 * (size_t)hi; i += gsz) {
         const double v = a.rows[i];
         a.rows[i] = 0.0;
         for (int k = 0; k < c.world; k++) reinterpret_cast<double *>(c.win[k] + off)[i] = v;
+        wrote = true;
     }
-    if (blockIdx.x == 0 && threadIdx.x < c.world)
+    if (blockIdx.x == 0 && threadIdx.x < c.world) {
         reinterpret_cast<uint2 *>(c.win[threadIdx.x] + kCommRanges)[half * kCommMaxWorld + c.rank] = make_uint2(lo, hi);
-    __threadfence_system();
-    comm_grid_barrier(loc + 1);
-    if (blockIdx.x == 0 && threadIdx.x < c.world)
-        st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommFlagForce) + half * kCommMaxWorld + c.rank, e);
+        wrote = true;
+    }
+    if (wrote) __threadfence_system(); // (a system-scope fence per thread is dear: only the threads that stored to a peer)
+    __syncthreads();
+    // the block that finishes last stores the flags; nobody waits for it here -- every block goes on to wait for the peers
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(loc + 1, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < c.world)
+            st_release_sys(reinterpret_cast<unsigned long long *>(c.win[threadIdx.x] + kCommFlagForce) + half * kCommMaxWorld + c.rank, e);
+    }
     // (3) wait for every rank's rows (local polling), add them in rank order
     __shared__ uint2 s_rng[kCommMaxWorld];
     __shared__ int s_failed;

@@ -291,7 +291,7 @@ constexpr int kStgRecBytes = kRecWords * 32 * 4;
 //             guard-band test, per-label fixed-point sums in registers; releases the slot through its "empty" mbarrier.
 // The phases of different tiles overlap: the dependent global loads of phase A, the TMA transfers and the sample streams of up to
 // `stg_slots` tiles are in flight on one SM.
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S>
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S, int PMAX>
 __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kernel(const __grid_constant__ TetArgs a)
 {
     extern __shared__ __align__(1024) unsigned char s_dyn[];
@@ -528,9 +528,9 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
         if (lane == 0 && nsamp) atomicAdd(a.sample_count, nsamp);
     } else {
         // ======================================= consumer =======================================
-        long long acc_tot[kMaxPhase], acc_sq[kMaxPhase], acc_vol[kMaxPhase];
+        long long acc_tot[PMAX], acc_sq[PMAX], acc_vol[PMAX]; // labels 1..PMAX (the host picks PMAX >= nb_phase: 4 or 8)
 #pragma unroll
-        for (int k = 0; k < kMaxPhase; k++) acc_tot[k] = acc_sq[k] = acc_vol[k] = 0;
+        for (int k = 0; k < PMAX; k++) acc_tot[k] = acc_sq[k] = acc_vol[k] = 0;
         for (;;) {
             unsigned q = 0;
             if (lane == 0) q = atomicAdd(&s_seq[1], 1u);
@@ -565,16 +565,19 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
                 r.d1xy = pk2(d1x, d1y); r.d1zz = pk2(d1z, d1z);
                 r.d2xy = pk2(d2x, d2y); r.d2zz = pk2(d2z, d2z);
                 r.d3xy = pk2(d3x, d3y); r.d3zz = pk2(d3z, d3z);
-                const float e1x = 0.25f * d1x, e1y = 0.25f * d1y, e1z = 0.25f * d1z, e2x = 0.25f * d2x, e2y = 0.25f * d2y, e2z = 0.25f * d2z;
-                const float e3x = 0.25f * d3x, e3y = 0.25f * d3y, e3z = 0.25f * d3z;
-                float ofz[6];
+                // centroid offsets oy E1 + ox E2 + oz E3, E_k = D_k / 4: quarters are exact, so (o/4) D_k in the FMA is the same product
+                const f32x2 Z2 = pk2(0.f, 0.f);
 #pragma unroll
                 for (int o = 0; o < 6; o++) {
-                    const float fx = (float)stg_off(o, 0), fy = (float)stg_off(o, 1), fz = (float)stg_off(o, 2);
-                    r.oxy[o] = pk2(fmaf(fz, e3x, fmaf(fx, e2x, fy * e1x)), fmaf(fz, e3y, fmaf(fx, e2y, fy * e1y)));
-                    ofz[o] = fmaf(fz, e3z, fmaf(fx, e2z, fy * e1z));
+                    const float fx = 0.25f * (float)stg_off(o, 0), fy = 0.25f * (float)stg_off(o, 1), fz = 0.25f * (float)stg_off(o, 2);
+                    r.oxy[o] = fma2(pk2(fz, fz), r.d3xy, fma2(pk2(fx, fx), r.d2xy, fma2(pk2(fy, fy), r.d1xy, Z2)));
                 }
-                r.ozz[0] = pk2(ofz[0], ofz[1]); r.ozz[1] = pk2(ofz[2], ofz[3]); r.ozz[2] = pk2(ofz[4], ofz[5]);
+#pragma unroll
+                for (int o = 0; o < 6; o += 2) { // z of offsets (o, o + 1) in the two halves
+                    const f32x2 cx = pk2(0.25f * (float)stg_off(o, 0), 0.25f * (float)stg_off(o + 1, 0)), cy = pk2(0.25f * (float)stg_off(o, 1), 0.25f * (float)stg_off(o + 1, 1));
+                    const f32x2 cz = pk2(0.25f * (float)stg_off(o, 2), 0.25f * (float)stg_off(o + 1, 2));
+                    r.ozz[o >> 1] = fma2(cz, r.d3zz, fma2(cx, r.d2zz, fma2(cy, r.d1zz, Z2)));
+                }
                 const float epz = rec[32 * (kRecEp + 2)];
                 r.epxy = pk2(rec[32 * (kRecEp + 0)], rec[32 * (kRecEp + 1)]); r.epzz = pk2(epz, epz);
                 r.thr = rec[32 * kRecThr];
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
                 long long fsq = 0;
                 if (WANT_SQ) fsq = __double2ll_rn(t_sq * w * a.stg_scale[1]);
 #pragma unroll
-                for (int k = 0; k < kMaxPhase; k++)
+                for (int k = 0; k < PMAX; k++)
                     if (label == k + 1 && k < a.nb_phase) {
                         acc_tot[k] += ftot;
                         acc_vol[k] += fvol;
@@ -623,7 +626,10 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
         }
         // per-warp rows (integers: any order gives the same sums)
 #pragma unroll
-        for (int k = 0; k < kMaxPhase; k++) {
+        if (lane < 3 * kMaxPhase) s_red[warp - kStgProd][lane] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < PMAX; k++) {
             long long x = acc_tot[k], y = acc_sq[k], z = acc_vol[k];
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) {

@@ -329,9 +329,9 @@ int ensure_staged(dscgpu_ctx *ctx)
     return DSCGPU_OK;
 }
 
-template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S> int launch_staged_t(dscgpu_ctx *ctx, TetArgs &a)
+template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S, int PMAX> int launch_staged_t(dscgpu_ctx *ctx, TetArgs &a)
 {
-    auto kern = tet_staged_kernel<VoxT, WANT_SQ, PER_TET, F32S>;
+    auto kern = tet_staged_kernel<VoxT, WANT_SQ, PER_TET, F32S, PMAX>;
     const int smem = ctx->stg_slots * (ctx->stg_slot_bytes + kStgRecBytes);
     static bool attr_set = false; // per instantiation
     static int attr_dev = -1;
@@ -401,11 +401,17 @@ int launch_exact_list(dscgpu_ctx *ctx)
     }
 }
 
-template <typename VoxT, bool F32S> int launch_staged_v(dscgpu_ctx *ctx, TetArgs &a)
+template <typename VoxT, bool F32S, int PMAX> int launch_staged_p(dscgpu_ctx *ctx, TetArgs &a)
 {
     const bool per_tet = a.tet_total || a.tet_vol || a.tet_mean;
-    if (a.want_sq) return per_tet ? launch_staged_t<VoxT, true, true, F32S>(ctx, a) : launch_staged_t<VoxT, true, false, F32S>(ctx, a);
-    return per_tet ? launch_staged_t<VoxT, false, true, F32S>(ctx, a) : launch_staged_t<VoxT, false, false, F32S>(ctx, a);
+    if (a.want_sq) return per_tet ? launch_staged_t<VoxT, true, true, F32S, PMAX>(ctx, a) : launch_staged_t<VoxT, true, false, F32S, PMAX>(ctx, a);
+    return per_tet ? launch_staged_t<VoxT, false, true, F32S, PMAX>(ctx, a) : launch_staged_t<VoxT, false, false, F32S, PMAX>(ctx, a);
+}
+
+// per-label accumulators live in registers of the consumer lanes: four labels cover the usual cases with half the registers of eight
+template <typename VoxT, bool F32S> int launch_staged_v(dscgpu_ctx *ctx, TetArgs &a)
+{
+    return a.nb_phase <= 4 ? launch_staged_p<VoxT, F32S, 4>(ctx, a) : launch_staged_p<VoxT, F32S, kMaxPhase>(ctx, a);
 }
 
 int launch_staged(dscgpu_ctx *ctx, TetArgs &a)

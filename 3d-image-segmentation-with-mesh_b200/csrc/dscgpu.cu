@@ -2042,6 +2042,32 @@ int dscgpu_set_compact_forces(dscgpu_ctx *ctx, int on)
     return DSCGPU_OK;
 }
 
+int dscgpu_read_forces_compact(dscgpu_ctx *ctx, const double *d_forces, uint32_t *n_rows, const uint32_t **node_keys, const double **rows)
+{
+    NEED_SNAPSHOT();
+    ARG(d_forces && n_rows && node_keys && rows, "null argument");
+    ARG(ctx->ev_nact, "no node -> face table on this snapshot");
+    CK(cudaEventSynchronize(ctx->ev_nact)); // recorded when the snapshot was committed
+    const unsigned na = std::min<unsigned>(*ctx->h_nact.as<unsigned>(), ctx->n_nodes);
+    CK(ctx->crows.ensure(3 * (size_t)na * sizeof(double) + 8));
+    CK(ctx->h_node_active.ensure((size_t)na * sizeof(unsigned) + 8));
+    CK(ctx->h_out.ensure(3 * (size_t)na * sizeof(double) + 4 * kMaxPhase * sizeof(double)));
+    double *h = ctx->h_out.as<double>() + 4 * kMaxPhase;
+    if (na) {
+        TimerScope ts(ctx, DSCGPU_T_D2H);
+        gather_rows_kernel<<<(na + 255) / 256, 256, 0, ctx->stream>>>(d_forces, ctx->node_active.as<unsigned>(), na, ctx->crows.as<double>());
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h, ctx->crows.p, 3 * (size_t)na * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_node_active.p, ctx->node_active.p, (size_t)na * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    int r = sync_and_check(ctx);
+    if (r) return r;
+    ctx->compact_n = na;
+    *n_rows = na; *node_keys = ctx->h_node_active.as<uint32_t>(); *rows = h;
+    return DSCGPU_OK;
+}
+
 int dscgpu_forces_compact_pinned(dscgpu_ctx *ctx, uint32_t *n_rows, const uint32_t **node_keys, const double **rows)
 {
     if (!ctx) return DSCGPU_ERR_ARG;

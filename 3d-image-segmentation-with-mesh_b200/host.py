@@ -517,6 +517,16 @@ class SegmentFunction:
         """Starts the mean-independent half of the external force on the context's second stream (joined by the next gather-mode force call)."""
         self._img._check(self.lib.dscgpu_face_geometry_async(self._img._ctx), "dscgpu_face_geometry_async")
 
+    def read_forces_compact(self, d_forces_ptr):
+        """(node keys, rows) of the nodes with interface faces from a device-resident force array: views of the pinned result buffers."""
+        n = C.c_uint32(0)
+        keys, rows = C.POINTER(C.c_uint32)(), C.POINTER(C.c_double)()
+        self._img._check(self.lib.dscgpu_read_forces_compact(self._img._ctx, C.c_void_p(d_forces_ptr), C.byref(n), C.byref(keys), C.byref(rows)),
+                         "dscgpu_read_forces_compact")
+        if not n.value:
+            return np.zeros(0, np.uint32), np.zeros((0, 3))
+        return np.ctypeslib.as_array(keys, shape=(n.value,)), np.ctypeslib.as_array(rows, shape=(n.value * 3,)).reshape(-1, 3)
+
     def face_forces_dev(self, d_mean_ptr, d_forces_ptr, mode=FORCE_GATHER):
         self._img._check(self.lib.dscgpu_face_forces_dev(self._img._ctx, C.c_int(self.NB_PHASE), C.c_void_p(d_mean_ptr), C.c_int(mode),
                                                          C.c_void_p(d_forces_ptr)), "dscgpu_face_forces_dev")

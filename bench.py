@@ -535,8 +535,8 @@ def main_b200(args):
     host_fill_ms = (time.perf_counter() - t_fill) * 1e3  # numpy copies into the pinned arrays; the adapter's is_mesh walk is timed in oracle/dropin_test.cpp
     h2d_bytes = n_nodes * 32 + n_tets * 20 + n_faces * (12 + 8 + 1)  # pos4, tet ids+labels, face ids/tets/flags; the CSR is built on the device
     n_active_nodes = len(np.unique(snap["face_nodes"]))
-    # one GPU: the forces come back as the rows of the nodes that have interface faces (+ their keys), every other row is zero
-    d2h_bytes = (n_active_nodes * 28 if world == 1 else n_nodes * 24) + 4 * P * 8
+    # the forces come back as the rows of the nodes that have interface faces (+ their keys), every other row is zero; N > 1: on rank 0
+    d2h_bytes = n_active_nodes * 28 + 4 * P * 8
 
     def step_e2e():
         if world == 1:
@@ -552,9 +552,9 @@ def main_b200(args):
             step_device()
             # every rank ends up with the same forces (rank-ordered sums): the job's result crosses PCIe once, on rank 0;
             # the other ranks read the means back (their synchronisation point)
-            if rank == 0:
-                pinned_forces.copy_(d_forces, non_blocking=True)
             pinned_mean.copy_(d_mean, non_blocking=True)
+            if rank == 0:
+                seg.read_forces_compact(d_forces.data_ptr())  # rows of the nodes with interface faces + their keys (synchronises)
             torch.cuda.synchronize(dev)
 
     for _ in range(3):

@@ -287,6 +287,9 @@ const double *dscgpu_forces_pinned(dscgpu_ctx *ctx, uint32_t *n_nodes_buffer);
  * gives the pinned result: rows[3 i .. 3 i + 2] is the force of node node_keys[i], keys ascending. */
 int dscgpu_set_compact_forces(dscgpu_ctx *ctx, int on);
 int dscgpu_forces_compact_pinned(dscgpu_ctx *ctx, uint32_t *n_rows, const uint32_t **node_keys, const double **rows);
+/* The same read-back for a force array that lives on the device (the output of dscgpu_face_forces_dev / _allreduce_dev): gathers the
+ * rows of the nodes with interface faces, copies them and their keys to the context's pinned buffers, synchronises. */
+int dscgpu_read_forces_compact(dscgpu_ctx *ctx, const double *d_forces, uint32_t *n_rows, const uint32_t **node_keys, const double **rows);
 
 /* Device-resident pieces for multi-GPU composition (NCCL all-reduce happens between them, on
  * the caller's stream set with dscgpu_set_stream):

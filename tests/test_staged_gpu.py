@@ -117,3 +117,30 @@ def test_non_cubic_and_partition(pkg, flat):
     sq, _, _ = flat.phase_reduce(lab, ref["sq"][:, 0], ref["vol"], P)
     np.testing.assert_allclose(o["phase_sumsq"], sq, rtol=1e-9)
     img.close()
+
+
+@pytest.mark.parametrize("slots,slot_kb", [(2, 24), (3, 12), (5, 8), (8, 24)])
+def test_slot_ring_under_stress(pkg, flat, slots, slot_kb, monkeypatch):
+    """The hand-over protocol of the slot ring (sequence counters + mbarrier) with few and small slots: items finish out of order, warps
+    run several rounds of the ring apart, boxes are split until they fit -- every run must give the oracle's per-tet sums bit for bit and the
+    same fixed-point per-label sums.  (compute-sanitizer is closed on this pool: this and the comparison with the CPU reference stand in.)"""
+    monkeypatch.setenv("DSCGPU_STG_SLOTS", str(slots))
+    monkeypatch.setenv("DSCGPU_STG_SLOT_KB", str(slot_kb))
+    syn = pkg.synthetic
+    vol = syn.shells_phantom(96, sigma=0.05, seed=9, dtype=np.float32)
+    snap = syn.build_case(vol, 6.3, 3, (0.3, 0.7), lambda pos, tets, base: flat.tet_integrate(vol, tets, pos, want_hash=False)["mean"],
+                          jitter=0.3, seed=23)
+    ref = flat.tet_integrate(vol, snap["tet_nodes"], snap["pos"], want_hash=False)
+    img = pkg.Image3D(vol)
+    seg = pkg.SegmentFunction(img, 3)
+    seg.set_snapshot(snap)
+    seg.set_tet_variant(STAGED)
+    first = None
+    for rep in range(6):
+        o = seg.tet_integrate(include_bound=True)
+        assert np.array_equal(o["vol"], ref["vol"]) and np.array_equal(o["total"], ref["total"]), rep
+        s = seg.tet_integrate(per_tet=False)
+        key = (tuple(s["phase_total"]), tuple(s["phase_volume"]), tuple(s["phase_sumsq"]))
+        first = first or key
+        assert key == first, rep
+    img.close()

@@ -522,3 +522,18 @@ def test_free_slots_of_a_key_indexed_snapshot_are_skipped(pkg, flat, variant):
     np.testing.assert_allclose(b["phase_total"], a["phase_total"], rtol=1e-12)
     assert np.array_equal(seg.compute_external_force(mean=a["phase_mean"]), Fa)
     img.close()
+
+
+def test_read_forces_compact_from_a_device_array(case, pkg):
+    """dscgpu_read_forces_compact: the rows of the nodes with interface faces out of a device-resident force array."""
+    torch = pytest.importorskip("torch")
+    g, img, seg = case
+    P = g["meta"]["nb_phase"]
+    n = len(g["pos"])
+    d_mean = torch.tensor(np.asarray(g["mean"], np.float64), device="cuda")
+    d_F = torch.zeros(3 * n, dtype=torch.float64, device="cuda")
+    seg.face_forces_dev(d_mean.data_ptr(), d_F.data_ptr(), pkg.FORCE_GATHER)
+    keys, rows = seg.read_forces_compact(d_F.data_ptr())
+    F = d_F.cpu().numpy().reshape(-1, 3)
+    assert np.array_equal(keys, np.unique(g["face_nodes"])) and np.array_equal(rows, F[keys])
+    assert np.array_equal(F, g["forces"].reshape(-1, 3)) or np.allclose(F, g["forces"].reshape(-1, 3), rtol=1e-6, atol=1e-9)

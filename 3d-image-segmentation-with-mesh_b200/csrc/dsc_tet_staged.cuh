@@ -460,6 +460,12 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
                 const bool ride = in && (L + 1 == NB || L + 2 == NB);
                 exact = exact || (in && !ride);
                 if (!__any_sync(0xffffffffu, ride)) continue;
+                const TmapBlob *map = a.stg_maps + (((exu - 1) * kStgMaxRows + (ey - 1)) * kStgMaxSlices + (ez - 1));
+#ifndef STG_NO_L2_PREFETCH
+                // the box on its way into L2 while this warp waits for a slot: the load into the slot then finds most of it there
+                if (lane == 0)
+                    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x0), "r"(y0), "r"(z0) : "memory");
+#endif
                 unsigned slot, q;
                 take_slot(slot, q);
                 const unsigned slot_a = box0 + slot * (unsigned)a.stg_slot_bytes;
@@ -499,7 +505,6 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
                     __threadfence_block();
                     *reinterpret_cast<volatile unsigned *>(&s_fillseq[slot]) = q + 1u;
                     mbar_arrive_tx(bar, bxy * (unsigned)ez);
-                    const TmapBlob *map = a.stg_maps + (((exu - 1) * kStgMaxRows + (ey - 1)) * kStgMaxSlices + (ez - 1));
                     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(slot_a), "l"(map),
                                  "r"(x0), "r"(y0), "r"(z0), "r"(bar)
                                  : "memory");

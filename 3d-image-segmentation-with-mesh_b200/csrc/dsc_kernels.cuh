@@ -1149,6 +1149,7 @@ struct ForceGeomArgs {
     unsigned begin, end; // face range
 };
 
+// (1, 2 or 4 lanes per face time the same: the kernel moves 115 MB of 32-byte sectors for its scattered trilinear reads at C4 -- 3.5 TB/s)
 template <typename VoxT> __global__ void __launch_bounds__(128) force_geom_kernel(const ForceGeomArgs a)
 {
     const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1192,6 +1193,39 @@ struct ForceNode2Args {
     const unsigned *active_nodes; // nodes that have interface faces, ascending (built with the CSR)
     const unsigned *n_active;     // device-resident length of that list
 };
+
+// The same sums with one lane per component (x, y, z; the fourth lane of a quad idles): a lane walks the node's faces in ascending order and
+// their Gauss points in table order and adds ITS component of every addend f * coord -- the reference's order of additions
+// (DEMO/segment_function.cpp:1466-1467), no shared memory, no cross-lane traffic, every node of the mesh resident at once.
+__global__ void __launch_bounds__(128) force_node3_kernel(const ForceNode2Args a)
+{
+    const int c = threadIdx.x & 3;
+    const unsigned n_active = __ldg(a.n_active);
+    for (unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; item < n_active; item += (gridDim.x * blockDim.x) >> 2) {
+        const unsigned v = __ldg(a.active_nodes + item);
+        if (c == 3 || v < a.begin || v >= a.end) continue;
+        const unsigned e0 = __ldg(a.mesh.node_off + v), e1 = __ldg(a.mesh.node_off + v + 1);
+        double acc = 0;
+#pragma unroll 2
+        for (unsigned e = e0; e < e1; e++) {
+            const unsigned inc = __ldg(a.mesh.node_inc + e);
+            const unsigned f = inc >> 2, corner = inc & 3u;
+            const int gs = a.fset[f];
+            if (gs < 0) continue;
+            const double *ge = a.fgeo + 4 * (size_t)f;
+            const double nc = __ldg(ge + c), area = __ldg(ge + 3);
+            const double c0 = phase_intensity(a.flab[2 * (size_t)f], a.nb_phase, a.mean), c1 = phase_intensity(a.flab[2 * (size_t)f + 1], a.nb_phase, a.mean);
+            const double *fi = a.fint + 12 * (size_t)f;
+            const int q0 = c_gauss_off[gs], ng = c_gauss_off[gs + 1] - q0;
+            for (int k = 0; k < ng; k++) {
+                const double w = c_gauss[4 * (q0 + k)], bc = c_gauss[4 * (q0 + k) + 1 + corner];
+                const double fvc = nc * ((2 * __ldg(fi + k) - c0 - c1) * (c0 - c1) * w * area); // component c of Norm * magnitude (:1463-1465)
+                acc += fvc * bc;
+            }
+        }
+        a.forces[3 * (size_t)v + c] = acc;
+    }
+}
 
 __global__ void __launch_bounds__(128) force_node2_kernel(const ForceNode2Args a)
 {

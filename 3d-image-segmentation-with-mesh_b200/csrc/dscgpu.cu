@@ -103,6 +103,7 @@ struct dscgpu_ctx {
     bool upd_keys = false, upd_staged = false;
     bool forces_resident = false, iforces_resident = false; // ctx->forces / ctx->iforce (and nflags, vbound) hold the results of the last force calls on this snapshot
     DevBuf ndisp, ndest, crows;
+    int force_node_form = 3;     // 3: force_node3_kernel (lane per component), 2: force_node2_kernel (8 lanes per node through shared memory); DSCGPU_FORCE_NODE_FORM
     int overlap_geom = 0;        // tet passes of the per-iteration entry points start the mean-independent half of the force pass next to their exact-list kernel
     int compact_forces = 0;      // dscgpu_image_force_eval(forces == NULL) reads back the rows of the nodes with interface faces only
     PinBuf h_nact;               // their number, copied to the host when the node -> face table is built
@@ -659,8 +660,13 @@ int run_forces(dscgpu_ctx *ctx, int nb_phase, const double *d_mean, int mode, do
         CK(cudaMemsetAsync(d_forces, 0, sizeof(double) * 3 * (size_t)ctx->n_nodes, ctx->stream));
         const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * nf);
         if (na.end > na.begin && max_active) {
-            const unsigned grid = std::min<unsigned>((max_active + 15) / 16, (unsigned)ctx->num_sms * 16);
-            force_node2_kernel<<<grid, 128, 0, ctx->stream>>>(na);
+            if (ctx->force_node_form == 2) {
+                const unsigned grid = std::min<unsigned>((max_active + 15) / 16, (unsigned)ctx->num_sms * 16);
+                force_node2_kernel<<<grid, 128, 0, ctx->stream>>>(na);
+            } else { // lane per component: every node resident at once
+                const unsigned grid = std::min<unsigned>((max_active + 31) / 32, (unsigned)ctx->num_sms * 16);
+                force_node3_kernel<<<grid, 128, 0, ctx->stream>>>(na);
+            }
             ctx->launches++;
         }
         CK(cudaGetLastError());
@@ -1067,6 +1073,7 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
         if (rf) return rf;
     }
     if (const char *ev = getenv("DSCGPU_FORCE_THREAD_GATHER")) ctx->force_thread_gather = atoi(ev);
+    if (const char *ev = getenv("DSCGPU_FORCE_NODE_FORM")) ctx->force_node_form = atoi(ev) == 2 ? 2 : 3;
     CK(cudaMemcpyToSymbolAsync(c_gauss, DSC_GAUSS, sizeof(DSC_GAUSS), 0, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyToSymbolAsync(c_gauss_off, DSC_GAUSS_SET_OFFSET, sizeof(DSC_GAUSS_SET_OFFSET), 0, cudaMemcpyHostToDevice, ctx->stream));
     int r = ensure_scratch(ctx);

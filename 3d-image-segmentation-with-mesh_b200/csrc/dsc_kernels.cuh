@@ -1895,8 +1895,11 @@ __global__ void init_label_kernel(const int *__restrict__ tet_label, const doubl
 //                       FaceKey), :2186-2196), and the face normal get_normal(fid) (src/DSC.h:3129-3133) for the node normals;
 //   iforce_node_kernel  thread per node that has interface faces: ordered sums over its CSR entries, then for interface,
 //                       non-crossing nodes with |f| > EPSILON the projection f = n dot(n, f) on the node normal
-//                       (DSC::get_normal(node), src/DSC.h:3138-3159; the reference adds the face normals in get_faces(node)
-//                       order, here ascending faces: the unprojected sums are bit-identical, the projected ones agree to rounding).
+//                       (DSC::get_normal(node), src/DSC.h:3138-3159).  The reference adds the face normals in get_faces(node)
+//                       order (is_mesh/is_mesh.h:691-699: edges of the node, faces of each edge, first occurrence): topology the
+//                       flat snapshot does not carry.  With ord_off / ord_idx (dscgpu_set_node_face_order) the normal is summed in
+//                       that order and every force is bit-identical; without, in ascending face order: the unprojected sums are
+//                       bit-identical, the projected ones agree to rounding.
 // =================================================================================================
 __global__ void __launch_bounds__(128) iforce_face_kernel(MeshView m, const unsigned char *__restrict__ vb, double *__restrict__ fterm, double *__restrict__ fnorm,
                                                           unsigned char *__restrict__ fskip)
@@ -1930,7 +1933,8 @@ __global__ void __launch_bounds__(128) iforce_face_kernel(MeshView m, const unsi
 
 __global__ void __launch_bounds__(128) iforce_node_kernel(MeshView m, const unsigned *__restrict__ active_nodes, const unsigned *__restrict__ n_active,
                                                           const unsigned char *__restrict__ node_flags, const double *__restrict__ fterm,
-                                                          const double *__restrict__ fnorm, const unsigned char *__restrict__ fskip, double *__restrict__ out)
+                                                          const double *__restrict__ fnorm, const unsigned char *__restrict__ fskip,
+                                                          const unsigned *__restrict__ ord_off, const unsigned *__restrict__ ord_idx, double *__restrict__ out)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *n_active) return;
@@ -1946,6 +1950,13 @@ __global__ void __launch_bounds__(128) iforce_node_kernel(MeshView m, const unsi
     }
     const unsigned char fl = node_flags[n];
     if ((fl & 1) && !(fl & 2) && length(F) > 1e-8) { // is_interface && !is_crossing && |f| > EPSILON (is_mesh/util.h:43)
+        if (ord_off) { // the caller's get_faces(node) order
+            S = V3{0, 0, 0};
+            for (unsigned k = ord_off[n]; k < ord_off[n + 1]; k++) {
+                const size_t f = ord_idx[k];
+                S = add(S, V3{fnorm[3 * f], fnorm[3 * f + 1], fnorm[3 * f + 2]});
+            }
+        }
         V3 norm = {0, 0, 0};
         if (!(length(S) < 1e-8)) norm = normalize(S);
         F = mul(norm, dot(norm, F));

@@ -103,6 +103,8 @@ struct dscgpu_ctx {
     bool upd_keys = false, upd_staged = false;
     bool forces_resident = false, iforces_resident = false; // ctx->forces / ctx->iforce (and nflags, vbound) hold the results of the last force calls on this snapshot
     DevBuf ndisp, ndest, crows;
+    DevBuf ord_off, ord_idx;     // dscgpu_set_node_face_order: get_faces(node) order of the interface faces, CSR by node key
+    bool has_face_order = false;
     int force_node_form = 3;     // 3: force_node3_kernel (lane per component), 2: force_node2_kernel (8 lanes per node through shared memory); DSCGPU_FORCE_NODE_FORM
     int overlap_geom = 0;        // tet passes of the per-iteration entry points start the mean-independent half of the force pass next to their exact-list kernel
     int compact_forces = 0;      // dscgpu_image_force_eval(forces == NULL) reads back the rows of the nodes with interface faces only
@@ -924,6 +926,7 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     ctx->geom_async = false;
     ctx->init_means_valid = false;
     ctx->forces_resident = ctx->iforces_resident = false;
+    ctx->has_face_order = false; // face indices and get_faces(node) belong to one snapshot
     ctx->has_tet_faces = false;
     CK(cudaMemsetAsync(ctr(ctx, 4), 0, sizeof(unsigned long long), ks));
     CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[16], 0));
@@ -1329,6 +1332,7 @@ static int commit_snapshot_impl(dscgpu_ctx *ctx, bool sharded)
     ctx->geom_async = false;
     ctx->init_means_valid = false;
     ctx->forces_resident = ctx->iforces_resident = false;
+    ctx->has_face_order = false; // face indices and get_faces(node) belong to one snapshot
     ctx->has_tet_faces = false;
 
     // choose lanes per tet from a sample of tet volumes (heuristic only; never affects results)
@@ -1408,6 +1412,7 @@ int dscgpu_update_commit(dscgpu_ctx *ctx, int replace_faces)
     CK(ctx->upd.ensure(L.total));
     CK(ctx->h_flag.ensure(sizeof(int)));
     ctx->forces_resident = ctx->iforces_resident = false; // the mesh moves: forces of the previous state do not apply
+    if (replace_faces) ctx->has_face_order = false;       // indices into the face list that is being replaced
     TimerScope ts(ctx, DSCGPU_T_H2D);
     // one H2D copy for everything that is scattered; the face arrays go straight to their place
     const size_t scatter_bytes = L.fn;
@@ -1775,6 +1780,25 @@ int dscgpu_init_labels(dscgpu_ctx *ctx, int n_thresholds, const int32_t *thresho
     return sync_and_check(ctx);
 }
 
+int dscgpu_set_node_face_order(dscgpu_ctx *ctx, uint32_t n_entries, const uint32_t *node_off, const uint32_t *face_idx)
+{
+    NEED_SNAPSHOT();
+    if (!node_off) { ctx->has_face_order = false; return DSCGPU_OK; }
+    ARG(n_entries == 0 || face_idx, "face_idx is required");
+    const size_t nn = ctx->n_nodes;
+    // checked on the host: a bad list would read outside the per-face arrays
+    ARG(node_off[0] == 0 && node_off[nn] == n_entries, "node_off must start at 0 and end at n_entries");
+    for (size_t i = 0; i < nn; i++) ARG(node_off[i] <= node_off[i + 1], "node_off must not decrease");
+    for (uint32_t k = 0; k < n_entries; k++) ARG(face_idx[k] < ctx->n_faces, "face_idx out of range");
+    CK(ctx->ord_off.ensure((nn + 1) * sizeof(unsigned)));
+    CK(ctx->ord_idx.ensure(((size_t)n_entries + 1) * sizeof(unsigned)));
+    CK(cudaMemcpyAsync(ctx->ord_off.p, node_off, (nn + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_entries) CK(cudaMemcpyAsync(ctx->ord_idx.p, face_idx, (size_t)n_entries * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    const int r = sync_and_check(ctx); // the host arrays may go away after the call
+    ctx->has_face_order = r == DSCGPU_OK;
+    return r;
+}
+
 int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uint8_t *vertex_bound, double *internal_forces)
 {
     NEED_SNAPSHOT();
@@ -1802,7 +1826,8 @@ int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uin
         const unsigned max_active = std::min<unsigned>(ctx->n_nodes, 3u * ctx->n_faces);
         iforce_node_kernel<<<(max_active + 127) / 128, 128, 0, ctx->stream>>>(mesh_view(ctx), ctx->node_active.as<unsigned>(), reinterpret_cast<const unsigned *>(ctr(ctx, 5)),
                                                                              ctx->nflags.as<unsigned char>(), ctx->iterm.as<double>(), ctx->inorm.as<double>(),
-                                                                             ctx->iskip.as<unsigned char>(), ctx->iforce.as<double>());
+                                                                             ctx->iskip.as<unsigned char>(), ctx->has_face_order ? ctx->ord_off.as<unsigned>() : nullptr,
+                                                                             ctx->has_face_order ? ctx->ord_idx.as<unsigned>() : nullptr, ctx->iforce.as<double>());
         ctx->launches += 2;
         CK(cudaGetLastError());
     }

@@ -396,12 +396,28 @@ class SegmentFunction:
         self._img._check(self.lib.dscgpu_init_labels(self._img._ctx, C.c_int(len(t)), _ptr(t) if len(t) else None, _ptr(out)), "dscgpu_init_labels")
         return out
 
-    def compute_internal_force_2(self, node_flags, vertex_bound=None):
+    def set_node_face_order(self, node_off, face_idx):
+        """The order in which DSC::get_normal(node) (src/DSC.h:3138-3159) adds the face normals: per node key the interface faces of
+        get_faces(node) (is_mesh/is_mesh.h:691-699) as indices into the snapshot's face list, CSR.  None drops it."""
+        if node_off is None:
+            self._img._check(self.lib.dscgpu_set_node_face_order(self._img._ctx, C.c_uint32(0), None, None), "dscgpu_set_node_face_order")
+            return
+        off = np.ascontiguousarray(node_off, np.uint32)
+        idx = np.ascontiguousarray(face_idx, np.uint32)
+        if len(off) != self.n_nodes_buffer + 1:
+            raise ValueError("node_off must have n_nodes_buffer + 1 entries")
+        self._img._check(self.lib.dscgpu_set_node_face_order(self._img._ctx, C.c_uint32(len(idx)), _ptr(off), _ptr(idx) if len(idx) else None),
+                         "dscgpu_set_node_face_order")
+
+    def compute_internal_force_2(self, node_flags, vertex_bound=None, face_order=None):
         """segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232).  node_flags: bit 0 is_interface,
-        bit 1 is_crossing per node (is_mesh attributes)."""
+        bit 1 is_crossing per node (is_mesh attributes).  face_order = (node_off, face_idx): see set_node_face_order; with it every
+        force is bit-identical to the reference's, without it the projected ones agree to rounding."""
         nf = np.ascontiguousarray(node_flags, np.uint8)
         if len(nf) != self.n_nodes_buffer:
             raise ValueError("node_flags must have one byte per node of the buffer")
+        if face_order is not None:
+            self.set_node_face_order(*face_order)
         vb = None if vertex_bound is None else np.ascontiguousarray(vertex_bound, np.uint8)
         f = np.empty((self.n_nodes_buffer, 3))
         self._img._check(self.lib.dscgpu_internal_forces(self._img._ctx, _ptr(nf), _ptr(vb), _ptr(f)), "dscgpu_internal_forces")

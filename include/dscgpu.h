@@ -234,9 +234,20 @@ int dscgpu_init_labels(dscgpu_ctx *ctx, int n_thresholds, const int32_t *thresho
  *                 is_crossing comes from connected components of the tets around a node (is_mesh/is_mesh.h:523-573): topology,
  *                 kept by the host; reading the attribute is free.
  *   vertex_bound  n_nodes_buffer bytes (m_vertex_bound) or NULL to derive it from the snapshot like dscgpu_vertex_bound.
- * Nodes that are not projected (crossing, or not interface) are bit-identical to the reference; projected ones agree to
- * rounding (the node normal adds the face normals in ascending face order, the reference in get_faces(node) order). */
+ * Nodes that are not projected (crossing, or not interface) are bit-identical to the reference.  Projected ones are bit-identical
+ * when dscgpu_set_node_face_order handed in the order of DSC::get_normal(node) for this snapshot; otherwise they agree to rounding
+ * (the node normal then adds the face normals in ascending face order). */
 int dscgpu_internal_forces(dscgpu_ctx *ctx, const uint8_t *node_flags, const uint8_t *vertex_bound, double *internal_forces);
+
+/* The order in which DSC::get_normal(node_key) (src/DSC.h:3138-3159) adds the normals of a node's interface faces: that of
+ * ISMesh::get_faces(NodeKey) (is_mesh/is_mesh.h:691-699 -- the node's edges, the faces of each edge, first occurrence; the DSC_CACHE
+ * copy get_faces_cache is filled by the same walk, src/DSC.h:243-251).  It is topology of the complex, not derivable from the flat arrays.
+ *   node_off  n_nodes_buffer + 1 offsets (node_off[0] = 0, node_off[n_nodes_buffer] = n_entries); nodes the reference does not
+ *             project (not is_interface, or is_crossing) may have empty ranges.
+ *   face_idx  n_entries indices into the snapshot's interface-face list, the faces of get_faces(node) with is_interface() in that order.
+ * Belongs to the snapshot it was set on: dscgpu_set_snapshot, dscgpu_commit_snapshot* and a dscgpu_update_snapshot that replaces the
+ * face list drop it.  node_off == NULL drops it.  Returns DSCGPU_ERR_ARG for offsets or indices out of range. */
+int dscgpu_set_node_face_order(dscgpu_ctx *ctx, uint32_t n_entries, const uint32_t *node_off, const uint32_t *face_idx);
 
 /* A9b -- the force loop of segment_function::thickenning_surface (DEMO/segment_function.cpp:1990-2051): the external force over the
  * interface faces whose three nodes are not all in m_vertex_bound (segment_function::is_boundary(FaceKey), :2186-2196), and per face the

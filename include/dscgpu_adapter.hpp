@@ -255,10 +255,44 @@ public:
             if (labels[i] > 0) seg._dsc->set_label(typename std::decay<decltype(seg._dsc->tetrahedra_begin().key())>::type(snap_.tet_key[i]), labels[i]);
     }
 
+    // The order in which DSC::get_normal(node) adds the face normals (src/DSC.h:3138-3159) for the nodes compute_internal_force_2
+    // projects: the interface faces of get_faces(node) -- with DSC_CACHE the complex's own per-node copy, which get_normal reads and the
+    // reference's segment() has filled anyway -- as indices into the snapshot's face list.  Topology, so it is walked here and handed
+    // to the device; with it the projected forces are bit-identical to the reference's, without it they agree to 1e-12.
+    void send_node_face_order(SEG &seg)
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        auto &dsc = *seg._dsc;
+        const size_t nnb = snap_.pos.size() / 3;
+        std::vector<int32_t> face_index(dsc.get_no_faces_buffer(), -1);
+        for (size_t i = 0; i < snap_.face_key.size(); i++) face_index[snap_.face_key[i]] = (int32_t)i;
+        std::vector<uint32_t> off(nnb + 1, 0), idx;
+        for (auto nit = dsc.nodes_begin(); nit != dsc.nodes_end(); nit++) {
+            const unsigned k = (unsigned)nit.key();
+            if (!(snap_.node_flags[k] & 1) || (snap_.node_flags[k] & 2)) continue;
+#ifdef DSC_CACHE
+            const auto &fids = *dsc.get_faces_cache(nit.key());
+#else
+            const auto fids = dsc.get_faces(nit.key());
+#endif
+            for (auto f : fids) {
+                const int32_t i = face_index[(unsigned)f];
+                if (i >= 0) { idx.push_back((uint32_t)i); off[k + 1]++; } // face_index holds exactly the is_interface() faces
+            }
+        }
+        for (size_t k = 0; k < nnb; k++) off[k + 1] += off[k];
+        check(dscgpu_set_node_face_order(ctx_, (uint32_t)idx.size(), off.data(), idx.data()), "dscgpu_set_node_face_order");
+        last_face_order_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    double last_face_order_ms() const { return last_face_order_ms_; }
+
     // Body of segment_function::compute_internal_force_2; m_vertex_bound is read from seg (update_vertex_boundary ran before).
-    void compute_internal_force_2(SEG &seg)
+    // exact_normal_order: walk get_faces(node) for the projected nodes first (send_node_face_order): bit-identical forces.
+    void compute_internal_force_2(SEG &seg, bool exact_normal_order = true)
     {
         const size_t nnb = snap_.pos.size() / 3;
+        if (exact_normal_order) send_node_face_order(seg);
+        else check(dscgpu_set_node_face_order(ctx_, 0, nullptr, nullptr), "dscgpu_set_node_face_order");
         forces_.resize(3 * nnb);
         std::vector<uint8_t> vb(nnb, 0);
         for (size_t i = 0; i < nnb && i < seg.m_vertex_bound.size(); i++) vb[i] = seg.m_vertex_bound[i] ? 1 : 0;
@@ -337,7 +371,7 @@ private:
     Snapshot snap_;
     bool have_snapshot_ = false, last_refresh_incremental_ = false;
     size_t last_moved_nodes_ = 0, last_changed_tets_ = 0;
-    double last_flatten_ms_ = 0, last_refresh_ms_ = 0;
+    double last_flatten_ms_ = 0, last_refresh_ms_ = 0, last_face_order_ms_ = 0;
     int volume_dtype_ = DSCGPU_F64;
     std::vector<double> forces_, dest_;
     bool move_init_ = false;

@@ -156,7 +156,7 @@ int main(int argc, char **argv)
                 if (bad_vb) failures++;
                 seg.m_vertex_bound = vb_ref;
             }
-            { double t = now_ms(); gpu.compute_internal_force_2(seg); t_gpu[3] = now_ms() - t; } // unprojected nodes bit for bit, projected ones to rounding
+            { double t = now_ms(); gpu.compute_internal_force_2(seg); t_gpu[3] = now_ms() - t; } // SURVEY 8(f) row 3 with the get_faces(node) order of the complex: bit for bit
             double imax = 0, idmax = 0;
             size_t bad_i = seg._internal_forces.size() != internal_ref.size() ? 1 : 0;
             for (size_t i = 0; i < internal_ref.size() && !bad_i; i++) for (int c = 0; c < 3; c++) {
@@ -185,8 +185,8 @@ int main(int argc, char **argv)
             double e_data = 0, e_area = 0;
             { double t = now_ms(); gpu.compute_energy(seg, &e_data, &e_area); t_gpu[4] = now_ms() - t; }
             if (!close_rel(e_data, e_data_ref, 1e-6) || !close_rel(e_area, e_area_ref, 1e-6)) ok = false;
-            if (bad_i || idmax > 1e-9 * std::max(imax, 1e-300)) ok = false;
-            printf("iter %d: internal forces max abs diff %.3g of %.3g\n", it, idmax, imax);
+            if (bad_i || idmax != 0.0) ok = false;
+            printf("iter %d: internal forces max abs diff %.3g of %.3g (get_faces(node) walk %.2f ms of the %.2f ms call)\n", it, idmax, imax, gpu.last_face_order_ms(), t_gpu[3]);
             printf("iter %d: %zu tets %zu interface faces | phase_volume %s | forces(ref means) %zu mismatching components | "
                    "forces(gpu means) max abs diff %.3g of %.3g | energy %.10g/%.10g vs %.10g/%.10g | %s\n",
                    it, gpu.snapshot().tet_label.size(), gpu.snapshot().face_is_boundary.size(),

@@ -134,8 +134,9 @@ def init_labels(tet_label, tet_mean, thresholds):
     return np.where(np.asarray(tet_label) != 0, lab, 0).astype(np.int32)
 
 
-def internal_forces(snap, node_flags, vb=None):
-    """segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232) over a flat snapshot."""
+def internal_forces(snap, node_flags, vb=None, order=None):
+    """segment_function::compute_internal_force_2 (DEMO/segment_function.cpp:2197-2232) over a flat snapshot.
+    order = (node_face_off, node_face_idx): the interface faces of get_faces(node) per node (bit-identical to the reference then)."""
     pos = _c(snap["pos"], np.float64)
     nnb = pos.size // 3
     fn = _c(snap["face_nodes"], np.uint32)
@@ -145,7 +146,12 @@ def internal_forces(snap, node_flags, vb=None):
     vb = vertex_bound(snap) if vb is None else _c(vb, np.uint8)
     nf = _c(node_flags, np.uint8)
     out = np.zeros(3 * nnb)
-    lib().fo_internal_forces(C.c_uint32(nnb), _p(pos), _p(tn), _p(tl), C.c_uint32(fn.size // 3), _p(fn), _p(ft), _p(vb), _p(nf), _p(out))
+    off = idx = None
+    if order is not None:
+        off, idx = _c(order[0], np.uint32), _c(order[1], np.uint32)
+        assert off.size == nnb + 1 and int(off[-1]) == idx.size
+    lib().fo_internal_forces(C.c_uint32(nnb), _p(pos), _p(tn), _p(tl), C.c_uint32(fn.size // 3), _p(fn), _p(ft), _p(vb), _p(nf),
+                             _p(off), _p(idx), _p(out))
     return out.reshape(-1, 3)
 
 

@@ -319,15 +319,17 @@ int fo_thicken_forces(const int dims[3], int dtype, const void *voxels, uint32_t
 //   pass 2, nodes that are interface and not crossing (node_flags bit 0 / bit 1, is_mesh/attributes.h:84-102) with
 //           |f| > EPSILON (1e-8, is_mesh/util.h:43): f = n * dot(n, f), n = DSC::get_normal(node) (src/DSC.h:3138-3159):
 //           the normalised sum of get_normal(face) over the node's interface faces, 0 when that sum is shorter than EPSILON.
-// The reference adds the face normals in get_faces(node) order, which a flat snapshot does not carry: here ascending face
-// order; the projected forces agree to rounding (1e-12), the unprojected sums bit for bit.
+// The reference adds the face normals in get_faces(node) order, which a flat snapshot does not carry.  order_off / order_idx
+// (may be NULL) hand it in: the interface faces of get_faces(node) for node n are order_idx[order_off[n] .. order_off[n+1]) as indices
+// into the face arrays -- then every force is bit-identical to the reference's.  Without them: ascending face order; the projected
+// forces agree to rounding (1e-12), the unprojected sums bit for bit.
 int fo_internal_forces(uint32_t n_nodes_buffer, const double *pos, const uint32_t *tet_nodes, const int32_t *tet_label, uint32_t n_faces,
                        const uint32_t *face_nodes, const uint32_t *face_tets, const uint8_t *vertex_bound, const uint8_t *node_flags,
-                       double *internal_forces)
+                       const uint32_t *order_off, const uint32_t *order_idx, double *internal_forces)
 {
     const double EPS = 1e-8;
     memset(internal_forces, 0, sizeof(double) * 3 * (size_t)n_nodes_buffer);
-    std::vector<double> nsum(3 * (size_t)n_nodes_buffer, 0.0);
+    std::vector<double> nsum(3 * (size_t)n_nodes_buffer, 0.0), fnorm(order_off ? 3 * (size_t)n_faces : 0, 0.0);
     for (uint32_t f = 0; f < n_faces; f++) {
         const uint32_t *fn = face_nodes + 3 * (size_t)f;
         uint32_t t0 = face_tets[2 * f], t1 = face_tets[2 * f + 1];
@@ -338,6 +340,7 @@ int fo_internal_forces(uint32_t n_nodes_buffer, const double *pos, const uint32_
         if (tid != 0xFFFFFFFFu) {
             V3 N = face_normal_wrt(pos, fn, tet_nodes + 4 * (size_t)tid);
             for (int k = 0; k < 3; k++) { double *o = nsum.data() + 3 * (size_t)fn[k]; o[0] += N.x; o[1] += N.y; o[2] += N.z; }
+            if (order_off) { fnorm[3 * (size_t)f] = N.x; fnorm[3 * (size_t)f + 1] = N.y; fnorm[3 * (size_t)f + 2] = N.z; }
         }
         if (vertex_bound[fn[0]] && vertex_bound[fn[1]] && vertex_bound[fn[2]]) continue;
         V3 p[3] = {P(pos, fn[0]), P(pos, fn[1]), P(pos, fn[2])};
@@ -357,6 +360,13 @@ int fo_internal_forces(uint32_t n_nodes_buffer, const double *pos, const uint32_
         V3 F{o[0], o[1], o[2]};
         if (!(length(F) > EPS)) continue;
         V3 S{nsum[3 * (size_t)n], nsum[3 * (size_t)n + 1], nsum[3 * (size_t)n + 2]};
+        if (order_off) {
+            S = V3{0, 0, 0};
+            for (uint32_t k = order_off[n]; k < order_off[n + 1]; k++) {
+                const double *q = fnorm.data() + 3 * (size_t)order_idx[k];
+                S = add(S, V3{q[0], q[1], q[2]});
+            }
+        }
         V3 norm{0, 0, 0};
         if (!(length(S) < EPS)) norm = normalize(S);
         V3 r = mul(norm, dot(norm, F));

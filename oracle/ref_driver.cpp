@@ -421,6 +421,22 @@ static void dump_state(const Args &a, segment_function &seg, const std::string &
     write_bin(dir, "init_labels.i32", init_labels);
     write_bin(dir, "internal_forces.f64", internal_forces);
     write_bin(dir, "node_flags.u8", node_flags);
+    // the order in which DSC::get_normal(node) (src/DSC.h:3138-3159) adds the face normals: the interface faces of get_faces(node)
+    // (is_mesh/is_mesh.h:691-699; the DSC_CACHE copy is filled by the same walk, src/DSC.h:243-251), as indices into the interface-face list
+    {
+        std::vector<int32_t> face_index(dsc->get_no_faces_buffer(), -1);
+        for (size_t i = 0; i < face_key.size(); i++) face_index[face_key[i]] = (int32_t)i;
+        std::vector<uint32_t> order_off(nnb + 1, 0), order_idx;
+        for (auto nit = dsc->nodes_begin(); nit != dsc->nodes_end(); nit++) {
+            const unsigned k = (unsigned)nit.key();
+            if (nit->is_interface() && !nit->is_crossing())
+                for (auto f : dsc->get_faces(nit.key()))
+                    if (dsc->get(f).is_interface()) { order_idx.push_back((uint32_t)face_index[(unsigned)f]); order_off[k + 1]++; }
+        }
+        for (unsigned k = 0; k < nnb; k++) order_off[k + 1] += order_off[k];
+        write_bin(dir, "node_face_off.u32", order_off);
+        write_bin(dir, "node_face_idx.u32", order_idx);
+    }
 
     write_bin(dir, "pos.f64", pos);
     write_bin(dir, "node_valid.u8", node_valid);

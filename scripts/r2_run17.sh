@@ -1,6 +1,5 @@
 #!/bin/bash
-for f in 4 2 1; do
-DSCGPU_GEOM_LANES=$f timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-parity --no-overlap-geometry 2>/dev/null | python -c "
-import json,sys
-d=json.loads([x for x in sys.stdin if x.startswith('{')][-1]); print('geom lanes $f:', round(d['ms_per_step'],4), d['kernel_ms'])"
-done
+# full GPU tests (incl. the drop-in run against the live reference objects) and the default bench line
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2w_tests.log 2>&1; tail -5 gpurun_out/r2w_tests.log
+grep -h "internal forces\|TOTAL\|refresh" gpurun_out/dropin_edge3.log 2>/dev/null | tail -8
+timeout 600 python bench.py > gpurun_out/r2w_bench_c4_n1.json 2> gpurun_out/r2w_bench_c4_n1.err; tail -c 300 gpurun_out/r2w_bench_c4_n1.json; tail -2 gpurun_out/r2w_bench_c4_n1.err

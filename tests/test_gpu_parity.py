@@ -137,6 +137,19 @@ def test_internal_force(case, flat):
     F2 = seg.compute_internal_force_2(fl, vertex_bound=g["vertex_bound"])
     assert np.array_equal(F2, F)
     assert np.array_equal(F, flat.internal_forces(golden_io.snapshot_of(g), fl, g["vertex_bound"]))  # same order as the flat oracle
+    # with the get_faces(node) order of the reference's complex (DSC::get_normal, src/DSC.h:3138-3159): every node bit for bit
+    order = (g["node_face_off"], g["node_face_idx"])
+    Fo = seg.compute_internal_force_2(fl, face_order=order)
+    assert np.array_equal(Fo, ref)
+    assert np.array_equal(Fo, flat.internal_forces(golden_io.snapshot_of(g), fl, g["vertex_bound"], order=order))
+    bad = g["node_face_idx"].copy()
+    if bad.size:
+        bad[0] = g["face_nodes"].size // 3  # one past the face list
+        with pytest.raises(Exception):
+            seg.set_node_face_order(g["node_face_off"], bad)
+    seg.set_node_face_order(None, None)
+    assert np.array_equal(seg.compute_internal_force_2(fl), F)  # dropped: ascending order again
+    seg.set_node_face_order(*order)
     # get_node_displacement (DEMO/segment_function.cpp:581-584)
     Fe = seg.compute_external_force(mean=g["mean"])
     d = seg.get_node_displacements(0.5)

@@ -96,8 +96,9 @@ def test_relabel_energies_bit_exact(case, flat):
 
 
 def test_internal_forces_match_the_reference(flat):
-    """compute_internal_force_2.  Nodes that are not projected on their normal (crossing or not interface) are
-    bit-identical; projected ones differ by the order in which the face normals of a node are added (rounding)."""
+    """compute_internal_force_2.  With the get_faces(node) order of the reference's complex (node_face_off /
+    node_face_idx of the fixture: what DSC::get_normal(node) iterates) every node is bit-identical.  Without it the nodes that are
+    not projected on their normal (crossing or not interface) are bit-identical and the projected ones differ by rounding."""
     for name in golden_io.CASES:
         g = golden_io.load(name)
         s = golden_io.snapshot_of(g)
@@ -109,6 +110,13 @@ def test_internal_forces_match_the_reference(flat):
         np.testing.assert_allclose(F, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
         assert np.abs(ref).max() > 1.0  # the fixture exercises the path
         assert np.array_equal(flat.internal_forces(s, fl), F)  # vertex_bound derived from the snapshot
+        off, idx = g["node_face_off"], g["node_face_idx"]
+        assert off.size == fl.size + 1 and off[-1] == idx.size and idx.size > 0
+        assert np.array_equal(flat.internal_forces(s, fl, g["vertex_bound"], order=(off, idx)), ref)
+        # the order lists exactly the interface faces around each projected node
+        cnt = np.bincount(s["face_nodes"].reshape(-1), minlength=fl.size)
+        projected = ~unprojected
+        assert np.array_equal(np.diff(off)[projected], cnt[projected])
 
 
 def test_initialisation_pass_matches_the_reference(flat):

@@ -76,7 +76,7 @@ template <bool FIXED>
 __global__ void __launch_bounds__(32 * 3 * kMaxPhase) comm_phase_allreduce_kernel(CommView c, const void *__restrict__ partials_v, int n_rows, int nb_phase, double s_tot,
                                                                                   double s_sq, double s_vol, double *sums, double *mean, unsigned *stg_counters)
 {
-    if (FIXED && threadIdx.x < 2 && stg_counters) stg_counters[threadIdx.x] = 0u; // staged kernel: tile counter, exact-list length
+    if (FIXED && threadIdx.x < 4 && stg_counters) stg_counters[threadIdx.x] = 0u; // staged kernel: tile counter, exact-list length, worked-off part
     const int col = threadIdx.x >> 5, lane = threadIdx.x & 31; // 24 warps, one per column of the partial rows
     unsigned char *mine = c.win[c.rank];
     __shared__ unsigned long long s_epoch;

@@ -219,6 +219,7 @@ struct TetArgs {
     unsigned *stg_counter;           // tile fetch counter, zero at launch
     int stg_chunk;                   // tiles a producer warp claims at a time
     unsigned *stg_exact_count;       // tets left to the exact path (stg_counter + 1), zero at the first launch of a pass
+    const unsigned *stg_exact_done;  // how many of them earlier tet_exact_list_kernel launches of this pass have worked off (stg_counter + 2)
     unsigned *stg_exact_list;        // ... and their indices, capacity tet_end - tet_begin
     unsigned long long *stg_acc;     // [3*kMaxPhase] fixed-point sums (total, sumsq, volume per label) the CTAs of both staged kernels add theirs to
     double stg_scale[3];             // fixed-point scales (powers of two) of total, sumsq, volume
@@ -2140,5 +2141,24 @@ __global__ void gather_rows_kernel(const double *__restrict__ forces, const unsi
     const size_t v = active_nodes[i];
     rows[3 * (size_t)i] = forces[3 * v]; rows[3 * (size_t)i + 1] = forces[3 * v + 1]; rows[3 * (size_t)i + 2] = forces[3 * v + 2];
 }
+
+// The whole result of an evaluation in one buffer, so that one copy brings it to the host: header [3 kMaxPhase sums | kMaxPhase means],
+// then rows[i] = forces[active_nodes[i]], then the keys active_nodes[0..n).
+__global__ void gather_result_kernel(const double *__restrict__ forces, const unsigned *__restrict__ active_nodes, unsigned n, const double *__restrict__ sums,
+                                     const double *__restrict__ mean, int nb_phase, double *__restrict__ out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (unsigned)(3 * nb_phase)) out[i] = sums[i];
+    if (i < (unsigned)nb_phase) out[3 * kMaxPhase + i] = mean[i];
+    if (i >= n) return;
+    double *rows = out + 4 * kMaxPhase;
+    unsigned *keys = reinterpret_cast<unsigned *>(rows + 3 * (size_t)n);
+    const unsigned v = active_nodes[i];
+    rows[3 * (size_t)i] = forces[3 * (size_t)v]; rows[3 * (size_t)i + 1] = forces[3 * (size_t)v + 1]; rows[3 * (size_t)i + 2] = forces[3 * (size_t)v + 2];
+    keys[i] = v;
+}
+
+// dst = src on the stream (a 4-byte device-to-device copy would queue on a copy engine behind the snapshot upload)
+__global__ void copy_u32_kernel(unsigned *dst, const unsigned *src) { *dst = *src; }
 
 } // namespace dsc

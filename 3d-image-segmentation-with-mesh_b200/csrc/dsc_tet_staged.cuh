@@ -670,6 +670,7 @@ __global__ void __launch_bounds__(256, 4) tet_exact_list_kernel(const __grid_con
     const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
     const int lane = threadIdx.x & 31;
     const unsigned n = *a.stg_exact_count;
+    const unsigned done = a.stg_exact_done ? *a.stg_exact_done : 0u; // entries an earlier launch of this pass has worked off
     const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     constexpr unsigned NONE = 0xffffffffu;
     auto entry = [&](unsigned i) { return i < n ? __ldg(a.stg_exact_list + i) : NONE; };
@@ -677,7 +678,7 @@ __global__ void __launch_bounds__(256, 4) tet_exact_list_kernel(const __grid_con
         lab = 0; nd = make_uint4(0, 0, 0, 0);
         if (t != NONE) { lab = __ldg(a.mesh.tet_label + t); nd = __ldg(a.mesh.tet_nodes + t); }
     };
-    unsigned i = wid;
+    unsigned i = done + wid;
     unsigned t = entry(i), t1 = entry(i + nw), t2 = NONE;
     int label, label1;
     uint4 nd, nd1;
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(32) tet_finalize_fixed_kernel(unsigned long lo
 {
     __shared__ double tot[kMaxPhase], vol[kMaxPhase];
     const int col = threadIdx.x;
-    if (col < 2 && stg_counters) stg_counters[col] = 0u;
+    if (col < 4 && stg_counters) stg_counters[col] = 0u;
     if (col < 3 * kMaxPhase) {
         const long long r = (long long)acc[col];
         acc[col] = 0ull;

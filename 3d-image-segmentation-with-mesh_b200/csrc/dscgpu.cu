@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cmath>
 #include <string>
+#include <chrono>
 #include <vector>
 #include <algorithm>
 #include <new>
@@ -67,6 +68,8 @@ struct dscgpu_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_chunk[20];
     int pipeline_chunks = 4; // tet-array upload chunks overlapped with the tet kernel in dscgpu_image_force_eval (0 = off)
+    double pipeline_ratio = 0.85; // size of a chunk relative to the one before it (bit 2 of pipeline_flags; DSCGPU_PIPELINE_RATIO)
+    int pipeline_flags = 7;  // bit 2: shrinking chunks; bit 0: face arrays right behind tet chunk 0 and the node -> face table built while chunk 1 is in flight; bit 1: exact list worked off per chunk (DSCGPU_PIPELINE_FLAGS)
     int dims[3] = {0, 0, 0};
     int dtype = DSCGPU_F32;
     void *d_vol = nullptr;
@@ -80,10 +83,11 @@ struct dscgpu_ctx {
     int tet_variant = 131072 | 128 | 16384; // see dscgpu_set_tet_variant; default = the staged kernel, w2 (clamp-free full batches on the sums-only path) for volumes it cannot describe
     // staged kernel (variant bit 131072, dsc_tet_staged.cuh): tensor-map family in device memory, tile counter, fixed-point scales
     TmapBlob *d_stg_maps = nullptr;
-    unsigned *d_stg_counter = nullptr; // [0] tile counter, [1] length of the exact list, then (at byte 16) the row of 3 * kMaxPhase fixed-point sums
+    unsigned *d_stg_counter = nullptr; // [0] tile counter, [1] length of the exact list, [2] its worked-off part, then (at byte 16) the row of 3 * kMaxPhase fixed-point sums
     DevBuf stg_exact;           // the exact list
     TetArgs stg_args;           // arguments of the staged launches of the running pass (for tet_exact_list_kernel at its end)
-    int stg_list_kernel = -1;   // which instantiation works the list off: (want_sq << 1 | per_tet), -1: no staged launch in this pass
+    int stg_list_kernel = -1;   // which instantiation works the list off: (want_sq << 1 | per_tet), -1: nothing on the list that a launch has not been issued for
+    bool stg_pass_open = false; // staged launches of this pass have been issued and its finalize has not
     bool stg_counters_dirty = true; // tile counter / list length may be non-zero (first use, or a pass that did not reach its finalize)
     int stg_state = 0;          // 0 not tried, 1 ready, -1 unavailable
     int stg_slot_bytes = 24 * 1024, stg_slots = 8;
@@ -111,6 +115,7 @@ struct dscgpu_ctx {
     PinBuf h_nact;               // their number, copied to the host when the node -> face table is built
     cudaEvent_t ev_nact = nullptr;
     uint32_t compact_n = 0xffffffffu; // rows of the last compact read-back (0xffffffff: the last read-back was the full array)
+    const uint32_t *compact_keys = nullptr; // their node keys (pinned)
     bool init_means_valid = false; // o_mean holds the per-tet means of the current snapshot (dscgpu_init_histogram)
     double *comm_rows = nullptr; // local scatter target of the force exchange: 3 doubles per active node, zero between evaluations
 
@@ -137,6 +142,12 @@ struct dscgpu_ctx {
     cudaEvent_t ev[DSCGPU_T_COUNT][2];
     bool ev_used[DSCGPU_T_COUNT];
     bool timers_on = false;
+    // DSCGPU_E2E_TRACE=1: time line of dscgpu_image_force_eval on stderr (events on both streams + when the host issued them)
+    bool trace_on = false;
+    struct TraceMark { const char *name; cudaEvent_t ev; double host_us; };
+    std::vector<TraceMark> trace;
+    std::vector<cudaEvent_t> trace_pool;
+    std::chrono::steady_clock::time_point trace_t0;
     uint64_t launches = 0;
     int lanes_per_tet = 0;
     int auto_lanes = 8;
@@ -199,6 +210,31 @@ int sync_and_check(dscgpu_ctx *ctx)
         }
     }
     return DSCGPU_OK;
+}
+
+void trace_mark(dscgpu_ctx *c, const char *name, cudaStream_t st)
+{
+    if (!c->trace_on) return;
+    if (c->trace.empty()) c->trace_t0 = std::chrono::steady_clock::now();
+    cudaEvent_t e;
+    if (c->trace.size() < c->trace_pool.size()) e = c->trace_pool[c->trace.size()];
+    else { cudaEventCreate(&e); c->trace_pool.push_back(e); }
+    cudaEventRecord(e, st);
+    c->trace.push_back({name, e, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - c->trace_t0).count()});
+}
+
+void trace_dump(dscgpu_ctx *c)
+{
+    if (!c->trace_on || c->trace.empty()) return;
+    const double done = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - c->trace_t0).count();
+    fprintf(stderr, "[dscgpu trace] %-22s %10s %10s\n", "mark", "gpu us", "issued us");
+    for (const auto &m : c->trace) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->trace[0].ev, m.ev);
+        fprintf(stderr, "[dscgpu trace] %-22s %10.1f %10.1f\n", m.name, ms * 1e3, m.host_us);
+    }
+    fprintf(stderr, "[dscgpu trace] %-22s %10s %10.1f\n", "host: synchronised", "", done);
+    c->trace.clear();
 }
 
 struct TimerScope {
@@ -356,6 +392,7 @@ template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S, int PMAX> int la
     a.stg_slots = ctx->stg_slots;
     a.stg_counter = ctx->d_stg_counter;
     a.stg_exact_count = ctx->d_stg_counter + 1;
+    a.stg_exact_done = ctx->d_stg_counter + 2;
     a.stg_exact_list = ctx->stg_exact.as<unsigned>();
     // tiles per claim: a chunk is also the grain of the tail, so launches with few tiles per producer warp claim them one at a time
     const unsigned per_warp = n_tiles / (grid * kStgProd);
@@ -363,8 +400,9 @@ template <typename VoxT, bool WANT_SQ, bool PER_TET, bool F32S, int PMAX> int la
     for (int k = 0; k < 3; k++) a.stg_scale[k] = ctx->stg_scale[k];
     // the counters are zero after the finalize of the previous pass; a second range launch of one pass restarts the tile counter only
     if (ctx->stg_counters_dirty) CK(cudaMemsetAsync(ctx->d_stg_counter, 0, 16 + 3 * kMaxPhase * sizeof(unsigned long long), ctx->stream));
-    else if (ctx->stg_list_kernel >= 0) CK(cudaMemsetAsync(ctx->d_stg_counter, 0, sizeof(unsigned), ctx->stream));
+    else if (ctx->stg_pass_open) CK(cudaMemsetAsync(ctx->d_stg_counter, 0, sizeof(unsigned), ctx->stream));
     ctx->stg_counters_dirty = false;
+    ctx->stg_pass_open = true;
     kern<<<grid, (kStgProd + kStgCons) * 32, smem, ctx->stream>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -394,14 +432,23 @@ template <typename VoxT, bool F32S> int launch_exact_list_v(dscgpu_ctx *ctx)
     return DSCGPU_OK;
 }
 
-int launch_exact_list(dscgpu_ctx *ctx)
+// more_follow: further staged launches of the same pass come after this one (the chunks of the pipelined upload): the part of the list
+// worked off so far is remembered on the device, so that every entry is evaluated exactly once
+int launch_exact_list(dscgpu_ctx *ctx, bool more_follow = false)
 {
     if (ctx->stg_list_kernel < 0) return DSCGPU_OK;
+    int r;
     switch (ctx->dtype) {
-    case DSCGPU_U8: return launch_exact_list_v<unsigned char, false>(ctx);
-    case DSCGPU_U16: return launch_exact_list_v<unsigned short, false>(ctx);
-    default: return launch_exact_list_v<float, true>(ctx);
+    case DSCGPU_U8: r = launch_exact_list_v<unsigned char, false>(ctx); break;
+    case DSCGPU_U16: r = launch_exact_list_v<unsigned short, false>(ctx); break;
+    default: r = launch_exact_list_v<float, true>(ctx); break;
     }
+    if (r == DSCGPU_OK && more_follow) {
+        copy_u32_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_stg_counter + 2, ctx->d_stg_counter + 1);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return r;
 }
 
 template <typename VoxT, bool F32S, int PMAX> int launch_staged_p(dscgpu_ctx *ctx, TetArgs &a)
@@ -537,7 +584,7 @@ int tet_pass_begin(dscgpu_ctx *ctx)
 {
     ctx->tet_grid = 0;
     ctx->tet_rows_fixed = false;
-    if (ctx->stg_list_kernel >= 0) { ctx->stg_list_kernel = -1; ctx->stg_counters_dirty = true; } // a pass that never reached its finalize
+    if (ctx->stg_pass_open) { ctx->stg_list_kernel = -1; ctx->stg_pass_open = false; ctx->stg_counters_dirty = true; } // a pass that never reached its finalize
     CK(cudaMemsetAsync(ctr(ctx, 0), 0, sizeof(unsigned long long), ctx->stream));
     return DSCGPU_OK;
 }
@@ -553,6 +600,7 @@ int tet_pass_finish(dscgpu_ctx *ctx, int nb_phase, double *d_sums_out, double *d
     else
         tet_finalize_kernel<<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(ctx->partials.as<double>(), ctx->tet_grid, nb_phase, d_sums_out, d_mean_out);
     ctx->launches++;
+    ctx->stg_pass_open = false; // (both finalize kernels leave the staged kernel's counters zero)
     CK(cudaGetLastError());
     return DSCGPU_OK;
 }
@@ -917,8 +965,10 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     CK(cudaEventRecord(ctx->ev_chunk[18], ks));
     CK(cudaStreamWaitEvent(cs, ctx->ev_chunk[18], 0));
     if (ctx->timers_on) CK(cudaEventRecord(ctx->ev[DSCGPU_T_H2D][0], cs));
+    trace_mark(ctx, "start (copy stream)", cs);
     if (nn) CK(cudaMemcpyAsync(ctx->pos4.p, ctx->h_pos4.p, (size_t)nn * 32, cudaMemcpyHostToDevice, cs));
     CK(cudaEventRecord(ctx->ev_chunk[16], cs));
+    trace_mark(ctx, "positions landed", cs);
     ctx->n_nodes = nn; ctx->n_tets = nt; ctx->n_faces = nf;
     ctx->tet_b = 0; ctx->tet_e = nt; ctx->face_b = 0; ctx->face_e = nf; ctx->node_b = 0; ctx->node_e = nn;
     ctx->partition_stale = false;
@@ -938,12 +988,61 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
     if (r) return r;
     TetPassOut none;
     if (ctx->timers_on) CK(cudaEventRecord(ctx->ev[DSCGPU_T_TET][0], ks));
+    // Order on the copy stream: tet chunk 0, the (small) face arrays, the other tet chunks.  The compute stream integrates chunk 0 as soon as
+    // it is there, builds the node -> face table while chunk 1 is in flight, and works the exact list of every chunk off right behind
+    // its staged launch -- so that after the last byte has landed only the last chunk's kernels, the finalize and the forces remain.
+    bool faces_done = false;
+    auto faces = [&]() -> int {
+        if (nf) {
+            CK(cudaMemcpyAsync(ctx->face_nodes.p, ctx->h_face_nodes.p, (size_t)nf * 12, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(ctx->face_tets.p, ctx->h_face_tets.p, (size_t)nf * 8, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(ctx->face_isb.p, ctx->h_face_isb.p, (size_t)nf, cudaMemcpyHostToDevice, cs));
+        }
+        CK(cudaEventRecord(ctx->ev_chunk[17], cs));
+        trace_mark(ctx, "faces landed", cs);
+        faces_done = true;
+        return DSCGPU_OK;
+    };
+    auto faces_device_side = [&]() -> int { // validation of the face ids and the node -> face table, on the compute stream
+        CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[17], 0));
+        const size_t n_ids = 3 * (size_t)nf + 2 * (size_t)nf;
+        if (n_ids) {
+            const unsigned grid = (unsigned)std::min<size_t>((n_ids + 255) / 256, (size_t)ctx->num_sms * 16);
+            validate_snapshot_kernel<<<grid, 256, 0, ks>>>(nullptr, 0, ctx->face_nodes.as<unsigned>(), 3 * (size_t)nf, ctx->face_tets.as<unsigned>(), 2 * (size_t)nf,
+                                                          nn, nt, reinterpret_cast<int *>(ctr(ctx, 4)));
+            ctx->launches++;
+        }
+        const int rc = build_csr_device(ctx);
+        trace_mark(ctx, "node->face table built", ks);
+        return rc;
+    };
+    const bool hoist = ctx->pipeline_flags & 1, exact_per_chunk = ctx->pipeline_flags & 2;
+    uint32_t chunk_begin[17];
+    {
+        const double ratio = (ctx->pipeline_flags & 4) ? ctx->pipeline_ratio : 1.0;
+        double wsum = 0, w = 1;
+        for (int c = 0; c < C; c++) { wsum += w; w *= ratio; }
+        double acc = 0;
+        w = 1;
+        chunk_begin[0] = 0;
+        for (int c = 0; c < C; c++) {
+            acc += w; w *= ratio;
+            uint64_t e = (uint64_t)((double)nt * acc / wsum);
+            e = (e + 31) / 32 * 32;
+            chunk_begin[c + 1] = c == C - 1 ? nt : (uint32_t)std::min<uint64_t>(e, nt);
+        }
+    }
+    bool first = true;
     for (int c = 0; c < C; c++) {
-        const uint32_t b = (uint32_t)((uint64_t)nt * c / C), e = (uint32_t)((uint64_t)nt * (c + 1) / C);
+        // shrinking chunks (multiples of 32 tets): a chunk's kernels finish well inside the copy of the next one, and what is left to do
+        // when the last byte has landed is the smallest chunk
+        const uint32_t b = chunk_begin[c], e = chunk_begin[c + 1];
         if (e <= b) continue;
         CK(cudaMemcpyAsync(ctx->tet_nodes.as<char>() + (size_t)b * 16, ctx->h_tet_nodes.as<char>() + (size_t)b * 16, (size_t)(e - b) * 16, cudaMemcpyHostToDevice, cs));
         CK(cudaMemcpyAsync(ctx->tet_label.as<char>() + (size_t)b * 4, ctx->h_tet_label.as<char>() + (size_t)b * 4, (size_t)(e - b) * 4, cudaMemcpyHostToDevice, cs));
         CK(cudaEventRecord(ctx->ev_chunk[c], cs));
+        trace_mark(ctx, "tet chunk landed", cs);
+        if (first && hoist) { r = faces(); if (r) return r; }
         CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[c], 0));
         const size_t n_ids = 4 * (size_t)(e - b);
         const unsigned grid = (unsigned)std::min<size_t>((n_ids + 255) / 256, (size_t)ctx->num_sms * 16);
@@ -952,32 +1051,24 @@ int upload_and_tet_pass_pipelined(dscgpu_ctx *ctx, int nb_phase, int want_sq, do
         ctx->launches++;
         r = tet_pass_range(ctx, nb_phase, 0, 0, nullptr, none, b, e, want_sq);
         if (r) return r;
+        trace_mark(ctx, "tet chunk staged done", ks);
+        if (exact_per_chunk) { r = launch_exact_list(ctx, /*more_follow=*/true); if (r) return r; }
+        if (first && hoist) { r = faces_device_side(); if (r) return r; }
+        first = false;
+    }
+    if (!faces_done) { // (no tets at all, or the face arrays last)
+        r = faces(); if (r) return r;
+        r = faces_device_side(); if (r) return r;
     }
     if (ctx->timers_on) { CK(cudaEventRecord(ctx->ev[DSCGPU_T_TET][1], ks)); ctx->ev_used[DSCGPU_T_TET] = true; }
-    if (nf) {
-        CK(cudaMemcpyAsync(ctx->face_nodes.p, ctx->h_face_nodes.p, (size_t)nf * 12, cudaMemcpyHostToDevice, cs));
-        CK(cudaMemcpyAsync(ctx->face_tets.p, ctx->h_face_tets.p, (size_t)nf * 8, cudaMemcpyHostToDevice, cs));
-        CK(cudaMemcpyAsync(ctx->face_isb.p, ctx->h_face_isb.p, (size_t)nf, cudaMemcpyHostToDevice, cs));
-    }
     if (ctx->timers_on) { CK(cudaEventRecord(ctx->ev[DSCGPU_T_H2D][1], cs)); ctx->ev_used[DSCGPU_T_H2D] = true; }
-    CK(cudaEventRecord(ctx->ev_chunk[17], cs));
-    CK(cudaStreamWaitEvent(ks, ctx->ev_chunk[17], 0));
-    {
-        const size_t n_ids = 3 * (size_t)nf + 2 * (size_t)nf;
-        if (n_ids) {
-            const unsigned grid = (unsigned)std::min<size_t>((n_ids + 255) / 256, (size_t)ctx->num_sms * 16);
-            validate_snapshot_kernel<<<grid, 256, 0, ks>>>(nullptr, 0, ctx->face_nodes.as<unsigned>(), 3 * (size_t)nf, ctx->face_tets.as<unsigned>(), 2 * (size_t)nf,
-                                                          nn, nt, reinterpret_cast<int *>(ctr(ctx, 4)));
-            ctx->launches++;
-        }
-        CK(cudaMemcpyAsync(ctx->h_flag.p, ctr(ctx, 4), sizeof(int), cudaMemcpyDeviceToHost, ks));
-        ctx->validation_pending = true;
-    }
-    r = build_csr_device(ctx);
-    if (r) return r;
+    CK(cudaMemcpyAsync(ctx->h_flag.p, ctr(ctx, 4), sizeof(int), cudaMemcpyDeviceToHost, ks));
+    ctx->validation_pending = true;
     ctx->staging_valid = false; // uploaded (see commit_snapshot_impl)
     ctx->partition_stale = false;
-    return tet_pass_finish(ctx, nb_phase, d_sums_out, d_mean_out);
+    r = tet_pass_finish(ctx, nb_phase, d_sums_out, d_mean_out);
+    trace_mark(ctx, "tet pass finalised", ks);
+    return r;
 }
 
 } // namespace
@@ -1018,6 +1109,9 @@ int dscgpu_ctx_create(dscgpu_ctx **out, int device, const int dims[3], int dtype
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 20; i++) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
     if (const char *ev = getenv("DSCGPU_PIPELINE_CHUNKS")) ctx->pipeline_chunks = atoi(ev);
+    if (const char *ev = getenv("DSCGPU_PIPELINE_FLAGS")) ctx->pipeline_flags = atoi(ev);
+    if (const char *ev = getenv("DSCGPU_E2E_TRACE")) ctx->trace_on = atoi(ev) != 0;
+    if (const char *ev = getenv("DSCGPU_PIPELINE_RATIO")) { const double v = atof(ev); if (v > 0.1 && v <= 1.0) ctx->pipeline_ratio = v; }
     ctx->stream = ctx->own_stream;
     for (int i = 0; i < DSCGPU_T_COUNT; i++) { CK(cudaEventCreate(&ctx->ev[i][0])); CK(cudaEventCreate(&ctx->ev[i][1])); }
     ctx->dims[0] = dims[0]; ctx->dims[1] = dims[1]; ctx->dims[2] = dims[2];
@@ -1117,6 +1211,7 @@ int dscgpu_ctx_destroy(dscgpu_ctx *ctx)
         if (ctx->ev[i][1]) cudaEventDestroy(ctx->ev[i][1]);
     }
     for (int i = 0; i < 20; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+    for (cudaEvent_t e : ctx->trace_pool) cudaEventDestroy(e);
     if (ctx->ev_nact) cudaEventDestroy(ctx->ev_nact);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -2027,33 +2122,42 @@ int dscgpu_image_force_eval(dscgpu_ctx *ctx, const dscgpu_snapshot *snap, int nb
     r = run_forces(ctx, nb_phase, ctx->mean.as<double>(), force_mode, ctx->forces.as<double>());
     ctx->forces_resident = r == DSCGPU_OK;
     if (r) return r;
+    trace_mark(ctx, "forces done", ctx->stream);
     double *h = ctx->h_out.as<double>();
     {
         TimerScope ts(ctx, DSCGPU_T_D2H);
-        CK(cudaMemcpyAsync(h, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(h + 3 * kMaxPhase, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        if (fbytes && !forces && ctx->compact_forces && ctx->ev_nact) {
+        const bool compact = fbytes && !forces && ctx->compact_forces && ctx->ev_nact;
+        if (!compact) {
+            CK(cudaMemcpyAsync(h, ctx->sums.p, 3 * nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h + 3 * kMaxPhase, ctx->mean.p, nb_phase * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (compact) {
             // only the rows that can be non-zero cross PCIe: nodes with interface faces (about one node in seven on a DSC mesh)
             cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
             ARG(cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone, "the compact read-back cannot be captured");
             CK(cudaEventSynchronize(ctx->ev_nact)); // recorded when the snapshot was committed
             const unsigned na = std::min<unsigned>(*ctx->h_nact.as<unsigned>(), ctx->n_nodes);
-            CK(ctx->crows.ensure(3 * (size_t)na * sizeof(double) + 8));
-            CK(ctx->h_node_active.ensure((size_t)na * sizeof(unsigned) + 8));
-            if (na) {
-                gather_rows_kernel<<<(na + 255) / 256, 256, 0, ctx->stream>>>(ctx->forces.as<double>(), ctx->node_active.as<unsigned>(), na, ctx->crows.as<double>());
-                ctx->launches++;
-                CK(cudaGetLastError());
-                CK(cudaMemcpyAsync(h + 4 * kMaxPhase, ctx->crows.p, 3 * (size_t)na * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaMemcpyAsync(ctx->h_node_active.p, ctx->node_active.p, (size_t)na * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-            }
+            // statistics, rows and keys in one buffer: one copy (every copy costs a launch on the tail of the evaluation)
+            const size_t bytes = (4 * (size_t)kMaxPhase + 3 * (size_t)na) * sizeof(double) + (size_t)na * sizeof(unsigned);
+            CK(ctx->crows.ensure(bytes + 8));
+            CK(ctx->h_out.ensure(std::max(bytes + 8, fbytes + 4 * kMaxPhase * sizeof(double))));
+            h = ctx->h_out.as<double>();
+            gather_result_kernel<<<(std::max<unsigned>(na, 3 * kMaxPhase) + 255) / 256, 256, 0, ctx->stream>>>(ctx->forces.as<double>(), ctx->node_active.as<unsigned>(), na,
+                                                                                                              ctx->sums.as<double>(), ctx->mean.as<double>(), nb_phase,
+                                                                                                              ctx->crows.as<double>());
+            ctx->launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(h, ctx->crows.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
             ctx->compact_n = na;
+            ctx->compact_keys = reinterpret_cast<const uint32_t *>(h + 4 * kMaxPhase + 3 * (size_t)na);
         } else if (fbytes) {
             CK(cudaMemcpyAsync(h + 4 * kMaxPhase, ctx->forces.p, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
             ctx->compact_n = 0xffffffffu;
         }
     }
+    trace_mark(ctx, "results on the host", ctx->stream);
     r = sync_and_check(ctx);
+    trace_dump(ctx);
     if (r) return r;
     if (stats) fill_stats(stats, h, h + 3 * kMaxPhase, nb_phase);
     if (forces && fbytes) memcpy(forces, h + 4 * kMaxPhase, fbytes);
@@ -2096,7 +2200,8 @@ int dscgpu_read_forces_compact(dscgpu_ctx *ctx, const double *d_forces, uint32_t
     int r = sync_and_check(ctx);
     if (r) return r;
     ctx->compact_n = na;
-    *n_rows = na; *node_keys = ctx->h_node_active.as<uint32_t>(); *rows = h;
+    ctx->compact_keys = ctx->h_node_active.as<uint32_t>();
+    *n_rows = na; *node_keys = ctx->compact_keys; *rows = h;
     return DSCGPU_OK;
 }
 
@@ -2106,7 +2211,7 @@ int dscgpu_forces_compact_pinned(dscgpu_ctx *ctx, uint32_t *n_rows, const uint32
     ARG(n_rows && node_keys && rows, "null output");
     ARG(ctx->h_out.p && ctx->compact_n != 0xffffffffu, "the last dscgpu_image_force_eval did not read the forces back in compact form");
     *n_rows = ctx->compact_n;
-    *node_keys = ctx->h_node_active.as<uint32_t>();
+    *node_keys = ctx->compact_keys;
     *rows = ctx->h_out.as<double>() + 4 * kMaxPhase;
     return DSCGPU_OK;
 }
@@ -2277,6 +2382,7 @@ int dscgpu_tet_phase_sums_allreduce_dev(dscgpu_ctx *ctx, int nb_phase, double *d
     else
         comm_phase_allreduce_kernel<false><<<1, 32 * 3 * kMaxPhase, 0, ctx->stream>>>(comm_view(ctx), ctx->partials.p, ctx->tet_grid, nb_phase, 1.0, 1.0, 1.0, d_sums, d_mean, nullptr);
     ctx->launches++;
+    ctx->stg_pass_open = false;
     CK(cudaGetLastError());
     return DSCGPU_OK;
 }

@@ -536,7 +536,8 @@ def main_b200(args):
     h2d_bytes = n_nodes * 32 + n_tets * 20 + n_faces * (12 + 8 + 1)  # pos4, tet ids+labels, face ids/tets/flags; the CSR is built on the device
     n_active_nodes = len(np.unique(snap["face_nodes"]))
     # the forces come back as the rows of the nodes that have interface faces (+ their keys), every other row is zero; N > 1: on rank 0
-    d2h_bytes = n_active_nodes * 28 + 4 * P * 8
+    # (N = 1: one copy -- a header of 4 x 8 doubles for sums and means, the rows, the keys; N > 1: rows and keys on rank 0, the means on every rank)
+    d2h_bytes = n_active_nodes * 28 + (4 * 8 * 8 if world == 1 else P * 8)
 
     def step_e2e():
         if world == 1:
@@ -571,6 +572,17 @@ def main_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = te.item() / e2e_steps * 1e3
     e2e_value = units / (e2e_ms * 1e-3)
+    # where an end-to-end step spends its time: the library's own CUDA-event timers on one extra (untimed) step
+    e2e_parts = None
+    if world == 1:
+        seg.enable_timers(True)
+        t1 = time.perf_counter()
+        step_e2e()
+        wall = (time.perf_counter() - t1) * 1e3
+        e2e_parts = {k + "_ms": round(seg.timer_ms(k), 4) for k in ("h2d", "tet", "phase_final", "force", "d2h")}
+        e2e_parts["wall_ms_with_timers"] = round(wall, 4)
+        e2e_parts["what"] = "h2d: first to last byte on the copy stream; tet: first staged launch to the last (they wait for their chunks); one extra step with event timers on"
+        seg.enable_timers(False)
     # ---- the same with an incremental snapshot: every node position re-sent, 2 % of the tets replaced, the
     # interface-face list re-sent; reported next to e2e, never instead of it
     e2e_incr = None
@@ -687,7 +699,7 @@ def main_b200(args):
             "comm": ("none" if world == 1 else ("fused exchange kernels over NVLink peer memory (CUDA IPC windows)" if p2p else "2 NCCL all-reduces")),
             "samples_per_step": n_samples_all, "gauss_points_per_step": n_gauss_all},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
-                "steps": e2e_steps, "host_fill_ms": host_fill_ms},
+                "steps": e2e_steps, "host_fill_ms": host_fill_ms, "parts": e2e_parts},
         "with_sumsq": with_sumsq, "parity": parity, "zray": zray,
         "e2e_incremental": e2e_incr,
         "gpu_launches": int(launches_per_step[0] * args.steps),

@@ -505,6 +505,36 @@ def test_compact_force_read_back(case, pkg):
     assert not F[rest].any()
 
 
+@pytest.mark.parametrize("name", ["sph48_f32", "sh40_u16", "c1n_e9_j"])
+def test_pipelined_upload_orders_give_the_same_result(pkg, monkeypatch, name):
+    """dscgpu_image_force_eval with a host snapshot overlaps the upload with the tet pass in chunks (face arrays behind chunk 0, node -> face
+    table built meanwhile, exact list worked off per chunk, shrinking chunks): every order and chunk count gives the numbers of the plain
+    commit-then-evaluate path -- bit for bit where the staged kernel runs (integer sums), 1e-13 where the w2 kernel's double sums re-associate."""
+    g = golden_io.load(name)
+    snap = golden_io.snapshot_of(g)
+    P = g["meta"]["nb_phase"]
+    results = []
+    for flags, chunks, ratio in [("0", "0", "1"), ("0", "4", "1"), ("3", "3", "1"), ("7", "4", "0.85"), ("7", "7", "0.5"), ("2", "16", "1")]:
+        monkeypatch.setenv("DSCGPU_PIPELINE_FLAGS", flags)
+        monkeypatch.setenv("DSCGPU_PIPELINE_CHUNKS", chunks)
+        monkeypatch.setenv("DSCGPU_PIPELINE_RATIO", ratio)
+        img = pkg.Image3D(g["volume"])
+        seg = pkg.SegmentFunction(img, P)
+        mean, F = seg.image_force_eval(snap, mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_GATHER)
+        mean_c, (keys, rows) = seg.image_force_eval(snap, mean_mode=pkg.MEAN_TET, force_mode=pkg.FORCE_GATHER, want_forces="compact")
+        staged = seg.get_tet_variant() & 131072
+        assert np.array_equal(mean, mean_c) and np.array_equal(rows, F[keys]) and np.array_equal(keys, np.unique(snap["face_nodes"]))
+        results.append((mean, F))
+        img.close()
+    m0, F0 = results[0]
+    for m, F in results[1:]:
+        if staged and name != "c1n_e9_j":  # (a 100-byte row pitch cannot be staged by TMA: w2 kernel)
+            assert np.array_equal(m, m0) and np.array_equal(F, F0)
+        else:
+            np.testing.assert_allclose(m, m0, rtol=1e-13)
+            np.testing.assert_allclose(F, F0, rtol=1e-10, atol=1e-12)
+
+
 @pytest.mark.parametrize("variant", [0, 16512, 131072 | 16512])
 def test_free_slots_of_a_key_indexed_snapshot_are_skipped(pkg, flat, variant):
     """Slots that hold no tet (label DSCGPU_LABEL_FREE = -1, nodes 0 0 0 0) take part in nothing, also with include_bound: the sums are

@@ -307,6 +307,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
     const int X = a.vol.X, Y = a.vol.Y, Z = a.vol.Z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int S = a.stg_slots;
+    const unsigned s_rcp = 0xffffffffu / (unsigned)S + 1u; // q / S = umulhi(q, ceil(2^32 / S)) while q S < 2^32 (a CTA hands out fewer than 2^20 items, S <= 16)
     const unsigned box0 = smem_u32(s_dyn);
     const unsigned rec0 = box0 + (unsigned)S * (unsigned)a.stg_slot_bytes;
     if (threadIdx.x < 4) s_zero[threadIdx.x] = 0u;
@@ -331,8 +332,8 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
             q = 0;
             if (lane == 0) q = atomicAdd(&s_seq[0], 1u);
             q = __shfl_sync(0xffffffffu, q, 0);
-            slot = q % (unsigned)S;
-            const unsigned round = q / (unsigned)S;
+            const unsigned round = __umulhi(q, s_rcp);
+            slot = q - round * (unsigned)S;
             while (*reinterpret_cast<volatile unsigned *>(&s_released[slot]) != round) __nanosleep(40);
             __threadfence_block();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the consumers' reads of the slot precede the TMA writes into it
@@ -470,6 +471,14 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
                 take_slot(slot, q);
                 const unsigned slot_a = box0 + slot * (unsigned)a.stg_slot_bytes;
                 const unsigned bx = (unsigned)(exu * 16), bxy = bx * (unsigned)ey;
+                // the box first: its bytes travel while the records are written (the consumer needs the records before the voxels)
+                if (lane == 0) {
+                    const unsigned bar = smem_u32(&s_full[slot]);
+                    mbar_arrive_tx(bar, bxy * (unsigned)ez);
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(slot_a), "l"(map),
+                                 "r"(x0), "r"(y0), "r"(z0), "r"(bar)
+                                 : "memory");
+                }
                 {
                     float *rec = reinterpret_cast<float *>(s_dyn + (size_t)S * a.stg_slot_bytes + (size_t)slot * kStgRecBytes) + lane;
                     const int n = L + 1;
@@ -501,13 +510,8 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    const unsigned bar = smem_u32(&s_full[slot]);
                     __threadfence_block();
                     *reinterpret_cast<volatile unsigned *>(&s_fillseq[slot]) = q + 1u;
-                    mbar_arrive_tx(bar, bxy * (unsigned)ez);
-                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(slot_a), "l"(map),
-                                 "r"(x0), "r"(y0), "r"(z0), "r"(bar)
-                                 : "memory");
                 }
             }
             exact_append(a, exact, t, lane);
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
             unsigned q = 0;
             if (lane == 0) q = atomicAdd(&s_seq[1], 1u);
             q = __shfl_sync(0xffffffffu, q, 0);
-            const unsigned slot = q % (unsigned)S, round = q / (unsigned)S;
+            const unsigned round = __umulhi(q, s_rcp), slot = q - round * (unsigned)S;
             // first the producer of THIS item must have started filling the slot (then the mbarrier is in the phase of this round) ...
             while (*reinterpret_cast<volatile unsigned *>(&s_fillseq[slot]) != q + 1u) __nanosleep(40);
             __threadfence_block(); // the records and the header were written before the sequence number

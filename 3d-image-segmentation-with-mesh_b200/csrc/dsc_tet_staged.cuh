@@ -37,6 +37,9 @@ namespace dsc {
 #ifndef STG_CONS
 #define STG_CONS 8
 #endif
+#ifndef STG_PROD_SLEEP
+#define STG_PROD_SLEEP 100 // ns between two looks of a producer at its slot's release counter
+#endif
 constexpr int kStgProd = STG_PROD, kStgCons = STG_CONS; // producer / consumer warps of a CTA
 constexpr int kStgMaxSlots = 16;
 constexpr int kStgMaxChunk = 4; // most tiles a producer claims with one atomic
@@ -155,13 +158,77 @@ template <typename VoxT, bool SEL> DSC_D unsigned stg_addr(const StgLane &r, flo
     return SEL ? (full ? addr : r.zero_addr) : addr;
 }
 
-// The level-NB instruction stream.  `full`: this lane's tet is of level NB (else NB-1, or the lane is idle with an all-zero
-// record whose reads hit the first voxel of the slot and whose sums are never looked at).
-template <int NB, typename VoxT, bool WANT_SQ, bool F32S> DSC_D void stg_block(const StgLane &r, bool full, StgAcc<VoxT, WANT_SQ, F32S> &acc)
+// One or two samples of a cell, positions qa, qb (x, y) and qzz (z of both): voxel index bits by the magic-number add, guard-band residue,
+// shared address, load, add.  sel_a / sel_b: the slot exists at level NB only (a level NB-1 lane reads the zero word instead).
+// (two, sel_a, sel_b, cnt are constants at every call once the callers are unrolled / inlined)
+template <typename VoxT, bool WANT_SQ, bool F32S>
+DSC_D void stg_pair(const StgLane &r, bool full, StgAcc<VoxT, WANT_SQ, F32S> &acc, f32x2 qa, f32x2 qb, f32x2 qzz, bool two, bool sel_a, bool sel_b, int cnt, float &em,
+                    float &em1)
 {
     const float MAGIC = 12582912.0f; // 1.5 * 2^23
     const f32x2 M2 = pk2(MAGIC, MAGIC);
-    float em = 0.f, em1 = 0.f;
+    const f32x2 ta = add2(qa, M2), tz2 = add2(qzz, M2);
+    const f32x2 ea2 = sub2(qa, sub2(ta, M2)), ez2 = sub2(qzz, sub2(tz2, M2));
+    float tax, tay, tz0, tz1, eax, eay, ez0, ez1;
+    upk2(ta, tax, tay); upk2(tz2, tz0, tz1); upk2(ea2, eax, eay); upk2(ez2, ez0, ez1);
+    em = fmax3abs(em, eax, eay);
+    const unsigned addr_a = sel_a ? stg_addr<VoxT, true>(r, tax, tay, tz0, full) : stg_addr<VoxT, false>(r, tax, tay, tz0, full);
+    const VoxT va = lds_vox<VoxT>(addr_a);
+    if (two) {
+        const f32x2 tb = add2(qb, M2);
+        const f32x2 eb2 = sub2(qb, sub2(tb, M2));
+        float tbx, tby, ebx, eby;
+        upk2(tb, tbx, tby); upk2(eb2, ebx, eby);
+        em1 = fmax3abs(em1, ebx, eby);
+        em1 = fmax3abs(em1, ez0, ez1);
+        const unsigned addr_b = sel_b ? stg_addr<VoxT, true>(r, tbx, tby, tz1, full) : stg_addr<VoxT, false>(r, tbx, tby, tz1, full);
+        const VoxT vb = lds_vox<VoxT>(addr_b);
+        acc.add(va, cnt);
+        acc.add(vb, cnt + 1);
+    } else {
+        em1 = fmax3abs(em1, ez0, ez0);
+        acc.add(va, cnt);
+    }
+}
+
+// The samples of cell (i, j, k) of the level-NB stream, corner (cxy, czz): its offsets in pairs.
+template <int NB, typename VoxT, bool WANT_SQ, bool F32S>
+DSC_D void stg_cell(const StgLane &r, bool full, StgAcc<VoxT, WANT_SQ, F32S> &acc, int i, int j, int k, f32x2 cxy, f32x2 czz, float &em, float &em1, int &cnt)
+{
+    const int s = i + j + k;
+    const int m = (NB - s >= 3) ? 6 : (NB - s == 2 ? 5 : 1); // offsets kept in this cell
+#pragma unroll
+    for (int t = 0; t < 6; t += 2) {
+        if (t < m) {
+            const bool two = t + 1 < m;
+            // z of the two samples in one packed add; x,y one packed add per sample
+            f32x2 qzz = add2(czz, r.ozz[t >> 1]);
+            f32x2 qa = add2(cxy, r.oxy[t]);
+            f32x2 qb = two ? add2(cxy, r.oxy[t + 1]) : qa;
+            if (NB >= 3) { // level-3 rows whose literals sum to 1 -/+ 1e-6 (every other level: eps = 0)
+                const int ea = (NB == 3 || stg_need(s, t) <= 3) ? stg_eps3(i, j, k, t) : 0;
+                const int eb = (two && (NB == 3 || stg_need(s, t + 1) <= 3)) ? stg_eps3(i, j, k, t + 1) : 0;
+                if (ea > 0) qa = add2(qa, r.epxy);
+                if (ea < 0) qa = sub2(qa, r.epxy);
+                if (eb > 0) qb = add2(qb, r.epxy);
+                if (eb < 0) qb = sub2(qb, r.epxy);
+                if (ea != 0 || eb != 0) {
+                    float ez0, ez1;
+                    upk2(r.epzz, ez0, ez1);
+                    qzz = add2(qzz, pk2(ea > 0 ? ez0 : (ea < 0 ? -ez0 : 0.f), eb > 0 ? ez1 : (eb < 0 ? -ez1 : 0.f)));
+                }
+            }
+            stg_pair<VoxT, WANT_SQ, F32S>(r, full, acc, qa, qb, qzz, two, NB > 1 && stg_need(s, t) == NB, NB > 1 && two && stg_need(s, t + 1) == NB, cnt, em, em1);
+            cnt += two ? 2 : 1;
+        }
+    }
+}
+
+// The level-NB instruction stream.  `full`: this lane's tet is of level NB (else NB-1, or the lane is idle with an all-zero
+// record whose reads hit the first voxel of the slot and whose sums are never looked at).  Cells with i + j + k <= SMAX only.
+template <int NB, typename VoxT, bool WANT_SQ, bool F32S, int SMAX = NB>
+DSC_D void stg_cells(const StgLane &r, bool full, StgAcc<VoxT, WANT_SQ, F32S> &acc, float &em, float &em1)
+{
     int cnt = 0; // samples so far (a constant at every point of the unrolled stream)
 #pragma unroll
     for (int j = 0; j < NB; j++) {
@@ -173,58 +240,106 @@ template <int NB, typename VoxT, bool WANT_SQ, bool F32S> DSC_D void stg_block(c
             const f32x2 cizz = i ? fma2(pk2((float)i, (float)i), r.d2zz, cjzz) : cjzz;
 #pragma unroll
             for (int k = 0; k < NB - j - i; k++) {
-                const f32x2 cxy = k ? fma2(pk2((float)k, (float)k), r.d3xy, cixy) : cixy;
-                const f32x2 czz = k ? fma2(pk2((float)k, (float)k), r.d3zz, cizz) : cizz;
-                const int s = i + j + k;
-                const int m = (NB - s >= 3) ? 6 : (NB - s == 2 ? 5 : 1); // offsets kept in this cell
-#pragma unroll
-                for (int t = 0; t < m; t += 2) {
-                    const bool two = t + 1 < m;
-                    // z of the two samples in one packed add; x,y one packed add per sample
-                    f32x2 qzz = add2(czz, r.ozz[t >> 1]);
-                    f32x2 qa = add2(cxy, r.oxy[t]);
-                    f32x2 qb = two ? add2(cxy, r.oxy[t + 1]) : qa;
-                    if (NB >= 3) { // level-3 rows whose literals sum to 1 -/+ 1e-6 (every other level: eps = 0)
-                        const int ea = (NB == 3 || stg_need(s, t) <= 3) ? stg_eps3(i, j, k, t) : 0;
-                        const int eb = (two && (NB == 3 || stg_need(s, t + 1) <= 3)) ? stg_eps3(i, j, k, t + 1) : 0;
-                        if (ea > 0) qa = add2(qa, r.epxy);
-                        if (ea < 0) qa = sub2(qa, r.epxy);
-                        if (eb > 0) qb = add2(qb, r.epxy);
-                        if (eb < 0) qb = sub2(qb, r.epxy);
-                        if (ea != 0 || eb != 0) {
-                            float ez0, ez1;
-                            upk2(r.epzz, ez0, ez1);
-                            qzz = add2(qzz, pk2(ea > 0 ? ez0 : (ea < 0 ? -ez0 : 0.f), eb > 0 ? ez1 : (eb < 0 ? -ez1 : 0.f)));
-                        }
-                    }
-                    const f32x2 ta = add2(qa, M2), tz2 = add2(qzz, M2);
-                    const f32x2 ea2 = sub2(qa, sub2(ta, M2)), ez2 = sub2(qzz, sub2(tz2, M2));
-                    float tax, tay, tz0, tz1, eax, eay, ez0, ez1;
-                    upk2(ta, tax, tay); upk2(tz2, tz0, tz1); upk2(ea2, eax, eay); upk2(ez2, ez0, ez1);
-                    em = fmax3abs(em, eax, eay);
-                    const bool sel_a = NB > 1 && stg_need(s, t) == NB;
-                    const unsigned addr_a = sel_a ? stg_addr<VoxT, true>(r, tax, tay, tz0, full) : stg_addr<VoxT, false>(r, tax, tay, tz0, full);
-                    const VoxT va = lds_vox<VoxT>(addr_a);
-                    if (two) {
-                        const f32x2 tb = add2(qb, M2);
-                        const f32x2 eb2 = sub2(qb, sub2(tb, M2));
-                        float tbx, tby, ebx, eby;
-                        upk2(tb, tbx, tby); upk2(eb2, ebx, eby);
-                        em1 = fmax3abs(em1, ebx, eby);
-                        em1 = fmax3abs(em1, ez0, ez1);
-                        const bool sel_b = NB > 1 && stg_need(s, t + 1) == NB;
-                        const unsigned addr_b = sel_b ? stg_addr<VoxT, true>(r, tbx, tby, tz1, full) : stg_addr<VoxT, false>(r, tbx, tby, tz1, full);
-                        const VoxT vb = lds_vox<VoxT>(addr_b);
-                        acc.add(va, cnt);
-                        acc.add(vb, cnt + 1);
-                        cnt += 2;
-                    } else {
-                        em1 = fmax3abs(em1, ez0, ez0);
-                        acc.add(va, cnt);
-                        cnt += 1;
-                    }
+                if (i + j + k <= SMAX) {
+                    const f32x2 cxy = k ? fma2(pk2((float)k, (float)k), r.d3xy, cixy) : cixy;
+                    const f32x2 czz = k ? fma2(pk2((float)k, (float)k), r.d3zz, cizz) : cizz;
+                    stg_cell<NB, VoxT, WANT_SQ, F32S>(r, full, acc, i, j, k, cxy, czz, em, em1, cnt);
                 }
             }
+        }
+    }
+}
+
+template <int NB, typename VoxT, bool WANT_SQ, bool F32S> DSC_D void stg_block(const StgLane &r, bool full, StgAcc<VoxT, WANT_SQ, F32S> &acc)
+{
+    float em = 0.f, em1 = 0.f;
+    stg_cells<NB, VoxT, WANT_SQ, F32S>(r, full, acc, em, em1);
+    acc.emax = fmaxf(em, em1);
+}
+
+// The level-4 stream with its outer cells as loops: the unrolled stream is 17 KB of straight-line code, which together with the producer's
+// code does not fit the SM's instruction cache.  The cell at P0 (6 samples) stays unrolled; the three cells with
+// i + j + k = 1 (six offsets each), the six with i + j + k = 2 (five each) and the ten with i + j + k = 3 (one each) are loop bodies fed from
+// constant tables.  The
+// floating-point operations of a sample are those of stg_cells (a corner's skipped FMAs have a zero multiplier here: the same values).
+struct StgCellRow { float j, i, k, e0; }; // cell indices, eps sign of its first offset (stg_eps3)
+#define STG_ROW(I, J, K) {(float)(J), (float)(I), (float)(K), (float)stg_eps3(I, J, K, 0)}
+struct StgCellRow6 { float j, i, k, e0, e1, e2, e3, e4; }; // i + j + k = 1: offsets 0..4 are level-3 rows as well
+#define STG_ROW6(I, J, K) {(float)(J), (float)(I), (float)(K), (float)stg_eps3(I, J, K, 0), (float)stg_eps3(I, J, K, 1), (float)stg_eps3(I, J, K, 2), (float)stg_eps3(I, J, K, 3), (float)stg_eps3(I, J, K, 4)}
+__constant__ StgCellRow6 c_stg4_s1[3] = {STG_ROW6(0, 0, 1), STG_ROW6(1, 0, 0), STG_ROW6(0, 1, 0)};
+#undef STG_ROW6
+__constant__ StgCellRow c_stg4_s2[6] = {STG_ROW(0, 0, 2), STG_ROW(1, 0, 1), STG_ROW(2, 0, 0), STG_ROW(0, 1, 1), STG_ROW(1, 1, 0), STG_ROW(0, 2, 0)};
+__constant__ StgCellRow c_stg4_s3[10] = {STG_ROW(0, 0, 3), STG_ROW(1, 0, 2), STG_ROW(2, 0, 1), STG_ROW(3, 0, 0), STG_ROW(0, 1, 2),
+                                         STG_ROW(1, 1, 1), STG_ROW(2, 1, 0), STG_ROW(0, 2, 1), STG_ROW(1, 2, 0), STG_ROW(0, 3, 0)};
+#undef STG_ROW
+
+template <typename VoxT, bool WANT_SQ, bool F32S> DSC_D void stg_block4_rolled(const StgLane &r, bool full, StgAcc<VoxT, WANT_SQ, F32S> &acc)
+{
+    float em = 0.f, em1 = 0.f;
+    stg_cells<4, VoxT, WANT_SQ, F32S, 0>(r, full, acc, em, em1); // the cell at P0: six level-3 rows
+    auto corner = [&](float j, float i, float k, f32x2 &cxy, f32x2 &czz) {
+        const f32x2 j2 = pk2(j, j), i2 = pk2(i, i), k2 = pk2(k, k);
+        cxy = fma2(k2, r.d3xy, fma2(i2, r.d2xy, fma2(j2, r.d1xy, r.q0xy)));
+        czz = fma2(k2, r.d3zz, fma2(i2, r.d2zz, fma2(j2, r.d1zz, r.q0zz)));
+    };
+    // i + j + k = 1: six offsets; 0..4 are level-3 rows as well (eps), offset 5 exists at level 4 only
+#pragma unroll 1
+    for (int c = 0; c < 3; c++) {
+        const StgCellRow6 row = c_stg4_s1[c];
+        f32x2 cxy, czz;
+        corner(row.j, row.i, row.k, cxy, czz);
+        {
+            const f32x2 qzz = fma2(pk2(row.e0, row.e1), r.epzz, add2(czz, r.ozz[0]));
+            const f32x2 qa = fma2(pk2(row.e0, row.e0), r.epxy, add2(cxy, r.oxy[0])), qb = fma2(pk2(row.e1, row.e1), r.epxy, add2(cxy, r.oxy[1]));
+            stg_pair<VoxT, WANT_SQ, F32S>(r, full, acc, qa, qb, qzz, true, false, false, 0, em, em1);
+        }
+        {
+            const f32x2 qzz = fma2(pk2(row.e2, row.e3), r.epzz, add2(czz, r.ozz[1]));
+            const f32x2 qa = fma2(pk2(row.e2, row.e2), r.epxy, add2(cxy, r.oxy[2])), qb = fma2(pk2(row.e3, row.e3), r.epxy, add2(cxy, r.oxy[3]));
+            stg_pair<VoxT, WANT_SQ, F32S>(r, full, acc, qa, qb, qzz, true, false, false, 2, em, em1);
+        }
+        {
+            const f32x2 qzz = fma2(pk2(row.e4, 0.f), r.epzz, add2(czz, r.ozz[2]));
+            const f32x2 qa = fma2(pk2(row.e4, row.e4), r.epxy, add2(cxy, r.oxy[4])), qb = add2(cxy, r.oxy[5]);
+            stg_pair<VoxT, WANT_SQ, F32S>(r, full, acc, qa, qb, qzz, true, false, true, 0, em, em1);
+        }
+    }
+    // i + j + k = 2: offsets 0..4; offset 0 is a level-3 row as well (eps), offsets 1..4 exist at level 4 only
+#pragma unroll 1
+    for (int c = 0; c < 6; c++) {
+        const StgCellRow row = c_stg4_s2[c];
+        f32x2 cxy, czz;
+        corner(row.j, row.i, row.k, cxy, czz);
+        {
+            f32x2 qzz = add2(czz, r.ozz[0]);
+            f32x2 qa = add2(cxy, r.oxy[0]);
+            const f32x2 qb = add2(cxy, r.oxy[1]);
+            qa = fma2(pk2(row.e0, row.e0), r.epxy, qa);       // +/- eps P0 (x, y), or nothing
+            qzz = fma2(pk2(row.e0, 0.f), r.epzz, qzz);        // the same for z of the first sample
+            stg_pair<VoxT, WANT_SQ, F32S>(r, full, acc, qa, qb, qzz, true, false, true, 0, em, em1);
+        }
+        {
+            const f32x2 qzz = add2(czz, r.ozz[1]);
+            const f32x2 qa = add2(cxy, r.oxy[2]), qb = add2(cxy, r.oxy[3]);
+            stg_pair<VoxT, WANT_SQ, F32S>(r, full, acc, qa, qb, qzz, true, true, true, 2, em, em1);
+        }
+        {
+            const f32x2 qzz = add2(czz, r.ozz[2]);
+            const f32x2 qa = add2(cxy, r.oxy[4]);
+            stg_pair<VoxT, WANT_SQ, F32S>(r, full, acc, qa, qa, qzz, false, true, false, 0, em, em1);
+        }
+    }
+    // i + j + k = 3: offset 0 only, at level 4 only
+#pragma unroll 1
+    for (int c0 = 0; c0 < 10; c0 += 5) {
+#pragma unroll
+        for (int u = 0; u < 5; u++) {
+            const StgCellRow row = c_stg4_s3[c0 + u];
+            f32x2 cxy, czz;
+            corner(row.j, row.i, row.k, cxy, czz);
+            const f32x2 qzz = add2(czz, r.ozz[0]);
+            const f32x2 qa = add2(cxy, r.oxy[0]);
+            stg_pair<VoxT, WANT_SQ, F32S>(r, full, acc, qa, qa, qzz, false, true, false, u & 3, em, em1);
         }
     }
     acc.emax = fmaxf(em, em1);
@@ -334,7 +449,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
             q = __shfl_sync(0xffffffffu, q, 0);
             const unsigned round = __umulhi(q, s_rcp);
             slot = q - round * (unsigned)S;
-            while (*reinterpret_cast<volatile unsigned *>(&s_released[slot]) != round) __nanosleep(40);
+            while (*reinterpret_cast<volatile unsigned *>(&s_released[slot]) != round) __nanosleep(STG_PROD_SLEEP);
             __threadfence_block();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the consumers' reads of the slot precede the TMA writes into it
         };
@@ -600,7 +715,11 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
             case 1: stg_block<1, VoxT, WANT_SQ, F32S>(r, full, acc); break;
             case 2: stg_block<2, VoxT, WANT_SQ, F32S>(r, full, acc); break;
             case 3: stg_block<3, VoxT, WANT_SQ, F32S>(r, full, acc); break;
-            default: stg_block<4, VoxT, WANT_SQ, F32S>(r, full, acc); break;
+#ifndef STG_UNROLLED
+            default: stg_block4_rolled<VoxT, WANT_SQ, F32S>(r, full, acc); break;
+#else
+            default: stg_block<4, VoxT, WANT_SQ, F32S>(r, full, acc); break; // (A/B: the fully unrolled level-4 stream)
+#endif
             }
             __syncwarp();
             if (lane == 0) { // every lane has read its voxels and its record

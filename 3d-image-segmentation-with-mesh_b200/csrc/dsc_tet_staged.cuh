@@ -17,7 +17,10 @@
 //  * the voxels a tile can touch form a small box (32 consecutive tets of a DSC grid mesh: ~52 x 10 x 10 voxels).  One lane
 //    per z slice asks the TMA unit for it (cp.async.bulk.tensor.3d, one tensor map per (row bytes, rows) pair), the warp waits
 //    on its mbarrier and every gather is an LDS: no L1 tags, no sectors, no DRAM latency inside the sample loop.
-//  * one CTA per SM, eight warps, one box slot per warp; tiles are fetched dynamically (one atomicAdd per tile).
+//  * one CTA per SM: eight producer warps (tile claim, ids, positions, FP64 geometry, box, TMA) and eight consumer warps (the sample stream)
+//    around a ring of box slots in shared memory; tiles are claimed dynamically in chunks of 1-4.
+//  * the level-4 stream is three loops over its outer cells (constant tables), not straight-line code: fully unrolled it is 17 KB, and with
+//    the producer's 17 KB the hot code missed the SM's instruction cache (hit rate 83 %, a quarter of the stream's stall samples).
 //  * per-label sums are accumulated as 64-bit fixed point (exact integer adds of per-tet contributions rounded to 2^-k), so
 //    the result does not depend on which warp took which tile, nor on the number of GPUs the tets are partitioned over.
 //
@@ -36,6 +39,9 @@ namespace dsc {
 #endif
 #ifndef STG_CONS
 #define STG_CONS 8
+#endif
+#ifndef STG_UNROLL_S2
+#define STG_UNROLL_S2 2 // cells of the i + j + k = 2 loop of the level-4 stream per iteration
 #endif
 #ifndef STG_PROD_SLEEP
 #define STG_PROD_SLEEP 100 // ns between two looks of a producer at its slot's release counter
@@ -305,7 +311,8 @@ template <typename VoxT, bool WANT_SQ, bool F32S> DSC_D void stg_block4_rolled(c
         }
     }
     // i + j + k = 2: offsets 0..4; offset 0 is a level-3 row as well (eps), offsets 1..4 exist at level 4 only
-#pragma unroll 1
+    constexpr int kUnrollS2 = STG_UNROLL_S2;
+#pragma unroll kUnrollS2
     for (int c = 0; c < 6; c++) {
         const StgCellRow row = c_stg4_s2[c];
         f32x2 cxy, czz;
@@ -381,6 +388,14 @@ DSC_D void mbar_wait(unsigned bar, unsigned parity)
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
+// one bounded look: the warp is suspended by the hardware until the phase completes or a time limit passes
+DSC_D bool mbar_try_wait(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+
 // Tets that leave the staged stream (level n >= 5, reaching outside the volume, a box that does not fit a slot, a sample inside the
 // guard band) are appended to a list; tet_exact_list_kernel runs the reference's exact sequence on them afterwards.
 DSC_D void exact_append(const TetArgs &a, bool flag, unsigned t, int lane)
@@ -414,6 +429,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
     __shared__ int4 s_hdr[kStgMaxSlots];         // tile base, NB (0: end of a producer's stream), row pitch, slice pitch
     __shared__ unsigned s_fillseq[kStgMaxSlots];  // sequence number + 1 of the item a producer has put into the slot
     __shared__ unsigned s_released[kStgMaxSlots]; // how many items of the slot the consumers are done with
+    __shared__ __align__(8) unsigned long long s_empty[kStgMaxSlots]; // one phase per release: what a producer sleeps on (s_released is what it believes)
     __shared__ long long s_red[kStgCons][3 * kMaxPhase];
     __shared__ unsigned s_zero[4];
     __shared__ unsigned s_seq[2]; // next slot sequence number of the producers / of the consumers
@@ -429,6 +445,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
     if (threadIdx.x < 2) s_seq[threadIdx.x] = 0u;
     if (threadIdx.x < S) {
         mbar_init(smem_u32(&s_full[threadIdx.x]), 1);
+        mbar_init(smem_u32(&s_empty[threadIdx.x]), 1);
         s_fillseq[threadIdx.x] = 0u;
         s_released[threadIdx.x] = 0u;
     }
@@ -449,7 +466,13 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
             q = __shfl_sync(0xffffffffu, q, 0);
             const unsigned round = __umulhi(q, s_rcp);
             slot = q - round * (unsigned)S;
+#ifdef STG_POLL_RELEASE
             while (*reinterpret_cast<volatile unsigned *>(&s_released[slot]) != round) __nanosleep(STG_PROD_SLEEP);
+#else
+            // the release counter says when; between two looks at it the warp sleeps on the slot's "empty" barrier, whose phase `round - 1`
+            // completes with that release (a warp several rounds behind sees an aliased phase and simply looks again)
+            while (*reinterpret_cast<volatile unsigned *>(&s_released[slot]) != round) mbar_try_wait(smem_u32(&s_empty[slot]), (round - 1u) & 1u);
+#endif
             __threadfence_block();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the consumers' reads of the slot precede the TMA writes into it
         };
@@ -668,7 +691,10 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
             const int NB = hdr.y;
             if (NB == 0) { // a producer has finished
                 __syncwarp();
-                if (lane == 0) *reinterpret_cast<volatile unsigned *>(&s_released[slot]) = round + 1u;
+                if (lane == 0) {
+                    *reinterpret_cast<volatile unsigned *>(&s_released[slot]) = round + 1u;
+                    mbar_arrive(smem_u32(&s_empty[slot]));
+                }
                 break;
             }
             const float *rec = reinterpret_cast<const float *>(s_dyn + (size_t)S * a.stg_slot_bytes + (size_t)slot * kStgRecBytes) + lane;
@@ -725,6 +751,7 @@ __global__ void __launch_bounds__((kStgProd + kStgCons) * 32, 1) tet_staged_kern
             if (lane == 0) { // every lane has read its voxels and its record
                 __threadfence_block();
                 *reinterpret_cast<volatile unsigned *>(&s_released[slot]) = round + 1u;
+                mbar_arrive(smem_u32(&s_empty[slot])); // (release semantics: the counter is visible to whoever sees the phase complete)
             }
             const bool flagged = ride && !(acc.emax < r.thr);
             const unsigned t = (unsigned)hdr.x + (unsigned)lane;

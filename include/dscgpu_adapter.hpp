@@ -66,8 +66,12 @@ struct Snapshot {
 // carry DSCGPU_LABEL_FREE and are skipped by every kernel) instead of one per valid tet.  deform() collapses and splits simplices in
 // every iteration, so a dense list shifts all the time; with key-indexed arrays an unchanged tet keeps its place and
 // ImageEnergy::refresh can send differences only.
-template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s, bool key_indexed = false)
+struct WalkTimes { double nodes_ms = 0, tets_ms = 0, faces_ms = 0; }; // where snapshot_from_dsc spends its time (oracle/walk_timing.cpp)
+
+template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s, bool key_indexed = false, WalkTimes *times = nullptr)
 {
+    auto clock_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = clock_ms();
     const unsigned nnb = dsc.get_no_nodes_buffer();
     s.pos.assign(3 * (size_t)nnb, 0.0);
     s.node_flags.assign(nnb, 0);
@@ -77,6 +81,7 @@ template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s, bool key_inde
         s.pos[3 * (size_t)k] = p[0]; s.pos[3 * (size_t)k + 1] = p[1]; s.pos[3 * (size_t)k + 2] = p[2];
         s.node_flags[k] = (uint8_t)((nit->is_interface() ? 1 : 0) | (nit->is_crossing() ? 2 : 0));
     }
+    const double t_nodes = clock_ms();
     std::vector<int32_t> tet_index(dsc.get_no_tets_buffer(), -1);
     s.tet_key.clear(); s.tet_nodes.clear(); s.tet_label.clear();
     if (key_indexed) {
@@ -110,17 +115,24 @@ template <class DSC> void snapshot_from_dsc(DSC &dsc, Snapshot &s, bool key_inde
         for (int k = 0; k < 4; k++) s.tet_nodes.push_back(nids[k]);
         s.tet_label.push_back(dsc.get_label(tit.key()));
     }
+    const double t_tets = clock_ms();
     s.face_key.clear(); s.face_nodes.clear(); s.face_tets.clear(); s.face_is_boundary.clear();
     for (auto fit = dsc.faces_begin(); fit != dsc.faces_end(); fit++) {
         if (!fit->is_interface()) continue;
         s.face_key.push_back(fit.key());
+        // (get_nodes(f) unions the node sets of two edges on every call, is_mesh/is_mesh.h:665-671; the complex's own per-face copy holds the same set)
+#ifdef DSC_CACHE
+        const auto &nids = *dsc.get_nodes_cache(fit.key());
+#else
         const auto nids = dsc.get_nodes(fit.key());
+#endif
         for (int k = 0; k < 3; k++) s.face_nodes.push_back(nids[k]);
         const auto &tids = dsc.get_tets(fit.key());
         s.face_tets.push_back((uint32_t)tet_index[tids[0]]);
         s.face_tets.push_back(tids.size() > 1 ? (uint32_t)tet_index[tids[1]] : DSCGPU_NO_TET);
         s.face_is_boundary.push_back(fit->is_boundary() ? 1 : 0);
     }
+    if (times) { times->nodes_ms = t_nodes - t_start; times->tets_ms = t_tets - t_nodes; times->faces_ms = clock_ms() - t_tets; }
 }
 
 class Error : public std::runtime_error {
@@ -166,7 +178,7 @@ public:
             ImageEnergy *self; std::chrono::steady_clock::time_point t0;
             ~Stop() { self->last_refresh_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
         } stop{this, t0};
-        Snapshot next;
+        Snapshot &next = scratch_; // (the arrays of the snapshot before last: their capacity is reused)
         snapshot_from_dsc(*seg._dsc, next, /*key_indexed=*/true);
         last_flatten_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         const bool same_shape = have_snapshot_ && next.pos.size() == snap_.pos.size() && next.tet_label.size() == snap_.tet_label.size();
@@ -372,6 +384,7 @@ private:
     bool have_snapshot_ = false, last_refresh_incremental_ = false;
     size_t last_moved_nodes_ = 0, last_changed_tets_ = 0;
     double last_flatten_ms_ = 0, last_refresh_ms_ = 0, last_face_order_ms_ = 0;
+    Snapshot scratch_;
     int volume_dtype_ = DSCGPU_F64;
     std::vector<double> forces_, dest_;
     bool move_init_ = false;
